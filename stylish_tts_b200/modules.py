@@ -1,0 +1,351 @@
+"""Host-side mirror of the reference's model-build API (hot path only).
+
+``build_model(model_config)`` returns a mapping whose hot-path entries are
+``nn.Module`` shells with the SAME parameter / buffer names and shapes as the
+reference modules (reference: src/stylish_tts/train/models/models.py:29-85,
+state-dict layout SURVEY.md Appendix D), so reference checkpoints load with
+``load_state_dict(strict=True)``.  The shells own parameters only; their
+``forward`` hands raw device pointers to the sm_100a kernels in
+``csrc/`` through the C-ABI (``include/stylish_b200.h``).  There is no
+PyTorch/CPU fallback: calling ``forward`` without the CUDA library raises.
+
+The module tree is described declaratively (``Node`` = named container) rather
+than class-per-layer: the shells carry no arithmetic of their own.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict
+
+import torch
+from torch import nn
+from torch.nn.utils.parametrizations import weight_norm
+
+STYLE_DIM_DEFAULT = 64
+
+
+class Node(nn.Module):
+    """Named container: children may be modules, Parameters or buffers."""
+
+    def __init__(self, **children):
+        super().__init__()
+        for name, child in children.items():
+            self.put(name, child)
+
+    def put(self, name, child):
+        if isinstance(child, nn.Parameter):
+            self.register_parameter(name, child)
+        elif isinstance(child, torch.Tensor):
+            self.register_buffer(name, child)
+        elif isinstance(child, (list, tuple)):
+            self.add_module(name, seq(child))
+        else:
+            self.add_module(name, child)
+        return self
+
+
+def seq(items) -> Node:
+    """Index-named children ("0", "1", ...), like ModuleList/Sequential keys."""
+    n = Node()
+    for i, it in enumerate(items):
+        if it is not None:
+            n.put(str(i), it)
+    return n
+
+
+def ones(*shape):
+    return nn.Parameter(torch.ones(*shape))
+
+
+def zeros(*shape):
+    return nn.Parameter(torch.zeros(*shape))
+
+
+def conv(ci, co, k, *, bias=True, wn=False, groups=1):
+    c = nn.Conv1d(ci, co, k, groups=groups, bias=bias)
+    return weight_norm(c) if wn else c
+
+
+def chan_norm(c):
+    # reference text_encoder.LayerNorm: parameters gamma/beta (text_encoder.py:15-22)
+    return Node(gamma=ones(c), beta=zeros(c))
+
+
+def ada_fc(style_dim, c):
+    # AdaptiveInstance / AdaptiveLayerNorm: fc = Linear(style, 2*C) (ada_norm.py:129-133,195-201)
+    return Node(fc=nn.Linear(style_dim, 2 * c))
+
+
+# --------------------------------------------------------------------------
+# text encoder (reference text_encoder.py:397-463)
+# --------------------------------------------------------------------------
+def text_encoder_tree(inter_dim, cfg) -> Node:
+    c, f, k, L = cfg.hidden_dim, cfg.filter_channels, cfg.kernel_size, cfg.layers
+    emb = nn.Embedding(cfg.tokens, c)
+    nn.init.normal_(emb.weight, 0.0, c ** -0.5)
+    proj = conv(c, c, 1)
+    nn.init.zeros_(proj.weight)
+    nn.init.zeros_(proj.bias)
+    prenet = Node(
+        conv_layers=[conv(c, c, 5) for _ in range(3)],
+        norm_layers=[chan_norm(c) for _ in range(3)],
+        proj=proj,
+    )
+
+    def mha():
+        m = Node(conv_q=conv(c, c, 1), conv_k=conv(c, c, 1), conv_v=conv(c, c, 1),
+                 conv_o=conv(c, c, 1))
+        for n in ("conv_q", "conv_k", "conv_v"):
+            nn.init.xavier_uniform_(getattr(m, n).weight)
+        return m
+
+    encoder = Node(
+        attn_layers=[mha() for _ in range(L)],
+        norm_layers_1=[chan_norm(c) for _ in range(L)],
+        ffn_layers=[Node(conv_1=conv(c, f, k), conv_2=conv(f, c, k)) for _ in range(L)],
+        norm_layers_2=[chan_norm(c) for _ in range(L)],
+    )
+    return Node(emb=emb, prenet=prenet, encoder=encoder, proj_m=conv(c, inter_dim, 1))
+
+
+# --------------------------------------------------------------------------
+# decoder (reference decoder.py:7-90, ada_norm.py:143-192)
+# --------------------------------------------------------------------------
+def decoder_block_tree(dim_in, dim_out, style_dim) -> Node:
+    n = Node(
+        conv1=conv(dim_in, dim_out, 3, wn=True),
+        conv2=conv(dim_out, dim_out, 3, wn=True),
+        norm1=ada_fc(style_dim, dim_in),
+        norm2=ada_fc(style_dim, dim_out),
+    )
+    if dim_in != dim_out:
+        n.put("conv1x1", conv(dim_in, dim_out, 1, bias=False, wn=True))
+    return n
+
+
+def decoder_tree(dim_in, style_dim, hidden, residual) -> Node:
+    return Node(
+        encode=decoder_block_tree(dim_in + 3, hidden, style_dim),
+        decode=[decoder_block_tree(hidden + 3 + residual, hidden, style_dim) for _ in range(4)],
+        F0_conv=conv(1, 1, 3, wn=True),
+        N_conv=conv(1, 1, 3, wn=True),
+        voiced_conv=conv(1, 1, 3, wn=True),
+        asr_res=[conv(dim_in, residual, 1, wn=True)],
+    )
+
+
+# --------------------------------------------------------------------------
+# vocoder (reference generator.py:513-901, conv_next.py:57-93, conformer.py)
+# --------------------------------------------------------------------------
+def convnext_tree(dim, style_dim) -> Node:
+    inter = 4 * dim
+    return Node(
+        snake=ones(1, 1, inter),
+        dwconv=conv(dim, dim, 7, groups=dim),
+        norm=ada_fc(style_dim, dim),
+        pwconv1=nn.Linear(dim, inter),
+        grn=Node(gamma=zeros(1, 1, inter), beta=zeros(1, 1, inter)),
+        pwconv2=nn.Linear(inter, dim),
+    )
+
+
+def gen_block_tree(ch, style_dim, k=11) -> Node:
+    return Node(
+        convs1=[conv(ch, ch, k, wn=True) for _ in range(3)],
+        convs2=[conv(ch, ch, k, wn=True) for _ in range(3)],
+        adain1=[ada_fc(style_dim, ch) for _ in range(3)],
+        adain2=[ada_fc(style_dim, ch) for _ in range(3)],
+        alpha1=[ones(1, ch, 1) for _ in range(3)],
+        alpha2=[ones(1, ch, 1) for _ in range(3)],
+    )
+
+
+def conformer_block_tree(dim, style_dim, heads=8, dim_head=64, ff_mult=4, expansion=2,
+                         kernel=31) -> Node:
+    inner = heads * dim_head
+    cin = dim * expansion
+
+    def ff():
+        net = Node()
+        net.put("0", nn.Linear(dim, dim * ff_mult))
+        net.put("3", nn.Linear(dim * ff_mult, dim))
+        # Scale(PreNorm(FeedForward)) -> keys  ffN.fn.fn.net.K / ffN.fn.norm.fc
+        return Node(fn=Node(fn=Node(net=net), norm=ada_fc(style_dim, dim)))
+
+    attn = Node(
+        fn=Node(to_q=nn.Linear(dim, inner, bias=False),
+                to_kv=nn.Linear(dim, inner * 2, bias=False),
+                to_out=nn.Linear(inner, dim)),
+        norm=ada_fc(style_dim, dim),
+    )
+    net = Node()
+    net.put("1", conv(dim, cin * 2, 1))
+    net.put("3", Node(conv=conv(cin, cin, kernel, groups=cin)))
+    net.put("4", nn.BatchNorm1d(cin))
+    net.put("6", conv(cin, dim, 1))
+    cmod = Node(norm=ada_fc(style_dim, dim), net=net)
+    return Node(ff1=ff(), attn=attn, conv=cmod, ff2=ff(), post_norm=ada_fc(style_dim, dim))
+
+
+def stft_buffers(n_fft, win_length):
+    """Windowed DFT bases of the conv-STFT (reference stft.py:39-96): periodic
+    hann, forward cos/-sin, backward cos/sin scaled by 1/n_fft (no OLA
+    normalisation, no doubling of interior bins)."""
+    bins = n_fft // 2 + 1
+    window = torch.hann_window(win_length, periodic=True, dtype=torch.float32)
+    if win_length < n_fft:
+        window = torch.nn.functional.pad(window, (0, n_fft - win_length))
+    elif win_length > n_fft:
+        window = window[:n_fft]
+    n = torch.arange(n_fft, dtype=torch.float64)
+    k = torch.arange(bins, dtype=torch.float64)
+    ang = 2.0 * math.pi * torch.outer(k, n) / n_fft
+    w64 = window.double()
+    f_re = (torch.cos(ang) * w64).float().unsqueeze(1)
+    f_im = (-torch.sin(ang) * w64).float().unsqueeze(1)
+    b_re = (torch.cos(ang) * (w64 / n_fft)).float().unsqueeze(1)
+    b_im = (torch.sin(ang) * (w64 / n_fft)).float().unsqueeze(1)
+    return Node(window=window, weight_forward_real=f_re, weight_forward_imag=f_im,
+                weight_backward_real=b_re, weight_backward_imag=b_im)
+
+
+def basegen_tree(*, style_dim, n_fft, win_length, hop_length, scale, scalehop, hidden_dim,
+                 input_dim, io_k, conv_layers, upsample_rates) -> Node:
+    amp_layers = conv_layers - len(upsample_rates)
+    upconvs, upblocks = [], []
+    after = input_dim
+    for s in upsample_rates:
+        before, after = after, after // 2
+        upconvs.append(conv(before, after * s, 11))
+        upblocks.append(convnext_tree(after, style_dim))
+    h = hidden_dim
+    g = Node(
+        amp_convnext=[convnext_tree(input_dim, style_dim) for _ in range(amp_layers)],
+        upconvs=upconvs,
+        upblocks=upblocks,
+        m_source=Node(l_linear=nn.Linear(9, 1)),
+        amp_prior_conv=conv(h, h, io_k),
+        phase_prior_conv=conv(h, h, io_k),
+        amp_prior_block=gen_block_tree(h, style_dim),
+        phase_prior_block=gen_block_tree(h, style_dim),
+        phase_input_conv=conv(3 * h, h, io_k),
+        amp_output_conv=conv(h, h, io_k),
+        phase_output_real_conv=conv(h, h, io_k),
+        phase_output_imag_conv=conv(h, h, io_k),
+        phase_norm=nn.LayerNorm(h, eps=1e-6),
+        phase_convnext=[convnext_tree(h, style_dim) for _ in range(conv_layers)],
+        amp_final_layer_norm=nn.LayerNorm(h, eps=1e-6),
+        phase_final_layer_norm=nn.LayerNorm(h, eps=1e-6),
+    )
+    # reference Generator._init_weights (generator.py:705-708): every Conv1d inside
+    for m in g.modules():
+        if isinstance(m, nn.Conv1d):
+            with torch.no_grad():
+                w = torch.empty_like(m.weight)
+                nn.init.trunc_normal_(w, std=0.02)
+                if torch.nn.utils.parametrize.is_parametrized(m, "weight"):
+                    m.weight = w  # routed through weight_norm's right_inverse
+                else:
+                    m.weight.copy_(w)
+                if m.bias is not None:
+                    m.bias.zero_()
+    g.put("stft", stft_buffers(n_fft // scale, win_length // scale))
+    return g
+
+
+def generator_tree(*, style_dim, n_fft, win_length, hop_length, cfg) -> Node:
+    hidden = n_fft // 2
+    return Node(
+        amp_input_conv=conv(cfg.input_dim, hidden, cfg.io_conv_kernel_size),
+        amp_norm=nn.LayerNorm(hidden, eps=1e-6),
+        amp_conformer=Node(layers=[conformer_block_tree(hidden, style_dim)
+                                   for _ in range(cfg.conformer_layers)]),
+        basegen=basegen_tree(
+            style_dim=style_dim, n_fft=n_fft, win_length=win_length, hop_length=hop_length,
+            scale=8, scalehop=75, hidden_dim=n_fft // 2 // 8, input_dim=hidden,
+            io_k=cfg.io_conv_kernel_size, conv_layers=cfg.conv_layers,
+            upsample_rates=[3, 5, 5]),
+    )
+
+
+class DecoderPrediction:
+    """Same result object as the reference (utils.py:643-653)."""
+
+    def __init__(self, *, audio, magnitude=None, phase=None):
+        self.audio = audio
+        self.magnitude = magnitude
+        self.phase = phase
+
+
+class SpeechPredictor(nn.Module):
+    """Drop-in for reference SpeechPredictor (speech_predictor.py:11-73).
+
+    forward(texts, text_lengths, alignment, pitch, energy, voiced, style,
+            denormal_pitch) -> DecoderPrediction(audio (B,1,L))
+    """
+
+    def __init__(self, model_config):
+        super().__init__()
+        mc = model_config
+        self.model_config = mc
+        self.text_encoder = text_encoder_tree(mc.inter_dim, mc.text_encoder)
+        self.decoder = decoder_tree(mc.inter_dim, mc.style_dim, mc.decoder.hidden_dim,
+                                    mc.decoder.residual_dim)
+        self.generator = generator_tree(style_dim=mc.style_dim, n_fft=mc.n_fft,
+                                        win_length=mc.win_length, hop_length=mc.hop_length,
+                                        cfg=mc.generator)
+        self._engine = None
+
+    def engine(self):
+        from .engine import SpeechEngine
+
+        if self._engine is None:
+            self._engine = SpeechEngine(self)
+        return self._engine
+
+    def forward(self, texts, text_lengths, alignment, pitch, energy, voiced, style,
+                denormal_pitch, *, source_draws=None, taps=None):
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise NotImplementedError(
+                "stylish_tts_b200: the backward kernels of speech_predictor are not built "
+                "yet; call under torch.no_grad() (forward/inference path)")
+        audio = self.engine().forward(texts, text_lengths, alignment, pitch, energy, voiced,
+                                      style, denormal_pitch, source_draws=source_draws,
+                                      taps=taps)
+        return DecoderPrediction(audio=audio, magnitude=None, phase=None)
+
+
+HOT_PATH_KEYS = ("speech_predictor",)
+ALL_KEYS = ("text_aligner", "duration_predictor", "pitch_energy_predictor", "speech_predictor",
+            "disc", "mrd0", "mrd1", "mrd2", "speech_style_encoder", "pe_style_encoder",
+            "duration_style_encoder", "pitch_disc", "dur_disc")
+
+
+class ModelSet(dict):
+    """dict with attribute access (the reference returns a ``Munch``)."""
+
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError:
+            raise AttributeError(k)
+
+    def __setattr__(self, k, v):
+        self[k] = v
+
+
+def build_model(model_config, *, extra: Dict[str, nn.Module] | None = None) -> ModelSet:
+    """Mirror of reference ``build_model`` (models.py:29-85).
+
+    Returns the B200-native modules for the keys on the hot path.  Keys that
+    are out of this engine's scope (aligner, discriminators, ...) can be
+    supplied by the caller through ``extra`` (e.g. the reference's own modules
+    when dropped into its train.py); they are passed through untouched.
+    """
+    nets = ModelSet()
+    nets["speech_predictor"] = SpeechPredictor(model_config)
+    if extra:
+        for k, v in extra.items():
+            if k not in nets:
+                nets[k] = v
+    return nets

@@ -1,0 +1,108 @@
+"""Pin the CPU oracle (oracle/speech_oracle.py) against the reference.
+
+(1) against the committed golden fixtures produced by the unmodified reference
+    (tests/golden/make_golden.py) — runs everywhere;
+(2) against the live reference when /root/reference is mounted.
+Tolerance: fp32 CPU vs fp32 CPU, 2e-5 rel-L2 (observed ~4e-6).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_loader
+from oracle import speech_oracle as so
+from tests import util
+
+TOL = 2e-5
+CASES = ["sp_b2_t16_ragged", "sp_b1_t12"]
+
+
+def run_oracle(sp, inp, taps=None, dtype=torch.float32):
+    sd = so.to_dtype(util.state_dict_of(sp), dtype)
+    f = lambda t: t.to(dtype) if t.is_floating_point() else t
+    draws = {k: f(v) for k, v in inp["draws"].items()}
+    return so.speech_predictor(sd, inp["texts"], inp["text_lengths"], f(inp["alignment"]),
+                               f(inp["pitch"]), f(inp["energy"]), f(inp["voiced"]),
+                               f(inp["style"]), f(inp["denormal_pitch"]), draws, taps=taps)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_matches_golden(name):
+    sp, inp, gold, stride = util.golden_case(name)
+    taps = {}
+    audio = run_oracle(sp, inp, taps)
+    assert audio.shape == gold["audio"].shape
+    assert util.rel_l2(audio, gold["audio"]) < TOL
+    checked = 0
+    for k, g in gold.items():
+        if not k.startswith("tap_"):
+            continue
+        t = util.decimate(taps[k[4:]], stride)
+        assert t.shape == g.shape, k
+        if k == "tap_har_phase":
+            assert util.wrap_aware_phase_err(t, g) < 1e-4
+        else:
+            assert util.rel_l2(t, g) < TOL, k
+        checked += 1
+    assert checked >= 14
+
+
+def test_alignment_matches_golden():
+    gold = util.load_golden("alignment")
+    al = so.duration_to_alignment(gold["duration"])
+    assert al.shape == gold["alignment"].shape
+    assert torch.equal(al, gold["alignment"])  # same ops, same order: bit-exact on CPU
+
+
+def test_injected_prior_equals_recomputed():
+    """Feeding the oracle its own (har_spec, har_phase) reproduces the audio bit-for-bit:
+    the injection seam used by the GPU parity tests is a pure split."""
+    sp, inp, gold, _ = util.golden_case("sp_b1_t12")
+    taps = {}
+    a1 = run_oracle(sp, inp, taps)
+    sd = util.state_dict_of(sp)
+    a2 = so.speech_predictor(sd, inp["texts"], inp["text_lengths"], inp["alignment"],
+                             inp["pitch"], inp["energy"], inp["voiced"], inp["style"],
+                             inp["denormal_pitch"], None,
+                             prior=(taps["har_spec"], taps["har_phase"]))
+    assert torch.equal(a1, a2)
+
+
+def test_fp64_oracle_close_to_fp32_with_injected_prior():
+    """fp32 vs fp64 oracle agree to ~1e-4 once the phase-wrap-chaotic prior is injected
+     — this is the noise floor GPU parity is judged against."""
+    sp, inp, gold, _ = util.golden_case("sp_b1_t12")
+    taps = {}
+    run_oracle(sp, inp, taps)
+    prior32 = (taps["har_spec"], taps["har_phase"])
+    sd32 = util.state_dict_of(sp)
+    a32 = so.speech_predictor(sd32, inp["texts"], inp["text_lengths"], inp["alignment"],
+                              inp["pitch"], inp["energy"], inp["voiced"], inp["style"],
+                              inp["denormal_pitch"], None, prior=prior32)
+    sd64 = so.to_dtype(sd32, torch.float64)
+    d = lambda t: t.double()
+    a64 = so.speech_predictor(sd64, inp["texts"], inp["text_lengths"], d(inp["alignment"]),
+                              d(inp["pitch"]), d(inp["energy"]), d(inp["voiced"]),
+                              d(inp["style"]), d(inp["denormal_pitch"]), None,
+                              prior=(d(prior32[0]), d(prior32[1])))
+    assert util.rel_l2(a32, a64) < 1e-3
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="/root/reference not mounted")
+def test_oracle_matches_live_reference():
+    from oracle import ref_run
+    import stylish_tts_b200 as st
+    from stylish_tts_b200 import synth
+
+    sp = st.build_model(st.default_model_config()).speech_predictor
+    synth.randomize_(sp, 11)
+    ref = ref_loader.build_model().speech_predictor.eval()
+    ref.load_state_dict(sp.state_dict(), strict=True)
+    inp = synth.speech_inputs(2, 20, seed=4, ragged=True)
+    rt, ot = {}, {}
+    a_ref = ref_run.speech_predictor_forward(ref, inp, rt)
+    a_or = run_oracle(sp, inp, ot)
+    assert util.rel_l2(a_or, a_ref) < TOL
+    for k in rt:
+        if k in ot and k != "har_phase":
+            assert util.rel_l2(ot[k], rt[k]) < TOL, k
