@@ -1,0 +1,221 @@
+/*
+ * stylish_b200.h — C ABI of libstylish_b200.so (sm_100a kernels for the
+ * Stylish-TTS forward hot path).
+ *
+ * The reference (Stylish-TTS/stylish-tts) is pure Python/PyTorch and has no FFI
+ * of its own: the seam it offers is the nn.Module call protocol (SURVEY.md
+ * §8b).  Each entry point below therefore replaces the *library call sequence*
+ * the reference issues at the cited file:line (paths relative to
+ * src/stylish_tts/train/).  INTEGRATION.md shows the ctypes binding.
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers owned by the caller (torch allocates,
+ *     the library never frees or retains them); `stream` is a cudaStream_t;
+ *   - activations are fp32, channel-major (B, C, T) with T contiguous; where a
+ *     tensor has `_bs` / `_cs` arguments they are the batch / channel strides in
+ *     elements (so a slice of a wider concat buffer can be addressed);
+ *   - return 0 on success, STY_ERR_* (<0) otherwise; sty_last_error() returns a
+ *     thread-local message for the last failure;
+ *   - no global mutable state; every call is re-entrant per stream; nothing
+ *     synchronises the device.
+ */
+#ifndef STYLISH_B200_H
+#define STYLISH_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* sty_stream_t; /* cudaStream_t */
+
+#if defined(__GNUC__)
+#define STY_API __attribute__((visibility("default")))
+#else
+#define STY_API
+#endif
+
+#define STY_OK 0
+#define STY_ERR_BAD_ARG (-1)
+#define STY_ERR_WORKSPACE (-2)
+#define STY_ERR_CUDA (-3)
+
+/* activation codes */
+#define STY_ACT_NONE 0
+#define STY_ACT_RELU 1
+#define STY_ACT_LEAKY02 2 /* LeakyReLU(0.2)                     ada_norm.py:148 */
+#define STY_ACT_SNAKE 3   /* x + sin^2(a x)/a, a per channel    ada_norm.py:114, conv_next.py:77 */
+#define STY_ACT_SWISH 4   /* x * sigmoid(x)                      conformer.py:33 */
+
+STY_API int sty_version(void);
+STY_API const char* sty_last_error(void);
+/* number of SMs of the current device (grid sizing / diagnostics) */
+STY_API int sty_device_sm_count(void);
+
+/* ---- embedding ---------------------------------------------------------
+ * out[b,c,t] = emb[tokens[b,t], c] * scale * (t < lengths[b])   (lengths NULL: no mask).
+ * Replaces `self.emb(x) * sqrt(C); transpose(1,-1)` models/text_encoder.py:451-452; the
+ * mask is the `x * x_mask` every consumer of the embedding applies (text_encoder.py:82,86). */
+STY_API int sty_embed_fwd(const int64_t* tokens, const int64_t* lengths, const float* emb, float* out,
+                          int B, int T, int C, int n_tokens, float scale, sty_stream_t stream);
+
+/* ---- sequence mask -----------------------------------------------------------
+ * out[b,t] = (t < lengths[b]) ? 1 : 0   (utils.py:54-58, as float like text_encoder.py:453) */
+STY_API int sty_sequence_mask_fwd(const int64_t* lengths, float* out, int B, int T,
+                                  sty_stream_t stream);
+
+/* ---- generic Conv1d (stride 1) with fused prologue / epilogue ------------
+ * y[b,co,t] = out_scale * mask_o[b,t] * act_o( bias[co] +
+ *                 sum_{ci,k} w[ci,k,co] * xin[b,ci,t + k*dil - pad] )
+ *             + res_scale * res[b,co,t]
+ * xin[b,ci,u] = 0 outside [0,T), else act_i( in_scale[b,ci] * (x[b,ci,u]*mask_i[b,u])
+ *                                            + in_shift[b,ci] )
+ * Weights are PRE-PACKED as (CI, K, CO) (the reference stores (CO, CI, K));
+ * `w_bs` != 0 selects a per-batch weight (used for `text_encoding @ alignment`).
+ * Optional `out_sumsq[b,co] += sum_t y^2` (GRN statistics, conv_next.py:15-18).
+ * `shuffle` = s > 1 stores co = c*s + r at y[b, c, t*s + r]
+ * (einops "b (c s) t -> b c (t s)", generator.py:746).
+ * Replaces F.conv1d / nn.Linear(+transpose) + the elementwise kernels around
+ * them: text_encoder.py:79-86,195-222,325-330; ada_norm.py:109-120,176-192;
+ * conv_next.py:80-93; conformer.py:84-95,173-187; generator.py:731-781,885. */
+typedef struct sty_conv1d_args {
+  const float* x;
+  int64_t x_bs, x_cs;
+  const float* w;
+  int64_t w_bs;
+  const float* bias; /* (CO) or NULL */
+  float* y;
+  int64_t y_bs, y_cs;
+  const float* res; /* NULL or same indexing as y */
+  int64_t r_bs, r_cs;
+  const float* in_scale; /* (B,CI) or NULL */
+  const float* in_shift; /* (B,CI) or NULL */
+  const float* in_alpha; /* (CI): snake alpha of the prologue activation */
+  const float* in_mask;  /* (B,T) or NULL */
+  const float* out_mask; /* (B,T) or NULL */
+  const float* out_alpha; /* (CO): snake alpha of the epilogue activation */
+  float* out_sumsq;       /* (B,CO) accumulated with atomics, or NULL */
+  int32_t B, CI, CO, T, K, dil, pad;
+  int32_t in_act, out_act, shuffle;
+  float out_scale, res_scale;
+} sty_conv1d_args;
+STY_API int sty_conv1d_fwd(const sty_conv1d_args* a, sty_stream_t stream);
+
+/* ---- depthwise Conv1d ----------------------------------------------------
+ * y[b,c,t] = act( post_scale[c] * (bias[c] + sum_k w[c,k] x[b,c,t+k-pad_left]) + post_shift[c] )
+ * Replaces the depthwise k31 conv + eval BatchNorm1d + Swish of the conformer conv
+ * module (conformer.py:176-186) and the weight-normed 1->1 k3 convs on F0 / N /
+ * voiced (decoder.py:77-79). */
+STY_API int sty_dwconv1d_fwd(const float* x, int64_t x_bs, int64_t x_cs, const float* w,
+                     const float* bias, const float* post_scale, const float* post_shift,
+                     float* y, int64_t y_bs, int64_t y_cs, int B, int C, int T, int K,
+                     int pad_left, int act, sty_stream_t stream);
+
+/* ---- ConvNeXt front: depthwise k7 + LayerNorm over C + adaptive affine ----
+ * d = dwconv7(x)+bias;  y[b,c,t] = (1+gamma[b,c]) * LN_C(d)[c] + beta[b,c]
+ * gamma = gb[b*gb_bs + c], beta = gb[b*gb_bs + C + c].   Replaces
+ * conv_next.py:82-84 (+ AdaptiveLayerNorm ada_norm.py:203-211). */
+STY_API int sty_dwconv_ln_fwd(const float* x, int64_t x_bs, const float* w, const float* bias,
+                              const float* gb, int64_t gb_bs, float* y, int64_t y_bs, int B, int C,
+                              int T, float eps, sty_stream_t stream);
+
+/* ---- LayerNorm over the channel axis of (B,C,T) --------------------------
+ * v = x (+ res);  n = (v-mean_c)/sqrt(var_c+eps)
+ * y = act( (g_plus_one ? 1+g : g) * n + b ) * mask[b,t]
+ * g = gamma[b*g_bs + c], b = beta[b*g_bs + c]  (g_bs = 0: shared over the batch).
+ * x and res share the batch stride x_bs; channel stride is T for x, res and y.
+ * Replaces text_encoder.LayerNorm (text_encoder.py:24-33, eps 1e-4),
+ * nn.LayerNorm via transposes (generator.py:756-778,887) and AdaptiveLayerNorm
+ * (ada_norm.py:203-211, conformer.py:74-77,250). */
+STY_API int sty_chan_layernorm_fwd(const float* x, const float* res, int64_t x_bs, const float* gamma,
+                                   const float* beta, int64_t g_bs, int g_plus_one, float* y,
+                                   int64_t y_bs, const float* mask, int B, int C, int T, float eps,
+                                   int act, sty_stream_t stream);
+
+/* ---- InstanceNorm statistics folded with the style affine ----------------
+ * mean/var over T per (b,c) (biased variance), then
+ * scale[b,c] = (1+gamma[b,c]) / sqrt(var+eps),  shift[b,c] = beta[b,c] - mean*scale
+ * so that AdaIN(x) = scale*x + shift, applied in the consumer conv's prologue.
+ * gamma = gb[b*gb_bs + c], beta = gb[b*gb_bs + C + c].
+ * Replaces AdaptiveInstance ada_norm.py:129-140. */
+STY_API int sty_instnorm_affine_fwd(const float* x, int64_t x_bs, int64_t x_cs, const float* gb,
+                            int64_t gb_bs, float* scale, float* shift, int B, int C, int T,
+                            float eps, sty_stream_t stream);
+
+/* ---- small dense layer on vectors -----------------------------------------
+ * out[b,j] = bias[j] + sum_i W[j,i] * s[b,i]      (all style FCs of a model packed
+ * row-wise into one W: ada_norm.py:136,204 `self.fc(s)`). */
+STY_API int sty_linear_rows_fwd(const float* s, const float* W, const float* bias, float* out, int B,
+                        int I, int J, sty_stream_t stream);
+
+/* ---- GRN scale -------------------------------------------------------------
+ * gx[b,j] = sqrt(sumsq[b,j]); nx = gx / (mean_j gx + 1e-6)
+ * scale[b,j] = 1 + gamma[j]*nx[b,j]      (conv_next.py:15-18: gamma*(x*nx)+beta+x;
+ * the `beta` term is folded into the bias of the following pointwise conv). */
+STY_API int sty_grn_scale_fwd(const float* sumsq, const float* gamma, float* scale, int B, int J,
+                      sty_stream_t stream);
+
+/* ---- rotary table ------------------------------------------------------------
+ * cos/sin of t * 10000^(-2i/d_rot), i < d_rot/2, t < T  -> (T, d_rot/2) each.
+ * text_encoder.py:112-137. */
+STY_API int sty_rope_table(float* cos_out, float* sin_out, int T, int d_rot, float base,
+                   sty_stream_t stream);
+
+/* ---- multi-head attention core ----------------------------------------------
+ * q,k,v: (B, H*D, T) channel-major (head h owns channels [h*D,(h+1)*D)).
+ * o[b,h*D+j,t] = sum_u softmax_u( scale * <rope(q_t), rope(k_u)> + m(t,u) ) v[u][j]
+ * m(t,u) = 0 if (t < len[b] and u < len[b]) else -1e4 (lengths==NULL: no mask).
+ * rope tables (T, d_rot/2) or NULL.  Replaces arrange_heads + RoPE + mask +
+ * F.scaled_dot_product_attention (text_encoder.py:233-272; conformer.py:112-131). */
+STY_API int sty_attention_fwd(const float* q, const float* k, const float* v, int64_t qkv_bs,
+                      float* o, int64_t o_bs, const int64_t* lengths, const float* rope_cos,
+                      const float* rope_sin, int d_rot, int B, int H, int D, int T, float scale,
+                      sty_stream_t stream);
+
+/* ---- batched matrix product ---------------------------------------------------
+ * C[b] (M,N) = A[b] (M,K) @ Bm[b] (K,N), all row-major, batch strides in elements.
+ * `text_encoding @ alignment` speech_predictor.py:60. */
+STY_API int sty_bmm_fwd(const float* A, int64_t a_bs, const float* Bm, int64_t b_bs, float* C,
+                int64_t c_bs, int B, int M, int N, int K, sty_stream_t stream);
+
+/* ---- gated linear unit over channels -------------------------------------------
+ * y[b,c,t] = x[b,c,t] * sigmoid(x[b,c+C,t])   conformer.py:37-44 */
+STY_API int sty_glu_fwd(const float* x, float* y, int B, int C, int T, sty_stream_t stream);
+
+/* ---- harmonic source (SineGen + merge) --------------------------------------------
+ * pitch, voiced: (B,F).  noise: (B, F*hop, H) standard normal draws (the reference
+ * draws them with torch.randn, generator.py:440).  lin_w (H), lin_b (1).
+ * work: (B,H,F) doubles scratch.  out: excitation (B, F*hop).
+ * Replaces f0_upsamp + SourceModuleHnNSF + SineGen (generator.py:336-447,496-510,
+ * 719-723).  The phase accumulation is carried in fp64 cycles. */
+STY_API int sty_source_fwd(const float* pitch, const float* voiced, const float* noise,
+                   const float* lin_w, const float* lin_b, double* work, float* out, int B,
+                   int F, int hop, int H, float sample_rate, float sine_amp, float noise_std,
+                   float voiced_threshold, sty_stream_t stream);
+
+/* ---- conv-STFT of the excitation -------------------------------------------------------
+ * wave (B,L) -> spec, phase (B, bins_keep, L/hop): replicate-pad n_fft/2, windowed DFT
+ * with bases basis_re/basis_im (bins, n_fft), mag = sqrt(re^2+im^2+1e-14),
+ * phase = atan2(im/mag, re/mag); the last frame and bins >= bins_keep are dropped.
+ * stft.py:98-136 + generator.py:724-729. */
+STY_API int sty_stft_fwd(const float* wave, const float* basis_re, const float* basis_im, float* spec,
+                 float* phase, int B, int L, int n_fft, int hop, int bins_keep,
+                 sty_stream_t stream);
+
+/* ---- spectral head + conv-iSTFT + tanh ------------------------------------------------
+ * logamp, real, imag: (B, bins, S) with batch strides logamp_bs / ri_bs (real and imag may be
+ * the two halves of one fused conv output).  Per frame f in [0,S] (frame S replicates S-1):
+ * mag = exp(logamp), ph = atan2(imag, real), re = mag*cos(ph), im = mag*sin(ph);
+ * overlap-add with basis_re/basis_im (bins, n_fft) (already windowed and scaled),
+ * wave = sum re*B_re - im*B_im, trimmed by n_fft/2 at both ends, then tanh.
+ * out: (B, S*hop).  generator.py:782-799,896 + stft.py:138-187. */
+STY_API int sty_istft_head_fwd(const float* logamp, int64_t logamp_bs, const float* real,
+                               const float* imag, int64_t ri_bs, const float* basis_re,
+                               const float* basis_im, float* out, int B, int S, int bins, int n_fft,
+                               int hop, sty_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STYLISH_B200_H */

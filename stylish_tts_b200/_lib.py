@@ -1,0 +1,164 @@
+"""ctypes binding of libstylish_b200.so (C ABI in include/stylish_b200.h).
+
+The library is built in-tree by ``python -m stylish_tts_b200.csrc.build``
+(``__graft_entry__.build()``).  There is deliberately NO fallback: if the
+library is missing, or a call fails, a RuntimeError is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libstylish_b200.so")
+
+ACT_NONE, ACT_RELU, ACT_LEAKY02, ACT_SNAKE, ACT_SWISH = 0, 1, 2, 3, 4
+
+_f32p = C.c_void_p
+_i64 = C.c_int64
+_i32 = C.c_int32
+_f32 = C.c_float
+
+
+class ConvArgs(C.Structure):
+    """Mirror of ``sty_conv1d_args``."""
+    _fields_ = [
+        ("x", _f32p), ("x_bs", _i64), ("x_cs", _i64),
+        ("w", _f32p), ("w_bs", _i64),
+        ("bias", _f32p),
+        ("y", _f32p), ("y_bs", _i64), ("y_cs", _i64),
+        ("res", _f32p), ("r_bs", _i64), ("r_cs", _i64),
+        ("in_scale", _f32p), ("in_shift", _f32p), ("in_alpha", _f32p),
+        ("in_mask", _f32p), ("out_mask", _f32p), ("out_alpha", _f32p),
+        ("out_sumsq", _f32p),
+        ("B", _i32), ("CI", _i32), ("CO", _i32), ("T", _i32), ("K", _i32), ("dil", _i32),
+        ("pad", _i32),
+        ("in_act", _i32), ("out_act", _i32), ("shuffle", _i32),
+        ("out_scale", _f32), ("res_scale", _f32),
+    ]
+
+
+# name -> argtypes (restype is always int unless listed in _SPECIAL)
+_SIGNATURES = {
+    "sty_embed_fwd": [_f32p, _f32p, _f32p, _f32p, _i32, _i32, _i32, _i32, _f32, _f32p],
+    "sty_sequence_mask_fwd": [_f32p, _f32p, _i32, _i32, _f32p],
+    "sty_conv1d_fwd": [C.POINTER(ConvArgs), _f32p],
+    "sty_dwconv1d_fwd": [_f32p, _i64, _i64, _f32p, _f32p, _f32p, _f32p, _f32p, _i64, _i64, _i32,
+                         _i32, _i32, _i32, _i32, _i32, _f32p],
+    "sty_dwconv_ln_fwd": [_f32p, _i64, _f32p, _f32p, _f32p, _i64, _f32p, _i64, _i32, _i32, _i32,
+                          _f32, _f32p],
+    "sty_chan_layernorm_fwd": [_f32p, _f32p, _i64, _f32p, _f32p, _i64, _i32, _f32p, _i64, _f32p,
+                               _i32, _i32, _i32, _f32, _i32, _f32p],
+    "sty_instnorm_affine_fwd": [_f32p, _i64, _i64, _f32p, _i64, _f32p, _f32p, _i32, _i32, _i32,
+                                _f32, _f32p],
+    "sty_linear_rows_fwd": [_f32p, _f32p, _f32p, _f32p, _i32, _i32, _i32, _f32p],
+    "sty_grn_scale_fwd": [_f32p, _f32p, _f32p, _i32, _i32, _f32p],
+    "sty_rope_table": [_f32p, _f32p, _i32, _i32, _f32, _f32p],
+    "sty_attention_fwd": [_f32p, _f32p, _f32p, _i64, _f32p, _i64, _f32p, _f32p, _f32p, _i32, _i32,
+                          _i32, _i32, _i32, _f32, _f32p],
+    "sty_bmm_fwd": [_f32p, _i64, _f32p, _i64, _f32p, _i64, _i32, _i32, _i32, _i32, _f32p],
+    "sty_glu_fwd": [_f32p, _f32p, _i32, _i32, _i32, _f32p],
+    "sty_source_fwd": [_f32p, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, _i32, _i32, _i32, _i32,
+                       _f32, _f32, _f32, _f32, _f32p],
+    "sty_stft_fwd": [_f32p, _f32p, _f32p, _f32p, _f32p, _i32, _i32, _i32, _i32, _i32, _f32p],
+    "sty_istft_head_fwd": [_f32p, _i64, _f32p, _f32p, _i64, _f32p, _f32p, _f32p, _i32, _i32, _i32,
+                           _i32, _i32, _f32p],
+}
+_SPECIAL = {
+    "sty_version": ([], C.c_int),
+    "sty_last_error": ([], C.c_char_p),
+    "sty_device_sm_count": ([], C.c_int),
+}
+EXPORTED = tuple(_SIGNATURES) + tuple(_SPECIAL)
+
+_lib: Optional[C.CDLL] = None
+launches = 0  # number of kernel-launching C-ABI calls made (diagnostics / bench)
+
+
+def load() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"stylish_tts_b200: CUDA library not built ({LIB_PATH} missing). Run "
+                "`python -m stylish_tts_b200.csrc.build`; there is no CPU/PyTorch fallback.")
+        lib = C.CDLL(LIB_PATH)
+        for name, argt in _SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.argtypes = argt
+            fn.restype = C.c_int
+        for name, (argt, rest) in _SPECIAL.items():
+            fn = getattr(lib, name)
+            fn.argtypes = argt
+            fn.restype = rest
+        _lib = lib
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().sty_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"stylish_tts_b200.{what} failed (code {rc}): {msg}")
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _req(t: torch.Tensor, name: str, dtype=torch.float32) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"stylish_tts_b200: `{name}` must be a CUDA tensor (no CPU fallback)")
+    if t.dtype != dtype:
+        raise TypeError(f"stylish_tts_b200: `{name}` must be {dtype}, got {t.dtype}")
+
+
+def _bct(t: torch.Tensor, name: str):
+    """(B,C,T) view with unit time stride -> (batch stride, channel stride)."""
+    _req(t, name)
+    if t.dim() != 3 or (t.shape[2] > 1 and t.stride(2) != 1):
+        raise ValueError(f"stylish_tts_b200: `{name}` must be (B,C,T) with contiguous T")
+    return t.stride(0), t.stride(1)
+
+
+profile_log = None  # set to a list to time every call with CUDA events (bench.py roofline leg)
+
+
+def _signature(name: str, args) -> str:
+    if name == "sty_conv1d_fwd":
+        a = args[0]._obj
+        extra = ""
+        if a.in_act or a.in_scale:
+            extra += "+pro"
+        if a.out_sumsq:
+            extra += "+ssq"
+        if a.shuffle > 1:
+            extra += f"+shuf{a.shuffle}"
+        return f"conv1d[ci={a.CI},co={a.CO},k={a.K},d={a.dil},B={a.B},T={a.T}{extra}]"
+    return name[4:]
+
+
+def call(name: str, *args) -> None:
+    global launches
+    lib = load()
+    launches += 2 if name == "sty_source_fwd" else 1  # source = phase + wave kernels
+    if profile_log is not None:
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(lib, name)(*args)
+        e1.record()
+        info = None
+        if name == "sty_conv1d_fwd":
+            a = args[0]._obj
+            info = dict(B=a.B, CI=a.CI, CO=a.CO, K=a.K, T=a.T, res=bool(a.res))
+        profile_log.append((_signature(name, args), e0, e1, info))
+        check(rc, name)
+        return
+    check(getattr(lib, name)(*args), name)

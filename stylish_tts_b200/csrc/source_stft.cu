@@ -1,0 +1,270 @@
+// Harmonic source (SineGen + merge), conv-STFT of the excitation, and the
+// spectral head + conv-iSTFT + tanh.  See include/stylish_b200.h for semantics.
+//
+// Numerics of the source: the reference accumulates phase = cumsum(f/sr)*2*pi*hop
+// in fp32, where |phase| reaches 1e5..1e6 rad and one fp32 ulp is 0.01..0.1 rad,
+// so its own output carries that rounding noise.  We carry the
+// accumulated phase in fp64 *cycles* and reduce it mod 1 before the fp32 sin, so
+// the excitation is closer to the exact-arithmetic value than the reference's
+// fp32 evaluation; parity is judged against the fp64 oracle (tests/test_gpu_*.py).
+#include <math.h>
+
+#include "common.cuh"
+
+namespace sty {
+
+// linear-interpolation source coordinate of torch's F.interpolate(mode="linear",
+// align_corners=False): src = (dst + 0.5) * (in/out) - 0.5, clamped at 0.
+__device__ __forceinline__ void lerp_coord(double src, int n_in, int& i0, int& i1, double& lam) {
+  if (src < 0.0) src = 0.0;
+  i0 = (int)floor(src);
+  if (i0 > n_in - 1) i0 = n_in - 1;
+  i1 = min(i0 + 1, n_in - 1);
+  lam = src - (double)i0;
+}
+
+__device__ __forceinline__ double f0_up(const float* __restrict__ pitch,
+                                        const float* __restrict__ voiced, int F, int hop, int j) {
+  int i0, i1;
+  double lam;
+  lerp_coord(((double)j + 0.5) / (double)hop - 0.5, F, i0, i1, lam);
+  const double a = (double)pitch[i0] * (double)voiced[i0];
+  const double b = (double)pitch[i1] * (double)voiced[i1];
+  return (1.0 - lam) * a + lam * b;
+}
+
+// one thread per (b, harmonic): frame-rate phase accumulation (F sequential steps)
+__global__ void source_phase_kernel(const float* __restrict__ pitch,
+                                    const float* __restrict__ voiced, double* __restrict__ work,
+                                    int B, int F, int hop, int H, double sr) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * H) return;
+  const int b = idx / H, h = idx - b * H;
+  const float* __restrict__ pb = pitch + (int64_t)b * F;
+  const float* __restrict__ vb = voiced + (int64_t)b * F;
+  const int L = F * hop;
+  double cum = 0.0;
+  for (int i = 0; i < F; ++i) {
+    int j0, j1;
+    double lam;
+    lerp_coord(((double)i + 0.5) * (double)hop - 0.5, L, j0, j1, lam);
+    double r0 = f0_up(pb, vb, F, hop, j0) * (double)(h + 1) / sr;
+    double r1 = f0_up(pb, vb, F, hop, j1) * (double)(h + 1) / sr;
+    r0 -= floor(r0);
+    r1 -= floor(r1);
+    cum += (1.0 - lam) * r0 + lam * r1;
+    work[((int64_t)b * H + h) * F + i] = cum;
+  }
+}
+
+template <int HMAX>
+__global__ void __launch_bounds__(256)
+source_wave_kernel(const float* __restrict__ pitch, const float* __restrict__ voiced,
+                   const float* __restrict__ noise, const float* __restrict__ lin_w,
+                   const float* __restrict__ lin_b, const double* __restrict__ work,
+                   float* __restrict__ out, int F, int hop, int H, float sine_amp, float noise_std,
+                   float vthr) {
+  const int b = blockIdx.y;
+  const int L = F * hop;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= L) return;
+  const float* __restrict__ pb = pitch + (int64_t)b * F;
+  const float* __restrict__ vb = voiced + (int64_t)b * F;
+  int i0, i1;
+  double lam;
+  lerp_coord(((double)j + 0.5) / (double)hop - 0.5, F, i0, i1, lam);
+  const double f0 = (1.0 - lam) * ((double)pb[i0] * (double)vb[i0]) + lam * ((double)pb[i1] * (double)vb[i1]);
+  const float uv = ((float)f0 > vthr) ? 1.f : 0.f;
+  const float namp = uv * noise_std + (1.f - uv) * sine_amp / 3.f;
+  const float* __restrict__ nz = noise + ((int64_t)b * L + j) * H;
+  float acc = lin_b[0];
+#pragma unroll
+  for (int h = 0; h < HMAX; ++h) {
+    if (h < H) {
+      const double* __restrict__ wr = work + ((int64_t)b * H + h) * F;
+      double cyc = ((1.0 - lam) * wr[i0] + lam * wr[i1]) * (double)hop;
+      cyc -= floor(cyc);
+      const float sv = sinf((float)(cyc * 6.283185307179586476925286766559));
+      const float val = sv * sine_amp * uv + namp * nz[h];
+      acc = fmaf(lin_w[h], val, acc);
+    }
+  }
+  out[(int64_t)b * L + j] = tanhf(acc);
+}
+
+// ---------------------------------------------------------------------- STFT
+// thread = one frame; the NFFT-sample window sits in registers, the windowed DFT
+// bases (bins_keep x NFFT, re and im) in shared memory (broadcast 128-bit loads).
+template <int NFFT>
+__global__ void __launch_bounds__(128)
+stft_kernel(const float* __restrict__ wave, const float* __restrict__ basis_re,
+            const float* __restrict__ basis_im, float* __restrict__ spec,
+            float* __restrict__ phase, int L, int hop, int S, int bins_keep) {
+  extern __shared__ __align__(16) float sm[];
+  float* bre = sm;                      // [bins_keep][NFFT]
+  float* bim = sm + bins_keep * NFFT;   // [bins_keep][NFFT]
+  float* xs = bim + bins_keep * NFFT;   // [(128-1)*hop + NFFT]
+  const int b = blockIdx.y;
+  const int f0 = blockIdx.x * 128;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < bins_keep * NFFT; i += 128) {
+    bre[i] = basis_re[i];
+    bim[i] = basis_im[i];
+  }
+  const int span = 127 * hop + NFFT;
+  const float* __restrict__ wb = wave + (int64_t)b * L;
+  for (int i = tid; i < span; i += 128) {
+    int n = f0 * hop + i - NFFT / 2;  // replicate padding (stft.py:105-107)
+    n = max(0, min(L - 1, n));
+    xs[i] = wb[n];
+  }
+  __syncthreads();
+  const int f = f0 + tid;
+  if (f >= S) return;
+  float x[NFFT];
+#pragma unroll
+  for (int n = 0; n < NFFT; ++n) x[n] = xs[tid * hop + n];
+  for (int kb = 0; kb < bins_keep; ++kb) {
+    float re = 0.f, im = 0.f;
+#pragma unroll
+    for (int n = 0; n < NFFT; n += 4) {
+      const float4 cr = *reinterpret_cast<const float4*>(bre + kb * NFFT + n);
+      const float4 ci = *reinterpret_cast<const float4*>(bim + kb * NFFT + n);
+      re = fmaf(x[n], cr.x, re); re = fmaf(x[n + 1], cr.y, re);
+      re = fmaf(x[n + 2], cr.z, re); re = fmaf(x[n + 3], cr.w, re);
+      im = fmaf(x[n], ci.x, im); im = fmaf(x[n + 1], ci.y, im);
+      im = fmaf(x[n + 2], ci.z, im); im = fmaf(x[n + 3], ci.w, im);
+    }
+    const float mag = sqrtf(re * re + im * im + 1e-14f);
+    const int64_t o = ((int64_t)b * bins_keep + kb) * S + f;
+    spec[o] = mag;
+    phase[o] = atan2f(im / mag, re / mag);
+  }
+}
+
+// ---------------------------------------------------------------- iSTFT head
+// thread = HOP consecutive output samples.  R = NFFT/HOP frames overlap each sample.
+template <int NFFT, int HOP, int BINS, int MT>
+__global__ void __launch_bounds__(MT)
+istft_head_kernel(const float* __restrict__ logamp, int64_t logamp_bs,
+                  const float* __restrict__ real, const float* __restrict__ imag, int64_t ri_bs,
+                  const float* __restrict__ basis_re, const float* __restrict__ basis_im,
+                  float* __restrict__ out, int S) {
+  static_assert(HOP == 4, "vectorised basis loads assume hop 4");
+  constexpr int R = NFFT / HOP;
+  constexpr int FT = MT + R - 1;
+  constexpr int FTP = (FT + 3) & ~3;
+  extern __shared__ __align__(16) float sm[];
+  float* bre = sm;                // [BINS][NFFT]
+  float* bim = bre + BINS * NFFT; // [BINS][NFFT]
+  float* res = bim + BINS * NFFT; // [BINS][FTP]
+  float* ims = res + BINS * FTP;  // [BINS][FTP]
+  const int b = blockIdx.y;
+  const int tid = threadIdx.x;
+  const int mo0 = blockIdx.x * MT;  // first output group of this CTA
+  // output group mo covers padded samples n' = HOP*(mo + R/2) + r; frames f with
+  // 0 <= n' - HOP*f < NFFT  <=>  f in [mo + R/2 - (R-1), mo + R/2]
+  const int fbase = mo0 + R / 2 - (R - 1);
+  for (int i = tid; i < BINS * NFFT; i += MT) {
+    bre[i] = basis_re[i];
+    bim[i] = basis_im[i];
+  }
+  for (int idx = tid; idx < BINS * FTP; idx += MT) {
+    const int kb = idx / FTP, fl = idx - kb * FTP;
+    const int f = fbase + fl;
+    float re = 0.f, im = 0.f;
+    if (fl < FT && f >= 0 && f <= S) {
+      const int fs = min(f, S - 1);  // replicate-pad of one frame (generator.py:784-785)
+      const int64_t o = (int64_t)kb * S + fs;
+      const float mag = expf(logamp[(int64_t)b * logamp_bs + o]);
+      const float ph = atan2f(imag[(int64_t)b * ri_bs + o], real[(int64_t)b * ri_bs + o]);
+      re = mag * cosf(ph);
+      im = mag * sinf(ph);
+    }
+    res[idx] = re;
+    ims[idx] = im;
+  }
+  __syncthreads();
+  const int mo = mo0 + tid;
+  if (mo >= S) return;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 4
+  for (int fr = 0; fr < R; ++fr) {
+    const int tap = HOP * (R - 1 - fr);
+    const float* __restrict__ rr = res + tid + fr;
+    const float* __restrict__ ii = ims + tid + fr;
+#pragma unroll 8
+    for (int kb = 0; kb < BINS; ++kb) {
+      const float re = rr[kb * FTP], im = ii[kb * FTP];
+      const float4 cr = *reinterpret_cast<const float4*>(bre + kb * NFFT + tap);
+      const float4 ci = *reinterpret_cast<const float4*>(bim + kb * NFFT + tap);
+      a0 = fmaf(re, cr.x, a0); a0 = fmaf(-im, ci.x, a0);
+      a1 = fmaf(re, cr.y, a1); a1 = fmaf(-im, ci.y, a1);
+      a2 = fmaf(re, cr.z, a2); a2 = fmaf(-im, ci.z, a2);
+      a3 = fmaf(re, cr.w, a3); a3 = fmaf(-im, ci.w, a3);
+    }
+  }
+  float4 o4 = make_float4(tanhf(a0), tanhf(a1), tanhf(a2), tanhf(a3));
+  *reinterpret_cast<float4*>(out + (int64_t)b * S * HOP + (int64_t)mo * HOP) = o4;
+}
+
+}  // namespace sty
+
+using namespace sty;
+
+extern "C" int sty_source_fwd(const float* pitch, const float* voiced, const float* noise,
+                              const float* lin_w, const float* lin_b, double* work, float* out,
+                              int B, int F, int hop, int H, float sample_rate, float sine_amp,
+                              float noise_std, float voiced_threshold, sty_stream_t stream) {
+  STY_REQUIRE(pitch && voiced && noise && lin_w && lin_b && work && out, "source: null pointer");
+  STY_REQUIRE(B > 0 && F > 1 && hop > 0 && H > 0 && H <= 16, "source: bad shape (H<=16)");
+  cudaStream_t st = as_stream(stream);
+  source_phase_kernel<<<cdiv(B * H, 64), 64, 0, st>>>(pitch, voiced, work, B, F, hop, H,
+                                                      (double)sample_rate);
+  STY_CHECK_LAUNCH("source_phase");
+  dim3 grid(cdiv((int64_t)F * hop, 256), B);
+  source_wave_kernel<16><<<grid, 256, 0, st>>>(pitch, voiced, noise, lin_w, lin_b, work, out, F, hop,
+                                               H, sine_amp, noise_std, voiced_threshold);
+  STY_CHECK_LAUNCH("source_wave");
+  return STY_OK;
+}
+
+extern "C" int sty_stft_fwd(const float* wave, const float* basis_re, const float* basis_im,
+                            float* spec, float* phase, int B, int L, int n_fft, int hop,
+                            int bins_keep, sty_stream_t stream) {
+  STY_REQUIRE(wave && basis_re && basis_im && spec && phase, "stft: null pointer");
+  STY_REQUIRE(n_fft == 64, "stft: built for n_fft=64 (got %d)", n_fft);
+  STY_REQUIRE(B > 0 && L > 0 && hop > 0 && L % hop == 0 && bins_keep > 0 && bins_keep <= n_fft / 2 + 1,
+              "stft: bad shape");
+  const int S = L / hop;  // frames kept (the trailing frame is dropped, generator.py:725,728)
+  const size_t smem = ((size_t)2 * bins_keep * n_fft + 127 * hop + n_fft) * sizeof(float);
+  STY_REQUIRE(smem <= 48 * 1024, "stft: hop too large for the staging buffer");
+  dim3 grid(cdiv(S, 128), B);
+  stft_kernel<64><<<grid, 128, smem, as_stream(stream)>>>(wave, basis_re, basis_im, spec, phase, L,
+                                                         hop, S, bins_keep);
+  STY_CHECK_LAUNCH("stft");
+  return STY_OK;
+}
+
+extern "C" int sty_istft_head_fwd(const float* logamp, int64_t logamp_bs, const float* real,
+                                  const float* imag, int64_t ri_bs, const float* basis_re,
+                                  const float* basis_im, float* out, int B, int S, int bins,
+                                  int n_fft, int hop, sty_stream_t stream) {
+  STY_REQUIRE(logamp && real && imag && basis_re && basis_im && out, "istft_head: null pointer");
+  STY_REQUIRE(n_fft == 64 && hop == 4 && bins == 32,
+              "istft_head: built for n_fft=64 hop=4 bins=32 (got %d %d %d)", n_fft, hop, bins);
+  STY_REQUIRE(B > 0 && S > 0, "istft_head: bad shape");
+  constexpr int MT = 128, R = 16, FTP = (MT + R - 1 + 3) & ~3;
+  const size_t smem = ((size_t)2 * 32 * 64 + 2 * 32 * FTP) * sizeof(float);
+  auto kern = istft_head_kernel<64, 4, 32, MT>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr_set = true;
+  }
+  dim3 grid(cdiv(S, MT), B);
+  kern<<<grid, MT, smem, as_stream(stream)>>>(logamp, logamp_bs, real, imag, ri_bs, basis_re,
+                                              basis_im, out, S);
+  STY_CHECK_LAUNCH("istft_head");
+  return STY_OK;
+}

@@ -1,0 +1,550 @@
+"""Forward engine of ``speech_predictor``: packs the shell's parameters into
+kernel-friendly device buffers and drives the sm_100a kernels through the
+C ABI.  PyTorch is used for device memory and the stream only.
+
+Stage order follows the reference forward graph
+(speech_predictor.py:47-73 -> text_encoder.py:434-463 -> decoder.py:77-90 ->
+generator.py:884-901 -> generator.py:710-799), see DESIGN.md for the kernel
+each stage maps to and where normalisations are fused.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Dict, Optional
+
+import torch
+
+from . import _lib as L
+from ._lib import ACT_LEAKY02, ACT_NONE, ACT_RELU, ACT_SNAKE, ACT_SWISH, ConvArgs
+
+INV_SQRT2 = 1.0 / math.sqrt(2.0)
+
+
+# --------------------------------------------------------------------------
+# thin op wrappers (tensor -> raw pointers)
+# --------------------------------------------------------------------------
+class ConvW:
+    """A conv/linear weight pre-packed as (CI, K, CO) plus its bias."""
+
+    __slots__ = ("w", "bias", "CI", "K", "CO")
+
+    def __init__(self, w_oik: torch.Tensor, bias: Optional[torch.Tensor]):
+        co, ci, k = w_oik.shape
+        self.w = w_oik.permute(1, 2, 0).contiguous()
+        self.bias = None if bias is None else bias.contiguous()
+        self.CI, self.K, self.CO = ci, k, co
+
+
+def conv1d(x, cw: ConvW, *, dil=1, out=None, res=None, in_scale=None, in_shift=None,
+           in_alpha=None, in_act=ACT_NONE, in_mask=None, out_mask=None, out_act=ACT_NONE,
+           out_alpha=None, out_sumsq=None, shuffle=0, out_scale=1.0, res_scale=1.0):
+    B, CI, T = x.shape
+    assert CI == cw.CI, (CI, cw.CI)
+    x_bs, x_cs = L._bct(x, "x")
+    s = shuffle if shuffle > 1 else 1
+    if out is None:
+        out = torch.empty((B, cw.CO // s, T * s), device=x.device, dtype=torch.float32)
+    assert out.shape == (B, cw.CO // s, T * s), (out.shape, (B, cw.CO // s, T * s))
+    y_bs, y_cs = L._bct(out, "out")
+    a = ConvArgs()
+    a.x, a.x_bs, a.x_cs = x.data_ptr(), x_bs, x_cs
+    a.w, a.w_bs = cw.w.data_ptr(), 0
+    a.bias = L.ptr(cw.bias)
+    a.y, a.y_bs, a.y_cs = out.data_ptr(), y_bs, y_cs
+    if res is not None:
+        assert res.shape == out.shape
+        r_bs, r_cs = L._bct(res, "res")
+        a.res, a.r_bs, a.r_cs = res.data_ptr(), r_bs, r_cs
+    a.in_scale, a.in_shift, a.in_alpha = L.ptr(in_scale), L.ptr(in_shift), L.ptr(in_alpha)
+    a.in_mask, a.out_mask, a.out_alpha = L.ptr(in_mask), L.ptr(out_mask), L.ptr(out_alpha)
+    a.out_sumsq = L.ptr(out_sumsq)
+    a.B, a.CI, a.CO, a.T, a.K, a.dil = B, CI, cw.CO, T, cw.K, dil
+    a.pad = (cw.K - 1) * dil // 2
+    a.in_act, a.out_act, a.shuffle = in_act, out_act, shuffle
+    a.out_scale, a.res_scale = out_scale, res_scale
+    L.call("sty_conv1d_fwd", C.byref(a), L.stream_ptr())
+    return out
+
+
+def chan_layernorm(x, gamma, beta, *, eps, res=None, g_bs=0, plus_one=False, out=None, mask=None,
+                   act=ACT_NONE):
+    B, Cc, T = x.shape
+    x_bs, x_cs = L._bct(x, "x")
+    assert x_cs == T
+    if res is not None:
+        assert res.stride() == x.stride()
+    if out is None:
+        out = torch.empty((B, Cc, T), device=x.device, dtype=torch.float32)
+    y_bs, y_cs = L._bct(out, "out")
+    assert y_cs == T
+    L.call("sty_chan_layernorm_fwd", x.data_ptr(), L.ptr(res), x_bs, gamma.data_ptr(),
+           beta.data_ptr(), g_bs, int(plus_one), out.data_ptr(), y_bs, L.ptr(mask), B, Cc, T,
+           eps, act, L.stream_ptr())
+    return out
+
+
+def instnorm_affine(x, gb, gb_bs, eps=1e-5):
+    B, Cc, T = x.shape
+    x_bs, x_cs = L._bct(x, "x")
+    scale = torch.empty((B, Cc), device=x.device, dtype=torch.float32)
+    shift = torch.empty((B, Cc), device=x.device, dtype=torch.float32)
+    L.call("sty_instnorm_affine_fwd", x.data_ptr(), x_bs, x_cs, gb.data_ptr(), gb_bs,
+           scale.data_ptr(), shift.data_ptr(), B, Cc, T, eps, L.stream_ptr())
+    return scale, shift
+
+
+def dwconv1d(x, w, bias, *, K, pad_left, out, post_scale=None, post_shift=None, act=ACT_NONE):
+    B, Cc, T = x.shape
+    x_bs, x_cs = L._bct(x, "x")
+    y_bs, y_cs = L._bct(out, "out")
+    L.call("sty_dwconv1d_fwd", x.data_ptr(), x_bs, x_cs, w.data_ptr(), L.ptr(bias),
+           L.ptr(post_scale), L.ptr(post_shift), out.data_ptr(), y_bs, y_cs, B, Cc, T, K, pad_left,
+           act, L.stream_ptr())
+    return out
+
+
+def attention(qkv, n_q, n_k, n_v, *, H, D, lengths=None, rope=None, scale):
+    """qkv: (B, n_q+n_k+n_v, T) fused projection output."""
+    B, _, T = qkv.shape
+    bs, cs = L._bct(qkv, "qkv")
+    assert cs == T and n_q == n_k == n_v == H * D
+    out = torch.empty((B, H * D, T), device=qkv.device, dtype=torch.float32)
+    q = qkv.data_ptr()
+    k = q + 4 * n_q * T
+    v = k + 4 * n_k * T
+    rc, rs, d_rot = (None, None, 0) if rope is None else (rope[0].data_ptr(), rope[1].data_ptr(),
+                                                          rope[2])
+    L.call("sty_attention_fwd", q, k, v, bs, out.data_ptr(), out.stride(0), L.ptr(lengths), rc, rs,
+           d_rot, B, H, D, T, scale, L.stream_ptr())
+    return out
+
+
+class Packed:
+    """Device-resident, kernel-layout copy of a SpeechPredictor's parameters."""
+
+    def __init__(self, module, device):
+        sd = {k: v.detach().to(device=device, dtype=torch.float32) if v.is_floating_point()
+              else v.detach().to(device) for k, v in module.state_dict().items()}
+        self.device = device
+        mc = module.model_config
+        self.mc = mc
+        te = mc.text_encoder
+        self.n_layers, self.n_heads, self.hidden = te.layers, te.heads, te.hidden_dim
+
+        def wn(prefix):
+            k0 = prefix + ".parametrizations.weight.original0"
+            if k0 in sd:
+                return torch._weight_norm(sd[prefix + ".parametrizations.weight.original1"],
+                                          sd[k0], 0)
+            return sd[prefix + ".weight"]
+
+        def cv(prefix):
+            return ConvW(wn(prefix), sd.get(prefix + ".bias"))
+
+        def lin(prefix, bias=True):
+            return ConvW(sd[prefix + ".weight"].unsqueeze(-1),
+                         sd.get(prefix + ".bias") if bias else None)
+
+        # ---- all style FCs packed row-wise into one matrix --------------------
+        fc_names = sorted(k[:-len(".fc.weight")] for k in sd if k.endswith(".fc.weight"))
+        self.fc_off: Dict[str, int] = {}
+        rows, biases, off = [], [], 0
+        for n in fc_names:
+            w = sd[n + ".fc.weight"]
+            self.fc_off[n] = off
+            rows.append(w)
+            biases.append(sd[n + ".fc.bias"])
+            off += w.shape[0]
+        self.fc_w = torch.cat(rows, 0).contiguous()
+        self.fc_b = torch.cat(biases, 0).contiguous()
+        self.fc_rows = off
+
+        # ---- text encoder -------------------------------------------------------
+        t = "text_encoder"
+        self.emb = sd[t + ".emb.weight"].contiguous()
+        self.prenet = [(cv(f"{t}.prenet.conv_layers.{i}"),
+                        sd[f"{t}.prenet.norm_layers.{i}.gamma"].contiguous(),
+                        sd[f"{t}.prenet.norm_layers.{i}.beta"].contiguous()) for i in range(3)]
+        self.prenet_proj = cv(t + ".prenet.proj")
+        self.enc = []
+        e = t + ".encoder"
+        for i in range(self.n_layers):
+            a = f"{e}.attn_layers.{i}"
+            wqkv = torch.cat([sd[a + ".conv_q.weight"], sd[a + ".conv_k.weight"],
+                              sd[a + ".conv_v.weight"]], 0)
+            bqkv = torch.cat([sd[a + ".conv_q.bias"], sd[a + ".conv_k.bias"],
+                              sd[a + ".conv_v.bias"]], 0)
+            self.enc.append(dict(
+                qkv=ConvW(wqkv, bqkv), o=cv(a + ".conv_o"),
+                n1=(sd[f"{e}.norm_layers_1.{i}.gamma"].contiguous(),
+                    sd[f"{e}.norm_layers_1.{i}.beta"].contiguous()),
+                f1=cv(f"{e}.ffn_layers.{i}.conv_1"), f2=cv(f"{e}.ffn_layers.{i}.conv_2"),
+                n2=(sd[f"{e}.norm_layers_2.{i}.gamma"].contiguous(),
+                    sd[f"{e}.norm_layers_2.{i}.beta"].contiguous())))
+        self.proj_m = cv(t + ".proj_m")
+
+        # ---- decoder --------------------------------------------------------------
+        d = "decoder"
+
+        def dblock(p):
+            has_sc = (p + ".conv1x1.parametrizations.weight.original0") in sd
+            return dict(c1=cv(p + ".conv1"), c2=cv(p + ".conv2"),
+                        sc=cv(p + ".conv1x1") if has_sc else None,
+                        n1=p + ".norm1", n2=p + ".norm2")
+
+        self.dec_encode = dblock(d + ".encode")
+        self.dec_decode = [dblock(f"{d}.decode.{i}") for i in range(4)]
+        self.dec_side = [(wn(f"{d}.{n}").reshape(1, 3).contiguous(), sd[f"{d}.{n}.bias"].contiguous())
+                         for n in ("F0_conv", "N_conv", "voiced_conv")]
+        self.asr_res = cv(d + ".asr_res.0")
+
+        # ---- generator front + conformer ---------------------------------------------
+        g = "generator"
+        self.amp_input = cv(g + ".amp_input_conv")
+        self.amp_norm = (sd[g + ".amp_norm.weight"].contiguous(), sd[g + ".amp_norm.bias"].contiguous())
+        c = g + ".amp_conformer.layers.0"
+
+        def ff(p):
+            return dict(norm=p + ".fn.norm", w0=lin(p + ".fn.fn.net.0"), w3=lin(p + ".fn.fn.net.3"))
+
+        bn = c + ".conv.net.4"
+        bn_scale = sd[bn + ".weight"] / torch.sqrt(sd[bn + ".running_var"] + 1e-5)
+        bn_shift = sd[bn + ".bias"] - sd[bn + ".running_mean"] * bn_scale
+        wqkv = torch.cat([sd[c + ".attn.fn.to_q.weight"], sd[c + ".attn.fn.to_kv.weight"]], 0)
+        self.conf = dict(
+            ff1=ff(c + ".ff1"), ff2=ff(c + ".ff2"),
+            attn_norm=c + ".attn.norm", qkv=ConvW(wqkv.unsqueeze(-1), None),
+            out=lin(c + ".attn.fn.to_out"),
+            conv_norm=c + ".conv.norm", pw1=cv(c + ".conv.net.1"),
+            dw_w=sd[c + ".conv.net.3.conv.weight"].reshape(-1, 31).contiguous(),
+            dw_b=sd[c + ".conv.net.3.conv.bias"].contiguous(),
+            bn_scale=bn_scale.contiguous(), bn_shift=bn_shift.contiguous(),
+            pw2=cv(c + ".conv.net.6"), post_norm=c + ".post_norm")
+
+        # ---- basegen ----------------------------------------------------------------------
+        bg = g + ".basegen"
+
+        def cnx(p):
+            w2 = sd[p + ".pwconv2.weight"]
+            b2 = sd[p + ".pwconv2.bias"] + w2 @ sd[p + ".grn.beta"].reshape(-1)
+            return dict(dw_w=sd[p + ".dwconv.weight"].reshape(-1, 7).contiguous(),
+                        dw_b=sd[p + ".dwconv.bias"].contiguous(), norm=p + ".norm",
+                        pw1=lin(p + ".pwconv1"), snake=sd[p + ".snake"].reshape(-1).contiguous(),
+                        grn_gamma=sd[p + ".grn.gamma"].reshape(-1).contiguous(),
+                        pw2=ConvW(w2.unsqueeze(-1), b2))
+
+        def gblock(p):
+            return [dict(c1=cv(f"{p}.convs1.{i}"), c2=cv(f"{p}.convs2.{i}"),
+                         n1=f"{p}.adain1.{i}", n2=f"{p}.adain2.{i}",
+                         a1=sd[f"{p}.alpha1.{i}"].reshape(-1).contiguous(),
+                         a2=sd[f"{p}.alpha2.{i}"].reshape(-1).contiguous(), dil=dl)
+                    for i, dl in enumerate((1, 3, 5))]
+
+        self.amp_convnext = [cnx(f"{bg}.amp_convnext.{i}")
+                             for i in range(mc.generator.conv_layers - 3)]
+        self.upconvs = [cv(f"{bg}.upconvs.{i}") for i in range(3)]
+        self.upblocks = [cnx(f"{bg}.upblocks.{i}") for i in range(3)]
+        self.rates = (3, 5, 5)
+        self.src_w = sd[bg + ".m_source.l_linear.weight"].reshape(-1).contiguous()
+        self.src_b = sd[bg + ".m_source.l_linear.bias"].contiguous()
+        self.amp_prior_conv = cv(bg + ".amp_prior_conv")
+        self.phase_prior_conv = cv(bg + ".phase_prior_conv")
+        self.amp_prior_block = gblock(bg + ".amp_prior_block")
+        self.phase_prior_block = gblock(bg + ".phase_prior_block")
+        self.phase_input = cv(bg + ".phase_input_conv")
+        self.amp_output = cv(bg + ".amp_output_conv")
+        wri = torch.cat([sd[bg + ".phase_output_real_conv.weight"],
+                         sd[bg + ".phase_output_imag_conv.weight"]], 0)
+        bri = torch.cat([sd[bg + ".phase_output_real_conv.bias"],
+                         sd[bg + ".phase_output_imag_conv.bias"]], 0)
+        self.phase_out_ri = ConvW(wri, bri)
+        self.phase_norm = (sd[bg + ".phase_norm.weight"].contiguous(),
+                           sd[bg + ".phase_norm.bias"].contiguous())
+        self.phase_convnext = [cnx(f"{bg}.phase_convnext.{i}")
+                               for i in range(mc.generator.conv_layers)]
+        self.amp_final_ln = (sd[bg + ".amp_final_layer_norm.weight"].contiguous(),
+                             sd[bg + ".amp_final_layer_norm.bias"].contiguous())
+        self.phase_final_ln = (sd[bg + ".phase_final_layer_norm.weight"].contiguous(),
+                               sd[bg + ".phase_final_layer_norm.bias"].contiguous())
+        self.stft_f_re = sd[bg + ".stft.weight_forward_real"].reshape(-1, 64).contiguous()
+        self.stft_f_im = sd[bg + ".stft.weight_forward_imag"].reshape(-1, 64).contiguous()
+        self.stft_b_re = sd[bg + ".stft.weight_backward_real"].reshape(-1, 64).contiguous()
+        self.stft_b_im = sd[bg + ".stft.weight_backward_imag"].reshape(-1, 64).contiguous()
+        self.hidden_s = mc.n_fft // 2 // 8  # 32 channels at the STFT-frame rate
+        self.rope_cache: Dict[int, tuple] = {}
+
+    def rope(self, T: int):
+        if T not in self.rope_cache:
+            d = self.hidden // self.n_heads
+            d_rot = int(d * 0.5)
+            c = torch.empty((T, d_rot // 2), device=self.device, dtype=torch.float32)
+            s = torch.empty_like(c)
+            L.call("sty_rope_table", c.data_ptr(), s.data_ptr(), T, d_rot, 10000.0, L.stream_ptr())
+            self.rope_cache[T] = (c, s, d_rot)
+        return self.rope_cache[T]
+
+
+class SpeechEngine:
+    def __init__(self, module):
+        L.load()  # fail loudly if the CUDA library is missing
+        self.module = module
+        self._packed: Optional[Packed] = None
+        self._packed_key = None
+
+    # parameters are repacked when any of them changed (optimizer step, load_state_dict)
+    def packed(self, device) -> Packed:
+        key = (str(device),) + tuple(p._version for p in self.module.parameters()) + \
+            tuple(b._version for b in self.module.buffers())
+        if self._packed is None or key != self._packed_key:
+            self._packed = Packed(self.module, device)
+            self._packed_key = key
+        return self._packed
+
+    # ------------------------------------------------------------------ stages
+    @staticmethod
+    def _gb(P: Packed, h, name):
+        """pointer view of the (gamma|beta) rows of style FC `name` inside h (B, J)."""
+        return h[:, P.fc_off[name]:]
+
+    def text_encoder(self, P: Packed, texts, lengths, taps=None):
+        B, T = texts.shape
+        Cc = P.hidden
+        dev = texts.device
+        x0 = torch.empty((B, Cc, T), device=dev, dtype=torch.float32)
+        L.call("sty_embed_fwd", texts.data_ptr(), lengths.data_ptr(), P.emb.data_ptr(),
+               x0.data_ptr(), B, T, Cc, P.emb.shape[0], math.sqrt(Cc), L.stream_ptr())
+        mask = torch.empty((B, T), device=dev, dtype=torch.float32)
+        L.call("sty_sequence_mask_fwd", lengths.data_ptr(), mask.data_ptr(), B, T, L.stream_ptr())
+        h = x0
+        for cw, gm, bt in P.prenet:
+            y = conv1d(h, cw, in_mask=mask)
+            h = chan_layernorm(y, gm, bt, eps=1e-4, act=ACT_RELU)
+        x = conv1d(h, P.prenet_proj, out_mask=mask, res=x0)  # x0 is already masked
+        if taps is not None:
+            taps["prenet"] = x.clone()
+        rope = P.rope(T)
+        H = P.n_heads
+        D = Cc // H
+        for i, ly in enumerate(P.enc):
+            qkv = conv1d(x, ly["qkv"], in_mask=mask)
+            att = attention(qkv, Cc, Cc, Cc, H=H, D=D, lengths=lengths, rope=rope,
+                            scale=1.0 / math.sqrt(D))
+            y = conv1d(att, ly["o"])
+            x1 = chan_layernorm(y, *ly["n1"], eps=1e-4, res=x)
+            hh = conv1d(x1, ly["f1"], in_mask=mask, out_act=ACT_RELU)
+            y2 = conv1d(hh, ly["f2"], in_mask=mask, out_mask=mask)
+            x = chan_layernorm(y2, *ly["n2"], eps=1e-4, res=x1, mask=mask)
+        mu = conv1d(x, P.proj_m, out_mask=mask)
+        return mu, x, mask
+
+    def _decoder_block(self, P, blk, x, h, out):
+        J = P.fc_rows
+        sc1, sh1 = instnorm_affine(x, self._gb(P, h, blk["n1"]), J)
+        t1 = conv1d(x, blk["c1"], in_scale=sc1, in_shift=sh1, in_act=ACT_LEAKY02)
+        sc2, sh2 = instnorm_affine(t1, self._gb(P, h, blk["n2"]), J)
+        short = conv1d(x, blk["sc"]) if blk["sc"] is not None else x
+        return conv1d(t1, blk["c2"], in_scale=sc2, in_shift=sh2, in_act=ACT_LEAKY02, res=short,
+                      out_scale=INV_SQRT2, res_scale=INV_SQRT2, out=out)
+
+    def decoder(self, P: Packed, mu, alignment, pitch, energy, voiced, h, taps=None):
+        B, Cm, T = mu.shape
+        Fr = alignment.shape[2]
+        dev = mu.device
+        res_dim = P.asr_res.CO
+        cat0 = torch.empty((B, Cm + 3, Fr), device=dev, dtype=torch.float32)
+        cat_a = torch.empty((B, Cm + res_dim + 3, Fr), device=dev, dtype=torch.float32)
+        cat_b = torch.empty_like(cat_a)
+        # asr = text_encoding @ alignment, written straight into the concat buffer
+        L.call("sty_bmm_fwd", mu.data_ptr(), mu.stride(0), alignment.data_ptr(),
+               alignment.stride(0), cat0.data_ptr(), cat0.stride(0), B, Cm, Fr, T, L.stream_ptr())
+        asr = cat0[:, :Cm]
+        sides = (pitch, energy, voiced)
+        for j, (src, (w, b)) in enumerate(zip(sides, P.dec_side)):
+            s3 = src.reshape(B, 1, Fr)
+            dwconv1d(s3, w, b, K=3, pad_left=1, out=cat0[:, Cm + j:Cm + j + 1])
+            for cat in (cat_a, cat_b):
+                c0 = Cm + res_dim + j
+                dwconv1d(s3, w, b, K=3, pad_left=1, out=cat[:, c0:c0 + 1])
+        for cat in (cat_a, cat_b):
+            conv1d(asr, P.asr_res, out=cat[:, Cm:Cm + res_dim])
+        x = self._decoder_block(P, P.dec_encode, cat0, h, cat_a[:, :Cm])
+        if taps is not None:
+            taps["dec_encode"] = x.clone()
+        cur, nxt = cat_a, cat_b
+        for i, blk in enumerate(P.dec_decode):
+            last = i == len(P.dec_decode) - 1
+            out = torch.empty((B, Cm, Fr), device=dev, dtype=torch.float32) if last else nxt[:, :Cm]
+            x = self._decoder_block(P, blk, cur, h, out)
+            cur, nxt = nxt, cur
+        return x
+
+    def _ada_ln(self, P, x, h, name, eps):
+        gb = self._gb(P, h, name)
+        Cc = x.shape[1]
+        return chan_layernorm(x, gb, gb[:, Cc:], eps=eps, g_bs=P.fc_rows, plus_one=True)
+
+    def conformer(self, P: Packed, x, h):
+        cf = P.conf
+        B, Cc, T = x.shape
+
+        def ff(blk, xin):
+            n = self._ada_ln(P, xin, h, blk["norm"], 1e-5)
+            u = conv1d(n, blk["w0"], out_act=ACT_SWISH)
+            return conv1d(u, blk["w3"], res=xin, out_scale=0.5, res_scale=1.0)
+
+        x_ff1 = ff(cf["ff1"], x)
+        n = self._ada_ln(P, x, h, cf["attn_norm"], 1e-5)
+        qkv = conv1d(n, cf["qkv"])
+        att = attention(qkv, 512, 512, 512, H=8, D=64, scale=64 ** -0.5)
+        x2 = conv1d(att, cf["out"], res=x_ff1)
+        n = self._ada_ln(P, x2, h, cf["conv_norm"], 1e-5)
+        g = conv1d(n, cf["pw1"])
+        half = g.shape[1] // 2
+        gl = torch.empty((B, half, T), device=x.device, dtype=torch.float32)
+        L.call("sty_glu_fwd", g.data_ptr(), gl.data_ptr(), B, half, T, L.stream_ptr())
+        d = torch.empty_like(gl)
+        dwconv1d(gl, cf["dw_w"], cf["dw_b"], K=31, pad_left=15, out=d, post_scale=cf["bn_scale"],
+                 post_shift=cf["bn_shift"], act=ACT_SWISH)
+        x3 = conv1d(d, cf["pw2"], res=x2)
+        x4 = ff(cf["ff2"], x3)
+        return self._ada_ln(P, x4, h, cf["post_norm"], 1e-5)
+
+    def convnext(self, P: Packed, blk, x, h):
+        """GeneratorConvNeXtBlock, in place on x (B,C,T) (conv_next.py:80-93)."""
+        B, Cc, T = x.shape
+        J = P.fc_rows
+        gb = self._gb(P, h, blk["norm"])
+        y = torch.empty((B, Cc, T), device=x.device, dtype=torch.float32)
+        L.call("sty_dwconv_ln_fwd", x.data_ptr(), x.stride(0), blk["dw_w"].data_ptr(),
+               blk["dw_b"].data_ptr(), gb.data_ptr(), J, y.data_ptr(), y.stride(0), B, Cc, T, 1e-6,
+               L.stream_ptr())
+        inter = blk["pw1"].CO
+        sumsq = torch.zeros((B, inter), device=x.device, dtype=torch.float32)
+        hb = conv1d(y, blk["pw1"], out_act=ACT_SNAKE, out_alpha=blk["snake"], out_sumsq=sumsq)
+        gs = torch.empty_like(sumsq)
+        L.call("sty_grn_scale_fwd", sumsq.data_ptr(), blk["grn_gamma"].data_ptr(), gs.data_ptr(), B,
+               inter, L.stream_ptr())
+        conv1d(hb, blk["pw2"], in_scale=gs, res=x, out=x)
+        return x
+
+    def gen_block(self, P: Packed, blocks, x, h):
+        """AdaptiveGeneratorBlock, in place on x (ada_norm.py:109-120)."""
+        J = P.fc_rows
+        for blk in blocks:
+            sc1, sh1 = instnorm_affine(x, self._gb(P, h, blk["n1"]), J)
+            xt = conv1d(x, blk["c1"], dil=blk["dil"], in_scale=sc1, in_shift=sh1, in_act=ACT_SNAKE,
+                        in_alpha=blk["a1"])
+            sc2, sh2 = instnorm_affine(xt, self._gb(P, h, blk["n2"]), J)
+            conv1d(xt, blk["c2"], in_scale=sc2, in_shift=sh2, in_act=ACT_SNAKE, in_alpha=blk["a2"],
+                   res=x, out=x)
+        return x
+
+    def harmonic_prior(self, P: Packed, pitch, voiced, noise, taps=None):
+        B, Fr = pitch.shape
+        mc = P.mc
+        hop = mc.hop_length
+        Lw = Fr * hop
+        H = P.src_w.numel()
+        dev = pitch.device
+        if noise is None:
+            # the reference draws these with torch.randn (generator.py:440)
+            noise = torch.randn((B, Lw, H), device=dev, dtype=torch.float32)
+        assert noise.shape == (B, Lw, H) and noise.is_contiguous()
+        work = torch.empty((B, H, Fr), device=dev, dtype=torch.float64)
+        wave = torch.empty((B, Lw), device=dev, dtype=torch.float32)
+        L.call("sty_source_fwd", pitch.data_ptr(), voiced.data_ptr(), noise.data_ptr(),
+               P.src_w.data_ptr(), P.src_b.data_ptr(), work.data_ptr(), wave.data_ptr(), B, Fr, hop,
+               H, float(mc.sample_rate), 0.1, 0.003, 10.0, L.stream_ptr())
+        hop_s = hop // 75
+        S = Lw // hop_s
+        spec = torch.empty((B, P.hidden_s, S), device=dev, dtype=torch.float32)
+        phase = torch.empty_like(spec)
+        L.call("sty_stft_fwd", wave.data_ptr(), P.stft_f_re.data_ptr(), P.stft_f_im.data_ptr(),
+               spec.data_ptr(), phase.data_ptr(), B, Lw, 64, hop_s, P.hidden_s, L.stream_ptr())
+        if taps is not None:
+            taps["prior_wave"] = wave
+        return spec, phase
+
+    def generator(self, P: Packed, mel, h, pitch, voiced, noise, prior=None, taps=None):
+        B, _, Fr = mel.shape
+        dev = mel.device
+        x = conv1d(mel, P.amp_input)
+        x = chan_layernorm(x, *P.amp_norm, eps=1e-6)
+        if taps is not None:
+            taps["amp_norm"] = x.clone()
+        x = self.conformer(P, x, h)
+        if taps is not None:
+            taps["conformer"] = x.clone()
+        if prior is None:
+            har_spec, har_phase = self.harmonic_prior(P, pitch, voiced, noise, taps)
+        else:
+            har_spec, har_phase = prior
+        if taps is not None:
+            taps["har_spec"], taps["har_phase"] = har_spec, har_phase
+        S = har_spec.shape[2]
+        Hs = P.hidden_s
+        # phase-head input: [upsampled mel | logamp prior | phase prior] in one buffer
+        pin = torch.empty((B, 3 * Hs, S), device=dev, dtype=torch.float32)
+        lp = conv1d(har_spec, P.amp_prior_conv, out=pin[:, Hs:2 * Hs])
+        self.gen_block(P, P.amp_prior_block, lp, h)
+        pp = conv1d(har_phase, P.phase_prior_conv, out=pin[:, 2 * Hs:])
+        self.gen_block(P, P.phase_prior_block, pp, h)
+        if taps is not None:
+            taps["logamp_prior"], taps["phase_prior"] = lp.clone(), pp.clone()
+        for blk in P.amp_convnext:
+            x = self.convnext(P, blk, x, h)
+        if taps is not None:
+            taps["amp_convnext"] = x.clone()
+        for i, (cw, blk, r) in enumerate(zip(P.upconvs, P.upblocks, P.rates)):
+            last = i == len(P.rates) - 1
+            out = pin[:, :Hs] if last else None
+            x = conv1d(x, cw, shuffle=r, out=out)
+            x = self.convnext(P, blk, x, h)
+        if taps is not None:
+            taps["upsampled"] = x.clone()
+        la = chan_layernorm(x, *P.amp_final_ln, eps=1e-6)
+        logamp = conv1d(la, P.amp_output)
+        ph = conv1d(pin, P.phase_input)
+        ph = chan_layernorm(ph, *P.phase_norm, eps=1e-6, out=ph)
+        for blk in P.phase_convnext:
+            ph = self.convnext(P, blk, ph, h)
+        ph = chan_layernorm(ph, *P.phase_final_ln, eps=1e-6, out=ph)
+        ri = conv1d(ph, P.phase_out_ri)  # (B, 2*Hs, S): real | imag
+        if taps is not None:
+            taps["logamp"], taps["real"], taps["imag"] = logamp, ri[:, :Hs], ri[:, Hs:]
+        hop_s = P.mc.hop_length // 75
+        audio = torch.empty((B, 1, S * hop_s), device=dev, dtype=torch.float32)
+        L.call("sty_istft_head_fwd", logamp.data_ptr(), logamp.stride(0), ri.data_ptr(),
+               ri.data_ptr() + 4 * Hs * S, ri.stride(0), P.stft_b_re.data_ptr(),
+               P.stft_b_im.data_ptr(), audio.data_ptr(), B, S, Hs, 64, hop_s, L.stream_ptr())
+        return audio
+
+    # ------------------------------------------------------------------ forward
+    @torch.no_grad()
+    def forward(self, texts, text_lengths, alignment, pitch, energy, voiced, style,
+                denormal_pitch, *, source_draws=None, prior=None, taps=None):
+        dev = texts.device
+        if dev.type != "cuda":
+            raise RuntimeError("stylish_tts_b200: inputs must live on a CUDA device; "
+                               "there is no CPU fallback")
+        P = self.packed(dev)
+        f32 = lambda t: t.to(device=dev, dtype=torch.float32).contiguous()
+        texts = texts.to(torch.int64).contiguous()
+        text_lengths = text_lengths.to(device=dev, dtype=torch.int64).contiguous()
+        alignment, pitch, energy = f32(alignment), f32(pitch), f32(energy)
+        voiced, style, denormal_pitch = f32(voiced), f32(style), f32(denormal_pitch)
+        B = texts.shape[0]
+        h = torch.empty((B, P.fc_rows), device=dev, dtype=torch.float32)
+        L.call("sty_linear_rows_fwd", style.data_ptr(), P.fc_w.data_ptr(), P.fc_b.data_ptr(),
+               h.data_ptr(), B, style.shape[1], P.fc_rows, L.stream_ptr())
+        mu, _, _ = self.text_encoder(P, texts, text_lengths, taps)
+        if taps is not None:
+            taps["text_encoding"] = mu
+        mel = self.decoder(P, mu, alignment, pitch, energy, voiced, h, taps)
+        if taps is not None:
+            taps["decoder"] = mel
+        noise = None
+        if source_draws is not None:
+            noise = f32(source_draws["noise"])
+        return self.generator(P, mel, h, denormal_pitch, voiced, noise, prior=prior, taps=taps)

@@ -304,14 +304,14 @@ class SpeechPredictor(nn.Module):
         return self._engine
 
     def forward(self, texts, text_lengths, alignment, pitch, energy, voiced, style,
-                denormal_pitch, *, source_draws=None, taps=None):
+                denormal_pitch, *, source_draws=None, prior=None, taps=None):
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             raise NotImplementedError(
                 "stylish_tts_b200: the backward kernels of speech_predictor are not built "
                 "yet; call under torch.no_grad() (forward/inference path)")
         audio = self.engine().forward(texts, text_lengths, alignment, pitch, energy, voiced,
                                       style, denormal_pitch, source_draws=source_draws,
-                                      taps=taps)
+                                      prior=prior, taps=taps)
         return DecoderPrediction(audio=audio, magnitude=None, phase=None)
 
 
