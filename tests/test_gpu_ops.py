@@ -126,7 +126,8 @@ def test_conv1d_snake_epilogue_sumsq_and_grn():
     assert rel_l2(hb, h.transpose(1, 2)) < TOL
     assert rel_l2(sumsq, (h ** 2).sum(1)) < TOL
     gs = torch.empty_like(sumsq)
-    L.call("sty_grn_scale_fwd", sumsq.data_ptr(), gam.to(d).data_ptr(), gs.data_ptr(), B, inter,
+    gamd = gam.to(d)
+    L.call("sty_grn_scale_fwd", sumsq.data_ptr(), gamd.data_ptr(), gs.data_ptr(), B, inter,
            L.stream_ptr())
     b2f = b2 + w2 @ bet
     xr = res.to(d)
@@ -185,9 +186,9 @@ def test_dwconv_ln(Cc, T):
     d = dev()
     bigd = big.to(d)
     y = torch.empty(B, Cc, T, device=d)
-    L.call("sty_dwconv_ln_fwd", bigd.data_ptr(), bigd.stride(0), w.reshape(Cc, 7).contiguous().to(d).data_ptr(),
-           b.to(d).data_ptr(), gb.to(d).data_ptr(), 2 * Cc, y.data_ptr(), y.stride(0), B, Cc, T, 1e-6,
-           L.stream_ptr())
+    wd, bd, gbd = w.reshape(Cc, 7).contiguous().to(d), b.to(d), gb.to(d)  # keep alive
+    L.call("sty_dwconv_ln_fwd", bigd.data_ptr(), bigd.stride(0), wd.data_ptr(), bd.data_ptr(),
+           gbd.data_ptr(), 2 * Cc, y.data_ptr(), y.stride(0), B, Cc, T, 1e-6, L.stream_ptr())
     assert rel_l2(y, ref) < TOL
 
 
