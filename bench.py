@@ -305,9 +305,9 @@ def run_ours(args):
                         "fp32_tflops": round(flops / avg_s / 1e12, 2),
                         "note": "fp32-FMA conv (parity-first); limited by the FP32 pipe, not HBM "
                                 "— see DESIGN.md"}
-        log("[bench] per-kernel device time of one step (event-timed, eager):")
-        for r in top:
-            log("   ", r)
+        log(f"[bench] per-kernel device time of one step (event-timed, eager; total {total / 2:.2f} ms):")
+        for k, v in ranked:
+            log(f"    {v['ms'] / total * 100:6.2f}%  n={v['n'] // 2:3d}  avg {v['ms'] / v['n']:8.4f} ms  {k}")
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:

@@ -37,22 +37,39 @@ static inline cudaStream_t as_stream(sty_stream_t s) { return reinterpret_cast<c
 static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
 // ---------------------------------------------------------------- device math
-__device__ __forceinline__ float act_apply(float v, int act, float alpha) {
+// sin^2(y): even and pi-periodic, so reduce to r in [-pi/2, pi/2] with a two-term
+// Cody-Waite step and evaluate the odd Taylor polynomial through r^11
+// (|error| < 1e-7 on the interval).  ~15 instructions instead of sinf's ~40; this
+// is the Snake activation's inner function and sits in conv prologues/epilogues.
+__device__ __forceinline__ float sin_sq(float y) {
+  const float k = rintf(y * 0.318309886183790672f);
+  float r = fmaf(k, -3.14159274101257324f, y);
+  r = fmaf(k, 8.74227800037247e-08f, r);
+  const float r2 = r * r;
+  float p = fmaf(r2, -2.50521083854417e-08f, 2.75573192239859e-06f);
+  p = fmaf(p, r2, -1.98412698412698e-04f);
+  p = fmaf(p, r2, 8.33333333333333e-03f);
+  p = fmaf(p, r2, -1.66666666666667e-01f);
+  const float s = fmaf(r * r2, p, r);
+  return s * s;
+}
+
+// `alpha` / `inv_alpha` are only read for STY_ACT_SNAKE.
+__device__ __forceinline__ float act_apply(float v, int act, float alpha, float inv_alpha) {
   switch (act) {
     case STY_ACT_RELU:
       return fmaxf(v, 0.f);
     case STY_ACT_LEAKY02:
       return v > 0.f ? v : 0.2f * v;
-    case STY_ACT_SNAKE: {
-      float s = sinf(alpha * v);
-      return v + (1.0f / alpha) * (s * s);
-    }
+    case STY_ACT_SNAKE:
+      return fmaf(inv_alpha, sin_sq(alpha * v), v);
     case STY_ACT_SWISH:
       return v / (1.0f + expf(-v));
     default:
       return v;
   }
 }
+__device__ __forceinline__ float act_apply(float v, int act) { return act_apply(v, act, 1.f, 1.f); }
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -7,14 +7,15 @@
 // staged next to it in (ci, k, co) order so each thread reads its CO_R weights
 // as broadcast 128-bit loads.  Threads own a CO_R x T_R register tile whose T
 // positions are interleaved by the lane count (lane-consecutive shared loads,
-// fully coalesced global stores).
+// fully coalesced global stores).  Staging loads are issued 8 rows at a time so
+// each thread keeps 8+ global loads in flight.
 //
 // Semantics: see sty_conv1d_fwd in include/stylish_b200.h.
 #include "common.cuh"
 
 namespace sty {
 
-template <int CO_TILE, int T_TILE, int CO_R, int T_R, int KT>
+template <int CO_TILE, int T_TILE, int CO_R, int T_R, int KT, bool PRO>
 __global__ void __launch_bounds__((CO_TILE / CO_R) * (T_TILE / T_R))
 conv1d_kernel(const sty_conv1d_args p, const int ci_chunk, const int xtp) {
   constexpr int TL = T_TILE / T_R;  // threads along time
@@ -44,29 +45,55 @@ conv1d_kernel(const sty_conv1d_args p, const int ci_chunk, const int xtp) {
 
   const float* __restrict__ xb = p.x + (int64_t)b * p.x_bs;
   const float* __restrict__ wb = p.w + (int64_t)b * p.w_bs;
-  const float* __restrict__ in_mask = p.in_mask ? p.in_mask + (int64_t)b * p.T : nullptr;
+  const float* __restrict__ in_mask = (PRO && p.in_mask) ? p.in_mask + (int64_t)b * p.T : nullptr;
+  const float* __restrict__ in_scale = (PRO && p.in_scale) ? p.in_scale + (int64_t)b * p.CI : nullptr;
+  const float* __restrict__ in_shift = (PRO && p.in_shift) ? p.in_shift + (int64_t)b * p.CI : nullptr;
+  const float* __restrict__ in_alpha = (PRO && p.in_alpha) ? p.in_alpha : nullptr;
+  const int in_act = PRO ? p.in_act : STY_ACT_NONE;
   const bool co_vec = (p.CO % 4 == 0);
 
   for (int ci0 = 0; ci0 < p.CI; ci0 += ci_chunk) {
     const int cc = min(ci_chunk, p.CI - ci0);
     // ---- stage the input rows, prologue applied, zero outside [0,T)
-    for (int ci = 0; ci < cc; ++ci) {
-      const int c = ci0 + ci;
-      const float* __restrict__ xr = xb + (int64_t)c * p.x_cs;
-      float sc = 1.f, sh = 0.f, al = 1.f;
-      if (p.in_scale) sc = p.in_scale[(int64_t)b * p.CI + c];
-      if (p.in_shift) sh = p.in_shift[(int64_t)b * p.CI + c];
-      if (p.in_alpha) al = p.in_alpha[c];
-      for (int tt = tid; tt < xtp; tt += NT) {
-        const int t = t0 - p.pad + tt;
-        float v = 0.f;
-        if (tt < XT && t >= 0 && t < p.T) {
-          v = xr[t];
-          if (in_mask) v *= in_mask[t];
-          v = fmaf(v, sc, sh);
-          v = act_apply(v, p.in_act, al);
+    for (int tt = tid; tt < xtp; tt += NT) {
+      const int t = t0 - p.pad + tt;
+      const bool ok = (tt < XT) && (t >= 0) && (t < p.T);
+      const float* __restrict__ xr = xb + (int64_t)ci0 * p.x_cs + t;
+      float* __restrict__ xd = xs + tt;
+      float m = 1.f;
+      if (PRO && ok && in_mask) m = in_mask[t];
+      constexpr int U = 8;  // rows per batch: all loads of a batch are issued before any use
+      for (int cb = 0; cb < cc; cb += U) {
+        float v[U], sc[U], sh[U], al[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int ci = cb + u;
+          v[u] = (ok && ci < cc) ? xr[(int64_t)ci * p.x_cs] : 0.f;
         }
-        xs[ci * xtp + tt] = v;
+        if constexpr (PRO) {
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int c = min(ci0 + cb + u, p.CI - 1);
+            sc[u] = in_scale ? in_scale[c] : 1.f;
+            sh[u] = in_shift ? in_shift[c] : 0.f;
+            al[u] = in_alpha ? in_alpha[c] : 1.f;
+          }
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            float w = fmaf(v[u] * m, sc[u], sh[u]);
+            if (in_act == STY_ACT_SNAKE) {
+              w = fmaf(1.0f / al[u], sin_sq(al[u] * w), w);
+            } else if (in_act == STY_ACT_LEAKY02) {
+              w = w > 0.f ? w : 0.2f * w;
+            } else if (in_act != STY_ACT_NONE) {
+              w = act_apply(w, in_act);
+            }
+            v[u] = ok ? w : 0.f;
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          if (cb + u < cc) xd[(cb + u) * xtp] = v[u];
       }
     }
     // ---- stage the weight chunk (rows of CO_TILE contiguous floats)
@@ -75,6 +102,7 @@ conv1d_kernel(const sty_conv1d_args p, const int ci_chunk, const int xtp) {
       const float* __restrict__ wsrc = wb + (int64_t)ci0 * K * p.CO + co0;
       if (co_vec) {
         constexpr int V = CO_TILE / 4;
+#pragma unroll 4
         for (int idx = tid; idx < rows * V; idx += NT) {
           const int r = idx / V, c4 = (idx - r * V) * 4;
           float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -122,26 +150,35 @@ conv1d_kernel(const sty_conv1d_args p, const int ci_chunk, const int xtp) {
   float* __restrict__ yb = p.y + (int64_t)b * p.y_bs;
   const float* __restrict__ rb = p.res ? p.res + (int64_t)b * p.r_bs : nullptr;
   const int s = p.shuffle > 1 ? p.shuffle : 1;
+  const int out_act = p.out_act;
+  float om[T_R];
+#pragma unroll
+  for (int j = 0; j < T_R; ++j) {
+    const int t = t0 + tl + j * TL;
+    om[j] = (out_mask && t < p.T) ? out_mask[t] : 1.f;
+    om[j] *= p.out_scale;
+  }
 #pragma unroll
   for (int i = 0; i < CO_R; ++i) {
     const int co = co0 + cg * CO_R + i;
     const bool co_ok = co < p.CO;
     const float bias = (co_ok && p.bias) ? p.bias[co] : 0.f;
     const float al = (co_ok && p.out_alpha) ? p.out_alpha[co] : 1.f;
+    const float inv_al = 1.0f / al;
     float ssq = 0.f;
     if (co_ok) {
       const int c_out = co / s, r_out = co - c_out * s;
+      float* __restrict__ yrow = yb + (int64_t)c_out * p.y_cs + r_out;
+      const float* __restrict__ rrow = rb ? rb + (int64_t)c_out * p.r_cs + r_out : nullptr;
 #pragma unroll
       for (int j = 0; j < T_R; ++j) {
         const int t = t0 + tl + j * TL;
         if (t < p.T) {
           float v = acc[i][j] + bias;
-          v = act_apply(v, p.out_act, al);
-          if (out_mask) v *= out_mask[t];
-          v *= p.out_scale;
-          const int64_t off = (int64_t)c_out * p.y_cs + (int64_t)t * s + r_out;
-          if (rb) v = fmaf(p.res_scale, rb[(int64_t)c_out * p.r_cs + (int64_t)t * s + r_out], v);
-          yb[off] = v;
+          v = act_apply(v, out_act, al, inv_al);
+          v *= om[j];
+          if (rrow) v = fmaf(p.res_scale, rrow[(int64_t)t * s], v);
+          yrow[(int64_t)t * s] = v;
           ssq = fmaf(v, v, ssq);
         }
       }
@@ -154,7 +191,11 @@ conv1d_kernel(const sty_conv1d_args p, const int ci_chunk, const int xtp) {
   }
 }
 
-template <int CO_TILE, int T_TILE, int CO_R, int T_R, int KT>
+struct Cfg {
+  int co_tile, t_tile, threads;
+};
+
+template <int CO_TILE, int T_TILE, int CO_R, int T_R, int KT, bool PRO>
 static int launch_cfg(const sty_conv1d_args& a, cudaStream_t st) {
   constexpr int NT = (CO_TILE / CO_R) * (T_TILE / T_R);
   const int XT = T_TILE + (a.K - 1) * a.dil;
@@ -165,7 +206,7 @@ static int launch_cfg(const sty_conv1d_args& a, cudaStream_t st) {
   if (chunk > 32) chunk = 32;
   if (chunk > a.CI) chunk = a.CI;
   const size_t smem = (size_t)chunk * per_ci;
-  auto kern = conv1d_kernel<CO_TILE, T_TILE, CO_R, T_R, KT>;
+  auto kern = conv1d_kernel<CO_TILE, T_TILE, CO_R, T_R, KT, PRO>;
   if (smem > 48 * 1024) {
     if (smem > 200 * 1024) {
       set_error("conv1d: kernel footprint too large (K=%d dil=%d)", a.K, a.dil);
@@ -179,16 +220,53 @@ static int launch_cfg(const sty_conv1d_args& a, cudaStream_t st) {
   return STY_OK;
 }
 
-template <int CO_TILE, int T_TILE, int CO_R, int T_R>
+template <int CO_TILE, int T_TILE, int CO_R, int T_R, bool PRO>
 static int launch_k(const sty_conv1d_args& a, cudaStream_t st) {
   switch (a.K) {
-    case 1: return launch_cfg<CO_TILE, T_TILE, CO_R, T_R, 1>(a, st);
-    case 3: return launch_cfg<CO_TILE, T_TILE, CO_R, T_R, 3>(a, st);
-    case 5: return launch_cfg<CO_TILE, T_TILE, CO_R, T_R, 5>(a, st);
-    case 11: return launch_cfg<CO_TILE, T_TILE, CO_R, T_R, 11>(a, st);
-    case 21: return launch_cfg<CO_TILE, T_TILE, CO_R, T_R, 21>(a, st);
-    default: return launch_cfg<CO_TILE, T_TILE, CO_R, T_R, 0>(a, st);
+    case 1: return launch_cfg<CO_TILE, T_TILE, CO_R, T_R, 1, PRO>(a, st);
+    case 3: return launch_cfg<CO_TILE, T_TILE, CO_R, T_R, 3, PRO>(a, st);
+    case 5: return launch_cfg<CO_TILE, T_TILE, CO_R, T_R, 5, PRO>(a, st);
+    case 11: return launch_cfg<CO_TILE, T_TILE, CO_R, T_R, 11, PRO>(a, st);
+    case 21: return launch_cfg<CO_TILE, T_TILE, CO_R, T_R, 21, PRO>(a, st);
+    default: return launch_cfg<CO_TILE, T_TILE, CO_R, T_R, 0, PRO>(a, st);
   }
+}
+
+template <int CO_TILE, int T_TILE, int CO_R, int T_R>
+static int launch_p(const sty_conv1d_args& a, cudaStream_t st) {
+  const bool pro = a.in_scale || a.in_shift || a.in_mask || a.in_act != STY_ACT_NONE;
+  return pro ? launch_k<CO_TILE, T_TILE, CO_R, T_R, true>(a, st)
+             : launch_k<CO_TILE, T_TILE, CO_R, T_R, false>(a, st);
+}
+
+// Tile choice: minimise (#waves x tile work), i.e. prefer the largest tile that still
+// fills the 148 SMs for about two waves; small T / few channels fall to small tiles.
+static int pick_config(const sty_conv1d_args& a) {
+  static int sms = 0;
+  if (sms <= 0) {
+    sms = sty_device_sm_count();
+    if (sms <= 0) sms = 148;
+  }
+  //                co_tile t_tile threads  resident CTAs per SM (registers/threads)
+  const int cfg[5][4] = {{128, 128, 256, 2}, {64, 128, 128, 4}, {32, 256, 128, 4},
+                         {64, 64, 128, 4},   {32, 64, 64, 8}};
+  double best = 1e30;
+  int pick = 4;
+  for (int i = 0; i < 5; ++i) {
+    const int cot = cfg[i][0], tt = cfg[i][1], thr = cfg[i][2], occ = cfg[i][3];
+    if (cot > 32 && cot > ((a.CO + 31) / 32) * 32) continue;  // tile wider than the output
+    const int64_t blocks = (int64_t)cdiv(a.T, tt) * cdiv(a.CO, cot) * a.B;
+    const int64_t per_sm = (blocks + sms - 1) / sms;  // CTAs the busiest SM executes
+    const double resident = (double)(per_sm < occ ? per_sm : occ) * thr / 32.0;
+    const double eff = resident >= 8.0 ? 1.0 : resident / 8.0;  // too few warps: latency-bound
+    double cost = (double)per_sm * cot * tt / eff;
+    cost *= 1.0 + 4.0 / cot + 8.0 / tt;  // smaller tiles re-read more weights / inputs
+    if (cost < best) {
+      best = cost;
+      pick = i;
+    }
+  }
+  return pick;
 }
 
 }  // namespace sty
@@ -199,6 +277,7 @@ extern "C" int sty_conv1d_fwd(const sty_conv1d_args* a, sty_stream_t stream) {
   STY_REQUIRE(a->x && a->w && a->y, "conv1d: null tensor pointer");
   STY_REQUIRE(a->B > 0 && a->CI > 0 && a->CO > 0 && a->T > 0, "conv1d: bad shape B=%d CI=%d CO=%d T=%d",
               a->B, a->CI, a->CO, a->T);
+  STY_REQUIRE(a->B <= 65535, "conv1d: batch too large for the grid");
   STY_REQUIRE(a->K >= 1 && a->K <= 64 && a->dil >= 1 && a->pad >= 0, "conv1d: bad K=%d dil=%d pad=%d",
               a->K, a->dil, a->pad);
   STY_REQUIRE(2 * a->pad == (a->K - 1) * a->dil, "conv1d: only 'same' padding is supported (K=%d dil=%d pad=%d)",
@@ -208,10 +287,11 @@ extern "C" int sty_conv1d_fwd(const sty_conv1d_args* a, sty_stream_t stream) {
   STY_REQUIRE(a->shuffle <= 1 || a->CO % a->shuffle == 0, "conv1d: CO %% shuffle != 0");
   STY_REQUIRE(a->shuffle <= 1 || a->out_sumsq == nullptr, "conv1d: sumsq with shuffle unsupported");
   cudaStream_t st = as_stream(stream);
-  if (a->CO <= 32) {
-    if (a->T > 96) return launch_k<32, 256, 8, 8>(*a, st);
-    return launch_k<32, 64, 8, 4>(*a, st);
+  switch (pick_config(*a)) {
+    case 0: return launch_p<128, 128, 8, 8>(*a, st);
+    case 1: return launch_p<64, 128, 8, 8>(*a, st);
+    case 2: return launch_p<32, 256, 8, 8>(*a, st);
+    case 3: return launch_p<64, 64, 8, 4>(*a, st);
+    default: return launch_p<32, 64, 8, 4>(*a, st);
   }
-  if (a->T > 96) return launch_k<64, 128, 8, 8>(*a, st);
-  return launch_k<64, 64, 8, 4>(*a, st);
 }

@@ -88,7 +88,7 @@ chan_layernorm_kernel(const float* __restrict__ xin, const float* __restrict__ r
     for (int c = 0; c < CREG; ++c) {
       const float gg = g_plus_one ? 1.0f + g[c] : g[c];
       float o = (v[c] - mean) * rstd * gg + be[c];
-      y[base + (int64_t)c * T] = act_apply(o, act, 1.f) * m;
+      y[base + (int64_t)c * T] = act_apply(o, act) * m;
     }
   } else {
     float s = 0.f;
@@ -111,7 +111,7 @@ chan_layernorm_kernel(const float* __restrict__ xin, const float* __restrict__ r
       if (res) v += res[base + (int64_t)c * T];
       const float gg = g_plus_one ? 1.0f + g[c] : g[c];
       float o = (v - mean) * rstd * gg + be[c];
-      y[base + (int64_t)c * T] = act_apply(o, act, 1.f) * m;
+      y[base + (int64_t)c * T] = act_apply(o, act) * m;
     }
   }
 }
@@ -192,7 +192,7 @@ dwconv1d_kernel(const float* __restrict__ x, int64_t x_bs, int64_t x_cs,
     if (u >= 0 && u < T) a = fmaf(w[c * K + k], xr[u], a);
   }
   if (post_scale) a = fmaf(a, post_scale[c], post_shift ? post_shift[c] : 0.f);
-  y[(int64_t)b * y_bs + (int64_t)c * y_cs + t] = act_apply(a, act, 1.f);
+  y[(int64_t)b * y_bs + (int64_t)c * y_cs + t] = act_apply(a, act);
 }
 
 // ----------------------------------------------------------------- GRN scale
