@@ -99,6 +99,10 @@ typedef struct sty_conv1d_args {
   int32_t B, CI, CO, T, K, dil, pad;
   int32_t in_act, out_act, shuffle;
   float out_scale, res_scale;
+  /* Optional tensor-core path (tcgen05, "bf16x3" split precision): the same weights
+   * pre-split into bf16 (hi, lo) in the UMMA K-major layout [K][2][CI/8][CO][8].
+   * NULL selects the fp32 FMA kernel.  Used when CI%16==0, CO%16==0 and T>=128. */
+  const void* w_split;
 } sty_conv1d_args;
 STY_API int sty_conv1d_fwd(const sty_conv1d_args* a, sty_stream_t stream);
 

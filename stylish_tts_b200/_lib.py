@@ -38,6 +38,7 @@ class ConvArgs(C.Structure):
         ("pad", _i32),
         ("in_act", _i32), ("out_act", _i32), ("shuffle", _i32),
         ("out_scale", _f32), ("res_scale", _f32),
+        ("w_split", _f32p),
     ]
 
 
@@ -140,6 +141,8 @@ def _signature(name: str, args) -> str:
             extra += "+ssq"
         if a.shuffle > 1:
             extra += f"+shuf{a.shuffle}"
+        if a.w_split:
+            extra += "+umma"
         return f"conv1d[ci={a.CI},co={a.CO},k={a.K},d={a.dil},B={a.B},T={a.T}{extra}]"
     return name[4:]
 

@@ -191,9 +191,8 @@ conv1d_kernel(const sty_conv1d_args p, const int ci_chunk, const int xtp) {
   }
 }
 
-struct Cfg {
-  int co_tile, t_tile, threads;
-};
+bool conv1d_umma_eligible(const sty_conv1d_args& a);         // conv1d_umma.cu
+int conv1d_umma_launch(const sty_conv1d_args& a, cudaStream_t st);
 
 template <int CO_TILE, int T_TILE, int CO_R, int T_R, int KT, bool PRO>
 static int launch_cfg(const sty_conv1d_args& a, cudaStream_t st) {
@@ -287,6 +286,7 @@ extern "C" int sty_conv1d_fwd(const sty_conv1d_args* a, sty_stream_t stream) {
   STY_REQUIRE(a->shuffle <= 1 || a->CO % a->shuffle == 0, "conv1d: CO %% shuffle != 0");
   STY_REQUIRE(a->shuffle <= 1 || a->out_sumsq == nullptr, "conv1d: sumsq with shuffle unsupported");
   cudaStream_t st = as_stream(stream);
+  if (conv1d_umma_eligible(*a)) return conv1d_umma_launch(*a, st);
   switch (pick_config(*a)) {
     case 0: return launch_p<128, 128, 8, 8>(*a, st);
     case 1: return launch_p<64, 128, 8, 8>(*a, st);

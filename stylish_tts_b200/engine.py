@@ -11,6 +11,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from typing import Dict, Optional
 
 import torch
@@ -19,6 +20,21 @@ from . import _lib as L
 from ._lib import ACT_LEAKY02, ACT_NONE, ACT_RELU, ACT_SNAKE, ACT_SWISH, ConvArgs
 
 INV_SQRT2 = 1.0 / math.sqrt(2.0)
+# tensor-core (tcgen05, bf16x3) path for eligible convs; STYLISH_B200_UMMA=0 forces fp32 FMA
+USE_UMMA = os.environ.get("STYLISH_B200_UMMA", "1") != "0"
+UMMA_MIN_T = 512
+
+
+def split_bf16(w_oik: torch.Tensor) -> torch.Tensor:
+    """(CO,CI,K) fp32 -> bf16 (hi, lo) pair in the UMMA K-major layout [K][2][CI/8][CO][8]."""
+    co, ci, k = w_oik.shape
+    hi = w_oik.to(torch.bfloat16)
+    lo = (w_oik - hi.float()).to(torch.bfloat16)
+
+    def lay(t):
+        return t.permute(2, 1, 0).reshape(k, ci // 8, 8, co).permute(0, 1, 3, 2)
+
+    return torch.stack([lay(hi), lay(lo)], dim=1).contiguous()
 
 
 # --------------------------------------------------------------------------
@@ -27,13 +43,15 @@ INV_SQRT2 = 1.0 / math.sqrt(2.0)
 class ConvW:
     """A conv/linear weight pre-packed as (CI, K, CO) plus its bias."""
 
-    __slots__ = ("w", "bias", "CI", "K", "CO")
+    __slots__ = ("w", "bias", "CI", "K", "CO", "split")
 
     def __init__(self, w_oik: torch.Tensor, bias: Optional[torch.Tensor]):
         co, ci, k = w_oik.shape
         self.w = w_oik.permute(1, 2, 0).contiguous()
         self.bias = None if bias is None else bias.contiguous()
         self.CI, self.K, self.CO = ci, k, co
+        ok = ci % 16 == 0 and co % 16 == 0 and co >= 16
+        self.split = split_bf16(w_oik) if ok else None
 
 
 def conv1d(x, cw: ConvW, *, dil=1, out=None, res=None, in_scale=None, in_shift=None,
@@ -63,6 +81,8 @@ def conv1d(x, cw: ConvW, *, dil=1, out=None, res=None, in_scale=None, in_shift=N
     a.pad = (cw.K - 1) * dil // 2
     a.in_act, a.out_act, a.shuffle = in_act, out_act, shuffle
     a.out_scale, a.res_scale = out_scale, res_scale
+    if USE_UMMA and cw.split is not None and T >= UMMA_MIN_T:
+        a.w_split = cw.split.data_ptr()
     L.call("sty_conv1d_fwd", C.byref(a), L.stream_ptr())
     return out
 

@@ -284,3 +284,60 @@ def test_bmm_glu_embed_mask_linear():
     L.call("sty_linear_rows_fwd", sd_.data_ptr(), Wd.data_ptr(), bd.data_ptr(), ho.data_ptr(), 4, 64,
            300, L.stream_ptr())
     assert rel_l2(ho, F.linear(s, W, bb)) < TOL
+
+
+@pytest.mark.parametrize("ci,co,k,dil,T", [
+    (32, 32, 21, 1, 1000), (96, 32, 21, 1, 700), (32, 64, 21, 1, 600), (32, 32, 11, 3, 777),
+    (32, 32, 11, 5, 640), (32, 128, 1, 1, 1111), (128, 32, 1, 1, 513), (256, 1024, 1, 1, 803),
+    (256, 1536, 1, 1, 515), (256, 384, 11, 1, 803),
+    (1024, 256, 1, 1, 803), (128, 256, 21, 1, 803), (64, 160, 11, 1, 600), (48, 16, 3, 1, 515),
+])
+def test_conv1d_tensor_core_bf16x3(ci, co, k, dil, T):
+    """tcgen05 path (bf16 hi/lo split, 3 MMAs, fp32 accumulate): ~16-bit operands."""
+    gen = g(ci * 7 + co + k)
+    B = 2
+    x = torch.randn(B, ci, T, generator=gen)
+    w = torch.randn(co, ci, k, generator=gen) / math.sqrt(ci * k)
+    b = torch.randn(co, generator=gen)
+    ref = F.conv1d(x.double(), w.double(), b.double(), padding=(k - 1) * dil // 2, dilation=dil)
+    cw = E.ConvW(w.to(dev()), b.to(dev()))
+    assert cw.split is not None
+    before = L.launches
+    out = E.conv1d(x.to(dev()), cw, dil=dil)
+    assert rel_l2(out, ref) < 3e-5, rel_l2(out, ref)
+
+
+def test_conv1d_tensor_core_fused_ops():
+    """prologue (affine+snake), epilogue (snake, sumsq, residual, shuffle) on the tcgen05 path."""
+    gen = g(77)
+    B, ci, co, T, k = 2, 32, 32, 900, 11
+    x = torch.randn(B, ci, T, generator=gen)
+    w = torch.randn(co, ci, k, generator=gen) / math.sqrt(ci * k)
+    bias = torch.randn(co, generator=gen)
+    sc, sh = torch.randn(B, ci, generator=gen), torch.randn(B, ci, generator=gen)
+    al = 0.5 + torch.rand(ci, generator=gen)
+    res = torch.randn(B, co, T, generator=gen)
+    xin = so.snake(sc[:, :, None] * x + sh[:, :, None], al.view(1, -1, 1))
+    ref = F.conv1d(xin.double(), w.double(), bias.double(), padding=5).float() + res
+    d = dev()
+    cw = E.ConvW(w.to(d), bias.to(d))
+    r = res.to(d)
+    E.conv1d(x.to(d), cw, in_scale=sc.to(d), in_shift=sh.to(d), in_alpha=al.to(d),
+             in_act=L.ACT_SNAKE, res=r, out=r)
+    assert rel_l2(r, ref) < 3e-5
+    # snake epilogue + sum of squares (pwconv1 of the ConvNeXt block)
+    w1 = torch.randn(128, 32, 1, generator=gen) / math.sqrt(32)
+    b1 = torch.randn(128, generator=gen) * 0.1
+    a1 = 0.75 + 0.5 * torch.rand(128, generator=gen)
+    h = so.snake(F.conv1d(x.double(), w1.double(), b1.double()), a1.view(1, -1, 1).double())
+    ssq = torch.zeros(B, 128, device=d)
+    hb = E.conv1d(x.to(d), E.ConvW(w1.to(d), b1.to(d)), out_act=L.ACT_SNAKE, out_alpha=a1.to(d),
+                  out_sumsq=ssq)
+    assert rel_l2(hb, h) < 3e-5
+    assert rel_l2(ssq, (h ** 2).sum(2)) < 3e-5
+    # pixel shuffle store
+    w2 = torch.randn(160, 32, 11, generator=gen) / math.sqrt(32 * 11)
+    b2 = torch.randn(160, generator=gen)
+    ref2 = so.pixel_shuffle_1d(F.conv1d(x.double(), w2.double(), b2.double(), padding=5), 5)
+    out2 = E.conv1d(x.to(d), E.ConvW(w2.to(d), b2.to(d)), shuffle=5)
+    assert rel_l2(out2, ref2) < 3e-5
