@@ -14,6 +14,14 @@
 // staging; the epilogue (bias, activation, mask, scale, residual, GRN sum of
 // squares, pixel-shuffle store) runs on the accumulator rows read back with
 // tcgen05.ld.  Semantics identical to the SIMT kernel in conv1d.cu.
+//
+// Execution: persistent, warp-specialised CTAs (one per SM).  Warps 0-7 stage
+// input tiles into a ring of shared-memory stages (up to 32 global loads in
+// flight per thread), warp 8 issues the MMAs (one elected thread) into one of
+// two TMEM accumulator stages, warps 9-16 drain the other accumulator stage
+// (epilogue) — the three roles hand over through mbarriers, so staging of tile
+// i+1, MMA of tile i and the epilogue of tile i-1 overlap.  Weights stay resident in shared memory when they fit, otherwise
+// they are streamed per input-channel chunk together with the input rows.
 #include <cuda_bf16.h>
 
 #include "common.cuh"
@@ -39,6 +47,25 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "r"(addr), "r"(parity)
         : "memory");
   } while (!done);
+}
+// waits of the non-critical roles back off so their polling does not steal issue slots
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done;
+  for (;;) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) break;
+    __nanosleep(64);
+  }
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -71,6 +98,19 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// same, descriptors passed as 32-bit words: only the low word (start address) changes inside a
+// tile, so the issuing thread does 32-bit adds instead of 64-bit descriptor rebuilds
+__device__ __forceinline__ void umma_bf16_w(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                            uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+      ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
@@ -92,6 +132,19 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* r) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// 32 lanes x 16 columns
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* r) {
+  uint32_t* u = reinterpret_cast<uint32_t*>(r);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]),
+        "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 // shared-memory matrix descriptor: K-major, SWIZZLE_NONE, sm_100 version bit.
 // lbo / sbo in units of 16 bytes (K-direction / 8-row-group strides).
 __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo16, uint32_t sbo16) {
@@ -105,226 +158,468 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 }
 
 // -------------------------------------------------------------------- kernel
-// grid: (ceil(T/128), CO/NT, B); 128 threads.  Thread t of the CTA owns accumulator row t;
-// NT (<= 256, multiple of 16) output channels per CTA.
-template <bool PRO>
-__global__ void __launch_bounds__(128)
-conv1d_umma_kernel(const sty_conv1d_args p, const int ci_chunk, const int rows, const int NT,
-                   const uint32_t tmem_cols) {
+struct UmmaPlan {
+  int ci_chunk;    // input channels per staged chunk (multiple of 16)
+  int n_chunks;    // ceil(CI / ci_chunk)
+  int rows;        // staged time steps per tile: 128 + (K-1)*dil
+  int NT;          // output channels per CTA (multiple of 16, <= 256)
+  int n_stages;    // shared-memory ring depth
+  int resident;    // 1: all weights of this CTA's NT channels stay in shared memory
+  int acc_cols;    // TMEM columns per accumulator stage (power of two >= NT, >= 32)
+  int stage_u4;    // uint4 per stage
+  int wres_u4;     // uint4 of the resident weight block (0 when streaming)
+  int tiles_per_b; // ceil(T / 128)
+  int prm_floats;  // floats of the per-channel parameter block (prologue + epilogue)
+};
+
+constexpr int kProducerWarps = 8;
+constexpr int kProducerThreads = kProducerWarps * 32;
+constexpr int kMmaWarp = kProducerWarps;
+constexpr int kEpilogueWarp0 = kMmaWarp + 1;
+constexpr int kEpilogueWarps = 8;
+constexpr int kThreads = (kEpilogueWarp0 + kEpilogueWarps) * 32;
+constexpr int kMaxStages = 4;
+constexpr int kItemBatch = 4;  // (row, 8-channel) items staged per thread per batch: 32 loads in flight
+
+// column sums over the 32 lanes of 16 per-lane values: lanes l and l+16 return sum_lanes v[l & 15]
+__device__ __forceinline__ float warp_colsum16(float (&v)[16], int lane) {
+#pragma unroll
+  for (int off = 8; off >= 1; off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = up ? v[i] : v[i + off];
+      const float keep = up ? v[i + off] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 16);
+}
+
+// IN_MODE : 0 no prologue | 1 mask/affine | 2 mask/affine + LeakyReLU(0.2) | 3 mask/affine + Snake
+// OUT_MODE: 0 none | 1 Snake | 2 ReLU | 3 Swish          (compile-time: keeps each role's loop small
+// enough for the instruction cache — three roles run different code on one SM)
+template <int IN_MODE, int OUT_MODE>
+__global__ void __launch_bounds__(kThreads, 1)
+conv1d_umma_kernel(const sty_conv1d_args p, const UmmaPlan pl) {
+  constexpr bool PRO = IN_MODE != 0;
   constexpr int MT = 128;
   extern __shared__ __align__(128) uint8_t smem_raw[];
-  const int K = p.K, dil = p.dil, CO = p.CO, CI = p.CI;
+  const int K = p.K, dil = p.dil, CO = p.CO, CI = p.CI, NT = pl.NT, rows = pl.rows;
+  const int NS = pl.n_stages;
+  const int c8c = pl.ci_chunk >> 3;  // 16-byte K chunks per staged chunk
   const int co0 = blockIdx.y * NT;
-  const int c8n = ci_chunk >> 3;                       // 16-byte K chunks per staged chunk
-  uint4* Xs = reinterpret_cast<uint4*>(smem_raw);      // [2][c8n][rows]
-  uint4* Ws = Xs + 2 * c8n * rows;                     // [K][2][c8n][NT]
-  uint64_t* bar = reinterpret_cast<uint64_t*>(Ws + (size_t)K * 2 * c8n * NT);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+  uint4* Wres = reinterpret_cast<uint4*>(smem_raw);       // resident: [K][2][CI/8][NT]
+  uint4* stage0 = Wres + pl.wres_u4;                       // stage: X [2][c8c][rows] (+ W [K][2][c8c][NT])
+  float* prm = reinterpret_cast<float*>(stage0 + (size_t)NS * pl.stage_u4);
+  float* pro_s = prm;                // [4][CI]: scale, shift, alpha, 1/alpha of the current batch element
+  float* epi_s = prm + 4 * CI;       // [3][NT]: bias, alpha, 1/alpha
+  uint64_t* bars = reinterpret_cast<uint64_t*>(prm + pl.prm_floats);
+  uint64_t* x_full = bars;
+  uint64_t* x_empty = bars + kMaxStages;
+  uint64_t* acc_full = bars + 2 * kMaxStages;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int b = blockIdx.z;
-  const int t0 = blockIdx.x * MT;
+  const uint4* __restrict__ wsplit = reinterpret_cast<const uint4*>(p.w_split);
 
-  if (warp == 0) tmem_alloc(tmem_slot, tmem_cols);
+  if (warp == kMmaWarp) tmem_alloc(tmem_slot, (uint32_t)(2 * pl.acc_cols));
   if (tid == 0) {
-    mbar_init(bar, 1);
+    for (int i = 0; i < NS; ++i) {
+      mbar_init(&x_full[i], kProducerThreads);
+      mbar_init(&x_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], kEpilogueWarps * 32);
+    }
     fence_barrier_init();
+  }
+  for (int i = tid; i < NT; i += kThreads) {
+    const float al = p.out_alpha ? p.out_alpha[co0 + i] : 1.f;
+    epi_s[i] = p.bias ? p.bias[co0 + i] : 0.f;
+    epi_s[NT + i] = al;
+    epi_s[2 * NT + i] = 1.0f / al;
+  }
+  if (pl.resident) {
+    // all weights of this CTA's output channels, staged once: [K*2 blocks][CI/8][NT]
+    const int total = K * 2 * (CI >> 3) * NT;
+    for (int idx = tid; idx < total; idx += kThreads) {
+      const int row = idx / NT, n = idx - row * NT;  // row = blk*(CI/8) + c8
+      Wres[idx] = wsplit[(int64_t)row * CO + co0 + n];
+    }
+    fence_proxy_async_smem();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const float* __restrict__ xb = p.x + (int64_t)b * p.x_bs;
-  const uint4* __restrict__ wsplit = reinterpret_cast<const uint4*>(p.w_split);
-  const float* __restrict__ in_mask = (PRO && p.in_mask) ? p.in_mask + (int64_t)b * p.T : nullptr;
-  const float* __restrict__ in_scale = (PRO && p.in_scale) ? p.in_scale + (int64_t)b * CI : nullptr;
-  const float* __restrict__ in_shift = (PRO && p.in_shift) ? p.in_shift + (int64_t)b * CI : nullptr;
-  const float* __restrict__ in_alpha = (PRO && p.in_alpha) ? p.in_alpha : nullptr;
-  const int in_act = PRO ? p.in_act : STY_ACT_NONE;
-  // instruction descriptor: D=f32, A=B=bf16, both K-major, N = CO, M = 128
-  const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(MT >> 4) << 24);
+  const int64_t n_tiles = (int64_t)p.B * pl.tiles_per_b;
+  const int tile_begin = (int)((n_tiles * blockIdx.x) / gridDim.x);
+  const int tile_end = (int)((n_tiles * (blockIdx.x + 1)) / gridDim.x);
 
-  uint32_t phase = 0, accumulate = 0;
-  for (int c0 = 0; c0 < CI; c0 += ci_chunk) {
-    const int cc8 = min(ci_chunk, CI - c0) >> 3;
-    // ---- weights of this chunk: K*2 blocks of cc8*CO 16-byte vectors (pre-split bf16 hi/lo)
-    {
-      const int blk_elems = cc8 * NT;
-      const int total = K * 2 * blk_elems;
-      for (int idx = tid; idx < total; idx += MT) {
-        const int blk = idx / blk_elems, within = idx - blk * blk_elems;
-        const int c8l = within / NT, n = within - c8l * NT;
-        Ws[blk * (c8n * NT) + within] =
-            wsplit[((int64_t)blk * (CI >> 3) + (c0 >> 3) + c8l) * CO + co0 + n];
-      }
-    }
-    // ---- input rows: 8 channels x 1 time step per item -> two 16-byte vectors (hi, lo)
-    for (int c8 = 0; c8 < cc8; ++c8) {
-      const int cbase = c0 + c8 * 8;
-      float sc[8], sh[8], al[8], ia[8];
-      if constexpr (PRO) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          sc[j] = in_scale ? in_scale[cbase + j] : 1.f;
-          sh[j] = in_shift ? in_shift[cbase + j] : 0.f;
-          al[j] = in_alpha ? in_alpha[cbase + j] : 1.f;
-          ia[j] = 1.0f / al[j];
+  if (warp < kProducerWarps) {
+    // =========================== producers: stage input rows (and streamed weights)
+    uint32_t it = 0;
+    int cur_b = -1;
+    for (int tile = tile_begin; tile < tile_end; ++tile) {
+      const int b = tile / pl.tiles_per_b;
+      const int t0 = (tile - b * pl.tiles_per_b) * MT;
+      const float* __restrict__ xb = p.x + (int64_t)b * p.x_bs;
+      const float* __restrict__ in_mask = (PRO && p.in_mask) ? p.in_mask + (int64_t)b * p.T : nullptr;
+      if (PRO && b != cur_b) {  // per-channel prologue parameters of this batch element -> smem
+        asm volatile("bar.sync 2, %0;" ::"n"(kProducerThreads) : "memory");
+        for (int c = tid; c < CI; c += kProducerThreads) {
+          const float al = p.in_alpha ? p.in_alpha[c] : 1.f;
+          pro_s[c] = p.in_scale ? p.in_scale[(int64_t)b * CI + c] : 1.f;
+          pro_s[CI + c] = p.in_shift ? p.in_shift[(int64_t)b * CI + c] : 0.f;
+          pro_s[2 * CI + c] = al;
+          pro_s[3 * CI + c] = 1.0f / al;
         }
+        asm volatile("bar.sync 2, %0;" ::"n"(kProducerThreads) : "memory");
+        cur_b = b;
       }
-      for (int row = tid; row < rows; row += MT) {
-        const int t = t0 - p.pad + row;
-        const bool ok = (t >= 0) && (t < p.T);
-        float v[8];
+      for (int ch = 0; ch < pl.n_chunks; ++ch, ++it) {
+        const int c0 = ch * pl.ci_chunk;
+        const int cc8 = min(pl.ci_chunk, CI - c0) >> 3;
+        const int s = it % NS;
+        mbar_wait_sleep(&x_empty[s], ((it / NS) & 1) ^ 1);
+        uint4* Xs = stage0 + (size_t)s * pl.stage_u4;
+        if (!pl.resident) {
+          uint4* Ws = Xs + 2 * c8c * rows;  // [K*2 blocks][c8c][NT]
+          const int blk_elems = cc8 * NT;
+          const int total = K * 2 * blk_elems;
+#pragma unroll 4
+          for (int idx = tid; idx < total; idx += kProducerThreads) {
+            const int blk = idx / blk_elems, within = idx - blk * blk_elems;
+            const int c8l = within / NT, n = within - c8l * NT;
+            Ws[blk * (c8c * NT) + within] =
+                wsplit[((int64_t)blk * (CI >> 3) + (c0 >> 3) + c8l) * CO + co0 + n];
+          }
+        }
+        // items: (c8, row) pairs, row fastest; thread takes items tid, tid+256, ...
+        const int n_items = cc8 * rows;
+        int row = tid, c8 = 0;
+        while (row >= rows && c8 < cc8) { row -= rows; ++c8; }
+        for (int i0 = tid; i0 < n_items; i0 += kProducerThreads * kItemBatch) {
+          float v[kItemBatch][8];
+          int irow[kItemBatch], ic8[kItemBatch];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = ok ? xb[(int64_t)(cbase + j) * p.x_cs + t] : 0.f;
-        if constexpr (PRO) {
-          const float m = (ok && in_mask) ? in_mask[t] : 1.f;
+          for (int u = 0; u < kItemBatch; ++u) {
+            irow[u] = row;
+            ic8[u] = c8;
+            const int t = t0 - p.pad + row;
+            const bool ok = (c8 < cc8) && (t >= 0) && (t < p.T);
+            const float* __restrict__ src = xb + (int64_t)(c0 + c8 * 8) * p.x_cs + t;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float w = fmaf(v[j] * m, sc[j], sh[j]);
-            if (in_act == STY_ACT_SNAKE) {
-              w = fmaf(ia[j], sin_sq(al[j] * w), w);
-            } else if (in_act == STY_ACT_LEAKY02) {
-              w = w > 0.f ? w : 0.2f * w;
-            } else if (in_act != STY_ACT_NONE) {
-              w = act_apply(w, in_act);
+            for (int j = 0; j < 8; ++j) v[u][j] = ok ? src[(int64_t)j * p.x_cs] : 0.f;
+            row += kProducerThreads;
+            while (row >= rows && c8 < cc8) { row -= rows; ++c8; }
+          }
+#pragma unroll
+          for (int u = 0; u < kItemBatch; ++u) {
+            if (ic8[u] < cc8) {
+              const int t = t0 - p.pad + irow[u];
+              const bool ok = (t >= 0) && (t < p.T);
+              if constexpr (PRO) {
+                const int cbase = c0 + ic8[u] * 8;
+                const float m = (ok && in_mask) ? in_mask[t] : 1.f;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  float w = fmaf(v[u][j] * m, pro_s[cbase + j], pro_s[CI + cbase + j]);
+                  if constexpr (IN_MODE == 3) {
+                    w = fmaf(pro_s[3 * CI + cbase + j], sin_sq(pro_s[2 * CI + cbase + j] * w), w);
+                  } else if constexpr (IN_MODE == 2) {
+                    w = w > 0.f ? w : 0.2f * w;
+                  }
+                  v[u][j] = ok ? w : 0.f;
+                }
+              }
+              uint32_t h[4], l[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float a0 = v[u][2 * j], a1 = v[u][2 * j + 1];
+                h[j] = pack_bf16(a0, a1);
+                const float l0 = a0 - __uint_as_float(h[j] << 16);
+                const float l1 = a1 - __uint_as_float(h[j] & 0xffff0000u);
+                l[j] = pack_bf16(l0, l1);
+              }
+              Xs[(0 * c8c + ic8[u]) * rows + irow[u]] = make_uint4(h[0], h[1], h[2], h[3]);
+              Xs[(1 * c8c + ic8[u]) * rows + irow[u]] = make_uint4(l[0], l[1], l[2], l[3]);
             }
-            v[j] = ok ? w : 0.f;
           }
         }
-        float hi[8], lo[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          hi[j] = __bfloat162float(__float2bfloat16_rn(v[j]));
-          lo[j] = v[j] - hi[j];
-        }
-        uint4 h4, l4;
-        h4.x = pack_bf16(hi[0], hi[1]); h4.y = pack_bf16(hi[2], hi[3]);
-        h4.z = pack_bf16(hi[4], hi[5]); h4.w = pack_bf16(hi[6], hi[7]);
-        l4.x = pack_bf16(lo[0], lo[1]); l4.y = pack_bf16(lo[2], lo[3]);
-        l4.z = pack_bf16(lo[4], lo[5]); l4.w = pack_bf16(lo[6], lo[7]);
-        Xs[(0 * c8n + c8) * rows + row] = h4;
-        Xs[(1 * c8n + c8) * rows + row] = l4;
+        fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core proxy
+        mbar_arrive(&x_full[s]);
       }
     }
-    fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
-    __syncthreads();
-    if (tid == 0) {
+  } else if (warp == kMmaWarp) {
+    // =========================== MMA issuer (one elected lane)
+    // instruction descriptor: D=f32, A=B=bf16, both K-major, N = NT, M = 128
+    const uint32_t idesc =
+        (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(MT >> 4) << 24);
+    const int wc8 = pl.resident ? (CI >> 3) : c8c;  // K-chunk rows per (tap, split) weight block
+    uint32_t it = 0, j = 0;
+    for (int tile = tile_begin; tile < tile_end; ++tile, ++j) {
+      const uint32_t a = j & 1;
+      mbar_wait(&acc_empty[a], ((j >> 1) & 1) ^ 1);
       tc_fence_after();
-      const uint32_t xs_addr = smem_u32(Xs), ws_addr = smem_u32(Ws);
-      const int kblocks = cc8 >> 1;  // MMA K = 16 bf16 = two 16-byte chunks
-      // (x split, w split): hi*hi, lo*hi, hi*lo
+      const uint32_t d_tmem = tmem_base + a * (uint32_t)pl.acc_cols;
+      for (int ch = 0; ch < pl.n_chunks; ++ch, ++it) {
+        const int c0 = ch * pl.ci_chunk;
+        const int cc8 = min(pl.ci_chunk, CI - c0) >> 3;
+        const int s = it % NS;
+        mbar_wait(&x_full[s], (it / NS) & 1);
+        tc_fence_after();
+        if (lane == 0) {
+          // single issuing thread; only the low descriptor word (start address) changes per MMA
+          const uint4* Xs = stage0 + (size_t)s * pl.stage_u4;
+          const uint32_t ws_addr = pl.resident ? smem_u32(Wres) : smem_u32(Xs + 2 * c8c * rows);
+          const uint64_t a_d = make_desc(smem_u32(Xs), (uint32_t)rows, 8u);
+          const uint64_t b_d = make_desc(ws_addr, (uint32_t)NT, 8u);
+          const uint32_t a_hi32 = (uint32_t)(a_d >> 32), b_hi32 = (uint32_t)(b_d >> 32);
+          uint32_t a_t = (uint32_t)a_d, b_t = (uint32_t)b_d;  // low words: (tap 0, kb 0, hi split)
+          const uint32_t a_lo_off = (uint32_t)(c8c * rows);    // 16-byte units to the lo-split copy
+          const uint32_t b_lo_off = (uint32_t)(wc8 * NT);
+          const int kblocks = cc8 >> 1;                         // MMA K = 16 bf16 = two 16-byte chunks
+          const uint32_t a_kstep = 2 * rows, b_kstep = 2 * NT;
+          const uint32_t b_tstep = 2 * wc8 * NT;                // per tap (hi and lo blocks)
+          uint32_t accumulate = ch > 0 ? 1u : 0u;
 #pragma unroll 1
-      for (int combo = 0; combo < 3; ++combo) {
-        const int sx = (combo == 1) ? 1 : 0, sw = (combo == 2) ? 1 : 0;
+          for (int tap = 0; tap < K; ++tap, a_t += (uint32_t)dil, b_t += b_tstep) {
+            uint32_t ak = a_t, bk = b_t;
+#pragma unroll 2
+            for (int kb = 0; kb < kblocks; ++kb, ak += a_kstep, bk += b_kstep) {
+              umma_bf16_w(d_tmem, ak, a_hi32, bk, b_hi32, idesc, accumulate);             // hi * hi
+              umma_bf16_w(d_tmem, ak + a_lo_off, a_hi32, bk, b_hi32, idesc, 1u);          // lo * hi
+              umma_bf16_w(d_tmem, ak, a_hi32, bk + b_lo_off, b_hi32, idesc, 1u);          // hi * lo
+              accumulate = 1;
+            }
+          }
+          umma_commit(&x_empty[s]);                               // stage free once read
+          if (ch == pl.n_chunks - 1) umma_commit(&acc_full[a]);  // accumulator complete
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // =========================== epilogue: thread owns accumulator row (TMEM lane) q*32+lane
+    // and the 16-column chunks c with (c & 1) == half
+    const int ew = warp - kEpilogueWarp0;
+    const int q = warp & 3;
+    const int half = ew >> 2;
+    const int s = p.shuffle > 1 ? p.shuffle : 1;
+    const int n_chunks16 = NT >> 4;
+    float ssq_acc[8];  // column (16*c + (lane & 15)) sums of this thread's chunks c = half, half+2, ...
+#pragma unroll
+    for (int i = 0; i < 8; ++i) ssq_acc[i] = 0.f;
+    uint32_t j = 0;
+    int ssq_b = -1;
+    auto flush_ssq = [&](int bb) {
+      if (lane < 16) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int c = half + 2 * i;
+          if (c < n_chunks16) atomicAdd(p.out_sumsq + (int64_t)bb * CO + co0 + c * 16 + lane, ssq_acc[i]);
+          ssq_acc[i] = 0.f;
+        }
+      }
+    };
+    for (int tile = tile_begin; tile < tile_end; ++tile, ++j) {
+      const int b = tile / pl.tiles_per_b;
+      const int t0 = (tile - b * pl.tiles_per_b) * MT;
+      const uint32_t a = j & 1;
+      if (p.out_sumsq && ssq_b != b) {
+        if (ssq_b >= 0) flush_ssq(ssq_b);
+        ssq_b = b;
+      }
+      mbar_wait_sleep(&acc_full[a], (j >> 1) & 1);
+      tc_fence_after();
+      const int t = t0 + q * 32 + lane;
+      const bool t_ok = t < p.T;
+      const float* __restrict__ out_mask = p.out_mask ? p.out_mask + (int64_t)b * p.T : nullptr;
+      float* __restrict__ yb = p.y + (int64_t)b * p.y_bs;
+      const float* __restrict__ rb = p.res ? p.res + (int64_t)b * p.r_bs : nullptr;
+      const float om = ((out_mask && t_ok) ? out_mask[t] : 1.f) * p.out_scale;
+      const uint32_t acc_addr = tmem_base + a * (uint32_t)pl.acc_cols + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-        for (int tap = 0; tap < K; ++tap) {
-#pragma unroll 1
-          for (int kb = 0; kb < kblocks; ++kb) {
-            const uint32_t a_addr = xs_addr + (uint32_t)(((sx * c8n + 2 * kb) * rows + tap * dil) * 16);
-            const uint32_t b_addr = ws_addr + (uint32_t)((((tap * 2 + sw) * c8n + 2 * kb) * NT) * 16);
-            umma_bf16(tmem_base, make_desc(a_addr, (uint32_t)rows, 8u), make_desc(b_addr, (uint32_t)NT, 8u),
-                      idesc, accumulate);
-            accumulate = 1;
+      for (int ci = 0; ci < 8; ++ci) {
+        const int c = half + 2 * ci;
+        if (c >= n_chunks16) break;
+        const int n0 = c * 16;
+        float r[16], rv[16];
+        // residual rows first: all 16 loads in flight before any store (res may alias y)
+        if (rb && t_ok) {
+#pragma unroll
+          for (int jj = 0; jj < 16; ++jj) {
+            const int co = co0 + n0 + jj;
+            if (s == 1) {
+              rv[jj] = rb[(int64_t)co * p.r_cs + t];
+            } else {
+              const int c_out = co / s, r_out = co - c_out * s;
+              rv[jj] = rb[(int64_t)c_out * p.r_cs + (int64_t)t * s + r_out];
+            }
+          }
+        } else {
+#pragma unroll
+          for (int jj = 0; jj < 16; ++jj) rv[jj] = 0.f;
+        }
+        tmem_ld16(acc_addr + (uint32_t)n0, r);
+#pragma unroll
+        for (int jj = 0; jj < 16; ++jj) {
+          const int n = n0 + jj;
+          float v = r[jj] + epi_s[n];
+          if constexpr (OUT_MODE == 1) {
+            v = fmaf(epi_s[2 * NT + n], sin_sq(epi_s[NT + n] * v), v);
+          } else if constexpr (OUT_MODE == 2) {
+            v = fmaxf(v, 0.f);
+          } else if constexpr (OUT_MODE == 3) {
+            v = v / (1.0f + __expf(-v));
+          }
+          v = fmaf(p.res_scale, rv[jj], v * om);
+          if (!t_ok) v = 0.f;
+          r[jj] = v;
+        }
+        if (t_ok) {
+          if (s == 1) {
+            float* __restrict__ yp = yb + (int64_t)(co0 + n0) * p.y_cs + t;
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj) yp[(int64_t)jj * p.y_cs] = r[jj];
+          } else {
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj) {
+              const int co = co0 + n0 + jj;
+              const int c_out = co / s, r_out = co - c_out * s;
+              yb[(int64_t)c_out * p.y_cs + (int64_t)t * s + r_out] = r[jj];
+            }
           }
         }
-      }
-      umma_commit(bar);  // arrives on `bar` when every MMA above has finished reading smem
-    }
-    mbar_wait(bar, phase);
-    phase ^= 1;
-    tc_fence_after();
-    accumulate = 1;
-  }
-
-  // ---- epilogue: thread tid owns output time step t0 + tid (TMEM lane tid)
-  const int t = t0 + tid;
-  const bool t_ok = t < p.T;
-  const float* __restrict__ out_mask = p.out_mask ? p.out_mask + (int64_t)b * p.T : nullptr;
-  float* __restrict__ yb = p.y + (int64_t)b * p.y_bs;
-  const float* __restrict__ rb = p.res ? p.res + (int64_t)b * p.r_bs : nullptr;
-  const int s = p.shuffle > 1 ? p.shuffle : 1;
-  const int out_act = p.out_act;
-  const float om = ((out_mask && t_ok) ? out_mask[t] : 1.f) * p.out_scale;
-  for (int n0 = 0; n0 < NT; n0 += 32) {
-    float r[32];
-    tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)n0, r);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const int co = co0 + n0 + j;
-      if (n0 + j < NT) {  // NT % 16 == 0: the tail chunk may be half used
-        const float bias = p.bias ? p.bias[co] : 0.f;
-        float v = r[j] + bias;
-        if (out_act == STY_ACT_SNAKE) {
-          const float al = p.out_alpha[co];
-          v = fmaf(1.0f / al, sin_sq(al * v), v);
-        } else if (out_act != STY_ACT_NONE) {
-          v = act_apply(v, out_act);
-        }
-        v *= om;
-        float sq = 0.f;
-        if (t_ok) {
-          const int c_out = co / s, r_out = co - c_out * s;
-          const int64_t off = (int64_t)t * s + r_out;
-          if (rb) v = fmaf(p.res_scale, rb[(int64_t)c_out * p.r_cs + off], v);
-          yb[(int64_t)c_out * p.y_cs + off] = v;
-          sq = v * v;
-        }
+        for (int jj = 0; jj < 16; ++jj) r[jj] *= r[jj];
         if (p.out_sumsq) {
-          sq = warp_sum(sq);
-          if (lane == 0) atomicAdd(p.out_sumsq + (int64_t)b * CO + co, sq);
+          const float colsum = warp_colsum16(r, lane);
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (i == ci) ssq_acc[i] += colsum;
         }
       }
+      tc_fence_before();
+      mbar_arrive(&acc_empty[a]);
     }
+    if (p.out_sumsq && ssq_b >= 0) flush_ssq(ssq_b);
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_base, tmem_cols);
+  if (warp == kMmaWarp) tmem_dealloc(tmem_base, (uint32_t)(2 * pl.acc_cols));
 }
 
-// smem bytes for a chunk of `chunk` input channels
-static size_t umma_smem_bytes(int chunk, int rows, int K, int NT) {
-  return (size_t)chunk * rows * 4 + (size_t)K * chunk * NT * 4 + 16;
+// ------------------------------------------------------------------ host side
+static const size_t kSmemBudget = 224 * 1024;
+static const size_t kSmemBars = 256;  // barriers + tmem slot
+
+static bool make_plan(const sty_conv1d_args& a, UmmaPlan& pl) {
+  if (a.CI % 16 != 0 || a.CO % 16 != 0 || a.CO < 16 || a.CI > 4096) return false;
+  pl.rows = 128 + (a.K - 1) * a.dil;
+  if (pl.rows >= 16384) return false;
+  pl.tiles_per_b = cdiv(a.T, 128);
+  // output-channel tile candidates: CO itself if <= 128, else multiple-of-16 divisors, largest first
+  // (each epilogue thread keeps GRN partial sums for at most 8 of its 16-column chunks => NT <= 256)
+  for (int nt = a.CO <= 256 ? a.CO : 256; nt >= 16; nt -= 16) {
+    if (a.CO % nt != 0) continue;
+    if (a.CO / nt > 65535) break;
+    pl.NT = nt;
+    pl.acc_cols = 32;
+    while (pl.acc_cols < nt) pl.acc_cols <<= 1;
+    pl.prm_floats = 4 * a.CI + 3 * nt;
+    pl.prm_floats = (pl.prm_floats + 3) & ~3;
+    const size_t misc = kSmemBars + (size_t)pl.prm_floats * 4;
+    const size_t w_all = (size_t)a.K * a.CI * nt * 4;
+    const size_t x_all = (size_t)a.CI * pl.rows * 4;
+    if (w_all + 2 * x_all + misc <= kSmemBudget) {  // weights resident, >= 2 input stages
+      pl.resident = 1;
+      pl.ci_chunk = a.CI;
+      pl.n_chunks = 1;
+      pl.wres_u4 = (int)(w_all / 16);
+      pl.stage_u4 = (int)(x_all / 16);
+      size_t ns = (kSmemBudget - misc - w_all) / x_all;
+      pl.n_stages = (int)(ns > kMaxStages ? kMaxStages : ns);
+      return true;
+    }
+    // stream weights with the input rows, per chunk of input channels
+    for (int c = a.CI - a.CI % 16; c >= 16; c -= 16) {
+      const size_t st = (size_t)c * ((size_t)pl.rows * 4 + (size_t)a.K * nt * 4);
+      if (2 * st + misc <= kSmemBudget) {
+        pl.resident = 0;
+        pl.ci_chunk = c;
+        pl.n_chunks = cdiv(a.CI, c);
+        pl.wres_u4 = 0;
+        pl.stage_u4 = (int)(st / 16);
+        size_t ns = (kSmemBudget - misc) / st;
+        pl.n_stages = (int)(ns > kMaxStages ? kMaxStages : ns);
+        return true;
+      }
+    }
+  }
+  return false;
 }
 
-// output-channel tile: all of CO when <= 256, else the largest multiple-of-16 divisor <= 256
-static int umma_co_tile(int CO) {
-  if (CO <= 256) return CO;
-  for (int n = 256; n >= 16; n -= 16)
-    if (CO % n == 0) return n;
-  return 0;
+static int umma_in_mode(const sty_conv1d_args& a) {
+  if (a.in_act == STY_ACT_SNAKE) return 3;
+  if (a.in_act == STY_ACT_LEAKY02) return 2;
+  if (a.in_act != STY_ACT_NONE) return -1;
+  return (a.in_scale || a.in_shift || a.in_mask) ? 1 : 0;
+}
+static int umma_out_mode(const sty_conv1d_args& a) {
+  switch (a.out_act) {
+    case STY_ACT_NONE: return 0;
+    case STY_ACT_SNAKE: return 1;
+    case STY_ACT_RELU: return 2;
+    case STY_ACT_SWISH: return 3;
+    default: return -1;
+  }
 }
 
 bool conv1d_umma_eligible(const sty_conv1d_args& a) {
-  if (!a.w_split) return false;
-  if (a.CI % 16 != 0 || a.CO % 16 != 0 || a.CO < 16) return false;
-  if (a.w_bs != 0 || a.T < 128) return false;
-  const int nt = umma_co_tile(a.CO);
-  if (nt < 16 || a.CO / nt > 65535) return false;
-  const int rows = 128 + (a.K - 1) * a.dil;
-  return umma_smem_bytes(16, rows, a.K, nt) <= 200 * 1024 && rows < 16384;
+  if (!a.w_split || a.w_bs != 0 || a.T < 128) return false;
+  if (umma_in_mode(a) < 0 || umma_out_mode(a) < 0) return false;
+  UmmaPlan pl;
+  return make_plan(a, pl);
 }
 
 int conv1d_umma_launch(const sty_conv1d_args& a, cudaStream_t st) {
-  const int rows = 128 + (a.K - 1) * a.dil;
-  const int nt = umma_co_tile(a.CO);
-  // largest chunk (multiple of 16) whose footprint allows two CTAs per SM, else one
-  int chunk = 16;
-  for (int c = a.CI - a.CI % 16; c >= 16; c -= 16) {
-    if (umma_smem_bytes(c, rows, a.K, nt) <= 100 * 1024) {
-      chunk = c;
-      break;
-    }
+  UmmaPlan pl;
+  if (!make_plan(a, pl)) {
+    set_error("conv1d_umma: shape not supported");
+    return STY_ERR_BAD_ARG;
   }
-  const size_t smem = umma_smem_bytes(chunk, rows, a.K, nt);
-  uint32_t cols = 32;
-  while ((int)cols < nt) cols <<= 1;
-  const bool pro = a.in_scale || a.in_shift || a.in_mask || a.in_act != STY_ACT_NONE;
-  auto kern = pro ? conv1d_umma_kernel<true> : conv1d_umma_kernel<false>;
-  if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  dim3 grid(cdiv(a.T, 128), a.CO / nt, a.B);
-  kern<<<grid, 128, smem, st>>>(a, chunk, rows, nt, cols);
+  static int sms = 0;
+  if (sms <= 0) {
+    sms = sty_device_sm_count();
+    if (sms <= 0) sms = 148;
+  }
+  const size_t smem = (size_t)pl.wres_u4 * 16 + (size_t)pl.n_stages * pl.stage_u4 * 16 +
+                      (size_t)pl.prm_floats * 4 + kSmemBars;
+  using KernPtr = void (*)(const sty_conv1d_args, const UmmaPlan);
+  static const KernPtr table[4][4] = {
+      {conv1d_umma_kernel<0, 0>, conv1d_umma_kernel<0, 1>, conv1d_umma_kernel<0, 2>, conv1d_umma_kernel<0, 3>},
+      {conv1d_umma_kernel<1, 0>, conv1d_umma_kernel<1, 1>, conv1d_umma_kernel<1, 2>, conv1d_umma_kernel<1, 3>},
+      {conv1d_umma_kernel<2, 0>, conv1d_umma_kernel<2, 1>, conv1d_umma_kernel<2, 2>, conv1d_umma_kernel<2, 3>},
+      {conv1d_umma_kernel<3, 0>, conv1d_umma_kernel<3, 1>, conv1d_umma_kernel<3, 2>, conv1d_umma_kernel<3, 3>}};
+  KernPtr kern = table[umma_in_mode(a)][umma_out_mode(a)];
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const int64_t n_tiles = (int64_t)a.B * pl.tiles_per_b;
+  const int n_co = a.CO / pl.NT;
+  int gx = (int)(n_tiles < sms ? n_tiles : sms);
+  // several output-channel tiles: split the SMs between them (at least one CTA each)
+  if (n_co > 1) {
+    gx = sms / n_co;
+    if (gx < 1) gx = 1;
+    if (gx > n_tiles) gx = (int)n_tiles;
+  }
+  dim3 grid(gx, n_co, 1);
+  kern<<<grid, kThreads, smem, st>>>(a, pl);
   STY_CHECK_LAUNCH("conv1d_umma");
   return STY_OK;
 }
