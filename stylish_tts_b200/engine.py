@@ -22,7 +22,7 @@ from ._lib import ACT_LEAKY02, ACT_NONE, ACT_RELU, ACT_SNAKE, ACT_SWISH, ConvArg
 INV_SQRT2 = 1.0 / math.sqrt(2.0)
 # tensor-core (tcgen05, bf16x3) path for eligible convs; STYLISH_B200_UMMA=0 forces fp32 FMA
 USE_UMMA = os.environ.get("STYLISH_B200_UMMA", "1") != "0"
-UMMA_MIN_T = 512
+UMMA_MIN_T = 128
 
 
 def split_bf16(w_oik: torch.Tensor) -> torch.Tensor:
@@ -56,7 +56,7 @@ class ConvW:
 
 def conv1d(x, cw: ConvW, *, dil=1, out=None, res=None, in_scale=None, in_shift=None,
            in_alpha=None, in_act=ACT_NONE, in_mask=None, out_mask=None, out_act=ACT_NONE,
-           out_alpha=None, out_sumsq=None, shuffle=0, out_scale=1.0, res_scale=1.0):
+           out_alpha=None, out_sumsq=None, shuffle=0, out_scale=1.0, res_scale=1.0, umma=True):
     B, CI, T = x.shape
     assert CI == cw.CI, (CI, cw.CI)
     x_bs, x_cs = L._bct(x, "x")
@@ -81,7 +81,7 @@ def conv1d(x, cw: ConvW, *, dil=1, out=None, res=None, in_scale=None, in_shift=N
     a.pad = (cw.K - 1) * dil // 2
     a.in_act, a.out_act, a.shuffle = in_act, out_act, shuffle
     a.out_scale, a.res_scale = out_scale, res_scale
-    if USE_UMMA and cw.split is not None and T >= UMMA_MIN_T:
+    if umma and USE_UMMA and cw.split is not None and T >= UMMA_MIN_T:
         a.w_split = cw.split.data_ptr()
     L.call("sty_conv1d_fwd", C.byref(a), L.stream_ptr())
     return out
@@ -361,11 +361,13 @@ class SpeechEngine:
     def _decoder_block(self, P, blk, x, h, out):
         J = P.fc_rows
         sc1, sh1 = instnorm_affine(x, self._gb(P, h, blk["n1"]), J)
-        t1 = conv1d(x, blk["c1"], in_scale=sc1, in_shift=sh1, in_act=ACT_LEAKY02)
+        # fp32 FMA path: the F0 side channel is in Hz (|x| ~ 1e2 next to O(1) features), so the
+        # bf16x3 operand split would cost ~1e-4 relative here (measured); the decoder is ~2 % of FLOPs
+        t1 = conv1d(x, blk["c1"], in_scale=sc1, in_shift=sh1, in_act=ACT_LEAKY02, umma=False)
         sc2, sh2 = instnorm_affine(t1, self._gb(P, h, blk["n2"]), J)
-        short = conv1d(x, blk["sc"]) if blk["sc"] is not None else x
+        short = conv1d(x, blk["sc"], umma=False) if blk["sc"] is not None else x
         return conv1d(t1, blk["c2"], in_scale=sc2, in_shift=sh2, in_act=ACT_LEAKY02, res=short,
-                      out_scale=INV_SQRT2, res_scale=INV_SQRT2, out=out)
+                      out_scale=INV_SQRT2, res_scale=INV_SQRT2, out=out, umma=False)
 
     def decoder(self, P: Packed, mu, alignment, pitch, energy, voiced, h, taps=None):
         B, Cm, T = mu.shape
@@ -387,7 +389,7 @@ class SpeechEngine:
                 c0 = Cm + res_dim + j
                 dwconv1d(s3, w, b, K=3, pad_left=1, out=cat[:, c0:c0 + 1])
         for cat in (cat_a, cat_b):
-            conv1d(asr, P.asr_res, out=cat[:, Cm:Cm + res_dim])
+            conv1d(asr, P.asr_res, out=cat[:, Cm:Cm + res_dim], umma=False)
         x = self._decoder_block(P, P.dec_encode, cat0, h, cat_a[:, :Cm])
         if taps is not None:
             taps["dec_encode"] = x.clone()

@@ -7,7 +7,9 @@
   against the fp64 oracle, and injected (from the oracle) for everything downstream;
 * size-independent properties at the full BASELINE config-2 batch (B=16).
 
-Tolerance: the north-star bound is 1e-3 relative (fp32); we assert 2e-4 on audio.
+Tolerance: the north-star bound is 1e-3 relative (fp32).  The vocoder / encoder convs run on
+the tensor cores with a bf16 hi/lo operand split ("bf16x3", ~2^-17 relative per operand), so we
+assert 5e-4 on the audio and 2e-4 on the intermediate taps (observed 1e-4 / 3e-5).
 """
 import pytest
 import torch
@@ -19,8 +21,8 @@ from tests import util
 from tests.util import rel_l2
 
 pytestmark = pytest.mark.gpu
-AUDIO_TOL = 2e-4
-TAP_TOL = 1e-4
+AUDIO_TOL = 5e-4
+TAP_TOL = 2e-4
 
 
 def dev():
@@ -157,10 +159,11 @@ def test_full_batch_properties():
         one = {k: (v[b:b + 1] if torch.is_tensor(v) else {kk: vv[b:b + 1] for kk, vv in v.items()})
                for k, v in inp.items()}
         alone = run_gpu(sp, one)
-        assert rel_l2(full[b:b + 1], alone) < 2e-5, b
+        # not bit-exact: GRN statistics are accumulated with atomics (order varies with the grid)
+        assert rel_l2(full[b:b + 1], alone) < 1e-4, b
     inp2 = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in inp.items()}
     for b in range(16):
         n = int(inp["text_lengths"][b])
         inp2["texts"][b, n:] = 77  # garbage in the padded region
     again = run_gpu(sp, inp2)
-    assert rel_l2(again, full) < 2e-5
+    assert rel_l2(again, full) < 1e-4
