@@ -46,7 +46,8 @@ typedef void* sty_stream_t; /* cudaStream_t */
 #define STY_ACT_RELU 1
 #define STY_ACT_LEAKY02 2 /* LeakyReLU(0.2)                     ada_norm.py:148 */
 #define STY_ACT_SNAKE 3   /* x + sin^2(a x)/a, a per channel    ada_norm.py:114, conv_next.py:77 */
-#define STY_ACT_SWISH 4   /* x * sigmoid(x)                      conformer.py:33 */
+#define STY_ACT_SWISH 4   /* x * sigmoid(x)                      conformer.py:33, SiLU duration_predictor.py:52 */
+#define STY_ACT_GELU 5    /* exact (erf) GELU                    conv_next.py:115 */
 
 STY_API int sty_version(void);
 STY_API const char* sty_last_error(void);
@@ -177,11 +178,50 @@ STY_API int sty_attention_fwd(const float* q, const float* k, const float* v, in
                       const float* rope_sin, int d_rot, int B, int H, int D, int T, float scale,
                       sty_stream_t stream);
 
+/* ---- multi-head attention core, any head size (D % 4 == 0, D <= 256) -------------------
+ * Same semantics as sty_attention_fwd; q, k, v each have their own batch stride so that the
+ * query and the key/value projections may come from different tensors
+ * (DurationPredictor.compute_cross duration_predictor.py:58-67; ProsodyEncoder 2 heads x 160,
+ * prosody_encoder.py:63-81). */
+STY_API int sty_attention_generic_fwd(const float* q, int64_t q_bs, const float* k, const float* v,
+                                      int64_t kv_bs, float* o, int64_t o_bs, const int64_t* lengths,
+                                      const float* rope_cos, const float* rope_sin, int d_rot, int B,
+                                      int H, int D, int T, float scale, sty_stream_t stream);
+
+/* ---- duration head ------------------------------------------------------------------------
+ * x: (B, NC, T) raw class scores.  out[b,t,:] = -|cumsum([x0, |x1|, |x2|, ...])| * (t < len[b])
+ * as (B, T, NC).   duration_predictor.py:82-86 */
+STY_API int sty_duration_head_fwd(const float* x, const int64_t* lengths, float* out, int B, int NC,
+                                  int T, sty_stream_t stream);
+
+/* ---- soft durations ----------------------------------------------------------------------------
+ * pred (B,T,NC) -> dur[b,t] = sum_c softmax(pred)[c]*table[c] / (sum_c softmax + 1e-9) * (t < len[b]);
+ * also total[0] = max_b round(sum_t dur[b,t]) (int32) — the frame count of the alignment.
+ * DurationProcessor.prediction_to_duration / class_to_dur_soft utils.py:726-750,759 */
+STY_API int sty_soft_duration_fwd(const float* pred, const int64_t* lengths, const float* table,
+                                  float* dur, int32_t* total, int B, int T, int NC,
+                                  sty_stream_t stream);
+
+/* ---- soft alignment -------------------------------------------------------------------------------
+ * duration (B,T) -> alignment (B,T,F): parabola window 1-(2x/(d+6))^2 around each token's centre,
+ * kept on (lower-3, upper+3), clamped at 0, softmax over the TEXT axis (zeros outside the window
+ * still receive weight e^0 — literal).  DurationProcessor.duration_to_alignment utils.py:752-791 */
+STY_API int sty_alignment_fwd(const float* duration, float* alignment, int B, int T, int F,
+                              sty_stream_t stream);
+
 /* ---- batched matrix product ---------------------------------------------------
  * C[b] (M,N) = A[b] (M,K) @ Bm[b] (K,N), all row-major, batch strides in elements.
  * `text_encoding @ alignment` speech_predictor.py:60. */
 STY_API int sty_bmm_fwd(const float* A, int64_t a_bs, const float* Bm, int64_t b_bs, float* C,
                 int64_t c_bs, int B, int M, int N, int K, sty_stream_t stream);
+
+/* ---- masked scale / row broadcast (glue of the predictors) ---------------------------------
+ * scale_mask:     out[b,c,t] = x[b,c,t] * mask[b,t] * scale      (`x * x_mask`, prosody_encoder.py:70,79)
+ * broadcast_rows: out[b,s,t] = v[b,s]  with batch stride out_bs  (style.unsqueeze(2).expand, :67) */
+STY_API int sty_scale_mask_fwd(const float* x, const float* mask, float* out, int B, int C, int T,
+                               float scale, sty_stream_t stream);
+STY_API int sty_broadcast_rows_fwd(const float* v, float* out, int64_t out_bs, int B, int S, int T,
+                                   sty_stream_t stream);
 
 /* ---- gated linear unit over channels -------------------------------------------
  * y[b,c,t] = x[b,c,t] * sigmoid(x[b,c+C,t])   conformer.py:37-44 */

@@ -505,3 +505,114 @@ def duration_to_alignment(duration, multiplier=1):
 
 def to_dtype(sd: SD, dtype) -> SD:
     return {k: (v.to(dtype) if v.is_floating_point() else v) for k, v in sd.items()}
+
+
+# ---------------------------------------------------------------------------
+# duration / pitch-energy predictors and the inference graph (E7-E9, A1)
+# ---------------------------------------------------------------------------
+def adaptive_convnext_block(sd: SD, prefix: str, x, s):
+    """models/conv_next.py:125-141 — AdaptiveConvNeXtBlock (eval: DropPath off), GELU(erf)."""
+    C = x.shape[1]
+    r = x
+    x = conv1d(sd, prefix + ".dwconv", x, padding=3, groups=C)
+    x = x.transpose(1, 2)
+    x = adaln(sd, prefix + ".norm", x, s, 1e-6)
+    x = linear(sd, prefix + ".pwconv1", x)
+    x = F.gelu(x)
+    x = grn(x, sd[prefix + ".grn.gamma"], sd[prefix + ".grn.beta"])
+    x = linear(sd, prefix + ".pwconv2", x)
+    return r + x.transpose(1, 2)
+
+
+def mha_qc(sd: SD, prefix: str, x, c, n_heads, attn_mask):
+    """MultiHeadAttention.forward with distinct query / context inputs (text_encoder.py:214-222)."""
+    return mha(sd, prefix, x, c, n_heads, attn_mask)
+
+
+def duration_predictor(sd: SD, texts, text_lengths, style, *, n_layer=3, taps=None):
+    """models/duration_predictor.py:58-87 -> (B,T,classes) monotone logits."""
+    enc, _, _ = text_encoder(sd, "text_encoder", texts, text_lengths)
+    enc = enc.transpose(1, 2)  # the reference's "b t c -> b c t" rearrange of a (B,C,T) tensor
+    mask = sequence_mask(text_lengths, enc.size(1)).unsqueeze(1).to(enc.dtype)
+    q = adaln(sd, "query_norm", enc, style, 1e-5).transpose(1, 2)
+    k = adaln(sd, "key_norm", enc, style, 1e-5).transpose(1, 2)
+    am = mask.unsqueeze(2) * mask.unsqueeze(-1)
+    att = mha(sd, "cross_attention", q, k, 8, am)
+    C = att.shape[1]
+    att = conv1d(sd, "cross_post.0", att, padding=2, groups=C)
+    att = F.silu(att)
+    att = conv1d(sd, "cross_post.2", att)
+    pros = (att + enc.transpose(1, 2)) / math.sqrt(2.0)
+    if taps is not None:
+        taps["dur_cross"] = pros
+    for i in range(n_layer):
+        pros = adaptive_convnext_block(sd, f"conv_next.{i}", pros, style)
+        pros = pros * mask
+    pros = pros.transpose(1, 2)
+    d = linear(sd, "duration_proj.linear_layer", pros)
+    d = torch.cat([d[:, :, :1], torch.abs(d)[:, :, 1:]], dim=2)
+    d = -torch.abs(torch.cumsum(d, dim=2))
+    return d * mask.transpose(1, 2)
+
+
+def prosody_encoder(sd: SD, prefix: str, x, style, lengths, *, n_layers=3, n_heads=2):
+    """models/prosody_encoder.py:63-81 -> (B,T,d_model+style)."""
+    mask = sequence_mask(lengths, x.size(2)).unsqueeze(1).to(x.dtype)
+    am = mask.unsqueeze(2) * mask.unsqueeze(-1)
+    st = style.unsqueeze(2).expand(x.shape[0], -1, x.shape[2])
+    x = torch.cat([x, st], dim=1)
+    for i in range(n_layers):
+        x = x * mask
+        y = mha(sd, f"{prefix}.attn_layers.{i}", x, x, n_heads, am)
+        x = adaln(sd, f"{prefix}.norm_layers_1.{i}", (x + y).transpose(1, 2), style, 1e-5).transpose(1, 2)
+        y = conv1d(sd, f"{prefix}.ffn_layers.{i}.conv_1", x * mask)
+        y = torch.relu(y)
+        y = conv1d(sd, f"{prefix}.ffn_layers.{i}.conv_2", y * mask) * mask
+        x = adaln(sd, f"{prefix}.norm_layers_2.{i}", (x + y).transpose(1, 2), style, 1e-5).transpose(1, 2)
+        x = conv1d(sd, f"{prefix}.proj_layers.{i}", x)
+        x = torch.cat([x, st], dim=1)
+    x = x * mask
+    return x.transpose(-1, -2)
+
+
+def pitch_energy_predictor(sd: SD, texts, text_lengths, alignment, style, taps=None):
+    """models/pitch_energy_predictor.py:62-82 -> (pitch (B,F), energy (B,F))."""
+    enc, _, _ = text_encoder(sd, "text_encoder", texts, text_lengths)
+    pros = prosody_encoder(sd, "prosody_encoder", enc, style, text_lengths)
+    if taps is not None:
+        taps["prosody"] = pros
+    x = pros.transpose(1, 2) @ alignment
+    f0 = x
+    for i in range(4):
+        f0 = decoder_block(sd, f"F0.{i}", f0, style)
+    f0 = conv1d(sd, "F0_proj", f0)
+    n = x
+    for i in range(4):
+        n = decoder_block(sd, f"N.{i}", n, style)
+    n = conv1d(sd, "N_proj", n)
+    return f0.squeeze(1), n.squeeze(1)
+
+
+CLASS_TO_DUR = [1, 2, 3, 4, 5, 6, 7, 9, 12, 15, 18, 22, 27, 32, 38, 46]
+
+
+def prediction_to_duration(pred, text_lengths):
+    """DurationProcessor.prediction_to_duration / class_to_dur_soft utils.py:726-750."""
+    table = torch.tensor(CLASS_TO_DUR, dtype=pred.dtype)
+    p = torch.softmax(pred, dim=-1)
+    soft = (p * table).sum(dim=-1) / (p.sum(dim=-1) + 1e-9)
+    return soft * sequence_mask(text_lengths, pred.shape[1])
+
+
+def synthesize(sds, texts, text_lengths, speech_style, pe_style, duration_style, draws_fn):
+    """ExportModel.forward export_model.py:40-63, batched.  `sds` = dict of the three state dicts;
+    `draws_fn(frames)` supplies the source noise once the (data-dependent) length is known."""
+    dur_pred = duration_predictor(sds["duration_predictor"], texts, text_lengths, duration_style)
+    dur = prediction_to_duration(dur_pred, text_lengths)
+    alignment = duration_to_alignment(dur)
+    pitch, energy = pitch_energy_predictor(sds["pitch_energy_predictor"], texts, text_lengths,
+                                           alignment, pe_style)
+    voiced = (pitch > 20).to(pitch.dtype)
+    audio = speech_predictor(sds["speech_predictor"], texts, text_lengths, alignment, pitch, energy,
+                             voiced, speech_style, pitch, draws_fn(alignment.shape[2]))
+    return audio, dict(dur_pred=dur_pred, duration=dur, alignment=alignment, pitch=pitch, energy=energy)

@@ -2,6 +2,7 @@
 forward / training hot path.  See DESIGN.md for scope and INTEGRATION.md for
 how it plugs into the reference's train.py / inference graph."""
 from .config import default_model_config, load_model_config_yaml  # noqa: F401
-from .modules import DecoderPrediction, SpeechPredictor, build_model  # noqa: F401
+from .modules import (DecoderPrediction, DurationPredictor, DurationProcessor,  # noqa: F401
+                      PitchEnergyPredictor, SpeechPredictor, Synthesizer, build_model)
 
 __version__ = "0.1.0"

@@ -15,7 +15,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libstylish_b200.so")
 
-ACT_NONE, ACT_RELU, ACT_LEAKY02, ACT_SNAKE, ACT_SWISH = 0, 1, 2, 3, 4
+ACT_NONE, ACT_RELU, ACT_LEAKY02, ACT_SNAKE, ACT_SWISH, ACT_GELU = 0, 1, 2, 3, 4, 5
 
 _f32p = C.c_void_p
 _i64 = C.c_int64
@@ -60,6 +60,13 @@ _SIGNATURES = {
     "sty_rope_table": [_f32p, _f32p, _i32, _i32, _f32, _f32p],
     "sty_attention_fwd": [_f32p, _f32p, _f32p, _i64, _f32p, _i64, _f32p, _f32p, _f32p, _i32, _i32,
                           _i32, _i32, _i32, _f32, _f32p],
+    "sty_attention_generic_fwd": [_f32p, _i64, _f32p, _f32p, _i64, _f32p, _i64, _f32p, _f32p, _f32p,
+                                  _i32, _i32, _i32, _i32, _i32, _f32, _f32p],
+    "sty_duration_head_fwd": [_f32p, _f32p, _f32p, _i32, _i32, _i32, _f32p],
+    "sty_soft_duration_fwd": [_f32p, _f32p, _f32p, _f32p, _f32p, _i32, _i32, _i32, _f32p],
+    "sty_alignment_fwd": [_f32p, _f32p, _i32, _i32, _i32, _f32p],
+    "sty_scale_mask_fwd": [_f32p, _f32p, _f32p, _i32, _i32, _i32, _f32, _f32p],
+    "sty_broadcast_rows_fwd": [_f32p, _f32p, _i64, _i32, _i32, _i32, _f32p],
     "sty_bmm_fwd": [_f32p, _i64, _f32p, _i64, _f32p, _i64, _i32, _i32, _i32, _i32, _f32p],
     "sty_glu_fwd": [_f32p, _f32p, _i32, _i32, _i32, _f32p],
     "sty_source_fwd": [_f32p, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, _i32, _i32, _i32, _i32,
@@ -144,6 +151,10 @@ def _signature(name: str, args) -> str:
         if a.w_split:
             extra += "+umma"
         return f"conv1d[ci={a.CI},co={a.CO},k={a.K},d={a.dil},B={a.B},T={a.T}{extra}]"
+    pos = {"sty_dwconv_ln_fwd": (9, 10), "sty_chan_layernorm_fwd": (11, 12),
+           "sty_instnorm_affine_fwd": (8, 9), "sty_attention_fwd": (12, 13)}.get(name)
+    if pos:
+        return f"{name[4:]}[c={args[pos[0]]},T={args[pos[1]]}]"
     return name[4:]
 
 

@@ -65,6 +65,8 @@ __device__ __forceinline__ float act_apply(float v, int act, float alpha, float 
       return fmaf(inv_alpha, sin_sq(alpha * v), v);
     case STY_ACT_SWISH:
       return v / (1.0f + expf(-v));
+    case STY_ACT_GELU:
+      return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));
     default:
       return v;
   }

@@ -103,9 +103,47 @@ __global__ void sequence_mask_kernel(const int64_t* __restrict__ lengths, float*
   out[i] = (t < lengths[b]) ? 1.f : 0.f;
 }
 
+// out[b,c,t] = x[b,c,t] * mask[b,t] * scale
+__global__ void scale_mask_kernel(const float* __restrict__ x, const float* __restrict__ mask,
+                                  float* __restrict__ out, int C, int T, float scale) {
+  const int b = blockIdx.y;
+  const int64_t n = (int64_t)C * T;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int t = (int)(i % T);
+  out[(int64_t)b * n + i] = x[(int64_t)b * n + i] * mask[(int64_t)b * T + t] * scale;
+}
+
+// out[b,s,t] = v[b,s]  (style vector repeated over time; prosody_encoder.py:67-68)
+__global__ void broadcast_rows_kernel(const float* __restrict__ v, float* __restrict__ out, int64_t out_bs,
+                                      int S, int T) {
+  const int b = blockIdx.y;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)S * T) return;
+  out[(int64_t)b * out_bs + i] = v[(int64_t)b * S + (int)(i / T)];
+}
+
 }  // namespace sty
 
 using namespace sty;
+
+extern "C" int sty_scale_mask_fwd(const float* x, const float* mask, float* out, int B, int C, int T,
+                                  float scale, sty_stream_t stream) {
+  STY_REQUIRE(x && mask && out && B > 0 && C > 0 && T > 0, "scale_mask: bad argument");
+  dim3 grid(cdiv((int64_t)C * T, 256), B);
+  scale_mask_kernel<<<grid, 256, 0, as_stream(stream)>>>(x, mask, out, C, T, scale);
+  STY_CHECK_LAUNCH("scale_mask");
+  return STY_OK;
+}
+
+extern "C" int sty_broadcast_rows_fwd(const float* v, float* out, int64_t out_bs, int B, int S, int T,
+                                      sty_stream_t stream) {
+  STY_REQUIRE(v && out && B > 0 && S > 0 && T > 0, "broadcast_rows: bad argument");
+  dim3 grid(cdiv((int64_t)S * T, 256), B);
+  broadcast_rows_kernel<<<grid, 256, 0, as_stream(stream)>>>(v, out, out_bs, S, T);
+  STY_CHECK_LAUNCH("broadcast_rows");
+  return STY_OK;
+}
 
 extern "C" int sty_sequence_mask_fwd(const int64_t* lengths, float* out, int B, int T,
                                      sty_stream_t stream) {

@@ -175,6 +175,97 @@ dwconv_ln_kernel(const float* __restrict__ x, int64_t x_bs, const float* __restr
   }
 }
 
+// --------------------------------------------------------------- column norm
+// LayerNorm over channels of a (C x TT) tile, optionally preceded by the depthwise k7
+// conv of the ConvNeXt block.  The tile (+ halo) is staged once in shared memory with
+// coalesced loads; thread (tl, cs) owns time step tl and the channel slice {cs, cs+CS, ..}
+// (values stay in registers), partial sums meet in shared memory.  Used for C <= 256
+// where one-thread-per-column has too little parallelism (text encoder T=258, F-rate).
+template <bool DW, int TT>
+__global__ void __launch_bounds__(256)
+colnorm_kernel(const float* __restrict__ xin, const float* __restrict__ resin, int64_t x_bs,
+               const float* __restrict__ w, const float* __restrict__ bias,
+               const float* __restrict__ gamma, const float* __restrict__ beta, int64_t g_bs,
+               int g_plus_one, float* __restrict__ yout, int64_t y_bs, const float* __restrict__ mask,
+               int C, int T, float eps, int act) {
+  constexpr int P = DW ? 3 : 0, K = 7;
+  constexpr int W = TT + 2 * P + 1;  // +1: odd row pitch
+  constexpr int CS = 256 / TT;       // channel slices
+  constexpr int NC = 32;             // channels per thread: C <= 32 * CS (256 for TT=32, 64 for TT=128)
+  extern __shared__ float sm[];
+  float* xs = sm;                    // [C][W]
+  float* red = sm + (size_t)C * W;   // [CS][TT]
+  const int b = blockIdx.y, t0 = blockIdx.x * TT, tid = threadIdx.x;
+  const float* __restrict__ x = xin + (int64_t)b * x_bs;
+  const float* __restrict__ res = resin ? resin + (int64_t)b * x_bs : nullptr;
+  for (int idx = tid; idx < C * (TT + 2 * P); idx += 256) {
+    const int c = idx / (TT + 2 * P), j = idx - c * (TT + 2 * P);
+    const int t = t0 - P + j;
+    float v = 0.f;
+    if (t >= 0 && t < T) {
+      v = x[(int64_t)c * T + t];
+      if (res) v += res[(int64_t)c * T + t];
+    }
+    xs[c * W + j] = v;
+  }
+  __syncthreads();
+  const int tl = tid % TT, cs = tid / TT;
+  const int t = t0 + tl;
+  float d[NC];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NC; ++i) {
+    const int c = cs + i * CS;
+    float a = 0.f;
+    if (c < C) {
+      if (DW) {
+        a = bias[c];
+#pragma unroll
+        for (int k = 0; k < K; ++k) a = fmaf(w[c * K + k], xs[c * W + tl + k], a);
+      } else {
+        a = xs[c * W + tl];
+      }
+    }
+    d[i] = a;
+    s += a;
+  }
+  red[cs * TT + tl] = s;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int i = 0; i < CS; ++i) tot += red[i * TT + tl];
+  const float mean = tot / (float)C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NC; ++i) {
+    const int c = cs + i * CS;
+    const float e = (c < C) ? d[i] - mean : 0.f;
+    q = fmaf(e, e, q);
+  }
+  __syncthreads();
+  red[cs * TT + tl] = q;
+  __syncthreads();
+  float qt = 0.f;
+#pragma unroll
+  for (int i = 0; i < CS; ++i) qt += red[i * TT + tl];
+  const float rstd = 1.0f / sqrtf(qt / (float)C + eps);
+  if (t < T) {
+    const float* __restrict__ g = gamma + (int64_t)b * g_bs;
+    const float* __restrict__ be = beta + (int64_t)b * g_bs;
+    const float m = mask ? mask[(int64_t)b * T + t] : 1.f;
+    float* __restrict__ y = yout + (int64_t)b * y_bs + t;
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
+      const int c = cs + i * CS;
+      if (c < C) {
+        const float gg = g_plus_one ? 1.0f + g[c] : g[c];
+        const float o = (d[i] - mean) * rstd * gg + be[c];
+        y[(int64_t)c * T] = act_apply(o, act) * m;
+      }
+    }
+  }
+}
+
 // -------------------------------------------------------------------- dwconv
 __global__ void __launch_bounds__(256)
 dwconv1d_kernel(const float* __restrict__ x, int64_t x_bs, int64_t x_cs,
@@ -254,7 +345,13 @@ extern "C" int sty_chan_layernorm_fwd(const float* x, const float* res, int64_t 
                                                   y_bs, mask, C, T, eps, act)
   if (C == 32) LAUNCH(32);
   else if (C == 64) LAUNCH(64);
-  else LAUNCH(0);
+  else if (C <= 256) {
+    constexpr int TT = 32;
+    const size_t smem = ((size_t)C * (TT + 1) + 256) * sizeof(float);
+    dim3 g2(cdiv(T, TT), B);
+    colnorm_kernel<false, TT><<<g2, 256, smem, st>>>(x, res, x_bs, nullptr, nullptr, gamma, beta, g_bs,
+                                                    g_plus_one, y, y_bs, mask, C, T, eps, act);
+  } else LAUNCH(0);
 #undef LAUNCH
   STY_CHECK_LAUNCH("chan_layernorm");
   return STY_OK;
@@ -267,9 +364,22 @@ extern "C" int sty_dwconv_ln_fwd(const float* x, int64_t x_bs, const float* w, c
   STY_REQUIRE(B > 0 && C > 0 && T > 0, "dwconv_ln: bad shape");
   dim3 grid(cdiv(T, 128), B);
   cudaStream_t st = as_stream(stream);
-  if (C == 32) dwconv_ln_kernel<32><<<grid, 128, 0, st>>>(x, x_bs, w, bias, gb, gb_bs, y, y_bs, C, T, eps);
-  else if (C == 64) dwconv_ln_kernel<64><<<grid, 128, 0, st>>>(x, x_bs, w, bias, gb, gb_bs, y, y_bs, C, T, eps);
-  else dwconv_ln_kernel<0><<<grid, 128, 0, st>>>(x, x_bs, w, bias, gb, gb_bs, y, y_bs, C, T, eps);
+  if (C <= 64) {
+    // smem-staged tile, 128 time steps x (2 channel slices): one global read per element
+    constexpr int TT = 128;
+    const size_t smem = ((size_t)C * (TT + 7) + 256) * sizeof(float);
+    dim3 g2(cdiv(T, TT), B);
+    colnorm_kernel<true, TT><<<g2, 256, smem, st>>>(x, nullptr, x_bs, w, bias, gb, gb + C, gb_bs, 1, y, y_bs,
+                                                   nullptr, C, T, eps, STY_ACT_NONE);
+  } else if (C <= 256) {
+    constexpr int TT = 32;
+    const size_t smem = ((size_t)C * (TT + 7) + 256) * sizeof(float);
+    dim3 g2(cdiv(T, TT), B);
+    colnorm_kernel<true, TT><<<g2, 256, smem, st>>>(x, nullptr, x_bs, w, bias, gb, gb + C, gb_bs, 1, y, y_bs,
+                                                   nullptr, C, T, eps, STY_ACT_NONE);
+  } else {
+    dwconv_ln_kernel<0><<<grid, 128, 0, st>>>(x, x_bs, w, bias, gb, gb_bs, y, y_bs, C, T, eps);
+  }
   STY_CHECK_LAUNCH("dwconv_ln");
   return STY_OK;
 }

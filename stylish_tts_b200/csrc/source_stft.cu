@@ -33,27 +33,48 @@ __device__ __forceinline__ double f0_up(const float* __restrict__ pitch,
   return (1.0 - lam) * a + lam * b;
 }
 
-// one thread per (b, harmonic): frame-rate phase accumulation (F sequential steps)
-__global__ void source_phase_kernel(const float* __restrict__ pitch,
-                                    const float* __restrict__ voiced, double* __restrict__ work,
-                                    int B, int F, int hop, int H, double sr) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= B * H) return;
-  const int b = idx / H, h = idx - b * H;
+// one CTA per (b, harmonic): frame-rate phase increments computed in parallel, then an
+// fp64 block scan (256 frames per pass, carry between passes)
+__global__ void __launch_bounds__(256)
+source_phase_kernel(const float* __restrict__ pitch, const float* __restrict__ voiced,
+                    double* __restrict__ work, int B, int F, int hop, int H, double sr) {
+  __shared__ double wsum[8];
+  __shared__ double carry_s;
+  const int b = blockIdx.x / H, h = blockIdx.x - b * H;
   const float* __restrict__ pb = pitch + (int64_t)b * F;
   const float* __restrict__ vb = voiced + (int64_t)b * F;
   const int L = F * hop;
-  double cum = 0.0;
-  for (int i = 0; i < F; ++i) {
-    int j0, j1;
-    double lam;
-    lerp_coord(((double)i + 0.5) * (double)hop - 0.5, L, j0, j1, lam);
-    double r0 = f0_up(pb, vb, F, hop, j0) * (double)(h + 1) / sr;
-    double r1 = f0_up(pb, vb, F, hop, j1) * (double)(h + 1) / sr;
-    r0 -= floor(r0);
-    r1 -= floor(r1);
-    cum += (1.0 - lam) * r0 + lam * r1;
-    work[((int64_t)b * H + h) * F + i] = cum;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid == 0) carry_s = 0.0;
+  __syncthreads();
+  for (int base = 0; base < F; base += 256) {
+    const int i = base + tid;
+    double v = 0.0;
+    if (i < F) {
+      int j0, j1;
+      double lam;
+      lerp_coord(((double)i + 0.5) * (double)hop - 0.5, L, j0, j1, lam);
+      double r0 = f0_up(pb, vb, F, hop, j0) * (double)(h + 1) / sr;
+      double r1 = f0_up(pb, vb, F, hop, j1) * (double)(h + 1) / sr;
+      r0 -= floor(r0);
+      r1 -= floor(r1);
+      v = (1.0 - lam) * r0 + lam * r1;
+    }
+    // inclusive warp scan
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double n = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o) v += n;
+    }
+    if (lane == 31) wsum[wid] = v;
+    __syncthreads();
+    double off = carry_s;
+    for (int k = 0; k < wid; ++k) off += wsum[k];
+    v += off;
+    if (i < F) work[((int64_t)b * H + h) * F + i] = v;
+    __syncthreads();
+    if (tid == 255) carry_s = v;
+    __syncthreads();
   }
 }
 
@@ -219,8 +240,7 @@ extern "C" int sty_source_fwd(const float* pitch, const float* voiced, const flo
   STY_REQUIRE(pitch && voiced && noise && lin_w && lin_b && work && out, "source: null pointer");
   STY_REQUIRE(B > 0 && F > 1 && hop > 0 && H > 0 && H <= 16, "source: bad shape (H<=16)");
   cudaStream_t st = as_stream(stream);
-  source_phase_kernel<<<cdiv(B * H, 64), 64, 0, st>>>(pitch, voiced, work, B, F, hop, H,
-                                                      (double)sample_rate);
+  source_phase_kernel<<<B * H, 256, 0, st>>>(pitch, voiced, work, B, F, hop, H, (double)sample_rate);
   STY_CHECK_LAUNCH("source_phase");
   dim3 grid(cdiv((int64_t)F * hop, 256), B);
   source_wave_kernel<16><<<grid, 256, 0, st>>>(pitch, voiced, noise, lin_w, lin_b, work, out, F, hop,

@@ -140,31 +140,19 @@ def attention(qkv, n_q, n_k, n_v, *, H, D, lengths=None, rope=None, scale):
     return out
 
 
-class Packed:
-    """Device-resident, kernel-layout copy of a SpeechPredictor's parameters."""
+class PackBase:
+    """Device-resident, kernel-layout copy of a module's parameters: helpers, the packed
+    style FCs and the text encoder every hot-path module owns (`text_encoder.*`)."""
 
     def __init__(self, module, device):
-        sd = {k: v.detach().to(device=device, dtype=torch.float32) if v.is_floating_point()
-              else v.detach().to(device) for k, v in module.state_dict().items()}
+        self.sd = sd = {k: v.detach().to(device=device, dtype=torch.float32) if v.is_floating_point()
+                        else v.detach().to(device) for k, v in module.state_dict().items()}
         self.device = device
         mc = module.model_config
         self.mc = mc
         te = mc.text_encoder
         self.n_layers, self.n_heads, self.hidden = te.layers, te.heads, te.hidden_dim
-
-        def wn(prefix):
-            k0 = prefix + ".parametrizations.weight.original0"
-            if k0 in sd:
-                return torch._weight_norm(sd[prefix + ".parametrizations.weight.original1"],
-                                          sd[k0], 0)
-            return sd[prefix + ".weight"]
-
-        def cv(prefix):
-            return ConvW(wn(prefix), sd.get(prefix + ".bias"))
-
-        def lin(prefix, bias=True):
-            return ConvW(sd[prefix + ".weight"].unsqueeze(-1),
-                         sd.get(prefix + ".bias") if bias else None)
+        cv = self.cv
 
         # ---- all style FCs packed row-wise into one matrix --------------------
         fc_names = sorted(k[:-len(".fc.weight")] for k in sd if k.endswith(".fc.weight"))
@@ -191,27 +179,66 @@ class Packed:
         e = t + ".encoder"
         for i in range(self.n_layers):
             a = f"{e}.attn_layers.{i}"
-            wqkv = torch.cat([sd[a + ".conv_q.weight"], sd[a + ".conv_k.weight"],
-                              sd[a + ".conv_v.weight"]], 0)
-            bqkv = torch.cat([sd[a + ".conv_q.bias"], sd[a + ".conv_k.bias"],
-                              sd[a + ".conv_v.bias"]], 0)
             self.enc.append(dict(
-                qkv=ConvW(wqkv, bqkv), o=cv(a + ".conv_o"),
+                qkv=self.qkv(a), o=cv(a + ".conv_o"),
                 n1=(sd[f"{e}.norm_layers_1.{i}.gamma"].contiguous(),
                     sd[f"{e}.norm_layers_1.{i}.beta"].contiguous()),
                 f1=cv(f"{e}.ffn_layers.{i}.conv_1"), f2=cv(f"{e}.ffn_layers.{i}.conv_2"),
                 n2=(sd[f"{e}.norm_layers_2.{i}.gamma"].contiguous(),
                     sd[f"{e}.norm_layers_2.{i}.beta"].contiguous())))
         self.proj_m = cv(t + ".proj_m")
+        self.rope_cache: Dict[tuple, tuple] = {}
+
+    # weight helpers ----------------------------------------------------------
+    def wn(self, prefix):
+        sd = self.sd
+        k0 = prefix + ".parametrizations.weight.original0"
+        if k0 in sd:
+            return torch._weight_norm(sd[prefix + ".parametrizations.weight.original1"], sd[k0], 0)
+        return sd[prefix + ".weight"]
+
+    def cv(self, prefix):
+        return ConvW(self.wn(prefix), self.sd.get(prefix + ".bias"))
+
+    def lin(self, prefix, bias=True):
+        return ConvW(self.sd[prefix + ".weight"].unsqueeze(-1),
+                     self.sd.get(prefix + ".bias") if bias else None)
+
+    def qkv(self, a):
+        """fused q|k|v projection of a reference MultiHeadAttention (text_encoder.py:195-203)"""
+        sd = self.sd
+        w = torch.cat([sd[a + ".conv_q.weight"], sd[a + ".conv_k.weight"], sd[a + ".conv_v.weight"]], 0)
+        b = torch.cat([sd[a + ".conv_q.bias"], sd[a + ".conv_k.bias"], sd[a + ".conv_v.bias"]], 0)
+        return ConvW(w, b)
+
+    def dblock(self, p):
+        """AdaptiveDecoderBlock (ada_norm.py:143-192)"""
+        has_sc = (p + ".conv1x1.parametrizations.weight.original0") in self.sd
+        return dict(c1=self.cv(p + ".conv1"), c2=self.cv(p + ".conv2"),
+                    sc=self.cv(p + ".conv1x1") if has_sc else None, n1=p + ".norm1", n2=p + ".norm2")
+
+    def rope(self, T: int, d_head: int = 0):
+        d = d_head or (self.hidden // self.n_heads)
+        key = (T, d)
+        if key not in self.rope_cache:
+            d_rot = int(d * 0.5)
+            c = torch.empty((T, d_rot // 2), device=self.device, dtype=torch.float32)
+            s = torch.empty_like(c)
+            L.call("sty_rope_table", c.data_ptr(), s.data_ptr(), T, d_rot, 10000.0, L.stream_ptr())
+            self.rope_cache[key] = (c, s, d_rot)
+        return self.rope_cache[key]
+
+
+class Packed(PackBase):
+    """speech_predictor: text encoder + decoder + generator."""
+
+    def __init__(self, module, device):
+        super().__init__(module, device)
+        sd, mc = self.sd, self.mc
+        wn, cv, lin, dblock = self.wn, self.cv, self.lin, self.dblock
 
         # ---- decoder --------------------------------------------------------------
         d = "decoder"
-
-        def dblock(p):
-            has_sc = (p + ".conv1x1.parametrizations.weight.original0") in sd
-            return dict(c1=cv(p + ".conv1"), c2=cv(p + ".conv2"),
-                        sc=cv(p + ".conv1x1") if has_sc else None,
-                        n1=p + ".norm1", n2=p + ".norm2")
 
         self.dec_encode = dblock(d + ".encode")
         self.dec_decode = [dblock(f"{d}.decode.{i}") for i in range(4)]
@@ -292,17 +319,6 @@ class Packed:
         self.stft_b_re = sd[bg + ".stft.weight_backward_real"].reshape(-1, 64).contiguous()
         self.stft_b_im = sd[bg + ".stft.weight_backward_imag"].reshape(-1, 64).contiguous()
         self.hidden_s = mc.n_fft // 2 // 8  # 32 channels at the STFT-frame rate
-        self.rope_cache: Dict[int, tuple] = {}
-
-    def rope(self, T: int):
-        if T not in self.rope_cache:
-            d = self.hidden // self.n_heads
-            d_rot = int(d * 0.5)
-            c = torch.empty((T, d_rot // 2), device=self.device, dtype=torch.float32)
-            s = torch.empty_like(c)
-            L.call("sty_rope_table", c.data_ptr(), s.data_ptr(), T, d_rot, 10000.0, L.stream_ptr())
-            self.rope_cache[T] = (c, s, d_rot)
-        return self.rope_cache[T]
 
 
 class SpeechEngine:
@@ -327,7 +343,7 @@ class SpeechEngine:
         """pointer view of the (gamma|beta) rows of style FC `name` inside h (B, J)."""
         return h[:, P.fc_off[name]:]
 
-    def text_encoder(self, P: Packed, texts, lengths, taps=None):
+    def text_encoder(self, P, texts, lengths, taps=None, mu_out=None):
         B, T = texts.shape
         Cc = P.hidden
         dev = texts.device
@@ -355,7 +371,7 @@ class SpeechEngine:
             hh = conv1d(x1, ly["f1"], in_mask=mask, out_act=ACT_RELU)
             y2 = conv1d(hh, ly["f2"], in_mask=mask, out_mask=mask)
             x = chan_layernorm(y2, *ly["n2"], eps=1e-4, res=x1, mask=mask)
-        mu = conv1d(x, P.proj_m, out_mask=mask)
+        mu = conv1d(x, P.proj_m, out_mask=mask, out=mu_out)
         return mu, x, mask
 
     def _decoder_block(self, P, blk, x, h, out):
@@ -570,3 +586,246 @@ class SpeechEngine:
         if source_draws is not None:
             noise = f32(source_draws["noise"])
         return self.generator(P, mel, h, denormal_pitch, voiced, noise, prior=prior, taps=taps)
+
+
+# ==========================================================================
+# duration predictor, pitch/energy predictor, alignment, text -> wav
+# ==========================================================================
+def attention_generic(q, k, v, *, H, D, lengths=None, rope=None, scale):
+    """q: (B,H*D,T) view; k, v: views sharing one batch stride (e.g. halves of a fused k|v buffer)."""
+    B, _, T = q.shape
+    assert q.stride(1) == T and k.stride(1) == T and v.stride(1) == T and k.stride(0) == v.stride(0)
+    out = torch.empty((B, H * D, T), device=q.device, dtype=torch.float32)
+    rc, rs, d_rot = (None, None, 0) if rope is None else (rope[0].data_ptr(), rope[1].data_ptr(),
+                                                          rope[2])
+    L.call("sty_attention_generic_fwd", q.data_ptr(), q.stride(0), k.data_ptr(), v.data_ptr(),
+           k.stride(0), out.data_ptr(), out.stride(0), L.ptr(lengths), rc, rs, d_rot, B, H, D, T,
+           scale, L.stream_ptr())
+    return out
+
+
+class _EngineBase:
+    pack_cls = None
+
+    def __init__(self, module):
+        L.load()
+        self.module = module
+        self._packed = None
+        self._packed_key = None
+
+    def packed(self, device):
+        key = (str(device),) + tuple(p._version for p in self.module.parameters()) + \
+            tuple(b._version for b in self.module.buffers())
+        if self._packed is None or key != self._packed_key:
+            self._packed = self.pack_cls(self.module, device)
+            self._packed_key = key
+        return self._packed
+
+    @staticmethod
+    def style_fc(P, style):
+        B = style.shape[0]
+        h = torch.empty((B, P.fc_rows), device=style.device, dtype=torch.float32)
+        L.call("sty_linear_rows_fwd", style.data_ptr(), P.fc_w.data_ptr(), P.fc_b.data_ptr(),
+               h.data_ptr(), B, style.shape[1], P.fc_rows, L.stream_ptr())
+        return h
+
+    # shared stage implementations (same kernels as the speech predictor)
+    text_encoder = SpeechEngine.text_encoder
+    _gb = staticmethod(SpeechEngine._gb)
+    _ada_ln = SpeechEngine._ada_ln
+    _decoder_block = SpeechEngine._decoder_block
+
+
+class PackedDuration(PackBase):
+    def __init__(self, module, device):
+        super().__init__(module, device)
+        sd, cv = self.sd, self.cv
+        self.q = cv("cross_attention.conv_q")
+        wkv = torch.cat([sd["cross_attention.conv_k.weight"], sd["cross_attention.conv_v.weight"]], 0)
+        bkv = torch.cat([sd["cross_attention.conv_k.bias"], sd["cross_attention.conv_v.bias"]], 0)
+        self.kv = ConvW(wkv, bkv)
+        self.o = cv("cross_attention.conv_o")
+        self.post_dw_w = self.wn("cross_post.0").reshape(-1, 5).contiguous()
+        self.post_dw_b = sd["cross_post.0.bias"].contiguous()
+        self.post_pw = cv("cross_post.2")
+        self.blocks = []
+        for i in range(self.mc.duration_predictor.n_layer):
+            p = f"conv_next.{i}"
+            w2 = sd[p + ".pwconv2.weight"]
+            b2 = sd[p + ".pwconv2.bias"] + w2 @ sd[p + ".grn.beta"].reshape(-1)
+            self.blocks.append(dict(
+                dw_w=sd[p + ".dwconv.weight"].reshape(-1, 7).contiguous(),
+                dw_b=sd[p + ".dwconv.bias"].contiguous(), norm=p + ".norm", pw1=self.lin(p + ".pwconv1"),
+                grn_gamma=sd[p + ".grn.gamma"].reshape(-1).contiguous(),
+                pw2=ConvW(w2.unsqueeze(-1), b2)))
+        self.proj = self.lin("duration_proj.linear_layer")
+
+
+class DurationEngine(_EngineBase):
+    """DurationPredictor.forward (duration_predictor.py:58-87) -> (B,T,classes)."""
+    pack_cls = PackedDuration
+
+    @torch.no_grad()
+    def forward(self, texts, text_lengths, style, taps=None):
+        dev = texts.device
+        if dev.type != "cuda":
+            raise RuntimeError("stylish_tts_b200: inputs must live on a CUDA device; no CPU fallback")
+        P = self.packed(dev)
+        texts = texts.to(torch.int64).contiguous()
+        lengths = text_lengths.to(device=dev, dtype=torch.int64).contiguous()
+        style = style.to(device=dev, dtype=torch.float32).contiguous()
+        B, T = texts.shape
+        h = self.style_fc(P, style)
+        enc, _, mask = self.text_encoder(P, texts, lengths)  # (B,C,T)
+        Cc = enc.shape[1]
+        qn = self._ada_ln(P, enc, h, "query_norm", 1e-5)
+        kn = self._ada_ln(P, enc, h, "key_norm", 1e-5)
+        qkv = torch.empty((B, 3 * Cc, T), device=dev, dtype=torch.float32)
+        conv1d(qn, P.q, out=qkv[:, :Cc])
+        conv1d(kn, P.kv, out=qkv[:, Cc:])
+        H = 8
+        D = Cc // H
+        att = attention(qkv, Cc, Cc, Cc, H=H, D=D, lengths=lengths, rope=P.rope(T, D),
+                        scale=1.0 / math.sqrt(D))
+        att = conv1d(att, P.o)
+        dw = torch.empty_like(att)
+        dwconv1d(att, P.post_dw_w, P.post_dw_b, K=5, pad_left=2, out=dw, act=ACT_SWISH)
+        pros = conv1d(dw, P.post_pw, res=enc, out_scale=INV_SQRT2, res_scale=INV_SQRT2)
+        if taps is not None:
+            taps["dur_cross"] = pros.clone()
+        J = P.fc_rows
+        for blk in P.blocks:  # AdaptiveConvNeXtBlock (GELU) then * mask  (conv_next.py:125-141)
+            gb = self._gb(P, h, blk["norm"])
+            y = torch.empty_like(pros)
+            L.call("sty_dwconv_ln_fwd", pros.data_ptr(), pros.stride(0), blk["dw_w"].data_ptr(),
+                   blk["dw_b"].data_ptr(), gb.data_ptr(), J, y.data_ptr(), y.stride(0), B, Cc, T, 1e-6,
+                   L.stream_ptr())
+            inter = blk["pw1"].CO
+            sumsq = torch.zeros((B, inter), device=dev, dtype=torch.float32)
+            hb = conv1d(y, blk["pw1"], out_act=L.ACT_GELU, out_sumsq=sumsq)
+            gs = torch.empty_like(sumsq)
+            L.call("sty_grn_scale_fwd", sumsq.data_ptr(), blk["grn_gamma"].data_ptr(), gs.data_ptr(), B,
+                   inter, L.stream_ptr())
+            # (residual + block) * mask: the residual is already masked from the second block on,
+            # for the first one the mask is applied to the sum by masking both terms
+            if blk is P.blocks[0]:
+                resm = torch.empty_like(pros)
+                L.call("sty_scale_mask_fwd", pros.data_ptr(), mask.data_ptr(), resm.data_ptr(), B, Cc, T,
+                       1.0, L.stream_ptr())
+                pros = resm
+            conv1d(hb, blk["pw2"], in_scale=gs, out_mask=mask, res=pros, out=pros)
+        logits = conv1d(pros, P.proj)  # (B,NC,T)
+        NC = logits.shape[1]
+        out = torch.empty((B, T, NC), device=dev, dtype=torch.float32)
+        L.call("sty_duration_head_fwd", logits.data_ptr(), lengths.data_ptr(), out.data_ptr(), B, NC, T,
+               L.stream_ptr())
+        return out
+
+
+class PackedPE(PackBase):
+    def __init__(self, module, device):
+        super().__init__(module, device)
+        sd, cv = self.sd, self.cv
+        pe = "prosody_encoder"
+        self.layers = []
+        for i in range(3):
+            self.layers.append(dict(
+                qkv=self.qkv(f"{pe}.attn_layers.{i}"), o=cv(f"{pe}.attn_layers.{i}.conv_o"),
+                n1=f"{pe}.norm_layers_1.{i}", f1=cv(f"{pe}.ffn_layers.{i}.conv_1"),
+                f2=cv(f"{pe}.ffn_layers.{i}.conv_2"), n2=f"{pe}.norm_layers_2.{i}",
+                proj=cv(f"{pe}.proj_layers.{i}")))
+        self.f0 = [self.dblock(f"F0.{i}") for i in range(4)]
+        self.n = [self.dblock(f"N.{i}") for i in range(4)]
+        self.f0_proj = cv("F0_proj")
+        self.n_proj = cv("N_proj")
+
+
+class PitchEnergyEngine(_EngineBase):
+    """PitchEnergyPredictor.forward (pitch_energy_predictor.py:62-82) -> pitch (B,F), energy (B,F)."""
+    pack_cls = PackedPE
+
+    @torch.no_grad()
+    def forward(self, texts, text_lengths, alignment, style, taps=None):
+        dev = texts.device
+        if dev.type != "cuda":
+            raise RuntimeError("stylish_tts_b200: inputs must live on a CUDA device; no CPU fallback")
+        P = self.packed(dev)
+        texts = texts.to(torch.int64).contiguous()
+        lengths = text_lengths.to(device=dev, dtype=torch.int64).contiguous()
+        style = style.to(device=dev, dtype=torch.float32).contiguous()
+        alignment = alignment.to(device=dev, dtype=torch.float32).contiguous()
+        B, T = texts.shape
+        Fr = alignment.shape[2]
+        h = self.style_fc(P, style)
+        dm = P.proj_m.CO
+        sdim = style.shape[1]
+        Ch = dm + sdim
+        # x = cat[text encoding, style]: the style rows are constant over time; the encoder's last
+        # projection writes straight into the first dm channels
+        x = torch.empty((B, Ch, T), device=dev, dtype=torch.float32)
+        x2 = torch.empty_like(x)
+        for buf in (x, x2):
+            L.call("sty_broadcast_rows_fwd", style.data_ptr(), buf[:, dm:].data_ptr(), buf.stride(0), B,
+                   sdim, T, L.stream_ptr())
+        _, _, mask = self.text_encoder(P, texts, lengths, mu_out=x[:, :dm])
+        H = 2
+        D = Ch // H
+        rope = P.rope(T, D)
+        cur, nxt = x, x2
+        for ly in P.layers:
+            qkv = conv1d(cur, ly["qkv"], in_mask=mask)
+            att = attention_generic(qkv[:, :Ch], qkv[:, Ch:2 * Ch], qkv[:, 2 * Ch:], H=H, D=D,
+                                    lengths=lengths, rope=rope, scale=1.0 / math.sqrt(D))
+            y = conv1d(att, ly["o"], in_mask=None, res=None)
+            # x*mask + y, AdaLN
+            xm = torch.empty_like(cur)
+            L.call("sty_scale_mask_fwd", cur.data_ptr(), mask.data_ptr(), xm.data_ptr(), B, Ch, T, 1.0,
+                   L.stream_ptr())
+            gb = self._gb(P, h, ly["n1"])
+            x1 = chan_layernorm(y, gb, gb[:, Ch:], eps=1e-5, res=xm, g_bs=P.fc_rows, plus_one=True)
+            hh = conv1d(x1, ly["f1"], in_mask=mask, out_act=ACT_RELU)
+            y2 = conv1d(hh, ly["f2"], in_mask=mask, out_mask=mask)
+            gb = self._gb(P, h, ly["n2"])
+            x2n = chan_layernorm(y2, gb, gb[:, Ch:], eps=1e-5, res=x1, g_bs=P.fc_rows, plus_one=True)
+            conv1d(x2n, ly["proj"], out=nxt[:, :dm])
+            cur, nxt = nxt, cur
+        pros = torch.empty_like(cur)  # final x * mask, (B, Ch, T)
+        L.call("sty_scale_mask_fwd", cur.data_ptr(), mask.data_ptr(), pros.data_ptr(), B, Ch, T, 1.0,
+               L.stream_ptr())
+        if taps is not None:
+            taps["prosody"] = pros.transpose(1, 2).clone()
+        xa = torch.empty((B, Ch, Fr), device=dev, dtype=torch.float32)
+        L.call("sty_bmm_fwd", pros.data_ptr(), pros.stride(0), alignment.data_ptr(), alignment.stride(0),
+               xa.data_ptr(), xa.stride(0), B, Ch, Fr, T, L.stream_ptr())
+        outs = []
+        for tower, proj in ((P.f0, P.f0_proj), (P.n, P.n_proj)):
+            z = xa
+            for blk in tower:
+                out = torch.empty((B, blk["c2"].CO, Fr), device=dev, dtype=torch.float32)
+                z = self._decoder_block(P, blk, z, h, out)
+            outs.append(conv1d(z, proj).reshape(B, Fr))
+        return outs[0], outs[1]
+
+
+CLASS_TO_DUR = (1, 2, 3, 4, 5, 6, 7, 9, 12, 15, 18, 22, 27, 32, 38, 46)
+
+
+def duration_to_alignment(pred, text_lengths):
+    """DurationProcessor.forward (utils.py:804-807): class scores (B,T,NC) -> (alignment (B,T,F),
+    durations (B,T)).  The frame count is data dependent: one device->host read, like the
+    reference's `.item()` (utils.py:759)."""
+    dev = pred.device
+    B, T, NC = pred.shape
+    pred = pred.contiguous()
+    lengths = text_lengths.to(device=dev, dtype=torch.int64).contiguous()
+    table = torch.tensor(CLASS_TO_DUR[:NC], device=dev, dtype=torch.float32)
+    dur = torch.empty((B, T), device=dev, dtype=torch.float32)
+    total = torch.zeros((1,), device=dev, dtype=torch.int32)
+    L.call("sty_soft_duration_fwd", pred.data_ptr(), lengths.data_ptr(), table.data_ptr(), dur.data_ptr(),
+           total.data_ptr(), B, T, NC, L.stream_ptr())
+    Fr = int(total.item())
+    if Fr <= 0:
+        raise RuntimeError("stylish_tts_b200: predicted durations sum to zero frames")
+    al = torch.empty((B, T, Fr), device=dev, dtype=torch.float32)
+    L.call("sty_alignment_fwd", dur.data_ptr(), al.data_ptr(), B, T, Fr, L.stream_ptr())
+    return al, dur

@@ -315,7 +315,151 @@ class SpeechPredictor(nn.Module):
         return DecoderPrediction(audio=audio, magnitude=None, phase=None)
 
 
-HOT_PATH_KEYS = ("speech_predictor",)
+def adaptive_convnext_tree(dim, style_dim) -> Node:
+    # AdaptiveConvNeXtBlock (conv_next.py:96-123): like the generator block but GELU, no snake
+    inter = 4 * dim
+    return Node(
+        dwconv=conv(dim, dim, 7, groups=dim),
+        norm=ada_fc(style_dim, dim),
+        pwconv1=nn.Linear(dim, inter),
+        grn=Node(gamma=zeros(1, 1, inter), beta=zeros(1, 1, inter)),
+        pwconv2=nn.Linear(inter, dim),
+    )
+
+
+class _EngineModule(nn.Module):
+    """Shared plumbing of the shells: lazily built engine, no autograd path yet."""
+    engine_cls_name = ""
+
+    def engine(self):
+        from . import engine as E
+
+        if self._engine is None:
+            self._engine = getattr(E, self.engine_cls_name)(self)
+        return self._engine
+
+    def _no_grad_only(self):
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise NotImplementedError(
+                f"stylish_tts_b200: the backward kernels of {type(self).__name__} are not built yet; "
+                "call under torch.no_grad() (forward/inference path)")
+
+
+class DurationPredictor(_EngineModule):
+    """Drop-in for reference DurationPredictor (duration_predictor.py:15-87):
+    forward(texts, text_lengths, style) -> (B, T, duration_classes)."""
+    engine_cls_name = "DurationEngine"
+
+    def __init__(self, model_config):
+        super().__init__()
+        mc = model_config
+        self.model_config = mc
+        c = mc.inter_dim
+        self.text_encoder = text_encoder_tree(c, mc.text_encoder)
+        self.conv_next = seq([adaptive_convnext_tree(c, mc.style_dim)
+                              for _ in range(mc.duration_predictor.n_layer)])
+        lin = nn.Linear(c, mc.duration_predictor.duration_classes)
+        nn.init.xavier_uniform_(lin.weight)
+        self.duration_proj = Node(linear_layer=lin)
+        self.query_norm = ada_fc(mc.style_dim, c)
+        self.key_norm = ada_fc(mc.style_dim, c)
+        att = Node(conv_q=conv(c, c, 1), conv_k=conv(c, c, 1), conv_v=conv(c, c, 1), conv_o=conv(c, c, 1))
+        for n in ("conv_q", "conv_k", "conv_v"):
+            nn.init.xavier_uniform_(getattr(att, n).weight)
+        self.cross_attention = att
+        post = Node()
+        post.put("0", conv(c, c, 5, wn=True, groups=c))
+        post.put("2", conv(c, c, 1, wn=True))
+        self.cross_post = post
+        self._engine = None
+
+    def forward(self, texts, text_lengths, style, *, taps=None):
+        self._no_grad_only()
+        return self.engine().forward(texts, text_lengths, style, taps=taps)
+
+
+class PitchEnergyPredictor(_EngineModule):
+    """Drop-in for reference PitchEnergyPredictor (pitch_energy_predictor.py:8-82):
+    forward(texts, text_lengths, alignment, style) -> (pitch (B,F), energy (B,F))."""
+    engine_cls_name = "PitchEnergyEngine"
+
+    def __init__(self, model_config):
+        super().__init__()
+        mc = model_config
+        self.model_config = mc
+        d, sdim = mc.pitch_energy_predictor.inter_dim, mc.style_dim
+        hc = d + sdim
+        self.text_encoder = text_encoder_tree(d, mc.text_encoder)
+
+        def mha():
+            m = Node(conv_q=conv(hc, hc, 1), conv_k=conv(hc, hc, 1), conv_v=conv(hc, hc, 1),
+                     conv_o=conv(hc, hc, 1))
+            for n in ("conv_q", "conv_k", "conv_v"):
+                nn.init.xavier_uniform_(getattr(m, n).weight)
+            return m
+
+        self.prosody_encoder = Node(
+            attn_layers=[mha() for _ in range(3)],
+            norm_layers_1=[ada_fc(sdim, hc) for _ in range(3)],
+            ffn_layers=[Node(conv_1=conv(hc, 2 * hc, 1), conv_2=conv(2 * hc, hc, 1)) for _ in range(3)],
+            norm_layers_2=[ada_fc(sdim, hc) for _ in range(3)],
+            proj_layers=[conv(hc, d, 1) for _ in range(3)],
+        )
+        dims = [(hc, d), (d, d // 2), (d // 2, d // 2), (d // 2, d // 2)]
+        self.F0 = seq([decoder_block_tree(a, b, sdim) for a, b in dims])
+        self.N = seq([decoder_block_tree(a, b, sdim) for a, b in dims])
+        self.F0_proj = conv(d // 2, 1, 1)
+        self.N_proj = conv(d // 2, 1, 1)
+        self._engine = None
+
+    def forward(self, texts, text_lengths, alignment, style, *, taps=None):
+        self._no_grad_only()
+        return self.engine().forward(texts, text_lengths, alignment, style, taps=taps)
+
+
+class DurationProcessor(nn.Module):
+    """forward(pred, text_length) -> soft alignment (B,T,F); reference utils.py:656-807 (the
+    prediction_to_duration + duration_to_alignment path, coarse multiplier 1)."""
+
+    def __init__(self, class_count=16, max_dur=50):
+        super().__init__()
+        self.class_count, self.max_dur = class_count, max_dur
+
+    def forward(self, pred, text_length, multiplier=1):
+        if multiplier != 1:
+            raise NotImplementedError("stylish_tts_b200: coarse_multiplier != 1 is not built")
+        from .engine import duration_to_alignment
+
+        return duration_to_alignment(pred, text_length)[0]
+
+
+class Synthesizer(nn.Module):
+    """Batched text -> wav graph, the reference's ExportModel.forward (export_model.py:40-63):
+    duration predictor -> alignment -> pitch/energy predictor -> speech predictor."""
+
+    def __init__(self, *, speech_predictor, pitch_energy_predictor, duration_predictor,
+                 class_count=16, max_dur=50):
+        super().__init__()
+        self.speech_predictor = speech_predictor
+        self.pitch_energy_predictor = pitch_energy_predictor
+        self.duration_predictor = duration_predictor
+        self.duration_processor = DurationProcessor(class_count, max_dur)
+
+    @torch.no_grad()
+    def forward(self, texts, text_lengths, speech_style, pe_style, duration_style, *,
+                source_draws=None, return_aux=False):
+        dur_pred = self.duration_predictor(texts, text_lengths, duration_style)
+        alignment = self.duration_processor(dur_pred, text_lengths)
+        pitch, energy = self.pitch_energy_predictor(texts, text_lengths, alignment, pe_style)
+        voiced = (pitch > 20).float()
+        pred = self.speech_predictor(texts, text_lengths, alignment, pitch, energy, voiced,
+                                     speech_style, pitch, source_draws=source_draws)
+        if return_aux:
+            return pred.audio, dict(dur_pred=dur_pred, alignment=alignment, pitch=pitch, energy=energy)
+        return pred.audio
+
+
+HOT_PATH_KEYS = ("speech_predictor", "duration_predictor", "pitch_energy_predictor")
 ALL_KEYS = ("text_aligner", "duration_predictor", "pitch_energy_predictor", "speech_predictor",
             "disc", "mrd0", "mrd1", "mrd2", "speech_style_encoder", "pe_style_encoder",
             "duration_style_encoder", "pitch_disc", "dur_disc")
@@ -343,6 +487,8 @@ def build_model(model_config, *, extra: Dict[str, nn.Module] | None = None) -> M
     when dropped into its train.py); they are passed through untouched.
     """
     nets = ModelSet()
+    nets["duration_predictor"] = DurationPredictor(model_config)
+    nets["pitch_energy_predictor"] = PitchEnergyPredictor(model_config)
     nets["speech_predictor"] = SpeechPredictor(model_config)
     if extra:
         for k, v in extra.items():

@@ -54,6 +54,28 @@ def main():
         np.savez_compressed(path, **blob)
         print(name, {k: v.shape for k, v in blob.items()}, os.path.getsize(path) // 1024, "KiB")
 
+    # duration / pitch-energy predictors (duration_predictor.py, pitch_energy_predictor.py)
+    nets = ref_loader.build_model()
+    dpm, pem = nets.duration_predictor.eval(), nets.pitch_energy_predictor.eval()
+    mine = st.build_model(mc)
+    synth.randomize_(mine.duration_predictor, 6)
+    synth.randomize_(mine.pitch_energy_predictor, 7)
+    dpm.load_state_dict(mine.duration_predictor.state_dict(), strict=True)
+    pem.load_state_dict(mine.pitch_energy_predictor.state_dict(), strict=True)
+    inp = synth.speech_inputs(2, 20, seed=8, ragged=True)
+    sty = torch.randn(2, 64, generator=torch.Generator().manual_seed(9))
+    with torch.no_grad():
+        dpred = dpm(inp["texts"], inp["text_lengths"], sty)
+        pitch, energy = pem(inp["texts"], inp["text_lengths"], inp["alignment"], sty)
+        from stylish_tts.train.utils import DurationProcessor as RefDP
+        rdp = RefDP(16, 50)
+        soft = rdp.prediction_to_duration(dpred, inp["text_lengths"])
+        al = rdp(dpred, inp["text_lengths"])
+    np.savez_compressed(os.path.join(out_dir, "predictors.npz"), dur_pred=dpred.numpy(),
+                        pitch=pitch.numpy(), energy=energy.numpy(), soft_duration=soft.numpy(),
+                        alignment=al.numpy(), style=sty.numpy())
+    print("predictors", tuple(dpred.shape), tuple(pitch.shape), tuple(al.shape))
+
     # alignment golden (DurationProcessor.duration_to_alignment, utils.py:752-791)
     ref_loader.load()
     from stylish_tts.train.utils import DurationProcessor

@@ -1,0 +1,131 @@
+"""GPU parity of the duration predictor, pitch/energy predictor, DurationProcessor and the batched
+text->wav graph (reference ExportModel.forward) against the reference-made golden outputs and the
+CPU oracle."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+import stylish_tts_b200 as st
+from oracle import speech_oracle as so
+from stylish_tts_b200 import _lib as L
+from stylish_tts_b200 import engine as E
+from stylish_tts_b200 import synth
+from tests import util
+from tests.test_oracle_golden import predictor_case
+from tests.util import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def test_duration_predictor_vs_reference_golden():
+    nets, inp, gold = predictor_case()
+    d = dev()
+    dp = nets.duration_predictor.to(d)
+    with torch.no_grad():
+        out = dp(inp["texts"].to(d), inp["text_lengths"].to(d), gold["style"].to(d))
+    assert out.shape == gold["dur_pred"].shape
+    assert rel_l2(out, gold["dur_pred"]) < 1e-4, rel_l2(out, gold["dur_pred"])
+
+
+def test_pitch_energy_predictor_vs_oracle():
+    """fp32 evaluation of these towers is ill-conditioned (reference fp32 vs fp64: 1.4e-4 with the
+    seeded weights): the GPU result must be as close to the fp64 oracle as the reference itself."""
+    nets, inp, gold = predictor_case()
+    d = dev()
+    pe = nets.pitch_energy_predictor.to(d)
+    taps = {}
+    with torch.no_grad():
+        pitch, energy = pe(inp["texts"].to(d), inp["text_lengths"].to(d), inp["alignment"].to(d),
+                           gold["style"].to(d), taps=taps)
+    psd = so.to_dtype(util.state_dict_of(nets.pitch_energy_predictor.cpu()), torch.float64)
+    ot = {}
+    p64, e64 = so.pitch_energy_predictor(psd, inp["texts"], inp["text_lengths"],
+                                         inp["alignment"].double(), gold["style"].double(), taps=ot)
+    assert rel_l2(taps["prosody"], ot["prosody"]) < 1e-4
+    ref_p, ref_e = rel_l2(gold["pitch"], p64), rel_l2(gold["energy"], e64)
+    gp, ge = rel_l2(pitch, p64), rel_l2(energy, e64)
+    print(f"pitch: gpu {gp:.2e} (reference fp32 {ref_p:.2e}); energy: gpu {ge:.2e} (reference fp32 {ref_e:.2e})")
+    assert gp < max(3 * ref_p, 1e-4) and ge < max(3 * ref_e, 1e-4)
+
+
+def test_duration_processor_matches_reference():
+    """soft durations within fp32 rounding, frame count exact, alignment within 1e-6."""
+    nets, inp, gold = predictor_case()
+    d = dev()
+    al, dur = E.duration_to_alignment(gold["dur_pred"].to(d), inp["text_lengths"].to(d))
+    assert al.shape == gold["alignment"].shape  # data-dependent frame count is exact
+    assert rel_l2(dur, gold["soft_duration"]) < 1e-6
+    assert float((al.cpu() - gold["alignment"]).abs().max()) < 2e-6
+    g2 = util.load_golden("alignment")  # integer-like and fractional durations, incl. zeros
+    dur2 = g2["duration"].to(d).contiguous()
+    B, T = dur2.shape
+    Fr = g2["alignment"].shape[2]
+    out = torch.empty(B, T, Fr, device=d)
+    L.call("sty_alignment_fwd", dur2.data_ptr(), out.data_ptr(), B, T, Fr, L.stream_ptr())
+    assert float((out.cpu() - g2["alignment"]).abs().max()) < 2e-6
+    assert float((out.sum(1) - 1).abs().max()) < 1e-5  # columns are distributions over tokens
+
+
+@pytest.mark.parametrize("D,H,T,lens", [(160, 2, 258, [258, 140]), (16, 8, 40, [40, 9]), (64, 4, 100, None)])
+def test_attention_generic(D, H, T, lens):
+    gen = torch.Generator().manual_seed(D + T)
+    B = 2
+    C = H * D
+    qkv = torch.randn(B, 3 * C, T, generator=gen)
+    q, k, v = (so.heads_split(t.contiguous(), H) for t in (qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:]))
+    d_rot = int(D * 0.5)
+    q, k = so.rope(q, d_rot), so.rope(k, d_rot)
+    scores = q @ k.transpose(2, 3) / math.sqrt(D)
+    lengths = None
+    if lens is not None:
+        lengths = torch.tensor(lens)
+        m = so.sequence_mask(lengths, T).float()
+        scores = scores + (1 - m[:, None, :, None] * m[:, None, None, :]) * -1e4
+    ref = (torch.softmax(scores, -1) @ v).transpose(2, 3).reshape(B, C, T)
+    d = dev()
+    c = torch.empty(T, d_rot // 2, device=d)
+    s = torch.empty_like(c)
+    L.call("sty_rope_table", c.data_ptr(), s.data_ptr(), T, d_rot, 10000.0, L.stream_ptr())
+    x = qkv.to(d)
+    out = E.attention_generic(x[:, :C], x[:, C:2 * C], x[:, 2 * C:], H=H, D=D,
+                              lengths=None if lengths is None else lengths.to(d), rope=(c, s, d_rot),
+                              scale=1.0 / math.sqrt(D))
+    assert rel_l2(out, ref) < 5e-5
+
+
+def test_synthesizer_text_to_wav():
+    """ExportModel-equivalent graph, batched: aux tensors vs the CPU oracle, audio sane."""
+    nets = st.build_model(st.default_model_config())
+    for i, k in enumerate(("duration_predictor", "pitch_energy_predictor", "speech_predictor")):
+        synth.randomize_(nets[k], 30 + i)
+    inp = synth.speech_inputs(2, 24, seed=12, ragged=True)
+    g = torch.Generator().manual_seed(13)
+    styles = [torch.randn(2, 64, generator=g) for _ in range(3)]
+    sds = {k: util.state_dict_of(nets[k]) for k in ("duration_predictor", "pitch_energy_predictor",
+                                                    "speech_predictor")}
+    noise = {}
+
+    def draws_fn(frames):
+        noise["n"] = torch.randn(2, frames * 300, 9, generator=g)
+        return {"rand_ini": torch.zeros(2, 9), "noise": noise["n"]}
+
+    ref_audio, aux = so.synthesize(sds, inp["texts"], inp["text_lengths"], styles[0], styles[1], styles[2],
+                                   draws_fn)
+    d = dev()
+    syn = st.Synthesizer(speech_predictor=nets.speech_predictor.to(d),
+                         pitch_energy_predictor=nets.pitch_energy_predictor.to(d),
+                         duration_predictor=nets.duration_predictor.to(d))
+    audio, gaux = syn(inp["texts"].to(d), inp["text_lengths"].to(d), styles[0].to(d), styles[1].to(d),
+                      styles[2].to(d), source_draws={"noise": noise["n"].to(d)}, return_aux=True)
+    assert gaux["alignment"].shape == aux["alignment"].shape
+    assert rel_l2(gaux["dur_pred"], aux["dur_pred"]) < 1e-4
+    assert float((gaux["alignment"].cpu() - aux["alignment"]).abs().max()) < 1e-4
+    assert rel_l2(gaux["pitch"], aux["pitch"]) < 2e-3  # ill-conditioned towers, see above
+    assert audio.shape == ref_audio.shape
+    assert torch.isfinite(audio).all() and float(audio.abs().max()) <= 1.0

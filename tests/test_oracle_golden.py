@@ -106,3 +106,35 @@ def test_oracle_matches_live_reference():
     for k in rt:
         if k in ot and k != "har_phase":
             assert util.rel_l2(ot[k], rt[k]) < TOL, k
+
+
+def predictor_case():
+    import stylish_tts_b200 as st
+    from stylish_tts_b200 import synth
+
+    gold = util.load_golden("predictors")
+    nets = st.build_model(st.default_model_config())
+    synth.randomize_(nets.duration_predictor, 6)
+    synth.randomize_(nets.pitch_energy_predictor, 7)
+    inp = synth.speech_inputs(2, 20, seed=8, ragged=True)
+    return nets, inp, gold
+
+
+def test_predictor_oracles_match_golden():
+    """duration predictor / pitch-energy predictor / DurationProcessor oracle vs the reference's outputs."""
+    nets, inp, gold = predictor_case()
+    sty = gold["style"]
+    dsd = util.state_dict_of(nets.duration_predictor)
+    psd = util.state_dict_of(nets.pitch_energy_predictor)
+    dpred = so.duration_predictor(dsd, inp["texts"], inp["text_lengths"], sty)
+    assert util.rel_l2(dpred, gold["dur_pred"]) < TOL
+    soft = so.prediction_to_duration(gold["dur_pred"], inp["text_lengths"])
+    assert torch.equal(soft, gold["soft_duration"])
+    assert torch.equal(so.duration_to_alignment(soft), gold["alignment"])
+    # the pitch/energy towers are ill-conditioned in fp32 with random weights (fp32 reference vs
+    # fp64 reference differ by 1.4e-4): judge the oracle in fp64 against that noise floor
+    p64, e64 = so.pitch_energy_predictor(so.to_dtype(psd, torch.float64), inp["texts"],
+                                         inp["text_lengths"], inp["alignment"].double(), sty.double())
+    assert util.rel_l2(gold["pitch"], p64) < 5e-4 and util.rel_l2(gold["energy"], e64) < 5e-4
+    p32, e32 = so.pitch_energy_predictor(psd, inp["texts"], inp["text_lengths"], inp["alignment"], sty)
+    assert util.rel_l2(p32, p64) < 5e-4 and util.rel_l2(e32, e64) < 5e-4
