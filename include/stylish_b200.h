@@ -104,6 +104,14 @@ typedef struct sty_conv1d_args {
    * pre-split into bf16 (hi, lo) in the UMMA K-major layout [K][2][CI/8][CO][8].
    * NULL selects the fp32 FMA kernel.  Used when CI%16==0, CO%16==0 and T>=128. */
   const void* w_split;
+  /* Optional fused ConvNeXt front (tensor-core path, K == 1, CI <= 64): the conv input is
+   * y = (1+gamma[b,c]) * LayerNorm_C(dwconv7(x) + dw_b)[c] + beta[b,c]   (conv_next.py:82-84)
+   * dw_w (CI,7), dw_b (CI), gamma = dw_gb[b*dw_gb_bs + c], beta = dw_gb[b*dw_gb_bs + CI + c]. */
+  const float* dw_w;
+  const float* dw_b;
+  const float* dw_gb;
+  int64_t dw_gb_bs;
+  float dw_eps;
 } sty_conv1d_args;
 STY_API int sty_conv1d_fwd(const sty_conv1d_args* a, sty_stream_t stream);
 

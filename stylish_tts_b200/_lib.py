@@ -39,6 +39,7 @@ class ConvArgs(C.Structure):
         ("in_act", _i32), ("out_act", _i32), ("shuffle", _i32),
         ("out_scale", _f32), ("res_scale", _f32),
         ("w_split", _f32p),
+        ("dw_w", _f32p), ("dw_b", _f32p), ("dw_gb", _f32p), ("dw_gb_bs", _i64), ("dw_eps", _f32),
     ]
 
 
@@ -150,6 +151,8 @@ def _signature(name: str, args) -> str:
             extra += f"+shuf{a.shuffle}"
         if a.w_split:
             extra += "+umma"
+        if a.dw_w:
+            extra += "+dwln"
         return f"conv1d[ci={a.CI},co={a.CO},k={a.K},d={a.dil},B={a.B},T={a.T}{extra}]"
     pos = {"sty_dwconv_ln_fwd": (9, 10), "sty_chan_layernorm_fwd": (11, 12),
            "sty_instnorm_affine_fwd": (8, 9), "sty_attention_fwd": (12, 13)}.get(name)

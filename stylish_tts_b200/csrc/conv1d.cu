@@ -287,6 +287,8 @@ extern "C" int sty_conv1d_fwd(const sty_conv1d_args* a, sty_stream_t stream) {
   STY_REQUIRE(a->shuffle <= 1 || a->out_sumsq == nullptr, "conv1d: sumsq with shuffle unsupported");
   cudaStream_t st = as_stream(stream);
   if (conv1d_umma_eligible(*a)) return conv1d_umma_launch(*a, st);
+  STY_REQUIRE(a->dw_w == nullptr, "conv1d: the fused ConvNeXt front needs the tensor-core path "
+                                  "(K=1, CI<=64, CI,CO %% 16 == 0, T>=128, w_split set)");
   switch (pick_config(*a)) {
     case 0: return launch_p<128, 128, 8, 8>(*a, st);
     case 1: return launch_p<64, 128, 8, 8>(*a, st);

@@ -170,6 +170,7 @@ struct UmmaPlan {
   int wres_u4;     // uint4 of the resident weight block (0 when streaming)
   int tiles_per_b; // ceil(T / 128)
   int prm_floats;  // floats of the per-channel parameter block (prologue + epilogue)
+  int dw_floats;   // IN_MODE 4: raw input tile [CI][134+1] + LN partial sums [2][128]
 };
 
 constexpr int kProducerWarps = 8;
@@ -197,12 +198,13 @@ __device__ __forceinline__ float warp_colsum16(float (&v)[16], int lane) {
 }
 
 // IN_MODE : 0 no prologue | 1 mask/affine | 2 mask/affine + LeakyReLU(0.2) | 3 mask/affine + Snake
+//           4 ConvNeXt front: depthwise k7 conv + LayerNorm over channels + adaptive affine (K=1 only)
 // OUT_MODE: 0 none | 1 Snake | 2 ReLU | 3 Swish          (compile-time: keeps each role's loop small
 // enough for the instruction cache — three roles run different code on one SM)
 template <int IN_MODE, int OUT_MODE>
 __global__ void __launch_bounds__(kThreads, 1)
 conv1d_umma_kernel(const sty_conv1d_args p, const UmmaPlan pl) {
-  constexpr bool PRO = IN_MODE != 0;
+  constexpr bool PRO = IN_MODE >= 1 && IN_MODE <= 3;
   constexpr int MT = 128;
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const int K = p.K, dil = p.dil, CO = p.CO, CI = p.CI, NT = pl.NT, rows = pl.rows;
@@ -213,8 +215,9 @@ conv1d_umma_kernel(const sty_conv1d_args p, const UmmaPlan pl) {
   uint4* stage0 = Wres + pl.wres_u4;                       // stage: X [2][c8c][rows] (+ W [K][2][c8c][NT])
   float* prm = reinterpret_cast<float*>(stage0 + (size_t)NS * pl.stage_u4);
   float* pro_s = prm;                // [4][CI]: scale, shift, alpha, 1/alpha of the current batch element
-  float* epi_s = prm + 4 * CI;       // [3][NT]: bias, alpha, 1/alpha
-  uint64_t* bars = reinterpret_cast<uint64_t*>(prm + pl.prm_floats);
+  float* epi_s = prm + (IN_MODE == 4 ? 10 : 4) * CI;  // [3][NT]: bias, alpha, 1/alpha
+  float* dw_s = prm + pl.prm_floats;  // IN_MODE 4 scratch
+  uint64_t* bars = reinterpret_cast<uint64_t*>(dw_s + pl.dw_floats);
   uint64_t* x_full = bars;
   uint64_t* x_empty = bars + kMaxStages;
   uint64_t* acc_full = bars + 2 * kMaxStages;
@@ -281,6 +284,91 @@ conv1d_umma_kernel(const sty_conv1d_args p, const UmmaPlan pl) {
         asm volatile("bar.sync 2, %0;" ::"n"(kProducerThreads) : "memory");
         cur_b = b;
       }
+      if constexpr (IN_MODE == 4) {
+        // ---- ConvNeXt front (conv_next.py:82-84): y = (1+g) * LN_C(dwconv7(x) + b) + beta, computed
+        // from a raw fp32 tile staged once; thread (row, half) owns CI/2 channels of one time step
+        constexpr int RP = 128 + 6 + 1;  // raw row pitch
+        float* raw = dw_s;               // [CI][RP]
+        float* red = dw_s + CI * RP;     // [2][128]
+        float* dwp = pro_s;              // [CI][8] taps+bias, then gamma[CI], beta[CI]
+        if (b != cur_b) {
+          asm volatile("bar.sync 2, %0;" ::"n"(kProducerThreads) : "memory");
+          for (int i = tid; i < CI * 8; i += kProducerThreads) {
+            const int c = i >> 3, k = i & 7;
+            dwp[i] = k < 7 ? p.dw_w[c * 7 + k] : p.dw_b[c];
+          }
+          for (int c = tid; c < 2 * CI; c += kProducerThreads)
+            dwp[CI * 8 + c] = p.dw_gb[(int64_t)b * p.dw_gb_bs + c];
+          cur_b = b;
+        }
+        const int s = it % NS;
+        mbar_wait_sleep(&x_empty[s], ((it / NS) & 1) ^ 1);
+        uint4* Xs = stage0 + (size_t)s * pl.stage_u4;
+        asm volatile("bar.sync 2, %0;" ::"n"(kProducerThreads) : "memory");  // raw/red free, params visible
+        for (int idx = tid; idx < CI * 134; idx += kProducerThreads) {
+          const int c = idx / 134, j = idx - c * 134;
+          const int t = t0 - 3 + j;
+          raw[c * RP + j] = (t >= 0 && t < p.T) ? xb[(int64_t)c * p.x_cs + t] : 0.f;
+        }
+        asm volatile("bar.sync 2, %0;" ::"n"(kProducerThreads) : "memory");
+        const int r = tid & 127, hf = tid >> 7;
+        const int ch2 = CI >> 1;  // channels per thread (<= 32)
+        float d[32];
+        float sum = 0.f;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float a = 0.f;
+          if (i < ch2) {
+            const int c = hf * ch2 + i;
+            const float* wr = dwp + c * 8;
+            const float* xr = raw + c * RP + r;
+            a = wr[7];
+#pragma unroll
+            for (int k = 0; k < 7; ++k) a = fmaf(wr[k], xr[k], a);
+          }
+          d[i] = a;
+          sum += a;
+        }
+        red[hf * 128 + r] = sum;
+        asm volatile("bar.sync 2, %0;" ::"n"(kProducerThreads) : "memory");
+        const float mean = (red[r] + red[128 + r]) / (float)CI;
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float e = (i < ch2) ? d[i] - mean : 0.f;
+          q = fmaf(e, e, q);
+        }
+        asm volatile("bar.sync 2, %0;" ::"n"(kProducerThreads) : "memory");
+        red[hf * 128 + r] = q;
+        asm volatile("bar.sync 2, %0;" ::"n"(kProducerThreads) : "memory");
+        const float rstd = 1.0f / sqrtf((red[r] + red[128 + r]) / (float)CI + p.dw_eps);
+        const bool ok = (t0 + r) < p.T;
+#pragma unroll
+        for (int g8 = 0; g8 < 4; ++g8) {
+          if (g8 * 8 < ch2) {
+            uint32_t h[4], l[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float a[2];
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const int i = g8 * 8 + 2 * j + e;
+                const int c = hf * ch2 + i;
+                const float y = (1.0f + dwp[CI * 8 + c]) * ((d[i] - mean) * rstd) + dwp[CI * 9 + c];
+                a[e] = ok ? y : 0.f;
+              }
+              h[j] = pack_bf16(a[0], a[1]);
+              l[j] = pack_bf16(a[0] - __uint_as_float(h[j] << 16), a[1] - __uint_as_float(h[j] & 0xffff0000u));
+            }
+            const int c8 = (hf * ch2 >> 3) + g8;
+            Xs[(0 * c8c + c8) * rows + r] = make_uint4(h[0], h[1], h[2], h[3]);
+            Xs[(1 * c8c + c8) * rows + r] = make_uint4(l[0], l[1], l[2], l[3]);
+          }
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(&x_full[s]);
+        ++it;
+      } else
       for (int ch = 0; ch < pl.n_chunks; ++ch, ++it) {
         const int c0 = ch * pl.ci_chunk;
         const int cc8 = min(pl.ci_chunk, CI - c0) >> 3;
@@ -532,9 +620,10 @@ static bool make_plan(const sty_conv1d_args& a, UmmaPlan& pl) {
     pl.NT = nt;
     pl.acc_cols = 32;
     while (pl.acc_cols < nt) pl.acc_cols <<= 1;
-    pl.prm_floats = 4 * a.CI + 3 * nt;
+    pl.prm_floats = (a.dw_w ? 10 : 4) * a.CI + 3 * nt;
     pl.prm_floats = (pl.prm_floats + 3) & ~3;
-    const size_t misc = kSmemBars + (size_t)pl.prm_floats * 4;
+    pl.dw_floats = a.dw_w ? ((a.CI * 135 + 256 + 3) & ~3) : 0;
+    const size_t misc = kSmemBars + (size_t)(pl.prm_floats + pl.dw_floats) * 4;
     const size_t w_all = (size_t)a.K * a.CI * nt * 4;
     const size_t x_all = (size_t)a.CI * pl.rows * 4;
     if (w_all + 2 * x_all + misc <= kSmemBudget) {  // weights resident, >= 2 input stages
@@ -566,6 +655,11 @@ static bool make_plan(const sty_conv1d_args& a, UmmaPlan& pl) {
 }
 
 static int umma_in_mode(const sty_conv1d_args& a) {
+  if (a.dw_w) {  // fused ConvNeXt front: pointwise conv only, nothing else in the prologue
+    const bool ok = a.K == 1 && a.CI <= 64 && a.CI % 16 == 0 && a.dw_b && a.dw_gb &&
+                    a.in_act == STY_ACT_NONE && !a.in_scale && !a.in_shift && !a.in_mask;
+    return ok ? 4 : -1;
+  }
   if (a.in_act == STY_ACT_SNAKE) return 3;
   if (a.in_act == STY_ACT_LEAKY02) return 2;
   if (a.in_act != STY_ACT_NONE) return -1;
@@ -600,13 +694,14 @@ int conv1d_umma_launch(const sty_conv1d_args& a, cudaStream_t st) {
     if (sms <= 0) sms = 148;
   }
   const size_t smem = (size_t)pl.wres_u4 * 16 + (size_t)pl.n_stages * pl.stage_u4 * 16 +
-                      (size_t)pl.prm_floats * 4 + kSmemBars;
+                      (size_t)(pl.prm_floats + pl.dw_floats) * 4 + kSmemBars;
   using KernPtr = void (*)(const sty_conv1d_args, const UmmaPlan);
-  static const KernPtr table[4][4] = {
+  static const KernPtr table[5][4] = {
       {conv1d_umma_kernel<0, 0>, conv1d_umma_kernel<0, 1>, conv1d_umma_kernel<0, 2>, conv1d_umma_kernel<0, 3>},
       {conv1d_umma_kernel<1, 0>, conv1d_umma_kernel<1, 1>, conv1d_umma_kernel<1, 2>, conv1d_umma_kernel<1, 3>},
       {conv1d_umma_kernel<2, 0>, conv1d_umma_kernel<2, 1>, conv1d_umma_kernel<2, 2>, conv1d_umma_kernel<2, 3>},
-      {conv1d_umma_kernel<3, 0>, conv1d_umma_kernel<3, 1>, conv1d_umma_kernel<3, 2>, conv1d_umma_kernel<3, 3>}};
+      {conv1d_umma_kernel<3, 0>, conv1d_umma_kernel<3, 1>, conv1d_umma_kernel<3, 2>, conv1d_umma_kernel<3, 3>},
+      {conv1d_umma_kernel<4, 0>, conv1d_umma_kernel<4, 1>, conv1d_umma_kernel<4, 2>, conv1d_umma_kernel<4, 3>}};
   KernPtr kern = table[umma_in_mode(a)][umma_out_mode(a)];
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const int64_t n_tiles = (int64_t)a.B * pl.tiles_per_b;

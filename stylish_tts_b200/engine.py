@@ -56,7 +56,8 @@ class ConvW:
 
 def conv1d(x, cw: ConvW, *, dil=1, out=None, res=None, in_scale=None, in_shift=None,
            in_alpha=None, in_act=ACT_NONE, in_mask=None, out_mask=None, out_act=ACT_NONE,
-           out_alpha=None, out_sumsq=None, shuffle=0, out_scale=1.0, res_scale=1.0, umma=True):
+           out_alpha=None, out_sumsq=None, shuffle=0, out_scale=1.0, res_scale=1.0, umma=True,
+           dwln=None):
     B, CI, T = x.shape
     assert CI == cw.CI, (CI, cw.CI)
     x_bs, x_cs = L._bct(x, "x")
@@ -83,6 +84,10 @@ def conv1d(x, cw: ConvW, *, dil=1, out=None, res=None, in_scale=None, in_shift=N
     a.out_scale, a.res_scale = out_scale, res_scale
     if umma and USE_UMMA and cw.split is not None and T >= UMMA_MIN_T:
         a.w_split = cw.split.data_ptr()
+    if dwln is not None:  # fused ConvNeXt front (dw_w, dw_b, gamma|beta rows, row stride, eps)
+        assert a.w_split, "fused ConvNeXt front needs the tensor-core path"
+        a.dw_w, a.dw_b, a.dw_gb = dwln[0].data_ptr(), dwln[1].data_ptr(), dwln[2].data_ptr()
+        a.dw_gb_bs, a.dw_eps = dwln[3], dwln[4]
     L.call("sty_conv1d_fwd", C.byref(a), L.stream_ptr())
     return out
 
@@ -453,13 +458,19 @@ class SpeechEngine:
         B, Cc, T = x.shape
         J = P.fc_rows
         gb = self._gb(P, h, blk["norm"])
-        y = torch.empty((B, Cc, T), device=x.device, dtype=torch.float32)
-        L.call("sty_dwconv_ln_fwd", x.data_ptr(), x.stride(0), blk["dw_w"].data_ptr(),
-               blk["dw_b"].data_ptr(), gb.data_ptr(), J, y.data_ptr(), y.stride(0), B, Cc, T, 1e-6,
-               L.stream_ptr())
         inter = blk["pw1"].CO
         sumsq = torch.zeros((B, inter), device=x.device, dtype=torch.float32)
-        hb = conv1d(y, blk["pw1"], out_act=ACT_SNAKE, out_alpha=blk["snake"], out_sumsq=sumsq)
+        fused_front = (USE_UMMA and blk["pw1"].split is not None and Cc <= 64 and Cc % 16 == 0
+                       and T >= UMMA_MIN_T and x.stride(1) == T)
+        if fused_front:  # depthwise k7 + LN + AdaLN computed by the pointwise conv's producer warps
+            hb = conv1d(x, blk["pw1"], out_act=ACT_SNAKE, out_alpha=blk["snake"], out_sumsq=sumsq,
+                        dwln=(blk["dw_w"], blk["dw_b"], gb, J, 1e-6))
+        else:
+            y = torch.empty((B, Cc, T), device=x.device, dtype=torch.float32)
+            L.call("sty_dwconv_ln_fwd", x.data_ptr(), x.stride(0), blk["dw_w"].data_ptr(),
+                   blk["dw_b"].data_ptr(), gb.data_ptr(), J, y.data_ptr(), y.stride(0), B, Cc, T, 1e-6,
+                   L.stream_ptr())
+            hb = conv1d(y, blk["pw1"], out_act=ACT_SNAKE, out_alpha=blk["snake"], out_sumsq=sumsq)
         gs = torch.empty_like(sumsq)
         L.call("sty_grn_scale_fwd", sumsq.data_ptr(), blk["grn_gamma"].data_ptr(), gs.data_ptr(), B,
                inter, L.stream_ptr())

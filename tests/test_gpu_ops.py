@@ -341,3 +341,31 @@ def test_conv1d_tensor_core_fused_ops():
     ref2 = so.pixel_shuffle_1d(F.conv1d(x.double(), w2.double(), b2.double(), padding=5), 5)
     out2 = E.conv1d(x.to(d), E.ConvW(w2.to(d), b2.to(d)), shuffle=5)
     assert rel_l2(out2, ref2) < 3e-5
+
+
+@pytest.mark.parametrize("Cc,T", [(32, 1000), (64, 700)])
+def test_convnext_front_fused_into_pointwise_conv(Cc, T):
+    """depthwise k7 + LayerNorm + adaptive affine computed by the tcgen05 conv's producer warps,
+    then pwconv1 + Snake + GRN sums (conv_next.py:82-86), on a strided input view."""
+    gen = g(Cc + 5)
+    B, inter = 2, 4 * Cc
+    big = torch.randn(B, Cc + 16, T, generator=gen)
+    x = big[:, :Cc]
+    dw_w = torch.randn(Cc, 1, 7, generator=gen) * 0.4
+    dw_b = torch.randn(Cc, generator=gen) * 0.1
+    gb = torch.randn(B, 2 * Cc + 4, generator=gen) * 0.3
+    w1 = torch.randn(inter, Cc, generator=gen) / math.sqrt(Cc)
+    b1 = torch.randn(inter, generator=gen) * 0.1
+    al = 0.75 + 0.5 * torch.rand(inter, generator=gen)
+    d = F.conv1d(x.double(), dw_w.double(), dw_b.double(), padding=3, groups=Cc).transpose(1, 2)
+    y = (1 + gb[:, None, :Cc].double()) * F.layer_norm(d, (Cc,), eps=1e-6) + gb[:, None, Cc:2 * Cc].double()
+    h = so.snake(F.linear(y, w1.double(), b1.double()), al.view(1, 1, -1).double()).transpose(1, 2)
+    dv = dev()
+    bigd, gbd = big.to(dv), gb.to(dv)
+    ssq = torch.zeros(B, inter, device=dv)
+    cw = E.ConvW(w1.unsqueeze(-1).to(dv), b1.to(dv))
+    dww, dwb, ald = dw_w.reshape(Cc, 7).contiguous().to(dv), dw_b.to(dv), al.to(dv)
+    hb = E.conv1d(bigd[:, :Cc], cw, out_act=L.ACT_SNAKE, out_alpha=ald, out_sumsq=ssq,
+                  dwln=(dww, dwb, gbd, gb.shape[1], 1e-6))
+    assert rel_l2(hb, h) < 3e-5
+    assert rel_l2(ssq, (h ** 2).sum(2)) < 3e-5
