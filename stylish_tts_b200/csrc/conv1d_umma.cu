@@ -170,7 +170,7 @@ struct UmmaPlan {
   int wres_u4;     // uint4 of the resident weight block (0 when streaming)
   int tiles_per_b; // ceil(T / 128)
   int prm_floats;  // floats of the per-channel parameter block (prologue + epilogue)
-  int dw_floats;   // IN_MODE 4: raw input tile [CI][134+1] + LN partial sums [2][128]
+  int dw_floats;   // IN_MODE 4: two raw input tiles [2][CI][134+1]
 };
 
 constexpr int kProducerWarps = 8;
@@ -230,7 +230,7 @@ conv1d_umma_kernel(const sty_conv1d_args p, const UmmaPlan pl) {
   if (warp == kMmaWarp) tmem_alloc(tmem_slot, (uint32_t)(2 * pl.acc_cols));
   if (tid == 0) {
     for (int i = 0; i < NS; ++i) {
-      mbar_init(&x_full[i], kProducerThreads);
+      mbar_init(&x_full[i], IN_MODE == 4 ? 128 : kProducerThreads);
       mbar_init(&x_empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
@@ -285,12 +285,13 @@ conv1d_umma_kernel(const sty_conv1d_args p, const UmmaPlan pl) {
         cur_b = b;
       }
       if constexpr (IN_MODE == 4) {
-        // ---- ConvNeXt front (conv_next.py:82-84): y = (1+g) * LN_C(dwconv7(x) + b) + beta, computed
-        // from a raw fp32 tile staged once; thread (row, half) owns CI/2 channels of one time step
+        // ---- ConvNeXt front (conv_next.py:82-84): y = (1+g) * LN_C(dwconv7(x) + b) + beta.
+        // Two producer groups of 128 threads take alternate tiles (two tiles in flight); a thread
+        // owns one time step with ALL channels, so LayerNorm needs no cross-thread exchange.
         constexpr int RP = 128 + 6 + 1;  // raw row pitch
-        float* raw = dw_s;               // [CI][RP]
-        float* red = dw_s + CI * RP;     // [2][128]
-        float* dwp = pro_s;              // [CI][8] taps+bias, then gamma[CI], beta[CI]
+        const int grp = tid >> 7, r = tid & 127;
+        float* raw = dw_s + grp * (CI * RP);  // [CI][RP] raw fp32 tile of this group
+        float* dwp = pro_s;                    // [CI][8] taps+bias, then gamma[CI], beta[CI]
         if (b != cur_b) {
           asm volatile("bar.sync 2, %0;" ::"n"(kProducerThreads) : "memory");
           for (int i = tid; i < CI * 8; i += kProducerThreads) {
@@ -299,74 +300,113 @@ conv1d_umma_kernel(const sty_conv1d_args p, const UmmaPlan pl) {
           }
           for (int c = tid; c < 2 * CI; c += kProducerThreads)
             dwp[CI * 8 + c] = p.dw_gb[(int64_t)b * p.dw_gb_bs + c];
+          asm volatile("bar.sync 2, %0;" ::"n"(kProducerThreads) : "memory");
           cur_b = b;
         }
-        const int s = it % NS;
-        mbar_wait_sleep(&x_empty[s], ((it / NS) & 1) ^ 1);
-        uint4* Xs = stage0 + (size_t)s * pl.stage_u4;
-        asm volatile("bar.sync 2, %0;" ::"n"(kProducerThreads) : "memory");  // raw/red free, params visible
-        for (int idx = tid; idx < CI * 134; idx += kProducerThreads) {
-          const int c = idx / 134, j = idx - c * 134;
-          const int t = t0 - 3 + j;
-          raw[c * RP + j] = (t >= 0 && t < p.T) ? xb[(int64_t)c * p.x_cs + t] : 0.f;
-        }
-        asm volatile("bar.sync 2, %0;" ::"n"(kProducerThreads) : "memory");
-        const int r = tid & 127, hf = tid >> 7;
-        const int ch2 = CI >> 1;  // channels per thread (<= 32)
-        float d[32];
-        float sum = 0.f;
+        if ((it & 1) == (uint32_t)grp) {
+          const int s = it % NS;
+          mbar_wait_sleep(&x_empty[s], ((it / NS) & 1) ^ 1);
+          uint4* Xs = stage0 + (size_t)s * pl.stage_u4;
+          // group-local barrier (ids 3, 4): previous tile's readers of `raw` are done
+          if (grp == 0) asm volatile("bar.sync 3, 128;" ::: "memory");
+          else asm volatile("bar.sync 4, 128;" ::: "memory");
+          {
+            const int ta = t0 - 3 + r, tb = ta + 128;
+            const bool oka = ta >= 0 && ta < p.T, okb = (r < 6) && tb >= 0 && tb < p.T;
+            // 32 independent loads in flight per thread before the first store (latency-bound otherwise)
+            for (int cb = 0; cb < CI; cb += 32) {
+              float va[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float a = 0.f;
-          if (i < ch2) {
-            const int c = hf * ch2 + i;
+              for (int u = 0; u < 32; ++u)
+                va[u] = (oka && cb + u < CI) ? xb[(int64_t)(cb + u) * p.x_cs + ta] : 0.f;
+#pragma unroll
+              for (int u = 0; u < 32; ++u)
+                if (cb + u < CI) raw[(cb + u) * RP + r] = va[u];
+            }
+            if (r < 6) {
+              for (int cb = 0; cb < CI; cb += 16) {
+                float vb[16];
+#pragma unroll
+                for (int u = 0; u < 16; ++u)
+                  vb[u] = (okb && cb + u < CI) ? xb[(int64_t)(cb + u) * p.x_cs + tb] : 0.f;
+#pragma unroll
+                for (int u = 0; u < 16; ++u)
+                  if (cb + u < CI) raw[(cb + u) * RP + 128 + r] = vb[u];
+              }
+            }
+          }
+          if (grp == 0) asm volatile("bar.sync 3, 128;" ::: "memory");
+          else asm volatile("bar.sync 4, 128;" ::: "memory");
+          auto dwc = [&](int c) {
             const float* wr = dwp + c * 8;
             const float* xr = raw + c * RP + r;
-            a = wr[7];
+            float a = wr[7];
 #pragma unroll
             for (int k = 0; k < 7; ++k) a = fmaf(wr[k], xr[k], a);
-          }
-          d[i] = a;
-          sum += a;
-        }
-        red[hf * 128 + r] = sum;
-        asm volatile("bar.sync 2, %0;" ::"n"(kProducerThreads) : "memory");
-        const float mean = (red[r] + red[128 + r]) / (float)CI;
-        float q = 0.f;
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float e = (i < ch2) ? d[i] - mean : 0.f;
-          q = fmaf(e, e, q);
-        }
-        asm volatile("bar.sync 2, %0;" ::"n"(kProducerThreads) : "memory");
-        red[hf * 128 + r] = q;
-        asm volatile("bar.sync 2, %0;" ::"n"(kProducerThreads) : "memory");
-        const float rstd = 1.0f / sqrtf((red[r] + red[128 + r]) / (float)CI + p.dw_eps);
-        const bool ok = (t0 + r) < p.T;
-#pragma unroll
-        for (int g8 = 0; g8 < 4; ++g8) {
-          if (g8 * 8 < ch2) {
+            return a;
+          };
+          const bool ok = (t0 + r) < p.T;
+          const float invC = 1.0f / (float)CI;
+          auto emit = [&](int c8, const float* y8) {
             uint32_t h[4], l[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              float a[2];
-#pragma unroll
-              for (int e = 0; e < 2; ++e) {
-                const int i = g8 * 8 + 2 * j + e;
-                const int c = hf * ch2 + i;
-                const float y = (1.0f + dwp[CI * 8 + c]) * ((d[i] - mean) * rstd) + dwp[CI * 9 + c];
-                a[e] = ok ? y : 0.f;
-              }
-              h[j] = pack_bf16(a[0], a[1]);
-              l[j] = pack_bf16(a[0] - __uint_as_float(h[j] << 16), a[1] - __uint_as_float(h[j] & 0xffff0000u));
+              const float a0 = ok ? y8[2 * j] : 0.f, a1 = ok ? y8[2 * j + 1] : 0.f;
+              h[j] = pack_bf16(a0, a1);
+              l[j] = pack_bf16(a0 - __uint_as_float(h[j] << 16), a1 - __uint_as_float(h[j] & 0xffff0000u));
             }
-            const int c8 = (hf * ch2 >> 3) + g8;
             Xs[(0 * c8c + c8) * rows + r] = make_uint4(h[0], h[1], h[2], h[3]);
             Xs[(1 * c8c + c8) * rows + r] = make_uint4(l[0], l[1], l[2], l[3]);
+          };
+          if (CI == 32) {  // whole column in registers
+            float d[32];
+            float sum = 0.f;
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+              d[c] = dwc(c);
+              sum += d[c];
+            }
+            const float mean = sum * invC;
+            float q = 0.f;
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+              const float e = d[c] - mean;
+              q = fmaf(e, e, q);
+            }
+            const float rstd = 1.0f / sqrtf(q * invC + p.dw_eps);
+#pragma unroll
+            for (int c8 = 0; c8 < 4; ++c8) {
+              float y8[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const int c = c8 * 8 + j;
+                y8[j] = (1.0f + dwp[CI * 8 + c]) * ((d[c] - mean) * rstd) + dwp[CI * 9 + c];
+              }
+              emit(c8, y8);
+            }
+          } else {  // recompute the cheap depthwise conv per pass instead of holding CI values
+            float sum = 0.f;
+            for (int c = 0; c < CI; ++c) sum += dwc(c);
+            const float mean = sum * invC;
+            float q = 0.f;
+            for (int c = 0; c < CI; ++c) {
+              const float e = dwc(c) - mean;
+              q = fmaf(e, e, q);
+            }
+            const float rstd = 1.0f / sqrtf(q * invC + p.dw_eps);
+            for (int c8 = 0; c8 < (CI >> 3); ++c8) {
+              float y8[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const int c = c8 * 8 + j;
+                y8[j] = (1.0f + dwp[CI * 8 + c]) * ((dwc(c) - mean) * rstd) + dwp[CI * 9 + c];
+              }
+              emit(c8, y8);
+            }
           }
+          fence_proxy_async_smem();
+          mbar_arrive(&x_full[s]);
         }
-        fence_proxy_async_smem();
-        mbar_arrive(&x_full[s]);
         ++it;
       } else
       for (int ch = 0; ch < pl.n_chunks; ++ch, ++it) {
@@ -622,7 +662,7 @@ static bool make_plan(const sty_conv1d_args& a, UmmaPlan& pl) {
     while (pl.acc_cols < nt) pl.acc_cols <<= 1;
     pl.prm_floats = (a.dw_w ? 10 : 4) * a.CI + 3 * nt;
     pl.prm_floats = (pl.prm_floats + 3) & ~3;
-    pl.dw_floats = a.dw_w ? ((a.CI * 135 + 256 + 3) & ~3) : 0;
+    pl.dw_floats = a.dw_w ? ((2 * a.CI * 135 + 3) & ~3) : 0;
     const size_t misc = kSmemBars + (size_t)(pl.prm_floats + pl.dw_floats) * 4;
     const size_t w_all = (size_t)a.K * a.CI * nt * 4;
     const size_t x_all = (size_t)a.CI * pl.rows * 4;

@@ -15,7 +15,7 @@ B, S = 16, 60225
 d = torch.device("cuda:0")
 
 
-def conv_case(ci, co, k, dil=1, T=S, pro=None, out_act=0, ssq=False, res=False, shuffle=0):
+def conv_case(ci, co, k, dil=1, T=S, pro=None, out_act=0, ssq=False, res=False, shuffle=0, dwln=False):
     x = torch.randn(B, ci, T, device=d)
     w = E.ConvW(torch.randn(co, ci, k, device=d) / math.sqrt(ci * k), torch.randn(co, device=d))
     kw = {}
@@ -32,6 +32,9 @@ def conv_case(ci, co, k, dil=1, T=S, pro=None, out_act=0, ssq=False, res=False, 
         kw["out_alpha"] = torch.rand(co, device=d) + 0.5
     if ssq:
         kw["out_sumsq"] = torch.zeros(B, co, device=d)
+    if dwln:
+        kw["dwln"] = (torch.randn(ci, 7, device=d) * 0.3, torch.randn(ci, device=d) * 0.1,
+                      torch.randn(B, 2 * ci, device=d) * 0.3, 2 * ci, 1e-6)
     s = shuffle if shuffle > 1 else 1
     out = torch.empty(B, co // s, T * s, device=d)
     if res:
@@ -43,6 +46,7 @@ def conv_case(ci, co, k, dil=1, T=S, pro=None, out_act=0, ssq=False, res=False, 
 
 CASES = {
     "pw1": lambda: conv_case(32, 128, 1, out_act=L.ACT_SNAKE, ssq=True),
+    "pw1dw": lambda: conv_case(32, 128, 1, out_act=L.ACT_SNAKE, ssq=True, dwln=True),
     "pw2": lambda: conv_case(128, 32, 1, pro="scale", res=True),
     "pw2_plain": lambda: conv_case(128, 32, 1),
     "k21": lambda: conv_case(32, 32, 21),
