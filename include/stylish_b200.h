@@ -267,6 +267,73 @@ STY_API int sty_istft_head_fwd(const float* logamp, int64_t logamp_bs, const flo
                                const float* basis_im, float* out, int B, int S, int bins, int n_fft,
                                int hop, sty_stream_t stream);
 
+/* ---- framed real FFT front-end: STFT -> |X| / phase / mel / log, one kernel -------------------
+ * torch.stft(center=True, pad_mode="reflect", onesided) semantics: frame f covers samples
+ * [f*hop - n_fft/2, f*hop + n_fft/2) of the reflect-padded signal, times `window` (n_fft floats,
+ * a shorter win_length already zero-padded to the centre as torch.stft does).
+ *   mag   (B, K, n_frames), K = n_fft/2+1 : |X|^power                         (may be NULL)
+ *   phase (B, K, n_frames)               : (|X| > phase_floor) * atan2(Im, Re) (may be NULL)
+ *   mel   (B, n_mels, n_frames)          : post( sum_k fb[k,m] |X[k]|^power )  (may be NULL)
+ *     mel_mode 0: raw   1: log1p(.)   2: (log(mel_eps + .) - mel_mean) / mel_std
+ * The filterbank is sparse (triangles): filter m covers bins [fb_start[m], fb_start[m]+fb_len[m])
+ * with weights fb_w[fb_off[m] ...]; `fbt_*` is the same matrix in CSR form by bin (backward only).
+ * `twiddle`: n_fft/2 complex values exp(-2 pi i q / n_fft) as interleaved floats.
+ * Replaces torchaudio MelSpectrogram + calculate_mel (train_context.py:155-169, utils.py:825-834)
+ * and MultiSpectrogram.calculate_single (multi_spectrogram.py:40-55: torch.stft, abs, masked
+ * angle, MelScale, log1p).  The backward accumulates into d_audio (which the caller zeroes):
+ * d_audio[b, l] += d(mel)/d(audio) . d_mel + d(phase)/d(audio) . d_phase + d(mag)/d(audio) . d_mag. */
+typedef struct sty_spectrogram_args {
+  const float* audio;
+  int64_t audio_bs;
+  const float* window;
+  const float* twiddle;
+  float* mag;
+  float* phase;
+  float* mel;
+  const int32_t* fb_start;
+  const int32_t* fb_len;
+  const int32_t* fb_off;
+  const float* fb_w;
+  const int32_t* fbt_ptr; /* (K+1) */
+  const int32_t* fbt_mel;
+  const float* fbt_w;
+  int32_t B, L, n_fft, hop, n_frames, n_mels, power, mel_mode;
+  float mel_eps, mel_mean, mel_std, phase_floor;
+} sty_spectrogram_args;
+STY_API int sty_spectrogram_fwd(const sty_spectrogram_args* a, sty_stream_t stream);
+STY_API int sty_spectrogram_bwd(const sty_spectrogram_args* a, const float* d_mel, const float* d_phase,
+                                const float* d_mag, float* d_audio, int64_t d_audio_bs,
+                                sty_stream_t stream);
+
+/* ---- log-energy of a normalised log-mel ------------------------------------------------------
+ * out[b,f] = log( || exp(mel[b,:,f]*std + mean) ||_2 + 1e-9 )   (utils.py:73-85 log_norm/raw_energy,
+ * stage_type.py:88-97) */
+STY_API int sty_mel_energy_fwd(const float* mel, float* out, int B, int n_mels, int F, float mean,
+                               float std, sty_stream_t stream);
+
+/* ---- STFT losses ----------------------------------------------------------------------------------
+ * l1_sums:    sums[0] += sum|t-p|, sums[1] += sum|t|   (spectral convergence, losses.py:27-28)
+ * l1 bwd:     d_pred = coef[0] * sign(pred - target)   (coef on the device)
+ * phase_loss: d = pred - target over (B,K,N), aw(x) = |x - 2 pi round(x / 2 pi)|, w_k = 2.5^(k/(K/2)):
+ *             sums[0] += sum w_k aw(d), sums[1] += sum_{k<K-1} w_k aw(diff_k d), sums[2] += sum_{n<N-1}
+ *             w_k aw(diff_n d)        (losses.py:41-84; the means are taken by the finalize step)
+ * phase bwd:  d_pred of  coef[0] * (sums[0]/(BKN) + sums[1]/(B(K-1)N) + sums[2]/(BK(N-1)))
+ * finalize:   out[0] = mel loss (mean over resolutions of sum|t-p|/(sum|t|+1e-6)), out[1] = multi-phase
+ *             loss, out[2] = total = gm*out[0] + gp*out[1] with gm = w_mel/(out[0]+1e-9) when
+ *             `normalize` (LossLog.backwards_loss loss_log.py:82-94) else w_mel (same for gp);
+ *             out[4+r] = backward coefficient of l1 bwd at resolution r, out[4+n_res+r] = of phase bwd. */
+STY_API int sty_l1_sums_fwd(const float* target, const float* pred, int64_t n, float* sums,
+                            sty_stream_t stream);
+STY_API int sty_l1_sums_bwd(const float* target, const float* pred, int64_t n, const float* coef,
+                            float* d_pred, sty_stream_t stream);
+STY_API int sty_phase_loss_fwd(const float* pred, const float* target, int B, int K, int N, float* sums,
+                               sty_stream_t stream);
+STY_API int sty_phase_loss_bwd(const float* pred, const float* target, int B, int K, int N,
+                               const float* coef, float* d_pred, sty_stream_t stream);
+STY_API int sty_stft_loss_finalize(const float* l1_sums, const float* phase_sums, const float* phase_counts,
+                                   int n_res, float w_mel, float w_phase, int normalize, float* out,
+                                   sty_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

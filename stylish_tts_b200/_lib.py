@@ -75,6 +75,15 @@ _SIGNATURES = {
     "sty_stft_fwd": [_f32p, _f32p, _f32p, _f32p, _f32p, _i32, _i32, _i32, _i32, _i32, _f32p],
     "sty_istft_head_fwd": [_f32p, _i64, _f32p, _f32p, _i64, _f32p, _f32p, _f32p, _i32, _i32, _i32,
                            _i32, _i32, _f32p],
+    # spectral front-end + STFT losses (struct mirror: spectral.SpecArgs)
+    "sty_spectrogram_fwd": [_f32p, _f32p],
+    "sty_spectrogram_bwd": [_f32p, _f32p, _f32p, _f32p, _f32p, _i64, _f32p],
+    "sty_mel_energy_fwd": [_f32p, _f32p, _i32, _i32, _i32, _f32, _f32, _f32p],
+    "sty_l1_sums_fwd": [_f32p, _f32p, _i64, _f32p, _f32p],
+    "sty_l1_sums_bwd": [_f32p, _f32p, _i64, _f32p, _f32p, _f32p],
+    "sty_phase_loss_fwd": [_f32p, _f32p, _i32, _i32, _i32, _f32p, _f32p],
+    "sty_phase_loss_bwd": [_f32p, _f32p, _i32, _i32, _i32, _f32p, _f32p, _f32p],
+    "sty_stft_loss_finalize": [_f32p, _f32p, _f32p, _i32, _f32, _f32, _i32, _f32p, _f32p],
 }
 _SPECIAL = {
     "sty_version": ([], C.c_int),
