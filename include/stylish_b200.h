@@ -334,6 +334,116 @@ STY_API int sty_stft_loss_finalize(const float* l1_sums, const float* phase_sums
                                    int n_res, float w_mel, float w_phase, int normalize, float* out,
                                    sty_stream_t stream);
 
+/* =====================================================================================
+ * Training path: backward kernels (the reference relies on ATen/cuDNN autograd formulas).
+ * Data gradients of Conv1d reuse sty_conv1d_fwd with transposed, tap-reversed weights.
+ * ===================================================================================== */
+
+/* ---- attention forward that also returns the row log-sum-exp (B,H,T) for the backward */
+STY_API int sty_attention_lse_fwd(const float* q, const float* k, const float* v, int64_t qkv_bs,
+                                  float* o, int64_t o_bs, const int64_t* lengths, const float* rope_cos,
+                                  const float* rope_sin, int d_rot, int B, int H, int D, int T, float scale,
+                                  float* lse, sty_stream_t stream);
+
+/* ---- attention backward: dq, dk, dv (same layout / batch stride dqkv_bs) from dO; the
+ * probabilities are recomputed from `lse`; `delta` (B,H,T) is scratch (= <dO, O> per row).
+ * Backward of F.scaled_dot_product_attention + RoPE + mask (text_encoder.py:233-272,
+ * conformer.py:112-131). */
+STY_API int sty_attention_bwd(const float* q, const float* k, const float* v, int64_t qkv_bs, const float* o,
+                              const float* d_o, int64_t o_bs, const float* lse, const int64_t* lengths,
+                              const float* rope_cos, const float* rope_sin, int d_rot, float* dq, float* dk,
+                              float* dv, int64_t dqkv_bs, float* delta, int B, int H, int D, int T, float scale,
+                              sty_stream_t stream);
+
+/* ---- Conv1d weight gradient ---------------------------------------------------------------
+ * dw[co,ci,k] += sum_{b,t} g[b,co,t] * xin[b,ci,t + k*dil - pad],  g = out_scale*mask_o[b,t]*dy[b,co,t],
+ * xin = the forward's prologue applied to x (see sty_conv1d_fwd).  dw is in the REFERENCE layout
+ * (CO, CI, K) and is accumulated (the caller zeroes it).  K in {1,3,5,7,11,21}. */
+typedef struct sty_conv1d_wgrad_args {
+  const float* x;
+  int64_t x_bs, x_cs;
+  const float* dy;
+  int64_t dy_bs, dy_cs;
+  const float* in_scale;
+  const float* in_shift;
+  const float* in_alpha;
+  const float* in_mask;
+  const float* out_mask;
+  float* dw;
+  int32_t B, CI, CO, T, K, dil, pad, in_act;
+  float out_scale;
+} sty_conv1d_wgrad_args;
+STY_API int sty_conv1d_wgrad(const sty_conv1d_wgrad_args* a, sty_stream_t stream);
+
+/* out[c] += scale * sum_{b,t} mask[b,t]*x[b,c,t]      (bias gradients) */
+STY_API int sty_channel_sum(const float* x, int64_t x_bs, int64_t x_cs, const float* mask, float* out, int B,
+                            int C, int T, float scale, sty_stream_t stream);
+/* out[r] = sum_t a[r,t]*b[r,t]                        (GRN: sum_t g*hb per (b,j)) */
+STY_API int sty_row_dot(const float* a, const float* b, float* out, int64_t rows, int T, sty_stream_t stream);
+/* mean[b,c], var[b,c] (biased) over T                 (InstanceNorm / BatchNorm statistics, training) */
+STY_API int sty_row_moments(const float* x, int64_t x_bs, int64_t x_cs, float* mean, float* var, int B, int C,
+                            int T, sty_stream_t stream);
+
+/* ---- backward of the conv prologue  u = act(scale[b,c]*(x*mask) + shift[b,c]) ------------------------
+ * given dxp = dL/du (B,C,T contiguous):  g_a = dxp*act'(a)
+ * reduce: sums[b,c,:] = (sum_t g_a, sum_t g_a*(x*mask - center[b,c]), sum_t dxp * d snake/d alpha)
+ * apply:  dx = g_a*scale*mask + c0[b,c] + c1[b,c]*x + add       (c0/c1: the statistics path of
+ *         InstanceNorm / BatchNorm, ada_norm.py:129-140, conformer.py:183; add: a residual gradient) */
+STY_API int sty_prologue_bwd_reduce(const float* dxp, const float* x, int64_t x_bs, int64_t x_cs,
+                                    const float* scale, const float* shift, const float* alpha,
+                                    const float* mask, const float* center, float* sums, int B, int C, int T,
+                                    int act, sty_stream_t stream);
+STY_API int sty_prologue_bwd_apply(const float* dxp, const float* x, int64_t x_bs, int64_t x_cs,
+                                   const float* scale, const float* shift, const float* alpha,
+                                   const float* mask, const float* c0, const float* c1, const float* add,
+                                   int64_t add_bs, int64_t add_cs, float* dx, int64_t dx_bs, int64_t dx_cs,
+                                   int B, int C, int T, int act, sty_stream_t stream);
+
+/* ---- GRN + Snake backward (conv_next.py:15-18,86-88) ---------------------------------------------------
+ * hb = snake(h; alpha_j); d_hb = g_u*gs[b,j] + kc[b,j]*hb; d_h = d_hb*(1+sin(2 alpha h));
+ * dalpha[j] += sum_{b,t} d_hb * d snake/d alpha.   d_h may alias g_u. */
+STY_API int sty_grn_snake_bwd(const float* g_u, const float* h, const float* gs, const float* kc,
+                              const float* alpha, float* d_h, float* dalpha, int B, int J, int T,
+                              sty_stream_t stream);
+
+/* ---- backward of sty_chan_layernorm_fwd: dv (= dx = dres), dgb[b*dg_bs + c] += d gamma,
+ * dgb[b*dg_bs + C + c] += d beta (dg_bs = 0: shared over the batch; the caller zeroes dgb). */
+STY_API int sty_chan_layernorm_bwd(const float* x, const float* res, int64_t x_bs, const float* gamma,
+                                   const float* beta, int64_t g_bs, int g_plus_one, const float* dy,
+                                   const float* mask, float* dv, float* dgb, int64_t dg_bs, int B, int C, int T,
+                                   float eps, int act, sty_stream_t stream);
+
+/* ---- backward of the plain depthwise conv (no post-affine): dx (may be NULL), dw (C,K) and db (C)
+ * accumulated (the caller zeroes them). */
+STY_API int sty_dwconv1d_bwd(const float* dy, const float* x, int64_t x_bs, int64_t x_cs, const float* w,
+                             float* dx, int64_t dx_bs, int64_t dx_cs, float* dw, float* db, int B, int C, int T,
+                             int K, int pad_left, sty_stream_t stream);
+
+STY_API int sty_glu_bwd(const float* x, const float* dy, float* dx, int B, int C, int T, sty_stream_t stream);
+/* inverse of the conv epilogue's pixel shuffle: x[b, c*s+r, t] = y[b, c, t*s+r] */
+STY_API int sty_unshuffle(const float* y, float* x, int B, int CO, int T, int s, sty_stream_t stream);
+/* d_emb[tokens[b,t], c] += dx[b,c,t]*scale*(t < lengths[b])   (the caller zeroes d_emb) */
+STY_API int sty_embed_bwd(const int64_t* tokens, const int64_t* lengths, const float* dx, float* d_emb, int B,
+                          int T, int C, int n_tokens, float scale, sty_stream_t stream);
+/* C[b] (M,N) = A[b] (M,K) @ Bt[b] (N,K)^T      (d text_encoding = d asr @ alignment^T) */
+STY_API int sty_bmm_nt_fwd(const float* A, int64_t a_bs, const float* Bt, int64_t b_bs, float* C, int64_t c_bs,
+                           int B, int M, int N, int K, sty_stream_t stream);
+/* backward of sty_linear_rows_fwd: dW (J,I), dbias (J), ds (B,I) (ds may be NULL) */
+STY_API int sty_linear_rows_bwd(const float* dh, const float* s, const float* W, float* dW, float* dbias,
+                                float* ds, int B, int I, int J, sty_stream_t stream);
+/* backward of sty_istft_head_fwd (out = its saved output): d_logamp (B,bins,S) contiguous; d_real / d_imag
+ * (bins,S) planes with batch stride dri_bs (the two halves of the fused real|imag conv's gradient) */
+STY_API int sty_istft_head_bwd(const float* dout, const float* out, const float* logamp, int64_t logamp_bs,
+                               const float* real, const float* imag, int64_t ri_bs, const float* basis_re,
+                               const float* basis_im, float* d_logamp, float* d_real, float* d_imag,
+                               int64_t dri_bs, int B, int S, int bins, int n_fft, int hop, sty_stream_t stream);
+
+/* ---- fused AdamW over a flat parameter arena (torch.optim.AdamW semantics, optimizers.py:106-117):
+ * g is multiplied by grad_scale first (e.g. 1/world_size after a sum all-reduce). */
+STY_API int sty_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
+                           float beta2, float eps, float weight_decay, int step, float grad_scale,
+                           sty_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

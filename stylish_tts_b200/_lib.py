@@ -43,6 +43,18 @@ class ConvArgs(C.Structure):
     ]
 
 
+class WgradArgs(C.Structure):
+    """Mirror of ``sty_conv1d_wgrad_args``."""
+    _fields_ = [
+        ("x", _f32p), ("x_bs", _i64), ("x_cs", _i64),
+        ("dy", _f32p), ("dy_bs", _i64), ("dy_cs", _i64),
+        ("in_scale", _f32p), ("in_shift", _f32p), ("in_alpha", _f32p), ("in_mask", _f32p),
+        ("out_mask", _f32p), ("dw", _f32p),
+        ("B", _i32), ("CI", _i32), ("CO", _i32), ("T", _i32), ("K", _i32), ("dil", _i32),
+        ("pad", _i32), ("in_act", _i32), ("out_scale", _f32),
+    ]
+
+
 # name -> argtypes (restype is always int unless listed in _SPECIAL)
 _SIGNATURES = {
     "sty_embed_fwd": [_f32p, _f32p, _f32p, _f32p, _i32, _i32, _i32, _i32, _f32, _f32p],
@@ -83,6 +95,32 @@ _SIGNATURES = {
     "sty_l1_sums_bwd": [_f32p, _f32p, _i64, _f32p, _f32p, _f32p],
     "sty_phase_loss_fwd": [_f32p, _f32p, _i32, _i32, _i32, _f32p, _f32p],
     "sty_phase_loss_bwd": [_f32p, _f32p, _i32, _i32, _i32, _f32p, _f32p, _f32p],
+    # training path
+    "sty_attention_lse_fwd": [_f32p, _f32p, _f32p, _i64, _f32p, _i64, _f32p, _f32p, _f32p, _i32, _i32,
+                              _i32, _i32, _i32, _f32, _f32p, _f32p],
+    "sty_attention_bwd": [_f32p, _f32p, _f32p, _i64, _f32p, _f32p, _i64, _f32p, _f32p, _f32p, _f32p, _i32,
+                          _f32p, _f32p, _f32p, _i64, _f32p, _i32, _i32, _i32, _i32, _f32, _f32p],
+    "sty_conv1d_wgrad": [_f32p, _f32p],
+    "sty_channel_sum": [_f32p, _i64, _i64, _f32p, _f32p, _i32, _i32, _i32, _f32, _f32p],
+    "sty_row_dot": [_f32p, _f32p, _f32p, _i64, _i32, _f32p],
+    "sty_row_moments": [_f32p, _i64, _i64, _f32p, _f32p, _i32, _i32, _i32, _f32p],
+    "sty_prologue_bwd_reduce": [_f32p, _f32p, _i64, _i64, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, _i32,
+                                _i32, _i32, _i32, _f32p],
+    "sty_prologue_bwd_apply": [_f32p, _f32p, _i64, _i64, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p,
+                               _i64, _i64, _f32p, _i64, _i64, _i32, _i32, _i32, _i32, _f32p],
+    "sty_grn_snake_bwd": [_f32p, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, _i32, _i32, _i32, _f32p],
+    "sty_chan_layernorm_bwd": [_f32p, _f32p, _i64, _f32p, _f32p, _i64, _i32, _f32p, _f32p, _f32p, _f32p,
+                               _i64, _i32, _i32, _i32, _f32, _i32, _f32p],
+    "sty_dwconv1d_bwd": [_f32p, _f32p, _i64, _i64, _f32p, _f32p, _i64, _i64, _f32p, _f32p, _i32, _i32, _i32,
+                         _i32, _i32, _f32p],
+    "sty_glu_bwd": [_f32p, _f32p, _f32p, _i32, _i32, _i32, _f32p],
+    "sty_unshuffle": [_f32p, _f32p, _i32, _i32, _i32, _i32, _f32p],
+    "sty_embed_bwd": [_f32p, _f32p, _f32p, _f32p, _i32, _i32, _i32, _i32, _f32, _f32p],
+    "sty_bmm_nt_fwd": [_f32p, _i64, _f32p, _i64, _f32p, _i64, _i32, _i32, _i32, _i32, _f32p],
+    "sty_linear_rows_bwd": [_f32p, _f32p, _f32p, _f32p, _f32p, _f32p, _i32, _i32, _i32, _f32p],
+    "sty_istft_head_bwd": [_f32p, _f32p, _f32p, _i64, _f32p, _f32p, _i64, _f32p, _f32p, _f32p, _f32p, _f32p,
+                           _i64, _i32, _i32, _i32, _i32, _i32, _f32p],
+    "sty_adamw_step": [_f32p, _f32p, _f32p, _f32p, _i64, _f32, _f32, _f32, _f32, _f32, _i32, _f32, _f32p],
     "sty_stft_loss_finalize": [_f32p, _f32p, _f32p, _i32, _f32, _f32, _i32, _f32p, _f32p],
 }
 _SPECIAL = {

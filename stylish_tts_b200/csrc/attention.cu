@@ -19,7 +19,7 @@ __global__ void __launch_bounds__(QB)
 attention_kernel(const float* __restrict__ q, const float* __restrict__ k,
                  const float* __restrict__ v, int64_t qkv_bs, float* __restrict__ o, int64_t o_bs,
                  const int64_t* __restrict__ lengths, const float* __restrict__ rope_cos,
-                 const float* __restrict__ rope_sin, int T, float scale) {
+                 const float* __restrict__ rope_sin, int T, float scale, float* __restrict__ lse) {
   constexpr int DP = D + 4;  // padded row (keeps 16 B alignment, spreads banks)
   __shared__ __align__(16) float Ks[KT * DP];
   __shared__ __align__(16) float Vs[KT * DP];
@@ -128,6 +128,7 @@ attention_kernel(const float* __restrict__ q, const float* __restrict__ k,
     float* __restrict__ ob = o + (int64_t)b * o_bs + (int64_t)h * D * T;
 #pragma unroll
     for (int j = 0; j < D; ++j) ob[(int64_t)j * T + tq] = acc[j] * inv;
+    if (lse) lse[((int64_t)b * gridDim.y + h) * T + tq] = m + logf(l);
   }
 }
 
@@ -158,10 +159,10 @@ extern "C" int sty_rope_table(float* cos_out, float* sin_out, int T, int d_rot, 
   return STY_OK;
 }
 
-extern "C" int sty_attention_fwd(const float* q, const float* k, const float* v, int64_t qkv_bs,
-                                 float* o, int64_t o_bs, const int64_t* lengths,
-                                 const float* rope_cos, const float* rope_sin, int d_rot, int B,
-                                 int H, int D, int T, float scale, sty_stream_t stream) {
+static int attention_launch(const float* q, const float* k, const float* v, int64_t qkv_bs,
+                            float* o, int64_t o_bs, const int64_t* lengths,
+                            const float* rope_cos, const float* rope_sin, int d_rot, int B,
+                            int H, int D, int T, float scale, float* lse, sty_stream_t stream) {
   STY_REQUIRE(q && k && v && o, "attention: null pointer");
   STY_REQUIRE(B > 0 && H > 0 && T > 0, "attention: bad shape");
   STY_REQUIRE((rope_cos == nullptr) == (rope_sin == nullptr), "attention: need both rope tables");
@@ -174,21 +175,38 @@ extern "C" int sty_attention_fwd(const float* q, const float* k, const float* v,
     if (rope_cos) {
       STY_REQUIRE(d_rot == 8, "attention: D=16 is built with d_rot=8 (got %d)", d_rot);
       attention_kernel<16, 32, QB, 4><<<grid, QB, 0, st>>>(q, k, v, qkv_bs, o, o_bs, lengths,
-                                                           rope_cos, rope_sin, T, scale);
+                                                           rope_cos, rope_sin, T, scale, lse);
     } else {
       attention_kernel<16, 32, QB, 0><<<grid, QB, 0, st>>>(q, k, v, qkv_bs, o, o_bs, lengths,
-                                                           rope_cos, rope_sin, T, scale);
+                                                           rope_cos, rope_sin, T, scale, lse);
     }
   } else if (D == 64) {
     constexpr int QB = 128;
     dim3 grid(cdiv(T, QB), H, B);
     STY_REQUIRE(!rope_cos, "attention: D=64 is built without RoPE");
     attention_kernel<64, 16, QB, 0><<<grid, QB, 0, st>>>(q, k, v, qkv_bs, o, o_bs, lengths, rope_cos,
-                                                         rope_sin, T, scale);
+                                                         rope_sin, T, scale, lse);
   } else {
     set_error("attention: unsupported head dim %d (built: 16, 64)", D);
     return STY_ERR_BAD_ARG;
   }
   STY_CHECK_LAUNCH("attention");
   return STY_OK;
+}
+
+extern "C" int sty_attention_fwd(const float* q, const float* k, const float* v, int64_t qkv_bs,
+                                 float* o, int64_t o_bs, const int64_t* lengths,
+                                 const float* rope_cos, const float* rope_sin, int d_rot, int B,
+                                 int H, int D, int T, float scale, sty_stream_t stream) {
+  return attention_launch(q, k, v, qkv_bs, o, o_bs, lengths, rope_cos, rope_sin, d_rot, B, H, D, T, scale,
+                          nullptr, stream);
+}
+
+extern "C" int sty_attention_lse_fwd(const float* q, const float* k, const float* v, int64_t qkv_bs,
+                                     float* o, int64_t o_bs, const int64_t* lengths,
+                                     const float* rope_cos, const float* rope_sin, int d_rot, int B,
+                                     int H, int D, int T, float scale, float* lse, sty_stream_t stream) {
+  STY_REQUIRE(lse, "attention_lse: null lse");
+  return attention_launch(q, k, v, qkv_bs, o, o_bs, lengths, rope_cos, rope_sin, d_rot, B, H, D, T, scale, lse,
+                          stream);
 }

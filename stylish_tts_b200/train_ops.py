@@ -1,0 +1,491 @@
+"""Differentiable primitives of the training path: ``torch.autograd.Function``s whose forward
+AND backward are the sm_100a kernels of ``csrc/`` (C ABI ``sty_*``).  PyTorch autograd only keeps the
+tape between them and does the (B,C)-sized bookkeeping of normalisation statistics; every tensor-sized
+pass is one of our kernels.  No CPU / ATen fallback: CPU tensors raise in ``_lib``.
+
+Each primitive cites the reference lines whose autograd formula it replaces.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Optional
+
+import torch
+from torch.autograd import Function
+
+from . import _lib as L
+from ._lib import ACT_NONE, ACT_SNAKE, WgradArgs
+from .engine import ConvW, conv1d, chan_layernorm, dwconv1d
+
+F32 = torch.float32
+
+
+def _new(shape, like):
+    return torch.empty(shape, device=like.device, dtype=F32)
+
+
+def _zeros(shape, like):
+    return torch.zeros(shape, device=like.device, dtype=F32)
+
+
+def transposed_weight(w_oik: torch.Tensor) -> ConvW:
+    """weights of the adjoint conv: w'[ci, co, k] = w[co, ci, K-1-k] (stride 1, 'same' padding)."""
+    return ConvW(w_oik.detach().flip(2).transpose(0, 1).contiguous(), None)
+
+
+def wgrad(x, dy, K, dil, *, in_scale=None, in_shift=None, in_alpha=None, in_act=ACT_NONE, in_mask=None,
+          out_mask=None, out_scale=1.0):
+    """-> dw (CO, CI, K) of a stride-1 'same' Conv1d (reference layout)."""
+    B, CI, T = x.shape
+    CO = dy.shape[1]
+    dw = _zeros((CO, CI, K), x)
+    a = WgradArgs()
+    x_bs, x_cs = L._bct(x, "x")
+    d_bs, d_cs = L._bct(dy, "dy")
+    a.x, a.x_bs, a.x_cs = x.data_ptr(), x_bs, x_cs
+    a.dy, a.dy_bs, a.dy_cs = dy.data_ptr(), d_bs, d_cs
+    a.in_scale, a.in_shift, a.in_alpha = L.ptr(in_scale), L.ptr(in_shift), L.ptr(in_alpha)
+    a.in_mask, a.out_mask, a.dw = L.ptr(in_mask), L.ptr(out_mask), dw.data_ptr()
+    a.B, a.CI, a.CO, a.T, a.K, a.dil, a.pad, a.in_act = B, CI, CO, T, K, dil, (K - 1) * dil // 2, in_act
+    a.out_scale = out_scale
+    L.call("sty_conv1d_wgrad", C.byref(a), L.stream_ptr())
+    return dw
+
+
+def channel_sum(x, mask=None, scale=1.0):
+    B, Cc, T = x.shape
+    bs, cs = L._bct(x, "x")
+    out = _zeros((Cc,), x)
+    L.call("sty_channel_sum", x.data_ptr(), bs, cs, L.ptr(mask), out.data_ptr(), B, Cc, T, scale, L.stream_ptr())
+    return out
+
+
+def row_moments(x):
+    B, Cc, T = x.shape
+    bs, cs = L._bct(x, "x")
+    mean, var = _new((B, Cc), x), _new((B, Cc), x)
+    L.call("sty_row_moments", x.data_ptr(), bs, cs, mean.data_ptr(), var.data_ptr(), B, Cc, T, L.stream_ptr())
+    return mean, var
+
+
+def unshuffle(dy, CO, T, s):
+    B = dy.shape[0]
+    out = _new((B, CO, T), dy)
+    L.call("sty_unshuffle", dy.data_ptr(), out.data_ptr(), B, CO, T, s, L.stream_ptr())
+    return out
+
+
+def prologue_bwd(dxp, x, *, scale, shift, alpha, mask, act, center=None, want_sums, c0=None, c1=None, add=None,
+                 sums_only=False):
+    """the two passes of the conv-prologue backward; returns (sums (B,C,3) or None, dx or None)."""
+    B, Cc, T = x.shape
+    x_bs, x_cs = L._bct(x, "x")
+    sums = None
+    if want_sums:
+        sums = _new((B, Cc, 3), x)
+        L.call("sty_prologue_bwd_reduce", dxp.data_ptr(), x.data_ptr(), x_bs, x_cs, L.ptr(scale), L.ptr(shift),
+               L.ptr(alpha), L.ptr(mask), L.ptr(center), sums.data_ptr(), B, Cc, T, act, L.stream_ptr())
+    if sums_only:
+        return sums, None
+    dx = _new((B, Cc, T), x)
+    a_bs, a_cs = (0, 0) if add is None else L._bct(add, "add")
+    L.call("sty_prologue_bwd_apply", dxp.data_ptr(), x.data_ptr(), x_bs, x_cs, L.ptr(scale), L.ptr(shift),
+           L.ptr(alpha), L.ptr(mask), L.ptr(c0), L.ptr(c1), L.ptr(add), a_bs, a_cs, dx.data_ptr(), Cc * T, T,
+           B, Cc, T, act, L.stream_ptr())
+    return sums, dx
+
+
+class ConvFn(Function):
+    """Conv1d / Linear with the fused prologue (mask, InstanceNorm- or BatchNorm-affine, activation) and
+    epilogue (bias, mask, residual, pixel shuffle) of ``sty_conv1d_fwd``.
+
+    norm = None | "instance" (AdaIN: gb (B,2C) = style FC output, ada_norm.py:129-140) |
+           "batch" (training-mode BatchNorm1d with weight/bias = bn_w/bn_b, conformer.py:183).
+    Backward: data gradient = the same conv kernel with transposed weights, weight gradient =
+    ``sty_conv1d_wgrad``, prologue / statistics = ``sty_prologue_bwd_*``.
+    """
+
+    @staticmethod
+    def forward(ctx, x, w, bias, gb, alpha, res, bn_w, bn_b, cfg):
+        B, CI, T = x.shape
+        CO, _, K = w.shape
+        dil, in_act = cfg.get("dil", 1), cfg.get("in_act", ACT_NONE)
+        norm, eps = cfg.get("norm"), cfg.get("eps", 1e-5)
+        in_mask, out_mask = cfg.get("in_mask"), cfg.get("out_mask")
+        shuffle, umma = cfg.get("shuffle", 0), cfg.get("umma", True)
+        out_scale, res_scale = cfg.get("out_scale", 1.0), cfg.get("res_scale", 1.0)
+        scale = shift = mean = rstd = None
+        if norm == "instance":
+            mean, var = row_moments(x)
+            rstd = torch.rsqrt(var + eps)
+            scale = ((1.0 + gb[:, :CI]) * rstd).contiguous()
+            shift = (gb[:, CI:] - mean * scale).contiguous()
+        elif norm == "batch":
+            m_bc, v_bc = row_moments(x)
+            mean_c = m_bc.mean(0)
+            var_c = (v_bc + m_bc * m_bc).mean(0) - mean_c * mean_c
+            rstd_c = torch.rsqrt(var_c + eps)
+            sc = bn_w * rstd_c
+            scale = sc.unsqueeze(0).expand(B, CI).contiguous()
+            shift = (bn_b - mean_c * sc).unsqueeze(0).expand(B, CI).contiguous()
+            mean, rstd = mean_c.unsqueeze(0).expand(B, CI).contiguous(), rstd_c
+            stats = cfg.get("bn_buffers")
+            if stats is not None:  # running statistics, momentum 0.1, unbiased variance (nn.BatchNorm1d)
+                n = B * T
+                stats[0].mul_(0.9).add_(mean_c, alpha=0.1)
+                stats[1].mul_(0.9).add_(var_c * (n / max(n - 1, 1)), alpha=0.1)
+        elif cfg.get("in_scale") is not None:
+            raise ValueError("ConvFn: constant in_scale is not supported; use a norm mode")
+        cw = ConvW(w.detach(), None if bias is None else bias.detach())
+        al = None if alpha is None else alpha.detach().contiguous()
+        y = conv1d(x, cw, dil=dil, res=res, in_scale=scale, in_shift=shift, in_alpha=al, in_act=in_act,
+                   in_mask=in_mask, out_mask=out_mask, shuffle=shuffle, out_scale=out_scale,
+                   res_scale=res_scale, umma=umma)
+        ctx.save_for_backward(x, w, gb, al, scale, shift, mean, rstd, bn_w)
+        ctx.cfg, ctx.has_bias, ctx.has_res = cfg, bias is not None, res is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, gb, al, scale, shift, mean, rstd, bn_w = ctx.saved_tensors
+        cfg = ctx.cfg
+        B, CI, T = x.shape
+        CO, _, K = w.shape
+        dil, in_act = cfg.get("dil", 1), cfg.get("in_act", ACT_NONE)
+        norm = cfg.get("norm")
+        in_mask, out_mask = cfg.get("in_mask"), cfg.get("out_mask")
+        shuffle, umma = cfg.get("shuffle", 0), cfg.get("umma", True)
+        out_scale, res_scale = cfg.get("out_scale", 1.0), cfg.get("res_scale", 1.0)
+        need = ctx.needs_input_grad
+        dy = dy.contiguous()
+        d_res = None
+        if ctx.has_res and need[5]:
+            d_res = dy if res_scale == 1.0 else dy * res_scale
+        g = unshuffle(dy, CO, T, shuffle) if shuffle > 1 else dy
+        d_bias = channel_sum(g, out_mask, out_scale) if (ctx.has_bias and need[2]) else None
+        d_w = None
+        if need[1]:
+            d_w = wgrad(x, g, K, dil, in_scale=scale, in_shift=shift, in_alpha=al, in_act=in_act,
+                        in_mask=in_mask, out_mask=out_mask, out_scale=out_scale)
+        d_x = d_gb = d_alpha = d_bnw = d_bnb = None
+        want_stats = norm is not None or (al is not None and need[4])
+        if need[0] or want_stats:
+            dxp = conv1d(g, transposed_weight(w), dil=dil, in_mask=out_mask, out_scale=out_scale, umma=umma)
+            plain = scale is None and in_mask is None and in_act == ACT_NONE
+            if plain:
+                d_x = dxp
+            else:
+                sums, _ = prologue_bwd(dxp, x, scale=scale, shift=shift, alpha=al, mask=in_mask, act=in_act,
+                                       center=mean, want_sums=want_stats, sums_only=True)
+                c0 = c1 = None
+                if sums is not None and al is not None:
+                    d_alpha = sums[:, :, 2].sum(0)
+                if norm == "instance":
+                    s0, s1 = sums[:, :, 0], sums[:, :, 1]  # s1 is centred: sum g_a (x - mean)
+                    d_gb = torch.cat([s1 * rstd, s0], 1)
+                    c1 = (-(scale * rstd * rstd) * s1 / T).contiguous()
+                    c0 = (-scale * s0 / T - c1 * mean).contiguous()
+                elif norm == "batch":
+                    s0, s1 = sums[:, :, 0].sum(0), sums[:, :, 1].sum(0)
+                    d_bnw, d_bnb = s1 * rstd, s0
+                    n = B * T
+                    sc = scale[0]
+                    c1c = -(sc * rstd * rstd) * s1 / n
+                    c0c = -sc * s0 / n - c1c * mean[0]
+                    c1 = c1c.unsqueeze(0).expand(B, CI).contiguous()
+                    c0 = c0c.unsqueeze(0).expand(B, CI).contiguous()
+                if need[0]:
+                    _, d_x = prologue_bwd(dxp, x, scale=scale, shift=shift, alpha=al, mask=in_mask, act=in_act,
+                                          want_sums=False, c0=c0, c1=c1)
+        return d_x, d_w, d_bias, d_gb, d_alpha, d_res, d_bnw, d_bnb, None
+
+
+def conv(x, w, bias=None, *, gb=None, alpha=None, res=None, bn_w=None, bn_b=None, **cfg):
+    return ConvFn.apply(x, w, bias, gb, alpha, res, bn_w, bn_b, cfg)
+
+
+class ConvNeXtTailFn(Function):
+    """pwconv1 -> Snake -> GRN -> pwconv2 -> + residual  (conv_next.py:85-93, GRN :15-18).
+
+    The 4C-wide pre-activation is not stored: the backward recomputes it with one more
+    tensor-core pointwise conv."""
+
+    @staticmethod
+    def forward(ctx, y, xres, w1, b1, alpha, gamma, w2, b2f, umma):
+        B, Cc, T = y.shape
+        J = w1.shape[0]
+        cw1 = ConvW(w1.detach().unsqueeze(-1), b1.detach())
+        cw2 = ConvW(w2.detach().unsqueeze(-1), b2f.detach())
+        al, gm = alpha.detach().contiguous(), gamma.detach().contiguous()
+        sumsq = _zeros((B, J), y)
+        hb = conv1d(y, cw1, out_act=ACT_SNAKE, out_alpha=al, out_sumsq=sumsq, umma=umma)
+        gs = _new((B, J), y)
+        L.call("sty_grn_scale_fwd", sumsq.data_ptr(), gm.data_ptr(), gs.data_ptr(), B, J, L.stream_ptr())
+        out = conv1d(hb, cw2, in_scale=gs, res=xres, umma=umma)
+        ctx.save_for_backward(y, hb, sumsq, gs, w1, b1, al, gm, w2)
+        ctx.umma = umma
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        y, hb, sumsq, gs, w1, b1, al, gm, w2 = ctx.saved_tensors
+        umma = ctx.umma
+        B, Cc, T = y.shape
+        J = w1.shape[0]
+        dout = dout.contiguous()
+        d_b2f = channel_sum(dout)
+        d_w2 = wgrad(hb, dout, 1, 1, in_scale=gs)[:, :, 0]
+        g_u = conv1d(dout, transposed_weight(w2.unsqueeze(-1)), umma=umma)  # (B,J,T)
+        r = _new((B, J), y)
+        L.call("sty_row_dot", g_u.data_ptr(), hb.data_ptr(), r.data_ptr(), B * J, T, L.stream_ptr())
+        gx = torch.sqrt(sumsq)
+        M = gx.mean(1, keepdim=True) + 1e-6
+        nx = gx / M
+        d_nx = r * gm
+        d_gamma = (r * nx).sum(0)
+        d_gx = d_nx / M - (d_nx * gx).sum(1, keepdim=True) / (M * M * J)
+        kc = torch.where(gx > 0, d_gx / gx.clamp_min(1e-30), torch.zeros_like(gx)).contiguous()
+        h = conv1d(y, ConvW(w1.unsqueeze(-1), b1), umma=umma)  # pre-activation, recomputed
+        d_alpha = _zeros((J,), y)
+        L.call("sty_grn_snake_bwd", g_u.data_ptr(), h.data_ptr(), gs.data_ptr(), kc.data_ptr(), al.data_ptr(),
+               g_u.data_ptr(), d_alpha.data_ptr(), B, J, T, L.stream_ptr())
+        d_h = g_u
+        del h
+        d_b1 = channel_sum(d_h)
+        d_w1 = wgrad(y, d_h, 1, 1)[:, :, 0]
+        d_y = conv1d(d_h, transposed_weight(w1.unsqueeze(-1)), umma=umma)
+        return d_y, dout, d_w1, d_b1, d_alpha, d_gamma, d_w2, d_b2f, None
+
+
+class ChanLNFn(Function):
+    """LayerNorm over channels of (B,C,T) with optional residual input, adaptive ((1+gamma(s)), beta(s))
+    or shared (gamma, beta) affine, output mask and ReLU  (text_encoder.py:24-33, ada_norm.py:203-211,
+    generator.py:756-778)."""
+
+    @staticmethod
+    def forward(ctx, x, res, gamma, beta, gb, cfg):
+        B, Cc, T = x.shape
+        eps, mask, act = cfg["eps"], cfg.get("mask"), cfg.get("act", ACT_NONE)
+        if gb is not None:  # adaptive: gb (B, 2C) rows of the style FC output
+            assert gb.stride(1) == 1
+            g, be, g_bs, plus_one = gb, gb[:, Cc:], gb.stride(0), True
+        else:
+            g, be, g_bs, plus_one = gamma.detach().contiguous(), beta.detach().contiguous(), 0, False
+        x = x.contiguous()
+        if res is not None:
+            res = res.contiguous()
+        y = chan_layernorm(x, g, be, eps=eps, res=res, g_bs=g_bs, plus_one=plus_one, mask=mask, act=act)
+        ctx.save_for_backward(x, res, g, be)
+        ctx.cfg, ctx.g_bs, ctx.plus_one, ctx.adaptive = cfg, g_bs, plus_one, gb is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, res, g, be = ctx.saved_tensors
+        cfg = ctx.cfg
+        B, Cc, T = x.shape
+        dy = dy.contiguous()
+        dv = _new((B, Cc, T), x)
+        dgb = _zeros((B, 2 * Cc) if ctx.adaptive else (2 * Cc,), x)
+        L.call("sty_chan_layernorm_bwd", x.data_ptr(), L.ptr(res), x.stride(0), g.data_ptr(), be.data_ptr(),
+               ctx.g_bs, int(ctx.plus_one), dy.data_ptr(), L.ptr(cfg.get("mask")), dv.data_ptr(), dgb.data_ptr(),
+               2 * Cc if ctx.adaptive else 0, B, Cc, T, cfg["eps"], cfg.get("act", ACT_NONE), L.stream_ptr())
+        d_res = dv if res is not None else None
+        if ctx.adaptive:
+            return dv, d_res, None, None, dgb, None
+        return dv, d_res, dgb[:Cc], dgb[Cc:], None, None
+
+
+def chan_ln(x, *, res=None, gamma=None, beta=None, gb=None, **cfg):
+    return ChanLNFn.apply(x, res, gamma, beta, gb, cfg)
+
+
+class DwConvFn(Function):
+    """depthwise Conv1d (conv_next.py:82, conformer.py:176, decoder.py:77-79)."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, K, pad_left):
+        B, Cc, T = x.shape
+        wk = w.detach().reshape(Cc, K).contiguous()
+        out = _new((B, Cc, T), x)
+        dwconv1d(x, wk, None if bias is None else bias.detach().contiguous(), K=K, pad_left=pad_left, out=out)
+        ctx.save_for_backward(x, wk)
+        ctx.K, ctx.pad_left, ctx.w_shape, ctx.has_bias = K, pad_left, w.shape, bias is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, wk = ctx.saved_tensors
+        B, Cc, T = x.shape
+        dy = dy.contiguous()
+        x_bs, x_cs = L._bct(x, "x")
+        dx = _new((B, Cc, T), x) if ctx.needs_input_grad[0] else None
+        dw, db = _zeros((Cc, ctx.K), x), _zeros((Cc,), x)
+        L.call("sty_dwconv1d_bwd", dy.data_ptr(), x.data_ptr(), x_bs, x_cs, wk.data_ptr(), L.ptr(dx), Cc * T, T,
+               dw.data_ptr(), db.data_ptr(), B, Cc, T, ctx.K, ctx.pad_left, L.stream_ptr())
+        return dx, dw.reshape(ctx.w_shape), (db if ctx.has_bias else None), None, None
+
+
+class AttentionFn(Function):
+    """attention core on a fused (B, 3*H*D, T) q|k|v tensor (text_encoder.py:233-272, conformer.py:112-131)."""
+
+    @staticmethod
+    def forward(ctx, qkv, H, D, lengths, rope, scale):
+        B, C3, T = qkv.shape
+        n = H * D
+        assert C3 == 3 * n and qkv.is_contiguous()
+        out = _new((B, n, T), qkv)
+        lse = _new((B, H, T), qkv)
+        q = qkv.data_ptr()
+        rc, rs, d_rot = (None, None, 0) if rope is None else (rope[0].data_ptr(), rope[1].data_ptr(), rope[2])
+        L.call("sty_attention_lse_fwd", q, q + 4 * n * T, q + 8 * n * T, qkv.stride(0), out.data_ptr(),
+               out.stride(0), L.ptr(lengths), rc, rs, d_rot, B, H, D, T, scale, lse.data_ptr(), L.stream_ptr())
+        ctx.save_for_backward(qkv, out, lse)
+        ctx.meta = (H, D, lengths, rope, scale)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        qkv, out, lse = ctx.saved_tensors
+        H, D, lengths, rope, scale = ctx.meta
+        B, C3, T = qkv.shape
+        n = H * D
+        d_out = d_out.contiguous()
+        d_qkv = _new((B, C3, T), qkv)
+        delta = _new((B, H, T), qkv)
+        q, dq = qkv.data_ptr(), d_qkv.data_ptr()
+        rc, rs, d_rot = (None, None, 0) if rope is None else (rope[0].data_ptr(), rope[1].data_ptr(), rope[2])
+        L.call("sty_attention_bwd", q, q + 4 * n * T, q + 8 * n * T, qkv.stride(0), out.data_ptr(),
+               d_out.data_ptr(), out.stride(0), lse.data_ptr(), L.ptr(lengths), rc, rs, d_rot, dq,
+               dq + 4 * n * T, dq + 8 * n * T, d_qkv.stride(0), delta.data_ptr(), B, H, D, T, scale,
+               L.stream_ptr())
+        return d_qkv, None, None, None, None, None
+
+
+class GluFn(Function):
+    @staticmethod
+    def forward(ctx, x):
+        B, C2, T = x.shape
+        x = x.contiguous()
+        y = _new((B, C2 // 2, T), x)
+        L.call("sty_glu_fwd", x.data_ptr(), y.data_ptr(), B, C2 // 2, T, L.stream_ptr())
+        ctx.save_for_backward(x)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        B, C2, T = x.shape
+        dx = torch.empty_like(x)
+        L.call("sty_glu_bwd", x.data_ptr(), dy.contiguous().data_ptr(), dx.data_ptr(), B, C2 // 2, T,
+               L.stream_ptr())
+        return dx
+
+
+class EmbedFn(Function):
+    """emb(tokens)*sqrt(C), transposed to (B,C,T) and masked (text_encoder.py:451-453)."""
+
+    @staticmethod
+    def forward(ctx, emb, tokens, lengths, scale):
+        B, T = tokens.shape
+        n_tok, Cc = emb.shape
+        out = _new((B, Cc, T), emb)
+        L.call("sty_embed_fwd", tokens.data_ptr(), lengths.data_ptr(), emb.detach().contiguous().data_ptr(),
+               out.data_ptr(), B, T, Cc, n_tok, scale, L.stream_ptr())
+        ctx.save_for_backward(tokens, lengths)
+        ctx.meta = (n_tok, Cc, scale)
+        return out
+
+    @staticmethod
+    def backward(ctx, dx):
+        tokens, lengths = ctx.saved_tensors
+        n_tok, Cc, scale = ctx.meta
+        B, T = tokens.shape
+        d_emb = _zeros((n_tok, Cc), dx)
+        L.call("sty_embed_bwd", tokens.data_ptr(), lengths.data_ptr(), dx.contiguous().data_ptr(),
+               d_emb.data_ptr(), B, T, Cc, n_tok, scale, L.stream_ptr())
+        return d_emb, None, None, None
+
+
+class BmmAlignFn(Function):
+    """text_encoding (B,C,T) @ alignment (B,T,F) (speech_predictor.py:60); the alignment is an input
+    built from integer durations in the acoustic stage (stage_type.py:99-106) and gets no gradient."""
+
+    @staticmethod
+    def forward(ctx, mu, alignment):
+        B, Cm, T = mu.shape
+        Fr = alignment.shape[2]
+        mu = mu.contiguous()
+        out = _new((B, Cm, Fr), mu)
+        L.call("sty_bmm_fwd", mu.data_ptr(), mu.stride(0), alignment.data_ptr(), alignment.stride(0),
+               out.data_ptr(), out.stride(0), B, Cm, Fr, T, L.stream_ptr())
+        ctx.save_for_backward(alignment)
+        ctx.T = T
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        (alignment,) = ctx.saved_tensors
+        B, Cm, Fr = d_out.shape
+        d_out = d_out.contiguous()
+        d_mu = _new((B, Cm, ctx.T), d_out)
+        L.call("sty_bmm_nt_fwd", d_out.data_ptr(), d_out.stride(0), alignment.data_ptr(), alignment.stride(0),
+               d_mu.data_ptr(), d_mu.stride(0), B, Cm, ctx.T, Fr, L.stream_ptr())
+        return d_mu, None
+
+
+class LinearRowsFn(Function):
+    """all style FCs of a module as one matrix: h = s @ W^T + b (ada_norm.py:136,204)."""
+
+    @staticmethod
+    def forward(ctx, s, W, bias):
+        B, I = s.shape
+        J = W.shape[0]
+        s, Wc = s.contiguous(), W.detach().contiguous()
+        h = _new((B, J), s)
+        L.call("sty_linear_rows_fwd", s.data_ptr(), Wc.data_ptr(), bias.detach().contiguous().data_ptr(),
+               h.data_ptr(), B, I, J, L.stream_ptr())
+        ctx.save_for_backward(s, Wc)
+        return h
+
+    @staticmethod
+    def backward(ctx, dh):
+        s, Wc = ctx.saved_tensors
+        B, I = s.shape
+        J = Wc.shape[0]
+        dh = dh.contiguous()
+        dW, db = _new((J, I), s), _new((J,), s)
+        ds = _new((B, I), s) if ctx.needs_input_grad[0] else None
+        L.call("sty_linear_rows_bwd", dh.data_ptr(), s.data_ptr(), Wc.data_ptr(), dW.data_ptr(), db.data_ptr(),
+               L.ptr(ds), B, I, J, L.stream_ptr())
+        return ds, dW, db
+
+
+class IstftHeadFn(Function):
+    """exp / atan2 / cos-sin head + conv-iSTFT + tanh (generator.py:782-799,896; stft.py:138-187)."""
+
+    @staticmethod
+    def forward(ctx, logamp, ri, basis_re, basis_im, hop):
+        B, Hs, S = logamp.shape
+        logamp, ri = logamp.contiguous(), ri.contiguous()
+        audio = _new((B, 1, S * hop), logamp)
+        L.call("sty_istft_head_fwd", logamp.data_ptr(), logamp.stride(0), ri.data_ptr(),
+               ri.data_ptr() + 4 * Hs * S, ri.stride(0), basis_re.data_ptr(), basis_im.data_ptr(),
+               audio.data_ptr(), B, S, Hs, 64, hop, L.stream_ptr())
+        ctx.save_for_backward(logamp, ri, audio, basis_re, basis_im)
+        ctx.hop = hop
+        return audio
+
+    @staticmethod
+    def backward(ctx, d_audio):
+        logamp, ri, audio, basis_re, basis_im = ctx.saved_tensors
+        B, Hs, S = logamp.shape
+        d_audio = d_audio.contiguous()
+        d_la = _new((B, Hs, S), logamp)
+        d_ri = _new((B, 2 * Hs, S), logamp)
+        L.call("sty_istft_head_bwd", d_audio.data_ptr(), audio.data_ptr(), logamp.data_ptr(), logamp.stride(0),
+               ri.data_ptr(), ri.data_ptr() + 4 * Hs * S, ri.stride(0), basis_re.data_ptr(), basis_im.data_ptr(),
+               d_la.data_ptr(), d_ri.data_ptr(), d_ri.data_ptr() + 4 * Hs * S, d_ri.stride(0), B, S, Hs, 64,
+               ctx.hop, L.stream_ptr())
+        return d_la, d_ri, None, None, None
