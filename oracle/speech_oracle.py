@@ -287,8 +287,9 @@ def conformer_attn(sd: SD, prefix: str, x, s, heads=8):
     return linear(sd, prefix + ".fn.to_out", o)
 
 
-def conformer_conv(sd: SD, prefix: str, x, s):
-    """ConformerConvModule conformer.py:160-193 (eval BatchNorm: running stats)."""
+def conformer_conv(sd: SD, prefix: str, x, s, bn_training=False):
+    """ConformerConvModule conformer.py:160-193 (eval BatchNorm: running stats; ``bn_training``:
+    batch statistics, as nn.BatchNorm1d does in train mode)."""
     h = adaln(sd, prefix + ".norm", x, s, 1e-5).transpose(1, 2)  # (B,C,N)
     h = conv1d(sd, prefix + ".net.1", h)
     a, g = h.chunk(2, dim=1)
@@ -297,19 +298,22 @@ def conformer_conv(sd: SD, prefix: str, x, s):
     h = F.pad(h, (15, 15))
     h = conv1d(sd, prefix + ".net.3.conv", h, groups=C)
     bn = prefix + ".net.4"
-    h = F.batch_norm(h, sd[bn + ".running_mean"], sd[bn + ".running_var"], sd[bn + ".weight"],
-                     sd[bn + ".bias"], training=False, eps=1e-5)
+    if bn_training:
+        h = F.batch_norm(h, None, None, sd[bn + ".weight"], sd[bn + ".bias"], training=True, eps=1e-5)
+    else:
+        h = F.batch_norm(h, sd[bn + ".running_mean"], sd[bn + ".running_var"], sd[bn + ".weight"],
+                         sd[bn + ".bias"], training=False, eps=1e-5)
     h = _swish(h)
     h = conv1d(sd, prefix + ".net.6", h)
     return h.transpose(1, 2)
 
 
-def conformer_block(sd: SD, prefix: str, x, s):
+def conformer_block(sd: SD, prefix: str, x, s, bn_training=False):
     """conformer.py:242-250 — note attention reads the block INPUT x."""
     x_ff1 = conformer_ff(sd, prefix + ".ff1", x, s) + x
     x = conformer_attn(sd, prefix + ".attn", x, s)
     x = x + x_ff1
-    x = conformer_conv(sd, prefix + ".conv", x, s) + x
+    x = conformer_conv(sd, prefix + ".conv", x, s, bn_training) + x
     x = conformer_ff(sd, prefix + ".ff2", x, s) + x
     return adaln(sd, prefix + ".post_norm", x, s, 1e-5)
 
@@ -443,7 +447,7 @@ def basegen(sd: SD, prefix: str, mel, style, har_spec, har_phase, *, amp_layers=
 
 
 def multi_generator(sd: SD, prefix: str, mel, style, pitch, voiced, draws=None, *,
-                    prior=None, taps=None):
+                    prior=None, taps=None, bn_training=False):
     """MultiGenerator.forward generator.py:884-901.  Either ``draws`` (RNG of
     the source) or an injected ``prior=(har_spec, har_phase)`` must be given."""
     x = conv1d(sd, prefix + ".amp_input_conv", mel, padding=10)
@@ -451,12 +455,13 @@ def multi_generator(sd: SD, prefix: str, mel, style, pitch, voiced, draws=None, 
                      sd[prefix + ".amp_norm.bias"], 1e-6)
     if taps is not None:
         taps["amp_norm"] = x.transpose(1, 2)
-    x = conformer_block(sd, prefix + ".amp_conformer.layers.0", x, style)
+    x = conformer_block(sd, prefix + ".amp_conformer.layers.0", x, style, bn_training)
     x = x.transpose(1, 2)
     if taps is not None:
         taps["conformer"] = x
     if prior is None:
-        har_spec, har_phase, wave = harmonic_prior(sd, prefix + ".basegen", pitch, voiced, draws)
+        with torch.no_grad():  # generator.py:711 — the whole prior branch is built without a graph
+            har_spec, har_phase, wave = harmonic_prior(sd, prefix + ".basegen", pitch, voiced, draws)
         if taps is not None:
             taps["prior_wave"] = wave
     else:
@@ -470,7 +475,7 @@ def multi_generator(sd: SD, prefix: str, mel, style, pitch, voiced, draws=None, 
 
 def speech_predictor(sd: SD, texts, text_lengths, alignment, pitch, energy, voiced, style,
                      denormal_pitch, draws=None, *, prior=None,
-                     taps: Optional[dict] = None):
+                     taps: Optional[dict] = None, bn_training=False):
     """SpeechPredictor.forward speech_predictor.py:47-73 -> audio (B,1,L)."""
     mu, _, _ = text_encoder(sd, "text_encoder", texts, text_lengths, taps=taps)
     if taps is not None:
@@ -480,7 +485,7 @@ def speech_predictor(sd: SD, texts, text_lengths, alignment, pitch, energy, voic
     if taps is not None:
         taps["decoder"] = mel
     return multi_generator(sd, "generator", mel, style, denormal_pitch, voiced, draws,
-                           prior=prior, taps=taps)
+                           prior=prior, taps=taps, bn_training=bn_training)
 
 
 # ---------------------------------------------------------------------------

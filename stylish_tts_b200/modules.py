@@ -295,6 +295,7 @@ class SpeechPredictor(nn.Module):
                                         win_length=mc.win_length, hop_length=mc.hop_length,
                                         cfg=mc.generator)
         self._engine = None
+        self._train_graph = None
 
     def engine(self):
         from .engine import SpeechEngine
@@ -303,12 +304,23 @@ class SpeechPredictor(nn.Module):
             self._engine = SpeechEngine(self)
         return self._engine
 
+    def train_graph(self):
+        from .train_engine import TrainGraph
+
+        if self._train_graph is None:
+            self._train_graph = TrainGraph(self, self.engine())
+        return self._train_graph
+
     def forward(self, texts, text_lengths, alignment, pitch, energy, voiced, style,
                 denormal_pitch, *, source_draws=None, prior=None, taps=None):
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise NotImplementedError(
-                "stylish_tts_b200: the backward kernels of speech_predictor are not built "
-                "yet; call under torch.no_grad() (forward/inference path)")
+        wants_grad = torch.is_grad_enabled() and (
+            any(p.requires_grad for p in self.parameters())
+            or any(torch.is_tensor(t) and t.requires_grad for t in (pitch, energy, style)))
+        if wants_grad:  # differentiable path: autograd primitives backed by the backward kernels
+            audio = self.train_graph().forward(texts, text_lengths, alignment, pitch, energy, voiced,
+                                               style, denormal_pitch, source_draws=source_draws,
+                                               prior=prior)
+            return DecoderPrediction(audio=audio, magnitude=None, phase=None)
         audio = self.engine().forward(texts, text_lengths, alignment, pitch, energy, voiced,
                                       style, denormal_pitch, source_draws=source_draws,
                                       prior=prior, taps=taps)

@@ -1,0 +1,174 @@
+"""Gradient parity of the speech_predictor training path (SURVEY §8 config 3 building block).
+
+CPU : the oracle's autograd gradients against golden gradients of the UNMODIFIED reference
+      (tests/golden/train_grads.npz: per-parameter norm + seeded probe dot, full input gradients).
+GPU : ``SpeechPredictor.forward`` under autograd (forward and backward on the CUDA kernels, through the
+      C ABI) against the fp64 oracle's full gradients for EVERY parameter, and against the reference
+      golden; BatchNorm running statistics; a full-size (config 3) step for finiteness and memory.
+Setting (both arms): batch-statistics BatchNorm, stochastic regularisers off, harmonic prior injected.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import speech_oracle as so
+import stylish_tts_b200 as st
+from stylish_tts_b200 import synth
+from tests import util
+from tests.golden.make_train_golden import CASE, cotangent, probe
+from tests.util import rel_l2
+
+BN = "generator.amp_conformer.layers.0.conv.net.4"
+
+
+def load_gold():
+    z = np.load(util.GOLDEN_DIR + "/train_grads.npz")
+    return {k: z[k] for k in z.files}
+
+
+def case():
+    sp = st.build_model(st.default_model_config()).speech_predictor
+    synth.randomize_(sp, CASE["wseed"])
+    inp = synth.speech_inputs(CASE["batch"], CASE["tokens"], seed=CASE["iseed"], ragged=CASE["ragged"])
+    return sp, inp
+
+
+def oracle_grads(sp, inp, dtype, prior=None):
+    sd = {k: (v.detach().clone().to(dtype).requires_grad_(True) if v.is_floating_point() else v.clone())
+          for k, v in sp.state_dict().items()}
+    f = lambda t: t.to(dtype) if t.is_floating_point() else t
+    style, pitch, energy = (f(inp[k]).clone().requires_grad_(True) for k in ("style", "pitch", "energy"))
+    draws = {k: f(v) for k, v in inp["draws"].items()}
+    if prior is not None:
+        prior = tuple(f(p) for p in prior)
+    taps = {}
+    audio = so.speech_predictor(sd, inp["texts"], inp["text_lengths"], f(inp["alignment"]), pitch, energy,
+                                f(inp["voiced"]), style, f(inp["denormal_pitch"]), draws, prior=prior, taps=taps,
+                                bn_training=True)
+    (audio * cotangent(audio.shape).to(dtype)).sum().backward()
+    grads = {k: v.grad for k, v in sd.items()
+             if v.is_floating_point() and v.grad is not None and ".stft." not in k}  # DFT bases are buffers
+    return audio.detach(), grads, dict(style=style.grad, pitch=pitch.grad, energy=energy.grad), taps
+
+
+def test_oracle_gradients_match_reference_golden():
+    gold = load_gold()
+    sp, inp = case()
+    audio, grads, dins, _ = oracle_grads(sp, inp, torch.float32)
+    assert rel_l2(audio, torch.from_numpy(gold["audio"])) < 1e-5
+    # two fp32 evaluations of the same graph: the gradient itself is conditioned at the 1e-2 level
+    # in fp32 with random weights (fp32 vs fp64 of the reference's own formula: 1.5e-2, see
+    # test_gpu_gradients_match_oracle_and_reference), different but valid summation orders give ~2e-3
+    for k in ("style", "pitch", "energy"):
+        assert rel_l2(dins[k], torch.from_numpy(gold["d_" + k])) < 5e-3, k
+    names = [str(n) for n in gold["names"]]
+    assert sorted(grads) == sorted(names)
+    scale = float(np.sqrt((gold["norms"] ** 2).sum()))
+    # parameters feeding a normalisation (biases, weight-norm gains) have an exactly-zero true gradient:
+    # what either implementation returns there is rounding noise, hence the absolute floor
+    for n, norm, dot in zip(names, gold["norms"], gold["dots"]):
+        gr = grads[n]
+        assert abs(float(gr.norm()) - norm) <= 1e-2 * norm + 1e-6 * scale, (n, float(gr.norm()), norm)
+        mine = float((gr * probe(n, gr.shape)).sum())
+        assert abs(mine - dot) <= 2e-2 * norm + 1e-6 * scale, (n, mine, dot, norm)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tensor_cores", [False, True])
+def test_gpu_gradients_match_oracle_and_reference(tensor_cores, monkeypatch):
+    from stylish_tts_b200 import engine as E
+
+    monkeypatch.setattr(E, "USE_UMMA", tensor_cores)
+    gold = load_gold()
+    sp, inp = case()
+    # prior from the fp32 oracle forward, injected identically into both arms
+    taps = {}
+    with torch.no_grad():
+        sd32 = util.state_dict_of(sp)
+        so.speech_predictor(sd32, inp["texts"], inp["text_lengths"], inp["alignment"], inp["pitch"], inp["energy"],
+                            inp["voiced"], inp["style"], inp["denormal_pitch"], inp["draws"], taps=taps)
+    prior = (taps["har_spec"], taps["har_phase"])
+    audio_ref, grads_ref, dins_ref, _ = oracle_grads(sp, inp, torch.float64, prior=prior)
+
+    dev = torch.device("cuda:0")
+    sp = sp.to(dev).train()
+    c = lambda t: t.to(dev)
+    style, pitch, energy = (c(inp[k]).clone().requires_grad_(True) for k in ("style", "pitch", "energy"))
+    out = sp(c(inp["texts"]), c(inp["text_lengths"]), c(inp["alignment"]), pitch, energy, c(inp["voiced"]), style,
+             c(inp["denormal_pitch"]), prior=(c(prior[0]), c(prior[1])))
+    audio = out.audio
+    assert audio.requires_grad
+    (audio * c(cotangent(audio.shape))).sum().backward()
+    torch.cuda.synchronize()
+    assert rel_l2(audio, audio_ref) < 5e-4
+    # Conditioning: phase = atan2(imag, real) has the derivative (-imag, real)/r^2, so bins where the
+    # predicted r is ~0 amplify forward rounding into the gradient of everything upstream of the phase head.
+    # Measured on this case (tools/debug_grads.py): the reference's own formula in fp32 vs fp64 = 1.7e-2;
+    # ours with fp32-FMA convs = 1.0e-2 (closer to fp64 than the reference's fp32), with the bf16x3
+    # tensor-core convs (forward error 9e-5 instead of 3e-5) = 6.5e-2.  The amplitude branch, which does not
+    # pass through atan2, agrees to 1e-4 in both modes, and every primitive holds 2e-4 on its own
+    # (tests/test_gpu_train_ops.py).
+    GRAD_TOL = 0.15 if tensor_cores else 3e-2
+    for k, t in (("style", style), ("pitch", pitch), ("energy", energy)):
+        assert rel_l2(t.grad, dins_ref[k]) < GRAD_TOL, (k, rel_l2(t.grad, dins_ref[k]))
+    params = dict(sp.named_parameters())
+    errs = {}
+    for n, gr in grads_ref.items():
+        assert params[n].grad is not None, f"no gradient for {n}"
+        errs[n] = rel_l2(params[n].grad, gr)
+    unused = [n for n, p in params.items() if p.grad is None]
+    assert sorted(unused) == ["generator.basegen.m_source.l_linear.bias",
+                              "generator.basegen.m_source.l_linear.weight"], unused
+    worst = sorted(errs.items(), key=lambda kv: -kv[1])[:8]
+    print("worst parameter-gradient errors vs fp64 oracle:", worst)
+    tot = torch.cat([params[n].grad.flatten().double().cpu() for n in grads_ref])
+    tot_ref = torch.cat([grads_ref[n].flatten() for n in grads_ref])
+    print("all parameter gradients vs fp64 oracle:", rel_l2(tot, tot_ref))
+    assert rel_l2(tot, tot_ref) < GRAD_TOL, rel_l2(tot, tot_ref)
+    scale = float(tot_ref.norm())
+    for n, gr in grads_ref.items():  # per parameter, with an absolute floor for the zero-gradient ones
+        d = float((params[n].grad.double().cpu() - gr).norm())
+        well_conditioned = "amp_output_conv" in n or "amp_final_layer_norm" in n
+        tol = 5e-4 if well_conditioned else 3 * GRAD_TOL
+        assert d <= tol * float(gr.norm()) + 1e-5 * scale, (n, d, float(gr.norm()))
+    # the UNMODIFIED reference's gradients (norm per parameter)
+    gscale = float(np.sqrt((gold["norms"] ** 2).sum()))
+    for n, norm in zip([str(x) for x in gold["names"]], gold["norms"]):
+        gcpu = params[n].grad.detach().cpu()
+        assert abs(float(gcpu.norm()) - norm) <= 2 * GRAD_TOL * norm + 1e-5 * gscale, (n, float(gcpu.norm()), norm)
+    # BatchNorm running statistics were updated like nn.BatchNorm1d(momentum=0.1)
+    sd = sp.state_dict()
+    assert rel_l2(sd[BN + ".running_mean"], torch.from_numpy(gold["bn_running_mean"])) < 1e-4
+    assert rel_l2(sd[BN + ".running_var"], torch.from_numpy(gold["bn_running_var"])) < 1e-4
+
+
+@pytest.mark.gpu
+def test_full_size_training_step_is_finite():
+    """config 3 size: B=32, 258 tokens, 803 frames; forward + STFT losses + backward"""
+    from stylish_tts_b200 import spectral
+
+    dev = torch.device("cuda:0")
+    sp = st.build_model(st.default_model_config()).speech_predictor
+    synth.randomize_(sp, 0)
+    sp = sp.to(dev).train()
+    inp = synth.speech_inputs(32, 258, seed=1)
+    c = lambda t: t.to(dev)
+    out = sp(c(inp["texts"]), c(inp["text_lengths"]), c(inp["alignment"]), c(inp["pitch"]), c(inp["energy"]),
+             c(inp["voiced"]), c(inp["style"]), c(inp["denormal_pitch"]))
+    audio = out.audio.squeeze(1)
+    target = 0.1 * torch.randn(audio.shape, device=dev, generator=torch.Generator(device=dev).manual_seed(3))
+    ms = spectral.MultiSpectrogram(sample_rate=24000)
+    t_spec, p_spec, t_ph, p_ph, _, _ = ms(target=target, pred=audio)
+    mel = spectral.MultiResolutionSTFTLoss()(target_list=t_spec, pred_list=p_spec)
+    ph = spectral.multi_phase_loss(p_ph, t_ph)
+    total = 5.0 * mel / (mel.detach() + 1e-9) + 8.0 * ph / (ph.detach() + 1e-9)
+    total.backward()
+    torch.cuda.synchronize()
+    n = 0
+    for name, p in sp.named_parameters():
+        if "m_source" in name:
+            continue
+        assert p.grad is not None and torch.isfinite(p.grad).all(), name
+        n += p.grad.numel()
+    assert n > 12_000_000
+    assert torch.cuda.max_memory_allocated() < 150e9
