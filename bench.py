@@ -169,6 +169,116 @@ def run_reference(args):
     }), flush=True)
 
 
+TRAIN_METRIC = "train steps/sec (speech_predictor fwd+bwd + multi-res STFT/phase loss + AdamW)"
+
+
+def oracle_train_fn(tokens, seed=1):
+    """CPU arm of the training step: oracle forward (batch-stat BN) + spectral losses + autograd backward
+    for ONE utterance; returns (closure, audio seconds per call)."""
+    import torch
+    import stylish_tts_b200 as st
+    from stylish_tts_b200 import synth
+    from oracle import speech_oracle as so, spectral_oracle as spo
+
+    sp = st.build_model(st.default_model_config()).speech_predictor
+    synth.randomize_(sp, 0)
+    sd = {k: (v.detach().clone().requires_grad_(True) if v.is_floating_point() else v.clone())
+          for k, v in sp.state_dict().items()}
+    inp = synth.speech_inputs(1, tokens, seed=seed)
+    frames = inp["alignment"].shape[2]
+    target = 0.1 * torch.randn(1, frames * 300, generator=torch.Generator().manual_seed(3))
+    secs = frames * 300 / SAMPLE_RATE
+
+    def run():
+        for v in sd.values():
+            v.grad = None
+        audio = so.speech_predictor(sd, inp["texts"], inp["text_lengths"], inp["alignment"], inp["pitch"],
+                                    inp["energy"], inp["voiced"], inp["style"], inp["denormal_pitch"],
+                                    inp["draws"], bn_training=True)
+        ls = spo.acoustic_spectral_losses(target, audio.squeeze(1), SAMPLE_RATE)
+        spo.backwards_total(ls, dict(mel=5.0, multi_phase=8.0)).backward()
+    return run, secs
+
+
+def measure_train(args, dev, world, rank, barrier, steps, warmup, batch):
+    """config 3 / 5: one optimizer step of speech_predictor on `batch` 10-s utterances per GPU."""
+    import torch
+    import torch.distributed as dist
+    import stylish_tts_b200 as st
+    from stylish_tts_b200 import _lib, synth, spectral, optim
+
+    sp = st.build_model(st.default_model_config()).speech_predictor
+    synth.randomize_(sp, 0)
+    sp = sp.to(dev).train()
+    opt = optim.FlatAdamW(sp.parameters(), lr=1e-4, betas=(0.85, 0.99), eps=1e-9, weight_decay=1e-4,
+                          world_size=world)
+    host = synth.speech_inputs(batch, args.tokens, seed=11 + rank)
+    keys = ("texts", "text_lengths", "alignment", "pitch", "energy", "voiced", "style", "denormal_pitch")
+    frames = host["alignment"].shape[2]
+    target_h = (0.1 * torch.randn(batch, frames * 300, generator=torch.Generator().manual_seed(5 + rank)))
+    pinned = {k: host[k].pin_memory() for k in keys}
+    target_p = target_h.pin_memory()
+    resident = {k: host[k].to(dev) for k in keys}
+    target_d = target_h.to(dev)
+    ms_mod = spectral.MultiSpectrogram(sample_rate=SAMPLE_RATE)
+    stft_loss = spectral.MultiResolutionSTFTLoss()
+    loss_host = torch.empty(3, dtype=torch.float32).pin_memory()
+
+    def train_step(inp, target):
+        out = sp(*[inp[k] for k in keys])  # source noise drawn on the device, as the reference does
+        total, mel, ph = optim.acoustic_losses(out.audio.squeeze(1), target, ms_mod, stft_loss)
+        total.backward()
+        opt.step()
+        opt.zero_grad()
+        return torch.stack([total.detach(), mel.detach(), ph.detach()])
+
+    def step_resident():
+        return train_step(resident, target_d)
+
+    def step_e2e():
+        inp = {k: pinned[k].to(dev, non_blocking=True) for k in keys}
+        tgt = target_p.to(dev, non_blocking=True)
+        loss_host.copy_(train_step(inp, tgt), non_blocking=True)
+
+    def timed(fn):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        before = _lib.launches
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), _lib.launches - before
+
+    ms, launched = timed(step_resident)
+    ms_e2e, _ = timed(step_e2e)
+    torch.cuda.synchronize()
+    audio_s = batch * frames * 300 / SAMPLE_RATE
+    h2d = sum(pinned[k].numel() * pinned[k].element_size() for k in keys) + target_p.numel() * 4
+    res = {
+        "steps_per_s": steps / (ms / 1e3), "ms_per_step": ms / steps,
+        "trained_audio_s_per_s": world * audio_s * steps / (ms / 1e3),
+        "batch_per_gpu": batch, "global_batch": batch * world, "frames": frames,
+        "e2e": {"steps_per_s": steps / (ms_e2e / 1e3), "ms_per_step": ms_e2e / steps,
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 12},
+        "gpu_launches": launched, "grad_allreduce_bytes": opt.numel * 4 if world > 1 else 0,
+        "params": opt.numel, "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 1e9, 1),
+        "loss": [round(float(x), 5) for x in loss_host.tolist()],
+        "scope": "speech_predictor forward (batch-stat BN, regularisers off) + MultiSpectrogram x3 + mel & "
+                 "multi-phase losses (backwards_loss normalisation) + backward + fused AdamW; style vector "
+                 "given (style encoder E10 not built); adversarial terms out of scope (SURVEY 8f)",
+    }
+    del opt, sp
+    torch.cuda.empty_cache()
+    return res
+
+
 def conv_alg_bytes(info):
     n = info["B"] * info["T"] * (info["CI"] + info["CO"]) * 4
     if info["res"]:
@@ -303,8 +413,8 @@ def run_ours(args):
                         "avg_launch_ms": round(avg_s * 1e3, 4),
                         "share_of_step": round(v["ms"] / total, 4),
                         "fp32_tflops": round(flops / avg_s / 1e12, 2),
-                        "note": "fp32-FMA conv (parity-first); limited by the FP32 pipe, not HBM "
-                                "— see DESIGN.md"}
+                        "note": "tcgen05 bf16x3 conv when the name carries +umma (fp32 FMA otherwise); "
+                                "achieved = algorithmic bytes / CUDA-event time of the launch"}
         log(f"[bench] per-kernel device time of one step (event-timed, eager; total {total / 2:.2f} ms):")
         for k, v in ranked:
             log(f"    {v['ms'] / total * 100:6.2f}%  n={v['n'] // 2:3d}  avg {v['ms'] / v['n']:8.4f} ms  {k}")
@@ -316,6 +426,17 @@ def run_ours(args):
         except Exception as e:
             log("[bench] cpu baseline failed:", e)
 
+    train = None
+    had_graph = graph is not None
+    if not args.no_train:
+        had_graph, graph = graph is not None, None  # free the captured graph's memory pool first
+        torch.cuda.empty_cache()
+        try:
+            train = measure_train(args, dev, world, rank, barrier, max(3, min(args.steps, 5)), 3,
+                                  args.train_batch)
+        except Exception as e:
+            log(f"[bench] train measurement failed: {type(e).__name__}: {e}")
+
     if rank == 0:
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -326,7 +447,7 @@ def run_ours(args):
                        "batch_per_gpu": B, "tokens": T, "frames": frames,
                        "audio_s_per_step_per_gpu": audio_s, "parallelism": f"dp{world} (no collective)",
                        "weights": "random-init (seeded), reference architecture",
-                       "cuda_graph": graph is not None,
+                       "cuda_graph": had_graph,
                        "l2": "no flush needed: per-step working set (~6 GB of activations) >> 126 MB L2"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
@@ -335,6 +456,67 @@ def run_ours(args):
             "roofline": roofline,
             "cpu_baseline": cpu,
             "top_kernels": top,
+            "train": train,
+        }), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_train(args):
+    """--mode train: BASELINE configs[2] (1 GPU) / configs[4] (DDP, batch 32 per GPU, gradient all-reduce)."""
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    t0 = time.time()
+    tr = measure_train(args, dev, world, rank, barrier, args.steps, max(args.warmup, 3), args.train_batch)
+    clocks = sampler.stop(t0, time.time()) if rank == 0 else None
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        try:
+            cores = os.cpu_count() or 1
+            torch.set_num_threads(cores)
+            run, secs = oracle_train_fn(args.tokens)
+            t = time.perf_counter()
+            run()
+            dt = time.perf_counter() - t
+            cpu = {"value": 1.0 / (dt * args.train_batch), "unit": "steps/s", "cores": cores, "kind": "port",
+                   "sample": f"1 utterance ({secs:.2f} audio-s) fwd+loss+bwd through the CPU oracle took {dt:.2f} s; "
+                             f"a batch-{args.train_batch} step is extrapolated as {args.train_batch}x that"}
+        except Exception as e:
+            log("[bench] cpu train baseline failed:", e)
+    if rank == 0:
+        e2e = tr.pop("e2e")
+        print(json.dumps({
+            "metric": TRAIN_METRIC, "value": tr["steps_per_s"], "unit": "steps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": tr["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": ("configs[2]: full train step, batch 32, 1xB200" if world == 1 else
+                                    "configs[4]: DDP train, batch 32/GPU, 10 s utterances, NCCL gradient all-reduce"),
+                       "batch_per_gpu": tr["batch_per_gpu"], "global_batch": tr["global_batch"],
+                       "tokens": args.tokens, "frames": tr["frames"], "parallelism": f"dp{world}",
+                       "l2": "no flush needed: per-step working set (~28 GB) >> 126 MB L2"},
+            "e2e": {"value": e2e["steps_per_s"], "unit": "steps/s", "h2d_bytes_per_step": e2e["h2d_bytes_per_step"],
+                    "d2h_bytes_per_step": e2e["d2h_bytes_per_step"], "ms_per_step": e2e["ms_per_step"]},
+            "gpu_launches": tr["gpu_launches"], "clocks": clocks, "cpu_baseline": cpu, "train": tr,
         }), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -350,9 +532,16 @@ def main():
     ap.add_argument("--tokens", type=int, default=258)
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--mode", default="fwd", choices=["fwd", "train"],
+                    help="fwd: configs[1] (the headline line, plus a short `train` sub-measurement); "
+                         "train: configs[2]/[4] as the line itself")
+    ap.add_argument("--train-batch", type=int, default=32)
+    ap.add_argument("--no-train", action="store_true", help="skip the train sub-measurement of --mode fwd")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.mode == "train":
+        run_train(args)
     else:
         run_ours(args)
 

@@ -132,6 +132,7 @@ EXPORTED = tuple(_SIGNATURES) + tuple(_SPECIAL)
 
 _lib: Optional[C.CDLL] = None
 launches = 0  # number of kernel-launching C-ABI calls made (diagnostics / bench)
+param_epoch = 0  # bumped by optim.FlatAdamW.step: parameters changed in place, repack cached weights
 
 
 def load() -> C.CDLL:

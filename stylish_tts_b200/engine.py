@@ -335,7 +335,7 @@ class SpeechEngine:
 
     # parameters are repacked when any of them changed (optimizer step, load_state_dict)
     def packed(self, device) -> Packed:
-        key = (str(device),) + tuple(p._version for p in self.module.parameters()) + \
+        key = (str(device), L.param_epoch) + tuple(p._version for p in self.module.parameters()) + \
             tuple(b._version for b in self.module.buffers())
         if self._packed is None or key != self._packed_key:
             self._packed = Packed(self.module, device)
@@ -625,7 +625,7 @@ class _EngineBase:
         self._packed_key = None
 
     def packed(self, device):
-        key = (str(device),) + tuple(p._version for p in self.module.parameters()) + \
+        key = (str(device), L.param_epoch) + tuple(p._version for p in self.module.parameters()) + \
             tuple(b._version for b in self.module.buffers())
         if self._packed is None or key != self._packed_key:
             self._packed = self.pack_cls(self.module, device)

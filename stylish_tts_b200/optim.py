@@ -1,0 +1,93 @@
+"""Flat-arena AdamW + data-parallel gradient exchange for the training path.
+
+The reference builds one ``torch.optim.AdamW`` per model key (optimizers.py:106-117: lr 1e-4,
+weight_decay 1e-4, betas (0.85, 0.99), eps 1e-9) and lets HuggingFace accelerate wrap the modules in
+DDP, i.e. a NCCL sum all-reduce of the gradient buckets followed by a division by the world size
+(train_context.py:94-104).  Here every parameter of the wrapped modules lives in ONE flat fp32 arena
+(``p.data`` are views into it), the gradients of a step are packed into a second arena, exchanged with a
+single ``all_reduce`` over NVLink (the only collective of the data-parallel step) and applied
+by one fused kernel launch (``sty_adamw_step``) that also folds in the 1/world averaging.
+"""
+from __future__ import annotations
+
+from typing import Iterable, List, Optional
+
+import torch
+
+from . import _lib as L
+
+
+class FlatAdamW:
+    def __init__(self, params: Iterable[torch.nn.Parameter], *, lr=1e-4, betas=(0.85, 0.99), eps=1e-9,
+                 weight_decay=1e-4, process_group=None, world_size: Optional[int] = None):
+        self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
+        if not self.params:
+            raise ValueError("FlatAdamW: no trainable parameters")
+        self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
+        self.group = process_group
+        if world_size is None:
+            import torch.distributed as dist
+            world_size = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
+        self.world = world_size
+        dev = self.params[0].device
+        self.offsets, n = [], 0
+        for p in self.params:
+            self.offsets.append(n)
+            n += p.numel()
+        self.numel = n
+        self.flat = torch.empty(n, device=dev, dtype=torch.float32)
+        with torch.no_grad():
+            for p, o in zip(self.params, self.offsets):  # re-home the parameters inside the arena
+                self.flat[o:o + p.numel()].copy_(p.detach().reshape(-1))
+                p.data = self.flat[o:o + p.numel()].view(p.shape)
+        self.grad = torch.zeros(n, device=dev, dtype=torch.float32)
+        self.m = torch.zeros(n, device=dev, dtype=torch.float32)
+        self.v = torch.zeros(n, device=dev, dtype=torch.float32)
+        self.step_count = 0
+
+    # -- gradient plumbing (works on any device; the gloo tests exercise it on CPU) --------------
+    def pack_gradients(self) -> torch.Tensor:
+        """copy the per-parameter ``.grad`` tensors into the flat arena (missing gradients = 0, like
+        DDP's find_unused_parameters for ``m_source.l_linear``)"""
+        views = []
+        for p in self.params:
+            g = p.grad
+            views.append(torch.zeros(p.numel(), device=self.grad.device, dtype=torch.float32) if g is None
+                         else g.detach().reshape(-1))
+        torch.cat(views, out=self.grad)
+        return self.grad
+
+    def reduce_gradients(self) -> torch.Tensor:
+        """sum over ranks; the 1/world factor is applied inside the update kernel"""
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self.grad, op=dist.ReduceOp.SUM, group=self.group)
+        return self.grad
+
+    def zero_grad(self):
+        for p in self.params:
+            p.grad = None
+
+    # -- the update (CUDA only) -------------------------------------------------------------------
+    def step(self):
+        if not self.flat.is_cuda:
+            raise RuntimeError("stylish_tts_b200: FlatAdamW.step needs CUDA parameters (no CPU fallback)")
+        self.pack_gradients()
+        self.reduce_gradients()
+        self.step_count += 1
+        L.call("sty_adamw_step", self.flat.data_ptr(), self.grad.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
+               self.numel, self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay, self.step_count,
+               1.0 / self.world, L.stream_ptr())
+        L.param_epoch += 1  # the arena changed under the views: invalidates the engines' packed weights
+
+
+def acoustic_losses(audio_pred, audio_target, multi_spectrogram, stft_loss, *, w_mel=5.0, w_phase=8.0):
+    """mel + multi_phase terms of the acoustic stage with LossLog.backwards_loss normalisation
+    (stage_type.py:170-193, loss_log.py:82-94, weights config.yml:73-107).  -> (total, mel, phase)"""
+    from .spectral import multi_phase_loss
+
+    t_spec, p_spec, t_ph, p_ph, _, _ = multi_spectrogram(target=audio_target, pred=audio_pred)
+    mel = stft_loss(target_list=t_spec, pred_list=p_spec)
+    ph = multi_phase_loss(p_ph, t_ph)
+    total = w_mel * mel / (mel.detach() + 1e-9) + w_phase * ph / (ph.detach() + 1e-9)
+    return total, mel, ph
