@@ -372,6 +372,10 @@ typedef struct sty_conv1d_wgrad_args {
   float* dw;
   int32_t B, CI, CO, T, K, dil, pad, in_act;
   float out_scale;
+  /* != 0: use the tcgen05 kernel (bf16x3 split precision, time as the contraction axis, taps folded
+   * into the M side by an overlapping shared-memory descriptor) when CI % 8 == 0 and CO % 8 == 0;
+   * 0 or ineligible shapes: fp32 FMA kernel (K in {1,3,5,7,11,21}). */
+  int32_t tensor_cores;
 } sty_conv1d_wgrad_args;
 STY_API int sty_conv1d_wgrad(const sty_conv1d_wgrad_args* a, sty_stream_t stream);
 

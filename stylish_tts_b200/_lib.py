@@ -51,7 +51,7 @@ class WgradArgs(C.Structure):
         ("in_scale", _f32p), ("in_shift", _f32p), ("in_alpha", _f32p), ("in_mask", _f32p),
         ("out_mask", _f32p), ("dw", _f32p),
         ("B", _i32), ("CI", _i32), ("CO", _i32), ("T", _i32), ("K", _i32), ("dil", _i32),
-        ("pad", _i32), ("in_act", _i32), ("out_scale", _f32),
+        ("pad", _i32), ("in_act", _i32), ("out_scale", _f32), ("tensor_cores", _i32),
     ]
 
 
@@ -188,6 +188,9 @@ profile_log = None  # set to a list to time every call with CUDA events (bench.p
 
 
 def _signature(name: str, args) -> str:
+    if name == "sty_conv1d_wgrad":
+        a = args[0]._obj
+        return f"conv1d_wgrad[ci={a.CI},co={a.CO},k={a.K},d={a.dil},B={a.B},T={a.T}{'+umma' if a.tensor_cores else ''}]"
     if name == "sty_conv1d_fwd":
         a = args[0]._obj
         extra = ""

@@ -640,12 +640,18 @@ adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restri
 
 using namespace sty;
 
+namespace sty {
+bool conv1d_wgrad_umma_eligible(const sty_conv1d_wgrad_args& a);  // wgrad_umma.cu
+int conv1d_wgrad_umma_launch(const sty_conv1d_wgrad_args& a, cudaStream_t st);
+}  // namespace sty
+
 extern "C" int sty_conv1d_wgrad(const sty_conv1d_wgrad_args* a, sty_stream_t stream) {
   STY_REQUIRE(a && a->x && a->dy && a->dw, "conv1d_wgrad: null pointer");
   STY_REQUIRE(a->B > 0 && a->CI > 0 && a->CO > 0 && a->T > 0 && a->dil >= 1, "conv1d_wgrad: bad shape");
   STY_REQUIRE(2 * a->pad == (a->K - 1) * a->dil, "conv1d_wgrad: only 'same' padding is supported");
   STY_REQUIRE(a->in_act != STY_ACT_SNAKE || a->in_alpha, "conv1d_wgrad: snake prologue needs in_alpha");
   cudaStream_t st = as_stream(stream);
+  if (conv1d_wgrad_umma_eligible(*a)) return conv1d_wgrad_umma_launch(*a, st);
   switch (a->K) {
     case 1: return launch_wgrad<1, 8>(*a, st);
     case 3: return launch_wgrad<3, 8>(*a, st);

@@ -35,7 +35,7 @@ def transposed_weight(w_oik: torch.Tensor) -> ConvW:
 
 
 def wgrad(x, dy, K, dil, *, in_scale=None, in_shift=None, in_alpha=None, in_act=ACT_NONE, in_mask=None,
-          out_mask=None, out_scale=1.0):
+          out_mask=None, out_scale=1.0, umma=True):
     """-> dw (CO, CI, K) of a stride-1 'same' Conv1d (reference layout)."""
     B, CI, T = x.shape
     CO = dy.shape[1]
@@ -49,6 +49,8 @@ def wgrad(x, dy, K, dil, *, in_scale=None, in_shift=None, in_alpha=None, in_act=
     a.in_mask, a.out_mask, a.dw = L.ptr(in_mask), L.ptr(out_mask), dw.data_ptr()
     a.B, a.CI, a.CO, a.T, a.K, a.dil, a.pad, a.in_act = B, CI, CO, T, K, dil, (K - 1) * dil // 2, in_act
     a.out_scale = out_scale
+    from . import engine as E
+    a.tensor_cores = int(bool(umma and E.USE_UMMA))
     L.call("sty_conv1d_wgrad", C.byref(a), L.stream_ptr())
     return dw
 
@@ -167,7 +169,7 @@ class ConvFn(Function):
         d_w = None
         if need[1]:
             d_w = wgrad(x, g, K, dil, in_scale=scale, in_shift=shift, in_alpha=al, in_act=in_act,
-                        in_mask=in_mask, out_mask=out_mask, out_scale=out_scale)
+                        in_mask=in_mask, out_mask=out_mask, out_scale=out_scale, umma=umma)
         d_x = d_gb = d_alpha = d_bnw = d_bnb = None
         want_stats = norm is not None or (al is not None and need[4])
         if need[0] or want_stats:
@@ -235,7 +237,7 @@ class ConvNeXtTailFn(Function):
         J = w1.shape[0]
         dout = dout.contiguous()
         d_b2f = channel_sum(dout)
-        d_w2 = wgrad(hb, dout, 1, 1, in_scale=gs)[:, :, 0]
+        d_w2 = wgrad(hb, dout, 1, 1, in_scale=gs, umma=umma)[:, :, 0]
         g_u = conv1d(dout, transposed_weight(w2.unsqueeze(-1)), umma=umma)  # (B,J,T)
         r = _new((B, J), y)
         L.call("sty_row_dot", g_u.data_ptr(), hb.data_ptr(), r.data_ptr(), B * J, T, L.stream_ptr())
@@ -253,7 +255,7 @@ class ConvNeXtTailFn(Function):
         d_h = g_u
         del h
         d_b1 = channel_sum(d_h)
-        d_w1 = wgrad(y, d_h, 1, 1)[:, :, 0]
+        d_w1 = wgrad(y, d_h, 1, 1, umma=umma)[:, :, 0]
         d_y = conv1d(d_h, transposed_weight(w1.unsqueeze(-1)), umma=umma)
         return d_y, dout, d_w1, d_b1, d_alpha, d_gamma, d_w2, d_b2f, None
 

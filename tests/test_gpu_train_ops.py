@@ -260,3 +260,37 @@ def test_istft_head():
     b_im = bufs.weight_backward_imag.reshape(-1, 64).contiguous().cuda()
     out = T.IstftHeadFn.apply(lc, rc, b_re, b_im, 4)
     check(dict(logamp=(lr, lc), ri=(rr, rc)), ref, out, rn(gen, B, 1, 4 * S))
+
+
+@pytest.mark.parametrize("ci,co,k,dil,T_", [
+    (32, 32, 21, 1, 1000), (32, 32, 11, 3, 777), (32, 32, 11, 5, 640), (96, 32, 21, 1, 700), (32, 64, 21, 1, 600),
+    (32, 128, 1, 1, 1111), (128, 32, 1, 1, 513), (256, 1024, 1, 1, 203), (1024, 256, 1, 1, 203),
+    (128, 512, 3, 1, 258), (512, 128, 3, 1, 258), (128, 128, 5, 1, 258), (64, 160, 11, 1, 600),
+    (128, 256, 21, 1, 300), (48, 24, 3, 1, 515), (256, 384, 11, 1, 100), (32, 32, 7, 2, 90),
+])
+@pytest.mark.parametrize("pro", [False, True])
+def test_wgrad_tensor_core_vs_fp64(ci, co, k, dil, T_, pro):
+    """sty_conv1d_wgrad on the tcgen05 path (taps folded into the M side) against fp64 autograd, and against
+    the fp32 FMA kernel where that one is built"""
+    gen = g(12)
+    B = 3
+    x, dy = rn(gen, B, ci, T_), rn(gen, B, co, T_)
+    lens = torch.tensor([T_, T_ - 21, T_ // 2])
+    mask = so.sequence_mask(lens, T_).float()
+    kw = {}
+    xin = x.double()
+    gy = dy.double()
+    if pro:
+        sc, sh, al = 1 + 0.3 * rn(gen, B, ci), 0.2 * rn(gen, B, ci), 1 + 0.2 * rn(gen, ci)
+        xin = so.snake(sc.double()[:, :, None] * (xin * mask.double()[:, None]) + sh.double()[:, :, None],
+                       al.double().view(1, -1, 1))
+        gy = gy * mask.double()[:, None] * 0.7
+        kw = dict(in_scale=sc.cuda(), in_shift=sh.cuda(), in_alpha=al.cuda(), in_act=L.ACT_SNAKE,
+                  in_mask=mask.cuda(), out_mask=mask.cuda(), out_scale=0.7)
+    w = torch.zeros(co, ci, k, dtype=torch.float64, requires_grad=True)
+    (F.conv1d(xin, w, padding=(k - 1) * dil // 2, dilation=dil) * gy).sum().backward()
+    dw_tc = T.wgrad(x.cuda(), dy.cuda(), k, dil, umma=True, **kw)
+    assert rel_l2(dw_tc, w.grad) < 5e-5, rel_l2(dw_tc, w.grad)
+    if k in (1, 3, 5, 7, 11, 21):
+        dw_simt = T.wgrad(x.cuda(), dy.cuda(), k, dil, umma=False, **kw)
+        assert rel_l2(dw_simt, w.grad) < 2e-5
