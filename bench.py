@@ -169,7 +169,7 @@ def run_reference(args):
     }), flush=True)
 
 
-TRAIN_METRIC = "train steps/sec (speech_predictor fwd+bwd + multi-res STFT/phase loss + AdamW)"
+TRAIN_METRIC = "train steps/sec (acoustic step: fwd+bwd + multi-res STFT/phase loss + AdamW)"
 
 
 def oracle_train_fn(tokens, seed=1):
@@ -178,22 +178,33 @@ def oracle_train_fn(tokens, seed=1):
     import torch
     import stylish_tts_b200 as st
     from stylish_tts_b200 import synth
-    from oracle import speech_oracle as so, spectral_oracle as spo
+    from oracle import speech_oracle as so, spectral_oracle as spo, style_oracle as sto
 
-    sp = st.build_model(st.default_model_config()).speech_predictor
+    nets = st.build_model(st.default_model_config())
+    sp, se = nets.speech_predictor, nets.speech_style_encoder
     synth.randomize_(sp, 0)
-    sd = {k: (v.detach().clone().requires_grad_(True) if v.is_floating_point() else v.clone())
-          for k, v in sp.state_dict().items()}
+    synth.converge_spectral_(se)
+    grad = lambda m: {k: (v.detach().clone().requires_grad_(k.split(".")[-1] not in ("weight_u", "weight_v")
+                                                            and "running" not in k)
+                          if v.is_floating_point() else v.clone()) for k, v in m.state_dict().items()}
+    sd, sde = grad(sp), grad(se)
     inp = synth.speech_inputs(1, tokens, seed=seed)
     frames = inp["alignment"].shape[2]
     target = 0.1 * torch.randn(1, frames * 300, generator=torch.Generator().manual_seed(3))
     secs = frames * 300 / SAMPLE_RATE
 
     def run():
-        for v in sd.values():
+        for v in list(sd.values()) + list(sde.values()):
             v.grad = None
+        with torch.no_grad():  # calculate_mel x2 + energy (stage_type.py:75-97)
+            mel = spo.calculate_mel(target, n_fft=512, win=512, hop=300, n_mels=80, sample_rate=SAMPLE_RATE,
+                                    mean=-4.0, std=4.0)
+            style_mel = spo.calculate_mel(target, n_fft=2048, win=1200, hop=300, n_mels=80,
+                                          sample_rate=SAMPLE_RATE, mean=-4.0, std=4.0)
+            spo.log_energy(mel, -4.0, 4.0)
+        style = sto.mel_style_encoder(sde, style_mel.unsqueeze(1), training=True)
         audio = so.speech_predictor(sd, inp["texts"], inp["text_lengths"], inp["alignment"], inp["pitch"],
-                                    inp["energy"], inp["voiced"], inp["style"], inp["denormal_pitch"],
+                                    inp["energy"], inp["voiced"], style, inp["denormal_pitch"],
                                     inp["draws"], bn_training=True)
         ls = spo.acoustic_spectral_losses(target, audio.squeeze(1), SAMPLE_RATE)
         spo.backwards_total(ls, dict(mel=5.0, multi_phase=8.0)).backward()
@@ -207,38 +218,48 @@ def measure_train(args, dev, world, rank, barrier, steps, warmup, batch):
     import stylish_tts_b200 as st
     from stylish_tts_b200 import _lib, synth, spectral, optim
 
-    sp = st.build_model(st.default_model_config()).speech_predictor
+    from types import SimpleNamespace
+    from stylish_tts_b200 import train_step as ts
+
+    mc = st.default_model_config()
+    nets = st.build_model(mc)
+    sp, se = nets.speech_predictor, nets.speech_style_encoder
     synth.randomize_(sp, 0)
-    sp = sp.to(dev).train()
-    opt = optim.FlatAdamW(sp.parameters(), lr=1e-4, betas=(0.85, 0.99), eps=1e-9, weight_decay=1e-4,
-                          world_size=world)
+    synth.converge_spectral_(se)
+    sp, se = sp.to(dev).train(), se.to(dev).train()
+    # acoustic stage: speech_predictor + speech_style_encoder are trained (stage_type.py:393-410)
+    opt = optim.FlatAdamW(list(sp.parameters()) + list(se.parameters()), lr=1e-4, betas=(0.85, 0.99), eps=1e-9,
+                          weight_decay=1e-4, world_size=world)
+    fe = ts.FrontEnd(mc)
     host = synth.speech_inputs(batch, args.tokens, seed=11 + rank)
-    keys = ("texts", "text_lengths", "alignment", "pitch", "energy", "voiced", "style", "denormal_pitch")
-    frames = host["alignment"].shape[2]
-    target_h = (0.1 * torch.randn(batch, frames * 300, generator=torch.Generator().manual_seed(5 + rank)))
-    pinned = {k: host[k].pin_memory() for k in keys}
-    target_p = target_h.pin_memory()
-    resident = {k: host[k].to(dev) for k in keys}
-    target_d = target_h.to(dev)
-    ms_mod = spectral.MultiSpectrogram(sample_rate=SAMPLE_RATE)
-    stft_loss = spectral.MultiResolutionSTFTLoss()
+    dur = torch.full((batch, args.tokens), 3.0)
+    dur[:, ::9] += 1.0  # the durations synth.speech_inputs builds its alignment from
+    frames = int(dur[0].sum())
+    pitch = host["pitch"]
+    if frames % 2:  # calculate_mel keeps an even number of frames (utils.py:829-830): the data path's audio is
+        dur[:, -1] += 1.0  # binned accordingly; make the synthetic utterance one frame longer
+        frames += 1
+        pitch = torch.cat([pitch, pitch[:, -1:]], 1)
+    hb = dict(audio_gt=0.1 * torch.randn(batch, frames * 300, generator=torch.Generator().manual_seed(5 + rank)),
+              text=host["texts"], text_length=host["text_lengths"], pitch=pitch, alignment=dur.unsqueeze(1))
+    assert pitch.shape[1] == frames
+    pinned = {k: v.pin_memory() for k, v in hb.items()}
+    resident = {k: v.to(dev) for k, v in hb.items()}
     loss_host = torch.empty(3, dtype=torch.float32).pin_memory()
 
-    def train_step(inp, target):
-        out = sp(*[inp[k] for k in keys])  # source noise drawn on the device, as the reference does
-        total, mel, ph = optim.acoustic_losses(out.audio.squeeze(1), target, ms_mod, stft_loss)
-        total.backward()
+    def train_step(b):
+        out = ts.acoustic_step(SimpleNamespace(**b), nets, fe)  # source noise drawn on the device (reference too)
+        out.total.backward()
         opt.step()
         opt.zero_grad()
-        return torch.stack([total.detach(), mel.detach(), ph.detach()])
+        return torch.stack([out.total.detach(), out.mel.detach(), out.multi_phase.detach()])
 
     def step_resident():
-        return train_step(resident, target_d)
+        return train_step(resident)
 
     def step_e2e():
-        inp = {k: pinned[k].to(dev, non_blocking=True) for k in keys}
-        tgt = target_p.to(dev, non_blocking=True)
-        loss_host.copy_(train_step(inp, tgt), non_blocking=True)
+        loss_host.copy_(train_step({k: v.to(dev, non_blocking=True) for k, v in pinned.items()}),
+                        non_blocking=True)
 
     def timed(fn):
         for _ in range(warmup):
@@ -260,7 +281,7 @@ def measure_train(args, dev, world, rank, barrier, steps, warmup, batch):
     ms_e2e, _ = timed(step_e2e)
     torch.cuda.synchronize()
     audio_s = batch * frames * 300 / SAMPLE_RATE
-    h2d = sum(pinned[k].numel() * pinned[k].element_size() for k in keys) + target_p.numel() * 4
+    h2d = sum(v.numel() * v.element_size() for v in pinned.values())
     res = {
         "steps_per_s": steps / (ms / 1e3), "ms_per_step": ms / steps,
         "trained_audio_s_per_s": world * audio_s * steps / (ms / 1e3),
@@ -270,11 +291,12 @@ def measure_train(args, dev, world, rank, barrier, steps, warmup, batch):
         "gpu_launches": launched, "grad_allreduce_bytes": opt.numel * 4 if world > 1 else 0,
         "params": opt.numel, "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 1e9, 1),
         "loss": [round(float(x), 5) for x in loss_host.tolist()],
-        "scope": "speech_predictor forward (batch-stat BN, regularisers off) + MultiSpectrogram x3 + mel & "
-                 "multi-phase losses (backwards_loss normalisation) + backward + fused AdamW; style vector "
-                 "given (style encoder E10 not built); adversarial terms out of scope (SURVEY 8f)",
+        "scope": "AcousticStep(use_predicted_pe=False, predict_audio=True): calculate_mel x2 + energy + alignment "
+                 "+ speech_style_encoder + speech_predictor (batch-stat BN, stochastic regularisers off) + "
+                 "MultiSpectrogram x3 + mel & multi-phase losses (backwards_loss normalisation) + backward of "
+                 "both modules + fused AdamW; adversarial / SLM terms out of scope (SURVEY 8f)",
     }
-    del opt, sp
+    del opt, sp, se, nets
     torch.cuda.empty_cache()
     return res
 

@@ -448,6 +448,31 @@ STY_API int sty_adamw_step(float* p, const float* g, float* m, float* v, int64_t
                            float beta2, float eps, float weight_decay, int step, float grad_scale,
                            sty_stream_t stream);
 
+/* =====================================================================================
+ * Mel style encoder (mel_style_encoder.py:121-152): images are kept "row-channel",
+ * X[b, r, c, w] contiguous (B, Hp = H+2, C, W) with zero border rows, so that an R x K Conv2d is
+ * sty_conv1d_fwd on R consecutive rows seen as R*C stacked channels (overlapping strided view).
+ * ===================================================================================== */
+/* gradient of that overlapping view back to the image: dx[b,r,c,w] = sum_{k<R} g[b*Hp + r - k][k*C + c][w],
+ * g: (B*Hp - (R-1), R*C, W) contiguous */
+STY_API int sty_fold_rows(const float* g, float* dx, int R, int B, int Hp, int C, int W, sty_stream_t stream);
+/* learned downsampling: depthwise Conv2d 3x3, stride 2, padding 1 (mel_style_encoder.py:28-38);
+ * y: (B, Ho+2, C, Wo), Ho = (H-1)/2+1, Wo = (W-1)/2+1; w (C,9), bias (C) or NULL.
+ * bwd: dx (may be NULL), dw (C,9) and db (C, may be NULL) accumulated (the caller zeroes them). */
+STY_API int sty_dwconv3x3s2_fwd(const float* x, const float* w, const float* bias, float* y, int B, int Hp, int C,
+                                int W, sty_stream_t stream);
+STY_API int sty_dwconv3x3s2_bwd(const float* dy, const float* x, const float* w, float* dx, float* dw, float* db,
+                                int B, int Hp, int C, int W, sty_stream_t stream);
+/* F.avg_pool2d(x, 2) with the last column replicated when W is odd (mel_style_encoder.py:57-60); H even */
+STY_API int sty_avgpool2_fwd(const float* x, float* y, int B, int Hp, int C, int W, sty_stream_t stream);
+STY_API int sty_avgpool2_bwd(const float* dy, float* dx, int B, int Hp, int C, int W, sty_stream_t stream);
+/* mean over rows [r0,r0+Rn) x columns [w0,w0+Wn): the valid region of the 5x5 conv followed by
+ * AdaptiveAvgPool2d(1) (mel_style_encoder.py:140-141) -> (B,C); bwd fills dx (B,Hp,C,W) */
+STY_API int sty_region_mean_fwd(const float* x, float* out, int B, int Hp, int C, int W, int r0, int Rn, int w0,
+                                int Wn, sty_stream_t stream);
+STY_API int sty_region_mean_bwd(const float* g, float* dx, int B, int Hp, int C, int W, int r0, int Rn, int w0,
+                                int Wn, sty_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -121,6 +121,14 @@ _SIGNATURES = {
     "sty_istft_head_bwd": [_f32p, _f32p, _f32p, _i64, _f32p, _f32p, _i64, _f32p, _f32p, _f32p, _f32p, _f32p,
                            _i64, _i32, _i32, _i32, _i32, _i32, _f32p],
     "sty_adamw_step": [_f32p, _f32p, _f32p, _f32p, _i64, _f32, _f32, _f32, _f32, _f32, _i32, _f32, _f32p],
+    # mel style encoder (row-channel images)
+    "sty_fold_rows": [_f32p, _f32p, _i32, _i32, _i32, _i32, _i32, _f32p],
+    "sty_dwconv3x3s2_fwd": [_f32p, _f32p, _f32p, _f32p, _i32, _i32, _i32, _i32, _f32p],
+    "sty_dwconv3x3s2_bwd": [_f32p, _f32p, _f32p, _f32p, _f32p, _f32p, _i32, _i32, _i32, _i32, _f32p],
+    "sty_avgpool2_fwd": [_f32p, _f32p, _i32, _i32, _i32, _i32, _f32p],
+    "sty_avgpool2_bwd": [_f32p, _f32p, _i32, _i32, _i32, _i32, _f32p],
+    "sty_region_mean_fwd": [_f32p, _f32p, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _f32p],
+    "sty_region_mean_bwd": [_f32p, _f32p, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _f32p],
     "sty_stft_loss_finalize": [_f32p, _f32p, _f32p, _i32, _f32, _f32, _i32, _f32p, _f32p],
 }
 _SPECIAL = {

@@ -255,9 +255,9 @@ prologue_bwd_apply_kernel(const float* __restrict__ dxp, const float* __restrict
                           const float* __restrict__ c0, const float* __restrict__ c1,
                           const float* __restrict__ add, int64_t add_bs, int64_t add_cs, float* __restrict__ dx,
                           int64_t dx_bs, int64_t dx_cs, int C, int T, int act) {
-  const int bc = blockIdx.y;
+  const int bc = blockIdx.x;
   const int b = bc / C, c = bc % C;
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int t = blockIdx.y * blockDim.x + threadIdx.x;
   if (t >= T) return;
   const float xv = x[(int64_t)b * x_bs + (int64_t)c * x_cs + t];
   const float m = mask ? mask[(int64_t)b * T + t] : 1.f;
@@ -708,8 +708,8 @@ extern "C" int sty_prologue_bwd_apply(const float* dxp, const float* x, int64_t 
                                       int B, int C, int T, int act, sty_stream_t stream) {
   STY_REQUIRE(dxp && x && dx && B > 0 && C > 0 && T > 0, "prologue_bwd_apply: bad argument");
   STY_REQUIRE(act != STY_ACT_SNAKE || alpha, "prologue_bwd_apply: snake needs alpha");
-  STY_REQUIRE((int64_t)B * C <= 65535, "prologue_bwd_apply: B*C too large for the grid");
-  dim3 grid(cdiv(T, 256), B * C);
+  STY_REQUIRE(cdiv(T, 256) <= 65535, "prologue_bwd_apply: T too large for the grid");
+  dim3 grid((unsigned)((int64_t)B * C), cdiv(T, 256));
   prologue_bwd_apply_kernel<<<grid, 256, 0, as_stream(stream)>>>(dxp, x, x_bs, x_cs, scale, shift, alpha, mask, c0,
                                                                  c1, add, add_bs, add_cs, dx, dx_bs, dx_cs, C, T,
                                                                  act);

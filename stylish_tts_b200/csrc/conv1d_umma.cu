@@ -585,7 +585,7 @@ static int umma_out_mode(const sty_conv1d_args& a) {
 }
 
 bool conv1d_umma_eligible(const sty_conv1d_args& a) {
-  if (!a.w_split || a.w_bs != 0 || a.T < 128) return false;
+  if (!a.w_split || a.w_bs != 0 || a.T < 64) return false;
   if (umma_in_mode(a) < 0 || umma_out_mode(a) < 0) return false;
   UmmaPlan pl;
   return make_plan(a, pl);

@@ -23,10 +23,13 @@ constexpr int kWgThreads = 512;
 constexpr int kTT = 128;  // time steps per chunk
 
 struct WgPlan {
-  int mode;        // 0: taps on the M side (K >= 2) | 1: K == 1, M side = input | 2: K == 1, M side = grad
+  int mode;        // 0: taps folded into the M side (K >= 8) | 1: K == 1, M side = input | 2: K == 1, M side = grad
+                   // 3: 2 <= K < 8: M side = grad (128 channels), one accumulator per tap, the tap shift is the
+                   //    start row of the N-side (input) descriptor
   int m_groups;    // staged 8-channel groups of the M side
   int n_groups;    // staged 8-channel groups of the N side (N = 8 * n_groups, multiple of 16)
   int rows_m;      // staged time steps of the M side
+  int rows_n;      // staged time steps of the N side
   int tap_chunks;  // ceil(K / 16) in mode 0
   int n_acc;       // accumulators (N columns each)
   int acc_cols;    // TMEM columns allocated (power of two >= 32)
@@ -118,7 +121,7 @@ conv1d_wgrad_umma_kernel(const sty_conv1d_wgrad_args p, const WgPlan pl) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   uint4* stage0 = reinterpret_cast<uint4*>(smem_raw);
   float* prm = reinterpret_cast<float*>(stage0 + (size_t)pl.stages * pl.stage_u4);  // [3][8*input groups]
-  const int in_groups = pl.mode == 2 ? pl.n_groups : pl.m_groups;
+  const int in_groups = pl.mode >= 2 ? pl.n_groups : pl.m_groups;
   uint64_t* bars = reinterpret_cast<uint64_t*>(prm + ((3 * 8 * in_groups + 3) & ~3));
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -126,7 +129,7 @@ conv1d_wgrad_umma_kernel(const sty_conv1d_wgrad_args p, const WgPlan pl) {
 
   const int m_tile = blockIdx.y / pl.n_tiles, n_tile = blockIdx.y % pl.n_tiles;
   const int m0 = m_tile * pl.m_groups * 8, n0 = n_tile * N;  // first channel of the M / N side
-  const int ci0 = pl.mode == 2 ? n0 : m0;                     // first INPUT channel of this tile
+  const int ci0 = pl.mode >= 2 ? n0 : m0;                     // first INPUT channel of this tile
 
   if (warp == 0) tmem_alloc(tmem_slot, (uint32_t)pl.acc_cols);
   if (tid == 0) {
@@ -145,7 +148,7 @@ conv1d_wgrad_umma_kernel(const sty_conv1d_wgrad_args p, const WgPlan pl) {
   const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
                          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   const int m_plane = pl.m_groups * pl.rows_m;  // uint4 per split plane of the M side
-  const int n_plane = pl.n_groups * kTT;
+  const int n_plane = pl.n_groups * pl.rows_n;
   const uint32_t sbo_m = pl.mode == 0 ? (uint32_t)p.dil : (uint32_t)pl.rows_m;
 
   int cur_b = -1;
@@ -178,9 +181,9 @@ conv1d_wgrad_umma_kernel(const sty_conv1d_wgrad_args p, const WgPlan pl) {
       const float* im = p.in_mask ? p.in_mask + (int64_t)b * p.T : nullptr;
       const float* om = p.out_mask ? p.out_mask + (int64_t)b * p.T : nullptr;
       SideDesc sm_, sn_;
-      if (pl.mode == 2) {  // M side = output gradient, N side = input
+      if (pl.mode >= 2) {  // M side = output gradient, N side = input
         sm_ = SideDesc{Ms, gb, om, p.dy_cs, p.CO, m0, pl.m_groups, pl.rows_m, kTT, t0, 0};
-        sn_ = SideDesc{Ns, xb, im, p.x_cs, p.CI, n0, pl.n_groups, kTT, kTT, t0 - p.pad, 1};
+        sn_ = SideDesc{Ns, xb, im, p.x_cs, p.CI, n0, pl.n_groups, pl.rows_n, pl.valid_rows, t0 - p.pad, 1};
       } else {             // M side = input (taps folded by the descriptor), N side = output gradient
         sm_ = SideDesc{Ms, xb, im, p.x_cs, p.CI, m0, pl.m_groups, pl.rows_m, pl.valid_rows, t0 - p.pad, 1};
         sn_ = SideDesc{Ns, gb, om, p.dy_cs, p.CO, n0, pl.n_groups, kTT, kTT, t0, 0};
@@ -192,10 +195,11 @@ conv1d_wgrad_umma_kernel(const sty_conv1d_wgrad_args p, const WgPlan pl) {
     if (tid == 0) {
       tc_fence_after();
       const uint32_t m_addr = smem_u32(Ms), n_addr = smem_u32(Ns);
-      const uint64_t bd = make_desc(n_addr, 8u, (uint32_t)kTT);
-      const uint32_t b_hi32 = (uint32_t)(bd >> 32), b_lo = (uint32_t)bd;
+      const uint64_t bd = make_desc(n_addr, 8u, (uint32_t)pl.rows_n);
+      const uint32_t b_hi32 = (uint32_t)(bd >> 32);
       const uint32_t first = it == 0 ? 0u : 1u;
       for (int acc = 0; acc < pl.n_acc; ++acc) {
+        const uint32_t b_lo = (uint32_t)bd + (pl.mode == 3 ? (uint32_t)(acc * p.dil) : 0u);  // mode 3: tap = acc
         // mode 0: accumulator (g, tc) = input-channel group g seen through taps [16 tc, 16 tc + 16)
         const int g = pl.mode == 0 ? acc / pl.tap_chunks : 0;
         const int tc = pl.mode == 0 ? acc - g * pl.tap_chunks : 0;
@@ -244,6 +248,13 @@ conv1d_wgrad_umma_kernel(const sty_conv1d_wgrad_args p, const WgPlan pl) {
         for (int j = 0; j < 16; ++j)
           if (row_ok && co_base + j < p.CO)
             atomicAdd(p.dw + ((int64_t)(co_base + j) * p.CI + ci) * p.K + tap, r[j]);
+      } else if (pl.mode == 3) {
+        const int co = m0 + m;
+        const int ci_base = n0 + nn;
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (co < p.CO && ci_base + j < p.CI)
+            atomicAdd(p.dw + ((int64_t)co * p.CI + ci_base + j) * p.K + acc, r[j]);
       } else if (pl.mode == 1) {
         ci = m0 + m;
         co_base = n0 + nn;
@@ -276,7 +287,7 @@ bool make_wg_plan(const sty_conv1d_wgrad_args& a, WgPlan& pl) {
     pl.mode = a.CO >= a.CI ? 2 : 1;
     const int Cm = pl.mode == 2 ? a.CO : a.CI, Cn = pl.mode == 2 ? a.CI : a.CO;
     pl.m_groups = 16;
-    pl.rows_m = kTT;
+    pl.rows_m = pl.rows_n = kTT;
     pl.valid_rows = kTT;
     pl.tap_chunks = 1;
     pl.n_acc = 1;
@@ -286,8 +297,24 @@ bool make_wg_plan(const sty_conv1d_wgrad_args& a, WgPlan& pl) {
     pl.n_groups = ng;
     pl.m_tiles = cdiv(Cm, 128);
     pl.n_tiles = cdiv(Cn, 8 * ng);
+  } else if (a.K < 8) {
+    pl.mode = 3;
+    pl.m_groups = 16;
+    pl.rows_m = kTT;
+    pl.valid_rows = pl.rows_n = kTT + (a.K - 1) * a.dil;
+    pl.tap_chunks = 1;
+    pl.n_acc = a.K;
+    int ng = (512 / a.K) / 16 * 2;  // N = 8*ng: multiple of 16, K accumulators within 512 TMEM columns
+    if (ng > 32) ng = 32;
+    int need = cdiv(a.CI, 8);
+    if (need & 1) ++need;
+    if (ng > need) ng = need;
+    pl.n_groups = ng;
+    pl.m_tiles = cdiv(a.CO, 128);
+    pl.n_tiles = cdiv(a.CI, 8 * ng);
   } else {
     pl.mode = 0;
+    pl.rows_n = kTT;
     pl.tap_chunks = cdiv(a.K, 16);
     pl.valid_rows = kTT + (a.K - 1) * a.dil;
     pl.rows_m = kTT + (16 * pl.tap_chunks - 1) * a.dil;
@@ -307,8 +334,8 @@ bool make_wg_plan(const sty_conv1d_wgrad_args& a, WgPlan& pl) {
   pl.acc_cols = 32;
   while (pl.acc_cols < pl.n_acc * pl.n_groups * 8) pl.acc_cols <<= 1;
   if (pl.acc_cols > 512) return false;
-  pl.stage_u4 = 2 * (pl.m_groups * pl.rows_m + pl.n_groups * kTT);
-  const int in_groups = pl.mode == 2 ? pl.n_groups : pl.m_groups;
+  pl.stage_u4 = 2 * (pl.m_groups * pl.rows_m + pl.n_groups * pl.rows_n);
+  const int in_groups = pl.mode >= 2 ? pl.n_groups : pl.m_groups;
   const size_t misc = (size_t)((3 * 8 * in_groups + 3) & ~3) * 4 + 64;
   const size_t st = (size_t)pl.stage_u4 * 16;
   if (2 * st + misc <= kWgSmemBudget) pl.stages = 2;
@@ -336,7 +363,7 @@ int conv1d_wgrad_umma_launch(const sty_conv1d_wgrad_args& a, cudaStream_t st) {
     sms = sty_device_sm_count();
     if (sms <= 0) sms = 148;
   }
-  const int in_groups = pl.mode == 2 ? pl.n_groups : pl.m_groups;
+  const int in_groups = pl.mode >= 2 ? pl.n_groups : pl.m_groups;
   const size_t smem = (size_t)pl.stages * pl.stage_u4 * 16 + (size_t)((3 * 8 * in_groups + 3) & ~3) * 4 + 64;
   cudaFuncSetAttribute(conv1d_wgrad_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const int tiles = pl.m_tiles * pl.n_tiles;

@@ -22,7 +22,7 @@ from ._lib import ACT_LEAKY02, ACT_NONE, ACT_RELU, ACT_SNAKE, ACT_SWISH, ConvArg
 INV_SQRT2 = 1.0 / math.sqrt(2.0)
 # tensor-core (tcgen05, bf16x3) path for eligible convs; STYLISH_B200_UMMA=0 forces fp32 FMA
 USE_UMMA = os.environ.get("STYLISH_B200_UMMA", "1") != "0"
-UMMA_MIN_T = 128
+UMMA_MIN_T = 64
 
 
 def split_bf16(w_oik: torch.Tensor) -> torch.Tensor:

@@ -471,7 +471,8 @@ class Synthesizer(nn.Module):
         return pred.audio
 
 
-HOT_PATH_KEYS = ("speech_predictor", "duration_predictor", "pitch_energy_predictor")
+HOT_PATH_KEYS = ("speech_predictor", "duration_predictor", "pitch_energy_predictor", "speech_style_encoder",
+                 "pe_style_encoder", "duration_style_encoder")
 ALL_KEYS = ("text_aligner", "duration_predictor", "pitch_energy_predictor", "speech_predictor",
             "disc", "mrd0", "mrd1", "mrd2", "speech_style_encoder", "pe_style_encoder",
             "duration_style_encoder", "pitch_disc", "dur_disc")
@@ -502,6 +503,14 @@ def build_model(model_config, *, extra: Dict[str, nn.Module] | None = None) -> M
     nets["duration_predictor"] = DurationPredictor(model_config)
     nets["pitch_energy_predictor"] = PitchEnergyPredictor(model_config)
     nets["speech_predictor"] = SpeechPredictor(model_config)
+    from .style_encoder import MelStyleEncoder, PitchStyleEncoder
+
+    se = model_config.style_encoder
+    for key in ("speech_style_encoder", "duration_style_encoder"):  # models.py:49-54,62-67
+        nets[key] = MelStyleEncoder(se.n_mels, model_config.style_dim, se.max_channels, se.skip_downsample)
+    nets["pe_style_encoder"] = PitchStyleEncoder(se.n_mels, model_config.style_dim, se.max_channels,
+                                                 se.skip_downsample,
+                                                 coarse_multiplier=model_config.coarse_multiplier)
     if extra:
         for k, v in extra.items():
             if k not in nets:

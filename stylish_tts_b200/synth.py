@@ -67,6 +67,25 @@ def randomize_(module: nn.Module, seed: int = 0) -> nn.Module:
     return module
 
 
+@torch.no_grad()
+def converge_spectral_(module: nn.Module, iters: int = 30) -> nn.Module:
+    """Run the spectral-norm power iteration on every (weight_orig, weight_u, weight_v) triple so that a
+    freshly initialised module is in the regime a trained checkpoint is in (sigma ~ largest singular value;
+    a fresh module has random u, v and sigma ~ 0, i.e. weights blown up by 1e3+ per layer)."""
+    sd = dict(module.named_parameters())
+    bufs = dict(module.named_buffers())
+    for name, W in sd.items():
+        if not name.endswith(".weight_orig"):
+            continue
+        p = name[:-len(".weight_orig")]
+        u, v = bufs[p + ".weight_u"], bufs[p + ".weight_v"]
+        Wm = W.reshape(W.shape[0], -1)
+        for _ in range(iters):
+            v.copy_(torch.nn.functional.normalize(torch.mv(Wm.t(), u), dim=0, eps=1e-12))
+            u.copy_(torch.nn.functional.normalize(torch.mv(Wm, v), dim=0, eps=1e-12))
+    return module
+
+
 def soft_alignment(duration: torch.Tensor) -> torch.Tensor:
     """Input generator: the soft (B,T,F) alignment matrix the reference's data
     path hands to speech_predictor (shape/meaning of utils.py:752-791)."""

@@ -1,0 +1,68 @@
+"""The acoustic training step on the CUDA engine: the forward graph the reference builds in
+``AcousticStep.__init__`` with ``use_predicted_pe=False, predict_audio=True`` (stage_type.py:61-180) plus its
+``mel`` and ``multi_phase`` losses with ``LossLog.backwards_loss`` normalisation (stage_type.py:170-193,
+loss_log.py:82-94) — SURVEY §8a row A3 / §8d config 3.  Adversarial and SLM terms are outside the hot
+path.
+
+    fe = FrontEnd(model_config, mel_log_mean, mel_log_std)
+    out = acoustic_step(batch, nets, fe)      # out.total is differentiable; out.pred.audio (B,1,L)
+    out.total.backward(); optimizer.step()
+"""
+from __future__ import annotations
+
+from types import SimpleNamespace
+
+import torch
+
+from . import _lib as L
+from . import spectral
+from .optim import acoustic_losses
+
+
+class FrontEnd:
+    """the TrainContext objects the step reads (train_context.py:155-178): to_mel, to_style_mel,
+    multi_spectrogram, stft_loss and the mel normalisation constants"""
+
+    def __init__(self, model_config, mel_log_mean=-4.0, mel_log_std=4.0):
+        mc = model_config
+        self.mean, self.std = float(mel_log_mean), float(mel_log_std)
+        self.to_mel = spectral.MelSpectrogram(n_mels=mc.n_mels, n_fft=mc.n_fft, win_length=mc.win_length,
+                                              hop_length=mc.hop_length, sample_rate=mc.sample_rate)
+        se = mc.style_encoder
+        self.to_style_mel = spectral.MelSpectrogram(n_mels=se.n_mels, n_fft=se.n_fft, win_length=se.win_length,
+                                                    hop_length=se.hop_length, sample_rate=mc.sample_rate)
+        self.multi_spectrogram = spectral.MultiSpectrogram(sample_rate=mc.sample_rate)
+        self.stft_loss = spectral.MultiResolutionSTFTLoss(sample_rate=mc.sample_rate)
+
+
+def alignment_from_durations(durations: torch.Tensor, frames: int = 0) -> torch.Tensor:
+    """DurationProcessor.duration_to_alignment (utils.py:752-791) for the integer durations of a batch
+    (stage_type.py:99-101): (B,T) -> soft alignment (B,T,F).  `frames` skips the device->host read of
+    round(max sum) that the reference does with .item() (utils.py:759)."""
+    dur = durations.to(torch.float32).contiguous()
+    B, Tn = dur.shape
+    Fr = frames or int(dur.sum(dim=1).round().max().item())
+    al = torch.empty((B, Tn, Fr), device=dur.device, dtype=torch.float32)
+    L.call("sty_alignment_fwd", dur.data_ptr(), al.data_ptr(), B, Tn, Fr, L.stream_ptr())
+    return al
+
+
+def acoustic_step(batch, nets, fe: FrontEnd, *, w_mel=5.0, w_phase=8.0, source_draws=None):
+    """batch: audio_gt (B,L), text (B,T), text_length (B,), pitch (B,F), alignment (B,1,T) integer durations
+    (the reference's collated batch, stage_type.py:61-106).  Returns total / mel / multi_phase losses and
+    the prediction."""
+    audio_gt = batch.audio_gt
+    with torch.no_grad():
+        mel, _ = spectral.calculate_mel(audio_gt, fe.to_mel, fe.mean, fe.std)
+        style_mel, _ = spectral.calculate_mel(audio_gt, fe.to_style_mel, fe.mean, fe.std)
+        energy = spectral.mel_energy(mel, fe.mean, fe.std)
+        pitch = batch.pitch
+        alignment = alignment_from_durations(batch.alignment[:, 0, :], frames=pitch.shape[1])
+        voiced = (pitch > 20).float()
+    style = nets.speech_style_encoder(style_mel.unsqueeze(1))
+    pred = nets.speech_predictor(batch.text, batch.text_length, alignment, pitch, energy, voiced, style, pitch,
+                                 source_draws=source_draws)
+    total, mel_loss, phase_loss = acoustic_losses(pred.audio.squeeze(1), audio_gt, fe.multi_spectrogram,
+                                                  fe.stft_loss, w_mel=w_mel, w_phase=w_phase)
+    return SimpleNamespace(total=total, mel=mel_loss, multi_phase=phase_loss, pred=pred, style=style,
+                           energy=energy, mel_target=mel)

@@ -291,6 +291,7 @@ def test_bmm_glu_embed_mask_linear():
     (32, 32, 11, 5, 640), (32, 128, 1, 1, 1111), (128, 32, 1, 1, 513), (256, 1024, 1, 1, 803),
     (256, 1536, 1, 1, 515), (256, 384, 11, 1, 803),
     (1024, 256, 1, 1, 803), (128, 256, 21, 1, 803), (64, 160, 11, 1, 600), (48, 16, 3, 1, 515),
+    (384, 1152, 3, 1, 101), (1920, 384, 5, 1, 101), (128, 128, 3, 1, 64),  # short rows (style encoder, T < 128)
 ])
 def test_conv1d_tensor_core_bf16x3(ci, co, k, dil, T):
     """tcgen05 path (bf16 hi/lo split, 3 MMAs, fp32 accumulate): ~16-bit operands."""

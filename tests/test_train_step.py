@@ -172,3 +172,50 @@ def test_full_size_training_step_is_finite():
         n += p.grad.numel()
     assert n > 12_000_000
     assert torch.cuda.max_memory_allocated() < 150e9
+
+
+@pytest.mark.gpu
+def test_acoustic_step_trains_both_modules():
+    """AcousticStep graph (stage_type.py:61-180) + FlatAdamW: every trainable parameter of speech_predictor and
+    speech_style_encoder receives a finite gradient, the update changes them, and the loss of the SAME batch
+    goes down over a few steps."""
+    from types import SimpleNamespace
+    from stylish_tts_b200 import optim, train_step as ts
+
+    dev = torch.device("cuda:0")
+    mc = st.default_model_config()
+    nets = st.build_model(mc)
+    synth.randomize_(nets.speech_predictor, 0)
+    synth.converge_spectral_(nets.speech_style_encoder)
+    sp, se = nets.speech_predictor.to(dev).train(), nets.speech_style_encoder.to(dev).train()
+    B, Tn = 2, 18
+    inp = synth.speech_inputs(B, Tn, seed=4)
+    dur = torch.full((B, Tn), 3.0)
+    dur[:, ::9] += 1.0
+    frames = int(dur[0].sum())
+    assert frames % 2 == 0 and frames == inp["pitch"].shape[1]
+    g = torch.Generator().manual_seed(8)
+    batch = SimpleNamespace(audio_gt=(0.1 * torch.randn(B, frames * 300, generator=g)).to(dev),
+                            text=inp["texts"].to(dev), text_length=inp["text_lengths"].to(dev),
+                            pitch=inp["pitch"].to(dev), alignment=dur.unsqueeze(1).to(dev))
+    fe = ts.FrontEnd(mc)
+    params = list(sp.parameters()) + list(se.parameters())
+    opt = optim.FlatAdamW(params, lr=1e-4, betas=(0.85, 0.99), eps=1e-9, weight_decay=1e-4, world_size=1)
+    draws = {"noise": inp["draws"]["noise"].to(dev)}
+    before = opt.flat.clone()
+    losses = []
+    for i in range(4):
+        out = ts.acoustic_step(batch, nets, fe, source_draws=draws)
+        assert out.pred.audio.shape == (B, 1, frames * 300) and out.energy.shape == (B, frames)
+        out.total.backward()
+        if i == 0:
+            for n, p in list(sp.named_parameters()) + list(se.named_parameters()):
+                if "m_source" in n:
+                    continue
+                assert p.grad is not None and torch.isfinite(p.grad).all(), n
+        losses.append((float(out.mel.detach()), float(out.multi_phase.detach())))
+        opt.step()
+        opt.zero_grad()
+    assert float((opt.flat - before).abs().max()) > 0
+    raw = [5.0 * m + 8.0 * p for m, p in losses]  # un-normalised weighted sum (config.yml:73-107 weights)
+    assert raw[-1] < raw[0], losses
