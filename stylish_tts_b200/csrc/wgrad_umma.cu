@@ -11,9 +11,10 @@
 // tensor with more channels, 128 per MMA.)  fp32 operands are split into bf16 (hi, lo) while staging and
 // three MMAs (hi*hi + lo*hi + hi*lo) accumulate in fp32, as in the forward kernel (conv1d_umma.cu).
 //
-// One CTA per SM walks a range of (batch, 128-step) chunks with a two-stage shared-memory ring:
-// all 16 warps stage chunk i+1 (prologue / mask applied on the fly) while the tensor core consumes
-// chunk i; the accumulators stay in TMEM for the whole range and are added to dw with atomics once.
+// One CTA per SM walks a range of (batch, 128-step) chunks with a two-stage shared-memory ring and two
+// roles handing over through mbarriers: 16 producer warps stage chunk i+1 (prologue / mask applied on the
+// fly, 32 global loads in flight per thread) while a dedicated warp issues the MMAs of chunk i; the
+// accumulators stay in TMEM for the whole range and are added to dw with atomics once.
 #include "umma.cuh"
 
 namespace sty {
@@ -116,14 +117,17 @@ __device__ __forceinline__ void stage_chunk(const SideDesc& A, const SideDesc& B
   }
 }
 
-__global__ void __launch_bounds__(kWgThreads, 1)
+__global__ void __launch_bounds__(kWgThreads + 32, 1)
 conv1d_wgrad_umma_kernel(const sty_conv1d_wgrad_args p, const WgPlan pl) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   uint4* stage0 = reinterpret_cast<uint4*>(smem_raw);
   float* prm = reinterpret_cast<float*>(stage0 + (size_t)pl.stages * pl.stage_u4);  // [3][8*input groups]
   const int in_groups = pl.mode >= 2 ? pl.n_groups : pl.m_groups;
   uint64_t* bars = reinterpret_cast<uint64_t*>(prm + ((3 * 8 * in_groups + 3) & ~3));
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+  uint64_t* full = bars;       // [2] producers -> MMA warp
+  uint64_t* empty = bars + 2;  // [2] tensor core -> producers
+  uint64_t* done = bars + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int N = pl.n_groups * 8;
 
@@ -133,8 +137,11 @@ conv1d_wgrad_umma_kernel(const sty_conv1d_wgrad_args p, const WgPlan pl) {
 
   if (warp == 0) tmem_alloc(tmem_slot, (uint32_t)pl.acc_cols);
   if (tid == 0) {
-    mbar_init(&bars[0], 1);
-    mbar_init(&bars[1], 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&full[i], kWgThreads);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(done, 1);
     fence_barrier_init();
   }
   tc_fence_before();
@@ -151,31 +158,30 @@ conv1d_wgrad_umma_kernel(const sty_conv1d_wgrad_args p, const WgPlan pl) {
   const int n_plane = pl.n_groups * pl.rows_n;
   const uint32_t sbo_m = pl.mode == 0 ? (uint32_t)p.dil : (uint32_t)pl.rows_m;
 
-  int cur_b = -1;
-  uint32_t it = 0;
-  for (int64_t chunk = c_begin; chunk < c_end; ++chunk, ++it) {
-    const int b = (int)(chunk / pl.n_tchunks);
-    const int t0 = (int)(chunk - (int64_t)b * pl.n_tchunks) * kTT;
-    const uint32_t s = it % (uint32_t)pl.stages;
-    if (it >= (uint32_t)pl.stages) {  // the MMAs that read this stage (iteration it - stages) are done
-      mbar_wait(&bars[s], ((it / (uint32_t)pl.stages) - 1u) & 1u);
-      tc_fence_after();
-    }
-    if (b != cur_b) {  // prologue parameters of this batch element
-      __syncthreads();
-      for (int c = tid; c < 8 * in_groups; c += kWgThreads) {
-        const int ci = ci0 + c;
-        const bool ok = ci < p.CI;
-        prm[c] = (ok && p.in_scale) ? p.in_scale[(int64_t)b * p.CI + ci] : 1.f;
-        prm[8 * in_groups + c] = (ok && p.in_shift) ? p.in_shift[(int64_t)b * p.CI + ci] : 0.f;
-        prm[16 * in_groups + c] = (ok && p.in_alpha) ? p.in_alpha[ci] : 1.f;
+  const uint32_t n_it = (uint32_t)(c_end - c_begin);
+  if (warp < kWgThreads / 32) {
+    // =========================== producers (16 warps): stage chunk after chunk into the ring
+    int cur_b = -1;
+    uint32_t it = 0;
+    for (int64_t chunk = c_begin; chunk < c_end; ++chunk, ++it) {
+      const int b = (int)(chunk / pl.n_tchunks);
+      const int t0 = (int)(chunk - (int64_t)b * pl.n_tchunks) * kTT;
+      const uint32_t s = it % (uint32_t)pl.stages;
+      mbar_wait_sleep(&empty[s], ((it / (uint32_t)pl.stages) & 1u) ^ 1u);  // MMAs that read this stage are done
+      if (b != cur_b) {  // prologue parameters of this batch element
+        asm volatile("bar.sync 1, %0;" ::"n"(kWgThreads) : "memory");
+        for (int c = tid; c < 8 * in_groups; c += kWgThreads) {
+          const int ci = ci0 + c;
+          const bool ok = ci < p.CI;
+          prm[c] = (ok && p.in_scale) ? p.in_scale[(int64_t)b * p.CI + ci] : 1.f;
+          prm[8 * in_groups + c] = (ok && p.in_shift) ? p.in_shift[(int64_t)b * p.CI + ci] : 0.f;
+          prm[16 * in_groups + c] = (ok && p.in_alpha) ? p.in_alpha[ci] : 1.f;
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(kWgThreads) : "memory");
+        cur_b = b;
       }
-      __syncthreads();
-      cur_b = b;
-    }
-    uint4* Ms = stage0 + (size_t)s * pl.stage_u4;
-    uint4* Ns = Ms + 2 * m_plane;
-    {
+      uint4* Ms = stage0 + (size_t)s * pl.stage_u4;
+      uint4* Ns = Ms + 2 * m_plane;
       const float* xb = p.x + (int64_t)b * p.x_bs;
       const float* gb = p.dy + (int64_t)b * p.dy_bs;
       const float* im = p.in_mask ? p.in_mask + (int64_t)b * p.T : nullptr;
@@ -189,45 +195,52 @@ conv1d_wgrad_umma_kernel(const sty_conv1d_wgrad_args p, const WgPlan pl) {
         sn_ = SideDesc{Ns, gb, om, p.dy_cs, p.CO, n0, pl.n_groups, kTT, kTT, t0, 0};
       }
       stage_chunk(sm_, sn_, p, prm, in_groups, tid);
+      fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor-core proxy
+      mbar_arrive(&full[s]);
     }
-    fence_proxy_async_smem();
-    __syncthreads();
-    if (tid == 0) {
+  } else {
+    // =========================== MMA issuer (one elected lane of the extra warp)
+    for (uint32_t it = 0; it < n_it; ++it) {
+      const uint32_t s = it % (uint32_t)pl.stages;
+      mbar_wait(&full[s], (it / (uint32_t)pl.stages) & 1u);
       tc_fence_after();
-      const uint32_t m_addr = smem_u32(Ms), n_addr = smem_u32(Ns);
-      const uint64_t bd = make_desc(n_addr, 8u, (uint32_t)pl.rows_n);
-      const uint32_t b_hi32 = (uint32_t)(bd >> 32);
-      const uint32_t first = it == 0 ? 0u : 1u;
-      for (int acc = 0; acc < pl.n_acc; ++acc) {
-        const uint32_t b_lo = (uint32_t)bd + (pl.mode == 3 ? (uint32_t)(acc * p.dil) : 0u);  // mode 3: tap = acc
-        // mode 0: accumulator (g, tc) = input-channel group g seen through taps [16 tc, 16 tc + 16)
-        const int g = pl.mode == 0 ? acc / pl.tap_chunks : 0;
-        const int tc = pl.mode == 0 ? acc - g * pl.tap_chunks : 0;
-        const uint32_t a_off = (uint32_t)(g * pl.rows_m + tc * 16 * p.dil);  // uint4 units
-        const uint64_t ad = make_desc(m_addr + a_off * 16u, 8u, sbo_m);
-        const uint32_t a_hi32 = (uint32_t)(ad >> 32), a_lo = (uint32_t)ad;
-        const uint32_t d = tmem_base + (uint32_t)(acc * N);
-#pragma unroll 1
-        for (uint32_t ks = 0; ks < kTT / 16; ++ks) {
-          const uint32_t ak = a_lo + ks * 16u, bk = b_lo + ks * 16u;  // 16 time steps = 16 units of 16 B
-          umma_bf16_w(d, ak, a_hi32, bk, b_hi32, idesc, ks == 0 ? first : 1u);            // hi * hi
-          umma_bf16_w(d, ak + (uint32_t)m_plane, a_hi32, bk, b_hi32, idesc, 1u);          // lo * hi
-          umma_bf16_w(d, ak, a_hi32, bk + (uint32_t)n_plane, b_hi32, idesc, 1u);          // hi * lo
+      if (lane == 0) {
+        const uint4* Ms = stage0 + (size_t)s * pl.stage_u4;
+        const uint32_t m_addr = smem_u32(Ms), n_addr = smem_u32(Ms + 2 * m_plane);
+        const uint64_t bd = make_desc(n_addr, 8u, (uint32_t)pl.rows_n);
+        const uint32_t b_hi32 = (uint32_t)(bd >> 32);
+        const uint32_t first = it == 0 ? 0u : 1u;
+        for (int acc = 0; acc < pl.n_acc; ++acc) {
+          const uint32_t b_lo = (uint32_t)bd + (pl.mode == 3 ? (uint32_t)(acc * p.dil) : 0u);  // mode 3: tap = acc
+          // mode 0: accumulator (g, tc) = input-channel group g seen through taps [16 tc, 16 tc + 16)
+          const int g = pl.mode == 0 ? acc / pl.tap_chunks : 0;
+          const int tc = pl.mode == 0 ? acc - g * pl.tap_chunks : 0;
+          const uint32_t a_off = (uint32_t)(g * pl.rows_m + tc * 16 * p.dil);  // uint4 units
+          const uint64_t ad = make_desc(m_addr + a_off * 16u, 8u, sbo_m);
+          const uint32_t a_hi32 = (uint32_t)(ad >> 32), a_lo = (uint32_t)ad;
+          const uint32_t d = tmem_base + (uint32_t)(acc * N);
+#pragma unroll 2
+          for (uint32_t ks = 0; ks < kTT / 16; ++ks) {
+            const uint32_t ak = a_lo + ks * 16u, bk = b_lo + ks * 16u;  // 16 time steps = 16 units of 16 B
+            umma_bf16_w(d, ak, a_hi32, bk, b_hi32, idesc, ks == 0 ? first : 1u);            // hi * hi
+            umma_bf16_w(d, ak + (uint32_t)m_plane, a_hi32, bk, b_hi32, idesc, 1u);          // lo * hi
+            umma_bf16_w(d, ak, a_hi32, bk + (uint32_t)n_plane, b_hi32, idesc, 1u);          // hi * lo
+          }
         }
+        umma_commit(&empty[s]);                      // stage free once the tensor core has read it
+        if (it == n_it - 1) umma_commit(done);      // ... and every accumulator is complete
       }
-      umma_commit(&bars[s]);
+      __syncwarp();
     }
   }
-  // drain: the last commit covers every MMA issued before it
-  if (it > 0) {
-    const uint32_t last = it - 1, s = last % (uint32_t)pl.stages;
-    mbar_wait(&bars[s], (last / (uint32_t)pl.stages) & 1u);
-  }
+  // everyone waits for the last MMA before the accumulators are read back
+  const uint32_t it = n_it;
+  if (n_it > 0) mbar_wait_sleep(done, 0);
   tc_fence_after();
 
   // ---- accumulators -> dw (atomics).  thread owns TMEM lane m = 32*(warp&3) + lane; the four warp
   // groups split the 16-column chunks
-  if (it > 0) {
+  if (it > 0 && warp < kWgThreads / 32) {
     const int q = warp & 3, part = warp >> 2;
     const int m = q * 32 + lane;
     const int chunks16 = (pl.n_acc * N) >> 4;
@@ -336,7 +349,7 @@ bool make_wg_plan(const sty_conv1d_wgrad_args& a, WgPlan& pl) {
   if (pl.acc_cols > 512) return false;
   pl.stage_u4 = 2 * (pl.m_groups * pl.rows_m + pl.n_groups * pl.rows_n);
   const int in_groups = pl.mode >= 2 ? pl.n_groups : pl.m_groups;
-  const size_t misc = (size_t)((3 * 8 * in_groups + 3) & ~3) * 4 + 64;
+  const size_t misc = (size_t)((3 * 8 * in_groups + 3) & ~3) * 4 + 128;
   const size_t st = (size_t)pl.stage_u4 * 16;
   if (2 * st + misc <= kWgSmemBudget) pl.stages = 2;
   else if (st + misc <= kWgSmemBudget) pl.stages = 1;
@@ -364,7 +377,7 @@ int conv1d_wgrad_umma_launch(const sty_conv1d_wgrad_args& a, cudaStream_t st) {
     if (sms <= 0) sms = 148;
   }
   const int in_groups = pl.mode >= 2 ? pl.n_groups : pl.m_groups;
-  const size_t smem = (size_t)pl.stages * pl.stage_u4 * 16 + (size_t)((3 * 8 * in_groups + 3) & ~3) * 4 + 64;
+  const size_t smem = (size_t)pl.stages * pl.stage_u4 * 16 + (size_t)((3 * 8 * in_groups + 3) & ~3) * 4 + 128;
   cudaFuncSetAttribute(conv1d_wgrad_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const int tiles = pl.m_tiles * pl.n_tiles;
   const int64_t total = (int64_t)a.B * pl.n_tchunks;
@@ -372,7 +385,7 @@ int conv1d_wgrad_umma_launch(const sty_conv1d_wgrad_args& a, cudaStream_t st) {
   if (gx < 1) gx = 1;
   if (gx > total) gx = total;
   dim3 grid((unsigned)gx, (unsigned)tiles);
-  conv1d_wgrad_umma_kernel<<<grid, kWgThreads, smem, st>>>(a, pl);
+  conv1d_wgrad_umma_kernel<<<grid, kWgThreads + 32, smem, st>>>(a, pl);
   STY_CHECK_LAUNCH("conv1d_wgrad_umma");
   return STY_OK;
 }
