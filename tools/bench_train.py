@@ -12,6 +12,7 @@ def main():
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--profile", action="store_true")
+    ap.add_argument("--warm", type=int, default=2)
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     sp = st.build_model(st.default_model_config()).speech_predictor
@@ -36,7 +37,7 @@ def main():
         total.backward()
         return total
 
-    for _ in range(2):
+    for _ in range(a.warm):
         step()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
