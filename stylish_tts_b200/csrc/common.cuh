@@ -37,11 +37,16 @@ static inline cudaStream_t as_stream(sty_stream_t s) { return reinterpret_cast<c
 static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
 // ---------------------------------------------------------------- device math
-// sin^2(y): even and pi-periodic, so reduce to r in [-pi/2, pi/2] with a two-term
-// Cody-Waite step and evaluate the odd Taylor polynomial through r^11
-// (|error| < 1e-7 on the interval).  ~15 instructions instead of sinf's ~40; this
-// is the Snake activation's inner function and sits in conv prologues/epilogues.
+// sin^2(y), the Snake activation's inner function; it sits in conv prologues / epilogues where it was 40 % of
+// all instructions of the fused ConvNeXt kernel (ncu source view, profiles/r01_ncu_pw1_source_blocks.txt).
+// Default: one MUFU.SIN (sin.approx, |abs error| ~ 1e-6 after the 1/2pi range scaling) and a multiply —
+// 3 instructions.  STY_PRECISE_SNAKE=1 selects the Cody-Waite + degree-11 polynomial (|error| < 1e-7, ~20
+// instructions) that the first parity runs used.
+#ifndef STY_PRECISE_SNAKE
+#define STY_PRECISE_SNAKE 0
+#endif
 __device__ __forceinline__ float sin_sq(float y) {
+#if STY_PRECISE_SNAKE
   const float k = rintf(y * 0.318309886183790672f);
   float r = fmaf(k, -3.14159274101257324f, y);
   r = fmaf(k, 8.74227800037247e-08f, r);
@@ -52,6 +57,10 @@ __device__ __forceinline__ float sin_sq(float y) {
   p = fmaf(p, r2, -1.66666666666667e-01f);
   const float s = fmaf(r * r2, p, r);
   return s * s;
+#else
+  const float s = __sinf(y);
+  return s * s;
+#endif
 }
 
 // `alpha` / `inv_alpha` are only read for STY_ACT_SNAKE.
