@@ -46,7 +46,8 @@ constexpr int kProducerWarps = 8;
 constexpr int kProducerThreads = kProducerWarps * 32;
 constexpr int kMmaWarp = kProducerWarps;
 constexpr int kEpilogueWarp0 = kMmaWarp + 1;
-constexpr int kEpilogueWarps = 8;
+constexpr int kEpilogueWarps = 8;  // 4 lane quadrants x kColParts column parts (12 or 16 warps cap the registers at 80 / 72 and spill in the prologue producers: measured slower)
+constexpr int kColParts = kEpilogueWarps / 4;
 constexpr int kThreads = (kEpilogueWarp0 + kEpilogueWarps) * 32;
 constexpr int kMaxStages = 4;
 constexpr int kItemBatch = 4;  // (row, 8-channel) items staged per thread per batch: 32 loads in flight
@@ -403,13 +404,13 @@ conv1d_umma_kernel(const sty_conv1d_args p, const UmmaPlan pl) {
     }
   } else {
     // =========================== epilogue: thread owns accumulator row (TMEM lane) q*32+lane
-    // and the 16-column chunks c with (c & 1) == half
+    // and the 16-column chunks c with (c % kColParts) == half
     const int ew = warp - kEpilogueWarp0;
     const int q = warp & 3;
     const int half = ew >> 2;
     const int s = p.shuffle > 1 ? p.shuffle : 1;
     const int n_chunks16 = NT >> 4;
-    float ssq_acc[8];  // column (16*c + (lane & 15)) sums of this thread's chunks c = half, half+2, ...
+    float ssq_acc[8];  // column (16*c + (lane & 15)) sums of this thread's chunks c = half, half+kColParts, ...
 #pragma unroll
     for (int i = 0; i < 8; ++i) ssq_acc[i] = 0.f;
     uint32_t j = 0;
@@ -418,7 +419,7 @@ conv1d_umma_kernel(const sty_conv1d_args p, const UmmaPlan pl) {
       if (lane < 16) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const int c = half + 2 * i;
+          const int c = half + kColParts * i;
           if (c < n_chunks16) atomicAdd(p.out_sumsq + (int64_t)bb * CO + co0 + c * 16 + lane, ssq_acc[i]);
           ssq_acc[i] = 0.f;
         }
@@ -443,7 +444,7 @@ conv1d_umma_kernel(const sty_conv1d_args p, const UmmaPlan pl) {
       const uint32_t acc_addr = tmem_base + a * (uint32_t)pl.acc_cols + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
       for (int ci = 0; ci < 8; ++ci) {
-        const int c = half + 2 * ci;
+        const int c = half + kColParts * ci;
         if (c >= n_chunks16) break;
         const int n0 = c * 16;
         float r[16], rv[16];
