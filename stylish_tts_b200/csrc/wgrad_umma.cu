@@ -63,7 +63,7 @@ struct SideDesc {
 __device__ __forceinline__ void stage_chunk(const SideDesc& A, const SideDesc& Bd, const sty_conv1d_wgrad_args& p,
                                             const float* prm, int in_groups, int tid) {
   const int nA = A.groups * A.rows, n_items = nA + Bd.groups * Bd.rows;
-  constexpr int U = 4;
+  constexpr int U = 4;  // 32 global loads in flight per thread (6 spills registers and is slower: measured)
   for (int i0 = tid; i0 < n_items; i0 += kWgThreads * U) {
     float v[U][8];
 #pragma unroll
@@ -72,7 +72,7 @@ __device__ __forceinline__ void stage_chunk(const SideDesc& A, const SideDesc& B
       const bool second = item >= nA;
       const SideDesc& S = second ? Bd : A;
       const int li = second ? item - nA : item;
-      const int g = li / S.rows, row = li - g * S.rows;
+      const int g = S.rows == kTT ? (li >> 7) : li / S.rows, row = li - g * S.rows;
       const int t = S.t_start + row;
       const bool ok = item < n_items && row < S.valid_rows && t >= 0 && t < p.T;
 #pragma unroll
@@ -88,7 +88,7 @@ __device__ __forceinline__ void stage_chunk(const SideDesc& A, const SideDesc& B
       const bool second = item >= nA;
       const SideDesc& S = second ? Bd : A;
       const int li = second ? item - nA : item;
-      const int g = li / S.rows, row = li - g * S.rows;
+      const int g = S.rows == kTT ? (li >> 7) : li / S.rows, row = li - g * S.rows;
       const int t = S.t_start + row;
       const bool ok = row < S.valid_rows && t >= 0 && t < p.T;
       const float m = (ok && S.mask) ? S.mask[t] : 1.f;

@@ -15,27 +15,32 @@ def main():
     ap.add_argument("--warm", type=int, default=2)
     a = ap.parse_args()
     dev = torch.device("cuda:0")
-    sp = st.build_model(st.default_model_config()).speech_predictor
+    from types import SimpleNamespace
+    from stylish_tts_b200 import train_step as ts, optim
+    mc = st.default_model_config()
+    nets = st.build_model(mc)
+    sp, se = nets.speech_predictor, nets.speech_style_encoder
     synth.randomize_(sp, 0)
-    sp = sp.to(dev).train()
-    inp = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in synth.speech_inputs(a.batch, 258, seed=1).items()}
-    noise = inp["draws"]["noise"].to(dev)
-    ms = spectral.MultiSpectrogram(sample_rate=24000)
-    stft_loss = spectral.MultiResolutionSTFTLoss()
-    target = 0.1 * torch.randn(a.batch, inp["pitch"].shape[1] * 300, device=dev)
+    synth.converge_spectral_(se)
+    sp, se = sp.to(dev).train(), se.to(dev).train()
+    opt = optim.FlatAdamW(list(sp.parameters()) + list(se.parameters()), world_size=1)
+    fe = ts.FrontEnd(mc)
+    inp = synth.speech_inputs(a.batch, 258, seed=1)
+    dur = torch.full((a.batch, 258), 3.0)
+    dur[:, ::9] += 1.0
+    dur[:, -1] += 1.0
+    frames = int(dur[0].sum())
+    pitch = torch.cat([inp["pitch"], inp["pitch"][:, -1:]], 1)
+    batch = SimpleNamespace(audio_gt=(0.1 * torch.randn(a.batch, frames * 300)).to(dev), text=inp["texts"].to(dev),
+                            text_length=inp["text_lengths"].to(dev), pitch=pitch.to(dev),
+                            alignment=dur.unsqueeze(1).to(dev))
 
     def step():
-        for p in sp.parameters():
-            p.grad = None
-        out = sp(inp["texts"], inp["text_lengths"], inp["alignment"], inp["pitch"], inp["energy"], inp["voiced"],
-                 inp["style"], inp["denormal_pitch"], source_draws={"noise": noise})
-        audio = out.audio.squeeze(1)
-        t_spec, p_spec, t_ph, p_ph, _, _ = ms(target=target, pred=audio)
-        mel = stft_loss(target_list=t_spec, pred_list=p_spec)
-        ph = spectral.multi_phase_loss(p_ph, t_ph)
-        total = 5.0 * mel / (mel.detach() + 1e-9) + 8.0 * ph / (ph.detach() + 1e-9)
-        total.backward()
-        return total
+        out = ts.acoustic_step(batch, nets, fe)
+        out.total.backward()
+        opt.step()
+        opt.zero_grad()
+        return out.total
 
     for _ in range(a.warm):
         step()
@@ -47,7 +52,7 @@ def main():
     e1.record()
     torch.cuda.synchronize()
     ms_step = e0.elapsed_time(e1) / a.steps
-    secs = a.batch * inp["pitch"].shape[1] * 300 / 24000
+    secs = a.batch * frames * 300 / 24000
     print(f"train step B={a.batch}: {ms_step:.1f} ms  ({1000/ms_step:.2f} steps/s, {secs/ms_step*1000:.0f} audio-s/s trained), "
           f"peak mem {torch.cuda.max_memory_allocated()/1e9:.1f} GB")
     if a.profile:
