@@ -324,11 +324,23 @@ conv1d_umma_kernel(const sty_conv1d_args p, const UmmaPlan pl) {
               if constexpr (PRO) {
                 const int cbase = c0 + ic8[u] * 8;
                 const float m = (ok && in_mask) ? in_mask[t] : 1.f;
+                // per-channel parameters as 128-bit shared loads (cbase is a multiple of 8, CI of 16)
+                float sc[8], sh[8], al[8], ial[8];
+                *reinterpret_cast<float4*>(sc) = *reinterpret_cast<const float4*>(pro_s + cbase);
+                *reinterpret_cast<float4*>(sc + 4) = *reinterpret_cast<const float4*>(pro_s + cbase + 4);
+                *reinterpret_cast<float4*>(sh) = *reinterpret_cast<const float4*>(pro_s + CI + cbase);
+                *reinterpret_cast<float4*>(sh + 4) = *reinterpret_cast<const float4*>(pro_s + CI + cbase + 4);
+                if constexpr (IN_MODE == 3) {
+                  *reinterpret_cast<float4*>(al) = *reinterpret_cast<const float4*>(pro_s + 2 * CI + cbase);
+                  *reinterpret_cast<float4*>(al + 4) = *reinterpret_cast<const float4*>(pro_s + 2 * CI + cbase + 4);
+                  *reinterpret_cast<float4*>(ial) = *reinterpret_cast<const float4*>(pro_s + 3 * CI + cbase);
+                  *reinterpret_cast<float4*>(ial + 4) = *reinterpret_cast<const float4*>(pro_s + 3 * CI + cbase + 4);
+                }
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                  float w = fmaf(v[u][j] * m, pro_s[cbase + j], pro_s[CI + cbase + j]);
+                  float w = fmaf(v[u][j] * m, sc[j], sh[j]);
                   if constexpr (IN_MODE == 3) {
-                    w = fmaf(pro_s[3 * CI + cbase + j], sin_sq(pro_s[2 * CI + cbase + j] * w), w);
+                    w = fmaf(ial[j], sin_sq(al[j] * w), w);
                   } else if constexpr (IN_MODE == 2) {
                     w = w > 0.f ? w : 0.2f * w;
                   }
