@@ -112,6 +112,9 @@ typedef struct sty_conv1d_args {
   const float* dw_gb;
   int64_t dw_gb_bs;
   float dw_eps;
+  /* Optional `out_sum[b,co] += sum_t y` (with out_sumsq: the InstanceNorm statistics of the NEXT AdaIN are
+   * accumulated by the conv that produces its input, ada_norm.py:109-140; tensor-core path: CO <= 64). */
+  float* out_sum;
 } sty_conv1d_args;
 STY_API int sty_conv1d_fwd(const sty_conv1d_args* a, sty_stream_t stream);
 
@@ -155,6 +158,14 @@ STY_API int sty_chan_layernorm_fwd(const float* x, const float* res, int64_t x_b
 STY_API int sty_instnorm_affine_fwd(const float* x, int64_t x_bs, int64_t x_cs, const float* gb,
                             int64_t gb_bs, float* scale, float* shift, int B, int C, int T,
                             float eps, sty_stream_t stream);
+
+/* ---- AdaIN affine from accumulated moments ------------------------------------------------------
+ * mean = sum/T, var = max(sumsq/T - mean^2, 0) (biased); scale = (1+gamma)/sqrt(var+eps),
+ * shift = beta - mean*scale, gamma/beta as in sty_instnorm_affine_fwd.  One-pass counterpart of
+ * sty_instnorm_affine_fwd for tensors whose producer conv accumulated out_sum / out_sumsq. */
+STY_API int sty_moments_affine_fwd(const float* sum, const float* sumsq, const float* gb, int64_t gb_bs,
+                                   float* scale, float* shift, int B, int C, int T, float eps,
+                                   sty_stream_t stream);
 
 /* ---- small dense layer on vectors -----------------------------------------
  * out[b,j] = bias[j] + sum_i W[j,i] * s[b,i]      (all style FCs of a model packed

@@ -40,6 +40,7 @@ class ConvArgs(C.Structure):
         ("out_scale", _f32), ("res_scale", _f32),
         ("w_split", _f32p),
         ("dw_w", _f32p), ("dw_b", _f32p), ("dw_gb", _f32p), ("dw_gb_bs", _i64), ("dw_eps", _f32),
+        ("out_sum", _f32p),
     ]
 
 
@@ -68,6 +69,7 @@ _SIGNATURES = {
                                _i32, _i32, _i32, _f32, _i32, _f32p],
     "sty_instnorm_affine_fwd": [_f32p, _i64, _i64, _f32p, _i64, _f32p, _f32p, _i32, _i32, _i32,
                                 _f32, _f32p],
+    "sty_moments_affine_fwd": [_f32p, _f32p, _f32p, _i64, _f32p, _f32p, _i32, _i32, _i32, _f32, _f32p],
     "sty_linear_rows_fwd": [_f32p, _f32p, _f32p, _f32p, _i32, _i32, _i32, _f32p],
     "sty_grn_scale_fwd": [_f32p, _f32p, _f32p, _i32, _i32, _f32p],
     "sty_rope_table": [_f32p, _f32p, _i32, _i32, _f32, _f32p],

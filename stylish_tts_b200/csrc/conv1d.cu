@@ -165,7 +165,7 @@ conv1d_kernel(const sty_conv1d_args p, const int ci_chunk, const int xtp) {
     const float bias = (co_ok && p.bias) ? p.bias[co] : 0.f;
     const float al = (co_ok && p.out_alpha) ? p.out_alpha[co] : 1.f;
     const float inv_al = 1.0f / al;
-    float ssq = 0.f;
+    float ssq = 0.f, ssum = 0.f;
     if (co_ok) {
       const int c_out = co / s, r_out = co - c_out * s;
       float* __restrict__ yrow = yb + (int64_t)c_out * p.y_cs + r_out;
@@ -180,6 +180,7 @@ conv1d_kernel(const sty_conv1d_args p, const int ci_chunk, const int xtp) {
           if (rrow) v = fmaf(p.res_scale, rrow[(int64_t)t * s], v);
           yrow[(int64_t)t * s] = v;
           ssq = fmaf(v, v, ssq);
+          ssum += v;
         }
       }
     }
@@ -187,6 +188,11 @@ conv1d_kernel(const sty_conv1d_args p, const int ci_chunk, const int xtp) {
 #pragma unroll
       for (int o = TL / 2; o > 0; o >>= 1) ssq += __shfl_xor_sync(0xffffffffu, ssq, o);
       if (tl == 0 && co_ok) atomicAdd(p.out_sumsq + (int64_t)b * p.CO + co, ssq);
+    }
+    if (p.out_sum) {
+#pragma unroll
+      for (int o = TL / 2; o > 0; o >>= 1) ssum += __shfl_xor_sync(0xffffffffu, ssum, o);
+      if (tl == 0 && co_ok) atomicAdd(p.out_sum + (int64_t)b * p.CO + co, ssum);
     }
   }
 }
@@ -284,7 +290,8 @@ extern "C" int sty_conv1d_fwd(const sty_conv1d_args* a, sty_stream_t stream) {
   STY_REQUIRE(a->in_act != STY_ACT_SNAKE || a->in_alpha, "conv1d: snake prologue needs in_alpha");
   STY_REQUIRE(a->out_act != STY_ACT_SNAKE || a->out_alpha, "conv1d: snake epilogue needs out_alpha");
   STY_REQUIRE(a->shuffle <= 1 || a->CO % a->shuffle == 0, "conv1d: CO %% shuffle != 0");
-  STY_REQUIRE(a->shuffle <= 1 || a->out_sumsq == nullptr, "conv1d: sumsq with shuffle unsupported");
+  STY_REQUIRE(a->shuffle <= 1 || (a->out_sumsq == nullptr && a->out_sum == nullptr),
+              "conv1d: sum / sumsq with shuffle unsupported");
   cudaStream_t st = as_stream(stream);
   if (conv1d_umma_eligible(*a)) return conv1d_umma_launch(*a, st);
   STY_REQUIRE(a->dw_w == nullptr, "conv1d: the fused ConvNeXt front needs the tensor-core path "

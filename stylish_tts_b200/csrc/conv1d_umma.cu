@@ -425,6 +425,7 @@ conv1d_umma_kernel(const sty_conv1d_args p, const UmmaPlan pl) {
     float ssq_acc[8];  // column (16*c + (lane & 15)) sums of this thread's chunks c = half, half+kColParts, ...
 #pragma unroll
     for (int i = 0; i < 8; ++i) ssq_acc[i] = 0.f;
+    float sum_acc[2] = {0.f, 0.f};  // same for out_sum (NT <= 64: at most two chunks per thread)
     uint32_t j = 0;
     int ssq_b = -1;
     auto flush_ssq = [&](int bb) {
@@ -432,8 +433,17 @@ conv1d_umma_kernel(const sty_conv1d_args p, const UmmaPlan pl) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int c = half + kColParts * i;
-          if (c < n_chunks16) atomicAdd(p.out_sumsq + (int64_t)bb * CO + co0 + c * 16 + lane, ssq_acc[i]);
+          if (p.out_sumsq && c < n_chunks16)
+            atomicAdd(p.out_sumsq + (int64_t)bb * CO + co0 + c * 16 + lane, ssq_acc[i]);
           ssq_acc[i] = 0.f;
+        }
+        if (p.out_sum) {
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const int c = half + kColParts * i;
+            if (c < n_chunks16) atomicAdd(p.out_sum + (int64_t)bb * CO + co0 + c * 16 + lane, sum_acc[i]);
+            sum_acc[i] = 0.f;
+          }
         }
       }
     };
@@ -441,7 +451,7 @@ conv1d_umma_kernel(const sty_conv1d_args p, const UmmaPlan pl) {
       const int b = tile / pl.tiles_per_b;
       const int t0 = (tile - b * pl.tiles_per_b) * MT;
       const uint32_t a = j & 1;
-      if (p.out_sumsq && ssq_b != b) {
+      if ((p.out_sumsq || p.out_sum) && ssq_b != b) {
         if (ssq_b >= 0) flush_ssq(ssq_b);
         ssq_b = b;
       }
@@ -506,6 +516,15 @@ conv1d_umma_kernel(const sty_conv1d_args p, const UmmaPlan pl) {
             }
           }
         }
+        if (p.out_sum) {
+          float cp[16];
+#pragma unroll
+          for (int jj = 0; jj < 16; ++jj) cp[jj] = r[jj];
+          const float colsum = warp_colsum16(cp, lane);
+#pragma unroll
+          for (int i = 0; i < 2; ++i)
+            if (i == ci) sum_acc[i] += colsum;
+        }
 #pragma unroll
         for (int jj = 0; jj < 16; ++jj) r[jj] *= r[jj];
         if (p.out_sumsq) {
@@ -518,7 +537,7 @@ conv1d_umma_kernel(const sty_conv1d_args p, const UmmaPlan pl) {
       tc_fence_before();
       mbar_arrive(&acc_empty[a]);
     }
-    if (p.out_sumsq && ssq_b >= 0) flush_ssq(ssq_b);
+    if ((p.out_sumsq || p.out_sum) && ssq_b >= 0) flush_ssq(ssq_b);
   }
   tc_fence_before();
   __syncthreads();
@@ -600,6 +619,7 @@ static int umma_out_mode(const sty_conv1d_args& a) {
 bool conv1d_umma_eligible(const sty_conv1d_args& a) {
   if (!a.w_split || a.w_bs != 0 || a.T < 64) return false;
   if (umma_in_mode(a) < 0 || umma_out_mode(a) < 0) return false;
+  if (a.out_sum && a.CO > 64) return false;
   UmmaPlan pl;
   return make_plan(a, pl);
 }

@@ -416,3 +416,30 @@ extern "C" int sty_linear_rows_fwd(const float* s, const float* W, const float* 
   STY_CHECK_LAUNCH("linear_rows");
   return STY_OK;
 }
+
+// ------------------------------------------------------------ AdaIN affine from accumulated moments
+namespace sty {
+__global__ void moments_affine_kernel(const float* __restrict__ sum, const float* __restrict__ sumsq,
+                                      const float* __restrict__ gb, int64_t gb_bs, float* __restrict__ scale,
+                                      float* __restrict__ shift, int B, int C, float invT, float eps) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * C) return;
+  const int b = i / C, c = i - b * C;
+  const float mean = sum[i] * invT;
+  const float var = fmaxf(fmaf(-mean, mean, sumsq[i] * invT), 0.f);
+  const float sc = (1.0f + gb[(int64_t)b * gb_bs + c]) / sqrtf(var + eps);
+  scale[i] = sc;
+  shift[i] = gb[(int64_t)b * gb_bs + C + c] - mean * sc;
+}
+}  // namespace sty
+
+extern "C" int sty_moments_affine_fwd(const float* sum, const float* sumsq, const float* gb, int64_t gb_bs,
+                                      float* scale, float* shift, int B, int C, int T, float eps,
+                                      sty_stream_t stream) {
+  using namespace sty;
+  STY_REQUIRE(sum && sumsq && gb && scale && shift && B > 0 && C > 0 && T > 0, "moments_affine: bad argument");
+  moments_affine_kernel<<<cdiv((int64_t)B * C, 128), 128, 0, as_stream(stream)>>>(sum, sumsq, gb, gb_bs, scale, shift,
+                                                                               B, C, 1.0f / (float)T, eps);
+  STY_CHECK_LAUNCH("moments_affine");
+  return STY_OK;
+}

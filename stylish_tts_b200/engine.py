@@ -23,6 +23,8 @@ INV_SQRT2 = 1.0 / math.sqrt(2.0)
 # tensor-core (tcgen05, bf16x3) path for eligible convs; STYLISH_B200_UMMA=0 forces fp32 FMA
 USE_UMMA = os.environ.get("STYLISH_B200_UMMA", "1") != "0"
 UMMA_MIN_T = 64
+# InstanceNorm statistics of the S-rate AdaINs accumulated in the producing conv's epilogue (one pass less)
+FUSE_STATS = os.environ.get("STYLISH_B200_FUSE_STATS", "1") != "0"
 
 
 def split_bf16(w_oik: torch.Tensor) -> torch.Tensor:
@@ -56,7 +58,7 @@ class ConvW:
 
 def conv1d(x, cw: ConvW, *, dil=1, out=None, res=None, in_scale=None, in_shift=None,
            in_alpha=None, in_act=ACT_NONE, in_mask=None, out_mask=None, out_act=ACT_NONE,
-           out_alpha=None, out_sumsq=None, shuffle=0, out_scale=1.0, res_scale=1.0, umma=True,
+           out_alpha=None, out_sumsq=None, out_sum=None, shuffle=0, out_scale=1.0, res_scale=1.0, umma=True,
            dwln=None):
     B, CI, T = x.shape
     assert CI == cw.CI, (CI, cw.CI)
@@ -78,6 +80,7 @@ def conv1d(x, cw: ConvW, *, dil=1, out=None, res=None, in_scale=None, in_shift=N
     a.in_scale, a.in_shift, a.in_alpha = L.ptr(in_scale), L.ptr(in_shift), L.ptr(in_alpha)
     a.in_mask, a.out_mask, a.out_alpha = L.ptr(in_mask), L.ptr(out_mask), L.ptr(out_alpha)
     a.out_sumsq = L.ptr(out_sumsq)
+    a.out_sum = L.ptr(out_sum)
     a.B, a.CI, a.CO, a.T, a.K, a.dil = B, CI, cw.CO, T, cw.K, dil
     a.pad = (cw.K - 1) * dil // 2
     a.in_act, a.out_act, a.shuffle = in_act, out_act, shuffle
@@ -115,6 +118,16 @@ def instnorm_affine(x, gb, gb_bs, eps=1e-5):
     scale = torch.empty((B, Cc), device=x.device, dtype=torch.float32)
     shift = torch.empty((B, Cc), device=x.device, dtype=torch.float32)
     L.call("sty_instnorm_affine_fwd", x.data_ptr(), x_bs, x_cs, gb.data_ptr(), gb_bs,
+           scale.data_ptr(), shift.data_ptr(), B, Cc, T, eps, L.stream_ptr())
+    return scale, shift
+
+
+def moments_affine(mom, gb, gb_bs, T, eps=1e-5):
+    """AdaIN affine from the (2, B, C) moments (sum, sum of squares) a producer conv accumulated."""
+    _, B, Cc = mom.shape
+    scale = torch.empty((B, Cc), device=mom.device, dtype=torch.float32)
+    shift = torch.empty((B, Cc), device=mom.device, dtype=torch.float32)
+    L.call("sty_moments_affine_fwd", mom[0].data_ptr(), mom[1].data_ptr(), gb.data_ptr(), gb_bs,
            scale.data_ptr(), shift.data_ptr(), B, Cc, T, eps, L.stream_ptr())
     return scale, shift
 
@@ -477,16 +490,30 @@ class SpeechEngine:
         conv1d(hb, blk["pw2"], in_scale=gs, res=x, out=x)
         return x
 
-    def gen_block(self, P: Packed, blocks, x, h):
-        """AdaptiveGeneratorBlock, in place on x (ada_norm.py:109-120)."""
+    def gen_block(self, P: Packed, blocks, x, h, mom=None):
+        """AdaptiveGeneratorBlock, in place on x (ada_norm.py:109-120).  The InstanceNorm statistics of
+        every AdaIN are accumulated (sum, sum of squares per (b,c)) by the conv that produces its input
+        (`mom` = those of x, from the caller's conv) instead of a separate pass over the tensor."""
         J = P.fc_rows
+        B, Cc, T = x.shape
+        fused = mom is not None and FUSE_STATS
         for blk in blocks:
-            sc1, sh1 = instnorm_affine(x, self._gb(P, h, blk["n1"]), J)
+            if fused:
+                sc1, sh1 = moments_affine(mom, self._gb(P, h, blk["n1"]), J, T)
+                mom_t = torch.zeros((2, B, Cc), device=x.device, dtype=torch.float32)
+                mom = torch.zeros((2, B, Cc), device=x.device, dtype=torch.float32)
+            else:
+                sc1, sh1 = instnorm_affine(x, self._gb(P, h, blk["n1"]), J)
+                mom_t = None
             xt = conv1d(x, blk["c1"], dil=blk["dil"], in_scale=sc1, in_shift=sh1, in_act=ACT_SNAKE,
-                        in_alpha=blk["a1"])
-            sc2, sh2 = instnorm_affine(xt, self._gb(P, h, blk["n2"]), J)
+                        in_alpha=blk["a1"], out_sum=None if mom_t is None else mom_t[0],
+                        out_sumsq=None if mom_t is None else mom_t[1])
+            if fused:
+                sc2, sh2 = moments_affine(mom_t, self._gb(P, h, blk["n2"]), J, T)
+            else:
+                sc2, sh2 = instnorm_affine(xt, self._gb(P, h, blk["n2"]), J)
             conv1d(xt, blk["c2"], in_scale=sc2, in_shift=sh2, in_act=ACT_SNAKE, in_alpha=blk["a2"],
-                   res=x, out=x)
+                   res=x, out=x, out_sum=mom[0] if fused else None, out_sumsq=mom[1] if fused else None)
         return x
 
     def harmonic_prior(self, P: Packed, pitch, voiced, noise, taps=None):
@@ -535,10 +562,11 @@ class SpeechEngine:
         Hs = P.hidden_s
         # phase-head input: [upsampled mel | logamp prior | phase prior] in one buffer
         pin = torch.empty((B, 3 * Hs, S), device=dev, dtype=torch.float32)
-        lp = conv1d(har_spec, P.amp_prior_conv, out=pin[:, Hs:2 * Hs])
-        self.gen_block(P, P.amp_prior_block, lp, h)
-        pp = conv1d(har_phase, P.phase_prior_conv, out=pin[:, 2 * Hs:])
-        self.gen_block(P, P.phase_prior_block, pp, h)
+        mom = torch.zeros((2, 2, B, Hs), device=dev, dtype=torch.float32)
+        lp = conv1d(har_spec, P.amp_prior_conv, out=pin[:, Hs:2 * Hs], out_sum=mom[0, 0], out_sumsq=mom[0, 1])
+        self.gen_block(P, P.amp_prior_block, lp, h, mom[0])
+        pp = conv1d(har_phase, P.phase_prior_conv, out=pin[:, 2 * Hs:], out_sum=mom[1, 0], out_sumsq=mom[1, 1])
+        self.gen_block(P, P.phase_prior_block, pp, h, mom[1])
         if taps is not None:
             taps["logamp_prior"], taps["phase_prior"] = lp.clone(), pp.clone()
         for blk in P.amp_convnext:

@@ -370,3 +370,25 @@ def test_convnext_front_fused_into_pointwise_conv(Cc, T):
                   dwln=(dww, dwb, gbd, gb.shape[1], 1e-6))
     assert rel_l2(hb, h) < 3e-5
     assert rel_l2(ssq, (h ** 2).sum(2)) < 3e-5
+
+
+@pytest.mark.parametrize("umma", [True, False])
+def test_conv1d_epilogue_moments_feed_adain(umma):
+    """out_sum / out_sumsq accumulated by the producing conv + sty_moments_affine_fwd == the two-pass
+    InstanceNorm statistics of sty_instnorm_affine_fwd (ada_norm.py:129-140)"""
+    gen = g(77)
+    B, ci, co, k, T = 3, 32, 32, 11, 1500
+    x = torch.randn(B, ci, T, generator=gen)
+    w = torch.randn(co, ci, k, generator=gen) / math.sqrt(ci * k)
+    b = torch.randn(co, generator=gen) * 0.5
+    res = torch.randn(B, co, T, generator=gen)
+    gb = torch.randn(B, 2 * co, generator=gen) * 0.3
+    cw = E.ConvW(w.to(dev()), b.to(dev()))
+    mom = torch.zeros(2, B, co, device=dev())
+    y = E.conv1d(x.to(dev()), cw, res=res.to(dev()), out_sum=mom[0], out_sumsq=mom[1], umma=umma)
+    ref = F.conv1d(x.double(), w.double(), b.double(), padding=5) + res.double()
+    assert rel_l2(y, ref) < 3e-5
+    assert rel_l2(mom[0], ref.sum(-1)) < 1e-4 and rel_l2(mom[1], (ref * ref).sum(-1)) < 1e-4
+    sc, sh = E.moments_affine(mom, gb.to(dev()), 2 * co, T)
+    sc2, sh2 = E.instnorm_affine(y, gb.to(dev()), 2 * co)
+    assert rel_l2(sc, sc2) < 2e-5 and rel_l2(sh, sh2) < 5e-5
