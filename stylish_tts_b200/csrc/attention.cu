@@ -9,6 +9,7 @@
 //
 // This is the fp32 SIMT path (parity-first).  See DESIGN.md for the tcgen05 plan.
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -159,6 +160,11 @@ extern "C" int sty_rope_table(float* cos_out, float* sin_out, int T, int d_rot, 
   return STY_OK;
 }
 
+namespace sty {
+int attention_umma_launch(const float* q, const float* k, const float* v, int64_t qkv_bs, float* o, int64_t o_bs,
+                          int B, int H, int T, float scale, float* lse, cudaStream_t st);  // attention_umma.cu
+}
+
 static int attention_launch(const float* q, const float* k, const float* v, int64_t qkv_bs,
                             float* o, int64_t o_bs, const int64_t* lengths,
                             const float* rope_cos, const float* rope_sin, int d_rot, int B,
@@ -180,6 +186,8 @@ static int attention_launch(const float* q, const float* k, const float* v, int6
       attention_kernel<16, 32, QB, 0><<<grid, QB, 0, st>>>(q, k, v, qkv_bs, o, o_bs, lengths,
                                                            rope_cos, rope_sin, T, scale, lse);
     }
+  } else if (D == 64 && !rope_cos && !lengths && T >= 64 && !getenv("STYLISH_B200_ATTN_SIMT")) {
+    return attention_umma_launch(q, k, v, qkv_bs, o, o_bs, B, H, T, scale, lse, st);  // tcgen05 path
   } else if (D == 64) {
     constexpr int QB = 128;
     dim3 grid(cdiv(T, QB), H, B);

@@ -198,9 +198,20 @@ istft_head_kernel(const float* __restrict__ logamp, int64_t logamp_bs,
       const int fs = min(f, S - 1);  // replicate-pad of one frame (generator.py:784-785)
       const int64_t o = (int64_t)kb * S + fs;
       const float mag = expf(logamp[(int64_t)b * logamp_bs + o]);
-      const float ph = atan2f(imag[(int64_t)b * ri_bs + o], real[(int64_t)b * ri_bs + o]);
-      re = mag * cosf(ph);
-      im = mag * sinf(ph);
+      // cos(atan2(y, x)) = x/|z|, sin(atan2(y, x)) = y/|z| (atan2(0, 0) = 0 -> cos 1, sin 0): one rsqrt
+      // instead of atan2f + cosf + sinf; the operands are scaled first so x^2 + y^2 cannot over/underflow
+      const float xr = real[(int64_t)b * ri_bs + o], yi = imag[(int64_t)b * ri_bs + o];
+      const float big = fmaxf(fabsf(xr), fabsf(yi));
+      float c = 1.f, sn = 0.f;
+      if (big > 0.f) {
+        const float inv = 1.0f / big;
+        const float xs = xr * inv, ys = yi * inv;
+        const float rn = rsqrtf(fmaf(xs, xs, ys * ys));
+        c = xs * rn;
+        sn = ys * rn;
+      }
+      re = mag * c;
+      im = mag * sn;
     }
     res[idx] = re;
     ims[idx] = im;

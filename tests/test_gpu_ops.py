@@ -234,14 +234,16 @@ def test_attention_text(T, lens):
     assert rel_l2(out, ref) < 5e-5
 
 
-def test_attention_conformer():
+@pytest.mark.parametrize("T", [203, 803, 64, 129])
+def test_attention_conformer(T):
+    """8 heads x 64, no mask: the tcgen05 flash kernel (bf16x3) against fp64 softmax attention"""
     gen = g(64)
-    B, H, D, T = 2, 8, 64, 203
-    qkv = torch.randn(B, 3 * H * D, T, generator=gen)
-    q, k, v = (so.heads_split(t.contiguous(), H) for t in (qkv[:, :512], qkv[:, 512:1024], qkv[:, 1024:]))
+    B, H, D = 2, 8, 64
+    qkv = torch.randn(B, 3 * H * D, T, generator=gen) * 1.5
+    q, k, v = (so.heads_split(t.contiguous().double(), H) for t in (qkv[:, :512], qkv[:, 512:1024], qkv[:, 1024:]))
     ref = (torch.softmax(q @ k.transpose(2, 3) * D ** -0.5, -1) @ v).transpose(2, 3).reshape(B, H * D, T)
     out = E.attention(qkv.to(dev()), 512, 512, 512, H=H, D=D, scale=D ** -0.5)
-    assert rel_l2(out, ref) < TOL
+    assert rel_l2(out, ref) < 3e-5, rel_l2(out, ref)
 
 
 def test_bmm_glu_embed_mask_linear():
