@@ -301,6 +301,19 @@ def measure_train(args, dev, world, rank, barrier, steps, warmup, batch):
     return res
 
 
+def ncu_traffic(sig):
+    """DRAM bytes per launch of the kernel from the committed `ncu --set full` captures (profiles/), if one
+    matches this kernel signature; None otherwise."""
+    try:
+        j = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")))
+        for key, val in j["traffic_bytes_per_launch"].items():
+            if key in sig:
+                return val
+    except Exception:
+        pass
+    return None
+
+
 def conv_alg_bytes(info):
     n = info["B"] * info["T"] * (info["CI"] + info["CO"]) * 4
     if info["res"]:
@@ -430,7 +443,7 @@ def run_ours(args):
             flops = 2.0 * v["info"]["B"] * v["info"]["T"] * v["info"]["CI"] * v["info"]["CO"] * v["info"]["K"]
             ach = byts / avg_s / 1e9
             roofline = {"bound": "hbm", "kernel": k, "achieved": round(ach, 1), "peak": peak,
-                        "unit": "GB/s", "frac": round(ach / peak, 4), "traffic": None,
+                        "unit": "GB/s", "frac": round(ach / peak, 4), "traffic": ncu_traffic(k),
                         "peak_source": how, "alg_bytes_per_launch": byts,
                         "avg_launch_ms": round(avg_s * 1e3, 4),
                         "share_of_step": round(v["ms"] / total, 4),

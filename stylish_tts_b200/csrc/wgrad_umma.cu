@@ -57,52 +57,65 @@ struct SideDesc {
   int C, c0, groups, rows, valid_rows, t_start, is_input;
 };
 
-// Stage both sides of a chunk.  The items (one 8-channel x 1-step cell each) of the two sides form one index
-// space; a thread first issues the global loads of up to U items (32 loads in flight — staging is
-// latency-bound otherwise), then transforms, splits and stores them.
-__device__ __forceinline__ void stage_chunk(const SideDesc& A, const SideDesc& Bd, const sty_conv1d_wgrad_args& p,
-                                            const float* prm, int in_groups, int tid) {
-  const int nA = A.groups * A.rows, n_items = nA + Bd.groups * Bd.rows;
-  constexpr int U = 4;  // 32 global loads in flight per thread (6 spills registers and is slower: measured)
-  for (int i0 = tid; i0 < n_items; i0 += kWgThreads * U) {
+// Stage one side of a chunk with `nthr` threads (this thread is `lt` of them).  Items = (8-channel group, time
+// step) cells; a thread first issues the global loads of up to U items (32 loads in flight — staging is
+// latency-bound otherwise), then transforms, splits and stores them.  (g, row) of successive items is stepped
+// incrementally — no integer division in the loop.
+template <bool IS_INPUT>
+__device__ __forceinline__ void stage_side(const SideDesc& S, const sty_conv1d_wgrad_args& p, const float* prm,
+                                           int in_groups, int lt, int nthr) {
+  constexpr int U = 4;
+  const int n_items = S.groups * S.rows;
+  const int g_step = nthr / S.rows, r_step = nthr - g_step * S.rows;
+  int g = lt / S.rows, row = lt - g * S.rows;
+  const bool chan_full = S.c0 + S.groups * 8 <= S.C;  // every staged channel exists: no per-channel checks
+  for (int i0 = lt; i0 < n_items; i0 += nthr * U) {
     float v[U][8];
+    int gg[U], rr[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const int item = i0 + u * kWgThreads;
-      const bool second = item >= nA;
-      const SideDesc& S = second ? Bd : A;
-      const int li = second ? item - nA : item;
-      const int g = S.rows == kTT ? (li >> 7) : li / S.rows, row = li - g * S.rows;
+      gg[u] = g;
+      rr[u] = row;
       const int t = S.t_start + row;
-      const bool ok = item < n_items && row < S.valid_rows && t >= 0 && t < p.T;
+      const bool ok = (i0 + u * nthr) < n_items && row < S.valid_rows && t >= 0 && t < p.T;
+      const float* __restrict__ src = S.src + (int64_t)(S.c0 + g * 8) * S.cs + t;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int c = S.c0 + g * 8 + j;
-        v[u][j] = (ok && c < S.C) ? S.src[(int64_t)c * S.cs + t] : 0.f;
+      for (int j = 0; j < 8; ++j)
+        v[u][j] = (ok && (chan_full || S.c0 + g * 8 + j < S.C)) ? src[(int64_t)j * S.cs] : 0.f;
+      row += r_step;
+      g += g_step;
+      if (row >= S.rows) {
+        row -= S.rows;
+        ++g;
       }
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const int item = i0 + u * kWgThreads;
-      if (item >= n_items) continue;
-      const bool second = item >= nA;
-      const SideDesc& S = second ? Bd : A;
-      const int li = second ? item - nA : item;
-      const int g = S.rows == kTT ? (li >> 7) : li / S.rows, row = li - g * S.rows;
-      const int t = S.t_start + row;
-      const bool ok = row < S.valid_rows && t >= 0 && t < p.T;
+      if (i0 + u * nthr >= n_items) continue;
+      const int t = S.t_start + rr[u];
+      const bool ok = rr[u] < S.valid_rows && t >= 0 && t < p.T;
       const float m = (ok && S.mask) ? S.mask[t] : 1.f;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int cl = g * 8 + j;
-        float w;
-        if (S.is_input) {
-          w = fmaf(v[u][j] * m, prm[cl], prm[in_groups * 8 + cl]);
-          if (p.in_act != STY_ACT_NONE) w = wg_act(w, p.in_act, prm[2 * in_groups * 8 + cl]);
-        } else {
-          w = v[u][j] * m * p.out_scale;
+      if (IS_INPUT) {
+        const int cl = gg[u] * 8;
+        float sc[8], sh[8], al[8];
+        *reinterpret_cast<float4*>(sc) = *reinterpret_cast<const float4*>(prm + cl);
+        *reinterpret_cast<float4*>(sc + 4) = *reinterpret_cast<const float4*>(prm + cl + 4);
+        *reinterpret_cast<float4*>(sh) = *reinterpret_cast<const float4*>(prm + in_groups * 8 + cl);
+        *reinterpret_cast<float4*>(sh + 4) = *reinterpret_cast<const float4*>(prm + in_groups * 8 + cl + 4);
+        if (p.in_act == STY_ACT_SNAKE) {
+          *reinterpret_cast<float4*>(al) = *reinterpret_cast<const float4*>(prm + 2 * in_groups * 8 + cl);
+          *reinterpret_cast<float4*>(al + 4) = *reinterpret_cast<const float4*>(prm + 2 * in_groups * 8 + cl + 4);
         }
-        v[u][j] = (ok && (S.c0 + cl) < S.C) ? w : 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float w = fmaf(v[u][j] * m, sc[j], sh[j]);
+          if (p.in_act != STY_ACT_NONE) w = wg_act(w, p.in_act, al[j]);
+          v[u][j] = (ok && (chan_full || S.c0 + cl + j < S.C)) ? w : 0.f;
+        }
+      } else {
+        const float mm = m * p.out_scale;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[u][j] *= mm;  // out-of-range cells were loaded as 0
       }
       uint32_t h[4], l[4];
 #pragma unroll
@@ -111,13 +124,26 @@ __device__ __forceinline__ void stage_chunk(const SideDesc& A, const SideDesc& B
         h[j] = pack_bf16(a0, a1);
         l[j] = pack_bf16(a0 - __uint_as_float(h[j] << 16), a1 - __uint_as_float(h[j] & 0xffff0000u));
       }
-      S.dst[(0 * S.groups + g) * S.rows + row] = make_uint4(h[0], h[1], h[2], h[3]);
-      S.dst[(1 * S.groups + g) * S.rows + row] = make_uint4(l[0], l[1], l[2], l[3]);
+      S.dst[(0 * S.groups + gg[u]) * S.rows + rr[u]] = make_uint4(h[0], h[1], h[2], h[3]);
+      S.dst[(1 * S.groups + gg[u]) * S.rows + rr[u]] = make_uint4(l[0], l[1], l[2], l[3]);
     }
   }
 }
 
-__global__ void __launch_bounds__(kWgThreads + 32, 1)
+// Both sides of a chunk, concurrently: the producer threads are split between the two sides in proportion
+// to their item counts (warp granularity), so a chunk costs one load round trip.
+__device__ __forceinline__ void stage_chunk(const SideDesc& A, const SideDesc& Bd, const sty_conv1d_wgrad_args& p,
+                                            const float* prm, int in_groups, int tid, int nthr_a) {
+  if (tid < nthr_a) {
+    if (A.is_input) stage_side<true>(A, p, prm, in_groups, tid, nthr_a);
+    else stage_side<false>(A, p, prm, in_groups, tid, nthr_a);
+  } else {
+    if (Bd.is_input) stage_side<true>(Bd, p, prm, in_groups, tid - nthr_a, kWgThreads - nthr_a);
+    else stage_side<false>(Bd, p, prm, in_groups, tid - nthr_a, kWgThreads - nthr_a);
+  }
+}
+
+__global__ void __maxnreg__(120)
 conv1d_wgrad_umma_kernel(const sty_conv1d_wgrad_args p, const WgPlan pl) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   uint4* stage0 = reinterpret_cast<uint4*>(smem_raw);
@@ -159,6 +185,14 @@ conv1d_wgrad_umma_kernel(const sty_conv1d_wgrad_args p, const WgPlan pl) {
   const uint32_t sbo_m = pl.mode == 0 ? (uint32_t)p.dil : (uint32_t)pl.rows_m;
 
   const uint32_t n_it = (uint32_t)(c_end - c_begin);
+  // producer threads given to the M side: proportional to its share of the items, whole warps, >= 1 warp each
+  int nthr_m;
+  {
+    const int im = pl.m_groups * pl.rows_m, in_ = pl.n_groups * pl.rows_n;
+    int wm = (int)(((int64_t)(kWgThreads / 32) * im + (im + in_) / 2) / (im + in_));
+    wm = wm < 1 ? 1 : (wm > kWgThreads / 32 - 1 ? kWgThreads / 32 - 1 : wm);
+    nthr_m = wm * 32;
+  }
   if (warp < kWgThreads / 32) {
     // =========================== producers (16 warps): stage chunk after chunk into the ring
     int cur_b = -1;
@@ -194,7 +228,7 @@ conv1d_wgrad_umma_kernel(const sty_conv1d_wgrad_args p, const WgPlan pl) {
         sm_ = SideDesc{Ms, xb, im, p.x_cs, p.CI, m0, pl.m_groups, pl.rows_m, pl.valid_rows, t0 - p.pad, 1};
         sn_ = SideDesc{Ns, gb, om, p.dy_cs, p.CO, n0, pl.n_groups, kTT, kTT, t0, 0};
       }
-      stage_chunk(sm_, sn_, p, prm, in_groups, tid);
+      stage_chunk(sm_, sn_, p, prm, in_groups, tid, nthr_m);
       fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor-core proxy
       mbar_arrive(&full[s]);
     }
