@@ -12,7 +12,7 @@
 // three MMAs (hi*hi + lo*hi + hi*lo) accumulate in fp32, as in the forward kernel (conv1d_umma.cu).
 //
 // One CTA per SM walks a range of (batch, 128-step) chunks with a two-stage shared-memory ring and two
-// roles handing over through mbarriers: 16 producer warps stage chunk i+1 (prologue / mask applied on the
+// roles handing over through mbarriers: 15 producer warps stage chunk i+1 (prologue / mask applied on the
 // fly, 32 global loads in flight per thread) while a dedicated warp issues the MMAs of chunk i; the
 // accumulators stay in TMEM for the whole range and are added to dw with atomics once.
 #include "umma.cuh"
@@ -20,7 +20,7 @@
 namespace sty {
 namespace {
 
-constexpr int kWgThreads = 512;
+constexpr int kWgThreads = 480;  // 15 producer warps + 1 MMA warp = 4 warps per SM sub-partition: 128 registers each
 constexpr int kTT = 128;  // time steps per chunk
 
 struct WgPlan {
@@ -55,6 +55,7 @@ struct SideDesc {
   const float* mask;  // (T) or nullptr
   int64_t cs;
   int C, c0, groups, rows, valid_rows, t_start, is_input;
+  int blocked;  // 1: [time/8][group][8 steps] (core matrices of one K block adjacent), 0: [group][time]
 };
 
 // Stage one side of a chunk with `nthr` threads (this thread is `lt` of them).  Items = (8-channel group, time
@@ -64,7 +65,7 @@ struct SideDesc {
 template <bool IS_INPUT>
 __device__ __forceinline__ void stage_side(const SideDesc& S, const sty_conv1d_wgrad_args& p, const float* prm,
                                            int in_groups, int lt, int nthr) {
-  constexpr int U = 4;
+  constexpr int U = 4;  // 32 loads in flight per thread (6 measured slower)
   const int n_items = S.groups * S.rows;
   const int g_step = nthr / S.rows, r_step = nthr - g_step * S.rows;
   int g = lt / S.rows, row = lt - g * S.rows;
@@ -124,8 +125,9 @@ __device__ __forceinline__ void stage_side(const SideDesc& S, const sty_conv1d_w
         h[j] = pack_bf16(a0, a1);
         l[j] = pack_bf16(a0 - __uint_as_float(h[j] << 16), a1 - __uint_as_float(h[j] & 0xffff0000u));
       }
-      S.dst[(0 * S.groups + gg[u]) * S.rows + rr[u]] = make_uint4(h[0], h[1], h[2], h[3]);
-      S.dst[(1 * S.groups + gg[u]) * S.rows + rr[u]] = make_uint4(l[0], l[1], l[2], l[3]);
+      const int at = S.blocked ? (((rr[u] >> 3) * S.groups + gg[u]) << 3) + (rr[u] & 7) : gg[u] * S.rows + rr[u];
+      S.dst[at] = make_uint4(h[0], h[1], h[2], h[3]);
+      S.dst[S.groups * S.rows + at] = make_uint4(l[0], l[1], l[2], l[3]);
     }
   }
 }
@@ -143,7 +145,7 @@ __device__ __forceinline__ void stage_chunk(const SideDesc& A, const SideDesc& B
   }
 }
 
-__global__ void __maxnreg__(120)
+__global__ void __launch_bounds__(kWgThreads + 32, 1)
 conv1d_wgrad_umma_kernel(const sty_conv1d_wgrad_args p, const WgPlan pl) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   uint4* stage0 = reinterpret_cast<uint4*>(smem_raw);
@@ -194,14 +196,14 @@ conv1d_wgrad_umma_kernel(const sty_conv1d_wgrad_args p, const WgPlan pl) {
     nthr_m = wm * 32;
   }
   if (warp < kWgThreads / 32) {
-    // =========================== producers (16 warps): stage chunk after chunk into the ring
+    // =========================== producers (15 warps): stage chunk after chunk into the ring
     int cur_b = -1;
     uint32_t it = 0;
     for (int64_t chunk = c_begin; chunk < c_end; ++chunk, ++it) {
       const int b = (int)(chunk / pl.n_tchunks);
       const int t0 = (int)(chunk - (int64_t)b * pl.n_tchunks) * kTT;
       const uint32_t s = it % (uint32_t)pl.stages;
-      mbar_wait_sleep(&empty[s], ((it / (uint32_t)pl.stages) & 1u) ^ 1u);  // MMAs that read this stage are done
+      mbar_wait(&empty[s], ((it / (uint32_t)pl.stages) & 1u) ^ 1u);  // MMAs that read this stage are done (no nanosleep: with a 2-stage ring an overslept wake-up stalls the tensor core)
       if (b != cur_b) {  // prologue parameters of this batch element
         asm volatile("bar.sync 1, %0;" ::"n"(kWgThreads) : "memory");
         for (int c = tid; c < 8 * in_groups; c += kWgThreads) {
@@ -222,11 +224,13 @@ conv1d_wgrad_umma_kernel(const sty_conv1d_wgrad_args p, const WgPlan pl) {
       const float* om = p.out_mask ? p.out_mask + (int64_t)b * p.T : nullptr;
       SideDesc sm_, sn_;
       if (pl.mode >= 2) {  // M side = output gradient, N side = input
-        sm_ = SideDesc{Ms, gb, om, p.dy_cs, p.CO, m0, pl.m_groups, pl.rows_m, kTT, t0, 0};
-        sn_ = SideDesc{Ns, xb, im, p.x_cs, p.CI, n0, pl.n_groups, pl.rows_n, pl.valid_rows, t0 - p.pad, 1};
+        sm_ = SideDesc{Ms, gb, om, p.dy_cs, p.CO, m0, pl.m_groups, pl.rows_m, kTT, t0, 0, pl.mode == 2};
+        sn_ = SideDesc{Ns, xb, im, p.x_cs, p.CI, n0, pl.n_groups, pl.rows_n, pl.valid_rows, t0 - p.pad, 1,
+                       pl.mode == 2};
       } else {             // M side = input (taps folded by the descriptor), N side = output gradient
-        sm_ = SideDesc{Ms, xb, im, p.x_cs, p.CI, m0, pl.m_groups, pl.rows_m, pl.valid_rows, t0 - p.pad, 1};
-        sn_ = SideDesc{Ns, gb, om, p.dy_cs, p.CO, n0, pl.n_groups, kTT, kTT, t0, 0};
+        sm_ = SideDesc{Ms, xb, im, p.x_cs, p.CI, m0, pl.m_groups, pl.rows_m, pl.valid_rows, t0 - p.pad, 1,
+                       pl.mode == 1};
+        sn_ = SideDesc{Ns, gb, om, p.dy_cs, p.CO, n0, pl.n_groups, kTT, kTT, t0, 0, 1};
       }
       stage_chunk(sm_, sn_, p, prm, in_groups, tid, nthr_m);
       fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor-core proxy
@@ -241,7 +245,12 @@ conv1d_wgrad_umma_kernel(const sty_conv1d_wgrad_args p, const WgPlan pl) {
       if (lane == 0) {
         const uint4* Ms = stage0 + (size_t)s * pl.stage_u4;
         const uint32_t m_addr = smem_u32(Ms), n_addr = smem_u32(Ms + 2 * m_plane);
-        const uint64_t bd = make_desc(n_addr, 8u, (uint32_t)pl.rows_n);
+        // blocked sides: K blocks are n_groups (m_groups) core matrices apart, groups adjacent (LBO = 8*groups, SBO = 8)
+        const bool n_blk = pl.mode != 3, m_blk = pl.mode == 1 || pl.mode == 2;
+        const uint64_t bd = n_blk ? make_desc(n_addr, 8u * (uint32_t)pl.n_groups, 8u)
+                                  : make_desc(n_addr, 8u, (uint32_t)pl.rows_n);
+        const uint32_t a_kstep = m_blk ? 16u * (uint32_t)pl.m_groups : 16u;  // 16 time steps, in 16-byte units
+        const uint32_t b_kstep = n_blk ? 16u * (uint32_t)pl.n_groups : 16u;
         const uint32_t b_hi32 = (uint32_t)(bd >> 32);
         const uint32_t first = it == 0 ? 0u : 1u;
         for (int acc = 0; acc < pl.n_acc; ++acc) {
@@ -250,12 +259,13 @@ conv1d_wgrad_umma_kernel(const sty_conv1d_wgrad_args p, const WgPlan pl) {
           const int g = pl.mode == 0 ? acc / pl.tap_chunks : 0;
           const int tc = pl.mode == 0 ? acc - g * pl.tap_chunks : 0;
           const uint32_t a_off = (uint32_t)(g * pl.rows_m + tc * 16 * p.dil);  // uint4 units
-          const uint64_t ad = make_desc(m_addr + a_off * 16u, 8u, sbo_m);
+          const uint64_t ad = m_blk ? make_desc(m_addr, 8u * (uint32_t)pl.m_groups, 8u)
+                                    : make_desc(m_addr + a_off * 16u, 8u, sbo_m);
           const uint32_t a_hi32 = (uint32_t)(ad >> 32), a_lo = (uint32_t)ad;
           const uint32_t d = tmem_base + (uint32_t)(acc * N);
 #pragma unroll 2
           for (uint32_t ks = 0; ks < kTT / 16; ++ks) {
-            const uint32_t ak = a_lo + ks * 16u, bk = b_lo + ks * 16u;  // 16 time steps = 16 units of 16 B
+            const uint32_t ak = a_lo + ks * a_kstep, bk = b_lo + ks * b_kstep;
             umma_bf16_w(d, ak, a_hi32, bk, b_hi32, idesc, ks == 0 ? first : 1u);            // hi * hi
             umma_bf16_w(d, ak + (uint32_t)m_plane, a_hi32, bk, b_hi32, idesc, 1u);          // lo * hi
             umma_bf16_w(d, ak, a_hi32, bk + (uint32_t)n_plane, b_hi32, idesc, 1u);          // hi * lo
@@ -274,11 +284,12 @@ conv1d_wgrad_umma_kernel(const sty_conv1d_wgrad_args p, const WgPlan pl) {
 
   // ---- accumulators -> dw (atomics).  thread owns TMEM lane m = 32*(warp&3) + lane; the four warp
   // groups split the 16-column chunks
-  if (it > 0 && warp < kWgThreads / 32) {
+  constexpr int kParts = (kWgThreads / 32) / 4;  // complete groups of 4 warps (one per TMEM lane quadrant)
+  if (it > 0 && warp < 4 * kParts) {
     const int q = warp & 3, part = warp >> 2;
     const int m = q * 32 + lane;
     const int chunks16 = (pl.n_acc * N) >> 4;
-    for (int c = part; c < chunks16; c += kWgThreads / 128) {
+    for (int c = part; c < chunks16; c += kParts) {
       float r[16];
       tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 16), r);
       const int col = c * 16;
