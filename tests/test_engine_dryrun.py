@@ -55,7 +55,10 @@ def test_forward_plumbing(recorder, monkeypatch):
     # C<=64 ConvNeXt fronts are fused into the pointwise conv (tensor-core path) when T >= 128
     assert cnt["sty_dwconv_ln_fwd"] == 5 + 1
     assert cnt["sty_grn_scale_fwd"] == 16
-    assert cnt["sty_instnorm_affine_fwd"] == 2 * 5 + 2 * 6
+    # decoder AdaINs keep the two-pass statistics kernel; the 12 S-rate AdaINs of the two generator blocks
+    # take their statistics from the producing conv's epilogue (out_sum / out_sumsq -> moments_affine)
+    assert cnt["sty_instnorm_affine_fwd"] == 2 * 5
+    assert cnt["sty_moments_affine_fwd"] == 2 * 6
     for k in ("prenet", "dec_encode", "conformer", "logamp_prior", "upsampled", "real", "imag"):
         assert k in taps
 
