@@ -366,6 +366,21 @@ STY_API int sty_attention_bwd(const float* q, const float* k, const float* v, in
                               float* dv, int64_t dqkv_bs, float* delta, int B, int H, int D, int T, float scale,
                               sty_stream_t stream);
 
+/* ---- attention backward for any head size through materialised probabilities (prosody encoder, 2 x 160) ----
+ * heads_to_rows: x (B,H*D,T) [batch stride x_bs] -> y (B,H,T,D) * mul with RoPE on the first d_rot features;
+ *                inverse != 0: x is (B,H,T,D), y the (B,H*D,T) tensor (batch stride x_bs), TRANSPOSED rotation.
+ * attn_probs:    P[b,h,i,:] = softmax_j(<q_rows[i], k_rows[j]> + mask), mask as in sty_attention_fwd.
+ * softmax_bwd:   dP <- P * (dP - sum_j P dP) row-wise, in place.
+ * bmm_tn:        C[b] (M,N) = A[b] (K,M)^T @ Bm[b] (K,N).
+ * Backward of text_encoder.py:233-272 as used by prosody_encoder.py:63-81 and duration_predictor.py:58-67. */
+STY_API int sty_heads_to_rows(const float* x, int64_t x_bs, float* y, const float* rope_cos, const float* rope_sin,
+                              int d_rot, int B, int H, int D, int T, float mul, int inverse, sty_stream_t stream);
+STY_API int sty_attn_probs(const float* q_rows, const float* k_rows, const int64_t* lengths, float* P, int B, int H,
+                           int D, int T, sty_stream_t stream);
+STY_API int sty_softmax_bwd(const float* P, float* dP, int64_t rows, int T, sty_stream_t stream);
+STY_API int sty_bmm_tn_fwd(const float* A, int64_t a_bs, const float* Bm, int64_t b_bs, float* C, int64_t c_bs,
+                           int B, int M, int N, int K, sty_stream_t stream);
+
 /* ---- Conv1d weight gradient ---------------------------------------------------------------
  * dw[co,ci,k] += sum_{b,t} g[b,co,t] * xin[b,ci,t + k*dil - pad],  g = out_scale*mask_o[b,t]*dy[b,co,t],
  * xin = the forward's prologue applied to x (see sty_conv1d_fwd).  dw is in the REFERENCE layout
@@ -420,6 +435,10 @@ STY_API int sty_prologue_bwd_apply(const float* dxp, const float* x, int64_t x_b
 STY_API int sty_grn_snake_bwd(const float* g_u, const float* h, const float* gs, const float* kc,
                               const float* alpha, float* d_h, float* dalpha, int B, int J, int T,
                               sty_stream_t stream);
+/* same with any activation `act` in place of Snake (alpha / dalpha unused unless act == STY_ACT_SNAKE):
+ * AdaptiveConvNeXtBlock uses GELU (conv_next.py:96-141) */
+STY_API int sty_grn_act_bwd(const float* g_u, const float* h, const float* gs, const float* kc, const float* alpha,
+                            float* d_h, float* dalpha, int B, int J, int T, int act, sty_stream_t stream);
 
 /* ---- backward of sty_chan_layernorm_fwd: dv (= dx = dres), dgb[b*dg_bs + c] += d gamma,
  * dgb[b*dg_bs + C + c] += d beta (dg_bs = 0: shared over the batch; the caller zeroes dgb). */

@@ -111,6 +111,11 @@ _SIGNATURES = {
     "sty_prologue_bwd_apply": [_f32p, _f32p, _i64, _i64, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p,
                                _i64, _i64, _f32p, _i64, _i64, _i32, _i32, _i32, _i32, _f32p],
     "sty_grn_snake_bwd": [_f32p, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, _i32, _i32, _i32, _f32p],
+    "sty_grn_act_bwd": [_f32p, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, _i32, _i32, _i32, _i32, _f32p],
+    "sty_heads_to_rows": [_f32p, _i64, _f32p, _f32p, _f32p, _i32, _i32, _i32, _i32, _i32, _f32, _i32, _f32p],
+    "sty_attn_probs": [_f32p, _f32p, _f32p, _f32p, _i32, _i32, _i32, _i32, _f32p],
+    "sty_softmax_bwd": [_f32p, _f32p, _i64, _i32, _f32p],
+    "sty_bmm_tn_fwd": [_f32p, _i64, _f32p, _i64, _f32p, _i64, _i32, _i32, _i32, _i32, _f32p],
     "sty_chan_layernorm_bwd": [_f32p, _f32p, _i64, _f32p, _f32p, _i64, _i32, _f32p, _f32p, _f32p, _f32p,
                                _i64, _i32, _i32, _i32, _f32, _i32, _f32p],
     "sty_dwconv1d_bwd": [_f32p, _f32p, _i64, _i64, _f32p, _f32p, _i64, _i64, _f32p, _f32p, _i32, _i32, _i32,

@@ -273,3 +273,216 @@ extern "C" int sty_attention_bwd(const float* q, const float* k, const float* v,
   STY_CHECK_LAUNCH("attention_bwd");
   return STY_OK;
 }
+
+// =====================================================================================================
+// Generic head size (prosody encoder: 2 heads x 160): backward through MATERIALISED probabilities —
+// T is a few hundred tokens, so P (B,H,T,T) is a few MB.  Pieces: heads <-> token-major rows (with RoPE
+// and its transpose), row softmax of the scores, softmax backward, and the batched products
+// (sty_bmm_fwd / sty_bmm_nt_fwd / sty_bmm_tn_fwd).
+// =====================================================================================================
+namespace sty {
+namespace {
+
+// x (B, H*D, T) [batch stride x_bs] -> y (B, H, T, D) * mul, RoPE on the first d_rot features (rope != null)
+__global__ void __launch_bounds__(256)
+heads_to_rows_kernel(const float* __restrict__ x, int64_t x_bs, float* __restrict__ y, const float* __restrict__ rc,
+                     const float* __restrict__ rs, int half, int H, int D, int T, float mul) {
+  __shared__ float tile[32][33];
+  const int bh = blockIdx.z, b = bh / H, h = bh - b * H;
+  const int t0 = blockIdx.x * 32, d0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const float* __restrict__ xb = x + (int64_t)b * x_bs + (int64_t)h * D * T;
+  for (int r = ty; r < 32; r += 8) {
+    const int d = d0 + r, t = t0 + tx;
+    float v = 0.f;
+    if (d < D && t < T) {
+      v = xb[(int64_t)d * T + t];
+      if (rc && d < 2 * half) {  // rotate-half convention on the first d_rot = 2*half features
+        const int i = d < half ? d : d - half;
+        const float c = rc[(int64_t)t * half + i], s = rs[(int64_t)t * half + i];
+        const float other = xb[(int64_t)(d < half ? d + half : d - half) * T + t];
+        v = d < half ? v * c - other * s : v * c + other * s;
+      }
+    }
+    tile[r][tx] = v * mul;
+  }
+  __syncthreads();
+  float* __restrict__ yb = y + (int64_t)bh * T * D;
+  for (int r = ty; r < 32; r += 8) {
+    const int t = t0 + r, d = d0 + tx;
+    if (t < T && d < D) yb[(int64_t)t * D + d] = tile[tx][r];
+  }
+}
+
+// y (B,H,T,D) -> x (B, H*D, T) [batch stride x_bs] * mul, with the TRANSPOSE of the RoPE rotation
+__global__ void __launch_bounds__(256)
+rows_to_heads_kernel(const float* __restrict__ y, float* __restrict__ x, int64_t x_bs, const float* __restrict__ rc,
+                     const float* __restrict__ rs, int half, int H, int D, int T, float mul) {
+  __shared__ float tile[32][33];
+  const int bh = blockIdx.z, b = bh / H, h = bh - b * H;
+  const int t0 = blockIdx.x * 32, d0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const float* __restrict__ yb = y + (int64_t)bh * T * D;
+  for (int r = ty; r < 32; r += 8) {
+    const int t = t0 + r, d = d0 + tx;
+    float v = 0.f;
+    if (t < T && d < D) {
+      v = yb[(int64_t)t * D + d];
+      if (rc && d < 2 * half) {
+        const int i = d < half ? d : d - half;
+        const float c = rc[(int64_t)t * half + i], s = rs[(int64_t)t * half + i];
+        const float other = yb[(int64_t)t * D + (d < half ? d + half : d - half)];
+        v = d < half ? v * c + other * s : v * c - other * s;
+      }
+    }
+    tile[r][tx] = v * mul;
+  }
+  __syncthreads();
+  float* __restrict__ xb = x + (int64_t)b * x_bs + (int64_t)h * D * T;
+  for (int r = ty; r < 32; r += 8) {
+    const int d = d0 + r, t = t0 + tx;
+    if (d < D && t < T) xb[(int64_t)d * T + t] = tile[tx][r];
+  }
+}
+
+// P[bh,i,:] = softmax_j( <q_r[i], k_r[j]> + mask(i,j) ), q_r already scaled; one CTA per (bh, i)
+__global__ void __launch_bounds__(128)
+attn_probs_kernel(const float* __restrict__ qr, const float* __restrict__ kr, const int64_t* __restrict__ lengths,
+                  float* __restrict__ P, int H, int D, int T) {
+  extern __shared__ float sm[];  // q row [D] + scores [T]
+  __shared__ float red[32];
+  float* qs = sm;
+  float* sc = sm + D;
+  const int bh = blockIdx.y, i = blockIdx.x, b = bh / H;
+  const int len = lengths ? (int)lengths[b] : T;
+  const float* __restrict__ qrow = qr + ((int64_t)bh * T + i) * D;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) qs[d] = qrow[d];
+  __syncthreads();
+  float mx = -INFINITY;
+  for (int j = threadIdx.x; j < T; j += blockDim.x) {
+    const float* __restrict__ krow = kr + ((int64_t)bh * T + j) * D;
+    float a = 0.f;
+    for (int d = 0; d < D; ++d) a = fmaf(qs[d], krow[d], a);
+    if (lengths && !(i < len && j < len)) a += -1e4f;
+    sc[j] = a;
+    mx = fmaxf(mx, a);
+  }
+  // block max / sum
+  mx = warp_max(mx);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  mx = red[0];
+  for (int w = 1; w < (int)(blockDim.x >> 5); ++w) mx = fmaxf(mx, red[w]);
+  float s = 0.f;
+  for (int j = threadIdx.x; j < T; j += blockDim.x) {
+    const float e = expf(sc[j] - mx);
+    sc[j] = e;
+    s += e;
+  }
+  s = block_sum(s, red);
+  const float inv = 1.f / s;
+  float* __restrict__ prow = P + ((int64_t)bh * T + i) * T;
+  for (int j = threadIdx.x; j < T; j += blockDim.x) prow[j] = sc[j] * inv;
+}
+
+// dS = P * (dP - sum_j P dP), in place on dP; one CTA per row
+__global__ void __launch_bounds__(128)
+softmax_bwd_kernel(const float* __restrict__ P, float* __restrict__ dP, int T) {
+  __shared__ float red[32];
+  const int64_t row = blockIdx.x;
+  const float* __restrict__ p = P + row * T;
+  float* __restrict__ g = dP + row * T;
+  float s = 0.f;
+  for (int j = threadIdx.x; j < T; j += blockDim.x) s = fmaf(p[j], g[j], s);
+  s = block_sum(s, red);
+  for (int j = threadIdx.x; j < T; j += blockDim.x) g[j] = p[j] * (g[j] - s);
+}
+
+// C[b] (M,N) = A[b] (K,M)^T @ Bm[b] (K,N)
+__global__ void __launch_bounds__(256)
+bmm_tn_kernel(const float* __restrict__ A, int64_t a_bs, const float* __restrict__ Bm, int64_t b_bs,
+              float* __restrict__ Cm, int64_t c_bs, int M, int N, int K) {
+  constexpr int BM = 64, BN = 64, BK = 16;
+  __shared__ float As[BK][BM + 4];
+  __shared__ float Bs[BK][BN + 4];
+  const int b = blockIdx.z;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int tid = threadIdx.x, tn = tid & 15, tm = tid >> 4;
+  const float* __restrict__ Ab = A + (int64_t)b * a_bs;
+  const float* __restrict__ Bb = Bm + (int64_t)b * b_bs;
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < K; k0 += BK) {
+    for (int idx = tid; idx < BK * BM; idx += 256) {
+      const int mm = idx % BM, kk = idx / BM;
+      const int k = k0 + kk;
+      As[kk][mm] = (m0 + mm < M && k < K) ? Ab[(int64_t)k * M + m0 + mm] : 0.f;
+      Bs[kk][mm] = (n0 + mm < N && k < K) ? Bb[(int64_t)k * N + n0 + mm] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      float a[4], bb[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[kk][tm + 16 * i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bb[j] = Bs[kk][tn + 16 * j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  float* __restrict__ Cb = Cm + (int64_t)b * c_bs;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + tm + 16 * i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tn + 16 * j;
+      if (n < N) Cb[(int64_t)m * N + n] = acc[i][j];
+    }
+  }
+}
+
+}  // namespace
+}  // namespace sty
+
+extern "C" int sty_heads_to_rows(const float* x, int64_t x_bs, float* y, const float* rope_cos, const float* rope_sin,
+                                 int d_rot, int B, int H, int D, int T, float mul, int inverse, sty_stream_t stream) {
+  STY_REQUIRE(x && y && B > 0 && H > 0 && D > 0 && T > 0, "heads_to_rows: bad argument");
+  STY_REQUIRE((rope_cos == nullptr) == (rope_sin == nullptr) && d_rot % 2 == 0 && d_rot <= D, "heads_to_rows: bad rope");
+  dim3 grid(cdiv(T, 32), cdiv(D, 32), B * H);
+  if (!inverse)
+    heads_to_rows_kernel<<<grid, 256, 0, as_stream(stream)>>>(x, x_bs, y, rope_cos, rope_sin, d_rot / 2, H, D, T, mul);
+  else  // x is the (B,H,T,D) input, y the (B,H*D,T) output with batch stride x_bs
+    rows_to_heads_kernel<<<grid, 256, 0, as_stream(stream)>>>(x, y, x_bs, rope_cos, rope_sin, d_rot / 2, H, D, T, mul);
+  STY_CHECK_LAUNCH("heads_to_rows");
+  return STY_OK;
+}
+
+extern "C" int sty_attn_probs(const float* q_rows, const float* k_rows, const int64_t* lengths, float* P, int B, int H,
+                              int D, int T, sty_stream_t stream) {
+  STY_REQUIRE(q_rows && k_rows && P && B > 0 && H > 0 && D > 0 && T > 0 && B * H <= 65535, "attn_probs: bad argument");
+  dim3 grid(T, B * H);
+  attn_probs_kernel<<<grid, 128, (size_t)(D + T) * sizeof(float), as_stream(stream)>>>(q_rows, k_rows, lengths, P, H, D, T);
+  STY_CHECK_LAUNCH("attn_probs");
+  return STY_OK;
+}
+
+extern "C" int sty_softmax_bwd(const float* P, float* dP, int64_t rows, int T, sty_stream_t stream) {
+  STY_REQUIRE(P && dP && rows > 0 && T > 0, "softmax_bwd: bad argument");
+  softmax_bwd_kernel<<<(unsigned)rows, 128, 0, as_stream(stream)>>>(P, dP, T);
+  STY_CHECK_LAUNCH("softmax_bwd");
+  return STY_OK;
+}
+
+extern "C" int sty_bmm_tn_fwd(const float* A, int64_t a_bs, const float* Bm, int64_t b_bs, float* C, int64_t c_bs,
+                              int B, int M, int N, int K, sty_stream_t stream) {
+  STY_REQUIRE(A && Bm && C && B > 0 && M > 0 && N > 0 && K > 0, "bmm_tn: bad argument");
+  dim3 grid(cdiv(N, 64), cdiv(M, 64), B);
+  bmm_tn_kernel<<<grid, 256, 0, as_stream(stream)>>>(A, a_bs, Bm, b_bs, C, c_bs, M, N, K);
+  STY_CHECK_LAUNCH("bmm_tn");
+  return STY_OK;
+}

@@ -726,6 +726,32 @@ extern "C" int sty_grn_snake_bwd(const float* g_u, const float* h, const float* 
   return STY_OK;
 }
 
+namespace sty {
+namespace {
+// generic-activation variant of grn_snake_bwd_kernel: hb = act(h)
+__global__ void __launch_bounds__(512)
+grn_act_bwd_kernel(const float* g_u, const float* __restrict__ h, const float* __restrict__ gs,
+                   const float* __restrict__ kc, float* d_h, int T, int act) {
+  const int64_t off = (int64_t)blockIdx.x * T;
+  const float s = gs[blockIdx.x], k = kc[blockIdx.x];
+  for (int t = threadIdx.x; t < T; t += blockDim.x) {
+    const float hv = h[off + t];
+    const float hb = act_apply(hv, act);
+    d_h[off + t] = fmaf(g_u[off + t], s, k * hb) * act_grad(hv, act, 1.f);
+  }
+}
+}  // namespace
+}  // namespace sty
+
+extern "C" int sty_grn_act_bwd(const float* g_u, const float* h, const float* gs, const float* kc, const float* alpha,
+                               float* d_h, float* dalpha, int B, int J, int T, int act, sty_stream_t stream) {
+  if (act == STY_ACT_SNAKE) return sty_grn_snake_bwd(g_u, h, gs, kc, alpha, d_h, dalpha, B, J, T, stream);
+  STY_REQUIRE(g_u && h && gs && kc && d_h && B > 0 && J > 0 && T > 0, "grn_act_bwd: bad argument");
+  grn_act_bwd_kernel<<<B * J, 512, 0, as_stream(stream)>>>(g_u, h, gs, kc, d_h, T, act);
+  STY_CHECK_LAUNCH("grn_act_bwd");
+  return STY_OK;
+}
+
 extern "C" int sty_chan_layernorm_bwd(const float* x, const float* res, int64_t x_bs, const float* gamma,
                                       const float* beta, int64_t g_bs, int g_plus_one, const float* dy,
                                       const float* mask, float* dv, float* dgb, int64_t dg_bs, int B, int C, int T,

@@ -340,8 +340,9 @@ def adaptive_convnext_tree(dim, style_dim) -> Node:
 
 
 class _EngineModule(nn.Module):
-    """Shared plumbing of the shells: lazily built engine, no autograd path yet."""
+    """Shared plumbing of the shells: lazily built inference engine (no_grad) and differentiable graph."""
     engine_cls_name = ""
+    graph_cls_name = ""
 
     def engine(self):
         from . import engine as E
@@ -350,17 +351,23 @@ class _EngineModule(nn.Module):
             self._engine = getattr(E, self.engine_cls_name)(self)
         return self._engine
 
-    def _no_grad_only(self):
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise NotImplementedError(
-                f"stylish_tts_b200: the backward kernels of {type(self).__name__} are not built yet; "
-                "call under torch.no_grad() (forward/inference path)")
+    def train_graph(self):
+        from . import train_engine as TE
+
+        if getattr(self, "_train_graph", None) is None:
+            self._train_graph = getattr(TE, self.graph_cls_name)(self)
+        return self._train_graph
+
+    def _wants_grad(self, *inputs):
+        return torch.is_grad_enabled() and (any(p.requires_grad for p in self.parameters()) or
+                                            any(torch.is_tensor(t) and t.requires_grad for t in inputs))
 
 
 class DurationPredictor(_EngineModule):
     """Drop-in for reference DurationPredictor (duration_predictor.py:15-87):
     forward(texts, text_lengths, style) -> (B, T, duration_classes)."""
     engine_cls_name = "DurationEngine"
+    graph_cls_name = "DurationTrainGraph"
 
     def __init__(self, model_config):
         super().__init__()
@@ -386,7 +393,8 @@ class DurationPredictor(_EngineModule):
         self._engine = None
 
     def forward(self, texts, text_lengths, style, *, taps=None):
-        self._no_grad_only()
+        if self._wants_grad(style):
+            return self.train_graph().forward(texts, text_lengths, style)
         return self.engine().forward(texts, text_lengths, style, taps=taps)
 
 
@@ -394,6 +402,7 @@ class PitchEnergyPredictor(_EngineModule):
     """Drop-in for reference PitchEnergyPredictor (pitch_energy_predictor.py:8-82):
     forward(texts, text_lengths, alignment, style) -> (pitch (B,F), energy (B,F))."""
     engine_cls_name = "PitchEnergyEngine"
+    graph_cls_name = "PitchEnergyTrainGraph"
 
     def __init__(self, model_config):
         super().__init__()
@@ -425,7 +434,8 @@ class PitchEnergyPredictor(_EngineModule):
         self._engine = None
 
     def forward(self, texts, text_lengths, alignment, style, *, taps=None):
-        self._no_grad_only()
+        if self._wants_grad(style):
+            return self.train_graph().forward(texts, text_lengths, alignment, style)
         return self.engine().forward(texts, text_lengths, alignment, style, taps=taps)
 
 

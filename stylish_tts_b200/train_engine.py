@@ -30,9 +30,9 @@ INV_SQRT2 = 1.0 / math.sqrt(2.0)
 class TrainGraph:
     """One differentiable forward over the live parameters of a ``SpeechPredictor`` shell."""
 
-    def __init__(self, module, engine):
+    def __init__(self, module, engine=None):
         self.m = module
-        self.engine = engine  # the inference engine: harmonic prior + rope tables are shared
+        self.engine = engine  # the inference engine (speech predictor: harmonic prior kernels)
         self.P: Dict[str, torch.Tensor] = dict(module.named_parameters())
         self.Bf: Dict[str, torch.Tensor] = dict(module.named_buffers())
         self.mc = module.model_config
@@ -117,7 +117,12 @@ class TrainGraph:
                         out_mask=mask)
             x = T.chan_ln(y2, res=x1, gamma=P[f"{e}.norm_layers_2.{i}.gamma"],
                           beta=P[f"{e}.norm_layers_2.{i}.beta"], eps=1e-4, mask=mask)
-        return T.conv(x, self.w(t + ".proj_m"), self.b(t + ".proj_m"), out_mask=mask)
+        return T.conv(x, self.w(t + ".proj_m"), self.b(t + ".proj_m"), out_mask=mask), mask
+
+    def style_fc(self, style):
+        fc_w = torch.cat([self.P[n + ".fc.weight"] for n in self.fc_names], 0)
+        fc_b = torch.cat([self.P[n + ".fc.bias"] for n in self.fc_names], 0)
+        return T.LinearRowsFn.apply(style, fc_w, fc_b)
 
     def decoder_block(self, p, x, h):
         """AdaptiveDecoderBlock (ada_norm.py:143-192); fp32 FMA convs (F0 channel in Hz)"""
@@ -246,10 +251,101 @@ class TrainGraph:
         lengths = text_lengths.to(device=dev, dtype=torch.int64).contiguous()
         alignment, pitch, energy = f32(alignment), f32(pitch), f32(energy)
         voiced, style, denormal_pitch = f32(voiced), f32(style), f32(denormal_pitch)
-        fc_w = torch.cat([self.P[n + ".fc.weight"] for n in self.fc_names], 0)
-        fc_b = torch.cat([self.P[n + ".fc.bias"] for n in self.fc_names], 0)
-        h = T.LinearRowsFn.apply(style, fc_w, fc_b)
-        mu = self.text_encoder(texts, lengths)
+        h = self.style_fc(style)
+        mu, _ = self.text_encoder(texts, lengths)
         mel = self.decoder(mu, alignment, pitch, energy, voiced, h)
         noise = None if source_draws is None else f32(source_draws["noise"])
         return self.generator(mel, h, denormal_pitch, voiced, noise, prior)
+
+
+def _prep(dev, texts, text_lengths, *floats):
+    if dev.type != "cuda":
+        raise RuntimeError("stylish_tts_b200: inputs must live on a CUDA device; there is no CPU fallback")
+    f32 = lambda t: t.to(device=dev, dtype=torch.float32).contiguous()
+    return (texts.to(torch.int64).contiguous(), text_lengths.to(device=dev, dtype=torch.int64).contiguous(),
+            *[f32(t) for t in floats])
+
+
+class DurationTrainGraph(TrainGraph):
+    """Differentiable DurationPredictor.forward (duration_predictor.py:58-87; DropPath / dropout off)."""
+
+    def forward(self, texts, text_lengths, style):
+        P = self.P
+        texts, lengths, style = _prep(texts.device, texts, text_lengths, style)
+        h = self.style_fc(style)
+        enc, mask = self.text_encoder(texts, lengths)
+        B, Cc, Tn = enc.shape
+        qn = T.chan_ln(enc, gb=self.gb(h, "query_norm", Cc), eps=1e-5)
+        kn = T.chan_ln(enc, gb=self.gb(h, "key_norm", Cc), eps=1e-5)
+        a = "cross_attention"
+        q = T.conv(qn, self.w(a + ".conv_q"), self.b(a + ".conv_q"))
+        wkv = torch.cat([P[a + ".conv_k.weight"], P[a + ".conv_v.weight"]], 0)
+        bkv = torch.cat([P[a + ".conv_k.bias"], P[a + ".conv_v.bias"]], 0)
+        kv = T.conv(kn, wkv, bkv)
+        H = 8
+        D = Cc // H
+        att = T.AttentionFn.apply(torch.cat([q, kv], 1), H, D, lengths, self.rope(Tn, D, enc.device),
+                                  1.0 / math.sqrt(D))
+        att = T.conv(att, self.w(a + ".conv_o"), self.b(a + ".conv_o"))
+        dw = T.DwConvFn.apply(att, self.w("cross_post.0"), self.b("cross_post.0"), 5, 2)
+        pros = T.conv(dw, self.w("cross_post.2"), self.b("cross_post.2"), in_act=ACT_SWISH, res=enc,
+                      out_scale=INV_SQRT2, res_scale=INV_SQRT2)
+        m3 = mask.unsqueeze(1)
+        for i in range(self.mc.duration_predictor.n_layer):  # AdaptiveConvNeXtBlock, then * mask
+            p = f"conv_next.{i}"
+            d = T.DwConvFn.apply(pros, P[p + ".dwconv.weight"], P[p + ".dwconv.bias"], 7, 3)
+            y = T.chan_ln(d, gb=self.gb(h, p + ".norm", Cc), eps=1e-6)
+            w2 = P[p + ".pwconv2.weight"]
+            b2f = P[p + ".pwconv2.bias"] + w2 @ P[p + ".grn.beta"].reshape(-1)
+            pros = T.ConvNeXtTailFn.apply(y, pros * m3, P[p + ".pwconv1.weight"], P[p + ".pwconv1.bias"], None,
+                                          P[p + ".grn.gamma"].reshape(-1), w2, b2f, True, L.ACT_GELU, mask)
+        logits = T.conv(pros, P["duration_proj.linear_layer.weight"].unsqueeze(-1),
+                        P["duration_proj.linear_layer.bias"])  # (B,NC,T)
+        # monotone head on the (B,NC,T) class scores (16 x T values per utterance): duration_predictor.py:82-86
+        d = torch.cat([logits[:, :1], logits[:, 1:].abs()], 1)
+        d = -torch.cumsum(d, 1).abs()
+        return d.transpose(1, 2) * mask.unsqueeze(2)
+
+
+class PitchEnergyTrainGraph(TrainGraph):
+    """Differentiable PitchEnergyPredictor.forward (pitch_energy_predictor.py:62-82, prosody_encoder.py:63-81)."""
+
+    def forward(self, texts, text_lengths, alignment, style):
+        P = self.P
+        texts, lengths, alignment, style = _prep(texts.device, texts, text_lengths, alignment, style)
+        h = self.style_fc(style)
+        enc, mask = self.text_encoder(texts, lengths)
+        B, dm, Tn = enc.shape
+        sdim = style.shape[1]
+        Ch = dm + sdim
+        st = style.unsqueeze(2).expand(B, sdim, Tn)
+        m3 = mask.unsqueeze(1)
+        H = 2
+        D = Ch // H
+        rope = self.rope(Tn, D, enc.device)
+        pe = "prosody_encoder"
+        x = torch.cat([enc, st], 1)
+        for i in range(3):
+            a = f"{pe}.attn_layers.{i}"
+            wqkv = torch.cat([P[a + ".conv_q.weight"], P[a + ".conv_k.weight"], P[a + ".conv_v.weight"]], 0)
+            bqkv = torch.cat([P[a + ".conv_q.bias"], P[a + ".conv_k.bias"], P[a + ".conv_v.bias"]], 0)
+            qkv = T.conv(x, wqkv, bqkv, in_mask=mask)
+            att = T.AttentionGenericFn.apply(qkv[:, :Ch], qkv[:, Ch:2 * Ch], qkv[:, 2 * Ch:], H, D, lengths, rope,
+                                             1.0 / math.sqrt(D))
+            y = T.conv(att, self.w(a + ".conv_o"), self.b(a + ".conv_o"))
+            x1 = T.chan_ln(y, res=x * m3, gb=self.gb(h, f"{pe}.norm_layers_1.{i}", Ch), eps=1e-5)
+            f = f"{pe}.ffn_layers.{i}"
+            hh = T.conv(x1, self.w(f + ".conv_1"), self.b(f + ".conv_1"), in_mask=mask)
+            y2 = T.conv(hh, self.w(f + ".conv_2"), self.b(f + ".conv_2"), in_act=ACT_RELU, in_mask=mask, out_mask=mask)
+            x2 = T.chan_ln(y2, res=x1, gb=self.gb(h, f"{pe}.norm_layers_2.{i}", Ch), eps=1e-5)
+            xp = T.conv(x2, self.w(f"{pe}.proj_layers.{i}"), self.b(f"{pe}.proj_layers.{i}"))
+            x = torch.cat([xp, st], 1)
+        pros = x * m3
+        xa = T.BmmAlignFn.apply(pros, alignment)
+        outs = []
+        for tower, proj in (("F0", "F0_proj"), ("N", "N_proj")):
+            z = xa
+            for i in range(4):
+                z = self.decoder_block(f"{tower}.{i}", z, h)
+            outs.append(T.conv(z, self.w(proj), self.b(proj), umma=False).squeeze(1))
+        return outs[0], outs[1]

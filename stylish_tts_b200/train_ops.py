@@ -15,7 +15,7 @@ import torch
 from torch.autograd import Function
 
 from . import _lib as L
-from ._lib import ACT_NONE, ACT_SNAKE, WgradArgs
+from ._lib import ACT_NONE, ACT_SNAKE, WgradArgs  # noqa: F401
 from .engine import ConvW, conv1d, chan_layernorm, dwconv1d
 
 F32 = torch.float32
@@ -214,31 +214,34 @@ class ConvNeXtTailFn(Function):
     tensor-core pointwise conv."""
 
     @staticmethod
-    def forward(ctx, y, xres, w1, b1, alpha, gamma, w2, b2f, umma):
+    def forward(ctx, y, xres, w1, b1, alpha, gamma, w2, b2f, umma, act=ACT_SNAKE, out_mask=None):
+        """act = ACT_SNAKE (generator blocks, alpha per channel) or e.g. ACT_GELU (AdaptiveConvNeXtBlock,
+        conv_next.py:96-141; alpha is then ignored); out_mask (B,T) masks the block output before the residual."""
         B, Cc, T = y.shape
         J = w1.shape[0]
         cw1 = ConvW(w1.detach().unsqueeze(-1), b1.detach())
         cw2 = ConvW(w2.detach().unsqueeze(-1), b2f.detach())
-        al, gm = alpha.detach().contiguous(), gamma.detach().contiguous()
+        al = alpha.detach().contiguous() if act == ACT_SNAKE else torch.ones(J, device=y.device)
+        gm = gamma.detach().contiguous()
         sumsq = _zeros((B, J), y)
-        hb = conv1d(y, cw1, out_act=ACT_SNAKE, out_alpha=al, out_sumsq=sumsq, umma=umma)
+        hb = conv1d(y, cw1, out_act=act, out_alpha=al if act == ACT_SNAKE else None, out_sumsq=sumsq, umma=umma)
         gs = _new((B, J), y)
         L.call("sty_grn_scale_fwd", sumsq.data_ptr(), gm.data_ptr(), gs.data_ptr(), B, J, L.stream_ptr())
-        out = conv1d(hb, cw2, in_scale=gs, res=xres, umma=umma)
-        ctx.save_for_backward(y, hb, sumsq, gs, w1, b1, al, gm, w2)
-        ctx.umma = umma
+        out = conv1d(hb, cw2, in_scale=gs, res=xres, out_mask=out_mask, umma=umma)
+        ctx.save_for_backward(y, hb, sumsq, gs, w1, b1, al, gm, w2, out_mask)
+        ctx.umma, ctx.act = umma, act
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        y, hb, sumsq, gs, w1, b1, al, gm, w2 = ctx.saved_tensors
-        umma = ctx.umma
+        y, hb, sumsq, gs, w1, b1, al, gm, w2, out_mask = ctx.saved_tensors
+        umma, act = ctx.umma, ctx.act
         B, Cc, T = y.shape
         J = w1.shape[0]
         dout = dout.contiguous()
-        d_b2f = channel_sum(dout)
-        d_w2 = wgrad(hb, dout, 1, 1, in_scale=gs, umma=umma)[:, :, 0]
-        g_u = conv1d(dout, transposed_weight(w2.unsqueeze(-1)), umma=umma)  # (B,J,T)
+        d_b2f = channel_sum(dout, out_mask)
+        d_w2 = wgrad(hb, dout, 1, 1, in_scale=gs, out_mask=out_mask, umma=umma)[:, :, 0]
+        g_u = conv1d(dout, transposed_weight(w2.unsqueeze(-1)), in_mask=out_mask, umma=umma)  # (B,J,T)
         r = _new((B, J), y)
         L.call("sty_row_dot", g_u.data_ptr(), hb.data_ptr(), r.data_ptr(), B * J, T, L.stream_ptr())
         gx = torch.sqrt(sumsq)
@@ -250,14 +253,15 @@ class ConvNeXtTailFn(Function):
         kc = torch.where(gx > 0, d_gx / gx.clamp_min(1e-30), torch.zeros_like(gx)).contiguous()
         h = conv1d(y, ConvW(w1.unsqueeze(-1), b1), umma=umma)  # pre-activation, recomputed
         d_alpha = _zeros((J,), y)
-        L.call("sty_grn_snake_bwd", g_u.data_ptr(), h.data_ptr(), gs.data_ptr(), kc.data_ptr(), al.data_ptr(),
-               g_u.data_ptr(), d_alpha.data_ptr(), B, J, T, L.stream_ptr())
+        L.call("sty_grn_act_bwd", g_u.data_ptr(), h.data_ptr(), gs.data_ptr(), kc.data_ptr(), al.data_ptr(),
+               g_u.data_ptr(), d_alpha.data_ptr(), B, J, T, act, L.stream_ptr())
         d_h = g_u
         del h
         d_b1 = channel_sum(d_h)
         d_w1 = wgrad(y, d_h, 1, 1, umma=umma)[:, :, 0]
         d_y = conv1d(d_h, transposed_weight(w1.unsqueeze(-1)), umma=umma)
-        return d_y, dout, d_w1, d_b1, d_alpha, d_gamma, d_w2, d_b2f, None
+        return (d_y, dout, d_w1, d_b1, d_alpha if act == ACT_SNAKE else None, d_gamma, d_w2, d_b2f, None, None,
+                None)
 
 
 class ChanLNFn(Function):
@@ -491,3 +495,52 @@ class IstftHeadFn(Function):
                d_la.data_ptr(), d_ri.data_ptr(), d_ri.data_ptr() + 4 * Hs * S, d_ri.stride(0), B, S, Hs, 64,
                ctx.hop, L.stream_ptr())
         return d_la, d_ri, None, None, None
+
+
+class AttentionGenericFn(Function):
+    """attention core for any head size on separate q / k / v views (prosody encoder 2 x 160 with RoPE 80,
+    prosody_encoder.py:63-81; text_encoder.py:233-272).  The backward materialises the probabilities
+    (B,H,T,T) — T is the token count — and uses the batched-product kernels."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, H, D, lengths, rope, scale):
+        from .engine import attention_generic
+        q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
+        out = attention_generic(q, k, v, H=H, D=D, lengths=lengths, rope=rope, scale=scale)
+        ctx.save_for_backward(q, k, v)
+        ctx.meta = (H, D, lengths, rope, scale)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        q, k, v = ctx.saved_tensors
+        H, D, lengths, rope, scale = ctx.meta
+        B, _, T = q.shape
+        d_out = d_out.contiguous()
+        rc, rs, d_rot = (None, None, 0) if rope is None else (rope[0].data_ptr(), rope[1].data_ptr(), rope[2])
+        st = L.stream_ptr()
+
+        def rows(x, use_rope, mul):
+            y = _new((B, H, T, D), x)
+            L.call("sty_heads_to_rows", x.data_ptr(), x.stride(0), y.data_ptr(), rc if use_rope else None,
+                   rs if use_rope else None, d_rot if use_rope else 0, B, H, D, T, mul, 0, st)
+            return y
+
+        def heads(y, use_rope, mul):
+            x = _new((B, H * D, T), y)
+            L.call("sty_heads_to_rows", y.data_ptr(), x.stride(0), x.data_ptr(), rc if use_rope else None,
+                   rs if use_rope else None, d_rot if use_rope else 0, B, H, D, T, mul, 1, st)
+            return x
+
+        q_r, k_r, v_t, do_t = rows(q, True, scale), rows(k, True, 1.0), rows(v, False, 1.0), rows(d_out, False, 1.0)
+        P = _new((B, H, T, T), q)
+        L.call("sty_attn_probs", q_r.data_ptr(), k_r.data_ptr(), L.ptr(lengths), P.data_ptr(), B, H, D, T, st)
+        BH, TT, TD = B * H, T * T, T * D
+        dv_t, dq_r, dk_r = _new((B, H, T, D), q), _new((B, H, T, D), q), _new((B, H, T, D), q)
+        dP = _new((B, H, T, T), q)
+        L.call("sty_bmm_tn_fwd", P.data_ptr(), TT, do_t.data_ptr(), TD, dv_t.data_ptr(), TD, BH, T, D, T, st)
+        L.call("sty_bmm_nt_fwd", do_t.data_ptr(), TD, v_t.data_ptr(), TD, dP.data_ptr(), TT, BH, T, T, D, st)
+        L.call("sty_softmax_bwd", P.data_ptr(), dP.data_ptr(), BH * T, T, st)
+        L.call("sty_bmm_fwd", dP.data_ptr(), TT, k_r.data_ptr(), TD, dq_r.data_ptr(), TD, BH, T, D, T, st)
+        L.call("sty_bmm_tn_fwd", dP.data_ptr(), TT, q_r.data_ptr(), TD, dk_r.data_ptr(), TD, BH, T, D, T, st)
+        return heads(dq_r, True, scale), heads(dk_r, True, 1.0), heads(dv_t, False, 1.0), None, None, None, None, None

@@ -1,0 +1,94 @@
+"""Backward of the duration and pitch-energy predictors (the duration and textual
+training stages, stage_type.py:415-448,507-522).
+
+CPU: the oracle's autograd against golden gradients of the UNMODIFIED reference.
+GPU: the differentiable CUDA graphs against the fp64 oracle (every parameter) and the golden."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import speech_oracle as so
+from tests import util
+from tests.golden.make_predictor_grad_golden import build, cot, probe
+from tests.util import rel_l2
+
+
+def gold():
+    z = np.load(util.GOLDEN_DIR + "/predictor_grads.npz")
+    return {k: z[k] for k in z.files}
+
+
+def sd_grad(m, dtype):
+    return {k: (v.detach().clone().to(dtype).requires_grad_(True) if v.is_floating_point() else v.clone())
+            for k, v in m.state_dict().items()}
+
+
+def oracle_run(nets, inp, sty, dtype):
+    f = lambda t: t.to(dtype)
+    sd_d, sd_p = sd_grad(nets.duration_predictor, dtype), sd_grad(nets.pitch_energy_predictor, dtype)
+    s1 = f(sty).clone().requires_grad_(True)
+    out = so.duration_predictor(sd_d, inp["texts"], inp["text_lengths"], s1)
+    (out * f(cot(out.shape, 41))).sum().backward()
+    s2 = f(sty).clone().requires_grad_(True)
+    pitch, energy = so.pitch_energy_predictor(sd_p, inp["texts"], inp["text_lengths"], f(inp["alignment"]), s2)
+    ((pitch * f(cot(pitch.shape, 42))).sum() + (energy * f(cot(energy.shape, 43))).sum()).backward()
+    return dict(dur=(out.detach(), s1.grad, sd_d), pe=((pitch.detach(), energy.detach()), s2.grad, sd_p))
+
+
+def check_golden(tag, grads_of, g, tol):
+    scale = float(np.sqrt((g[tag + "_norms"] ** 2).sum()))
+    for n, norm, dot in zip([str(s) for s in g[tag + "_names"]], g[tag + "_norms"], g[tag + "_dots"]):
+        gr = grads_of(n)
+        assert gr is not None, n
+        gr = gr.detach().cpu().float()
+        assert abs(float(gr.norm()) - norm) <= tol * norm + 1e-6 * scale, (tag, n, float(gr.norm()), norm)
+        assert abs(float((gr * probe(n, gr.shape)).sum()) - dot) <= 2 * tol * norm + 1e-6 * scale, (tag, n)
+
+
+def test_oracle_gradients_match_reference_golden():
+    g = gold()
+    nets, inp, sty = build()
+    r = oracle_run(nets, inp, sty, torch.float32)
+    assert rel_l2(r["dur"][0], torch.from_numpy(g["dur_out"])) < 1e-5
+    assert rel_l2(r["pe"][0][0], torch.from_numpy(g["pe_pitch"])) < 2e-4
+    assert rel_l2(r["dur"][1], torch.from_numpy(g["dur_dstyle"])) < 1e-3
+    assert rel_l2(r["pe"][1], torch.from_numpy(g["pe_dstyle"])) < 5e-3
+    check_golden("dur", lambda n: r["dur"][2][n].grad, g, 2e-3)
+    check_golden("pe", lambda n: r["pe"][2][n].grad, g, 1e-2)
+
+
+@pytest.mark.gpu
+def test_gpu_predictor_gradients():
+    g = gold()
+    nets, inp, sty = build()
+    ref = oracle_run(nets, inp, sty, torch.float64)
+    dev = torch.device("cuda:0")
+    c = lambda t: t.to(dev)
+    dp, pe = nets.duration_predictor.to(dev).train(), nets.pitch_energy_predictor.to(dev).train()
+    s1 = c(sty).clone().requires_grad_(True)
+    out = dp(c(inp["texts"]), c(inp["text_lengths"]), s1)
+    (out * c(cot(out.shape, 41))).sum().backward()
+    s2 = c(sty).clone().requires_grad_(True)
+    pitch, energy = pe(c(inp["texts"]), c(inp["text_lengths"]), c(inp["alignment"]), s2)
+    ((pitch * c(cot(pitch.shape, 42))).sum() + (energy * c(cot(energy.shape, 43))).sum()).backward()
+    torch.cuda.synchronize()
+    assert rel_l2(out, ref["dur"][0]) < 2e-4
+    # the pitch / energy towers are ill-conditioned in fp32 with random weights (reference fp32 vs fp64: 7.8e-5)
+    assert rel_l2(pitch, ref["pe"][0][0]) < 5e-4 and rel_l2(energy, ref["pe"][0][1]) < 5e-4
+    assert rel_l2(s1.grad, ref["dur"][1]) < 2e-3, rel_l2(s1.grad, ref["dur"][1])
+    assert rel_l2(s2.grad, ref["pe"][1]) < 1e-2, rel_l2(s2.grad, ref["pe"][1])
+    for tag, mod in (("dur", dp), ("pe", pe)):
+        params = dict(mod.named_parameters())
+        sd = ref[tag][2]
+        tot_ref = torch.cat([sd[n].grad.flatten() for n in params if sd[n].grad is not None])
+        tot = torch.cat([params[n].grad.flatten().double().cpu() for n in params if sd[n].grad is not None])
+        e = rel_l2(tot, tot_ref)
+        print(tag, "all parameter gradients vs fp64 oracle:", e)
+        assert e < (2e-3 if tag == "dur" else 1e-2), (tag, e)
+        scale = float(tot_ref.norm())
+        for n in params:
+            if sd[n].grad is None:
+                continue
+            d = float((params[n].grad.double().cpu() - sd[n].grad).norm())
+            assert d <= 5e-2 * float(sd[n].grad.norm()) + 1e-5 * scale, (tag, n, d)
+        check_golden(tag, lambda n: params[n].grad, g, 2e-2)
