@@ -254,12 +254,26 @@ def measure_train(args, dev, world, rank, barrier, steps, warmup, batch):
         opt.zero_grad()
         return torch.stack([out.total.detach(), out.mel.detach(), out.multi_phase.detach()])
 
+    graphed = None
+    if not args.no_graph:
+        try:  # the whole iteration (fwd, losses, bwd, all-reduce, AdamW) as one CUDA graph
+            from stylish_tts_b200.runtime import GraphedAcousticStep
+            graphed = GraphedAcousticStep(nets, fe, opt, SimpleNamespace(**resident))
+        except Exception as e:  # still our kernels, launched eagerly
+            log(f"[bench] train-step graph capture failed ({type(e).__name__}: {e}); eager launches")
+            graphed = None
+            torch.cuda.synchronize()
+            opt.zero_grad()
+
     def step_resident():
-        return train_step(resident)
+        return graphed() if graphed is not None else train_step(resident)
 
     def step_e2e():
-        loss_host.copy_(train_step({k: v.to(dev, non_blocking=True) for k, v in pinned.items()}),
-                        non_blocking=True)
+        if graphed is not None:
+            loss_host.copy_(graphed(SimpleNamespace(**pinned)), non_blocking=True)
+        else:
+            loss_host.copy_(train_step({k: v.to(dev, non_blocking=True) for k, v in pinned.items()}),
+                            non_blocking=True)
 
     def timed(fn):
         for _ in range(warmup):
@@ -280,6 +294,8 @@ def measure_train(args, dev, world, rank, barrier, steps, warmup, batch):
     ms, launched = timed(step_resident)
     ms_e2e, _ = timed(step_e2e)
     torch.cuda.synchronize()
+    if graphed is not None:
+        launched = graphed.launches_per_replay * steps
     audio_s = batch * frames * 300 / SAMPLE_RATE
     h2d = sum(v.numel() * v.element_size() for v in pinned.values())
     res = {
@@ -288,7 +304,8 @@ def measure_train(args, dev, world, rank, barrier, steps, warmup, batch):
         "batch_per_gpu": batch, "global_batch": batch * world, "frames": frames,
         "e2e": {"steps_per_s": steps / (ms_e2e / 1e3), "ms_per_step": ms_e2e / steps,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 12},
-        "gpu_launches": launched, "grad_allreduce_bytes": opt.numel * 4 if world > 1 else 0,
+        "gpu_launches": launched, "cuda_graph": graphed is not None,
+        "grad_allreduce_bytes": opt.numel * 4 if world > 1 else 0,
         "params": opt.numel, "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 1e9, 1),
         "loss": [round(float(x), 5) for x in loss_host.tolist()],
         "scope": "AcousticStep(use_predicted_pe=False, predict_audio=True): calculate_mel x2 + energy + alignment "
@@ -296,7 +313,7 @@ def measure_train(args, dev, world, rank, barrier, steps, warmup, batch):
                  "MultiSpectrogram x3 + mel & multi-phase losses (backwards_loss normalisation) + backward of "
                  "both modules + fused AdamW; adversarial / SLM terms out of scope (SURVEY 8f)",
     }
-    del opt, sp, se, nets
+    del graphed, opt, sp, se, nets
     torch.cuda.empty_cache()
     return res
 

@@ -502,6 +502,11 @@ STY_API int sty_region_mean_fwd(const float* x, float* out, int B, int Hp, int C
                                 int Wn, sty_stream_t stream);
 STY_API int sty_region_mean_bwd(const float* g, float* dx, int B, int Hp, int C, int W, int r0, int Rn, int w0,
                                 int Wn, sty_stream_t stream);
+/* same, with hyper = [learning rate, step count (>= 1)] in DEVICE memory: the launch can be captured in a CUDA
+ * graph and replayed while the schedule / bias correction advance */
+STY_API int sty_adamw_step_dev(float* p, const float* g, float* m, float* v, int64_t n, const float* hyper,
+                               float beta1, float beta2, float eps, float weight_decay, float grad_scale,
+                               sty_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -136,6 +136,7 @@ _SIGNATURES = {
     "sty_avgpool2_bwd": [_f32p, _f32p, _i32, _i32, _i32, _i32, _f32p],
     "sty_region_mean_fwd": [_f32p, _f32p, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _f32p],
     "sty_region_mean_bwd": [_f32p, _f32p, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _f32p],
+    "sty_adamw_step_dev": [_f32p, _f32p, _f32p, _f32p, _i64, _f32p, _f32, _f32, _f32, _f32, _f32, _f32p],
     "sty_stft_loss_finalize": [_f32p, _f32p, _f32p, _i32, _f32, _f32, _i32, _f32p, _f32p],
 }
 _SPECIAL = {

@@ -635,6 +635,24 @@ adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restri
   }
 }
 
+// same update with the learning rate and the step count read from device memory (hyper = [lr, step]) so that the
+// launch can be replayed from a CUDA graph while both advance
+__global__ void __launch_bounds__(256)
+adamw_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                 int64_t n, const float* __restrict__ hyper, float b1, float b2, float eps, float wd, float gscale) {
+  const float lr = hyper[0], step = hyper[1];
+  const float bc1 = 1.f - powf(b1, step), bc2 = sqrtf(1.f - powf(b2, step));
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float gi = g[i] * gscale;
+    const float pi = p[i] * (1.f - lr * wd);
+    const float mi = fmaf(b1, m[i], (1.f - b1) * gi);
+    const float vi = fmaf(b2, v[i], (1.f - b2) * gi * gi);
+    m[i] = mi;
+    v[i] = vi;
+    p[i] = pi - (lr / bc1) * (mi / (sqrtf(vi) / bc2 + eps));
+  }
+}
+
 }  // namespace
 }  // namespace sty
 
@@ -864,5 +882,17 @@ extern "C" int sty_adamw_step(float* p, const float* g, float* m, float* v, int6
   adamw_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay,
                                                                bc1, bc2, grad_scale);
   STY_CHECK_LAUNCH("adamw_step");
+  return STY_OK;
+}
+
+extern "C" int sty_adamw_step_dev(float* p, const float* g, float* m, float* v, int64_t n, const float* hyper,
+                                  float beta1, float beta2, float eps, float weight_decay, float grad_scale,
+                                  sty_stream_t stream) {
+  STY_REQUIRE(p && g && m && v && hyper && n > 0, "adamw_step_dev: bad argument");
+  int64_t blocks = (n + 1023) / 1024;
+  if (blocks > 1184) blocks = 1184;
+  adamw_dev_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(p, g, m, v, n, hyper, beta1, beta2, eps,
+                                                                   weight_decay, grad_scale);
+  STY_CHECK_LAUNCH("adamw_step_dev");
   return STY_OK;
 }

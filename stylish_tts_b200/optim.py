@@ -44,6 +44,12 @@ class FlatAdamW:
         self.m = torch.zeros(n, device=dev, dtype=torch.float32)
         self.v = torch.zeros(n, device=dev, dtype=torch.float32)
         self.step_count = 0
+        # [lr, step] on the device: read by the update kernel, so a captured step keeps advancing (CUDA graphs)
+        self.hyper = torch.tensor([lr, 0.0], device=dev, dtype=torch.float32)
+
+    def set_lr(self, lr: float):
+        self.lr = lr
+        self.hyper[0] = lr
 
     # -- gradient plumbing (works on any device; the gloo tests exercise it on CPU) --------------
     def pack_gradients(self) -> torch.Tensor:
@@ -75,9 +81,10 @@ class FlatAdamW:
         self.pack_gradients()
         self.reduce_gradients()
         self.step_count += 1
-        L.call("sty_adamw_step", self.flat.data_ptr(), self.grad.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
-               self.numel, self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay, self.step_count,
-               1.0 / self.world, L.stream_ptr())
+        self.hyper[1:2].add_(1.0)
+        L.call("sty_adamw_step_dev", self.flat.data_ptr(), self.grad.data_ptr(), self.m.data_ptr(),
+               self.v.data_ptr(), self.numel, self.hyper.data_ptr(), self.betas[0], self.betas[1], self.eps,
+               self.weight_decay, 1.0 / self.world, L.stream_ptr())
         L.param_epoch += 1  # the arena changed under the views: invalidates the engines' packed weights
 
 

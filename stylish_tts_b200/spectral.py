@@ -343,9 +343,8 @@ class _PhaseLossFn(torch.autograd.Function):
         L.call("sty_phase_loss_fwd", pred.data_ptr(), target.data_ptr(), B, K, N, sums.data_ptr(),
                L.stream_ptr())
         ctx.save_for_backward(pred, target)
-        cnt = torch.tensor([B * K * N, B * (K - 1) * N, B * K * (N - 1)], device=pred.device,
-                           dtype=torch.float32)
-        return (sums / cnt).sum()
+        # counts as Python floats: no host->device copy, so the call can be captured in a CUDA graph
+        return sums[0] / float(B * K * N) + sums[1] / float(B * (K - 1) * N) + sums[2] / float(B * K * (N - 1))
 
     @staticmethod
     def backward(ctx, g):
