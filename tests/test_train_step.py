@@ -103,7 +103,7 @@ def test_gpu_gradients_match_oracle_and_reference(tensor_cores, monkeypatch):
     assert rel_l2(audio, audio_ref) < 5e-4
     # Conditioning: phase = atan2(imag, real) has the derivative (-imag, real)/r^2, so bins where the
     # predicted r is ~0 amplify forward rounding into the gradient of everything upstream of the phase head.
-    # Measured on this case (tools/debug_grads.py): the reference's own formula in fp32 vs fp64 = 1.7e-2;
+    # Measured on this case (tests/debug_grads.py): the reference's own formula in fp32 vs fp64 = 1.7e-2;
     # ours with fp32-FMA convs = 1.0e-2 (closer to fp64 than the reference's fp32), with the bf16x3
     # tensor-core convs (forward error 9e-5 instead of 3e-5) = 6.5e-2.  The amplitude branch, which does not
     # pass through atan2, agrees to 1e-4 in both modes, and every primitive holds 2e-4 on its own
