@@ -178,7 +178,7 @@ def oracle_train_fn(tokens, seed=1):
     import torch
     import stylish_tts_b200 as st
     from stylish_tts_b200 import synth
-    from oracle import speech_oracle as so, spectral_oracle as spo, style_oracle as sto
+    from oracle import dropout_oracle as do, speech_oracle as so, spectral_oracle as spo, style_oracle as sto
 
     nets = st.build_model(st.default_model_config())
     sp, se = nets.speech_predictor, nets.speech_style_encoder
@@ -203,9 +203,13 @@ def oracle_train_fn(tokens, seed=1):
                                           sample_rate=SAMPLE_RATE, mean=-4.0, std=4.0)
             spo.log_energy(mel, -4.0, 4.0)
         style = sto.mel_style_encoder(sde, style_mel.unsqueeze(1), training=True)
-        audio = so.speech_predictor(sd, inp["texts"], inp["text_lengths"], inp["alignment"], inp["pitch"],
-                                    inp["energy"], inp["voiced"], style, inp["denormal_pitch"],
-                                    inp["draws"], bn_training=True)
+        so.MASKS = do.Masks(17)  # train() mode like the GPU arm: dropout sites + decoder box smoothing live
+        try:
+            audio = so.speech_predictor(sd, inp["texts"], inp["text_lengths"], inp["alignment"], inp["pitch"],
+                                        inp["energy"], inp["voiced"], style, inp["denormal_pitch"],
+                                        inp["draws"], bn_training=True, smoothing=(7, 15))
+        finally:
+            so.MASKS = None
         ls = spo.acoustic_spectral_losses(target, audio.squeeze(1), SAMPLE_RATE)
         spo.backwards_total(ls, dict(mel=5.0, multi_phase=8.0)).backward()
     return run, secs
@@ -309,7 +313,7 @@ def measure_train(args, dev, world, rank, barrier, steps, warmup, batch):
         "params": opt.numel, "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 1e9, 1),
         "loss": [round(float(x), 5) for x in loss_host.tolist()],
         "scope": "AcousticStep(use_predicted_pe=False, predict_audio=True): calculate_mel x2 + energy + alignment "
-                 "+ speech_style_encoder + speech_predictor (batch-stat BN, stochastic regularisers off) + "
+                 "+ speech_style_encoder + speech_predictor (train() mode: batch-stat BN, dropout sites and decoder box smoothing live) + "
                  "MultiSpectrogram x3 + mel & multi-phase losses (backwards_loss normalisation) + backward of "
                  "both modules + fused AdamW; adversarial / SLM terms out of scope (SURVEY 8f)",
     }

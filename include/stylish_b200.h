@@ -350,6 +350,38 @@ STY_API int sty_stft_loss_finalize(const float* l1_sums, const float* phase_sums
  * Data gradients of Conv1d reuse sty_conv1d_fwd with transposed, tap-reversed weights.
  * ===================================================================================== */
 
+/* ---- dropout (training-mode stochastic regularisers) ---------------------------------------
+ * Masks come from a stateless integer hash of (seed, site, element index) — see common.cuh drop_keep and its
+ * numpy restatement oracle/dropout_oracle.py — so forward and backward regenerate the same mask and nothing
+ * is stored.  `seed` is a DEVICE pointer to one uint64 read when the kernel runs (graph replays draw new masks);
+ * `site` separates the dropout sites of one step.  NULL / p == 0 = no dropout.
+ *   y[i]  = (res ? res[i] : 0) + scale * act(x[i]) * keep(i / group) / (1-p)      act: STY_ACT_NONE | STY_ACT_SWISH
+ *   dx[i] = dy[i] * scale * act'(x[i]) * keep(i / group) / (1-p)
+ * group = 1: nn.Dropout; group = T on (B,C,T): nn.Dropout1d; group = C*T: DropPath (conv_next.py:138-153).
+ * Replaces nn.Dropout in ConvReluNorm / Encoder / FFN (text_encoder.py:63,204,323,352,388-391), FeedForward /
+ * Attention / ConformerConvModule / ConformerBlock (conformer.py:90-92,144,187,245), AdaptiveDecoderBlock
+ * (ada_norm.py:183-186), Dropout1d duration_predictor.py:79. */
+typedef struct sty_dropout {
+  const void* seed; /* device pointer to a uint64 */
+  uint32_t site;
+  float p;
+} sty_dropout;
+STY_API int sty_dropout_fwd(const float* x, const float* res, float* y, int64_t n, int64_t group, int act,
+                            float scale, const sty_dropout* drop, sty_stream_t stream);
+STY_API int sty_dropout_bwd(const float* x, const float* dy, float* dx, int64_t n, int64_t group, int act,
+                            float scale, const sty_dropout* drop, sty_stream_t stream);
+/* attention with dropout on the probabilities (F.scaled_dot_product_attention(dropout_p=...),
+ * text_encoder.py:270-275): element index of the mask = ((b*H + h)*T + query)*T + key. */
+STY_API int sty_attention_drop_fwd(const float* q, const float* k, const float* v, int64_t qkv_bs,
+                                   float* o, int64_t o_bs, const int64_t* lengths, const float* rope_cos,
+                                   const float* rope_sin, int d_rot, int B, int H, int D, int T, float scale,
+                                   float* lse, const sty_dropout* drop, sty_stream_t stream);
+STY_API int sty_attention_drop_bwd(const float* q, const float* k, const float* v, int64_t qkv_bs, const float* o,
+                                   const float* d_o, int64_t o_bs, const float* lse, const int64_t* lengths,
+                                   const float* rope_cos, const float* rope_sin, int d_rot, float* dq, float* dk,
+                                   float* dv, int64_t dqkv_bs, float* delta, int B, int H, int D, int T,
+                                   float scale, const sty_dropout* drop, sty_stream_t stream);
+
 /* ---- attention forward that also returns the row log-sum-exp (B,H,T) for the backward */
 STY_API int sty_attention_lse_fwd(const float* q, const float* k, const float* v, int64_t qkv_bs,
                                   float* o, int64_t o_bs, const int64_t* lengths, const float* rope_cos,

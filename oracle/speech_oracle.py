@@ -29,6 +29,21 @@ import torch.nn.functional as F
 
 SD = Dict[str, torch.Tensor]
 
+# Training-mode dropout: ``MASKS`` is None (eval / regularisers off) or a callable (site, p, shape) -> keep/(1-p)
+# tensor — oracle/dropout_oracle.Masks, the numpy restatement of the kernels' mask hash.  Site ids are the ones
+# stylish_tts_b200/train_engine.py uses.
+MASKS = None
+
+
+def _drop(x, site, p, layout="bct"):
+    """nn.Dropout site: x is (B,C,T) ('bct') or token-major (B,N,C) ('bnc': the mask is laid out (B,C,N))"""
+    if MASKS is None or p <= 0.0:
+        return x
+    if layout == "bnc":
+        B, N, Cc = x.shape
+        return x * MASKS(site, p, (B, Cc, N)).transpose(1, 2)
+    return x * MASKS(site, p, tuple(x.shape))
+
 
 def _p(sd: SD, name: str) -> torch.Tensor:
     return sd[name]
@@ -95,9 +110,9 @@ def heads_split(x, n_heads):
     return x.view(B, n_heads, C // n_heads, T).permute(0, 1, 3, 2)
 
 
-def mha(sd: SD, prefix: str, x, c, n_heads: int, attn_mask=None):
-    """models/text_encoder.py:214-297 (eval: no dropout).  attn_mask is the
-    0/1 keep mask (B,1,T,T); masked entries get the additive value -1e4."""
+def mha(sd: SD, prefix: str, x, c, n_heads: int, attn_mask=None, drop=None):
+    """models/text_encoder.py:214-297.  attn_mask is the 0/1 keep mask (B,1,T,T); masked entries get the
+    additive value -1e4.  ``drop`` = (site, p): SDPA's dropout on the probabilities (:270-275)."""
     q = conv1d(sd, prefix + ".conv_q", x)
     k = conv1d(sd, prefix + ".conv_k", c)
     v = conv1d(sd, prefix + ".conv_v", c)
@@ -112,13 +127,15 @@ def mha(sd: SD, prefix: str, x, c, n_heads: int, attn_mask=None):
         add.masked_fill_(~attn_mask.to(torch.bool), -1e4)
         scores = scores + add
     p = torch.softmax(scores, dim=-1)
+    if drop is not None:
+        p = _drop(p, drop[0], drop[1])
     o = torch.matmul(p, v)  # (B,H,T,d)
     o = o.transpose(2, 3).contiguous().view(B, C, T)
     return conv1d(sd, prefix + ".conv_o", o)
 
 
 def text_encoder(sd: SD, prefix: str, tokens, lengths, *, n_heads=8, n_layers=8,
-                 kernel_size=3, taps=None):
+                 kernel_size=3, taps=None, p_dropout=0.2):
     """models/text_encoder.py:434-463 (+ prenet :79-86, Encoder :378-394,
     FFN :325-330).  Returns (mu, x, mask)."""
     emb = sd[prefix + ".emb.weight"]
@@ -132,7 +149,7 @@ def text_encoder(sd: SD, prefix: str, tokens, lengths, *, n_heads=8, n_layers=8,
         x = conv1d(sd, f"{prefix}.prenet.conv_layers.{i}", x * mask, padding=2)
         x = channel_layernorm(x, sd[f"{prefix}.prenet.norm_layers.{i}.gamma"],
                               sd[f"{prefix}.prenet.norm_layers.{i}.beta"])
-        x = torch.relu(x)
+        x = _drop(torch.relu(x), 1 + i, 0.5)  # ConvReluNorm.relu_drop, p_dropout=0.5 (:63,418)
     x = x_org + conv1d(sd, prefix + ".prenet.proj", x)
     x = x * mask
     if taps is not None:
@@ -143,13 +160,15 @@ def text_encoder(sd: SD, prefix: str, tokens, lengths, *, n_heads=8, n_layers=8,
     pad = kernel_size // 2
     for i in range(n_layers):
         x = x * mask
-        y = mha(sd, f"{e}.attn_layers.{i}", x, x, n_heads, attn_mask)
+        s0 = 16 + 4 * i
+        y = mha(sd, f"{e}.attn_layers.{i}", x, x, n_heads, attn_mask, drop=(s0, p_dropout))
+        y = _drop(y, s0 + 1, p_dropout)
         x = channel_layernorm(x + y, sd[f"{e}.norm_layers_1.{i}.gamma"],
                               sd[f"{e}.norm_layers_1.{i}.beta"])
         y = conv1d(sd, f"{e}.ffn_layers.{i}.conv_1", x * mask, padding=pad)
-        y = torch.relu(y)
+        y = _drop(torch.relu(y), s0 + 2, p_dropout)
         y = conv1d(sd, f"{e}.ffn_layers.{i}.conv_2", y * mask, padding=pad)
-        y = y * mask
+        y = _drop(y * mask, s0 + 3, p_dropout)
         x = channel_layernorm(x + y, sd[f"{e}.norm_layers_2.{i}.gamma"],
                               sd[f"{e}.norm_layers_2.{i}.beta"])
         if taps is not None and i == 0:
@@ -198,9 +217,17 @@ def decoder_block(sd: SD, prefix: str, x, s):
     return (h + sc) / math.sqrt(2)
 
 
-def decoder(sd: SD, prefix: str, asr, f0_curve, n, s, voiced, taps=None):
-    """models/decoder.py:77-90 (eval path; the train-only smoothing :53-75 is
-    not part of the forward oracle)."""
+def box_smooth(x, width):
+    """decoder.py:58-75: zero-padded moving average of odd ``width`` over (B,F)"""
+    if not width:
+        return x
+    w = torch.ones(1, 1, width, dtype=x.dtype)
+    return F.conv1d(x.unsqueeze(1), w, padding=width // 2).squeeze(1) / width
+
+
+def decoder(sd: SD, prefix: str, asr, f0_curve, n, s, voiced, taps=None, smoothing=(0, 0)):
+    """models/decoder.py:52-90; ``smoothing`` = the (F0, N) box widths the train-only branch :53-75 drew."""
+    f0_curve, n = box_smooth(f0_curve, smoothing[0]), box_smooth(n, smoothing[1])
     f0 = conv1d(sd, prefix + ".F0_conv", f0_curve.unsqueeze(1), padding=1)
     nn_ = conv1d(sd, prefix + ".N_conv", n.unsqueeze(1), padding=1)
     vo = conv1d(sd, prefix + ".voiced_conv", voiced.unsqueeze(1), padding=1)
@@ -261,7 +288,8 @@ def _swish(x):
 
 
 def conformer_ff(sd: SD, prefix: str, x, s):
-    """Scale(0.5, PreNorm(FeedForward)) conformer.py:59-95 (eval)."""
+    """Scale(0.5, PreNorm(FeedForward)) conformer.py:59-95.  The block's nn.Dropout modules all have p = 0.0:
+    Conformer.__init__ does not forward the rates generator.py:824-826 asks for (conformer.py:284-296)."""
     h = adaln(sd, prefix + ".fn.norm", x, s, 1e-5)
     h = linear(sd, prefix + ".fn.fn.net.0", h)
     h = _swish(h)
@@ -475,13 +503,14 @@ def multi_generator(sd: SD, prefix: str, mel, style, pitch, voiced, draws=None, 
 
 def speech_predictor(sd: SD, texts, text_lengths, alignment, pitch, energy, voiced, style,
                      denormal_pitch, draws=None, *, prior=None,
-                     taps: Optional[dict] = None, bn_training=False):
-    """SpeechPredictor.forward speech_predictor.py:47-73 -> audio (B,1,L)."""
+                     taps: Optional[dict] = None, bn_training=False, smoothing=(0, 0)):
+    """SpeechPredictor.forward speech_predictor.py:47-73 -> audio (B,1,L).  Training-mode regularisers:
+    set ``MASKS`` (dropout) and ``smoothing`` (decoder.py:53-75)."""
     mu, _, _ = text_encoder(sd, "text_encoder", texts, text_lengths, taps=taps)
     if taps is not None:
         taps["text_encoding"] = mu
     asr = mu @ alignment
-    mel, _ = decoder(sd, "decoder", asr, pitch, energy, style, voiced, taps=taps)
+    mel, _ = decoder(sd, "decoder", asr, pitch, energy, style, voiced, taps=taps, smoothing=smoothing)
     if taps is not None:
         taps["decoder"] = mel
     return multi_generator(sd, "generator", mel, style, denormal_pitch, voiced, draws,

@@ -56,6 +56,11 @@ class WgradArgs(C.Structure):
     ]
 
 
+class Dropout(C.Structure):
+    """Mirror of ``sty_dropout``."""
+    _fields_ = [("seed", _f32p), ("site", C.c_uint32), ("p", _f32)]
+
+
 # name -> argtypes (restype is always int unless listed in _SPECIAL)
 _SIGNATURES = {
     "sty_embed_fwd": [_f32p, _f32p, _f32p, _f32p, _i32, _i32, _i32, _i32, _f32, _f32p],
@@ -137,6 +142,13 @@ _SIGNATURES = {
     "sty_region_mean_fwd": [_f32p, _f32p, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _f32p],
     "sty_region_mean_bwd": [_f32p, _f32p, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _f32p],
     "sty_adamw_step_dev": [_f32p, _f32p, _f32p, _f32p, _i64, _f32p, _f32, _f32, _f32, _f32, _f32, _f32p],
+    "sty_dropout_fwd": [_f32p, _f32p, _f32p, _i64, _i64, _i32, _f32, C.POINTER(Dropout), _f32p],
+    "sty_dropout_bwd": [_f32p, _f32p, _f32p, _i64, _i64, _i32, _f32, C.POINTER(Dropout), _f32p],
+    "sty_attention_drop_fwd": [_f32p, _f32p, _f32p, _i64, _f32p, _i64, _f32p, _f32p, _f32p, _i32, _i32,
+                               _i32, _i32, _i32, _f32, _f32p, C.POINTER(Dropout), _f32p],
+    "sty_attention_drop_bwd": [_f32p, _f32p, _f32p, _i64, _f32p, _f32p, _i64, _f32p, _f32p, _f32p, _f32p, _i32,
+                               _f32p, _f32p, _f32p, _i64, _f32p, _i32, _i32, _i32, _i32, _f32,
+                               C.POINTER(Dropout), _f32p],
     "sty_stft_loss_finalize": [_f32p, _f32p, _f32p, _i32, _f32, _f32, _i32, _f32p, _f32p],
 }
 _SPECIAL = {

@@ -20,8 +20,11 @@ __global__ void __launch_bounds__(QB)
 attention_kernel(const float* __restrict__ q, const float* __restrict__ k,
                  const float* __restrict__ v, int64_t qkv_bs, float* __restrict__ o, int64_t o_bs,
                  const int64_t* __restrict__ lengths, const float* __restrict__ rope_cos,
-                 const float* __restrict__ rope_sin, int T, float scale, float* __restrict__ lse) {
+                 const float* __restrict__ rope_sin, int T, float scale, float* __restrict__ lse, DropSpec ds) {
   constexpr int DP = D + 4;  // padded row (keeps 16 B alignment, spreads banks)
+  const unsigned long long seed = ds.seed ? *ds.seed : 0ull;
+  const unsigned long long drow = (((unsigned long long)blockIdx.z * gridDim.y + blockIdx.y) * T +
+                                   (blockIdx.x * QB + threadIdx.x)) * (unsigned long long)T;
   __shared__ __align__(16) float Ks[KT * DP];
   __shared__ __align__(16) float Vs[KT * DP];
   const int b = blockIdx.z, h = blockIdx.y;
@@ -110,8 +113,10 @@ attention_kernel(const float* __restrict__ q, const float* __restrict__ k,
     for (int j = 0; j < D; ++j) acc[j] *= corr;
 #pragma unroll
     for (int u = 0; u < KT; ++u) {
-      const float pu = expf(sc[u] - m_new);  // -inf -> 0 for padded keys
+      float pu = expf(sc[u] - m_new);  // -inf -> 0 for padded keys
       l += pu;
+      // dropout acts on the normalised probabilities: the denominator keeps every key (SDPA dropout_p)
+      if (ds.seed) pu = drop_keep(seed, ds.site, drow + (unsigned long long)(k0 + u), ds.thresh) ? pu * ds.inv_keep : 0.f;
 #pragma unroll
       for (int j = 0; j < D; j += 4) {
         const float4 vv = *reinterpret_cast<const float4*>(&Vs[u * DP + j]);
@@ -168,8 +173,11 @@ int attention_umma_launch(const float* q, const float* k, const float* v, int64_
 static int attention_launch(const float* q, const float* k, const float* v, int64_t qkv_bs,
                             float* o, int64_t o_bs, const int64_t* lengths,
                             const float* rope_cos, const float* rope_sin, int d_rot, int B,
-                            int H, int D, int T, float scale, float* lse, sty_stream_t stream) {
+                            int H, int D, int T, float scale, float* lse, sty_stream_t stream,
+                            const sty_dropout* drop = nullptr) {
   STY_REQUIRE(q && k && v && o, "attention: null pointer");
+  STY_REQUIRE(!drop || (drop->p >= 0.f && drop->p < 1.f), "attention: dropout p must be in [0,1)");
+  const DropSpec ds = make_drop(drop);
   STY_REQUIRE(B > 0 && H > 0 && T > 0, "attention: bad shape");
   STY_REQUIRE((rope_cos == nullptr) == (rope_sin == nullptr), "attention: need both rope tables");
   STY_REQUIRE(!rope_cos || (d_rot >= 2 && d_rot % 2 == 0 && d_rot <= D), "attention: bad d_rot=%d", d_rot);
@@ -181,19 +189,19 @@ static int attention_launch(const float* q, const float* k, const float* v, int6
     if (rope_cos) {
       STY_REQUIRE(d_rot == 8, "attention: D=16 is built with d_rot=8 (got %d)", d_rot);
       attention_kernel<16, 32, QB, 4><<<grid, QB, 0, st>>>(q, k, v, qkv_bs, o, o_bs, lengths,
-                                                           rope_cos, rope_sin, T, scale, lse);
+                                                           rope_cos, rope_sin, T, scale, lse, ds);
     } else {
       attention_kernel<16, 32, QB, 0><<<grid, QB, 0, st>>>(q, k, v, qkv_bs, o, o_bs, lengths,
-                                                           rope_cos, rope_sin, T, scale, lse);
+                                                           rope_cos, rope_sin, T, scale, lse, ds);
     }
-  } else if (D == 64 && !rope_cos && !lengths && T >= 64 && !getenv("STYLISH_B200_ATTN_SIMT")) {
+  } else if (D == 64 && !rope_cos && !lengths && !ds.seed && T >= 64 && !getenv("STYLISH_B200_ATTN_SIMT")) {
     return attention_umma_launch(q, k, v, qkv_bs, o, o_bs, B, H, T, scale, lse, st);  // tcgen05 path
   } else if (D == 64) {
     constexpr int QB = 128;
     dim3 grid(cdiv(T, QB), H, B);
     STY_REQUIRE(!rope_cos, "attention: D=64 is built without RoPE");
     attention_kernel<64, 16, QB, 0><<<grid, QB, 0, st>>>(q, k, v, qkv_bs, o, o_bs, lengths, rope_cos,
-                                                         rope_sin, T, scale, lse);
+                                                         rope_sin, T, scale, lse, ds);
   } else {
     set_error("attention: unsupported head dim %d (built: 16, 64)", D);
     return STY_ERR_BAD_ARG;
@@ -217,4 +225,13 @@ extern "C" int sty_attention_lse_fwd(const float* q, const float* k, const float
   STY_REQUIRE(lse, "attention_lse: null lse");
   return attention_launch(q, k, v, qkv_bs, o, o_bs, lengths, rope_cos, rope_sin, d_rot, B, H, D, T, scale, lse,
                           stream);
+}
+
+extern "C" int sty_attention_drop_fwd(const float* q, const float* k, const float* v, int64_t qkv_bs, float* o,
+                                      int64_t o_bs, const int64_t* lengths, const float* rope_cos,
+                                      const float* rope_sin, int d_rot, int B, int H, int D, int T, float scale,
+                                      float* lse, const sty_dropout* drop, sty_stream_t stream) {
+  STY_REQUIRE(lse, "attention_drop: null lse");
+  return attention_launch(q, k, v, qkv_bs, o, o_bs, lengths, rope_cos, rope_sin, d_rot, B, H, D, T, scale, lse,
+                          stream, drop);
 }

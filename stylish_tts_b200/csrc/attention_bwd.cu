@@ -44,8 +44,11 @@ attn_bwd_dq_kernel(const float* __restrict__ q, const float* __restrict__ k, con
                    int64_t qkv_bs, const float* __restrict__ o, const float* __restrict__ dO, int64_t o_bs,
                    const float* __restrict__ lse, const int64_t* __restrict__ lengths,
                    const float* __restrict__ rope_cos, const float* __restrict__ rope_sin, int T, float scale,
-                   float* __restrict__ dq, int64_t dq_bs, float* __restrict__ delta) {
+                   float* __restrict__ dq, int64_t dq_bs, float* __restrict__ delta, DropSpec ds) {
   constexpr int DP = D + 4;
+  const unsigned long long seed = ds.seed ? *ds.seed : 0ull;
+  const unsigned long long drow = (((unsigned long long)blockIdx.z * gridDim.y + blockIdx.y) * T +
+                                   (blockIdx.x * QB + threadIdx.x)) * (unsigned long long)T;
   __shared__ __align__(16) float Ks[KT * DP];
   __shared__ __align__(16) float Vs[KT * DP];
   const int b = blockIdx.z, h = blockIdx.y, tid = threadIdx.x;
@@ -102,12 +105,13 @@ attn_bwd_dq_kernel(const float* __restrict__ q, const float* __restrict__ k, con
         dp = fmaf(dor[j + 2], vv.z, dp); dp = fmaf(dor[j + 3], vv.w, dp);
       }
       if (lengths && !(q_valid && (k0 + u) < len)) s += -1e4f;
-      const float ds = expf(s - ls) * (dp - di);
+      if (ds.seed) dp = drop_keep(seed, ds.site, drow + (unsigned long long)(k0 + u), ds.thresh) ? dp * ds.inv_keep : 0.f;
+      const float dsc = expf(s - ls) * (dp - di);
 #pragma unroll
       for (int j = 0; j < D; j += 4) {
         const float4 kk = *reinterpret_cast<const float4*>(&Ks[u * DP + j]);
-        acc[j] = fmaf(ds, kk.x, acc[j]); acc[j + 1] = fmaf(ds, kk.y, acc[j + 1]);
-        acc[j + 2] = fmaf(ds, kk.z, acc[j + 2]); acc[j + 3] = fmaf(ds, kk.w, acc[j + 3]);
+        acc[j] = fmaf(dsc, kk.x, acc[j]); acc[j + 1] = fmaf(dsc, kk.y, acc[j + 1]);
+        acc[j + 2] = fmaf(dsc, kk.z, acc[j + 2]); acc[j + 3] = fmaf(dsc, kk.w, acc[j + 3]);
       }
     }
     __syncthreads();
@@ -129,9 +133,11 @@ attn_bwd_dkv_kernel(const float* __restrict__ q, const float* __restrict__ k, co
                     int64_t qkv_bs, const float* __restrict__ dO, int64_t o_bs, const float* __restrict__ lse,
                     const float* __restrict__ delta, const int64_t* __restrict__ lengths,
                     const float* __restrict__ rope_cos, const float* __restrict__ rope_sin, int T, float scale,
-                    float* __restrict__ dk, float* __restrict__ dv, int64_t dq_bs) {
+                    float* __restrict__ dk, float* __restrict__ dv, int64_t dq_bs, DropSpec ds) {
   constexpr int DP = D + 4;
   constexpr bool DK = MODE != 1, DV = MODE != 2;
+  const unsigned long long seed = ds.seed ? *ds.seed : 0ull;
+  const unsigned long long dbase = ((unsigned long long)blockIdx.z * gridDim.y + blockIdx.y) * T;
   __shared__ __align__(16) float Qs[QT * DP];
   __shared__ __align__(16) float Gs[QT * DP];
   __shared__ float Ls[QT], Ds[QT];
@@ -192,21 +198,26 @@ attn_bwd_dkv_kernel(const float* __restrict__ q, const float* __restrict__ k, co
       }
       if (lengths && !(k_valid && (q0 + u) < len)) s += -1e4f;
       const float p = expf(s - Ls[u]);
+      float km = 1.f;  // keep mask * 1/(1-p) of probability (query q0+u, key tk)
+      if (ds.seed)
+        km = drop_keep(seed, ds.site, (dbase + (unsigned long long)(q0 + u)) * (unsigned long long)T + tk, ds.thresh)
+                 ? ds.inv_keep : 0.f;
       if constexpr (DV) {
+        const float pd = p * km;
 #pragma unroll
         for (int j = 0; j < D; j += 4) {
           const float4 gg = *reinterpret_cast<const float4*>(&Gs[u * DP + j]);
-          av[j] = fmaf(p, gg.x, av[j]); av[j + 1] = fmaf(p, gg.y, av[j + 1]);
-          av[j + 2] = fmaf(p, gg.z, av[j + 2]); av[j + 3] = fmaf(p, gg.w, av[j + 3]);
+          av[j] = fmaf(pd, gg.x, av[j]); av[j + 1] = fmaf(pd, gg.y, av[j + 1]);
+          av[j + 2] = fmaf(pd, gg.z, av[j + 2]); av[j + 3] = fmaf(pd, gg.w, av[j + 3]);
         }
       }
       if constexpr (DK) {
-        const float ds = p * (dp - Ds[u]);
+        const float dsc = p * (dp * km - Ds[u]);
 #pragma unroll
         for (int j = 0; j < D; j += 4) {
           const float4 qq = *reinterpret_cast<const float4*>(&Qs[u * DP + j]);
-          ak[j] = fmaf(ds, qq.x, ak[j]); ak[j + 1] = fmaf(ds, qq.y, ak[j + 1]);
-          ak[j + 2] = fmaf(ds, qq.z, ak[j + 2]); ak[j + 3] = fmaf(ds, qq.w, ak[j + 3]);
+          ak[j] = fmaf(dsc, qq.x, ak[j]); ak[j + 1] = fmaf(dsc, qq.y, ak[j + 1]);
+          ak[j + 2] = fmaf(dsc, qq.z, ak[j + 2]); ak[j + 3] = fmaf(dsc, qq.w, ak[j + 3]);
         }
       }
     }
@@ -232,11 +243,13 @@ attn_bwd_dkv_kernel(const float* __restrict__ q, const float* __restrict__ k, co
 
 using namespace sty;
 
-extern "C" int sty_attention_bwd(const float* q, const float* k, const float* v, int64_t qkv_bs, const float* o,
-                                 const float* d_o, int64_t o_bs, const float* lse, const int64_t* lengths,
-                                 const float* rope_cos, const float* rope_sin, int d_rot, float* dq, float* dk,
-                                 float* dv, int64_t dqkv_bs, float* delta, int B, int H, int D, int T, float scale,
-                                 sty_stream_t stream) {
+static int attention_bwd_launch(const float* q, const float* k, const float* v, int64_t qkv_bs, const float* o,
+                                const float* d_o, int64_t o_bs, const float* lse, const int64_t* lengths,
+                                const float* rope_cos, const float* rope_sin, int d_rot, float* dq, float* dk,
+                                float* dv, int64_t dqkv_bs, float* delta, int B, int H, int D, int T, float scale,
+                                const sty_dropout* drop, sty_stream_t stream) {
+  STY_REQUIRE(!drop || (drop->p >= 0.f && drop->p < 1.f), "attention_bwd: dropout p must be in [0,1)");
+  const DropSpec ds = make_drop(drop);
   STY_REQUIRE(q && k && v && o && d_o && lse && dq && dk && dv && delta, "attention_bwd: null pointer");
   STY_REQUIRE(B > 0 && H > 0 && T > 0 && H <= 65535 && B <= 65535, "attention_bwd: bad shape");
   STY_REQUIRE((rope_cos == nullptr) == (rope_sin == nullptr), "attention_bwd: need both rope tables");
@@ -247,31 +260,50 @@ extern "C" int sty_attention_bwd(const float* q, const float* k, const float* v,
     if (rope_cos) {
       STY_REQUIRE(d_rot == 8, "attention_bwd: D=16 is built with d_rot=8 (got %d)", d_rot);
       attn_bwd_dq_kernel<16, 32, QB, 4><<<grid, QB, 0, st>>>(q, k, v, qkv_bs, o, d_o, o_bs, lse, lengths, rope_cos,
-                                                             rope_sin, T, scale, dq, dqkv_bs, delta);
+                                                             rope_sin, T, scale, dq, dqkv_bs, delta, ds);
       attn_bwd_dkv_kernel<16, 32, QB, 4, 0><<<grid, QB, 0, st>>>(q, k, v, qkv_bs, d_o, o_bs, lse, delta, lengths,
-                                                                 rope_cos, rope_sin, T, scale, dk, dv, dqkv_bs);
+                                                                 rope_cos, rope_sin, T, scale, dk, dv, dqkv_bs, ds);
     } else {
       attn_bwd_dq_kernel<16, 32, QB, 0><<<grid, QB, 0, st>>>(q, k, v, qkv_bs, o, d_o, o_bs, lse, lengths, rope_cos,
-                                                             rope_sin, T, scale, dq, dqkv_bs, delta);
+                                                             rope_sin, T, scale, dq, dqkv_bs, delta, ds);
       attn_bwd_dkv_kernel<16, 32, QB, 0, 0><<<grid, QB, 0, st>>>(q, k, v, qkv_bs, d_o, o_bs, lse, delta, lengths,
-                                                                 rope_cos, rope_sin, T, scale, dk, dv, dqkv_bs);
+                                                                 rope_cos, rope_sin, T, scale, dk, dv, dqkv_bs, ds);
     }
   } else if (D == 64) {
     STY_REQUIRE(!rope_cos, "attention_bwd: D=64 is built without RoPE");
     constexpr int QB = 128;
     dim3 grid(cdiv(T, QB), H, B);
     attn_bwd_dq_kernel<64, 16, QB, 0><<<grid, QB, 0, st>>>(q, k, v, qkv_bs, o, d_o, o_bs, lse, lengths, rope_cos,
-                                                           rope_sin, T, scale, dq, dqkv_bs, delta);
+                                                           rope_sin, T, scale, dq, dqkv_bs, delta, ds);
     attn_bwd_dkv_kernel<64, 16, QB, 0, 1><<<grid, QB, 0, st>>>(q, k, v, qkv_bs, d_o, o_bs, lse, delta, lengths,
-                                                               rope_cos, rope_sin, T, scale, dk, dv, dqkv_bs);
+                                                               rope_cos, rope_sin, T, scale, dk, dv, dqkv_bs, ds);
     attn_bwd_dkv_kernel<64, 16, QB, 0, 2><<<grid, QB, 0, st>>>(q, k, v, qkv_bs, d_o, o_bs, lse, delta, lengths,
-                                                               rope_cos, rope_sin, T, scale, dk, dv, dqkv_bs);
+                                                               rope_cos, rope_sin, T, scale, dk, dv, dqkv_bs, ds);
   } else {
     set_error("attention_bwd: unsupported head dim %d (built: 16, 64)", D);
     return STY_ERR_BAD_ARG;
   }
   STY_CHECK_LAUNCH("attention_bwd");
   return STY_OK;
+}
+
+extern "C" int sty_attention_bwd(const float* q, const float* k, const float* v, int64_t qkv_bs, const float* o,
+                                 const float* d_o, int64_t o_bs, const float* lse, const int64_t* lengths,
+                                 const float* rope_cos, const float* rope_sin, int d_rot, float* dq, float* dk,
+                                 float* dv, int64_t dqkv_bs, float* delta, int B, int H, int D, int T, float scale,
+                                 sty_stream_t stream) {
+  return attention_bwd_launch(q, k, v, qkv_bs, o, d_o, o_bs, lse, lengths, rope_cos, rope_sin, d_rot, dq, dk, dv,
+                              dqkv_bs, delta, B, H, D, T, scale, nullptr, stream);
+}
+
+extern "C" int sty_attention_drop_bwd(const float* q, const float* k, const float* v, int64_t qkv_bs,
+                                      const float* o, const float* d_o, int64_t o_bs, const float* lse,
+                                      const int64_t* lengths, const float* rope_cos, const float* rope_sin,
+                                      int d_rot, float* dq, float* dk, float* dv, int64_t dqkv_bs, float* delta,
+                                      int B, int H, int D, int T, float scale, const sty_dropout* drop,
+                                      sty_stream_t stream) {
+  return attention_bwd_launch(q, k, v, qkv_bs, o, d_o, o_bs, lse, lengths, rope_cos, rope_sin, d_rot, dq, dk, dv,
+                              dqkv_bs, delta, B, H, D, T, scale, drop, stream);
 }
 
 // =====================================================================================================

@@ -1,6 +1,7 @@
 // Shared device/host helpers for libstylish_b200 (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdint.h>
 #include <stdio.h>
 
@@ -81,6 +82,41 @@ __device__ __forceinline__ float act_apply(float v, int act, float alpha, float 
   }
 }
 __device__ __forceinline__ float act_apply(float v, int act) { return act_apply(v, act, 1.f, 1.f); }
+
+// ---------------------------------------------------------------- dropout masks
+// Stateless counter-based keep mask: keep(seed, site, idx) = hash >= p * 2^24, the same three inputs in the
+// forward and the backward kernel, so no mask is ever stored.  `seed` is read from DEVICE memory at run time:
+// a captured CUDA graph draws new masks on every replay.  The integer hash is restated in numpy by
+// oracle/dropout_oracle.py (bit-exact), which is how the dropout sites are parity-tested.
+struct DropSpec {
+  const unsigned long long* seed;  // nullptr: dropout off
+  uint32_t site, thresh;
+  float inv_keep;
+};
+static inline DropSpec make_drop(const sty_dropout* d) {
+  DropSpec s{nullptr, 0u, 0u, 1.f};
+  if (d && d->seed && d->p > 0.f) {
+    s.seed = reinterpret_cast<const unsigned long long*>(d->seed);
+    s.site = d->site;
+    s.thresh = (uint32_t)llrint((double)d->p * 16777216.0);
+    s.inv_keep = 1.0f / (1.0f - d->p);
+  }
+  return s;
+}
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {
+  x ^= x >> 16;
+  x *= 0x7feb352du;
+  x ^= x >> 15;
+  x *= 0x846ca68bu;
+  x ^= x >> 16;
+  return x;
+}
+__device__ __forceinline__ bool drop_keep(unsigned long long seed, uint32_t site, unsigned long long idx,
+                                          uint32_t thresh) {
+  uint32_t x = mix32((uint32_t)idx ^ (uint32_t)seed);
+  x = mix32(x ^ ((uint32_t)(idx >> 32) + site * 0x9E3779B9u + (uint32_t)(seed >> 32)));
+  return (x >> 8) >= thresh;
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

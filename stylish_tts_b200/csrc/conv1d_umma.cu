@@ -34,7 +34,8 @@ struct UmmaPlan {
   int NT;          // output channels per CTA (multiple of 16, <= 256)
   int n_stages;    // shared-memory ring depth
   int resident;    // 1: all weights of this CTA's NT channels stay in shared memory
-  int acc_cols;    // TMEM columns per accumulator stage (power of two >= NT, >= 32)
+  int acc_cols;    // TMEM columns per accumulator stage (power of two >= NT (2*NT when dual), >= 32)
+  int dual;        // 1: NT <= 64 — hi*hi and hi*lo come from ONE MMA against [W_hi | W_lo] (N = 2*NT): 2 MMAs, not 3
   int stage_u4;    // uint4 per stage
   int wres_u4;     // uint4 of the resident weight block (0 when streaming)
   int tiles_per_b; // ceil(T / 128)
@@ -117,10 +118,17 @@ conv1d_umma_kernel(const sty_conv1d_args p, const UmmaPlan pl) {
   }
   if (pl.resident) {
     // all weights of this CTA's output channels, staged once: [K*2 blocks][CI/8][NT]
+    // (dual: [K][CI/8][hi | lo][NT], so that one descriptor spans the hi and the lo rows of a K chunk)
     const int total = K * 2 * (CI >> 3) * NT;
+    const int c8n = CI >> 3;
     for (int idx = tid; idx < total; idx += kThreads) {
-      const int row = idx / NT, n = idx - row * NT;  // row = blk*(CI/8) + c8
-      Wres[idx] = wsplit[(int64_t)row * CO + co0 + n];
+      const int row = idx / NT, n = idx - row * NT;  // row = blk*(CI/8) + c8, blk = tap*2 + split
+      int dst = idx;
+      if (pl.dual) {
+        const int blk = row / c8n, c8 = row - blk * c8n;
+        dst = (((blk >> 1) * c8n + c8) * 2 + (blk & 1)) * NT + n;
+      }
+      Wres[dst] = wsplit[(int64_t)row * CO + co0 + n];
     }
     fence_proxy_async_smem();
   }
@@ -293,8 +301,9 @@ conv1d_umma_kernel(const sty_conv1d_args p, const UmmaPlan pl) {
           for (int idx = tid; idx < total; idx += kProducerThreads) {
             const int blk = idx / blk_elems, within = idx - blk * blk_elems;
             const int c8l = within / NT, n = within - c8l * NT;
-            Ws[blk * (c8c * NT) + within] =
-                wsplit[((int64_t)blk * (CI >> 3) + (c0 >> 3) + c8l) * CO + co0 + n];
+            const int dst = pl.dual ? (((blk >> 1) * c8c + c8l) * 2 + (blk & 1)) * NT + n
+                                    : blk * (c8c * NT) + within;
+            Ws[dst] = wsplit[((int64_t)blk * (CI >> 3) + (c0 >> 3) + c8l) * CO + co0 + n];
           }
         }
         // items: (c8, row) pairs, row fastest; thread takes items tid, tid+256, ...
@@ -388,13 +397,14 @@ conv1d_umma_kernel(const sty_conv1d_args p, const UmmaPlan pl) {
           const uint4* Xs = stage0 + (size_t)s * pl.stage_u4;
           const uint32_t ws_addr = pl.resident ? smem_u32(Wres) : smem_u32(Xs + 2 * c8c * rows);
           const uint64_t a_d = make_desc(smem_u32(Xs), (uint32_t)rows, 8u);
-          const uint64_t b_d = make_desc(ws_addr, (uint32_t)NT, 8u);
+          const uint64_t b_d = make_desc(ws_addr, (uint32_t)(pl.dual ? 2 * NT : NT), 8u);
           const uint32_t a_hi32 = (uint32_t)(a_d >> 32), b_hi32 = (uint32_t)(b_d >> 32);
           uint32_t a_t = (uint32_t)a_d, b_t = (uint32_t)b_d;  // low words: (tap 0, kb 0, hi split)
           const uint32_t a_lo_off = (uint32_t)(c8c * rows);    // 16-byte units to the lo-split copy
           const uint32_t b_lo_off = (uint32_t)(wc8 * NT);
           const int kblocks = cc8 >> 1;                         // MMA K = 16 bf16 = two 16-byte chunks
-          const uint32_t a_kstep = 2 * rows, b_kstep = 2 * NT;
+          const uint32_t a_kstep = 2 * rows, b_kstep = pl.dual ? 4 * NT : 2 * NT;
+          const uint32_t idesc2 = (idesc & ~(0x3Fu << 17)) | ((uint32_t)((2 * NT) >> 3) << 17);  // N = 2*NT
           const uint32_t b_tstep = 2 * wc8 * NT;                // per tap (hi and lo blocks)
           uint32_t accumulate = ch > 0 ? 1u : 0u;
 #pragma unroll 1
@@ -402,9 +412,14 @@ conv1d_umma_kernel(const sty_conv1d_args p, const UmmaPlan pl) {
             uint32_t ak = a_t, bk = b_t;
 #pragma unroll 2
             for (int kb = 0; kb < kblocks; ++kb, ak += a_kstep, bk += b_kstep) {
-              umma_bf16_w(d_tmem, ak, a_hi32, bk, b_hi32, idesc, accumulate);             // hi * hi
-              umma_bf16_w(d_tmem, ak + a_lo_off, a_hi32, bk, b_hi32, idesc, 1u);          // lo * hi
-              umma_bf16_w(d_tmem, ak, a_hi32, bk + b_lo_off, b_hi32, idesc, 1u);          // hi * lo
+              if (pl.dual) {
+                umma_bf16_w(d_tmem, ak, a_hi32, bk, b_hi32, idesc2, accumulate);          // hi * [hi | lo]
+                umma_bf16_w(d_tmem, ak + a_lo_off, a_hi32, bk, b_hi32, idesc, 1u);        // lo * hi -> cols [0,NT)
+              } else {
+                umma_bf16_w(d_tmem, ak, a_hi32, bk, b_hi32, idesc, accumulate);           // hi * hi
+                umma_bf16_w(d_tmem, ak + a_lo_off, a_hi32, bk, b_hi32, idesc, 1u);        // lo * hi
+                umma_bf16_w(d_tmem, ak, a_hi32, bk + b_lo_off, b_hi32, idesc, 1u);        // hi * lo
+              }
               accumulate = 1;
             }
           }
@@ -487,6 +502,12 @@ conv1d_umma_kernel(const sty_conv1d_args p, const UmmaPlan pl) {
           for (int jj = 0; jj < 16; ++jj) rv[jj] = 0.f;
         }
         tmem_ld16(acc_addr + (uint32_t)n0, r);
+        if (pl.dual) {  // columns [NT, 2*NT) hold the hi*lo partial products
+          float r2[16];
+          tmem_ld16(acc_addr + (uint32_t)(NT + n0), r2);
+#pragma unroll
+          for (int jj = 0; jj < 16; ++jj) r[jj] += r2[jj];
+        }
 #pragma unroll
         for (int jj = 0; jj < 16; ++jj) {
           const int n = n0 + jj;
@@ -559,8 +580,9 @@ static bool make_plan(const sty_conv1d_args& a, UmmaPlan& pl) {
     if (a.CO % nt != 0) continue;
     if (a.CO / nt > 65535) break;
     pl.NT = nt;
+    pl.dual = nt <= 64 ? 1 : 0;  // small-N MMAs cost the same ~120 clk as N = 2*NT ones: fold two of the three
     pl.acc_cols = 32;
-    while (pl.acc_cols < nt) pl.acc_cols <<= 1;
+    while (pl.acc_cols < (pl.dual ? 2 * nt : nt)) pl.acc_cols <<= 1;
     pl.prm_floats = (a.dw_w ? 10 : 4) * a.CI + 3 * nt;
     pl.prm_floats = (pl.prm_floats + 3) & ~3;
     pl.dw_floats = a.dw_w ? ((2 * a.CI * 135 + 3) & ~3) : 0;

@@ -1,0 +1,66 @@
+// Dropout / Dropout1d / DropPath as one elementwise kernel with an optional fused activation, scale and
+// residual; the keep mask is a stateless hash (common.cuh drop_keep), regenerated in the backward.
+// Replaces nn.Dropout (text_encoder.py:63,323,352; conformer.py:90-92,144,187,245; ada_norm.py:157),
+// nn.Dropout1d (duration_predictor.py:30,79) and DropPath (conv_next.py:138-153) in training mode.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace sty {
+namespace {
+
+template <bool BWD>
+__global__ void __launch_bounds__(256)
+dropout_kernel(const float* __restrict__ x, const float* __restrict__ aux, float* __restrict__ y, int64_t n,
+               int64_t group, int act, float scale, DropSpec ds) {
+  const unsigned long long seed = ds.seed ? *ds.seed : 0ull;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int64_t mi = group == 1 ? i : i / group;
+    const float keep = (!ds.seed || drop_keep(seed, ds.site, (unsigned long long)mi, ds.thresh)) ? ds.inv_keep : 0.f;
+    const float xv = x[i];
+    if constexpr (!BWD) {
+      const float a = act == STY_ACT_SWISH ? xv / (1.0f + expf(-xv)) : xv;
+      y[i] = (aux ? aux[i] : 0.f) + scale * a * keep;
+    } else {
+      float d = 1.f;
+      if (act == STY_ACT_SWISH) {
+        const float sg = 1.0f / (1.0f + expf(-xv));
+        d = sg * (1.0f + xv * (1.0f - sg));
+      }
+      y[i] = aux[i] * scale * d * keep;
+    }
+  }
+}
+
+}  // namespace
+}  // namespace sty
+
+using namespace sty;
+
+static int dropout_launch(bool bwd, const float* x, const float* aux, float* y, int64_t n, int64_t group, int act,
+                          float scale, const sty_dropout* drop, sty_stream_t stream) {
+  STY_REQUIRE(x && y && n > 0 && group >= 1, "dropout: bad argument");
+  STY_REQUIRE(act == STY_ACT_NONE || act == STY_ACT_SWISH, "dropout: activation %d not built (none, swish)", act);
+  STY_REQUIRE(!drop || (drop->p >= 0.f && drop->p < 1.f), "dropout: p must be in [0,1)");
+  STY_REQUIRE(!bwd || aux, "dropout_bwd: null dy");
+  const DropSpec ds = make_drop(drop);
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (bwd)
+    dropout_kernel<true><<<(int)blocks, 256, 0, as_stream(stream)>>>(x, aux, y, n, group, act, scale, ds);
+  else
+    dropout_kernel<false><<<(int)blocks, 256, 0, as_stream(stream)>>>(x, aux, y, n, group, act, scale, ds);
+  STY_CHECK_LAUNCH("dropout");
+  return STY_OK;
+}
+
+extern "C" int sty_dropout_fwd(const float* x, const float* res, float* y, int64_t n, int64_t group, int act,
+                               float scale, const sty_dropout* drop, sty_stream_t stream) {
+  return dropout_launch(false, x, res, y, n, group, act, scale, drop, stream);
+}
+
+extern "C" int sty_dropout_bwd(const float* x, const float* dy, float* dx, int64_t n, int64_t group, int act,
+                               float scale, const sty_dropout* drop, sty_stream_t stream) {
+  return dropout_launch(true, x, dy, dx, n, group, act, scale, drop, stream);
+}

@@ -282,7 +282,12 @@ class SpeechPredictor(nn.Module):
 
     forward(texts, text_lengths, alignment, pitch, energy, voiced, style,
             denormal_pitch) -> DecoderPrediction(audio (B,1,L))
+
+    ``train()`` mode runs the reference's stochastic regularisers (dropout sites, decoder box smoothing);
+    set ``regularisers = False`` for a deterministic training forward, ``regulariser_seed`` seeds the masks.
     """
+    regularisers = True
+    regulariser_seed = 0
 
     def __init__(self, model_config):
         super().__init__()
@@ -343,6 +348,8 @@ class _EngineModule(nn.Module):
     """Shared plumbing of the shells: lazily built inference engine (no_grad) and differentiable graph."""
     engine_cls_name = ""
     graph_cls_name = ""
+    regularisers = False  # duration / pitch-energy graphs: dropout, Dropout1d, DropPath sites not built yet
+    regulariser_seed = 0
 
     def engine(self):
         from . import engine as E

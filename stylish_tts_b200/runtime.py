@@ -61,6 +61,11 @@ class GraphedAcousticStep:
         self.static = {k: v.clone() for k, v in vars(example_batch).items()}
         self.opt = optimizer
         batch = SimpleNamespace(**self.static)
+        # stochastic regularisers: the mask seed and the decoder's smoothing filters live in device memory and
+        # are renewed by begin_step() OUTSIDE the graph, before every replay
+        self.train_graphs = [nets.speech_predictor.train_graph()]
+        for g in self.train_graphs:
+            g.auto_step = False
 
         def iteration():
             out = acoustic_step(batch, nets, frontend, source_draws=source_draws)
@@ -73,8 +78,11 @@ class GraphedAcousticStep:
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):  # also fills the device-constant caches: no host copies while capturing
             for _ in range(max(warmup, 1)):
+                self.begin_step()
                 iteration()
         torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.begin_step()
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
         before = L.launches
@@ -83,7 +91,13 @@ class GraphedAcousticStep:
         self.launches_per_replay = L.launches - before
         optimizer.step_count -= 1  # capturing launches nothing: only the warm-up iterations were real updates
 
+    def begin_step(self):
+        for g in self.train_graphs:
+            if g.stochastic():
+                g.begin_step()
+
     def __call__(self, batch=None):
+        self.begin_step()
         if batch is not None:
             for k, v in vars(batch).items():
                 self.static[k].copy_(v, non_blocking=True)

@@ -7,14 +7,19 @@ module's LIVE parameters, so ``loss.backward()`` fills ``.grad`` of every ``nn.P
 ``pitch`` / ``energy`` / ``style`` inputs (stage_type.py:415-448 trains the PE predictor through them).
 
 Training-mode semantics: BatchNorm1d of the conformer conv module uses batch statistics and updates
-its running buffers (conformer.py:183); the stochastic regularisers (dropout, DropPath, the decoder's
-random box smoothing decoder.py:53-75) are disabled — SURVEY §8(d) config 3 pins them off in both
-arms; the harmonic prior is computed without a graph exactly as the reference does under
-``torch.no_grad()`` (generator.py:711-729).
+its running buffers (conformer.py:183); the harmonic prior is computed without a graph exactly as the
+reference does under ``torch.no_grad()`` (generator.py:711-729).  The stochastic regularisers are active
+when the module is in ``train()`` mode and ``module.regularisers`` is on (the default): every nn.Dropout /
+SDPA dropout_p / Dropout1d / DropPath site of the reference is a ``train_ops.dropout`` / attention-dropout
+site whose mask is a stateless hash of (device seed, site, element) — see ``DropoutRng`` — and the decoder's
+random box smoothing (decoder.py:53-75) draws its widths from Python's ``random`` like the reference.
+``begin_step()`` advances the seed and the widths once per forward (``auto_step``), or is called by
+``runtime.GraphedAcousticStep`` before each replay.
 """
 from __future__ import annotations
 
 import math
+import random
 from types import SimpleNamespace
 from typing import Dict, Optional
 
@@ -44,6 +49,48 @@ class TrainGraph:
             off += self.P[n + ".fc.weight"].shape[0]
         self.fc_rows = off
         self._rope: Dict[tuple, tuple] = {}
+        self.rng: Optional[T.DropoutRng] = None  # created on first stochastic forward
+        self.auto_step = True    # forward() calls begin_step() itself (False: a graph runner does)
+        self.active = None       # the DropoutRng while a stochastic forward is being built, else None
+        self.smooth_w = None     # (2, 1, 31) box filters of the decoder's F0 / N smoothing (decoder.py:53-75)
+        self.smooth = (0, 0)
+
+    # ---------------------------------------------------------------- stochastic regularisers
+    def stochastic(self) -> bool:
+        return bool(self.m.training and getattr(self.m, "regularisers", True))
+
+    def begin_step(self, device=None):
+        """next step's randomness: new mask seed; new F0 / N smoothing widths from ``random`` in the reference's
+        order (decoder.py:54-57).  Host -> device writes happen here, never inside forward()."""
+        device = device or next(iter(self.P.values())).device
+        if self.rng is None:
+            self.rng = T.DropoutRng(getattr(self.m, "regulariser_seed", 0), device)
+        else:
+            self.rng.advance()
+        if any(k.startswith("decoder.F0_conv") for k in self.P):
+            f0 = [0, 7, 15][random.randint(0, 2)]
+            nn_ = [0, 7, 15, 31][random.randint(0, 3)]
+            self.smooth = (f0, nn_)
+            rows = []
+            for wd in (f0, nn_):
+                wd = wd or 1
+                rows.append([1.0 / wd if abs(i - 15) <= wd // 2 else 0.0 for i in range(31)])
+            host = torch.tensor(rows, dtype=torch.float32).reshape(2, 1, 31)
+            if self.smooth_w is None:
+                self.smooth_w = host.to(device)
+            else:
+                self.smooth_w.copy_(host)
+
+    def start_forward(self, device):
+        if self.stochastic():
+            if self.auto_step or self.rng is None:
+                self.begin_step(device)
+            self.active = self.rng
+        else:
+            self.active = None
+
+    def drop(self, x, site, p, **kw):
+        return T.dropout(x, self.active, site, p, **kw)
 
     def rope(self, Tn: int, d_head: int, device):
         key = (Tn, d_head, str(device))
@@ -93,11 +140,13 @@ class TrainGraph:
         mask = torch.empty((B, Tn), device=dev, dtype=torch.float32)
         L.call("sty_sequence_mask_fwd", lengths.data_ptr(), mask.data_ptr(), B, Tn, L.stream_ptr())
         h = x0
+        pd = float(te.dropout)  # Encoder / MHA / FFN p_dropout (text_encoder.py:427); the prenet's is 0.5 (:418)
         for i in range(3):
             y = T.conv(h, self.w(f"{t}.prenet.conv_layers.{i}"), self.b(f"{t}.prenet.conv_layers.{i}"),
                        in_mask=mask)
             h = T.chan_ln(y, gamma=P[f"{t}.prenet.norm_layers.{i}.gamma"],
                           beta=P[f"{t}.prenet.norm_layers.{i}.beta"], eps=1e-4, act=ACT_RELU)
+            h = self.drop(h, 1 + i, 0.5)
         x = T.conv(h, self.w(t + ".prenet.proj"), self.b(t + ".prenet.proj"), out_mask=mask, res=x0)
         D = Cc // H
         rope = self.rope(Tn, D, dev)
@@ -107,14 +156,18 @@ class TrainGraph:
             wqkv = torch.cat([P[a + ".conv_q.weight"], P[a + ".conv_k.weight"], P[a + ".conv_v.weight"]], 0)
             bqkv = torch.cat([P[a + ".conv_q.bias"], P[a + ".conv_k.bias"], P[a + ".conv_v.bias"]], 0)
             qkv = T.conv(x, wqkv, bqkv, in_mask=mask)
-            att = T.AttentionFn.apply(qkv, H, D, lengths, rope, 1.0 / math.sqrt(D))
-            y = T.conv(att, self.w(a + ".conv_o"), self.b(a + ".conv_o"))
+            s0 = 16 + 4 * i
+            att = T.AttentionFn.apply(qkv, H, D, lengths, rope, 1.0 / math.sqrt(D),
+                                      (self.active, s0, pd) if self.active is not None else None)
+            y = self.drop(T.conv(att, self.w(a + ".conv_o"), self.b(a + ".conv_o")), s0 + 1, pd)
             x1 = T.chan_ln(y, res=x, gamma=P[f"{e}.norm_layers_1.{i}.gamma"],
                            beta=P[f"{e}.norm_layers_1.{i}.beta"], eps=1e-4)
             f = f"{e}.ffn_layers.{i}"
             hh = T.conv(x1, self.w(f + ".conv_1"), self.b(f + ".conv_1"), in_mask=mask)
+            hh = self.drop(hh, s0 + 2, pd)  # relu -> drop == drop -> relu (the keep factor is >= 0)
             y2 = T.conv(hh, self.w(f + ".conv_2"), self.b(f + ".conv_2"), in_act=ACT_RELU, in_mask=mask,
                         out_mask=mask)
+            y2 = self.drop(y2, s0 + 3, pd)
             x = T.chan_ln(y2, res=x1, gamma=P[f"{e}.norm_layers_2.{i}.gamma"],
                           beta=P[f"{e}.norm_layers_2.{i}.beta"], eps=1e-4, mask=mask)
         return T.conv(x, self.w(t + ".proj_m"), self.b(t + ".proj_m"), out_mask=mask), mask
@@ -141,6 +194,11 @@ class TrainGraph:
         d = "decoder"
         B, Fr = pitch.shape
         asr = T.BmmAlignFn.apply(mu, alignment)
+        if self.active is not None:
+            # train-only random box smoothing of F0 and N (decoder.py:53-75): always the same 31-tap kernel, the
+            # drawn width lives in the device-side filter (width 0 = identity), so a captured graph follows it
+            pitch = T.DwConvFn.apply(pitch.reshape(B, 1, Fr), self.smooth_w[0:1], None, 31, 15).reshape(B, Fr)
+            energy = T.DwConvFn.apply(energy.reshape(B, 1, Fr), self.smooth_w[1:2], None, 31, 15).reshape(B, Fr)
         side = []
         for src, n in ((pitch, "F0_conv"), (energy, "N_conv"), (voiced, "voiced_conv")):
             side.append(T.DwConvFn.apply(src.reshape(B, 1, Fr), self.w(f"{d}.{n}"), self.b(f"{d}.{n}"), 3, 1))
@@ -154,6 +212,10 @@ class TrainGraph:
         P, Bf = self.P, self.Bf
         c = "generator.amp_conformer.layers.0"
         Cc = x.shape[1]
+
+        # No dropout here even in train(): generator.py:824-826 asks for 0.2, but Conformer.__init__ does not
+        # forward attn/ff/conv_dropout to its ConformerBlocks (conformer.py:284-296), so every nn.Dropout of the
+        # block has p = 0.0 in the reference (pinned by tests/golden/train_grads_dropout.npz).
 
         def ff(p, xin):
             n = T.chan_ln(xin, gb=self.gb(h, p + ".fn.norm", Cc), eps=1e-5)
@@ -251,6 +313,7 @@ class TrainGraph:
         lengths = text_lengths.to(device=dev, dtype=torch.int64).contiguous()
         alignment, pitch, energy = f32(alignment), f32(pitch), f32(energy)
         voiced, style, denormal_pitch = f32(voiced), f32(style), f32(denormal_pitch)
+        self.start_forward(dev)
         h = self.style_fc(style)
         mu, _ = self.text_encoder(texts, lengths)
         mel = self.decoder(mu, alignment, pitch, energy, voiced, h)

@@ -333,11 +333,86 @@ class DwConvFn(Function):
         return dx, dw.reshape(ctx.w_shape), (db if ctx.has_bias else None), None, None
 
 
-class AttentionFn(Function):
-    """attention core on a fused (B, 3*H*D, T) q|k|v tensor (text_encoder.py:233-272, conformer.py:112-131)."""
+class DropoutRng:
+    """Source of the training-mode masks: one uint64 seed in DEVICE memory (so a captured CUDA graph draws new
+    masks on every replay) plus the per-site ids.  ``advance()`` moves to the next step's seed; the sequence is
+    a host-side splitmix64 of the user seed, written with ``fill_`` on the current stream."""
+
+    def __init__(self, seed: int = 0, device="cuda"):
+        self.state = (int(seed) * 0x9E3779B97F4A7C15 + 0x1234567) & (2 ** 64 - 1)
+        self.dev = torch.zeros(1, device=device, dtype=torch.int64)
+        self.value = 0
+        self.advance()
+
+    def advance(self) -> int:
+        self.state = (self.state + 0x9E3779B97F4A7C15) & (2 ** 64 - 1)
+        z = self.state
+        z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & (2 ** 64 - 1)
+        z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & (2 ** 64 - 1)
+        self.set(z ^ (z >> 31))
+        return self.value
+
+    def set(self, value: int) -> None:
+        self.value = int(value) & (2 ** 64 - 1)
+        self.dev.fill_(self.value - 2 ** 64 if self.value >= 2 ** 63 else self.value)
+
+    def spec(self, site: int, p: float) -> "L.Dropout":
+        return L.Dropout(self.dev.data_ptr(), int(site), float(p))
+
+
+class DropoutFn(Function):
+    """y = res + scale * act(x) * keep / (1-p)   (nn.Dropout / Dropout1d / DropPath, see sty_dropout_fwd)"""
 
     @staticmethod
-    def forward(ctx, qkv, H, D, lengths, rope, scale):
+    def forward(ctx, x, res, rng, site, p, group, act, scale):
+        x = x.contiguous()
+        y = torch.empty_like(x)
+        spec = rng.spec(site, p)
+        if res is not None:
+            res = res.contiguous()
+            assert res.shape == x.shape
+        L.call("sty_dropout_fwd", x.data_ptr(), L.ptr(res), y.data_ptr(), x.numel(), group, act, scale,
+               C.byref(spec), L.stream_ptr())
+        ctx.save_for_backward(x)
+        ctx.meta = (rng, site, p, group, act, scale, res is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        rng, site, p, group, act, scale, has_res = ctx.meta
+        dy = dy.contiguous()
+        dx = torch.empty_like(x)
+        spec = rng.spec(site, p)
+        L.call("sty_dropout_bwd", x.data_ptr(), dy.data_ptr(), dx.data_ptr(), x.numel(), group, act, scale,
+               C.byref(spec), L.stream_ptr())
+        return dx, (dy if has_res else None), None, None, None, None, None, None
+
+
+def dropout(x, rng, site, p, *, res=None, group=1, act=0, scale=1.0):
+    """training-mode dropout site; ``rng`` None = regularisers off (plain act / scale / residual)"""
+    if rng is None or p <= 0.0:
+        if act == 0 and res is None and scale == 1.0:
+            return x
+        p = 0.0
+        rng = _NULL_RNG
+    return DropoutFn.apply(x, res, rng, site, p, group, act, scale)
+
+
+class _NullRng:
+    def spec(self, site, p):
+        return L.Dropout(None, 0, 0.0)
+
+
+_NULL_RNG = _NullRng()
+
+
+class AttentionFn(Function):
+    """attention core on a fused (B, 3*H*D, T) q|k|v tensor (text_encoder.py:233-272, conformer.py:112-131);
+    ``drop`` = (DropoutRng, site, p) puts SDPA's dropout on the probabilities."""
+
+    @staticmethod
+    def forward(ctx, qkv, H, D, lengths, rope, scale, drop=None):
         B, C3, T = qkv.shape
         n = H * D
         assert C3 == 3 * n and qkv.is_contiguous()
@@ -345,16 +420,24 @@ class AttentionFn(Function):
         lse = _new((B, H, T), qkv)
         q = qkv.data_ptr()
         rc, rs, d_rot = (None, None, 0) if rope is None else (rope[0].data_ptr(), rope[1].data_ptr(), rope[2])
-        L.call("sty_attention_lse_fwd", q, q + 4 * n * T, q + 8 * n * T, qkv.stride(0), out.data_ptr(),
-               out.stride(0), L.ptr(lengths), rc, rs, d_rot, B, H, D, T, scale, lse.data_ptr(), L.stream_ptr())
+        if drop is not None and drop[2] > 0.0:
+            spec = drop[0].spec(drop[1], drop[2])
+            L.call("sty_attention_drop_fwd", q, q + 4 * n * T, q + 8 * n * T, qkv.stride(0), out.data_ptr(),
+                   out.stride(0), L.ptr(lengths), rc, rs, d_rot, B, H, D, T, scale, lse.data_ptr(), C.byref(spec),
+                   L.stream_ptr())
+        else:
+            drop = None
+            L.call("sty_attention_lse_fwd", q, q + 4 * n * T, q + 8 * n * T, qkv.stride(0), out.data_ptr(),
+                   out.stride(0), L.ptr(lengths), rc, rs, d_rot, B, H, D, T, scale, lse.data_ptr(),
+                   L.stream_ptr())
         ctx.save_for_backward(qkv, out, lse)
-        ctx.meta = (H, D, lengths, rope, scale)
+        ctx.meta = (H, D, lengths, rope, scale, drop)
         return out
 
     @staticmethod
     def backward(ctx, d_out):
         qkv, out, lse = ctx.saved_tensors
-        H, D, lengths, rope, scale = ctx.meta
+        H, D, lengths, rope, scale, drop = ctx.meta
         B, C3, T = qkv.shape
         n = H * D
         d_out = d_out.contiguous()
@@ -362,11 +445,15 @@ class AttentionFn(Function):
         delta = _new((B, H, T), qkv)
         q, dq = qkv.data_ptr(), d_qkv.data_ptr()
         rc, rs, d_rot = (None, None, 0) if rope is None else (rope[0].data_ptr(), rope[1].data_ptr(), rope[2])
-        L.call("sty_attention_bwd", q, q + 4 * n * T, q + 8 * n * T, qkv.stride(0), out.data_ptr(),
-               d_out.data_ptr(), out.stride(0), lse.data_ptr(), L.ptr(lengths), rc, rs, d_rot, dq,
-               dq + 4 * n * T, dq + 8 * n * T, d_qkv.stride(0), delta.data_ptr(), B, H, D, T, scale,
-               L.stream_ptr())
-        return d_qkv, None, None, None, None, None
+        args = (q, q + 4 * n * T, q + 8 * n * T, qkv.stride(0), out.data_ptr(),
+                d_out.data_ptr(), out.stride(0), lse.data_ptr(), L.ptr(lengths), rc, rs, d_rot, dq,
+                dq + 4 * n * T, dq + 8 * n * T, d_qkv.stride(0), delta.data_ptr(), B, H, D, T, scale)
+        if drop is not None:
+            spec = drop[0].spec(drop[1], drop[2])
+            L.call("sty_attention_drop_bwd", *args, C.byref(spec), L.stream_ptr())
+        else:
+            L.call("sty_attention_bwd", *args, L.stream_ptr())
+        return d_qkv, None, None, None, None, None, None
 
 
 class GluFn(Function):

@@ -15,6 +15,7 @@ a64, g64, d64, _ = oracle_grads(sp, inp, torch.float64, prior=prior)
 a32, g32, d32, _ = oracle_grads(sp, inp, torch.float32, prior=prior)
 dev = torch.device("cuda:0")
 sp = sp.to(dev).train()
+sp.regularisers = False
 c = lambda t: t.to(dev)
 style, pitch, energy = (c(inp[k]).clone().requires_grad_(True) for k in ("style", "pitch", "energy"))
 out = sp(c(inp["texts"]), c(inp["text_lengths"]), c(inp["alignment"]), pitch, energy, c(inp["voiced"]), style,

@@ -92,6 +92,7 @@ def test_gpu_gradients_match_oracle_and_reference(tensor_cores, monkeypatch):
 
     dev = torch.device("cuda:0")
     sp = sp.to(dev).train()
+    sp.regularisers = False  # deterministic arm; train()-mode regularisers: tests/test_dropout.py
     c = lambda t: t.to(dev)
     style, pitch, energy = (c(inp[k]).clone().requires_grad_(True) for k in ("style", "pitch", "energy"))
     out = sp(c(inp["texts"]), c(inp["text_lengths"]), c(inp["alignment"]), pitch, energy, c(inp["voiced"]), style,
@@ -151,6 +152,7 @@ def test_full_size_training_step_is_finite():
     sp = st.build_model(st.default_model_config()).speech_predictor
     synth.randomize_(sp, 0)
     sp = sp.to(dev).train()
+    sp.regularisers = False  # deterministic arm; train()-mode regularisers: tests/test_dropout.py
     inp = synth.speech_inputs(32, 258, seed=1)
     c = lambda t: t.to(dev)
     out = sp(c(inp["texts"]), c(inp["text_lengths"]), c(inp["alignment"]), c(inp["pitch"]), c(inp["energy"]),
@@ -188,6 +190,7 @@ def test_acoustic_step_trains_both_modules():
     synth.randomize_(nets.speech_predictor, 0)
     synth.converge_spectral_(nets.speech_style_encoder)
     sp, se = nets.speech_predictor.to(dev).train(), nets.speech_style_encoder.to(dev).train()
+    sp.regularisers = False  # deterministic steps (train()-mode regularisers: tests/test_dropout.py)
     B, Tn = 2, 18
     inp = synth.speech_inputs(B, Tn, seed=4)
     dur = torch.full((B, Tn), 3.0)
@@ -248,6 +251,7 @@ def test_graphed_acoustic_step_matches_eager():
         torch.manual_seed(5)
         nets["speech_style_encoder"] = synth.converge_spectral_(type(nets.speech_style_encoder)(80, 64, 384, True))
         sp, se = nets.speech_predictor.to(dev).train(), nets.speech_style_encoder.to(dev).train()
+        sp.regularisers = False  # deterministic steps (train()-mode regularisers: tests/test_dropout.py)
         fe = ts.FrontEnd(mc)
         opt = optim.FlatAdamW(list(sp.parameters()) + list(se.parameters()), lr=1e-4, world_size=1)
         losses = []
