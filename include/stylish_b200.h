@@ -370,6 +370,11 @@ STY_API int sty_dropout_fwd(const float* x, const float* res, float* y, int64_t 
                             float scale, const sty_dropout* drop, sty_stream_t stream);
 STY_API int sty_dropout_bwd(const float* x, const float* dy, float* dx, int64_t n, int64_t group, int act,
                             float scale, const sty_dropout* drop, sty_stream_t stream);
+/* y[r,t] = act(scale[r]*x[r,t] + shift[r]) * keep(r*T+t)/(1-p), x (rows,T) contiguous: AdaIN affine + LeakyReLU +
+ * Dropout ahead of the convs of AdaptiveDecoderBlock in train() mode (ada_norm.py:181-186).  Its backward is
+ * sty_dropout_bwd (act NONE) followed by sty_prologue_bwd_reduce / _apply. */
+STY_API int sty_affine_act_dropout_fwd(const float* x, const float* scale, const float* shift, float* y,
+                                       int rows, int T, int act, const sty_dropout* drop, sty_stream_t stream);
 /* attention with dropout on the probabilities (F.scaled_dot_product_attention(dropout_p=...),
  * text_encoder.py:270-275): element index of the mask = ((b*H + h)*T + query)*T + key. */
 STY_API int sty_attention_drop_fwd(const float* q, const float* k, const float* v, int64_t qkv_bs,

@@ -70,6 +70,25 @@ def speech_predictor_sites(n_layers=8):
     return seq
 
 
+def duration_predictor_sites(n_layer=3):
+    """DurationPredictor.forward in train(): text encoder, cross-attention probabilities, then per ConvNeXt
+    block its DropPath ('path', drawn with Tensor.bernoulli_) and the Dropout1d after it ('chan')"""
+    seq = speech_predictor_sites() + [(80, "attn")]
+    for i in range(n_layer):
+        seq += [(84 + 2 * i, "path"), (85 + 2 * i, "chan")]
+    return seq
+
+
+def pitch_energy_predictor_sites():
+    """PitchEnergyPredictor.forward in train(): text encoder, 3 prosody-encoder layers, 2 towers x 4 blocks x 2"""
+    seq = speech_predictor_sites()
+    for i in range(3):
+        s0 = 80 + 4 * i
+        seq += [(s0, "attn"), (s0 + 1, "bct"), (s0 + 2, "bct"), (s0 + 3, "bct")]
+    seq += [(96 + j, "bct") for j in range(16)]
+    return seq
+
+
 @contextlib.contextmanager
 def patched_reference(seed: int, sites, smoothing=(0, 0)):
     """Run UNMODIFIED reference modules in train() mode with the hash masks: replaces ``torch.nn.functional
@@ -82,11 +101,26 @@ def patched_reference(seed: int, sites, smoothing=(0, 0)):
     it = iter(sites)
     real_dropout, real_sdpa, real_randint, real_to = F.dropout, F.scaled_dot_product_attention, random.randint, \
         torch.Tensor.to
+    real_dropout1d, real_bernoulli = F.dropout1d, torch.Tensor.bernoulli_
+
+    def dropout1d(x, p=0.5, training=True, inplace=False):  # nn.Dropout1d: one draw per (b, c)
+        if not training or p == 0.0:
+            return x
+        site, layout = next(it)
+        assert layout == "chan", (site, layout)
+        return x * scale_mask(seed, site, tuple(x.shape[:2]), p, x.dtype).unsqueeze(-1)
+
+    def bernoulli_(self, keep_prob=0.5, *, generator=None):  # DropPath's per-sample draw (conv_next.py:138-143)
+        site, layout = next(it)
+        assert layout == "path", (site, layout)
+        m = keep_mask(seed, site, self.numel(), 1.0 - keep_prob).astype(np.float32)
+        return self.copy_(torch.from_numpy(m).reshape(self.shape).to(self.dtype))
 
     def dropout(x, p=0.5, training=True, inplace=False):
         if not training or p == 0.0:
             return x
         site, layout = next(it)
+        assert layout in ("bct", "bnc"), (site, layout)
         if layout == "bnc":
             B, N, Cc = x.shape
             m = scale_mask(seed, site, (B, Cc, N), p, x.dtype).transpose(1, 2)
@@ -113,13 +147,15 @@ def patched_reference(seed: int, sites, smoothing=(0, 0)):
             return self
         return real_to(self, *a, **kw)
 
-    F.dropout, F.scaled_dot_product_attention = dropout, sdpa
+    F.dropout, F.scaled_dot_product_attention, F.dropout1d = dropout, sdpa, dropout1d
     random.randint = lambda lo, hi: next(draws)
     torch.Tensor.to = to
+    torch.Tensor.bernoulli_ = bernoulli_
     try:
         yield
         left = list(it)
         assert not left, f"reference did not reach dropout sites {left}"
     finally:
         F.dropout, F.scaled_dot_product_attention, random.randint = real_dropout, real_sdpa, real_randint
+        F.dropout1d, torch.Tensor.bernoulli_ = real_dropout1d, real_bernoulli
         torch.Tensor.to = real_to

@@ -36,12 +36,17 @@ MASKS = None
 
 
 def _drop(x, site, p, layout="bct"):
-    """nn.Dropout site: x is (B,C,T) ('bct') or token-major (B,N,C) ('bnc': the mask is laid out (B,C,N))"""
+    """dropout site on x (B,C,T): 'bct' nn.Dropout (one mask value per element), 'chan' nn.Dropout1d (per (b,c)),
+    'path' DropPath (per sample); 'bnc': nn.Dropout on a token-major (B,N,C) tensor, mask laid out (B,C,N)"""
     if MASKS is None or p <= 0.0:
         return x
     if layout == "bnc":
         B, N, Cc = x.shape
         return x * MASKS(site, p, (B, Cc, N)).transpose(1, 2)
+    if layout == "chan":
+        return x * MASKS(site, p, tuple(x.shape[:2])).unsqueeze(-1)
+    if layout == "path":
+        return x * MASKS(site, p, (x.shape[0],)).reshape(-1, *([1] * (x.dim() - 1)))
     return x * MASKS(site, p, tuple(x.shape))
 
 
@@ -202,14 +207,14 @@ def snake(x, alpha):
     return x + (1 / alpha) * (torch.sin(alpha * x) ** 2)
 
 
-def decoder_block(sd: SD, prefix: str, x, s):
-    """models/ada_norm.py:143-192 (eval)."""
+def decoder_block(sd: SD, prefix: str, x, s, drop=(0, 0.0)):
+    """models/ada_norm.py:143-192; ``drop`` = (site, p) of the two nn.Dropout before conv1 / conv2 (:183,186)."""
     h = adain(sd, prefix + ".norm1", x, s)
     h = F.leaky_relu(h, 0.2)
-    h = conv1d(sd, prefix + ".conv1", h, padding=1)
+    h = conv1d(sd, prefix + ".conv1", _drop(h, drop[0], drop[1]), padding=1)
     h = adain(sd, prefix + ".norm2", h, s)
     h = F.leaky_relu(h, 0.2)
-    h = conv1d(sd, prefix + ".conv2", h, padding=1)
+    h = conv1d(sd, prefix + ".conv2", _drop(h, drop[0] + 1, drop[1]), padding=1)
     sc = x
     if (prefix + ".conv1x1.parametrizations.weight.original0") in sd or \
             (prefix + ".conv1x1.weight") in sd:
@@ -544,8 +549,8 @@ def to_dtype(sd: SD, dtype) -> SD:
 # ---------------------------------------------------------------------------
 # duration / pitch-energy predictors and the inference graph (E7-E9, A1)
 # ---------------------------------------------------------------------------
-def adaptive_convnext_block(sd: SD, prefix: str, x, s):
-    """models/conv_next.py:125-141 — AdaptiveConvNeXtBlock (eval: DropPath off), GELU(erf)."""
+def adaptive_convnext_block(sd: SD, prefix: str, x, s, site=0, p=0.0):
+    """models/conv_next.py:125-141 — AdaptiveConvNeXtBlock, GELU(erf); DropPath(p) on the branch (:130,138-153)."""
     C = x.shape[1]
     r = x
     x = conv1d(sd, prefix + ".dwconv", x, padding=3, groups=C)
@@ -555,7 +560,7 @@ def adaptive_convnext_block(sd: SD, prefix: str, x, s):
     x = F.gelu(x)
     x = grn(x, sd[prefix + ".grn.gamma"], sd[prefix + ".grn.beta"])
     x = linear(sd, prefix + ".pwconv2", x)
-    return r + x.transpose(1, 2)
+    return r + _drop(x.transpose(1, 2), site, p, "path")
 
 
 def mha_qc(sd: SD, prefix: str, x, c, n_heads, attn_mask):
@@ -563,15 +568,16 @@ def mha_qc(sd: SD, prefix: str, x, c, n_heads, attn_mask):
     return mha(sd, prefix, x, c, n_heads, attn_mask)
 
 
-def duration_predictor(sd: SD, texts, text_lengths, style, *, n_layer=3, taps=None):
-    """models/duration_predictor.py:58-87 -> (B,T,classes) monotone logits."""
+def duration_predictor(sd: SD, texts, text_lengths, style, *, n_layer=3, taps=None, last_dropout=0.5):
+    """models/duration_predictor.py:58-87 -> (B,T,classes) monotone logits.  With ``MASKS`` set: train() mode
+    (cross-attention dropout 0.5 :40, DropPath 0.5 :25, Dropout1d(last_dropout) :30,79)."""
     enc, _, _ = text_encoder(sd, "text_encoder", texts, text_lengths)
     enc = enc.transpose(1, 2)  # the reference's "b t c -> b c t" rearrange of a (B,C,T) tensor
     mask = sequence_mask(text_lengths, enc.size(1)).unsqueeze(1).to(enc.dtype)
     q = adaln(sd, "query_norm", enc, style, 1e-5).transpose(1, 2)
     k = adaln(sd, "key_norm", enc, style, 1e-5).transpose(1, 2)
     am = mask.unsqueeze(2) * mask.unsqueeze(-1)
-    att = mha(sd, "cross_attention", q, k, 8, am)
+    att = mha(sd, "cross_attention", q, k, 8, am, drop=(80, 0.5))
     C = att.shape[1]
     att = conv1d(sd, "cross_post.0", att, padding=2, groups=C)
     att = F.silu(att)
@@ -580,8 +586,9 @@ def duration_predictor(sd: SD, texts, text_lengths, style, *, n_layer=3, taps=No
     if taps is not None:
         taps["dur_cross"] = pros
     for i in range(n_layer):
-        pros = adaptive_convnext_block(sd, f"conv_next.{i}", pros, style)
+        pros = adaptive_convnext_block(sd, f"conv_next.{i}", pros, style, 84 + 2 * i, 0.5)
         pros = pros * mask
+        pros = _drop(pros, 85 + 2 * i, last_dropout, "chan")
     pros = pros.transpose(1, 2)
     d = linear(sd, "duration_proj.linear_layer", pros)
     d = torch.cat([d[:, :, :1], torch.abs(d)[:, :, 1:]], dim=2)
@@ -589,19 +596,21 @@ def duration_predictor(sd: SD, texts, text_lengths, style, *, n_layer=3, taps=No
     return d * mask.transpose(1, 2)
 
 
-def prosody_encoder(sd: SD, prefix: str, x, style, lengths, *, n_layers=3, n_heads=2):
-    """models/prosody_encoder.py:63-81 -> (B,T,d_model+style)."""
+def prosody_encoder(sd: SD, prefix: str, x, style, lengths, *, n_layers=3, n_heads=2, p=0.2):
+    """models/prosody_encoder.py:63-81 -> (B,T,d_model+style); dropout p (pitch_energy_predictor.py:27)."""
     mask = sequence_mask(lengths, x.size(2)).unsqueeze(1).to(x.dtype)
     am = mask.unsqueeze(2) * mask.unsqueeze(-1)
     st = style.unsqueeze(2).expand(x.shape[0], -1, x.shape[2])
     x = torch.cat([x, st], dim=1)
     for i in range(n_layers):
         x = x * mask
-        y = mha(sd, f"{prefix}.attn_layers.{i}", x, x, n_heads, am)
+        s0 = 80 + 4 * i
+        y = mha(sd, f"{prefix}.attn_layers.{i}", x, x, n_heads, am, drop=(s0, p))
+        y = _drop(y, s0 + 1, p)
         x = adaln(sd, f"{prefix}.norm_layers_1.{i}", (x + y).transpose(1, 2), style, 1e-5).transpose(1, 2)
         y = conv1d(sd, f"{prefix}.ffn_layers.{i}.conv_1", x * mask)
-        y = torch.relu(y)
-        y = conv1d(sd, f"{prefix}.ffn_layers.{i}.conv_2", y * mask) * mask
+        y = _drop(torch.relu(y), s0 + 2, p)
+        y = _drop(conv1d(sd, f"{prefix}.ffn_layers.{i}.conv_2", y * mask) * mask, s0 + 3, p)
         x = adaln(sd, f"{prefix}.norm_layers_2.{i}", (x + y).transpose(1, 2), style, 1e-5).transpose(1, 2)
         x = conv1d(sd, f"{prefix}.proj_layers.{i}", x)
         x = torch.cat([x, st], dim=1)
@@ -609,8 +618,9 @@ def prosody_encoder(sd: SD, prefix: str, x, style, lengths, *, n_layers=3, n_hea
     return x.transpose(-1, -2)
 
 
-def pitch_energy_predictor(sd: SD, texts, text_lengths, alignment, style, taps=None):
-    """models/pitch_energy_predictor.py:62-82 -> (pitch (B,F), energy (B,F))."""
+def pitch_energy_predictor(sd: SD, texts, text_lengths, alignment, style, taps=None, dropout=0.2):
+    """models/pitch_energy_predictor.py:62-82 -> (pitch (B,F), energy (B,F)); ``dropout`` = the towers'
+    AdaptiveDecoderBlock dropout_p (:22), live when ``MASKS`` is set."""
     enc, _, _ = text_encoder(sd, "text_encoder", texts, text_lengths)
     pros = prosody_encoder(sd, "prosody_encoder", enc, style, text_lengths)
     if taps is not None:
@@ -618,11 +628,11 @@ def pitch_energy_predictor(sd: SD, texts, text_lengths, alignment, style, taps=N
     x = pros.transpose(1, 2) @ alignment
     f0 = x
     for i in range(4):
-        f0 = decoder_block(sd, f"F0.{i}", f0, style)
+        f0 = decoder_block(sd, f"F0.{i}", f0, style, (96 + 2 * i, dropout))
     f0 = conv1d(sd, "F0_proj", f0)
     n = x
     for i in range(4):
-        n = decoder_block(sd, f"N.{i}", n, style)
+        n = decoder_block(sd, f"N.{i}", n, style, (104 + 2 * i, dropout))
     n = conv1d(sd, "N_proj", n)
     return f0.squeeze(1), n.squeeze(1)
 

@@ -144,6 +144,7 @@ _SIGNATURES = {
     "sty_adamw_step_dev": [_f32p, _f32p, _f32p, _f32p, _i64, _f32p, _f32, _f32, _f32, _f32, _f32, _f32p],
     "sty_dropout_fwd": [_f32p, _f32p, _f32p, _i64, _i64, _i32, _f32, C.POINTER(Dropout), _f32p],
     "sty_dropout_bwd": [_f32p, _f32p, _f32p, _i64, _i64, _i32, _f32, C.POINTER(Dropout), _f32p],
+    "sty_affine_act_dropout_fwd": [_f32p, _f32p, _f32p, _f32p, _i32, _i32, _i32, C.POINTER(Dropout), _f32p],
     "sty_attention_drop_fwd": [_f32p, _f32p, _f32p, _i64, _f32p, _i64, _f32p, _f32p, _f32p, _i32, _i32,
                                _i32, _i32, _i32, _f32, _f32p, C.POINTER(Dropout), _f32p],
     "sty_attention_drop_bwd": [_f32p, _f32p, _f32p, _i64, _f32p, _f32p, _i64, _f32p, _f32p, _f32p, _f32p, _i32,

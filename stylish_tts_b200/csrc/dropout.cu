@@ -11,7 +11,7 @@ namespace {
 
 template <bool BWD>
 __global__ void __launch_bounds__(256)
-dropout_kernel(const float* __restrict__ x, const float* __restrict__ aux, float* __restrict__ y, int64_t n,
+dropout_kernel(const float* x, const float* aux, float* y, int64_t n,  // may alias (in-place use)
                int64_t group, int act, float scale, DropSpec ds) {
   const unsigned long long seed = ds.seed ? *ds.seed : 0ull;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -33,10 +33,37 @@ dropout_kernel(const float* __restrict__ x, const float* __restrict__ aux, float
   }
 }
 
+// y[r,t] = act(scale[r] * x[r,t] + shift[r]) * keep(r*T + t) / (1-p): the AdaIN affine + LeakyReLU + Dropout in
+// front of the convs of AdaptiveDecoderBlock in train() mode (ada_norm.py:181-186), materialised once.
+__global__ void __launch_bounds__(256)
+affine_act_dropout_kernel(const float* __restrict__ x, const float* __restrict__ scale,
+                          const float* __restrict__ shift, float* __restrict__ y, int T, int act, DropSpec ds) {
+  const unsigned long long seed = ds.seed ? *ds.seed : 0ull;
+  const int64_t r = blockIdx.y;
+  const float sc = scale[r], sh = shift[r];
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < T; t += gridDim.x * blockDim.x) {
+    const int64_t i = r * T + t;
+    const float keep = (!ds.seed || drop_keep(seed, ds.site, (unsigned long long)i, ds.thresh)) ? ds.inv_keep : 0.f;
+    y[i] = act_apply(fmaf(sc, x[i], sh), act) * keep;
+  }
+}
+
 }  // namespace
 }  // namespace sty
 
 using namespace sty;
+
+extern "C" int sty_affine_act_dropout_fwd(const float* x, const float* scale, const float* shift, float* y,
+                                          int rows, int T, int act, const sty_dropout* drop, sty_stream_t stream) {
+  STY_REQUIRE(x && scale && shift && y && rows > 0 && T > 0 && rows <= 65535, "affine_act_dropout: bad argument");
+  STY_REQUIRE(act == STY_ACT_NONE || act == STY_ACT_RELU || act == STY_ACT_LEAKY02 || act == STY_ACT_SWISH ||
+                  act == STY_ACT_GELU, "affine_act_dropout: activation %d needs a parameter", act);
+  STY_REQUIRE(!drop || (drop->p >= 0.f && drop->p < 1.f), "affine_act_dropout: p must be in [0,1)");
+  dim3 grid(cdiv(T, 256) > 64 ? 64 : cdiv(T, 256), rows);
+  affine_act_dropout_kernel<<<grid, 256, 0, as_stream(stream)>>>(x, scale, shift, y, T, act, make_drop(drop));
+  STY_CHECK_LAUNCH("affine_act_dropout");
+  return STY_OK;
+}
 
 static int dropout_launch(bool bwd, const float* x, const float* aux, float* y, int64_t n, int64_t group, int act,
                           float scale, const sty_dropout* drop, sty_stream_t stream) {

@@ -348,7 +348,7 @@ class _EngineModule(nn.Module):
     """Shared plumbing of the shells: lazily built inference engine (no_grad) and differentiable graph."""
     engine_cls_name = ""
     graph_cls_name = ""
-    regularisers = False  # duration / pitch-energy graphs: dropout, Dropout1d, DropPath sites not built yet
+    regularisers = True  # train() mode: dropout / Dropout1d / DropPath sites live, like the reference
     regulariser_seed = 0
 
     def engine(self):

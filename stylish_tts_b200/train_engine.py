@@ -177,15 +177,24 @@ class TrainGraph:
         fc_b = torch.cat([self.P[n + ".fc.bias"] for n in self.fc_names], 0)
         return T.LinearRowsFn.apply(style, fc_w, fc_b)
 
-    def decoder_block(self, p, x, h):
-        """AdaptiveDecoderBlock (ada_norm.py:143-192); fp32 FMA convs (F0 channel in Hz)"""
+    def decoder_block(self, p, x, h, drop=None):
+        """AdaptiveDecoderBlock (ada_norm.py:143-192); fp32 FMA convs (F0 channel in Hz).
+        drop = (site, p): the two nn.Dropout in front of conv1 / conv2 (:183,186) — AdaIN + LeakyReLU + mask are
+        then materialised by one kernel instead of living in the conv prologue."""
         ci = x.shape[1]
         w1 = self.w(p + ".conv1")
         co = w1.shape[0]
-        t1 = T.conv(x, w1, self.b(p + ".conv1"), gb=self.gb(h, p + ".norm1", ci), in_act=ACT_LEAKY02,
-                    norm="instance", eps=1e-5, umma=False)
         has_sc = (p + ".conv1x1.parametrizations.weight.original0") in self.P
         short = T.conv(x, self.w(p + ".conv1x1"), None, umma=False) if has_sc else x
+        if drop is not None and self.active is not None and drop[1] > 0.0:
+            a1 = T.AdaInDropFn.apply(x, self.gb(h, p + ".norm1", ci), 1e-5, ACT_LEAKY02, self.active, drop[0], drop[1])
+            t1 = T.conv(a1, w1, self.b(p + ".conv1"), umma=False)
+            a2 = T.AdaInDropFn.apply(t1, self.gb(h, p + ".norm2", co), 1e-5, ACT_LEAKY02, self.active, drop[0] + 1,
+                                     drop[1])
+            return T.conv(a2, self.w(p + ".conv2"), self.b(p + ".conv2"), res=short, out_scale=INV_SQRT2,
+                          res_scale=INV_SQRT2, umma=False)
+        t1 = T.conv(x, w1, self.b(p + ".conv1"), gb=self.gb(h, p + ".norm1", ci), in_act=ACT_LEAKY02,
+                    norm="instance", eps=1e-5, umma=False)
         return T.conv(t1, self.w(p + ".conv2"), self.b(p + ".conv2"), gb=self.gb(h, p + ".norm2", co),
                       in_act=ACT_LEAKY02, norm="instance", eps=1e-5, res=short, out_scale=INV_SQRT2,
                       res_scale=INV_SQRT2, umma=False)
@@ -330,11 +339,16 @@ def _prep(dev, texts, text_lengths, *floats):
 
 
 class DurationTrainGraph(TrainGraph):
-    """Differentiable DurationPredictor.forward (duration_predictor.py:58-87; DropPath / dropout off)."""
+    """Differentiable DurationPredictor.forward (duration_predictor.py:58-87).  train() mode: text-encoder
+    dropout, SDPA dropout 0.5 of the cross attention (:40), DropPath 0.5 of every ConvNeXt block
+    (conv_next.py:130) and Dropout1d(last_dropout) after it (:79) — sites 80, 84+2i, 85+2i."""
 
     def forward(self, texts, text_lengths, style):
         P = self.P
         texts, lengths, style = _prep(texts.device, texts, text_lengths, style)
+        self.start_forward(texts.device)
+        on = self.active is not None
+        dcfg = self.mc.duration_predictor
         h = self.style_fc(style)
         enc, mask = self.text_encoder(texts, lengths)
         B, Cc, Tn = enc.shape
@@ -348,7 +362,7 @@ class DurationTrainGraph(TrainGraph):
         H = 8
         D = Cc // H
         att = T.AttentionFn.apply(torch.cat([q, kv], 1), H, D, lengths, self.rope(Tn, D, enc.device),
-                                  1.0 / math.sqrt(D))
+                                  1.0 / math.sqrt(D), (self.active, 80, 0.5) if on else None)
         att = T.conv(att, self.w(a + ".conv_o"), self.b(a + ".conv_o"))
         dw = T.DwConvFn.apply(att, self.w("cross_post.0"), self.b("cross_post.0"), 5, 2)
         pros = T.conv(dw, self.w("cross_post.2"), self.b("cross_post.2"), in_act=ACT_SWISH, res=enc,
@@ -360,6 +374,13 @@ class DurationTrainGraph(TrainGraph):
             y = T.chan_ln(d, gb=self.gb(h, p + ".norm", Cc), eps=1e-6)
             w2 = P[p + ".pwconv2.weight"]
             b2f = P[p + ".pwconv2.bias"] + w2 @ P[p + ".grn.beta"].reshape(-1)
+            if on:  # (residual + DropPath(branch)) * mask, then Dropout1d over (b, c)
+                br = T.ConvNeXtTailFn.apply(y, torch.zeros_like(pros), P[p + ".pwconv1.weight"],
+                                            P[p + ".pwconv1.bias"], None, P[p + ".grn.gamma"].reshape(-1), w2, b2f,
+                                            True, L.ACT_GELU, mask)
+                pros = self.drop(br, 84 + 2 * i, 0.5, group=Cc * Tn, res=pros * m3)
+                pros = self.drop(pros, 85 + 2 * i, float(dcfg.last_dropout), group=Tn)
+                continue
             pros = T.ConvNeXtTailFn.apply(y, pros * m3, P[p + ".pwconv1.weight"], P[p + ".pwconv1.bias"], None,
                                           P[p + ".grn.gamma"].reshape(-1), w2, b2f, True, L.ACT_GELU, mask)
         logits = T.conv(pros, P["duration_proj.linear_layer.weight"].unsqueeze(-1),
@@ -376,6 +397,10 @@ class PitchEnergyTrainGraph(TrainGraph):
     def forward(self, texts, text_lengths, alignment, style):
         P = self.P
         texts, lengths, alignment, style = _prep(texts.device, texts, text_lengths, alignment, style)
+        self.start_forward(texts.device)
+        on = self.active is not None
+        pp = 0.2  # ProsodyEncoder(dropout=0.2) pitch_energy_predictor.py:27; sites 80+4i .. 83+4i
+        pb = float(self.mc.pitch_energy_predictor.dropout)  # AdaptiveDecoderBlock dropout_p (:22,33-56); sites 96..
         h = self.style_fc(style)
         enc, mask = self.text_encoder(texts, lengths)
         B, dm, Tn = enc.shape
@@ -393,22 +418,25 @@ class PitchEnergyTrainGraph(TrainGraph):
             wqkv = torch.cat([P[a + ".conv_q.weight"], P[a + ".conv_k.weight"], P[a + ".conv_v.weight"]], 0)
             bqkv = torch.cat([P[a + ".conv_q.bias"], P[a + ".conv_k.bias"], P[a + ".conv_v.bias"]], 0)
             qkv = T.conv(x, wqkv, bqkv, in_mask=mask)
+            s0 = 80 + 4 * i
             att = T.AttentionGenericFn.apply(qkv[:, :Ch], qkv[:, Ch:2 * Ch], qkv[:, 2 * Ch:], H, D, lengths, rope,
-                                             1.0 / math.sqrt(D))
-            y = T.conv(att, self.w(a + ".conv_o"), self.b(a + ".conv_o"))
+                                             1.0 / math.sqrt(D), (self.active, s0, pp) if on else None)
+            y = self.drop(T.conv(att, self.w(a + ".conv_o"), self.b(a + ".conv_o")), s0 + 1, pp)
             x1 = T.chan_ln(y, res=x * m3, gb=self.gb(h, f"{pe}.norm_layers_1.{i}", Ch), eps=1e-5)
             f = f"{pe}.ffn_layers.{i}"
             hh = T.conv(x1, self.w(f + ".conv_1"), self.b(f + ".conv_1"), in_mask=mask)
+            hh = self.drop(hh, s0 + 2, pp)  # commutes with the ReLU of conv_2's prologue
             y2 = T.conv(hh, self.w(f + ".conv_2"), self.b(f + ".conv_2"), in_act=ACT_RELU, in_mask=mask, out_mask=mask)
+            y2 = self.drop(y2, s0 + 3, pp)
             x2 = T.chan_ln(y2, res=x1, gb=self.gb(h, f"{pe}.norm_layers_2.{i}", Ch), eps=1e-5)
             xp = T.conv(x2, self.w(f"{pe}.proj_layers.{i}"), self.b(f"{pe}.proj_layers.{i}"))
             x = torch.cat([xp, st], 1)
         pros = x * m3
         xa = T.BmmAlignFn.apply(pros, alignment)
         outs = []
-        for tower, proj in (("F0", "F0_proj"), ("N", "N_proj")):
+        for ti, (tower, proj) in enumerate((("F0", "F0_proj"), ("N", "N_proj"))):
             z = xa
             for i in range(4):
-                z = self.decoder_block(f"{tower}.{i}", z, h)
+                z = self.decoder_block(f"{tower}.{i}", z, h, drop=(96 + 8 * ti + 2 * i, pb))
             outs.append(T.conv(z, self.w(proj), self.b(proj), umma=False).squeeze(1))
         return outs[0], outs[1]

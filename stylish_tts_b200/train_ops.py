@@ -399,6 +399,48 @@ def dropout(x, rng, site, p, *, res=None, group=1, act=0, scale=1.0):
     return DropoutFn.apply(x, res, rng, site, p, group, act, scale)
 
 
+class AdaInDropFn(Function):
+    """Dropout(act(AdaIN(x))) materialised (ada_norm.py:181-186 in train() mode): InstanceNorm statistics ->
+    per-(b,c) affine -> activation -> hash-masked dropout in one pass; backward = dropout, then the two-pass
+    norm backward of the conv prologue (``sty_prologue_bwd_*``)."""
+
+    @staticmethod
+    def forward(ctx, x, gb, eps, act, rng, site, p):
+        B, Cc, Tn = x.shape
+        x = x.contiguous()
+        mean, var = row_moments(x)
+        rstd = torch.rsqrt(var + eps)
+        scale = ((1.0 + gb[:, :Cc]) * rstd).contiguous()
+        shift = (gb[:, Cc:] - mean * scale).contiguous()
+        y = torch.empty_like(x)
+        spec = rng.spec(site, p)
+        L.call("sty_affine_act_dropout_fwd", x.data_ptr(), scale.data_ptr(), shift.data_ptr(), y.data_ptr(), B * Cc,
+               Tn, act, C.byref(spec), L.stream_ptr())
+        ctx.save_for_backward(x, scale, shift, mean, rstd)
+        ctx.meta = (act, rng, site, p)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, scale, shift, mean, rstd = ctx.saved_tensors
+        act, rng, site, p = ctx.meta
+        B, Cc, Tn = x.shape
+        dy = dy.contiguous()
+        dxp = torch.empty_like(dy)
+        spec = rng.spec(site, p)
+        L.call("sty_dropout_bwd", dy.data_ptr(), dy.data_ptr(), dxp.data_ptr(), dy.numel(), 1, ACT_NONE, 1.0,
+               C.byref(spec), L.stream_ptr())
+        sums, _ = prologue_bwd(dxp, x, scale=scale, shift=shift, alpha=None, mask=None, act=act, center=mean,
+                               want_sums=True, sums_only=True)
+        s0, s1 = sums[:, :, 0], sums[:, :, 1]
+        d_gb = torch.cat([s1 * rstd, s0], 1)
+        c1 = (-(scale * rstd * rstd) * s1 / Tn).contiguous()
+        c0 = (-scale * s0 / Tn - c1 * mean).contiguous()
+        _, d_x = prologue_bwd(dxp, x, scale=scale, shift=shift, alpha=None, mask=None, act=act, want_sums=False,
+                              c0=c0, c1=c1)
+        return d_x, d_gb, None, None, None, None, None
+
+
 class _NullRng:
     def spec(self, site, p):
         return L.Dropout(None, 0, 0.0)
@@ -590,18 +632,43 @@ class AttentionGenericFn(Function):
     (B,H,T,T) — T is the token count — and uses the batched-product kernels."""
 
     @staticmethod
-    def forward(ctx, q, k, v, H, D, lengths, rope, scale):
+    def forward(ctx, q, k, v, H, D, lengths, rope, scale, drop=None):
+        """drop = (DropoutRng, site, p): SDPA dropout_p on the probabilities — the forward then also goes through
+        the materialised (B,H,T,T) matrix, masked by the elementwise dropout kernel (same element index)."""
         from .engine import attention_generic
         q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
-        out = attention_generic(q, k, v, H=H, D=D, lengths=lengths, rope=rope, scale=scale)
+        if drop is not None and drop[2] <= 0.0:
+            drop = None
         ctx.save_for_backward(q, k, v)
-        ctx.meta = (H, D, lengths, rope, scale)
+        ctx.meta = (H, D, lengths, rope, scale, drop)
+        if drop is None:
+            return attention_generic(q, k, v, H=H, D=D, lengths=lengths, rope=rope, scale=scale)
+        B, _, T = q.shape
+        rc, rs, d_rot = (None, None, 0) if rope is None else (rope[0].data_ptr(), rope[1].data_ptr(), rope[2])
+        st = L.stream_ptr()
+
+        def rows(x, use_rope, mul):
+            y = _new((B, H, T, D), x)
+            L.call("sty_heads_to_rows", x.data_ptr(), x.stride(0), y.data_ptr(), rc if use_rope else None,
+                   rs if use_rope else None, d_rot if use_rope else 0, B, H, D, T, mul, 0, st)
+            return y
+
+        q_r, k_r, v_t = rows(q, True, scale), rows(k, True, 1.0), rows(v, False, 1.0)
+        P = _new((B, H, T, T), q)
+        L.call("sty_attn_probs", q_r.data_ptr(), k_r.data_ptr(), L.ptr(lengths), P.data_ptr(), B, H, D, T, st)
+        spec = drop[0].spec(drop[1], drop[2])
+        L.call("sty_dropout_fwd", P.data_ptr(), None, P.data_ptr(), P.numel(), 1, ACT_NONE, 1.0, C.byref(spec), st)
+        o_r = _new((B, H, T, D), q)
+        L.call("sty_bmm_fwd", P.data_ptr(), T * T, v_t.data_ptr(), T * D, o_r.data_ptr(), T * D, B * H, T, D, T, st)
+        out = _new((B, H * D, T), q)
+        L.call("sty_heads_to_rows", o_r.data_ptr(), out.stride(0), out.data_ptr(), None, None, 0, B, H, D, T, 1.0,
+               1, st)
         return out
 
     @staticmethod
     def backward(ctx, d_out):
         q, k, v = ctx.saved_tensors
-        H, D, lengths, rope, scale = ctx.meta
+        H, D, lengths, rope, scale, drop = ctx.meta
         B, _, T = q.shape
         d_out = d_out.contiguous()
         rc, rs, d_rot = (None, None, 0) if rope is None else (rope[0].data_ptr(), rope[1].data_ptr(), rope[2])
@@ -625,9 +692,19 @@ class AttentionGenericFn(Function):
         BH, TT, TD = B * H, T * T, T * D
         dv_t, dq_r, dk_r = _new((B, H, T, D), q), _new((B, H, T, D), q), _new((B, H, T, D), q)
         dP = _new((B, H, T, T), q)
-        L.call("sty_bmm_tn_fwd", P.data_ptr(), TT, do_t.data_ptr(), TD, dv_t.data_ptr(), TD, BH, T, D, T, st)
+        Pd = P
+        if drop is not None:  # dV sees the dropped probabilities, dP is masked the same way
+            spec = drop[0].spec(drop[1], drop[2])
+            Pd = _new((B, H, T, T), q)
+            L.call("sty_dropout_fwd", P.data_ptr(), None, Pd.data_ptr(), P.numel(), 1, ACT_NONE, 1.0, C.byref(spec),
+                   st)
+        L.call("sty_bmm_tn_fwd", Pd.data_ptr(), TT, do_t.data_ptr(), TD, dv_t.data_ptr(), TD, BH, T, D, T, st)
         L.call("sty_bmm_nt_fwd", do_t.data_ptr(), TD, v_t.data_ptr(), TD, dP.data_ptr(), TT, BH, T, T, D, st)
+        if drop is not None:
+            L.call("sty_dropout_bwd", dP.data_ptr(), dP.data_ptr(), dP.data_ptr(), dP.numel(), 1, ACT_NONE, 1.0,
+                   C.byref(spec), st)
         L.call("sty_softmax_bwd", P.data_ptr(), dP.data_ptr(), BH * T, T, st)
         L.call("sty_bmm_fwd", dP.data_ptr(), TT, k_r.data_ptr(), TD, dq_r.data_ptr(), TD, BH, T, D, T, st)
         L.call("sty_bmm_tn_fwd", dP.data_ptr(), TT, q_r.data_ptr(), TD, dk_r.data_ptr(), TD, BH, T, D, T, st)
-        return heads(dq_r, True, scale), heads(dk_r, True, 1.0), heads(dv_t, False, 1.0), None, None, None, None, None
+        return (heads(dq_r, True, scale), heads(dk_r, True, 1.0), heads(dv_t, False, 1.0), None, None, None, None,
+                None, None)

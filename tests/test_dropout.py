@@ -240,3 +240,106 @@ def test_masks_advance_every_step_and_eval_is_deterministic():
         e1 = sp(*args, **kw).audio.clone()
         e2 = sp(*args, **kw).audio.clone()
     assert rel_l2(e1, e2) < 2e-4
+
+
+# ------------------------------------------------------------------------------------------------ predictors
+def predictor_gold():
+    z = np.load(util.GOLDEN_DIR + "/predictor_grads_dropout.npz")
+    return {k: z[k] for k in z.files}
+
+
+def predictor_oracle_run(nets, inp, sty, dtype):
+    from tests.golden.make_predictor_dropout_golden import SEED_DUR, SEED_PE
+    from tests.golden.make_predictor_grad_golden import cot
+    from tests.test_predictor_train import sd_grad
+
+    f = lambda t: t.to(dtype)
+    sd_d, sd_p = sd_grad(nets.duration_predictor, dtype), sd_grad(nets.pitch_energy_predictor, dtype)
+    used = {}
+    try:
+        so.MASKS = do.Masks(SEED_DUR, dtype)
+        s1 = f(sty).clone().requires_grad_(True)
+        out = so.duration_predictor(sd_d, inp["texts"], inp["text_lengths"], s1)
+        used["dur"] = list(so.MASKS.used)
+        (out * f(cot(out.shape, 41))).sum().backward()
+        so.MASKS = do.Masks(SEED_PE, dtype)
+        s2 = f(sty).clone().requires_grad_(True)
+        pitch, energy = so.pitch_energy_predictor(sd_p, inp["texts"], inp["text_lengths"], f(inp["alignment"]), s2)
+        used["pe"] = list(so.MASKS.used)
+        ((pitch * f(cot(pitch.shape, 42))).sum() + (energy * f(cot(energy.shape, 43))).sum()).backward()
+    finally:
+        so.MASKS = None
+    return dict(dur=(out.detach(), s1.grad, sd_d), pe=((pitch.detach(), energy.detach()), s2.grad, sd_p), used=used)
+
+
+def test_predictor_oracles_with_masks_match_reference_in_train_mode():
+    from tests.golden.make_predictor_grad_golden import build
+    from tests.test_predictor_train import check_golden
+
+    g = predictor_gold()
+    nets, inp, sty = build()
+    r = predictor_oracle_run(nets, inp, sty, torch.float32)
+    assert r["used"]["dur"] == [s for s, _ in do.duration_predictor_sites()]
+    assert r["used"]["pe"] == [s for s, _ in do.pitch_energy_predictor_sites()]
+    assert rel_l2(r["dur"][0], torch.from_numpy(g["dur_out"])) < 1e-5
+    assert rel_l2(r["pe"][0][0], torch.from_numpy(g["pe_pitch"])) < 2e-4
+    assert rel_l2(r["pe"][0][1], torch.from_numpy(g["pe_energy"])) < 2e-4
+    assert rel_l2(r["dur"][1], torch.from_numpy(g["dur_dstyle"])) < 1e-3
+    assert rel_l2(r["pe"][1], torch.from_numpy(g["pe_dstyle"])) < 5e-3
+    check_golden("dur", lambda n: r["dur"][2][n].grad, g, 2e-3)
+    check_golden("pe", lambda n: r["pe"][2][n].grad, g, 1e-2)
+    det = np.load(util.GOLDEN_DIR + "/predictor_grads.npz")
+    assert rel_l2(torch.from_numpy(det["dur_out"]), torch.from_numpy(g["dur_out"])) > 1e-2
+    assert rel_l2(torch.from_numpy(det["pe_pitch"]), torch.from_numpy(g["pe_pitch"])) > 1e-2
+
+
+@pytest.mark.gpu
+def test_gpu_predictors_in_train_mode_match_oracle_and_reference():
+    """DurationPredictor (text-encoder dropout, cross-attention dropout, DropPath, Dropout1d) and
+    PitchEnergyPredictor (prosody-encoder dropout incl. 2 x 160 attention, AdaIN+LeakyReLU+Dropout towers):
+    CUDA graphs vs the fp64 oracle on the same hash masks, and vs the patched reference's golden"""
+    from tests.golden.make_predictor_dropout_golden import SEED_DUR, SEED_PE
+    from tests.golden.make_predictor_grad_golden import build, cot
+    from tests.test_predictor_train import check_golden
+
+    g = predictor_gold()
+    nets, inp, sty = build()
+    ref = predictor_oracle_run(nets, inp, sty, torch.float64)
+    dev = torch.device("cuda:0")
+    c = lambda t: t.to(dev)
+    dp, pe = nets.duration_predictor.to(dev).train(), nets.pitch_energy_predictor.to(dev).train()
+    for mod, seed in ((dp, SEED_DUR), (pe, SEED_PE)):
+        gr = mod.train_graph()
+        gr.auto_step = False
+        gr.begin_step(dev)
+        gr.rng.set(seed)
+    s1 = c(sty).clone().requires_grad_(True)
+    out = dp(c(inp["texts"]), c(inp["text_lengths"]), s1)
+    (out * c(cot(out.shape, 41))).sum().backward()
+    s2 = c(sty).clone().requires_grad_(True)
+    pitch, energy = pe(c(inp["texts"]), c(inp["text_lengths"]), c(inp["alignment"]), s2)
+    ((pitch * c(cot(pitch.shape, 42))).sum() + (energy * c(cot(energy.shape, 43))).sum()).backward()
+    torch.cuda.synchronize()
+    assert rel_l2(out, ref["dur"][0]) < 2e-4, rel_l2(out, ref["dur"][0])
+    assert rel_l2(pitch, ref["pe"][0][0]) < 5e-4 and rel_l2(energy, ref["pe"][0][1]) < 5e-4
+    assert rel_l2(out, torch.from_numpy(g["dur_out"])) < 2e-4
+    assert rel_l2(pitch, torch.from_numpy(g["pe_pitch"])) < 1e-3
+    assert rel_l2(s1.grad, ref["dur"][1]) < 2e-3, rel_l2(s1.grad, ref["dur"][1])
+    assert rel_l2(s2.grad, ref["pe"][1]) < 1e-2, rel_l2(s2.grad, ref["pe"][1])
+    for tag, mod in (("dur", dp), ("pe", pe)):
+        params = dict(mod.named_parameters())
+        sd = ref[tag][2]
+        tot_ref = torch.cat([sd[n].grad.flatten() for n in params if sd[n].grad is not None])
+        tot = torch.cat([params[n].grad.flatten().double().cpu() for n in params if sd[n].grad is not None])
+        e = rel_l2(tot, tot_ref)
+        print(tag, "train-mode parameter gradients vs fp64 oracle:", e)
+        assert e < (2e-3 if tag == "dur" else 1e-2), (tag, e)
+        check_golden(tag, lambda n: params[n].grad, g, 2e-2)
+    # masks advance on their own when auto_step is on
+    gr = dp.train_graph()
+    gr.auto_step = True
+    with torch.no_grad():
+        pass
+    o1 = dp(c(inp["texts"]), c(inp["text_lengths"]), s1).detach().clone()
+    o2 = dp(c(inp["texts"]), c(inp["text_lengths"]), s1).detach().clone()
+    assert rel_l2(o1, o2) > 1e-3

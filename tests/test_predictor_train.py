@@ -65,6 +65,7 @@ def test_gpu_predictor_gradients():
     dev = torch.device("cuda:0")
     c = lambda t: t.to(dev)
     dp, pe = nets.duration_predictor.to(dev).train(), nets.pitch_energy_predictor.to(dev).train()
+    dp.regularisers = pe.regularisers = False  # deterministic arm; train()-mode regularisers: tests/test_dropout.py
     s1 = c(sty).clone().requires_grad_(True)
     out = dp(c(inp["texts"]), c(inp["text_lengths"]), s1)
     (out * c(cot(out.shape, 41))).sum().backward()
