@@ -170,7 +170,19 @@ channel_sum_kernel(const float* __restrict__ x, int64_t x_bs, int64_t x_cs, cons
   const float* __restrict__ row = x + (int64_t)b * x_bs + (int64_t)c * x_cs;
   const float* __restrict__ m = mask ? mask + (int64_t)b * T : nullptr;
   float s = 0.f;
-  for (int t = threadIdx.x; t < T; t += blockDim.x) s += m ? row[t] * m[t] : row[t];
+  if (m) {
+    const float* const rows[2] = {row, m};
+    rows_apply<2, false>(rows, nullptr, T, threadIdx.x, blockDim.x, [&](int, const float (&v)[2]) {
+      s = fmaf(v[0], v[1], s);
+      return 0.f;
+    });
+  } else {
+    const float* const rows[1] = {row};
+    rows_apply<1, false>(rows, nullptr, T, threadIdx.x, blockDim.x, [&](int, const float (&v)[1]) {
+      s += v[0];
+      return 0.f;
+    });
+  }
   s = block_sum(s, red);
   if (threadIdx.x == 0) atomicAdd(out + c, s * scale);
 }
@@ -183,7 +195,11 @@ row_dot_kernel(const float* __restrict__ a, const float* __restrict__ bb, float*
   const float* __restrict__ ar = a + r * T;
   const float* __restrict__ br = bb + r * T;
   float s = 0.f;
-  for (int t = threadIdx.x; t < T; t += blockDim.x) s = fmaf(ar[t], br[t], s);
+  const float* const rows[2] = {ar, br};
+  rows_apply<2, false>(rows, nullptr, T, threadIdx.x, blockDim.x, [&](int, const float (&v)[2]) {
+    s = fmaf(v[0], v[1], s);
+    return 0.f;
+  });
   s = block_sum(s, red);
   if (threadIdx.x == 0) out[r] = s;
 }
@@ -197,13 +213,18 @@ row_moments_kernel(const float* __restrict__ x, int64_t x_bs, int64_t x_cs, floa
   const int b = blockIdx.x / C, c = blockIdx.x % C;
   const float* __restrict__ row = x + (int64_t)b * x_bs + (int64_t)c * x_cs;
   float s = 0.f;
-  for (int i = threadIdx.x; i < T; i += blockDim.x) s += row[i];
+  const float* const rows[1] = {row};
+  rows_apply<1, false>(rows, nullptr, T, threadIdx.x, blockDim.x, [&](int, const float (&v)[1]) {
+    s += v[0];
+    return 0.f;
+  });
   const float mu = block_sum(s, red) / (float)T;
   float q = 0.f;
-  for (int i = threadIdx.x; i < T; i += blockDim.x) {
-    const float a = row[i] - mu;
+  rows_apply<1, false>(rows, nullptr, T, threadIdx.x, blockDim.x, [&](int, const float (&v)[1]) {
+    const float a = v[0] - mu;
     q = fmaf(a, a, q);
-  }
+    return 0.f;
+  });
   const float v = block_sum(q, red) / (float)T;
   if (threadIdx.x == 0) {
     mean[blockIdx.x] = mu;
@@ -228,14 +249,25 @@ prologue_bwd_reduce_kernel(const float* __restrict__ dxp, const float* __restric
   const float al = alpha ? alpha[c] : 1.f;
   const float ce = center ? center[blockIdx.x] : 0.f;
   float s0 = 0.f, s1 = 0.f, s2 = 0.f;
-  for (int t = threadIdx.x; t < T; t += blockDim.x) {
-    const float xm = m ? xr[t] * m[t] : xr[t];
+  auto body = [&](float xm, float g) {
     const float a = fmaf(xm, sc, sh);
-    const float g = gr[t];
     const float ga = g * act_grad(a, act, al);
     s0 += ga;
     s1 = fmaf(ga, xm - ce, s1);
     if (act == STY_ACT_SNAKE) s2 = fmaf(g, snake_dalpha(a, al), s2);
+  };
+  if (m) {
+    const float* const rows[3] = {xr, gr, m};
+    rows_apply<3, false>(rows, nullptr, T, threadIdx.x, blockDim.x, [&](int, const float (&v)[3]) {
+      body(v[0] * v[2], v[1]);
+      return 0.f;
+    });
+  } else {
+    const float* const rows[2] = {xr, gr};
+    rows_apply<2, false>(rows, nullptr, T, threadIdx.x, blockDim.x, [&](int, const float (&v)[2]) {
+      body(v[0], v[1]);
+      return 0.f;
+    });
   }
   s0 = block_sum(s0, red);
   s1 = block_sum(s1, red);
@@ -247,7 +279,8 @@ prologue_bwd_reduce_kernel(const float* __restrict__ dxp, const float* __restric
   }
 }
 
-// apply: dx = g_a*scale*m + c0[b,c] + c1[b,c]*x (+ add)
+// apply: dx = g_a*scale*m + c0[b,c] + c1[b,c]*x (+ add); one block = a 1024-element span of one (b,c) row
+constexpr int kApplySpan = 1024;
 __global__ void __launch_bounds__(256)
 prologue_bwd_apply_kernel(const float* __restrict__ dxp, const float* __restrict__ x, int64_t x_bs, int64_t x_cs,
                           const float* __restrict__ scale, const float* __restrict__ shift,
@@ -257,18 +290,37 @@ prologue_bwd_apply_kernel(const float* __restrict__ dxp, const float* __restrict
                           int64_t dx_bs, int64_t dx_cs, int C, int T, int act) {
   const int bc = blockIdx.x;
   const int b = bc / C, c = bc % C;
-  const int t = blockIdx.y * blockDim.x + threadIdx.x;
-  if (t >= T) return;
-  const float xv = x[(int64_t)b * x_bs + (int64_t)c * x_cs + t];
-  const float m = mask ? mask[(int64_t)b * T + t] : 1.f;
+  const int t0 = blockIdx.y * kApplySpan;
+  const int n = min(kApplySpan, T - t0);
   const float sc = scale ? scale[bc] : 1.f, sh = shift ? shift[bc] : 0.f;
   const float al = alpha ? alpha[c] : 1.f;
-  const float a = fmaf(xv * m, sc, sh);
-  float v = dxp[(int64_t)bc * T + t] * act_grad(a, act, al) * sc * m;
-  if (c0) v += c0[bc];
-  if (c1) v = fmaf(c1[bc], xv, v);
-  if (add) v += add[(int64_t)b * add_bs + (int64_t)c * add_cs + t];
-  dx[(int64_t)b * dx_bs + (int64_t)c * dx_cs + t] = v;
+  const float k0 = c0 ? c0[bc] : 0.f, k1 = c1 ? c1[bc] : 0.f;
+  const float* xr = x + (int64_t)b * x_bs + (int64_t)c * x_cs + t0;
+  const float* gr = dxp + (int64_t)bc * T + t0;
+  const float* mr = mask ? mask + (int64_t)b * T + t0 : nullptr;
+  const float* ar = add ? add + (int64_t)b * add_bs + (int64_t)c * add_cs + t0 : nullptr;
+  float* out = dx + (int64_t)b * dx_bs + (int64_t)c * dx_cs + t0;
+  auto body = [&](float xv, float g, float m, float addv) {
+    const float a = fmaf(xv * m, sc, sh);
+    return fmaf(k1, xv, g * act_grad(a, act, al) * sc * m + k0) + addv;
+  };
+  if (!mr && !ar) {  // the S-rate case: AdaIN / Snake prologues of the generator blocks
+    const float* const rows[2] = {xr, gr};
+    rows_apply<2, true>(rows, out, n, threadIdx.x, blockDim.x,
+                        [&](int, const float (&v)[2]) { return body(v[0], v[1], 1.f, 0.f); });
+  } else if (mr && !ar) {
+    const float* const rows[3] = {xr, gr, mr};
+    rows_apply<3, true>(rows, out, n, threadIdx.x, blockDim.x,
+                        [&](int, const float (&v)[3]) { return body(v[0], v[1], v[2], 0.f); });
+  } else if (!mr) {
+    const float* const rows[3] = {xr, gr, ar};
+    rows_apply<3, true>(rows, out, n, threadIdx.x, blockDim.x,
+                        [&](int, const float (&v)[3]) { return body(v[0], v[1], 1.f, v[2]); });
+  } else {
+    const float* const rows[4] = {xr, gr, mr, ar};
+    rows_apply<4, true>(rows, out, n, threadIdx.x, blockDim.x,
+                        [&](int, const float (&v)[4]) { return body(v[0], v[1], v[2], v[3]); });
+  }
 }
 
 // ------------------------------------------------------------------ GRN + Snake backward (apply)
@@ -283,13 +335,14 @@ grn_snake_bwd_kernel(const float* g_u, const float* __restrict__ h, const float*
   const int64_t off = (int64_t)blockIdx.x * T;
   const float s = gs[blockIdx.x], k = kc[blockIdx.x], al = alpha[j], inv = 1.f / al;
   float da = 0.f;
-  for (int t = threadIdx.x; t < T; t += blockDim.x) {
-    const float hv = h[off + t];
+  const float* const rows[2] = {h + off, g_u + off};
+  rows_apply<2, true>(rows, d_h + off, T, threadIdx.x, blockDim.x, [&](int, const float (&v)[2]) {
+    const float hv = v[0];
     const float hb = fmaf(inv, sin_sq(al * hv), hv);
-    const float dhb = fmaf(g_u[off + t], s, k * hb);
+    const float dhb = fmaf(v[1], s, k * hb);
     da = fmaf(dhb, snake_dalpha(hv, al), da);
-    d_h[off + t] = dhb * (1.f + sinf(2.f * al * hv));
-  }
+    return dhb * (1.f + sinf(2.f * al * hv));
+  });
   da = block_sum(da, red);
   if (threadIdx.x == 0) atomicAdd(dalpha + j, da);
 }
@@ -726,8 +779,8 @@ extern "C" int sty_prologue_bwd_apply(const float* dxp, const float* x, int64_t 
                                       int B, int C, int T, int act, sty_stream_t stream) {
   STY_REQUIRE(dxp && x && dx && B > 0 && C > 0 && T > 0, "prologue_bwd_apply: bad argument");
   STY_REQUIRE(act != STY_ACT_SNAKE || alpha, "prologue_bwd_apply: snake needs alpha");
-  STY_REQUIRE(cdiv(T, 256) <= 65535, "prologue_bwd_apply: T too large for the grid");
-  dim3 grid((unsigned)((int64_t)B * C), cdiv(T, 256));
+  STY_REQUIRE(cdiv(T, kApplySpan) <= 65535, "prologue_bwd_apply: T too large for the grid");
+  dim3 grid((unsigned)((int64_t)B * C), cdiv(T, kApplySpan));
   prologue_bwd_apply_kernel<<<grid, 256, 0, as_stream(stream)>>>(dxp, x, x_bs, x_cs, scale, shift, alpha, mask, c0,
                                                                  c1, add, add_bs, add_cs, dx, dx_bs, dx_cs, C, T,
                                                                  act);

@@ -130,6 +130,65 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// ---------------------------------------------------------------- vectorised row streaming
+// Walk N equally long rows (and optionally an output row) of T floats with the block's threads:
+// out[t] = f(t, {rows[0][t], ..., rows[N-1][t]}).  When all pointers share their 16-byte misalignment the bulk
+// goes through 128-bit loads / stores (<= 3 scalar elements at either end), otherwise everything is scalar.
+// Streaming kernels with one 4-byte load per thread and iteration keep ~32 KB in flight per SM, about half of
+// what HBM3e needs (tools/bench_bwd_stream.py: 1.1-2.3 TB/s before).
+template <int N, bool WRITE, typename F>
+__device__ __forceinline__ void rows_apply(const float* const (&rows)[N], float* out, int T, int tid, int nth,
+                                           F&& f) {
+  const unsigned mis = (unsigned)((uintptr_t)rows[0] & 15u);
+  bool alike = true;
+#pragma unroll
+  for (int k = 1; k < N; ++k) alike &= ((unsigned)((uintptr_t)rows[k] & 15u) == mis);
+  if (WRITE) alike &= ((unsigned)((uintptr_t)out & 15u) == mis);
+  int head = T;
+  if (alike) {
+    head = (int)(((16u - mis) & 15u) >> 2);
+    if (head > T) head = T;
+  }
+  const int nv = (T - head) >> 2;
+  const int tail = head + 4 * nv;
+  for (int t = tid; t < head; t += nth) {
+    float v[N];
+#pragma unroll
+    for (int k = 0; k < N; ++k) v[k] = rows[k][t];
+    const float o = f(t, v);
+    if (WRITE) out[t] = o;
+  }
+#pragma unroll 2
+  for (int i = tid; i < nv; i += nth) {
+    float4 q[N];
+#pragma unroll
+    for (int k = 0; k < N; ++k) q[k] = reinterpret_cast<const float4*>(rows[k] + head)[i];
+    const int t = head + 4 * i;
+    float v[N];
+    float4 o;
+#pragma unroll
+    for (int k = 0; k < N; ++k) v[k] = q[k].x;
+    o.x = f(t, v);
+#pragma unroll
+    for (int k = 0; k < N; ++k) v[k] = q[k].y;
+    o.y = f(t + 1, v);
+#pragma unroll
+    for (int k = 0; k < N; ++k) v[k] = q[k].z;
+    o.z = f(t + 2, v);
+#pragma unroll
+    for (int k = 0; k < N; ++k) v[k] = q[k].w;
+    o.w = f(t + 3, v);
+    if (WRITE) reinterpret_cast<float4*>(out + head)[i] = o;
+  }
+  for (int t = tail + tid; t < T; t += nth) {
+    float v[N];
+#pragma unroll
+    for (int k = 0; k < N; ++k) v[k] = rows[k][t];
+    const float o = f(t, v);
+    if (WRITE) out[t] = o;
+  }
+}
+
 // block-wide sum; `red` is >= 32 floats of shared memory; result broadcast to all threads
 __device__ __forceinline__ float block_sum(float v, float* red) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;

@@ -68,6 +68,16 @@ def randomize_(module: nn.Module, seed: int = 0) -> nn.Module:
 
 
 @torch.no_grad()
+def condition_phase_head_(speech_predictor: nn.Module, shift: float = 3.0) -> nn.Module:
+    """Move the real part of the phase head away from zero (bias += shift).  phase = atan2(imag, real) has the
+    derivative (-imag, real)/r^2; with purely random weights many bins have r ~ 0 and the gradient of everything
+    upstream becomes ill-conditioned (fp32 vs fp64 of the SAME formula: 1.4e-2).  With the shift that difference
+    is 3e-6, so gradient parity can be asserted at kernel accuracy.  Used by the gradient goldens / tests."""
+    with torch.no_grad():
+        speech_predictor.generator.basegen.phase_output_real_conv.bias += shift
+    return speech_predictor
+
+
 def converge_spectral_(module: nn.Module, iters: int = 30) -> nn.Module:
     """Run the spectral-norm power iteration on every (weight_orig, weight_u, weight_v) triple so that a
     freshly initialised module is in the regime a trained checkpoint is in (sigma ~ largest singular value;

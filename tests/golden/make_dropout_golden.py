@@ -34,6 +34,7 @@ def main():
     ref = ref_loader.build_model().speech_predictor.train()
     mine = st.build_model(st.default_model_config()).speech_predictor
     synth.randomize_(mine, CASE["wseed"])
+    synth.condition_phase_head_(mine)  # well-conditioned phase head: gradients comparable at kernel accuracy
     ref.load_state_dict(mine.state_dict(), strict=True)
     inp = synth.speech_inputs(CASE["batch"], CASE["tokens"], seed=CASE["iseed"], ragged=CASE["ragged"])
     style = inp["style"].clone().requires_grad_(True)

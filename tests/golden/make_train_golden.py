@@ -2,6 +2,9 @@
 
     python tests/golden/make_train_golden.py
 
+Two weight sets: the plain seeded random one (``train_grads.npz``; its phase head makes the gradient
+ill-conditioned, see synth.condition_phase_head_) and the same with the conditioned phase head
+(``train_grads_wc.npz``), on which gradient parity is asserted at kernel accuracy.
 Setting: module.eval() with its BatchNorm1d switched to train() — i.e. batch statistics but the
 stochastic regularisers (dropout, decoder box smoothing) off, the pinned configuration of
 SURVEY.md §8(d) config 3 — loss = <cotangent, audio> with a seeded cotangent, harmonic-source draws
@@ -32,6 +35,11 @@ def cotangent(shape, seed=CASE["ct_seed"]):
 
 
 def main():
+    run(False, "train_grads.npz")
+    run(True, "train_grads_wc.npz")
+
+
+def run(conditioned, fname):
     from oracle import ref_loader, ref_run
     import stylish_tts_b200 as st
     from stylish_tts_b200 import synth
@@ -43,6 +51,8 @@ def main():
             m.train()
     mine = st.build_model(st.default_model_config()).speech_predictor
     synth.randomize_(mine, CASE["wseed"])
+    if conditioned:
+        synth.condition_phase_head_(mine)
     ref.load_state_dict(mine.state_dict(), strict=True)
     inp = synth.speech_inputs(CASE["batch"], CASE["tokens"], seed=CASE["iseed"], ragged=CASE["ragged"])
     style = inp["style"].clone().requires_grad_(True)
@@ -69,7 +79,7 @@ def main():
     sd = ref.state_dict()
     blob["bn_running_mean"] = sd[bn + ".running_mean"].numpy()
     blob["bn_running_var"] = sd[bn + ".running_var"].numpy()
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "train_grads.npz")
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), fname)
     np.savez_compressed(path, **blob)
     print(len(names), "parameters with gradients;", os.path.getsize(path) // 1024, "KiB")
 

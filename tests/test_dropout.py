@@ -70,22 +70,22 @@ def oracle_grads(sp, inp, dtype, prior=None):
 
 def test_oracle_with_masks_matches_reference_in_train_mode():
     gold = load_gold()
-    sp, inp = case()
+    sp, inp = case(wc=True)
     audio, grads, dins, used = oracle_grads(sp, inp, torch.float32)
     assert used == [s for s, _ in do.speech_predictor_sites()]  # same sites, same order as the reference
     assert rel_l2(audio, torch.from_numpy(gold["audio"])) < 1e-5
     for k in ("style", "pitch", "energy"):
-        assert rel_l2(dins[k], torch.from_numpy(gold["d_" + k])) < 5e-3, k
+        assert rel_l2(dins[k], torch.from_numpy(gold["d_" + k])) < 1e-4, k
     names = [str(n) for n in gold["names"]]
     assert sorted(grads) == sorted(names)
     scale = float(np.sqrt((gold["norms"] ** 2).sum()))
     for n, norm, dot in zip(names, gold["norms"], gold["dots"]):
         gr = grads[n]
-        assert abs(float(gr.norm()) - norm) <= 1e-2 * norm + 1e-6 * scale, (n, float(gr.norm()), norm)
+        assert abs(float(gr.norm()) - norm) <= 2e-4 * norm + 1e-6 * scale, (n, float(gr.norm()), norm)
         mine = float((gr * probe(n, gr.shape)).sum())
-        assert abs(mine - dot) <= 2e-2 * norm + 1e-6 * scale, (n, mine, dot, norm)
+        assert abs(mine - dot) <= 4e-4 * norm + 1e-6 * scale, (n, mine, dot, norm)
     # and the regularisers do change the result: the deterministic golden differs
-    det = np.load(util.GOLDEN_DIR + "/train_grads.npz")["audio"]
+    det = np.load(util.GOLDEN_DIR + "/train_grads_wc.npz")["audio"]
     assert rel_l2(torch.from_numpy(det), torch.from_numpy(gold["audio"])) > 1e-2
 
 
@@ -164,7 +164,7 @@ def test_gpu_train_mode_graph_matches_oracle_and_reference():
     from stylish_tts_b200 import engine as E
 
     gold = load_gold()
-    sp, inp = case()
+    sp, inp = case(wc=True)  # conditioned phase head: gradients comparable at kernel accuracy
     taps = {}
     with torch.no_grad():
         so.speech_predictor(util.state_dict_of(sp), inp["texts"], inp["text_lengths"], inp["alignment"], inp["pitch"],
@@ -205,17 +205,18 @@ def test_gpu_train_mode_graph_matches_oracle_and_reference():
     assert rel_l2(audio, audio_ref) < 5e-4, rel_l2(audio, audio_ref)
     assert rel_l2(audio, torch.from_numpy(gold["audio"])) < 5e-4
     for k, t in (("style", style), ("pitch", pitch), ("energy", energy)):
-        assert rel_l2(t.grad, dins_ref[k]) < 3e-2, (k, rel_l2(t.grad, dins_ref[k]))
+        print("train-mode input gradient", k, rel_l2(t.grad, dins_ref[k]))
+        assert rel_l2(t.grad, dins_ref[k]) < 1e-4, (k, rel_l2(t.grad, dins_ref[k]))  # measured 5-9e-6
     params = dict(sp.named_parameters())
     tot = torch.cat([params[n].grad.flatten().double().cpu() for n in grads_ref])
     tot_ref = torch.cat([grads_ref[n].flatten() for n in grads_ref])
     print("train-mode parameter gradients vs fp64 oracle:", rel_l2(tot, tot_ref))
-    assert rel_l2(tot, tot_ref) < 3e-2
+    assert rel_l2(tot, tot_ref) < 1e-4  # measured 7e-6
     # text-encoder / conformer parameters sit right behind the dropout sites
     for n in ("text_encoder.encoder.attn_layers.3.conv_q.weight", "text_encoder.encoder.ffn_layers.5.conv_2.weight",
               "text_encoder.prenet.conv_layers.1.weight", "generator.amp_conformer.layers.0.ff1.fn.fn.net.0.weight",
               "generator.amp_conformer.layers.0.conv.net.6.weight"):
-        assert rel_l2(params[n].grad, grads_ref[n]) < 5e-2, (n, rel_l2(params[n].grad, grads_ref[n]))
+        assert rel_l2(params[n].grad, grads_ref[n]) < 1e-3, (n, rel_l2(params[n].grad, grads_ref[n]))
 
 
 @pytest.mark.gpu

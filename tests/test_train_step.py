@@ -21,14 +21,18 @@ from tests.util import rel_l2
 BN = "generator.amp_conformer.layers.0.conv.net.4"
 
 
-def load_gold():
-    z = np.load(util.GOLDEN_DIR + "/train_grads.npz")
+def load_gold(wc=False):
+    z = np.load(util.GOLDEN_DIR + ("/train_grads_wc.npz" if wc else "/train_grads.npz"))
     return {k: z[k] for k in z.files}
 
 
-def case():
+def case(wc=False):
+    """wc: well-conditioned phase head (synth.condition_phase_head_) — gradients comparable at kernel accuracy;
+    plain: purely random weights, where atan2 at |X| ~ 0 makes the gradient itself ill-conditioned in fp32."""
     sp = st.build_model(st.default_model_config()).speech_predictor
     synth.randomize_(sp, CASE["wseed"])
+    if wc:
+        synth.condition_phase_head_(sp)
     inp = synth.speech_inputs(CASE["batch"], CASE["tokens"], seed=CASE["iseed"], ragged=CASE["ragged"])
     return sp, inp
 
@@ -51,16 +55,18 @@ def oracle_grads(sp, inp, dtype, prior=None):
     return audio.detach(), grads, dict(style=style.grad, pitch=pitch.grad, energy=energy.grad), taps
 
 
-def test_oracle_gradients_match_reference_golden():
-    gold = load_gold()
-    sp, inp = case()
+@pytest.mark.parametrize("wc", [False, True])
+def test_oracle_gradients_match_reference_golden(wc):
+    gold = load_gold(wc)
+    sp, inp = case(wc)
     audio, grads, dins, _ = oracle_grads(sp, inp, torch.float32)
     assert rel_l2(audio, torch.from_numpy(gold["audio"])) < 1e-5
-    # two fp32 evaluations of the same graph: the gradient itself is conditioned at the 1e-2 level
-    # in fp32 with random weights (fp32 vs fp64 of the reference's own formula: 1.5e-2, see
-    # test_gpu_gradients_match_oracle_and_reference), different but valid summation orders give ~2e-3
+    # plain weights: two fp32 evaluations of the same graph; the gradient itself is conditioned at the 1e-2 level
+    # (fp32 vs fp64 of the reference's own formula: 1.5e-2), different but valid summation orders give ~2e-3.
+    # conditioned phase head: that difference is 3e-6, so the bounds are 50x tighter.
+    t_in, t_norm, t_dot = (1e-4, 2e-4, 4e-4) if wc else (5e-3, 1e-2, 2e-2)
     for k in ("style", "pitch", "energy"):
-        assert rel_l2(dins[k], torch.from_numpy(gold["d_" + k])) < 5e-3, k
+        assert rel_l2(dins[k], torch.from_numpy(gold["d_" + k])) < t_in, (k, rel_l2(dins[k], torch.from_numpy(gold["d_" + k])))
     names = [str(n) for n in gold["names"]]
     assert sorted(grads) == sorted(names)
     scale = float(np.sqrt((gold["norms"] ** 2).sum()))
@@ -68,19 +74,20 @@ def test_oracle_gradients_match_reference_golden():
     # what either implementation returns there is rounding noise, hence the absolute floor
     for n, norm, dot in zip(names, gold["norms"], gold["dots"]):
         gr = grads[n]
-        assert abs(float(gr.norm()) - norm) <= 1e-2 * norm + 1e-6 * scale, (n, float(gr.norm()), norm)
+        assert abs(float(gr.norm()) - norm) <= t_norm * norm + 1e-6 * scale, (n, float(gr.norm()), norm)
         mine = float((gr * probe(n, gr.shape)).sum())
-        assert abs(mine - dot) <= 2e-2 * norm + 1e-6 * scale, (n, mine, dot, norm)
+        assert abs(mine - dot) <= t_dot * norm + 1e-6 * scale, (n, mine, dot, norm)
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("wc", [True, False])
 @pytest.mark.parametrize("tensor_cores", [False, True])
-def test_gpu_gradients_match_oracle_and_reference(tensor_cores, monkeypatch):
+def test_gpu_gradients_match_oracle_and_reference(tensor_cores, wc, monkeypatch):
     from stylish_tts_b200 import engine as E
 
     monkeypatch.setattr(E, "USE_UMMA", tensor_cores)
-    gold = load_gold()
-    sp, inp = case()
+    gold = load_gold(wc)
+    sp, inp = case(wc)
     # prior from the fp32 oracle forward, injected identically into both arms
     taps = {}
     with torch.no_grad():
@@ -109,8 +116,16 @@ def test_gpu_gradients_match_oracle_and_reference(tensor_cores, monkeypatch):
     # tensor-core convs (forward error 9e-5 instead of 3e-5) = 6.5e-2.  The amplitude branch, which does not
     # pass through atan2, agrees to 1e-4 in both modes, and every primitive holds 2e-4 on its own
     # (tests/test_gpu_train_ops.py).
-    GRAD_TOL = 0.15 if tensor_cores else 3e-2
+    # Run-to-run (atomic accumulation order) the plain case moves between 1.8e-2 and 3.5e-2 (FMA) / 0.09-0.12
+    # (bf16x3): its bounds only say "same gradient up to the conditioning of the test problem".  The conditioned
+    # phase head (wc) removes the amplification — fp32 vs fp64 of the reference formula is then 3e-6 — and the
+    # same comparison holds at kernel accuracy.
+    if wc:
+        GRAD_TOL = 3e-4 if tensor_cores else 1e-4  # measured 3.1e-5 / 6.9e-6 over all 12.9 M gradients
+    else:
+        GRAD_TOL = 0.25 if tensor_cores else 6e-2
     for k, t in (("style", style), ("pitch", pitch), ("energy", energy)):
+        print("input gradient", k, rel_l2(t.grad, dins_ref[k]))
         assert rel_l2(t.grad, dins_ref[k]) < GRAD_TOL, (k, rel_l2(t.grad, dins_ref[k]))
     params = dict(sp.named_parameters())
     errs = {}
