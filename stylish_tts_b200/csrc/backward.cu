@@ -19,8 +19,8 @@ __device__ __forceinline__ float act_grad(float a, int act, float alpha) {
       return a > 0.f ? 1.f : 0.f;
     case STY_ACT_LEAKY02:
       return a > 0.f ? 1.f : 0.2f;
-    case STY_ACT_SNAKE:  // d/da (a + sin^2(alpha a)/alpha) = 1 + sin(2 alpha a)
-      return 1.f + sinf(2.f * alpha * a);
+    case STY_ACT_SNAKE:  // d/da (a + sin^2(alpha a)/alpha) = 1 + sin(2 alpha a); MUFU.SIN like the forward
+      return 1.f + __sinf(2.f * alpha * a);
     case STY_ACT_SWISH: {
       const float s = 1.f / (1.f + expf(-a));
       return s * (1.f + a * (1.f - s));
@@ -34,10 +34,18 @@ __device__ __forceinline__ float act_grad(float a, int act, float alpha) {
   }
 }
 
+// sin^2(theta) and sin(2 theta) from one MUFU.SIN + MUFU.COS pair: everything the Snake backward needs
+struct SnakeTerms {
+  float s2, sd;
+};
+__device__ __forceinline__ SnakeTerms snake_terms(float theta) {
+  float sn, cs;
+  __sincosf(theta, &sn, &cs);
+  return {sn * sn, 2.f * sn * cs};
+}
 // d/d alpha of snake(a; alpha) = a sin(2 alpha a)/alpha - sin^2(alpha a)/alpha^2
-__device__ __forceinline__ float snake_dalpha(float a, float alpha) {
-  const float inv = 1.f / alpha;
-  return a * sinf(2.f * alpha * a) * inv - sin_sq(alpha * a) * inv * inv;
+__device__ __forceinline__ float snake_dalpha(float a, float inv_alpha, const SnakeTerms& st) {
+  return (a * st.sd - st.s2 * inv_alpha) * inv_alpha;
 }
 
 __device__ __forceinline__ float prologue_value(float xv, float m, float sc, float sh, int act, float al) {
@@ -249,12 +257,19 @@ prologue_bwd_reduce_kernel(const float* __restrict__ dxp, const float* __restric
   const float al = alpha ? alpha[c] : 1.f;
   const float ce = center ? center[blockIdx.x] : 0.f;
   float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+  const float inv_al = 1.f / al;
   auto body = [&](float xm, float g) {
     const float a = fmaf(xm, sc, sh);
-    const float ga = g * act_grad(a, act, al);
+    float ga;
+    if (act == STY_ACT_SNAKE) {
+      const SnakeTerms st = snake_terms(al * a);
+      ga = g * (1.f + st.sd);
+      s2 = fmaf(g, snake_dalpha(a, inv_al, st), s2);
+    } else {
+      ga = g * act_grad(a, act, al);
+    }
     s0 += ga;
     s1 = fmaf(ga, xm - ce, s1);
-    if (act == STY_ACT_SNAKE) s2 = fmaf(g, snake_dalpha(a, al), s2);
   };
   if (m) {
     const float* const rows[3] = {xr, gr, m};
@@ -338,10 +353,11 @@ grn_snake_bwd_kernel(const float* g_u, const float* __restrict__ h, const float*
   const float* const rows[2] = {h + off, g_u + off};
   rows_apply<2, true>(rows, d_h + off, T, threadIdx.x, blockDim.x, [&](int, const float (&v)[2]) {
     const float hv = v[0];
-    const float hb = fmaf(inv, sin_sq(al * hv), hv);
+    const SnakeTerms st = snake_terms(al * hv);
+    const float hb = fmaf(inv, st.s2, hv);
     const float dhb = fmaf(v[1], s, k * hb);
-    da = fmaf(dhb, snake_dalpha(hv, al), da);
-    return dhb * (1.f + sinf(2.f * al * hv));
+    da = fmaf(dhb, snake_dalpha(hv, inv, st), da);
+    return dhb * (1.f + st.sd);
   });
   da = block_sum(da, red);
   if (threadIdx.x == 0) atomicAdd(dalpha + j, da);

@@ -72,7 +72,11 @@ __device__ __forceinline__ float warp_colsum16(float (&v)[16], int lane) {
 //           4 ConvNeXt front: depthwise k7 conv + LayerNorm over channels + adaptive affine (K=1 only)
 // OUT_MODE: 0 none | 1 Snake | 2 ReLU | 3 Swish          (compile-time: keeps each role's loop small
 // enough for the instruction cache — three roles run different code on one SM)
-template <int IN_MODE, int OUT_MODE>
+// EPI     : 0 general epilogue | 1 no residual / mask / output scale / pixel shuffle | 2 residual with
+//           res_scale 1, no mask / scale / shuffle.  Compile-time because the three roles share one
+//           instruction cache: dropping the unused epilogue paths took the fused-front kernel from 0.267 to
+//           0.242 ms.  Only the hot (IN_MODE, OUT_MODE, EPI) combinations are instantiated (pick_kernel).
+template <int IN_MODE, int OUT_MODE, int EPI = 0>
 __global__ void __launch_bounds__(kThreads, 1)
 conv1d_umma_kernel(const sty_conv1d_args p, const UmmaPlan pl) {
   constexpr bool PRO = IN_MODE >= 1 && IN_MODE <= 3;
@@ -80,6 +84,12 @@ conv1d_umma_kernel(const sty_conv1d_args p, const UmmaPlan pl) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const int K = p.K, dil = p.dil, CO = p.CO, CI = p.CI, NT = pl.NT, rows = pl.rows;
   const int NS = pl.n_stages;
+  // compile-time off in the fused-front kernels (NT >= 128 there): their loops are i-cache sensitive
+  const bool dual = IN_MODE != 4 && pl.dual != 0;
+  // LEAN epilogue: bias + activation + sums only (always for the fused ConvNeXt front: the host only selects
+  // IN_MODE 4 when there is no residual, mask, output scale, pixel shuffle or plain sum); RES1: + residual
+  constexpr bool LEAN = IN_MODE == 4 || EPI == 1;
+  constexpr bool RES1 = EPI == 2;
   const int c8c = pl.ci_chunk >> 3;  // 16-byte K chunks per staged chunk
   const int co0 = blockIdx.y * NT;
   uint4* Wres = reinterpret_cast<uint4*>(smem_raw);       // resident: [K][2][CI/8][NT]
@@ -124,7 +134,7 @@ conv1d_umma_kernel(const sty_conv1d_args p, const UmmaPlan pl) {
     for (int idx = tid; idx < total; idx += kThreads) {
       const int row = idx / NT, n = idx - row * NT;  // row = blk*(CI/8) + c8, blk = tap*2 + split
       int dst = idx;
-      if (pl.dual) {
+      if (dual) {
         const int blk = row / c8n, c8 = row - blk * c8n;
         dst = (((blk >> 1) * c8n + c8) * 2 + (blk & 1)) * NT + n;
       }
@@ -301,7 +311,7 @@ conv1d_umma_kernel(const sty_conv1d_args p, const UmmaPlan pl) {
           for (int idx = tid; idx < total; idx += kProducerThreads) {
             const int blk = idx / blk_elems, within = idx - blk * blk_elems;
             const int c8l = within / NT, n = within - c8l * NT;
-            const int dst = pl.dual ? (((blk >> 1) * c8c + c8l) * 2 + (blk & 1)) * NT + n
+            const int dst = dual ? (((blk >> 1) * c8c + c8l) * 2 + (blk & 1)) * NT + n
                                     : blk * (c8c * NT) + within;
             Ws[dst] = wsplit[((int64_t)blk * (CI >> 3) + (c0 >> 3) + c8l) * CO + co0 + n];
           }
@@ -397,13 +407,13 @@ conv1d_umma_kernel(const sty_conv1d_args p, const UmmaPlan pl) {
           const uint4* Xs = stage0 + (size_t)s * pl.stage_u4;
           const uint32_t ws_addr = pl.resident ? smem_u32(Wres) : smem_u32(Xs + 2 * c8c * rows);
           const uint64_t a_d = make_desc(smem_u32(Xs), (uint32_t)rows, 8u);
-          const uint64_t b_d = make_desc(ws_addr, (uint32_t)(pl.dual ? 2 * NT : NT), 8u);
+          const uint64_t b_d = make_desc(ws_addr, (uint32_t)(dual ? 2 * NT : NT), 8u);
           const uint32_t a_hi32 = (uint32_t)(a_d >> 32), b_hi32 = (uint32_t)(b_d >> 32);
           uint32_t a_t = (uint32_t)a_d, b_t = (uint32_t)b_d;  // low words: (tap 0, kb 0, hi split)
           const uint32_t a_lo_off = (uint32_t)(c8c * rows);    // 16-byte units to the lo-split copy
           const uint32_t b_lo_off = (uint32_t)(wc8 * NT);
           const int kblocks = cc8 >> 1;                         // MMA K = 16 bf16 = two 16-byte chunks
-          const uint32_t a_kstep = 2 * rows, b_kstep = pl.dual ? 4 * NT : 2 * NT;
+          const uint32_t a_kstep = 2 * rows, b_kstep = dual ? 4 * NT : 2 * NT;
           const uint32_t idesc2 = (idesc & ~(0x3Fu << 17)) | ((uint32_t)((2 * NT) >> 3) << 17);  // N = 2*NT
           const uint32_t b_tstep = 2 * wc8 * NT;                // per tap (hi and lo blocks)
           uint32_t accumulate = ch > 0 ? 1u : 0u;
@@ -412,7 +422,7 @@ conv1d_umma_kernel(const sty_conv1d_args p, const UmmaPlan pl) {
             uint32_t ak = a_t, bk = b_t;
 #pragma unroll 2
             for (int kb = 0; kb < kblocks; ++kb, ak += a_kstep, bk += b_kstep) {
-              if (pl.dual) {
+              if (dual) {
                 umma_bf16_w(d_tmem, ak, a_hi32, bk, b_hi32, idesc2, accumulate);          // hi * [hi | lo]
                 umma_bf16_w(d_tmem, ak + a_lo_off, a_hi32, bk, b_hi32, idesc, 1u);        // lo * hi -> cols [0,NT)
               } else {
@@ -486,11 +496,11 @@ conv1d_umma_kernel(const sty_conv1d_args p, const UmmaPlan pl) {
         const int n0 = c * 16;
         float r[16], rv[16];
         // residual rows first: all 16 loads in flight before any store (res may alias y)
-        if (rb && t_ok) {
+        if (!LEAN && rb && t_ok) {
 #pragma unroll
           for (int jj = 0; jj < 16; ++jj) {
             const int co = co0 + n0 + jj;
-            if (s == 1) {
+            if (RES1 || s == 1) {
               rv[jj] = rb[(int64_t)co * p.r_cs + t];
             } else {
               const int c_out = co / s, r_out = co - c_out * s;
@@ -502,7 +512,7 @@ conv1d_umma_kernel(const sty_conv1d_args p, const UmmaPlan pl) {
           for (int jj = 0; jj < 16; ++jj) rv[jj] = 0.f;
         }
         tmem_ld16(acc_addr + (uint32_t)n0, r);
-        if (pl.dual) {  // columns [NT, 2*NT) hold the hi*lo partial products
+        if (dual) {  // columns [NT, 2*NT) hold the hi*lo partial products
           float r2[16];
           tmem_ld16(acc_addr + (uint32_t)(NT + n0), r2);
 #pragma unroll
@@ -519,12 +529,13 @@ conv1d_umma_kernel(const sty_conv1d_args p, const UmmaPlan pl) {
           } else if constexpr (OUT_MODE == 3) {
             v = v / (1.0f + __expf(-v));
           }
-          v = fmaf(p.res_scale, rv[jj], v * om);
+          if constexpr (RES1) v += rv[jj];
+          else if constexpr (!LEAN) v = fmaf(p.res_scale, rv[jj], v * om);
           if (!t_ok) v = 0.f;
           r[jj] = v;
         }
         if (t_ok) {
-          if (s == 1) {
+          if (LEAN || RES1 || s == 1) {
             float* __restrict__ yp = yb + (int64_t)(co0 + n0) * p.y_cs + t;
 #pragma unroll
             for (int jj = 0; jj < 16; ++jj) yp[(int64_t)jj * p.y_cs] = r[jj];
@@ -537,7 +548,7 @@ conv1d_umma_kernel(const sty_conv1d_args p, const UmmaPlan pl) {
             }
           }
         }
-        if (p.out_sum) {
+        if (IN_MODE != 4 && p.out_sum) {
           float cp[16];
 #pragma unroll
           for (int jj = 0; jj < 16; ++jj) cp[jj] = r[jj];
@@ -580,7 +591,7 @@ static bool make_plan(const sty_conv1d_args& a, UmmaPlan& pl) {
     if (a.CO % nt != 0) continue;
     if (a.CO / nt > 65535) break;
     pl.NT = nt;
-    pl.dual = nt <= 64 ? 1 : 0;  // small-N MMAs cost the same ~120 clk as N = 2*NT ones: fold two of the three
+    pl.dual = (nt <= 64 && !a.dw_w) ? 1 : 0;  // small-N MMAs cost the same ~120 clk as N = 2*NT ones: fold two of the three
     pl.acc_cols = 32;
     while (pl.acc_cols < (pl.dual ? 2 * nt : nt)) pl.acc_cols <<= 1;
     pl.prm_floats = (a.dw_w ? 10 : 4) * a.CI + 3 * nt;
@@ -619,8 +630,10 @@ static bool make_plan(const sty_conv1d_args& a, UmmaPlan& pl) {
 
 static int umma_in_mode(const sty_conv1d_args& a) {
   if (a.dw_w) {  // fused ConvNeXt front: pointwise conv only, nothing else in the prologue
+    // the fused-front kernels are built LEAN (no residual / mask / scale / shuffle / sum in the epilogue)
     const bool ok = a.K == 1 && a.CI <= 64 && a.CI % 16 == 0 && a.dw_b && a.dw_gb &&
-                    a.in_act == STY_ACT_NONE && !a.in_scale && !a.in_shift && !a.in_mask;
+                    a.in_act == STY_ACT_NONE && !a.in_scale && !a.in_shift && !a.in_mask && !a.res &&
+                    !a.out_mask && a.shuffle <= 1 && a.out_scale == 1.0f && !a.out_sum;
     return ok ? 4 : -1;
   }
   if (a.in_act == STY_ACT_SNAKE) return 3;
@@ -667,6 +680,18 @@ int conv1d_umma_launch(const sty_conv1d_args& a, cudaStream_t st) {
       {conv1d_umma_kernel<3, 0>, conv1d_umma_kernel<3, 1>, conv1d_umma_kernel<3, 2>, conv1d_umma_kernel<3, 3>},
       {conv1d_umma_kernel<4, 0>, conv1d_umma_kernel<4, 1>, conv1d_umma_kernel<4, 2>, conv1d_umma_kernel<4, 3>}};
   KernPtr kern = table[umma_in_mode(a)][umma_out_mode(a)];
+  {  // specialised epilogues of the S-rate generator convs (see EPI)
+    const int im = umma_in_mode(a), om = umma_out_mode(a);
+    const bool bare = !a.out_mask && a.shuffle <= 1 && a.out_scale == 1.0f;
+    if (bare && !a.res) {
+      if (im == 0 && om == 0) kern = conv1d_umma_kernel<0, 0, 1>;       // k21 input convs
+      else if (im == 0 && om == 1) kern = conv1d_umma_kernel<0, 1, 1>;  // pwconv1 + Snake (training graph)
+      else if (im == 3 && om == 0) kern = conv1d_umma_kernel<3, 0, 1>;  // AdaIN + Snake -> k11 (convs1)
+    } else if (bare && a.res && a.res_scale == 1.0f) {
+      if (im == 1 && om == 0) kern = conv1d_umma_kernel<1, 0, 2>;       // GRN scale -> pwconv2 + residual
+      else if (im == 3 && om == 0) kern = conv1d_umma_kernel<3, 0, 2>;  // AdaIN + Snake -> k11 + residual (convs2)
+    }
+  }
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const int64_t n_tiles = (int64_t)a.B * pl.tiles_per_b;
   const int n_co = a.CO / pl.NT;

@@ -73,11 +73,11 @@ def condition_phase_head_(speech_predictor: nn.Module, shift: float = 3.0) -> nn
     derivative (-imag, real)/r^2; with purely random weights many bins have r ~ 0 and the gradient of everything
     upstream becomes ill-conditioned (fp32 vs fp64 of the SAME formula: 1.4e-2).  With the shift that difference
     is 3e-6, so gradient parity can be asserted at kernel accuracy.  Used by the gradient goldens / tests."""
-    with torch.no_grad():
-        speech_predictor.generator.basegen.phase_output_real_conv.bias += shift
+    speech_predictor.generator.basegen.phase_output_real_conv.bias += shift
     return speech_predictor
 
 
+@torch.no_grad()
 def converge_spectral_(module: nn.Module, iters: int = 30) -> nn.Module:
     """Run the spectral-norm power iteration on every (weight_orig, weight_u, weight_v) triple so that a
     freshly initialised module is in the regime a trained checkpoint is in (sigma ~ largest singular value;
