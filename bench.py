@@ -231,6 +231,7 @@ def measure_train(args, dev, world, rank, barrier, steps, warmup, batch):
     synth.randomize_(sp, 0)
     synth.converge_spectral_(se)
     sp, se = sp.to(dev).train(), se.to(dev).train()
+    sp.regulariser_seed = rank  # train() mode: dropout masks differ between the data-parallel ranks
     # acoustic stage: speech_predictor + speech_style_encoder are trained (stage_type.py:393-410)
     opt = optim.FlatAdamW(list(sp.parameters()) + list(se.parameters()), lr=1e-4, betas=(0.85, 0.99), eps=1e-9,
                           weight_decay=1e-4, world_size=world)
