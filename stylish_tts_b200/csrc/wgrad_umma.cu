@@ -62,14 +62,19 @@ struct SideDesc {
 // step) cells; a thread first issues the global loads of up to U items (32 loads in flight — staging is
 // latency-bound otherwise), then transforms, splits and stores them.  (g, row) of successive items is stepped
 // incrementally — no integer division in the loop.
-template <bool IS_INPUT>
-__device__ __forceinline__ void stage_side(const SideDesc& S, const sty_conv1d_wgrad_args& p, const float* prm,
-                                           int in_groups, int lt, int nthr) {
+// ACT : prologue activation known at compile time (STY_ACT_NONE, STY_ACT_SNAKE) or -1 = runtime switch.
+// FAST: no mask and every staged channel exists, so only the per-item time-range predicate is left.  The generic body executes ~45 instructions per element
+//       (ncu: 437 M warp instructions for 1.24 GB at 77 % i-cache hit rate, profiles/r01_ncu_full_wgrad_umma.txt);
+//       the specialised bodies are what the S-rate weight gradients run.
+template <bool IS_INPUT, int ACT, bool FAST>
+__device__ __forceinline__ void stage_side_t(const SideDesc& S, const sty_conv1d_wgrad_args& p, const float* prm,
+                                             int in_groups, int lt, int nthr) {
   constexpr int U = 4;  // 32 loads in flight per thread (6 measured slower)
   const int n_items = S.groups * S.rows;
   const int g_step = nthr / S.rows, r_step = nthr - g_step * S.rows;
   int g = lt / S.rows, row = lt - g * S.rows;
-  const bool chan_full = S.c0 + S.groups * 8 <= S.C;  // every staged channel exists: no per-channel checks
+  const bool chan_full = FAST || S.c0 + S.groups * 8 <= S.C;  // every staged channel exists: no per-channel checks
+  const int act = ACT >= 0 ? ACT : p.in_act;
   for (int i0 = lt; i0 < n_items; i0 += nthr * U) {
     float v[U][8];
     int gg[U], rr[U];
@@ -78,7 +83,8 @@ __device__ __forceinline__ void stage_side(const SideDesc& S, const sty_conv1d_w
       gg[u] = g;
       rr[u] = row;
       const int t = S.t_start + row;
-      const bool ok = (i0 + u * nthr) < n_items && row < S.valid_rows && t >= 0 && t < p.T;
+      const bool in_items = (i0 + u * nthr) < n_items;
+      const bool ok = in_items && row < S.valid_rows && t >= 0 && t < p.T;
       const float* __restrict__ src = S.src + (int64_t)(S.c0 + g * 8) * S.cs + t;
 #pragma unroll
       for (int j = 0; j < 8; ++j)
@@ -95,7 +101,7 @@ __device__ __forceinline__ void stage_side(const SideDesc& S, const sty_conv1d_w
       if (i0 + u * nthr >= n_items) continue;
       const int t = S.t_start + rr[u];
       const bool ok = rr[u] < S.valid_rows && t >= 0 && t < p.T;
-      const float m = (ok && S.mask) ? S.mask[t] : 1.f;
+      const float m = (!FAST && ok && S.mask) ? S.mask[t] : 1.f;
       if (IS_INPUT) {
         const int cl = gg[u] * 8;
         float sc[8], sh[8], al[8];
@@ -103,14 +109,19 @@ __device__ __forceinline__ void stage_side(const SideDesc& S, const sty_conv1d_w
         *reinterpret_cast<float4*>(sc + 4) = *reinterpret_cast<const float4*>(prm + cl + 4);
         *reinterpret_cast<float4*>(sh) = *reinterpret_cast<const float4*>(prm + in_groups * 8 + cl);
         *reinterpret_cast<float4*>(sh + 4) = *reinterpret_cast<const float4*>(prm + in_groups * 8 + cl + 4);
-        if (p.in_act == STY_ACT_SNAKE) {
+        if (act == STY_ACT_SNAKE) {  // prm[2] = alpha, prm[3] = 1/alpha
           *reinterpret_cast<float4*>(al) = *reinterpret_cast<const float4*>(prm + 2 * in_groups * 8 + cl);
           *reinterpret_cast<float4*>(al + 4) = *reinterpret_cast<const float4*>(prm + 2 * in_groups * 8 + cl + 4);
         }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          float w = fmaf(v[u][j] * m, sc[j], sh[j]);
-          if (p.in_act != STY_ACT_NONE) w = wg_act(w, p.in_act, al[j]);
+          float w = fmaf(FAST ? v[u][j] : v[u][j] * m, sc[j], sh[j]);
+          if (act == STY_ACT_SNAKE) {
+            const float sn = __sinf(al[j] * w);
+            w += __fdividef(sn * sn, al[j]);
+          } else if (act != STY_ACT_NONE) {
+            w = act_apply(w, act);
+          }
           v[u][j] = (ok && (chan_full || S.c0 + cl + j < S.C)) ? w : 0.f;
         }
       } else {
@@ -129,6 +140,24 @@ __device__ __forceinline__ void stage_side(const SideDesc& S, const sty_conv1d_w
       S.dst[at] = make_uint4(h[0], h[1], h[2], h[3]);
       S.dst[S.groups * S.rows + at] = make_uint4(l[0], l[1], l[2], l[3]);
     }
+  }
+}
+
+template <bool IS_INPUT>
+__device__ __forceinline__ void stage_side(const SideDesc& S, const sty_conv1d_wgrad_args& p, const float* prm,
+                                           int in_groups, int lt, int nthr) {
+  const bool fast = !S.mask && S.c0 + S.groups * 8 <= S.C;
+  if (!IS_INPUT) {
+    if (fast) stage_side_t<false, STY_ACT_NONE, true>(S, p, prm, in_groups, lt, nthr);
+    else stage_side_t<false, STY_ACT_NONE, false>(S, p, prm, in_groups, lt, nthr);
+  } else if (p.in_act == STY_ACT_NONE && fast) {
+    stage_side_t<true, STY_ACT_NONE, true>(S, p, prm, in_groups, lt, nthr);
+  } else if (p.in_act == STY_ACT_SNAKE && fast) {
+    stage_side_t<true, STY_ACT_SNAKE, true>(S, p, prm, in_groups, lt, nthr);
+  } else if (p.in_act == STY_ACT_LEAKY02 && fast) {  // style-encoder ResBlk convs
+    stage_side_t<true, STY_ACT_LEAKY02, true>(S, p, prm, in_groups, lt, nthr);
+  } else {
+    stage_side_t<true, -1, false>(S, p, prm, in_groups, lt, nthr);
   }
 }
 
