@@ -172,24 +172,28 @@ int launch_wgrad(const sty_conv1d_wgrad_args& a, cudaStream_t st) {
 // out[c] += scale * sum_{b,t} mask[b,t] * x[b,c,t]
 __global__ void __launch_bounds__(256)
 channel_sum_kernel(const float* __restrict__ x, int64_t x_bs, int64_t x_cs, const float* __restrict__ mask,
-                   float* __restrict__ out, int T, float scale) {
+                   float* __restrict__ out, int B, int T, float scale) {
   __shared__ float red[32];
-  const int c = blockIdx.x, b = blockIdx.y;
-  const float* __restrict__ row = x + (int64_t)b * x_bs + (int64_t)c * x_cs;
-  const float* __restrict__ m = mask ? mask + (int64_t)b * T : nullptr;
+  const int c = blockIdx.x;
   float s = 0.f;
-  if (m) {
-    const float* const rows[2] = {row, m};
-    rows_apply<2, false>(rows, nullptr, T, threadIdx.x, blockDim.x, [&](int, const float (&v)[2]) {
-      s = fmaf(v[0], v[1], s);
-      return 0.f;
-    });
-  } else {
-    const float* const rows[1] = {row};
-    rows_apply<1, false>(rows, nullptr, T, threadIdx.x, blockDim.x, [&](int, const float (&v)[1]) {
-      s += v[0];
-      return 0.f;
-    });
+  // grid.y <= 64 blocks per channel walk the batch (the image convs of the style encoder have B ~ 2600 rows of
+  // T ~ 800: one block and one atomic per (b, c) row was 210 K blocks)
+  for (int b = blockIdx.y; b < B; b += gridDim.y) {
+    const float* row = x + (int64_t)b * x_bs + (int64_t)c * x_cs;
+    const float* m = mask ? mask + (int64_t)b * T : nullptr;
+    if (m) {
+      const float* const rows[2] = {row, m};
+      rows_apply<2, false>(rows, nullptr, T, threadIdx.x, blockDim.x, [&](int, const float (&v)[2]) {
+        s = fmaf(v[0], v[1], s);
+        return 0.f;
+      });
+    } else {
+      const float* const rows[1] = {row};
+      rows_apply<1, false>(rows, nullptr, T, threadIdx.x, blockDim.x, [&](int, const float (&v)[1]) {
+        s += v[0];
+        return 0.f;
+      });
+    }
   }
   s = block_sum(s, red);
   if (threadIdx.x == 0) atomicAdd(out + c, s * scale);
@@ -373,7 +377,7 @@ chan_layernorm_bwd_kernel(const float* __restrict__ xin, const float* __restrict
                           int g_plus_one, const float* __restrict__ dyin, const float* __restrict__ mask,
                           float* __restrict__ dvout, float* __restrict__ dgb, int64_t dg_bs, int C, int T,
                           float eps, int act) {
-  extern __shared__ float sacc[];  // [2*C]
+  extern __shared__ float sacc[];  // [2*C] sums, then per warp two [32][33] reduction tiles
   const int b = blockIdx.y;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
@@ -404,21 +408,39 @@ chan_layernorm_bwd_kernel(const float* __restrict__ xin, const float* __restrict
   }
   const float rstd = 1.f / sqrtf(q * invC + eps);
   float m1 = 0.f, m2 = 0.f;
-  for (int c = 0; c < C; ++c) {
-    float v = x[(int64_t)c * T];
-    if (res) v += res[(int64_t)c * T];
-    const float n = (v - mean) * rstd;
-    const float G = g_plus_one ? 1.f + g[c] : g[c];
-    float dz = ok ? dy[(int64_t)c * T] * m : 0.f;
-    if (act != STY_ACT_NONE) dz *= act_grad(fmaf(G, n, be[c]), act, 1.f);
-    const float dn = dz * G;
-    m1 += dn;
-    m2 = fmaf(dn, n, m2);
-    const float a = warp_sum(dz * n), bsum = warp_sum(dz);
-    if (lane == 0) {
-      atomicAdd(&sacc[c], a);
-      atomicAdd(&sacc[C + c], bsum);
+  // d(gamma), d(beta) need sums over t, i.e. over the lanes: per 32 channels every lane parks its two values in
+  // a padded [channel][lane] tile of shared memory and then sums ONE channel over the 32 lanes — 4 shared-memory
+  // operations per value instead of two 5-step shuffle reductions (20 instructions)
+  float* ta = sacc + 2 * C + (threadIdx.x >> 5) * (2 * 32 * 33);
+  float* tb = ta + 32 * 33;
+  for (int c0 = 0; c0 < C; c0 += 32) {
+    const int nc = min(32, C - c0);
+    for (int i = 0; i < nc; ++i) {
+      const int c = c0 + i;
+      float v = x[(int64_t)c * T];
+      if (res) v += res[(int64_t)c * T];
+      const float n = (v - mean) * rstd;
+      const float G = g_plus_one ? 1.f + g[c] : g[c];
+      float dz = ok ? dy[(int64_t)c * T] * m : 0.f;
+      if (act != STY_ACT_NONE) dz *= act_grad(fmaf(G, n, be[c]), act, 1.f);
+      const float dn = dz * G;
+      m1 += dn;
+      m2 = fmaf(dn, n, m2);
+      ta[i * 33 + lane] = dz * n;
+      tb[i * 33 + lane] = dz;
     }
+    __syncwarp();
+    if (lane < nc) {
+      float a = 0.f, bsum = 0.f;
+#pragma unroll 8
+      for (int l = 0; l < 32; ++l) {
+        a += ta[lane * 33 + l];
+        bsum += tb[lane * 33 + l];
+      }
+      atomicAdd(&sacc[c0 + lane], a);
+      atomicAdd(&sacc[C + c0 + lane], bsum);
+    }
+    __syncwarp();
   }
   m1 *= invC;
   m2 *= invC;
@@ -487,6 +509,65 @@ dwconv1d_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, i
   __syncthreads();
   for (int k = threadIdx.x; k < K; k += blockDim.x) atomicAdd(dw + c * K + k, sacc[k]);
   if (threadIdx.x == 0 && db) atomicAdd(db + c, sacc[KMAX]);
+}
+
+// Windowed variant for the S-rate ConvNeXt depthwise convs (K = 7 exactly): a thread owns R = 4 consecutive
+// time steps and loads the dy / x windows they share once (20 loads per 4 outputs instead of 56).
+template <int K, int PAD, int R>
+__global__ void __launch_bounds__(256)
+dwconv1d_bwd_win_kernel(const float* __restrict__ dy, const float* __restrict__ x, int64_t x_bs, int64_t x_cs,
+                        const float* __restrict__ w, float* __restrict__ dx, int64_t dx_bs, int64_t dx_cs,
+                        float* __restrict__ dw, float* __restrict__ db, int C, int T) {
+  static_assert(PAD >= 0 && PAD <= K - 1, "window layout");
+  constexpr int pad = PAD;
+  __shared__ float sacc[K + 1];
+  const int c = blockIdx.x, b = blockIdx.y;
+  const float* __restrict__ dr = dy + ((int64_t)b * C + c) * T;
+  const float* __restrict__ xr = x + (int64_t)b * x_bs + (int64_t)c * x_cs;
+  float* __restrict__ dxr = dx ? dx + (int64_t)b * dx_bs + (int64_t)c * dx_cs : nullptr;
+  for (int i = threadIdx.x; i <= K; i += blockDim.x) sacc[i] = 0.f;
+  __syncthreads();
+  float wk[K], aw[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    wk[k] = w[c * K + k];
+    aw[k] = 0.f;
+  }
+  float ab = 0.f;
+  constexpr int W = R + K - 1;
+  for (int t0 = threadIdx.x * R; t0 < T; t0 += blockDim.x * R) {
+    float wd[W], wx[W];
+    const int bd = t0 - (K - 1) + pad, bx = t0 - pad;
+#pragma unroll
+    for (int j = 0; j < W; ++j) {
+      const int ud = bd + j, ux = bx + j;
+      wd[j] = (ud >= 0 && ud < T) ? dr[ud] : 0.f;
+      wx[j] = (ux >= 0 && ux < T) ? xr[ux] : 0.f;
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const float g = wd[r + (K - 1) - PAD];  // dy[t0 + r] (0 beyond T)
+      ab += g;
+      float v = 0.f;
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        v = fmaf(wk[k], wd[r - k + (K - 1)], v);  // dy[t - k + pad]
+        aw[k] = fmaf(g, wx[r + k], aw[k]);        // x[t + k - pad]
+      }
+      if (dxr && t0 + r < T) dxr[t0 + r] = v;
+    }
+  }
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const float a = warp_sum(aw[k]);
+    if (lane == 0) atomicAdd(&sacc[k], a);
+  }
+  ab = warp_sum(ab);
+  if (lane == 0) atomicAdd(&sacc[K], ab);
+  __syncthreads();
+  for (int k = threadIdx.x; k < K; k += blockDim.x) atomicAdd(dw + c * K + k, sacc[k]);
+  if (threadIdx.x == 0 && db) atomicAdd(db + c, sacc[K]);
 }
 
 // ------------------------------------------------------------------ small elementwise backward
@@ -755,8 +836,8 @@ extern "C" int sty_conv1d_wgrad(const sty_conv1d_wgrad_args* a, sty_stream_t str
 extern "C" int sty_channel_sum(const float* x, int64_t x_bs, int64_t x_cs, const float* mask, float* out, int B,
                                int C, int T, float scale, sty_stream_t stream) {
   STY_REQUIRE(x && out && B > 0 && C > 0 && T > 0 && B <= 65535, "channel_sum: bad argument");
-  dim3 grid(C, B);
-  channel_sum_kernel<<<grid, 256, 0, as_stream(stream)>>>(x, x_bs, x_cs, mask, out, T, scale);
+  dim3 grid(C, B < 64 ? B : 64);
+  channel_sum_kernel<<<grid, 256, 0, as_stream(stream)>>>(x, x_bs, x_cs, mask, out, B, T, scale);
   STY_CHECK_LAUNCH("channel_sum");
   return STY_OK;
 }
@@ -846,7 +927,7 @@ extern "C" int sty_chan_layernorm_bwd(const float* x, const float* res, int64_t 
   STY_REQUIRE(x && gamma && beta && dy && dv && dgb && B > 0 && C > 0 && T > 0, "chan_layernorm_bwd: bad argument");
   STY_REQUIRE(act == STY_ACT_NONE || act == STY_ACT_RELU, "chan_layernorm_bwd: only none/relu epilogues");
   dim3 grid(cdiv(T, 128), B);
-  chan_layernorm_bwd_kernel<<<grid, 128, 2 * C * sizeof(float), as_stream(stream)>>>(
+  chan_layernorm_bwd_kernel<<<grid, 128, (2 * C + 4 * 2 * 32 * 33) * sizeof(float), as_stream(stream)>>>(
       x, res, x_bs, gamma, beta, g_bs, g_plus_one, dy, mask, dv, dgb, dg_bs, C, T, eps, act);
   STY_CHECK_LAUNCH("chan_layernorm_bwd");
   return STY_OK;
@@ -859,7 +940,9 @@ extern "C" int sty_dwconv1d_bwd(const float* dy, const float* x, int64_t x_bs, i
   STY_REQUIRE(B <= 65535, "dwconv1d_bwd: batch too large");
   dim3 grid(C, B);
   cudaStream_t st = as_stream(stream);
-  if (K <= 7)
+  if (K == 7 && pad_left == 3)
+    dwconv1d_bwd_win_kernel<7, 3, 4><<<grid, 256, 0, st>>>(dy, x, x_bs, x_cs, w, dx, dx_bs, dx_cs, dw, db, C, T);
+  else if (K <= 7)
     dwconv1d_bwd_kernel<7><<<grid, 256, 0, st>>>(dy, x, x_bs, x_cs, w, dx, dx_bs, dx_cs, dw, db, C, T, K, pad_left);
   else
     dwconv1d_bwd_kernel<31><<<grid, 256, 0, st>>>(dy, x, x_bs, x_cs, w, dx, dx_bs, dx_cs, dw, db, C, T, K, pad_left);
