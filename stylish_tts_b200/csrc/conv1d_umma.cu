@@ -587,7 +587,21 @@ static bool make_plan(const sty_conv1d_args& a, UmmaPlan& pl) {
   pl.tiles_per_b = cdiv(a.T, 128);
   // output-channel tile candidates: CO itself if <= 128, else multiple-of-16 divisors, largest first
   // (each epilogue thread keeps GRN partial sums for at most 8 of its 16-column chunks => NT <= 256)
-  for (int nt = a.CO <= 256 ? a.CO : 256; nt >= 16; nt -= 16) {
+  int nt_first = a.CO <= 256 ? a.CO : 256;
+  {
+    // few tiles (text-rate convs: 16 x 258 steps = 33 tiles): prefer narrower output-channel tiles while twice
+    // as many CTAs still fit on the SMs, instead of leaving three quarters of the GPU idle
+    const int64_t n_tiles = (int64_t)a.B * pl.tiles_per_b;
+    while (nt_first >= 32) {
+      while (nt_first >= 16 && a.CO % nt_first != 0) nt_first -= 16;
+      if (nt_first < 32 || n_tiles * (a.CO / nt_first) * 2 > 148) break;
+      int d = nt_first - 16;
+      while (d >= 16 && a.CO % d != 0) d -= 16;
+      if (d < 16) break;
+      nt_first = d;
+    }
+  }
+  for (int nt = nt_first; nt >= 16; nt -= 16) {
     if (a.CO % nt != 0) continue;
     if (a.CO / nt > 65535) break;
     pl.NT = nt;
