@@ -41,11 +41,6 @@ struct WgPlan {
   int valid_rows;  // rows of the M side that carry data: 128 + (K-1)*dil
 };
 
-__device__ __forceinline__ float wg_act(float w, int act, float al) {
-  if (act == STY_ACT_SNAKE) return fmaf(1.f / al, sin_sq(al * w), w);
-  return act_apply(w, act);
-}
-
 // One side of a chunk: `groups` 8-channel groups x `rows` time steps of the conv INPUT (prologue applied)
 // or of the output GRADIENT (mask * scale applied), written as bf16 hi | lo planes
 // dst[(split*groups + g)*rows + row].
