@@ -70,6 +70,7 @@ __device__ __forceinline__ void stage_side_t(const SideDesc& S, const sty_conv1d
   int g = lt / S.rows, row = lt - g * S.rows;
   const bool chan_full = FAST || S.c0 + S.groups * 8 <= S.C;  // every staged channel exists: no per-channel checks
   const int act = ACT >= 0 ? ACT : p.in_act;
+  const int64_t cs = S.cs;
   for (int i0 = lt; i0 < n_items; i0 += nthr * U) {
     float v[U][8];
     int gg[U], rr[U];
@@ -80,10 +81,12 @@ __device__ __forceinline__ void stage_side_t(const SideDesc& S, const sty_conv1d
       const int t = S.t_start + row;
       const bool in_items = (i0 + u * nthr) < n_items;
       const bool ok = in_items && row < S.valid_rows && t >= 0 && t < p.T;
-      const float* __restrict__ src = S.src + (int64_t)(S.c0 + g * 8) * S.cs + t;
+      const float* __restrict__ src = S.src + (int64_t)(S.c0 + g * 8) * cs + t;
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        v[u][j] = (ok && (chan_full || S.c0 + g * 8 + j < S.C)) ? src[(int64_t)j * S.cs] : 0.f;
+      for (int j = 0; j < 8; ++j) {  // running pointer: 2 integer instructions per load
+        v[u][j] = (ok && (chan_full || S.c0 + g * 8 + j < S.C)) ? *src : 0.f;
+        src += cs;
+      }
       row += r_step;
       g += g_step;
       if (row >= S.rows) {
