@@ -512,11 +512,19 @@ conv1d_umma_kernel(const sty_conv1d_args p, const UmmaPlan pl) {
         const int n0 = c * 16;
         float r[16], rv[16];
         // residual rows first: all 16 loads in flight before any store (res may alias y)
-        if (!LEAN && rb && t_ok) {
+        if (!LEAN && rb && t_ok && (RES1 || s == 1)) {
+          const float* __restrict__ rp = rb + (int64_t)(co0 + n0) * p.r_cs + t;  // running pointer, see producers
+          const int64_t r_cs = p.r_cs;
+#pragma unroll
+          for (int jj = 0; jj < 16; ++jj) {
+            rv[jj] = *rp;
+            rp += r_cs;
+          }
+        } else if (!LEAN && rb && t_ok) {
 #pragma unroll
           for (int jj = 0; jj < 16; ++jj) {
             const int co = co0 + n0 + jj;
-            if (RES1 || s == 1) {
+            if (s == 1) {
               rv[jj] = rb[(int64_t)co * p.r_cs + t];
             } else {
               const int c_out = co / s, r_out = co - c_out * s;
