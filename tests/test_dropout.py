@@ -46,6 +46,32 @@ def test_hash_statistics():
     assert big.dtype == np.bool_
 
 
+def test_hash_known_answers():
+    """pins the mask hash itself (common.cuh drop_keep == oracle/dropout_oracle.keep_mask): a change of either
+    side shows up here on CPU and in test_dropout_kernel_matches_numpy_mask on the GPU"""
+    kat = {
+        (SEED, 1, 0.5): [1, 0, 1, 1, 1, 1, 1, 0, 1, 1, 0, 0, 1, 1, 1, 0, 1, 1, 1, 0, 1, 0, 0, 0, 1, 1, 0, 0, 0, 1, 0, 1],
+        (SEED, 20, 0.2): [1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 0, 1, 1, 1, 1, 0, 0, 1, 1, 1, 1, 1, 0, 1, 1, 1, 1, 0],
+        (7, 3, 0.1): [1, 1, 0, 1, 1, 1, 1, 0, 1, 1, 1, 1, 1, 1, 1, 1],
+    }
+    for (seed, site, p), want in kat.items():
+        assert do.keep_mask(seed, site, len(want), p).astype(int).tolist() == want, (seed, site, p)
+    assert float(do.scale_mask(SEED, 1, (4,), 0.2)[0]) == pytest.approx(1.25, rel=1e-6)
+    assert do.keep_mask(SEED, 5, 1000, 0.0).all()
+
+
+def test_dropout_rng_sequence_is_reproducible():
+    from stylish_tts_b200.train_ops import DropoutRng
+
+    a, b = DropoutRng(3, "cpu"), DropoutRng(3, "cpu")
+    seq_a = [a.value] + [a.advance() for _ in range(4)]
+    seq_b = [b.value] + [b.advance() for _ in range(4)]
+    assert seq_a == seq_b and len(set(seq_a)) == 5
+    assert DropoutRng(4, "cpu").value != seq_a[0]
+    a.set(2 ** 64 - 1)  # stored as the two's-complement int64 the kernels read back as uint64
+    assert int(a.dev[0]) == -1 and a.value == 2 ** 64 - 1
+
+
 def oracle_grads(sp, inp, dtype, prior=None):
     sd = {k: (v.detach().clone().to(dtype).requires_grad_(True) if v.is_floating_point() else v.clone())
           for k, v in sp.state_dict().items()}
