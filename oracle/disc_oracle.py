@@ -36,6 +36,19 @@ def spec_discriminator(sd: SD, y) -> List[torch.Tensor]:
     return out
 
 
+def pitch_discriminator(sd: SD, y, kernel: int) -> List[torch.Tensor]:
+    """models/pitch_discriminator.py:7-68 — five weight-normed Conv1d (same padding) + LeakyReLU(0.1), each with its
+    own output conv; `pitch_disc` (dim_in 2, kernel 21: pitch & energy curves) and `dur_disc` (dim_in 1, kernel 5:
+    durations), models/models.py:81-82.  y: (B, dim_in, T) -> five (B, T) score maps"""
+    out = []
+    for i in range(5):
+        y = F.leaky_relu(F.conv1d(y, wn_weight(sd, f"discriminators.{i}"), sd[f"discriminators.{i}.bias"],
+                                  padding=kernel // 2), 0.1)
+        out.append(torch.flatten(F.conv1d(y, wn_weight(sd, f"out.{i}"), sd[f"out.{i}.bias"], padding=kernel // 2),
+                                 1, -1))
+    return out
+
+
 def _cf_block(sd: SD, prefix: str, x, *, kernel, stride=1, groups=1, bn_training=True):
     """ContextFreeBlock models/discriminator.py:94-116: Conv1d -> BatchNorm1d -> GELU(erf)"""
     x = F.conv1d(x, sd[prefix + ".net.0.weight"], sd.get(prefix + ".net.0.bias"), stride=stride,

@@ -56,13 +56,21 @@ def inputs():
     return tf, pf, ta, pa
 
 
+def curve_inputs():
+    g = torch.Generator().manual_seed(23)
+    return torch.randn(2, 2, 50, generator=g), 5 * torch.rand(2, 1, 18, generator=g)
+
+
 def build_reference():
     from oracle import ref_loader
     ref_loader.load()
     from stylish_tts.train.models.discriminator import SpecDiscriminator, ContextFreeDiscriminator
+    from stylish_tts.train.models.pitch_discriminator import PitchDiscriminator
     torch.manual_seed(SEED)
     mods = dict(mrd0=SpecDiscriminator(), mrd1=SpecDiscriminator(), mrd2=SpecDiscriminator(),
-                disc=ContextFreeDiscriminator())
+                disc=ContextFreeDiscriminator(),
+                pitch_disc=PitchDiscriminator(dim_in=2, dim_hidden=64, kernel=21),   # models.py:81-82
+                dur_disc=PitchDiscriminator(dim_in=1, dim_hidden=64, kernel=5))
     tables = {}
     for key, m in mods.items():
         sd = m.state_dict()
@@ -92,7 +100,13 @@ def main():
             for j, o in enumerate(outs):
                 blob[f"mrd{i}_out{j}"] = o.numpy()
         blob["disc_out"] = mods["disc"](ta)[0][0].numpy()
-    kw = dict(mrd0=mods["mrd0"], mrd1=mods["mrd1"], mrd2=mods["mrd2"], disc=mods["disc"], pitch=None, duration=None)
+        pc, du = curve_inputs()
+        for j, o in enumerate(mods["pitch_disc"](pc)[0]):
+            blob[f"pitch_disc_out{j}"] = o.numpy()
+        for j, o in enumerate(mods["dur_disc"](du)[0]):
+            blob[f"dur_disc_out{j}"] = o.numpy()
+    kw = dict(mrd0=mods["mrd0"], mrd1=mods["mrd1"], mrd2=mods["mrd2"], disc=mods["disc"], pitch=mods["pitch_disc"],
+              duration=mods["dur_disc"])
     gl, dl = GeneratorLoss(**kw), DiscriminatorLoss(**kw)
     args = dict(target_list=tf, pred_list=pf, target_audio=ta, pred_audio=pa, used=["mrd0", "mrd1", "mrd2", "disc"],
                 index=0)
@@ -103,6 +117,11 @@ def main():
     blob["gen_loss"] = np.array(float(g.detach()))
     blob["gen_d_pred_audio"] = pa_g.grad.numpy()
     blob["gen_d_pred_fft0"] = pf_g[0].grad.numpy()
+    pc, du = curve_inputs()
+    blob["pitch_gen_loss"] = np.array(float(gl(target_list=[pc], pred_list=[pc * 0.9 + 0.1], target_audio=None,
+                                               pred_audio=None, used=["pitch_disc"], index=0).detach()))
+    blob["dur_disc_loss"] = np.array(float(dl(target_list=[du], pred_list=[du * 1.1 - 0.2], target_audio=None,
+                                              pred_audio=None, used=["dur_disc"], index=0).detach()))
     d = dl(**args)
     for m in mods.values():
         m.zero_grad()

@@ -6,7 +6,7 @@ import torch
 
 from oracle import disc_oracle as do
 from tests import util
-from tests.golden.make_disc_golden import inputs, state_dict_from_table
+from tests.golden.make_disc_golden import curve_inputs, inputs, state_dict_from_table
 from tests.util import rel_l2
 
 
@@ -18,7 +18,7 @@ def gold():
 
 def sds_of(gold, grad=False):
     out = {}
-    for key in ("mrd0", "mrd1", "mrd2", "disc"):
+    for key in ("mrd0", "mrd1", "mrd2", "disc", "pitch_disc", "dur_disc"):
         sd = state_dict_from_table(gold[key + "_names"], gold[key + "_shapes"])
         if grad:
             sd = {k: (v.requires_grad_(True) if v.is_floating_point() and "running" not in k else v)
@@ -58,6 +58,20 @@ def test_adversarial_losses_and_gradients(gold):
     v = sds["mrd1"]["discriminators.2.parametrizations.weight.original1"]
     assert float(v.grad.norm()) == pytest.approx(float(gold["disc_d_mrd1_conv2_v_norm"]), rel=1e-4)
     assert rel_l2(sds["disc"]["last.2.weight"].grad, torch.from_numpy(gold["disc_d_last2_w"])) < 1e-4
+
+
+def test_pitch_and_duration_discriminators(gold):
+    sds = sds_of(gold)
+    pc, du = curve_inputs()
+    with torch.no_grad():
+        for key, x, k in (("pitch_disc", pc, 21), ("dur_disc", du, 5)):
+            outs = do.pitch_discriminator(sds[key], x, k)
+            for j, o in enumerate(outs):
+                assert rel_l2(o, torch.from_numpy(gold[f"{key}_out{j}"])) < 2e-6, (key, j)
+        g = do.helper_generator(lambda y: do.pitch_discriminator(sds["pitch_disc"], y, 21), pc, pc * 0.9 + 0.1)
+        assert float(g) == pytest.approx(float(gold["pitch_gen_loss"]), rel=2e-6)
+        d, _ = do.helper_discriminator(lambda y: do.pitch_discriminator(sds["dur_disc"], y, 5), du, du * 1.1 - 0.2)
+        assert float(d) == pytest.approx(float(gold["dur_disc_loss"]), rel=2e-6)
 
 
 def test_lr_controller(gold):
