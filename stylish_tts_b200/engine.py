@@ -849,6 +849,20 @@ class PitchEnergyEngine(_EngineBase):
 CLASS_TO_DUR = (1, 2, 3, 4, 5, 6, 7, 9, 12, 15, 18, 22, 27, 32, 38, 46)
 
 
+def soft_durations(pred, text_lengths):
+    """DurationProcessor.prediction_to_duration (utils.py:745-750): class scores (B,T,NC) -> durations (B,T)"""
+    dev = pred.device
+    B, T, NC = pred.shape
+    pred = pred.contiguous()
+    lengths = text_lengths.to(device=dev, dtype=torch.int64).contiguous()
+    table = torch.tensor(CLASS_TO_DUR[:NC], device=dev, dtype=torch.float32)
+    dur = torch.empty((B, T), device=dev, dtype=torch.float32)
+    total = torch.zeros((1,), device=dev, dtype=torch.int32)
+    L.call("sty_soft_duration_fwd", pred.data_ptr(), lengths.data_ptr(), table.data_ptr(), dur.data_ptr(),
+           total.data_ptr(), B, T, NC, L.stream_ptr())
+    return dur
+
+
 def duration_to_alignment(pred, text_lengths):
     """DurationProcessor.forward (utils.py:804-807): class scores (B,T,NC) -> (alignment (B,T,F),
     durations (B,T)).  The frame count is data dependent: one device->host read, like the

@@ -447,12 +447,46 @@ class PitchEnergyPredictor(_EngineModule):
 
 
 class DurationProcessor(nn.Module):
-    """forward(pred, text_length) -> soft alignment (B,T,F); reference utils.py:656-807 (the
-    prediction_to_duration + duration_to_alignment path, coarse multiplier 1)."""
+    """Drop-in for the reference DurationProcessor (utils.py:656-807).
+
+    forward(pred, text_length) -> soft alignment (B,T,F) (prediction_to_duration + duration_to_alignment on the
+    CUDA kernels, coarse multiplier 1); the class <-> duration index maps (``dur_to_class``, ``class_to_dur_hard``,
+    ``align_to_class``: table lookups, bit-exact, device-agnostic indexing) and ``class_to_dur_soft`` /
+    ``prediction_to_duration`` that the duration stage uses for its targets and losses (stage_type.py:507-522)."""
+
+    # durations (frames) represented by the 16 classes, and how many consecutive durations 0..50 map to each class
+    CLASS_DURATIONS = (1, 2, 3, 4, 5, 6, 7, 9, 12, 15, 18, 22, 27, 32, 38, 46)
+    CLASS_RUNS = (2, 1, 1, 1, 1, 1, 1, 3, 3, 3, 3, 5, 5, 5, 7, 9)
 
     def __init__(self, class_count=16, max_dur=50):
         super().__init__()
         self.class_count, self.max_dur = class_count, max_dur
+        self.register_buffer("class_to_dur_table", torch.tensor(self.CLASS_DURATIONS, dtype=torch.float32))
+        self.register_buffer("dur_to_class_table", torch.repeat_interleave(
+            torch.arange(len(self.CLASS_RUNS), dtype=torch.float32), torch.tensor(self.CLASS_RUNS)))
+
+    def class_to_dur_soft(self, softdur):
+        """expected duration of a class distribution (utils.py:726-730)"""
+        return (softdur * self.class_to_dur_table).sum(dim=-1) / (softdur.sum(dim=-1) + 1e-9)
+
+    def class_to_dur_hard(self, classes):
+        return self.class_to_dur_table[classes.clamp(min=0, max=self.class_count)]
+
+    def dur_to_class(self, durs):
+        return self.dur_to_class_table[durs.clamp(min=1, max=self.max_dur).long()]
+
+    def align_to_class(self, alignment):
+        return self.dur_to_class(alignment.sum(dim=-1).clamp(min=1, max=50))
+
+    def prediction_to_duration(self, pred, text_length):
+        """softmax -> expected duration -> * sequence mask (utils.py:745-750); the CUDA kernel when pred is on the
+        device (same result as forward()'s first half), the torch formula otherwise"""
+        if pred.is_cuda and not pred.requires_grad:
+            from .engine import soft_durations
+            return soft_durations(pred, text_length)
+        soft = self.class_to_dur_soft(torch.softmax(pred, dim=-1))
+        mask = torch.arange(pred.shape[1], device=pred.device)[None, :] < text_length.to(pred.device)[:, None]
+        return soft * mask
 
     def forward(self, pred, text_length, multiplier=1):
         if multiplier != 1:

@@ -70,6 +70,15 @@ def test_duration_processor_matches_reference():
     L.call("sty_alignment_fwd", dur2.data_ptr(), out.data_ptr(), B, T, Fr, L.stream_ptr())
     assert float((out.cpu() - g2["alignment"]).abs().max()) < 2e-6
     assert float((out.sum(1) - 1).abs().max()) < 1e-5  # columns are distributions over tokens
+    # the module API: prediction_to_duration on the device == the kernel's first half == the torch formula
+    from stylish_tts_b200.modules import DurationProcessor
+    proc = DurationProcessor(16, 50).to(d)
+    soft = proc.prediction_to_duration(gold["dur_pred"].to(d), inp["text_lengths"].to(d))
+    assert torch.equal(soft, dur)
+    cpu = DurationProcessor(16, 50).prediction_to_duration(gold["dur_pred"], inp["text_lengths"])
+    assert rel_l2(soft, cpu) < 1e-6
+    assert torch.equal(proc.dur_to_class(torch.tensor([0, 1, 2, 8, 50, 77], device=d)).cpu(),
+                       torch.tensor([0., 0., 1., 7., 15., 15.]))
 
 
 @pytest.mark.parametrize("D,H,T,lens", [(160, 2, 258, [258, 140]), (16, 8, 40, [40, 9]), (64, 4, 100, None)])

@@ -138,3 +138,34 @@ def test_predictor_oracles_match_golden():
     assert util.rel_l2(gold["pitch"], p64) < 5e-4 and util.rel_l2(gold["energy"], e64) < 5e-4
     p32, e32 = so.pitch_energy_predictor(psd, inp["texts"], inp["text_lengths"], inp["alignment"], sty)
     assert util.rel_l2(p32, p64) < 5e-4 and util.rel_l2(e32, e64) < 5e-4
+
+
+def test_duration_processor_index_maps():
+    """A1 index ops (utils.py:656-750): class <-> duration tables and lookups, bit-exact against the live reference
+    when it is mounted and against the oracle's table otherwise"""
+    from stylish_tts_b200.modules import DurationProcessor
+
+    proc = DurationProcessor(16, 50)
+    assert proc.class_to_dur_table.tolist() == [float(v) for v in so.CLASS_TO_DUR]
+    tbl = proc.dur_to_class_table
+    assert tbl.shape == (51,) and tbl[0] == 0 and tbl[1] == 0 and tbl[50] == 15
+    assert bool((tbl[1:] >= tbl[:-1]).all()) and bool((tbl[1:] - tbl[:-1] <= 1).all())
+    # every class maps back into its own duration bucket
+    for c, dur in enumerate(so.CLASS_TO_DUR):
+        assert int(proc.dur_to_class(torch.tensor([dur]))[0]) == c, (c, dur)
+    durs = torch.arange(-3, 70)
+    al = torch.rand(2, 7, 30)
+    soft = torch.softmax(torch.randn(2, 7, 16), dim=-1)
+    if ref_loader.available():
+        ref_loader.load()
+        from stylish_tts.train.utils import DurationProcessor as RefDP
+
+        ref = RefDP(16, 50)
+        assert torch.equal(proc.dur_to_class_table, ref.dur_to_class_table)
+        assert torch.equal(proc.dur_to_class(durs), ref.dur_to_class(durs))
+        assert torch.equal(proc.class_to_dur_hard(torch.arange(0, 16)), ref.class_to_dur_hard(torch.arange(0, 16)))
+        assert torch.equal(proc.align_to_class(al * 9), ref.align_to_class(al * 9))
+        assert torch.equal(proc.class_to_dur_soft(soft), ref.class_to_dur_soft(soft))
+        lens = torch.tensor([7, 4])
+        assert torch.allclose(proc.prediction_to_duration(soft.log(), lens), ref.prediction_to_duration(soft.log(), lens),
+                              atol=1e-6)
