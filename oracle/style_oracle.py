@@ -58,10 +58,14 @@ def mel_style_encoder(sd, x, training=False):
     return F.linear(h, sd["unshared.weight"], sd["unshared.bias"])
 
 
-def pitch_style_encoder(sd, x, pitch, energy, training=False):
-    """PitchStyleEncoder.forward mel_style_encoder.py:188-206 with coarse_multiplier == 1 (the linear
-    interpolation to the same length is the identity)."""
-    xc = torch.cat([x, pitch.unsqueeze(1), energy.unsqueeze(1)], dim=1)
+def pitch_style_encoder(sd, x, pitch, energy, training=False, coarse_multiplier=1):
+    """PitchStyleEncoder.forward mel_style_encoder.py:188-206: pitch / energy are linearly resampled to
+    frames // coarse_multiplier (the identity for 1) and stacked under the mel rows."""
+    pitch, energy = pitch.unsqueeze(1), energy.unsqueeze(1)
+    if coarse_multiplier != 1:
+        pitch = F.interpolate(pitch, size=pitch.shape[2] // coarse_multiplier, mode="linear")
+        energy = F.interpolate(energy, size=energy.shape[2] // coarse_multiplier, mode="linear")
+    xc = torch.cat([x, pitch, energy], dim=1)
     w = torch._weight_norm(sd["preconv.parametrizations.weight.original1"],
                            sd["preconv.parametrizations.weight.original0"], 0)
     y = F.conv1d(xc, w, sd["preconv.bias"], padding=1)

@@ -863,10 +863,11 @@ def soft_durations(pred, text_lengths):
     return dur
 
 
-def duration_to_alignment(pred, text_lengths):
+def duration_to_alignment(pred, text_lengths, multiplier=1):
     """DurationProcessor.forward (utils.py:804-807): class scores (B,T,NC) -> (alignment (B,T,F),
     durations (B,T)).  The frame count is data dependent: one device->host read, like the
-    reference's `.item()` (utils.py:759)."""
+    reference's `.item()` (utils.py:759).  ``multiplier`` (ModelConfig.coarse_multiplier) scales the frame
+    count and the durations before the alignment is laid out (utils.py:759-761)."""
     dev = pred.device
     B, T, NC = pred.shape
     pred = pred.contiguous()
@@ -876,9 +877,10 @@ def duration_to_alignment(pred, text_lengths):
     total = torch.zeros((1,), device=dev, dtype=torch.int32)
     L.call("sty_soft_duration_fwd", pred.data_ptr(), lengths.data_ptr(), table.data_ptr(), dur.data_ptr(),
            total.data_ptr(), B, T, NC, L.stream_ptr())
-    Fr = int(total.item())
+    Fr = int(total.item()) * int(multiplier)
     if Fr <= 0:
         raise RuntimeError("stylish_tts_b200: predicted durations sum to zero frames")
     al = torch.empty((B, T, Fr), device=dev, dtype=torch.float32)
-    L.call("sty_alignment_fwd", dur.data_ptr(), al.data_ptr(), B, T, Fr, L.stream_ptr())
+    dur_m = dur if multiplier == 1 else (dur * float(multiplier)).contiguous()
+    L.call("sty_alignment_fwd", dur_m.data_ptr(), al.data_ptr(), B, T, Fr, L.stream_ptr())
     return al, dur

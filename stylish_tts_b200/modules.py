@@ -450,7 +450,7 @@ class DurationProcessor(nn.Module):
     """Drop-in for the reference DurationProcessor (utils.py:656-807).
 
     forward(pred, text_length) -> soft alignment (B,T,F) (prediction_to_duration + duration_to_alignment on the
-    CUDA kernels, coarse multiplier 1); the class <-> duration index maps (``dur_to_class``, ``class_to_dur_hard``,
+    CUDA kernels, any integer coarse multiplier); the class <-> duration index maps (``dur_to_class``, ``class_to_dur_hard``,
     ``align_to_class``: table lookups, bit-exact, device-agnostic indexing) and ``class_to_dur_soft`` /
     ``prediction_to_duration`` that the duration stage uses for its targets and losses (stage_type.py:507-522)."""
 
@@ -489,11 +489,9 @@ class DurationProcessor(nn.Module):
         return soft * mask
 
     def forward(self, pred, text_length, multiplier=1):
-        if multiplier != 1:
-            raise NotImplementedError("stylish_tts_b200: coarse_multiplier != 1 is not built")
         from .engine import duration_to_alignment
 
-        return duration_to_alignment(pred, text_length)[0]
+        return duration_to_alignment(pred, text_length, multiplier)[0]
 
 
 class Synthesizer(nn.Module):

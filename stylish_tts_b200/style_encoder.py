@@ -282,13 +282,16 @@ class PitchStyleEncoder(MelStyleEncoder):
     def forward(self, x, pitch, energy):
         if not x.is_cuda:
             raise RuntimeError("stylish_tts_b200: PitchStyleEncoder needs CUDA tensors (no CPU fallback)")
+        pitch, energy = pitch.unsqueeze(1).to(torch.float32), energy.unsqueeze(1).to(torch.float32)
         if self.coarse_multiplier != 1:
-            raise NotImplementedError("stylish_tts_b200: coarse_multiplier != 1 is not built")
+            # two (B,1,F) curves resampled to the coarse frame rate (mel_style_encoder.py:189-197): index plumbing
+            n = pitch.shape[2] // self.coarse_multiplier
+            pitch = F.interpolate(pitch, size=n, mode="linear")
+            energy = F.interpolate(energy, size=n, mode="linear")
         L.load()
         P = dict(self.named_parameters())
         w = torch._weight_norm(P["preconv.parametrizations.weight.original1"],
                                P["preconv.parametrizations.weight.original0"], 0)
-        xcat = torch.cat([x.to(torch.float32), pitch.unsqueeze(1).to(torch.float32),
-                          energy.unsqueeze(1).to(torch.float32)], dim=1)
+        xcat = torch.cat([x.to(torch.float32), pitch, energy], dim=1)
         y = T.conv(F.pad(xcat, (1, 1)).contiguous(), w, P["preconv.bias"], umma=False)
         return self.encode(y)

@@ -70,6 +70,10 @@ def test_duration_processor_matches_reference():
     L.call("sty_alignment_fwd", dur2.data_ptr(), out.data_ptr(), B, T, Fr, L.stream_ptr())
     assert float((out.cpu() - g2["alignment"]).abs().max()) < 2e-6
     assert float((out.sum(1) - 1).abs().max()) < 1e-5  # columns are distributions over tokens
+    # coarse multiplier (utils.py:759-761) against the oracle's formula
+    al2 = proc_al = E.duration_to_alignment(gold["dur_pred"].to(d), inp["text_lengths"].to(d), 2)[0]
+    ref2 = so.duration_to_alignment(gold["soft_duration"], 2)
+    assert proc_al.shape == ref2.shape and float((al2.cpu() - ref2).abs().max()) < 2e-6
     # the module API: prediction_to_duration on the device == the kernel's first half == the torch formula
     from stylish_tts_b200.modules import DurationProcessor
     proc = DurationProcessor(16, 50).to(d)

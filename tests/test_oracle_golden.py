@@ -166,6 +166,9 @@ def test_duration_processor_index_maps():
         assert torch.equal(proc.class_to_dur_hard(torch.arange(0, 16)), ref.class_to_dur_hard(torch.arange(0, 16)))
         assert torch.equal(proc.align_to_class(al * 9), ref.align_to_class(al * 9))
         assert torch.equal(proc.class_to_dur_soft(soft), ref.class_to_dur_soft(soft))
+        dd = torch.rand(2, 7) * 6
+        for mult in (1, 2, 4):  # coarse multiplier (utils.py:759-761): the oracle's restatement vs the reference
+            assert torch.equal(so.duration_to_alignment(dd, mult), ref.duration_to_alignment(dd, mult))
         lens = torch.tensor([7, 4])
         assert torch.allclose(proc.prediction_to_duration(soft.log(), lens), ref.prediction_to_duration(soft.log(), lens),
                               atol=1e-6)

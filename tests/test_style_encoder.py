@@ -10,6 +10,7 @@ import pytest
 import torch
 import torch.nn.functional as F
 
+from oracle import ref_loader
 from oracle import style_oracle as sto
 from tests import util
 from tests.golden.make_style_golden import build, probe, style_inputs
@@ -186,6 +187,44 @@ def test_pitch_style_encoder_oracle_matches_reference_golden():
     with torch.no_grad():
         out = sto.pitch_style_encoder(sd_of(m), *pitch_inputs())
     assert rel_l2(out, torch.from_numpy(gold()["pe_out_eval"])) < 1e-5
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="/root/reference not mounted")
+def test_pitch_style_encoder_coarse_multiplier_vs_live_reference():
+    """coarse_multiplier = 2: pitch / energy at the fine rate, mel at the coarse one (mel_style_encoder.py:188-206)"""
+    from tests.golden.make_style_golden import build_pitch, pitch_inputs
+
+    ref_loader.load()
+    from stylish_tts.train.models.mel_style_encoder import PitchStyleEncoder as RefPSE
+
+    m = build_pitch()
+    ref = RefPSE(80, 64, 384, True, coarse_multiplier=2).eval()
+    ref.load_state_dict(m.state_dict(), strict=True)
+    x, pitch, energy = pitch_inputs()
+    fine_p, fine_e = pitch.repeat_interleave(2, dim=1) * 1.01, energy.repeat_interleave(2, dim=1) + 0.1
+    with torch.no_grad():
+        want = ref(x, fine_p, fine_e)
+        got = sto.pitch_style_encoder(sd_of(m), x, fine_p, fine_e, coarse_multiplier=2)
+    assert rel_l2(got, want) < 1e-5
+
+
+@pytest.mark.gpu
+def test_pitch_style_encoder_coarse_multiplier_gpu():
+    from stylish_tts_b200.style_encoder import PitchStyleEncoder
+    from tests.golden.make_style_golden import build_pitch, pitch_inputs
+
+    m = build_pitch()
+    x, pitch, energy = pitch_inputs()
+    fine_p, fine_e = pitch.repeat_interleave(2, dim=1) * 1.01, energy.repeat_interleave(2, dim=1) + 0.1
+    with torch.no_grad():
+        want = sto.pitch_style_encoder(sd_of(m, torch.float64), x.double(), fine_p.double(), fine_e.double(),
+                                       coarse_multiplier=2)
+    mc = PitchStyleEncoder(80, 64, 384, True, coarse_multiplier=2)
+    mc.load_state_dict(m.state_dict(), strict=True)
+    mc = mc.cuda().eval()
+    with torch.no_grad():
+        got = mc(x.cuda(), fine_p.cuda(), fine_e.cuda())
+    assert rel_l2(got, want) < 2e-4
 
 
 @pytest.mark.gpu
