@@ -499,8 +499,9 @@ class Synthesizer(nn.Module):
     duration predictor -> alignment -> pitch/energy predictor -> speech predictor."""
 
     def __init__(self, *, speech_predictor, pitch_energy_predictor, duration_predictor,
-                 class_count=16, max_dur=50):
+                 class_count=16, max_dur=50, coarse_multiplier=1):
         super().__init__()
+        self.coarse_multiplier = coarse_multiplier
         self.speech_predictor = speech_predictor
         self.pitch_energy_predictor = pitch_energy_predictor
         self.duration_predictor = duration_predictor
@@ -511,9 +512,12 @@ class Synthesizer(nn.Module):
                 source_draws=None, return_aux=False):
         dur_pred = self.duration_predictor(texts, text_lengths, duration_style)
         alignment = self.duration_processor(dur_pred, text_lengths)
+        # export_model.py:42-45: the speech predictor gets the alignment at the fine frame rate
+        fine = alignment if self.coarse_multiplier == 1 else self.duration_processor(
+            dur_pred, text_lengths, multiplier=self.coarse_multiplier)
         pitch, energy = self.pitch_energy_predictor(texts, text_lengths, alignment, pe_style)
         voiced = (pitch > 20).float()
-        pred = self.speech_predictor(texts, text_lengths, alignment, pitch, energy, voiced,
+        pred = self.speech_predictor(texts, text_lengths, fine, pitch, energy, voiced,
                                      speech_style, pitch, source_draws=source_draws)
         if return_aux:
             return pred.audio, dict(dur_pred=dur_pred, alignment=alignment, pitch=pitch, energy=energy)
