@@ -143,6 +143,8 @@ def run_reference(args):
     import torch
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
+    if getattr(args, "mode", "fwd") == "train":
+        return run_reference_train(args, cores)
     run, secs = oracle_forward_fn(1, args.tokens)
     for _ in range(max(1, min(args.warmup, 2))):
         run()
@@ -170,6 +172,32 @@ def run_reference(args):
 
 
 TRAIN_METRIC = "train steps/sec (acoustic step: fwd+bwd + multi-res STFT/phase loss + AdamW)"
+
+
+def run_reference_train(args, cores):
+    """--impl reference --mode train: the acoustic step through the CPU oracles; each timed step is ONE utterance
+    (a bounded sample), a batch-`train_batch` step is that time x the batch size"""
+    batch = getattr(args, "train_batch", 32)
+    run, secs = oracle_train_fn(args.tokens)
+    for _ in range(max(1, min(args.warmup, 1))):
+        run()
+    steps = max(1, min(args.steps, 5))
+    t = time.perf_counter()
+    for _ in range(steps):
+        run()
+    dt = (time.perf_counter() - t) / steps
+    val = 1.0 / (dt * batch)
+    sample = (f"each step = 1 utterance ({secs:.2f} audio-s) fwd + losses + bwd through the CPU oracles "
+              f"({dt:.2f} s); a batch-{batch} step is extrapolated as {batch}x that")
+    print(json.dumps({
+        "impl": "reference", "metric": TRAIN_METRIC, "value": val, "unit": "steps/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt * batch, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"configs[2]: full train step, batch {batch}", "batch_per_step": 1,
+                   "tokens": args.tokens},
+        "cpu_baseline": {"value": val, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
 
 
 def oracle_train_fn(tokens, seed=1):
