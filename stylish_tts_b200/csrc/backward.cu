@@ -926,6 +926,8 @@ extern "C" int sty_chan_layernorm_bwd(const float* x, const float* res, int64_t 
                                       float eps, int act, sty_stream_t stream) {
   STY_REQUIRE(x && gamma && beta && dy && dv && dgb && B > 0 && C > 0 && T > 0, "chan_layernorm_bwd: bad argument");
   STY_REQUIRE(act == STY_ACT_NONE || act == STY_ACT_RELU, "chan_layernorm_bwd: only none/relu epilogues");
+  STY_REQUIRE((2 * (size_t)C + 4 * 2 * 32 * 33) * sizeof(float) <= 48 * 1024,
+              "chan_layernorm_bwd: C=%d needs more than 48 KB of shared memory", C);
   dim3 grid(cdiv(T, 128), B);
   chan_layernorm_bwd_kernel<<<grid, 128, (2 * C + 4 * 2 * 32 * 33) * sizeof(float), as_stream(stream)>>>(
       x, res, x_bs, gamma, beta, g_bs, g_plus_one, dy, mask, dv, dgb, dg_bs, C, T, eps, act);
