@@ -35,11 +35,14 @@ class FrontEnd:
         self.stft_loss = spectral.MultiResolutionSTFTLoss(sample_rate=mc.sample_rate)
 
 
-def alignment_from_durations(durations: torch.Tensor, frames: int = 0) -> torch.Tensor:
+def alignment_from_durations(durations: torch.Tensor, frames: int = 0, multiplier: int = 1) -> torch.Tensor:
     """DurationProcessor.duration_to_alignment (utils.py:752-791) for the integer durations of a batch
     (stage_type.py:99-101): (B,T) -> soft alignment (B,T,F).  `frames` skips the device->host read of
-    round(max sum) that the reference does with .item() (utils.py:759)."""
+    round(max sum) that the reference does with .item() (utils.py:759); `multiplier` =
+    ModelConfig.coarse_multiplier scales durations and frame count (utils.py:759-761)."""
     dur = durations.to(torch.float32).contiguous()
+    if multiplier != 1:
+        dur = (dur * float(multiplier)).contiguous()
     B, Tn = dur.shape
     Fr = frames or int(dur.sum(dim=1).round().max().item())
     al = torch.empty((B, Tn, Fr), device=dur.device, dtype=torch.float32)
@@ -47,21 +50,23 @@ def alignment_from_durations(durations: torch.Tensor, frames: int = 0) -> torch.
     return al
 
 
-def acoustic_step(batch, nets, fe: FrontEnd, *, w_mel=5.0, w_phase=8.0, source_draws=None):
+def acoustic_step(batch, nets, fe: FrontEnd, *, w_mel=5.0, w_phase=8.0, source_draws=None, prior=None):
     """batch: audio_gt (B,L), text (B,T), text_length (B,), pitch (B,F), alignment (B,1,T) integer durations
     (the reference's collated batch, stage_type.py:61-106).  Returns total / mel / multi_phase losses and
-    the prediction."""
+    the prediction.  `prior` = (har_spec, har_phase) injects the harmonic prior (parity tests)."""
     audio_gt = batch.audio_gt
+    cm = int(getattr(getattr(nets.speech_predictor, "model_config", None), "coarse_multiplier", 1) or 1)
     with torch.no_grad():
         mel, _ = spectral.calculate_mel(audio_gt, fe.to_mel, fe.mean, fe.std)
         style_mel, _ = spectral.calculate_mel(audio_gt, fe.to_style_mel, fe.mean, fe.std)
         energy = spectral.mel_energy(mel, fe.mean, fe.std)
         pitch = batch.pitch
-        alignment = alignment_from_durations(batch.alignment[:, 0, :], frames=pitch.shape[1])
+        # alignment_fine of stage_type.py:111-115 (the speech predictor reads the fine one)
+        alignment = alignment_from_durations(batch.alignment[:, 0, :], frames=pitch.shape[1], multiplier=cm)
         voiced = (pitch > 20).float()
     style = nets.speech_style_encoder(style_mel.unsqueeze(1))
     pred = nets.speech_predictor(batch.text, batch.text_length, alignment, pitch, energy, voiced, style, pitch,
-                                 source_draws=source_draws)
+                                 source_draws=source_draws, prior=prior)
     total, mel_loss, phase_loss = acoustic_losses(pred.audio.squeeze(1), audio_gt, fe.multi_spectrogram,
                                                   fe.stft_loss, w_mel=w_mel, w_phase=w_phase)
     return SimpleNamespace(total=total, mel=mel_loss, multi_phase=phase_loss, pred=pred, style=style,
