@@ -648,7 +648,7 @@ def prediction_to_duration(pred, text_lengths):
     return soft * sequence_mask(text_lengths, pred.shape[1])
 
 
-def synthesize(sds, texts, text_lengths, speech_style, pe_style, duration_style, draws_fn):
+def synthesize(sds, texts, text_lengths, speech_style, pe_style, duration_style, draws_fn, taps=None):
     """ExportModel.forward export_model.py:40-63, batched.  `sds` = dict of the three state dicts;
     `draws_fn(frames)` supplies the source noise once the (data-dependent) length is known."""
     dur_pred = duration_predictor(sds["duration_predictor"], texts, text_lengths, duration_style)
@@ -658,5 +658,5 @@ def synthesize(sds, texts, text_lengths, speech_style, pe_style, duration_style,
                                            alignment, pe_style)
     voiced = (pitch > 20).to(pitch.dtype)
     audio = speech_predictor(sds["speech_predictor"], texts, text_lengths, alignment, pitch, energy,
-                             voiced, speech_style, pitch, draws_fn(alignment.shape[2]))
+                             voiced, speech_style, pitch, draws_fn(alignment.shape[2]), taps=taps)
     return audio, dict(dur_pred=dur_pred, duration=dur, alignment=alignment, pitch=pitch, energy=energy)

@@ -8,6 +8,7 @@ statically so it can be dlopen'ed on a box without a GPU (symbol checks).
 from __future__ import annotations
 
 import concurrent.futures as cf
+import hashlib
 import os
 import subprocess
 import sys
@@ -20,11 +21,27 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std
          "--extended-lambda", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
 
 
+def _digest(paths) -> str:
+    h = hashlib.sha256(" ".join(FLAGS).encode())
+    for p in paths:
+        with open(p, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
 def _stale(target: str, deps) -> bool:
-    if not os.path.exists(target):
+    """content-hash staleness (mtimes do not survive a repo snapshot): `target`.sha holds the digest of the
+    flags and sources the target was built from"""
+    stamp = target + ".sha"
+    if not os.path.exists(target) or not os.path.exists(stamp):
         return True
-    t = os.path.getmtime(target)
-    return any(os.path.getmtime(d) > t for d in deps)
+    with open(stamp) as f:
+        return f.read().strip() != _digest(deps)
+
+
+def _stamp(target: str, deps) -> None:
+    with open(target + ".sha", "w") as f:
+        f.write(_digest(deps))
 
 
 def _compile(src: str) -> str:
@@ -36,6 +53,7 @@ def _compile(src: str) -> str:
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
+        _stamp(obj, deps)
     return obj
 
 
@@ -44,6 +62,8 @@ def build(force: bool = False) -> str:
     if force:
         for f in os.listdir(os.path.join(HERE, "build")):
             os.remove(os.path.join(HERE, "build", f))
+        if os.path.exists(LIB + ".sha"):
+            os.remove(LIB + ".sha")
     with cf.ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:
         objs = list(ex.map(_compile, SOURCES))
     if force or _stale(LIB, objs):
@@ -51,6 +71,7 @@ def build(force: bool = False) -> str:
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+        _stamp(LIB, objs)
     return LIB
 
 

@@ -316,6 +316,12 @@ class SpeechPredictor(nn.Module):
             self._train_graph = TrainGraph(self, self.engine())
         return self._train_graph
 
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        if getattr(self, "_train_graph", None) is not None:
+            self._train_graph.rebind()  # .to() / .cuda() rebind buffers: no stale pointers in the cached graph
+        return out
+
     def forward(self, texts, text_lengths, alignment, pitch, energy, voiced, style,
                 denormal_pitch, *, source_draws=None, prior=None, taps=None):
         wants_grad = torch.is_grad_enabled() and (
@@ -364,6 +370,12 @@ class _EngineModule(nn.Module):
         if getattr(self, "_train_graph", None) is None:
             self._train_graph = getattr(TE, self.graph_cls_name)(self)
         return self._train_graph
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        if getattr(self, "_train_graph", None) is not None:
+            self._train_graph.rebind()
+        return out
 
     def _wants_grad(self, *inputs):
         return torch.is_grad_enabled() and (any(p.requires_grad for p in self.parameters()) or
@@ -509,7 +521,7 @@ class Synthesizer(nn.Module):
 
     @torch.no_grad()
     def forward(self, texts, text_lengths, speech_style, pe_style, duration_style, *,
-                source_draws=None, return_aux=False):
+                source_draws=None, prior=None, return_aux=False):
         dur_pred = self.duration_predictor(texts, text_lengths, duration_style)
         alignment = self.duration_processor(dur_pred, text_lengths)
         # export_model.py:42-45: the speech predictor gets the alignment at the fine frame rate
@@ -518,7 +530,7 @@ class Synthesizer(nn.Module):
         pitch, energy = self.pitch_energy_predictor(texts, text_lengths, alignment, pe_style)
         voiced = (pitch > 20).float()
         pred = self.speech_predictor(texts, text_lengths, fine, pitch, energy, voiced,
-                                     speech_style, pitch, source_draws=source_draws)
+                                     speech_style, pitch, source_draws=source_draws, prior=prior)
         if return_aux:
             return pred.audio, dict(dur_pred=dur_pred, alignment=alignment, pitch=pitch, energy=energy)
         return pred.audio

@@ -38,8 +38,7 @@ class TrainGraph:
     def __init__(self, module, engine=None):
         self.m = module
         self.engine = engine  # the inference engine (speech predictor: harmonic prior kernels)
-        self.P: Dict[str, torch.Tensor] = dict(module.named_parameters())
-        self.Bf: Dict[str, torch.Tensor] = dict(module.named_buffers())
+        self.rebind()
         self.mc = module.model_config
         names = sorted(k[:-len(".fc.weight")] for k in self.P if k.endswith(".fc.weight"))
         self.fc_names = names
@@ -55,6 +54,14 @@ class TrainGraph:
         self.smooth_w = None     # (2, 1, 31) box filters of the decoder's F0 / N smoothing (decoder.py:53-75)
         self.smooth = (0, 0)
 
+    def rebind(self):
+        """(re)read the module's parameters and buffers: nn.Module.to() / .cuda() / .double() REBIND buffer tensors
+        (and may rebind parameters), so the shells call this from ``_apply``."""
+        self.P: Dict[str, torch.Tensor] = dict(self.m.named_parameters())
+        self.Bf: Dict[str, torch.Tensor] = dict(self.m.named_buffers())
+        self._rope = {}
+        self.smooth_w = None
+
     # ---------------------------------------------------------------- stochastic regularisers
     def stochastic(self) -> bool:
         return bool(self.m.training and getattr(self.m, "regularisers", True))
@@ -65,6 +72,8 @@ class TrainGraph:
         device = device or next(iter(self.P.values())).device
         if self.rng is None:
             self.rng = T.DropoutRng(getattr(self.m, "regulariser_seed", 0), device)
+        elif self.auto_step:
+            self.rng = self.rng.fork()  # eager: a seed cell (and smoothing filter) per forward, see fork()
         else:
             self.rng.advance()
         if any(k.startswith("decoder.F0_conv") for k in self.P):
@@ -76,7 +85,7 @@ class TrainGraph:
                 wd = wd or 1
                 rows.append([1.0 / wd if abs(i - 15) <= wd // 2 else 0.0 for i in range(31)])
             host = torch.tensor(rows, dtype=torch.float32).reshape(2, 1, 31)
-            if self.smooth_w is None:
+            if self.smooth_w is None or self.auto_step:
                 self.smooth_w = host.to(device)
             else:
                 self.smooth_w.copy_(host)
@@ -245,8 +254,9 @@ class TrainGraph:
         bn = c + ".conv.net.4"
         x3 = T.conv(dw, P[c + ".conv.net.6.weight"], P[c + ".conv.net.6.bias"], bn_w=P[bn + ".weight"],
                     bn_b=P[bn + ".bias"], in_act=ACT_SWISH, norm="batch", eps=1e-5,
-                    bn_buffers=(Bf[bn + ".running_mean"], Bf[bn + ".running_var"]), res=x2)
-        if bn + ".num_batches_tracked" in Bf:
+                    bn_buffers=(Bf[bn + ".running_mean"], Bf[bn + ".running_var"]), res=x2,
+                    bn_eval=not self.m.training)
+        if self.m.training and bn + ".num_batches_tracked" in Bf:
             Bf[bn + ".num_batches_tracked"].add_(1)
         x4 = ff(c + ".ff2", x3)
         return T.chan_ln(x4, gb=self.gb(h, c + ".post_norm", Cc), eps=1e-5)

@@ -124,15 +124,21 @@ class ConvFn(Function):
             scale = ((1.0 + gb[:, :CI]) * rstd).contiguous()
             shift = (gb[:, CI:] - mean * scale).contiguous()
         elif norm == "batch":
-            m_bc, v_bc = row_moments(x)
-            mean_c = m_bc.mean(0)
-            var_c = (v_bc + m_bc * m_bc).mean(0) - mean_c * mean_c
+            stats = cfg.get("bn_buffers")
+            if cfg.get("bn_eval"):
+                # module.eval() under autograd: nn.BatchNorm1d normalises with the running statistics and
+                # leaves them untouched; they are constants of the backward (no batch-statistics terms)
+                mean_c, var_c = stats[0].detach().clone(), stats[1].detach().clone()
+                stats = None
+            else:
+                m_bc, v_bc = row_moments(x)
+                mean_c = m_bc.mean(0)
+                var_c = (v_bc + m_bc * m_bc).mean(0) - mean_c * mean_c
             rstd_c = torch.rsqrt(var_c + eps)
             sc = bn_w * rstd_c
             scale = sc.unsqueeze(0).expand(B, CI).contiguous()
             shift = (bn_b - mean_c * sc).unsqueeze(0).expand(B, CI).contiguous()
             mean, rstd = mean_c.unsqueeze(0).expand(B, CI).contiguous(), rstd_c
-            stats = cfg.get("bn_buffers")
             if stats is not None:  # running statistics, momentum 0.1, unbiased variance (nn.BatchNorm1d)
                 n = B * T
                 stats[0].mul_(0.9).add_(mean_c, alpha=0.1)
@@ -191,12 +197,13 @@ class ConvFn(Function):
                 elif norm == "batch":
                     s0, s1 = sums[:, :, 0].sum(0), sums[:, :, 1].sum(0)
                     d_bnw, d_bnb = s1 * rstd, s0
-                    n = B * T
-                    sc = scale[0]
-                    c1c = -(sc * rstd * rstd) * s1 / n
-                    c0c = -sc * s0 / n - c1c * mean[0]
-                    c1 = c1c.unsqueeze(0).expand(B, CI).contiguous()
-                    c0 = c0c.unsqueeze(0).expand(B, CI).contiguous()
+                    if not cfg.get("bn_eval"):
+                        n = B * T
+                        sc = scale[0]
+                        c1c = -(sc * rstd * rstd) * s1 / n
+                        c0c = -sc * s0 / n - c1c * mean[0]
+                        c1 = c1c.unsqueeze(0).expand(B, CI).contiguous()
+                        c0 = c0c.unsqueeze(0).expand(B, CI).contiguous()
                 if need[0]:
                     _, d_x = prologue_bwd(dxp, x, scale=scale, shift=shift, alpha=al, mask=in_mask, act=in_act,
                                           want_sums=False, c0=c0, c1=c1)
@@ -355,6 +362,18 @@ class DropoutRng:
     def set(self, value: int) -> None:
         self.value = int(value) & (2 ** 64 - 1)
         self.dev.fill_(self.value - 2 ** 64 if self.value >= 2 ** 63 else self.value)
+
+    def fork(self) -> "DropoutRng":
+        """The next seed of the sequence in a FRESH device cell.  Eager forwards use one cell per forward, so a
+        backward that runs after a later forward (gradient accumulation, two batches in one loss) still
+        rebuilds ITS masks; only the CUDA-graph runner keeps one shared cell (``advance``)."""
+        nxt = object.__new__(DropoutRng)
+        nxt.state = self.state
+        nxt.dev = torch.zeros_like(self.dev)
+        nxt.value = 0
+        nxt.advance()
+        self.state = nxt.state
+        return nxt
 
     def spec(self, site: int, p: float) -> "L.Dropout":
         return L.Dropout(self.dev.data_ptr(), int(site), float(p))

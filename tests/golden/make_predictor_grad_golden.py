@@ -25,20 +25,28 @@ def cot(shape, seed):
     return torch.randn(shape, generator=torch.Generator().manual_seed(seed))
 
 
-def build():
+def build(conditioned=False):
+    """conditioned: every utterance is padded (synth.speech_inputs all_padded) — the well-conditioned case on
+    which gradient parity is asserted at kernel accuracy (``predictor_grads_wc.npz``)."""
     import stylish_tts_b200 as st
     from stylish_tts_b200 import synth
     nets = st.build_model(st.default_model_config())
     synth.randomize_(nets.duration_predictor, CASE["dseed"])
     synth.randomize_(nets.pitch_energy_predictor, CASE["pseed"])
-    inp = synth.speech_inputs(CASE["batch"], CASE["tokens"], seed=CASE["iseed"], ragged=True)
+    inp = synth.speech_inputs(CASE["batch"], CASE["tokens"], seed=CASE["iseed"], ragged=True,
+                              all_padded=conditioned)
     sty = torch.randn(CASE["batch"], 64, generator=torch.Generator().manual_seed(CASE["sseed"]))
     return nets, inp, sty
 
 
 def main():
+    run(False, "predictor_grads.npz")
+    run(True, "predictor_grads_wc.npz")
+
+
+def run(conditioned, fname):
     from oracle import ref_loader
-    nets, inp, sty = build()
+    nets, inp, sty = build(conditioned)
     ref = ref_loader.build_model()
     dpm, pem = ref.duration_predictor.eval(), ref.pitch_energy_predictor.eval()
     dpm.load_state_dict(nets.duration_predictor.state_dict(), strict=True)
@@ -59,7 +67,7 @@ def main():
                 continue
             names.append(n), norms.append(float(p.grad.norm())), dots.append(float((p.grad * probe(n, p.shape)).sum()))
         blob[tag + "_names"], blob[tag + "_norms"], blob[tag + "_dots"] = np.array(names), np.array(norms), np.array(dots)
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "predictor_grads.npz")
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), fname)
     np.savez_compressed(path, **blob)
     print(len(blob["dur_names"]), len(blob["pe_names"]), os.path.getsize(path) // 1024, "KiB")
 

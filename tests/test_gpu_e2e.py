@@ -143,6 +143,21 @@ def test_baseline_sized_utterance_vs_oracle():
         assert v < (AUDIO_TOL if k == "audio" else TAP_TOL), (k, v)
 
 
+def test_config2_full_batch_audio_vs_oracle():
+    """BASELINE config 2 itself (B=16, T=258, F=803): audio of every utterance against the CPU oracle."""
+    sp = st.build_model(st.default_model_config()).speech_predictor
+    synth.randomize_(sp, 21)
+    inp = synth.speech_inputs(16, 258, seed=3, ragged=True)
+    otaps = {}
+    ref = run_oracle(sp, inp, otaps)
+    audio = run_gpu(sp, inp, prior=(otaps["har_spec"], otaps["har_phase"]))
+    assert audio.shape == ref.shape == (16, 1, inp["alignment"].shape[2] * 300)
+    per_row = [rel_l2(audio[b], ref[b]) for b in range(16)]
+    print("config 2 audio rel-L2 per utterance:", [f"{e:.1e}" for e in per_row])
+    assert max(per_row) < AUDIO_TOL, per_row
+    assert rel_l2(audio, ref) < AUDIO_TOL
+
+
 def test_full_batch_properties():
     """BASELINE config 2 (B=16, T=258): size-independent properties.
     (1) utterances are independent: row b of the batch == the same utterance run alone;

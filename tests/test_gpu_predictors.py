@@ -142,3 +142,38 @@ def test_synthesizer_text_to_wav():
     assert rel_l2(gaux["pitch"], aux["pitch"]) < 2e-3  # ill-conditioned towers, see above
     assert audio.shape == ref_audio.shape
     assert torch.isfinite(audio).all() and float(audio.abs().max()) <= 1.0
+
+
+def test_synthesizer_audio_vs_oracle():
+    """text -> wav through all three predictors: the AUDIO against the CPU oracle of ExportModel.forward
+    (export_model.py:40-63), harmonic prior injected, every utterance padded (the well-conditioned
+    case of the pitch / energy towers, tests/test_predictor_train.py)."""
+    nets = st.build_model(st.default_model_config())
+    for i, k in enumerate(("duration_predictor", "pitch_energy_predictor", "speech_predictor")):
+        synth.randomize_(nets[k], 30 + i)
+    inp = synth.speech_inputs(2, 40, seed=12, ragged=True, all_padded=True)
+    g = torch.Generator().manual_seed(13)
+    styles = [torch.randn(2, 64, generator=g) for _ in range(3)]
+    sds = {k: util.state_dict_of(nets[k]) for k in ("duration_predictor", "pitch_energy_predictor",
+                                                    "speech_predictor")}
+    noise = {}
+
+    def draws_fn(frames):
+        noise["n"] = torch.randn(2, frames * 300, 9, generator=g)
+        return {"rand_ini": torch.rand(2, 9, generator=g), "noise": noise["n"]}
+
+    taps = {}
+    ref_audio, aux = so.synthesize(sds, inp["texts"], inp["text_lengths"], styles[0], styles[1], styles[2],
+                                   draws_fn, taps=taps)
+    d = dev()
+    syn = st.Synthesizer(speech_predictor=nets.speech_predictor.to(d),
+                         pitch_energy_predictor=nets.pitch_energy_predictor.to(d),
+                         duration_predictor=nets.duration_predictor.to(d))
+    audio, gaux = syn(inp["texts"].to(d), inp["text_lengths"].to(d), styles[0].to(d), styles[1].to(d),
+                      styles[2].to(d), prior=(taps["har_spec"].to(d), taps["har_phase"].to(d)), return_aux=True)
+    assert audio.shape == ref_audio.shape
+    e = dict(pitch=rel_l2(gaux["pitch"], aux["pitch"]), energy=rel_l2(gaux["energy"], aux["energy"]),
+             audio=rel_l2(audio, ref_audio))
+    print("synthesizer vs oracle:", e)
+    assert e["pitch"] < 2e-4 and e["energy"] < 2e-4
+    assert e["audio"] < 1e-3

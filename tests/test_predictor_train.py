@@ -13,8 +13,8 @@ from tests.golden.make_predictor_grad_golden import build, cot, probe
 from tests.util import rel_l2
 
 
-def gold():
-    z = np.load(util.GOLDEN_DIR + "/predictor_grads.npz")
+def gold(wc=False):
+    z = np.load(util.GOLDEN_DIR + ("/predictor_grads_wc.npz" if wc else "/predictor_grads.npz"))
     return {k: z[k] for k in z.files}
 
 
@@ -45,22 +45,28 @@ def check_golden(tag, grads_of, g, tol):
         assert abs(float((gr * probe(n, gr.shape)).sum()) - dot) <= 2 * tol * norm + 1e-6 * scale, (tag, n)
 
 
-def test_oracle_gradients_match_reference_golden():
-    g = gold()
-    nets, inp, sty = build()
+# wc ("well conditioned"): every utterance padded.  With a full-length utterance the 64 style channels of
+# `prosody @ alignment` are exactly constant over time; the towers' InstanceNorm (eps 1e-5) then amplifies their
+# rounding noise ~300x — the reference's own fp32 forward is 8e-5 and its gradient 9e-3 from fp64 on that case
+# (2e-5 on the padded one), so only the padded case can be held to kernel accuracy.
+@pytest.mark.parametrize("wc", [False, True])
+def test_oracle_gradients_match_reference_golden(wc):
+    g = gold(wc)
+    nets, inp, sty = build(wc)
     r = oracle_run(nets, inp, sty, torch.float32)
     assert rel_l2(r["dur"][0], torch.from_numpy(g["dur_out"])) < 1e-5
-    assert rel_l2(r["pe"][0][0], torch.from_numpy(g["pe_pitch"])) < 2e-4
+    assert rel_l2(r["pe"][0][0], torch.from_numpy(g["pe_pitch"])) < (2e-5 if wc else 2e-4)
     assert rel_l2(r["dur"][1], torch.from_numpy(g["dur_dstyle"])) < 1e-3
-    assert rel_l2(r["pe"][1], torch.from_numpy(g["pe_dstyle"])) < 5e-3
+    assert rel_l2(r["pe"][1], torch.from_numpy(g["pe_dstyle"])) < (2e-4 if wc else 5e-3)
     check_golden("dur", lambda n: r["dur"][2][n].grad, g, 2e-3)
-    check_golden("pe", lambda n: r["pe"][2][n].grad, g, 1e-2)
+    check_golden("pe", lambda n: r["pe"][2][n].grad, g, 5e-4 if wc else 1e-2)
 
 
 @pytest.mark.gpu
-def test_gpu_predictor_gradients():
-    g = gold()
-    nets, inp, sty = build()
+@pytest.mark.parametrize("wc", [True, False])
+def test_gpu_predictor_gradients(wc):
+    g = gold(wc)
+    nets, inp, sty = build(wc)
     ref = oracle_run(nets, inp, sty, torch.float64)
     dev = torch.device("cuda:0")
     c = lambda t: t.to(dev)
@@ -74,10 +80,14 @@ def test_gpu_predictor_gradients():
     ((pitch * c(cot(pitch.shape, 42))).sum() + (energy * c(cot(energy.shape, 43))).sum()).backward()
     torch.cuda.synchronize()
     assert rel_l2(out, ref["dur"][0]) < 2e-4
-    # the pitch / energy towers are ill-conditioned in fp32 with random weights (reference fp32 vs fp64: 7.8e-5)
-    assert rel_l2(pitch, ref["pe"][0][0]) < 5e-4 and rel_l2(energy, ref["pe"][0][1]) < 5e-4
-    assert rel_l2(s1.grad, ref["dur"][1]) < 2e-3, rel_l2(s1.grad, ref["dur"][1])
-    assert rel_l2(s2.grad, ref["pe"][1]) < 1e-2, rel_l2(s2.grad, ref["pe"][1])
+    # plain case: the pitch / energy towers are ill-conditioned in fp32 (reference fp32 vs fp64: 7.8e-5 forward,
+    # 9e-3 gradient, see above); the padded case is held to the north-star bound
+    t_out, t_sty, t_all, t_par, t_gold = (1e-4, 1e-3, 1e-3, 3e-3, 2e-3) if wc else (5e-4, 1e-2, 1e-2, 5e-2, 2e-2)
+    print("pitch / energy vs fp64 oracle:", rel_l2(pitch, ref["pe"][0][0]), rel_l2(energy, ref["pe"][0][1]))
+    print("d(style) dur / pe:", rel_l2(s1.grad, ref["dur"][1]), rel_l2(s2.grad, ref["pe"][1]))
+    assert rel_l2(pitch, ref["pe"][0][0]) < t_out and rel_l2(energy, ref["pe"][0][1]) < t_out
+    assert rel_l2(s1.grad, ref["dur"][1]) < 1e-3, rel_l2(s1.grad, ref["dur"][1])
+    assert rel_l2(s2.grad, ref["pe"][1]) < t_sty, rel_l2(s2.grad, ref["pe"][1])
     for tag, mod in (("dur", dp), ("pe", pe)):
         params = dict(mod.named_parameters())
         sd = ref[tag][2]
@@ -85,11 +95,11 @@ def test_gpu_predictor_gradients():
         tot = torch.cat([params[n].grad.flatten().double().cpu() for n in params if sd[n].grad is not None])
         e = rel_l2(tot, tot_ref)
         print(tag, "all parameter gradients vs fp64 oracle:", e)
-        assert e < (2e-3 if tag == "dur" else 1e-2), (tag, e)
+        assert e < (1e-3 if tag == "dur" else t_all), (tag, e)
         scale = float(tot_ref.norm())
         for n in params:
             if sd[n].grad is None:
                 continue
             d = float((params[n].grad.double().cpu() - sd[n].grad).norm())
-            assert d <= 5e-2 * float(sd[n].grad.norm()) + 1e-5 * scale, (tag, n, d)
-        check_golden(tag, lambda n: params[n].grad, g, 2e-2)
+            assert d <= t_par * float(sd[n].grad.norm()) + 1e-5 * scale, (tag, n, d)
+        check_golden(tag, lambda n: params[n].grad, g, t_gold)

@@ -159,6 +159,53 @@ def test_gpu_gradients_match_oracle_and_reference(tensor_cores, wc, monkeypatch)
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("tensor_cores", [True, False])
+def test_gpu_full_length_gradients_vs_fp64_oracle(tensor_cores, monkeypatch):
+    """BASELINE-length utterances (T=258 tokens, F=803 frames, S=60 225 steps — 471 tiles of 128 steps per batch
+    row, so the persistent multi-tile schedule, the per-batch-row atomic flushes and the weight-gradient chunk
+    ranges are all exercised), B=2 ragged, conditioned phase head: EVERY parameter gradient and the input gradients
+    against the fp64 oracle (about 20 s and 17 GB of host memory on the CPU side)."""
+    from stylish_tts_b200 import engine as E
+
+    monkeypatch.setattr(E, "USE_UMMA", tensor_cores)
+    sp = st.build_model(st.default_model_config()).speech_predictor
+    synth.randomize_(sp, CASE["wseed"])
+    synth.condition_phase_head_(sp)
+    inp = synth.speech_inputs(2, 258, seed=9, ragged=True)
+    taps = {}
+    with torch.no_grad():
+        so.speech_predictor(util.state_dict_of(sp), inp["texts"], inp["text_lengths"], inp["alignment"],
+                            inp["pitch"], inp["energy"], inp["voiced"], inp["style"], inp["denormal_pitch"],
+                            inp["draws"], taps=taps)
+    prior = (taps["har_spec"], taps["har_phase"])
+    assert prior[0].shape[2] == 60225
+    audio_ref, grads_ref, dins_ref, _ = oracle_grads(sp, inp, torch.float64, prior=prior)
+    dev = torch.device("cuda:0")
+    sp = sp.to(dev).train()
+    sp.regularisers = False
+    c = lambda t: t.to(dev)
+    style, pitch, energy = (c(inp[k]).clone().requires_grad_(True) for k in ("style", "pitch", "energy"))
+    out = sp(c(inp["texts"]), c(inp["text_lengths"]), c(inp["alignment"]), pitch, energy, c(inp["voiced"]), style,
+             c(inp["denormal_pitch"]), prior=(c(prior[0]), c(prior[1])))
+    (out.audio * c(cotangent(out.audio.shape))).sum().backward()
+    torch.cuda.synchronize()
+    assert rel_l2(out.audio, audio_ref) < 5e-4
+    tol = 3e-4 if tensor_cores else 1e-4
+    for k, t in (("style", style), ("pitch", pitch), ("energy", energy)):
+        print("input gradient", k, rel_l2(t.grad, dins_ref[k]))
+        assert rel_l2(t.grad, dins_ref[k]) < tol, (k, rel_l2(t.grad, dins_ref[k]))
+    params = dict(sp.named_parameters())
+    tot = torch.cat([params[n].grad.flatten().double().cpu() for n in grads_ref])
+    tot_ref = torch.cat([grads_ref[n].flatten() for n in grads_ref])
+    print("full length: all parameter gradients vs fp64 oracle:", rel_l2(tot, tot_ref))
+    assert rel_l2(tot, tot_ref) < tol, rel_l2(tot, tot_ref)
+    scale = float(tot_ref.norm())
+    for n, gr in grads_ref.items():
+        d = float((params[n].grad.double().cpu() - gr).norm())
+        assert d <= 3 * tol * float(gr.norm()) + 1e-5 * scale, (n, d, float(gr.norm()))
+
+
+@pytest.mark.gpu
 def test_full_size_training_step_is_finite():
     """config 3 size: B=32, 258 tokens, 803 frames; forward + STFT losses + backward"""
     from stylish_tts_b200 import spectral
@@ -292,3 +339,69 @@ def test_graphed_acoustic_step_matches_eager():
     assert torch.allclose(curves[0][0], curves[1][0], rtol=2e-3), (curves[0], curves[1])
     assert torch.allclose(curves[0], curves[1], rtol=0.1), (curves[0], curves[1])
     assert float(curves[1][-1, 1]) < float(curves[1][0, 1])  # the mel loss goes down under the graphed loop too
+
+
+@pytest.mark.gpu
+def test_eval_mode_under_autograd_uses_running_statistics():
+    """model.eval(); model(x) WITHOUT torch.no_grad(): nn.BatchNorm1d semantics of the reference conformer
+    (conformer.py:183) — running statistics are used and left untouched — so the differentiable path must agree
+    with the no_grad engine and must not corrupt the buffers the engine later packs."""
+    dev = torch.device("cuda:0")
+    sp = st.build_model(st.default_model_config()).speech_predictor
+    synth.randomize_(sp, 3)
+    inp = synth.speech_inputs(2, 16, seed=2, ragged=True)
+    sp = sp.to(dev).eval()
+    c = lambda t: t.to(dev)
+    args = [c(inp[k]) for k in ("texts", "text_lengths", "alignment", "pitch", "energy", "voiced", "style",
+                                "denormal_pitch")]
+    draws = {"noise": c(inp["draws"]["noise"])}
+    before = {k: v.clone() for k, v in sp.state_dict().items() if BN in k}
+    with torch.no_grad():
+        ref = sp(*args, source_draws=draws).audio
+    out = sp(*args, source_draws=draws).audio
+    assert out.requires_grad
+    assert rel_l2(out, ref) < 2e-4, rel_l2(out, ref)
+    out.square().mean().backward()
+    torch.cuda.synchronize()
+    for k, v in before.items():
+        assert torch.equal(sp.state_dict()[k], v), k
+    g = dict(sp.named_parameters())[BN + ".weight"].grad
+    assert g is not None and torch.isfinite(g).all() and float(g.abs().max()) > 0
+
+
+@pytest.mark.gpu
+def test_two_stochastic_forwards_before_backward_keep_their_own_masks():
+    """gradient accumulation with a deferred backward: the masks of forward #1 must survive forward #2
+    (the reference's autograd saves the mask per call)."""
+    dev = torch.device("cuda:0")
+    inp = synth.speech_inputs(2, 16, seed=2, ragged=True)
+    c = lambda t: t.to(dev)
+    args = [c(inp[k]) for k in ("texts", "text_lengths", "alignment", "pitch", "energy", "voiced", "style",
+                                "denormal_pitch")]
+    draws = {"noise": c(inp["draws"]["noise"])}
+    prior = None
+
+    def fresh():
+        sp = st.build_model(st.default_model_config()).speech_predictor
+        synth.randomize_(sp, 3)
+        synth.condition_phase_head_(sp)
+        sp.regulariser_seed = 77
+        return sp.to(dev).train()
+
+    import random
+    sp = fresh()
+    random.seed(5)
+    a1 = sp(*args, source_draws=draws).audio
+    a1.square().mean().backward()  # reference behaviour: backward right after its forward
+    g_alone = {n: p.grad.clone() for n, p in sp.named_parameters() if p.grad is not None}
+    sp = fresh()
+    random.seed(5)
+    b1 = sp(*args, source_draws=draws).audio
+    b2 = sp(*args, source_draws=draws).audio  # second stochastic forward BEFORE the first backward
+    assert rel_l2(b1, a1) < 1e-5
+    assert rel_l2(b2, b1) > 1e-3  # new masks
+    b1.square().mean().backward()
+    torch.cuda.synchronize()
+    tot_a = torch.cat([g_alone[n].flatten() for n in sorted(g_alone)])
+    tot_b = torch.cat([dict(sp.named_parameters())[n].grad.flatten() for n in sorted(g_alone)])
+    assert rel_l2(tot_b, tot_a) < 1e-3, rel_l2(tot_b, tot_a)
