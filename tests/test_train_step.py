@@ -163,14 +163,25 @@ def test_gpu_gradients_match_oracle_and_reference(tensor_cores, wc, monkeypatch)
 def test_gpu_full_length_gradients_vs_fp64_oracle(tensor_cores, monkeypatch):
     """BASELINE-length utterances (T=258 tokens, F=803 frames, S=60 225 steps — 471 tiles of 128 steps per batch
     row, so the persistent multi-tile schedule, the per-batch-row atomic flushes and the weight-gradient chunk
-    ranges are all exercised), B=2 ragged, conditioned phase head: EVERY parameter gradient and the input gradients
-    against the fp64 oracle (about 20 s and 17 GB of host memory on the CPU side)."""
+    ranges are all exercised), B=2 ragged: EVERY parameter gradient and the input gradients against the fp64
+    oracle (about 35 s and 17 GB of host memory on the CPU side).
+
+    Conditioning at this length (measured with the reference's own formulas, fp32 vs fp64 on the CPU):
+      * phase head: among 3.9 M bins some have |real + i imag| ~ 0.03 even with the +3 bias of the short cases,
+        and atan2's derivative (-imag, real)/r^2 turns forward rounding into 1.5e-3 (fp32) .. 2e-2 (bf16x3) of
+        gradient error for the WHOLE phase branch — so this case moves the head further out (bias +8, r > 4);
+      * text encoder / decoder: the soft alignment gives every one of the 258 tokens weight e^0/Z in every
+        frame (utils.py:752-791), so `text_encoding @ alignment` is a small signal on a large constant and the
+        decoder's InstanceNorms amplify rounding: the reference formula in fp32 is 1.2e-2 from fp64 on those
+        gradients, whatever the phase head.  They are therefore held to "as close to the exact gradient as the
+        reference's own fp32 evaluation" (3x its error), while the generator — all the S-rate multi-tile
+        kernels — is held to kernel accuracy."""
     from stylish_tts_b200 import engine as E
 
     monkeypatch.setattr(E, "USE_UMMA", tensor_cores)
     sp = st.build_model(st.default_model_config()).speech_predictor
     synth.randomize_(sp, CASE["wseed"])
-    synth.condition_phase_head_(sp)
+    synth.condition_phase_head_(sp, 8.0)
     inp = synth.speech_inputs(2, 258, seed=9, ragged=True)
     taps = {}
     with torch.no_grad():
@@ -180,6 +191,7 @@ def test_gpu_full_length_gradients_vs_fp64_oracle(tensor_cores, monkeypatch):
     prior = (taps["har_spec"], taps["har_phase"])
     assert prior[0].shape[2] == 60225
     audio_ref, grads_ref, dins_ref, _ = oracle_grads(sp, inp, torch.float64, prior=prior)
+    _, grads_32, dins_32, _ = oracle_grads(sp, inp, torch.float32, prior=prior)
     dev = torch.device("cuda:0")
     sp = sp.to(dev).train()
     sp.regularisers = False
@@ -191,18 +203,29 @@ def test_gpu_full_length_gradients_vs_fp64_oracle(tensor_cores, monkeypatch):
     torch.cuda.synchronize()
     assert rel_l2(out.audio, audio_ref) < 5e-4
     tol = 3e-4 if tensor_cores else 1e-4
-    for k, t in (("style", style), ("pitch", pitch), ("energy", energy)):
-        print("input gradient", k, rel_l2(t.grad, dins_ref[k]))
-        assert rel_l2(t.grad, dins_ref[k]) < tol, (k, rel_l2(t.grad, dins_ref[k]))
     params = dict(sp.named_parameters())
-    tot = torch.cat([params[n].grad.flatten().double().cpu() for n in grads_ref])
-    tot_ref = torch.cat([grads_ref[n].flatten() for n in grads_ref])
-    print("full length: all parameter gradients vs fp64 oracle:", rel_l2(tot, tot_ref))
-    assert rel_l2(tot, tot_ref) < tol, rel_l2(tot, tot_ref)
-    scale = float(tot_ref.norm())
-    for n, gr in grads_ref.items():
-        d = float((params[n].grad.double().cpu() - gr).norm())
-        assert d <= 3 * tol * float(gr.norm()) + 1e-5 * scale, (n, d, float(gr.norm()))
+
+    def group(pred):
+        names = [n for n in grads_ref if pred(n)]
+        ref = torch.cat([grads_ref[n].flatten() for n in names])
+        mine = torch.cat([params[n].grad.flatten().double().cpu() for n in names])
+        cpu32 = torch.cat([grads_32[n].flatten().double() for n in names])
+        return rel_l2(mine, ref), rel_l2(cpu32, ref), names
+
+    e_gen, r_gen, gen_names = group(lambda n: n.startswith("generator."))
+    e_up, r_up, _ = group(lambda n: not n.startswith("generator."))
+    print(f"full length: generator gradients vs fp64 oracle {e_gen:.2e} (reference formula in fp32: {r_gen:.2e}); "
+          f"text encoder + decoder {e_up:.2e} (reference formula in fp32: {r_up:.2e})")
+    assert e_gen < tol, e_gen
+    assert e_up < max(tol, 3 * r_up), (e_up, r_up)
+    scale = float(torch.cat([grads_ref[n].flatten() for n in gen_names]).norm())
+    for n in gen_names:  # per parameter, with an absolute floor for the (near) zero-gradient ones
+        d = float((params[n].grad.double().cpu() - grads_ref[n]).norm())
+        assert d <= 3 * tol * float(grads_ref[n].norm()) + 1e-5 * scale, (n, d, float(grads_ref[n].norm()))
+    for k, t in (("style", style), ("pitch", pitch), ("energy", energy)):
+        e, r = rel_l2(t.grad, dins_ref[k]), rel_l2(dins_32[k], dins_ref[k])
+        print(f"input gradient {k}: {e:.2e} (reference formula in fp32: {r:.2e})")
+        assert e < max(tol, 3 * r), (k, e, r)
 
 
 @pytest.mark.gpu

@@ -4,7 +4,7 @@ set -u
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > gpurun_out/gpu.txt 2>&1
 echo "== pytest gpu" 
-timeout 900 python -m pytest tests -m gpu -q --tb=short -rA -p no:cacheprovider > gpurun_out/pytest_gpu.log 2>&1
+timeout 1500 python -m pytest tests -m gpu -q --tb=short -rA -p no:cacheprovider > gpurun_out/pytest_gpu.log 2>&1
 echo "pytest exit $?"
 tail -n 40 gpurun_out/pytest_gpu.log
 echo "== smoke"
