@@ -148,6 +148,11 @@ STY_API int sty_chan_layernorm_fwd(const float* x, const float* res, int64_t x_b
                                    const float* beta, int64_t g_bs, int g_plus_one, float* y,
                                    int64_t y_bs, const float* mask, int B, int C, int T, float eps,
                                    int act, sty_stream_t stream);
+/* same, explicit channel strides x_cs (x and res) / y_cs >= T (pitch-padded rows) */
+STY_API int sty_chan_layernorm_pitched_fwd(const float* x, const float* res, int64_t x_bs, int64_t x_cs,
+                                           const float* gamma, const float* beta, int64_t g_bs, int g_plus_one,
+                                           float* y, int64_t y_bs, int64_t y_cs, const float* mask, int B, int C,
+                                           int T, float eps, int act, sty_stream_t stream);
 
 /* ---- InstanceNorm statistics folded with the style affine ----------------
  * mean/var over T per (b,c) (biased variance), then
@@ -265,6 +270,11 @@ STY_API int sty_source_fwd(const float* pitch, const float* voiced, const float*
 STY_API int sty_stft_fwd(const float* wave, const float* basis_re, const float* basis_im, float* spec,
                  float* phase, int B, int L, int n_fft, int hop, int bins_keep,
                  sty_stream_t stream);
+/* same, outputs with explicit batch / channel strides (rows padded to 16 bytes so that the consumer convs can
+ * fetch them with TMA) */
+STY_API int sty_stft_pitched_fwd(const float* wave, const float* basis_re, const float* basis_im, float* spec,
+                                 float* phase, int64_t out_bs, int64_t out_cs, int B, int L, int n_fft, int hop,
+                                 int bins_keep, sty_stream_t stream);
 
 /* ---- spectral head + conv-iSTFT + tanh ------------------------------------------------
  * logamp, real, imag: (B, bins, S) with batch strides logamp_bs / ri_bs (real and imag may be
@@ -277,6 +287,11 @@ STY_API int sty_istft_head_fwd(const float* logamp, int64_t logamp_bs, const flo
                                const float* imag, int64_t ri_bs, const float* basis_re,
                                const float* basis_im, float* out, int B, int S, int bins, int n_fft,
                                int hop, sty_stream_t stream);
+/* same, inputs with explicit channel strides (pitch-padded rows) */
+STY_API int sty_istft_head_pitched_fwd(const float* logamp, int64_t logamp_bs, int64_t logamp_cs, const float* real,
+                                       const float* imag, int64_t ri_bs, int64_t ri_cs, const float* basis_re,
+                                       const float* basis_im, float* out, int B, int S, int bins, int n_fft,
+                                       int hop, sty_stream_t stream);
 
 /* ---- framed real FFT front-end: STFT -> |X| / phase / mel / log, one kernel -------------------
  * torch.stft(center=True, pad_mode="reflect", onesided) semantics: frame f covers samples

@@ -72,6 +72,8 @@ _SIGNATURES = {
                           _f32, _f32p],
     "sty_chan_layernorm_fwd": [_f32p, _f32p, _i64, _f32p, _f32p, _i64, _i32, _f32p, _i64, _f32p,
                                _i32, _i32, _i32, _f32, _i32, _f32p],
+    "sty_chan_layernorm_pitched_fwd": [_f32p, _f32p, _i64, _i64, _f32p, _f32p, _i64, _i32, _f32p, _i64, _i64,
+                                       _f32p, _i32, _i32, _i32, _f32, _i32, _f32p],
     "sty_instnorm_affine_fwd": [_f32p, _i64, _i64, _f32p, _i64, _f32p, _f32p, _i32, _i32, _i32,
                                 _f32, _f32p],
     "sty_moments_affine_fwd": [_f32p, _f32p, _f32p, _i64, _f32p, _f32p, _i32, _i32, _i32, _f32, _f32p],
@@ -94,6 +96,9 @@ _SIGNATURES = {
     "sty_stft_fwd": [_f32p, _f32p, _f32p, _f32p, _f32p, _i32, _i32, _i32, _i32, _i32, _f32p],
     "sty_istft_head_fwd": [_f32p, _i64, _f32p, _f32p, _i64, _f32p, _f32p, _f32p, _i32, _i32, _i32,
                            _i32, _i32, _f32p],
+    "sty_stft_pitched_fwd": [_f32p, _f32p, _f32p, _f32p, _f32p, _i64, _i64, _i32, _i32, _i32, _i32, _i32, _f32p],
+    "sty_istft_head_pitched_fwd": [_f32p, _i64, _i64, _f32p, _f32p, _i64, _i64, _f32p, _f32p, _f32p, _i32, _i32,
+                                   _i32, _i32, _i32, _f32p],
     # spectral front-end + STFT losses (struct mirror: spectral.SpecArgs)
     "sty_spectrogram_fwd": [_f32p, _f32p],
     "sty_spectrogram_bwd": [_f32p, _f32p, _f32p, _f32p, _f32p, _i64, _f32p],
@@ -235,6 +240,7 @@ def _signature(name: str, args) -> str:
             extra += "+dwln"
         return f"conv1d[ci={a.CI},co={a.CO},k={a.K},d={a.dil},B={a.B},T={a.T}{extra}]"
     pos = {"sty_dwconv_ln_fwd": (9, 10), "sty_chan_layernorm_fwd": (11, 12),
+           "sty_chan_layernorm_pitched_fwd": (13, 14),
            "sty_instnorm_affine_fwd": (8, 9), "sty_attention_fwd": (12, 13)}.get(name)
     if pos:
         return f"{name[4:]}[c={args[pos[0]]},T={args[pos[1]]}]"

@@ -14,7 +14,7 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SOURCES = ["err.cu", "spectral.cu", "backward.cu", "wgrad_umma.cu", "attention_bwd.cu", "image_ops.cu", "conv1d.cu", "conv1d_umma.cu", "norms.cu", "attention.cu", "attention_umma.cu", "source_stft.cu", "misc.cu", "seq_ops.cu", "dropout.cu"]
+SOURCES = ["err.cu", "tma.cu", "spectral.cu", "backward.cu", "wgrad_umma.cu", "attention_bwd.cu", "image_ops.cu", "conv1d.cu", "conv1d_umma.cu", "norms.cu", "attention.cu", "attention_umma.cu", "source_stft.cu", "misc.cu", "seq_ops.cu", "dropout.cu"]
 LIB = os.path.join(HERE, "libstylish_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -46,7 +46,7 @@ def _stamp(target: str, deps) -> None:
 
 def _compile(src: str) -> str:
     obj = os.path.join(HERE, "build", src.replace(".cu", ".o"))
-    deps = [os.path.join(HERE, src), os.path.join(HERE, "common.cuh"), os.path.join(HERE, "umma.cuh"),
+    deps = [os.path.join(HERE, src), os.path.join(HERE, "common.cuh"), os.path.join(HERE, "umma.cuh"), os.path.join(HERE, "tma.cuh"),
             os.path.join(HERE, "..", "..", "include", "stylish_b200.h")]
     if _stale(obj, deps):
         cmd = [NVCC, *FLAGS, "-c", os.path.join(HERE, src), "-o", obj]

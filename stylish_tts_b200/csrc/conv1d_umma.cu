@@ -22,7 +22,10 @@
 // (epilogue) — the three roles hand over through mbarriers, so staging of tile
 // i+1, MMA of tile i and the epilogue of tile i-1 overlap.  Weights stay resident in shared memory when they fit, otherwise
 // they are streamed per input-channel chunk together with the input rows.
-#include "umma.cuh"
+#include <stdlib.h>
+#include <string.h>
+
+#include "tma.cuh"
 
 namespace sty {
 
@@ -41,6 +44,12 @@ struct UmmaPlan {
   int tiles_per_b; // ceil(T / 128)
   int prm_floats;  // floats of the per-channel parameter block (prologue + epilogue)
   int dw_floats;   // IN_MODE 4: two raw input tiles [2][CI][134+1]
+  int tma;         // 1: raw fp32 input tiles arrive by TMA (cp.async.bulk.tensor) into a ring of raw stages
+  int raw_rp;      // TMA: floats per channel row of a raw stage (rows rounded up to a multiple of 4)
+  int raw_stages;  // TMA: ring depth
+  int raw_u4;      // TMA: uint4 per raw stage
+  int raw_shift;   // TMA: the box starts at t0 - pad - raw_shift, a multiple of 4 steps (the hardware wants the
+                   // first element of a box on a 16-byte boundary, measured: tools/scratch/tma_test.cu)
 };
 
 constexpr int kProducerWarps = 8;
@@ -51,6 +60,9 @@ constexpr int kEpilogueWarps = 8;  // 4 lane quadrants x kColParts column parts 
 constexpr int kColParts = kEpilogueWarps / 4;
 constexpr int kThreads = (kEpilogueWarp0 + kEpilogueWarps) * 32;
 constexpr int kMaxStages = 4;
+constexpr int kMaxRaw = 4;
+constexpr int kLoaderWarp = kEpilogueWarp0 + kEpilogueWarps;  // TMA variants only: one more warp
+constexpr int kThreadsTma = kThreads + 32;
 constexpr int kItemBatch = 4;  // (row, 8-channel) items staged per thread per batch: 32 loads in flight
 
 // column sums over the 32 lanes of 16 per-lane values: lanes l and l+16 return sum_lanes v[l & 15]
@@ -76,9 +88,14 @@ __device__ __forceinline__ float warp_colsum16(float (&v)[16], int lane) {
 //           res_scale 1, no mask / scale / shuffle.  Compile-time because the three roles share one
 //           instruction cache: dropping the unused epilogue paths took the fused-front kernel from 0.267 to
 //           0.242 ms.  Only the hot (IN_MODE, OUT_MODE, EPI) combinations are instantiated (pick_kernel).
-template <int IN_MODE, int OUT_MODE, int EPI = 0>
-__global__ void __launch_bounds__(kThreads, 1)
-conv1d_umma_kernel(const sty_conv1d_args p, const UmmaPlan pl) {
+// TMA     : the raw fp32 input tile [ci_chunk][rows] is fetched by one cp.async.bulk.tensor per stage issued by a
+//           loader warp (zero fill outside [0, T)), several stages ahead; the producer warps then convert FROM
+//           SHARED MEMORY (prologue + bf16 hi/lo split).  No register is held across a global-memory latency,
+//           and the bytes in flight per SM are raw_stages x stage size (54-70 KB) instead of 32 KB.
+template <int IN_MODE, int OUT_MODE, int EPI = 0, bool TMA = false>
+__global__ void __launch_bounds__(TMA ? kThreadsTma : kThreads, 1)
+conv1d_umma_kernel(const sty_conv1d_args p, const UmmaPlan pl, const __grid_constant__ CUtensorMap tmap) {
+  static_assert(!(TMA && IN_MODE == 4), "the fused ConvNeXt front has its own kernel for TMA");
   constexpr bool PRO = IN_MODE >= 1 && IN_MODE <= 3;
   constexpr int MT = 128;
   extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -98,12 +115,18 @@ conv1d_umma_kernel(const sty_conv1d_args p, const UmmaPlan pl) {
   float* pro_s = prm;                // [4][CI]: scale, shift, alpha, 1/alpha of the current batch element
   float* epi_s = prm + (IN_MODE == 4 ? 10 : 4) * CI;  // [3][NT]: bias, alpha, 1/alpha
   float* dw_s = prm + pl.prm_floats;  // IN_MODE 4 scratch
-  uint64_t* bars = reinterpret_cast<uint64_t*>(dw_s + pl.dw_floats);
+  // TMA raw ring: 128-byte aligned (all preceding blocks are multiples of 16 B; round up)
+  uint8_t* raw_base = reinterpret_cast<uint8_t*>(dw_s + pl.dw_floats);
+  raw_base += (128u - (smem_u32(raw_base) & 127u)) & 127u;
+  float* raw0 = reinterpret_cast<float*>(raw_base);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(raw_base + (TMA ? (size_t)pl.raw_stages * pl.raw_u4 * 16 : 0));
   uint64_t* x_full = bars;
   uint64_t* x_empty = bars + kMaxStages;
   uint64_t* acc_full = bars + 2 * kMaxStages;
   uint64_t* acc_empty = acc_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint64_t* raw_full = acc_empty + 2;
+  uint64_t* raw_empty = raw_full + kMaxRaw;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(raw_empty + kMaxRaw);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint4* __restrict__ wsplit = reinterpret_cast<const uint4*>(p.w_split);
@@ -118,9 +141,15 @@ conv1d_umma_kernel(const sty_conv1d_args p, const UmmaPlan pl) {
       mbar_init(&acc_full[i], 1);
       mbar_init(&acc_empty[i], kEpilogueWarps * 32);
     }
+    if (TMA) {
+      for (int i = 0; i < pl.raw_stages; ++i) {
+        mbar_init(&raw_full[i], 1);
+        mbar_init(&raw_empty[i], kProducerThreads);
+      }
+    }
     fence_barrier_init();
   }
-  for (int i = tid; i < NT; i += kThreads) {
+  for (int i = tid; i < NT; i += (TMA ? kThreadsTma : kThreads)) {
     const float al = p.out_alpha ? p.out_alpha[co0 + i] : 1.f;
     epi_s[i] = p.bias ? p.bias[co0 + i] : 0.f;
     epi_s[NT + i] = al;
@@ -131,7 +160,7 @@ conv1d_umma_kernel(const sty_conv1d_args p, const UmmaPlan pl) {
     // (dual: [K][CI/8][hi | lo][NT], so that one descriptor spans the hi and the lo rows of a K chunk)
     const int total = K * 2 * (CI >> 3) * NT;
     const int c8n = CI >> 3;
-    for (int idx = tid; idx < total; idx += kThreads) {
+    for (int idx = tid; idx < total; idx += (TMA ? kThreadsTma : kThreads)) {
       const int row = idx / NT, n = idx - row * NT;  // row = blk*(CI/8) + c8, blk = tap*2 + split
       int dst = idx;
       if (dual) {
@@ -333,6 +362,9 @@ conv1d_umma_kernel(const sty_conv1d_args p, const UmmaPlan pl) {
         const int n_items = cc8 * rows;
         int row = tid, c8 = 0;
         while (row >= rows && c8 < cc8) { row -= rows; ++c8; }
+        const int rs = TMA ? (int)(it % (uint32_t)pl.raw_stages) : 0;
+        const float* raw = raw0 + (size_t)rs * pl.raw_u4 * 4;  // [ci_chunk][raw_rp] fp32, row 0 = t0 - pad
+        if constexpr (TMA) mbar_wait(&raw_full[rs], (it / (uint32_t)pl.raw_stages) & 1);
         for (int i0 = tid; i0 < n_items; i0 += kProducerThreads * kItemBatch) {
           float v[kItemBatch][8];
           int irow[kItemBatch], ic8[kItemBatch];
@@ -340,13 +372,20 @@ conv1d_umma_kernel(const sty_conv1d_args p, const UmmaPlan pl) {
           for (int u = 0; u < kItemBatch; ++u) {
             irow[u] = row;
             ic8[u] = c8;
-            const int t = t0 - p.pad + row;
-            const bool ok = (c8 < cc8) && (t >= 0) && (t < p.T);
-            const float* __restrict__ src = xb + (int64_t)(c0 + c8 * 8) * x_cs + t;
+            if constexpr (TMA) {
+              // shared-memory reads: lanes = consecutive rows -> conflict-free; out-of-range steps are zeros
+              const float* src = raw + (c8 < cc8 ? c8 * 8 : 0) * pl.raw_rp + row + pl.raw_shift;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {  // running pointer: 2 integer instructions per load instead of ~5
-              v[u][j] = ok ? *src : 0.f;
-              src += x_cs;
+              for (int j = 0; j < 8; ++j) v[u][j] = src[j * pl.raw_rp];
+            } else {
+              const int t = t0 - p.pad + row;
+              const bool ok = (c8 < cc8) && (t >= 0) && (t < p.T);
+              const float* __restrict__ src = xb + (int64_t)(c0 + c8 * 8) * x_cs + t;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {  // running pointer: 2 integer instructions per load instead of ~5
+                v[u][j] = ok ? *src : 0.f;
+                src += x_cs;
+              }
             }
             row += kProducerThreads;
             while (row >= rows && c8 < cc8) { row -= rows; ++c8; }
@@ -398,6 +437,7 @@ conv1d_umma_kernel(const sty_conv1d_args p, const UmmaPlan pl) {
         }
         fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core proxy
         mbar_arrive(&x_full[s]);
+        if constexpr (TMA) mbar_arrive(&raw_empty[rs]);  // raw stage read: the loader may refill it
       }
     }
   } else if (warp == kMmaWarp) {
@@ -418,7 +458,7 @@ conv1d_umma_kernel(const sty_conv1d_args p, const UmmaPlan pl) {
         const int s = it % NS;
         mbar_wait(&x_full[s], (it / NS) & 1);
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
           // single issuing thread; only the low descriptor word (start address) changes per MMA
           const uint4* Xs = stage0 + (size_t)s * pl.stage_u4;
           const uint32_t ws_addr = pl.resident ? smem_u32(Wres) : smem_u32(Xs + 2 * c8c * rows);
@@ -426,6 +466,8 @@ conv1d_umma_kernel(const sty_conv1d_args p, const UmmaPlan pl) {
           const uint64_t b_d = make_desc(ws_addr, (uint32_t)(dual ? 2 * NT : NT), 8u);
           const uint32_t a_hi32 = (uint32_t)(a_d >> 32), b_hi32 = (uint32_t)(b_d >> 32);
           uint32_t a_t = (uint32_t)a_d, b_t = (uint32_t)b_d;  // low words: (tap 0, kb 0, hi split)
+          // resident weights with a chunked input (TMA plans): this chunk's K rows of the weight block
+          if (pl.resident) b_t += (uint32_t)((c0 >> 3) * (dual ? 2 * NT : NT));
           const uint32_t a_lo_off = (uint32_t)(c8c * rows);    // 16-byte units to the lo-split copy
           const uint32_t b_lo_off = (uint32_t)(wc8 * NT);
           const int kblocks = cc8 >> 1;                         // MMA K = 16 bf16 = two 16-byte chunks
@@ -453,6 +495,25 @@ conv1d_umma_kernel(const sty_conv1d_args p, const UmmaPlan pl) {
           if (ch == pl.n_chunks - 1) umma_commit(&acc_full[a]);  // accumulator complete
         }
         __syncwarp();
+      }
+    }
+  } else if (TMA && warp == kLoaderWarp) {
+    // =========================== TMA loader: one lane keeps raw_stages tiles in flight
+    if (elect_one()) {
+      prefetch_tensormap(&tmap);
+      const uint32_t NR = (uint32_t)pl.raw_stages;
+      const uint32_t bytes = (uint32_t)pl.ci_chunk * (uint32_t)pl.raw_rp * 4u;
+      uint32_t it = 0;
+      for (int tile = tile_begin; tile < tile_end; ++tile) {
+        const int b = tile / pl.tiles_per_b;
+        const int t0 = (tile - b * pl.tiles_per_b) * MT;
+        for (int ch = 0; ch < pl.n_chunks; ++ch, ++it) {
+          const uint32_t r = it % NR;
+          mbar_wait_sleep(&raw_empty[r], ((it / NR) & 1) ^ 1);
+          mbar_arrive_expect_tx(&raw_full[r], bytes);
+          tma_load_3d(raw0 + (size_t)r * pl.raw_u4 * 4, &tmap, &raw_full[r], t0 - p.pad - pl.raw_shift,
+                      ch * pl.ci_chunk, b);
+        }
       }
     }
   } else {
@@ -601,7 +662,7 @@ conv1d_umma_kernel(const sty_conv1d_args p, const UmmaPlan pl) {
 }
 
 // ------------------------------------------------------------------ host side
-static const size_t kSmemBudget = 224 * 1024;
+static const size_t kSmemBudget = 226 * 1024;
 static const size_t kSmemBars = 256;  // barriers + tmem slot
 
 static bool make_plan(const sty_conv1d_args& a, UmmaPlan& pl) {
@@ -697,6 +758,73 @@ bool conv1d_umma_eligible(const sty_conv1d_args& a) {
   return make_plan(a, pl);
 }
 
+// TMA staging of the raw input (see the TMA template parameter): needs 16-byte aligned rows (x_cs, x_bs
+// multiples of 4 floats, aligned base), whole chunks, and room for >= 2 raw stages next to >= 2 operand stages.
+static void plan_tma(const sty_conv1d_args& a, UmmaPlan& pl) {
+  pl.tma = 0;
+  pl.raw_rp = pl.raw_stages = pl.raw_u4 = pl.raw_shift = 0;
+  static const bool off = getenv("STYLISH_B200_TMA") && atoi(getenv("STYLISH_B200_TMA")) == 0;
+  if (off || a.dw_w || a.T < 512 || !tma_layout_ok(a.x, a.x_bs, a.x_cs)) return;
+  const int shift = (4 - (a.pad & 3)) & 3;  // t0 is a multiple of 128: (t0 - pad - shift) % 4 == 0
+  const int rp = (pl.rows + shift + 3) & ~3;
+  if (rp > 256 || a.pad < 0) return;
+  const size_t fixed = (size_t)pl.wres_u4 * 16 + (size_t)(pl.prm_floats + pl.dw_floats) * 4 + kSmemBars + 128;
+  if (pl.resident) {
+    // resident weights: the input may be staged in chunks of channels (the MMA loop offsets the weight rows) —
+    // largest chunk that leaves room for 2 operand stages and 3 raw stages
+    int c = a.CI;
+    for (; c >= 16; c -= 16) {
+      if (a.CI % c != 0 || c > 256) continue;
+      if (fixed + 2 * ((size_t)c * pl.rows * 4) + 3 * ((size_t)c * rp * 4) <= kSmemBudget) break;
+    }
+    if (c < 16) return;
+    pl.ci_chunk = c;
+    pl.n_chunks = a.CI / c;
+    pl.stage_u4 = (int)((size_t)c * pl.rows * 4 / 16);
+  }
+  if (a.CI % pl.ci_chunk != 0 || pl.ci_chunk > 256) return;
+  const size_t raw_sz = (size_t)pl.ci_chunk * rp * 4;
+  const size_t st = (size_t)pl.stage_u4 * 16;
+  if (fixed + 2 * st + 2 * raw_sz > kSmemBudget) return;
+  int ns = 2, nr = 2;
+  while (nr < kMaxRaw && fixed + ns * st + (nr + 1) * raw_sz <= kSmemBudget) ++nr;
+  while (ns < 3 && fixed + (ns + 1) * st + nr * raw_sz <= kSmemBudget) ++ns;
+  pl.tma = 1;
+  pl.raw_shift = shift;
+  pl.raw_rp = rp;
+  pl.raw_stages = nr;
+  pl.raw_u4 = (int)(raw_sz / 16);
+  pl.n_stages = ns;
+}
+
+using KernPtr = void (*)(const sty_conv1d_args, const UmmaPlan, const CUtensorMap);
+
+template <bool TMA>
+static KernPtr pick_kernel(const sty_conv1d_args& a) {
+  const int im = umma_in_mode(a), om = umma_out_mode(a);
+  // specialised epilogues of the S-rate generator convs (see EPI)
+  const bool bare = !a.out_mask && a.shuffle <= 1 && a.out_scale == 1.0f;
+  if (bare && !a.res) {
+    if (im == 0 && om == 0) return conv1d_umma_kernel<0, 0, 1, TMA>;  // k21 input convs
+    if (im == 0 && om == 1) return conv1d_umma_kernel<0, 1, 1, TMA>;  // pwconv1 + Snake (training graph)
+    if (im == 3 && om == 0) return conv1d_umma_kernel<3, 0, 1, TMA>;  // AdaIN + Snake -> k11 (convs1)
+  } else if (bare && a.res && a.res_scale == 1.0f) {
+    if (im == 1 && om == 0) return conv1d_umma_kernel<1, 0, 2, TMA>;  // GRN scale -> pwconv2 + residual
+    if (im == 3 && om == 0) return conv1d_umma_kernel<3, 0, 2, TMA>;  // AdaIN + Snake -> k11 + residual (convs2)
+  }
+  static const KernPtr table[4][4] = {
+      {conv1d_umma_kernel<0, 0, 0, TMA>, conv1d_umma_kernel<0, 1, 0, TMA>, conv1d_umma_kernel<0, 2, 0, TMA>,
+       conv1d_umma_kernel<0, 3, 0, TMA>},
+      {conv1d_umma_kernel<1, 0, 0, TMA>, conv1d_umma_kernel<1, 1, 0, TMA>, conv1d_umma_kernel<1, 2, 0, TMA>,
+       conv1d_umma_kernel<1, 3, 0, TMA>},
+      {conv1d_umma_kernel<2, 0, 0, TMA>, conv1d_umma_kernel<2, 1, 0, TMA>, conv1d_umma_kernel<2, 2, 0, TMA>,
+       conv1d_umma_kernel<2, 3, 0, TMA>},
+      {conv1d_umma_kernel<3, 0, 0, TMA>, conv1d_umma_kernel<3, 1, 0, TMA>, conv1d_umma_kernel<3, 2, 0, TMA>,
+       conv1d_umma_kernel<3, 3, 0, TMA>}};
+  if (im >= 0 && im < 4) return table[im][om];
+  return nullptr;
+}
+
 int conv1d_umma_launch(const sty_conv1d_args& a, cudaStream_t st) {
   UmmaPlan pl;
   if (!make_plan(a, pl)) {
@@ -708,27 +836,29 @@ int conv1d_umma_launch(const sty_conv1d_args& a, cudaStream_t st) {
     sms = sty_device_sm_count();
     if (sms <= 0) sms = 148;
   }
+  plan_tma(a, pl);
+  CUtensorMap tmap;
+  memset(&tmap, 0, sizeof(tmap));
+  if (pl.tma && !make_tmap_bct(&tmap, a.x, a.B, a.CI, a.T, a.x_bs, a.x_cs, pl.raw_rp, pl.ci_chunk)) {
+    UmmaPlan again;
+    make_plan(a, again);
+    pl = again;
+    pl.tma = pl.raw_rp = pl.raw_stages = pl.raw_u4 = pl.raw_shift = 0;
+  }
   const size_t smem = (size_t)pl.wres_u4 * 16 + (size_t)pl.n_stages * pl.stage_u4 * 16 +
-                      (size_t)(pl.prm_floats + pl.dw_floats) * 4 + kSmemBars;
-  using KernPtr = void (*)(const sty_conv1d_args, const UmmaPlan);
-  static const KernPtr table[5][4] = {
-      {conv1d_umma_kernel<0, 0>, conv1d_umma_kernel<0, 1>, conv1d_umma_kernel<0, 2>, conv1d_umma_kernel<0, 3>},
-      {conv1d_umma_kernel<1, 0>, conv1d_umma_kernel<1, 1>, conv1d_umma_kernel<1, 2>, conv1d_umma_kernel<1, 3>},
-      {conv1d_umma_kernel<2, 0>, conv1d_umma_kernel<2, 1>, conv1d_umma_kernel<2, 2>, conv1d_umma_kernel<2, 3>},
-      {conv1d_umma_kernel<3, 0>, conv1d_umma_kernel<3, 1>, conv1d_umma_kernel<3, 2>, conv1d_umma_kernel<3, 3>},
-      {conv1d_umma_kernel<4, 0>, conv1d_umma_kernel<4, 1>, conv1d_umma_kernel<4, 2>, conv1d_umma_kernel<4, 3>}};
-  KernPtr kern = table[umma_in_mode(a)][umma_out_mode(a)];
-  {  // specialised epilogues of the S-rate generator convs (see EPI)
-    const int im = umma_in_mode(a), om = umma_out_mode(a);
-    const bool bare = !a.out_mask && a.shuffle <= 1 && a.out_scale == 1.0f;
-    if (bare && !a.res) {
-      if (im == 0 && om == 0) kern = conv1d_umma_kernel<0, 0, 1>;       // k21 input convs
-      else if (im == 0 && om == 1) kern = conv1d_umma_kernel<0, 1, 1>;  // pwconv1 + Snake (training graph)
-      else if (im == 3 && om == 0) kern = conv1d_umma_kernel<3, 0, 1>;  // AdaIN + Snake -> k11 (convs1)
-    } else if (bare && a.res && a.res_scale == 1.0f) {
-      if (im == 1 && om == 0) kern = conv1d_umma_kernel<1, 0, 2>;       // GRN scale -> pwconv2 + residual
-      else if (im == 3 && om == 0) kern = conv1d_umma_kernel<3, 0, 2>;  // AdaIN + Snake -> k11 + residual (convs2)
-    }
+                      (size_t)(pl.prm_floats + pl.dw_floats) * 4 + kSmemBars +
+                      (pl.tma ? (size_t)pl.raw_stages * pl.raw_u4 * 16 + 128 : 128);
+  KernPtr kern = nullptr;
+  if (umma_in_mode(a) == 4) {
+    static const KernPtr front[4] = {conv1d_umma_kernel<4, 0>, conv1d_umma_kernel<4, 1>, conv1d_umma_kernel<4, 2>,
+                                     conv1d_umma_kernel<4, 3>};
+    kern = front[umma_out_mode(a)];
+  } else {
+    kern = pl.tma ? pick_kernel<true>(a) : pick_kernel<false>(a);
+  }
+  if (!kern) {
+    set_error("conv1d_umma: no kernel for this prologue / epilogue");
+    return STY_ERR_BAD_ARG;
   }
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const int64_t n_tiles = (int64_t)a.B * pl.tiles_per_b;
@@ -741,7 +871,7 @@ int conv1d_umma_launch(const sty_conv1d_args& a, cudaStream_t st) {
     if (gx > n_tiles) gx = (int)n_tiles;
   }
   dim3 grid(gx, n_co, 1);
-  kern<<<grid, kThreads, smem, st>>>(a, pl);
+  kern<<<grid, pl.tma ? kThreadsTma : kThreads, smem, st>>>(a, pl, tmap);
   STY_CHECK_LAUNCH("conv1d_umma");
   return STY_OK;
 }

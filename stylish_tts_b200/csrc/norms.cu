@@ -55,7 +55,8 @@ __global__ void __launch_bounds__(128)
 chan_layernorm_kernel(const float* __restrict__ xin, const float* __restrict__ resin, int64_t x_bs,
                       const float* __restrict__ gamma, const float* __restrict__ beta,
                       int64_t g_bs, int g_plus_one, float* __restrict__ yout, int64_t y_bs,
-                      const float* __restrict__ mask, int C, int T, float eps, int act) {
+                      const float* __restrict__ mask, int C, int T, float eps, int act, int64_t x_cs,
+                      int64_t y_cs) {
   const int b = blockIdx.y;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= T) return;
@@ -72,8 +73,8 @@ chan_layernorm_kernel(const float* __restrict__ xin, const float* __restrict__ r
     float s = 0.f;
 #pragma unroll
     for (int c = 0; c < CREG; ++c) {
-      v[c] = x[base + (int64_t)c * T];
-      if (res) v[c] += res[base + (int64_t)c * T];
+      v[c] = x[base + (int64_t)c * x_cs];
+      if (res) v[c] += res[base + (int64_t)c * x_cs];
       s += v[c];
     }
     const float mean = s * invC;
@@ -88,30 +89,30 @@ chan_layernorm_kernel(const float* __restrict__ xin, const float* __restrict__ r
     for (int c = 0; c < CREG; ++c) {
       const float gg = g_plus_one ? 1.0f + g[c] : g[c];
       float o = (v[c] - mean) * rstd * gg + be[c];
-      y[base + (int64_t)c * T] = act_apply(o, act) * m;
+      y[base + (int64_t)c * y_cs] = act_apply(o, act) * m;
     }
   } else {
     float s = 0.f;
     for (int c = 0; c < C; ++c) {
-      float v = x[base + (int64_t)c * T];
-      if (res) v += res[base + (int64_t)c * T];
+      float v = x[base + (int64_t)c * x_cs];
+      if (res) v += res[base + (int64_t)c * x_cs];
       s += v;
     }
     const float mean = s * invC;
     float q = 0.f;
     for (int c = 0; c < C; ++c) {
-      float v = x[base + (int64_t)c * T];
-      if (res) v += res[base + (int64_t)c * T];
+      float v = x[base + (int64_t)c * x_cs];
+      if (res) v += res[base + (int64_t)c * x_cs];
       const float d = v - mean;
       q = fmaf(d, d, q);
     }
     const float rstd = 1.0f / sqrtf(q * invC + eps);
     for (int c = 0; c < C; ++c) {
-      float v = x[base + (int64_t)c * T];
-      if (res) v += res[base + (int64_t)c * T];
+      float v = x[base + (int64_t)c * x_cs];
+      if (res) v += res[base + (int64_t)c * x_cs];
       const float gg = g_plus_one ? 1.0f + g[c] : g[c];
       float o = (v - mean) * rstd * gg + be[c];
-      y[base + (int64_t)c * T] = act_apply(o, act) * m;
+      y[base + (int64_t)c * y_cs] = act_apply(o, act) * m;
     }
   }
 }
@@ -331,21 +332,21 @@ extern "C" int sty_instnorm_affine_fwd(const float* x, int64_t x_bs, int64_t x_c
   return STY_OK;
 }
 
-extern "C" int sty_chan_layernorm_fwd(const float* x, const float* res, int64_t x_bs,
-                                      const float* gamma, const float* beta, int64_t g_bs,
-                                      int g_plus_one, float* y, int64_t y_bs, const float* mask,
-                                      int B, int C, int T, float eps, int act,
-                                      sty_stream_t stream) {
+extern "C" int sty_chan_layernorm_pitched_fwd(const float* x, const float* res, int64_t x_bs, int64_t x_cs,
+                                              const float* gamma, const float* beta, int64_t g_bs,
+                                              int g_plus_one, float* y, int64_t y_bs, int64_t y_cs,
+                                              const float* mask, int B, int C, int T, float eps, int act,
+                                              sty_stream_t stream) {
   STY_REQUIRE(x && gamma && beta && y, "chan_layernorm: null pointer");
-  STY_REQUIRE(B > 0 && C > 0 && T > 0, "chan_layernorm: bad shape");
+  STY_REQUIRE(B > 0 && C > 0 && T > 0 && x_cs >= T && y_cs >= T, "chan_layernorm: bad shape");
   dim3 grid(cdiv(T, 128), B);
   cudaStream_t st = as_stream(stream);
 #define LAUNCH(CR)                                                                               \
   chan_layernorm_kernel<CR><<<grid, 128, 0, st>>>(x, res, x_bs, gamma, beta, g_bs, g_plus_one, y, \
-                                                  y_bs, mask, C, T, eps, act)
+                                                  y_bs, mask, C, T, eps, act, x_cs, y_cs)
   if (C == 32) LAUNCH(32);
   else if (C == 64) LAUNCH(64);
-  else if (C <= 256) {
+  else if (C <= 256 && x_cs == T && y_cs == T) {
     constexpr int TT = 32;
     const size_t smem = ((size_t)C * (TT + 1) + 256) * sizeof(float);
     dim3 g2(cdiv(T, TT), B);
@@ -355,6 +356,15 @@ extern "C" int sty_chan_layernorm_fwd(const float* x, const float* res, int64_t 
 #undef LAUNCH
   STY_CHECK_LAUNCH("chan_layernorm");
   return STY_OK;
+}
+
+extern "C" int sty_chan_layernorm_fwd(const float* x, const float* res, int64_t x_bs,
+                                      const float* gamma, const float* beta, int64_t g_bs,
+                                      int g_plus_one, float* y, int64_t y_bs, const float* mask,
+                                      int B, int C, int T, float eps, int act,
+                                      sty_stream_t stream) {
+  return sty_chan_layernorm_pitched_fwd(x, res, x_bs, T, gamma, beta, g_bs, g_plus_one, y, y_bs, T, mask, B, C, T,
+                                        eps, act, stream);
 }
 
 extern "C" int sty_dwconv_ln_fwd(const float* x, int64_t x_bs, const float* w, const float* bias,

@@ -120,7 +120,7 @@ template <int NFFT>
 __global__ void __launch_bounds__(128)
 stft_kernel(const float* __restrict__ wave, const float* __restrict__ basis_re,
             const float* __restrict__ basis_im, float* __restrict__ spec,
-            float* __restrict__ phase, int L, int hop, int S, int bins_keep) {
+            float* __restrict__ phase, int64_t o_bs, int64_t o_cs, int L, int hop, int S, int bins_keep) {
   extern __shared__ __align__(16) float sm[];
   float* bre = sm;                      // [bins_keep][NFFT]
   float* bim = sm + bins_keep * NFFT;   // [bins_keep][NFFT]
@@ -157,7 +157,7 @@ stft_kernel(const float* __restrict__ wave, const float* __restrict__ basis_re,
       im = fmaf(x[n + 2], ci.z, im); im = fmaf(x[n + 3], ci.w, im);
     }
     const float mag = sqrtf(re * re + im * im + 1e-14f);
-    const int64_t o = ((int64_t)b * bins_keep + kb) * S + f;
+    const int64_t o = (int64_t)b * o_bs + (int64_t)kb * o_cs + f;
     spec[o] = mag;
     phase[o] = atan2f(im / mag, re / mag);
   }
@@ -167,8 +167,8 @@ stft_kernel(const float* __restrict__ wave, const float* __restrict__ basis_re,
 // thread = HOP consecutive output samples.  R = NFFT/HOP frames overlap each sample.
 template <int NFFT, int HOP, int BINS, int MT>
 __global__ void __launch_bounds__(MT)
-istft_head_kernel(const float* __restrict__ logamp, int64_t logamp_bs,
-                  const float* __restrict__ real, const float* __restrict__ imag, int64_t ri_bs,
+istft_head_kernel(const float* __restrict__ logamp, int64_t logamp_bs, int64_t logamp_cs,
+                  const float* __restrict__ real, const float* __restrict__ imag, int64_t ri_bs, int64_t ri_cs,
                   const float* __restrict__ basis_re, const float* __restrict__ basis_im,
                   float* __restrict__ out, int S) {
   static_assert(HOP == 4, "vectorised basis loads assume hop 4");
@@ -196,8 +196,8 @@ istft_head_kernel(const float* __restrict__ logamp, int64_t logamp_bs,
     float re = 0.f, im = 0.f;
     if (fl < FT && f >= 0 && f <= S) {
       const int fs = min(f, S - 1);  // replicate-pad of one frame (generator.py:784-785)
-      const int64_t o = (int64_t)kb * S + fs;
-      const float mag = expf(logamp[(int64_t)b * logamp_bs + o]);
+      const int64_t o = (int64_t)kb * ri_cs + fs;
+      const float mag = expf(logamp[(int64_t)b * logamp_bs + (int64_t)kb * logamp_cs + fs]);
       // cos(atan2(y, x)) = x/|z|, sin(atan2(y, x)) = y/|z| (atan2(0, 0) = 0 -> cos 1, sin 0): one rsqrt
       // instead of atan2f + cosf + sinf; the operands are scaled first so x^2 + y^2 cannot over/underflow
       const float xr = real[(int64_t)b * ri_bs + o], yi = imag[(int64_t)b * ri_bs + o];
@@ -260,31 +260,40 @@ extern "C" int sty_source_fwd(const float* pitch, const float* voiced, const flo
   return STY_OK;
 }
 
-extern "C" int sty_stft_fwd(const float* wave, const float* basis_re, const float* basis_im,
-                            float* spec, float* phase, int B, int L, int n_fft, int hop,
-                            int bins_keep, sty_stream_t stream) {
+extern "C" int sty_stft_pitched_fwd(const float* wave, const float* basis_re, const float* basis_im,
+                                    float* spec, float* phase, int64_t out_bs, int64_t out_cs, int B, int L,
+                                    int n_fft, int hop, int bins_keep, sty_stream_t stream) {
   STY_REQUIRE(wave && basis_re && basis_im && spec && phase, "stft: null pointer");
   STY_REQUIRE(n_fft == 64, "stft: built for n_fft=64 (got %d)", n_fft);
   STY_REQUIRE(B > 0 && L > 0 && hop > 0 && L % hop == 0 && bins_keep > 0 && bins_keep <= n_fft / 2 + 1,
               "stft: bad shape");
   const int S = L / hop;  // frames kept (the trailing frame is dropped, generator.py:725,728)
+  STY_REQUIRE(out_cs >= S && out_bs >= out_cs * bins_keep, "stft: output strides too small");
   const size_t smem = ((size_t)2 * bins_keep * n_fft + 127 * hop + n_fft) * sizeof(float);
   STY_REQUIRE(smem <= 48 * 1024, "stft: hop too large for the staging buffer");
   dim3 grid(cdiv(S, 128), B);
-  stft_kernel<64><<<grid, 128, smem, as_stream(stream)>>>(wave, basis_re, basis_im, spec, phase, L,
-                                                         hop, S, bins_keep);
+  stft_kernel<64><<<grid, 128, smem, as_stream(stream)>>>(wave, basis_re, basis_im, spec, phase, out_bs, out_cs,
+                                                         L, hop, S, bins_keep);
   STY_CHECK_LAUNCH("stft");
   return STY_OK;
 }
 
-extern "C" int sty_istft_head_fwd(const float* logamp, int64_t logamp_bs, const float* real,
-                                  const float* imag, int64_t ri_bs, const float* basis_re,
-                                  const float* basis_im, float* out, int B, int S, int bins,
-                                  int n_fft, int hop, sty_stream_t stream) {
+extern "C" int sty_stft_fwd(const float* wave, const float* basis_re, const float* basis_im,
+                            float* spec, float* phase, int B, int L, int n_fft, int hop,
+                            int bins_keep, sty_stream_t stream) {
+  const int64_t S = hop > 0 ? L / hop : 0;
+  return sty_stft_pitched_fwd(wave, basis_re, basis_im, spec, phase, S * bins_keep, S, B, L, n_fft, hop,
+                              bins_keep, stream);
+}
+
+extern "C" int sty_istft_head_pitched_fwd(const float* logamp, int64_t logamp_bs, int64_t logamp_cs,
+                                          const float* real, const float* imag, int64_t ri_bs, int64_t ri_cs,
+                                          const float* basis_re, const float* basis_im, float* out, int B, int S,
+                                          int bins, int n_fft, int hop, sty_stream_t stream) {
   STY_REQUIRE(logamp && real && imag && basis_re && basis_im && out, "istft_head: null pointer");
   STY_REQUIRE(n_fft == 64 && hop == 4 && bins == 32,
               "istft_head: built for n_fft=64 hop=4 bins=32 (got %d %d %d)", n_fft, hop, bins);
-  STY_REQUIRE(B > 0 && S > 0, "istft_head: bad shape");
+  STY_REQUIRE(B > 0 && S > 0 && logamp_cs >= S && ri_cs >= S, "istft_head: bad shape");
   constexpr int MT = 128, R = 16, FTP = (MT + R - 1 + 3) & ~3;
   const size_t smem = ((size_t)2 * 32 * 64 + 2 * 32 * FTP) * sizeof(float);
   auto kern = istft_head_kernel<64, 4, 32, MT>;
@@ -294,8 +303,16 @@ extern "C" int sty_istft_head_fwd(const float* logamp, int64_t logamp_bs, const 
     attr_set = true;
   }
   dim3 grid(cdiv(S, MT), B);
-  kern<<<grid, MT, smem, as_stream(stream)>>>(logamp, logamp_bs, real, imag, ri_bs, basis_re,
+  kern<<<grid, MT, smem, as_stream(stream)>>>(logamp, logamp_bs, logamp_cs, real, imag, ri_bs, ri_cs, basis_re,
                                               basis_im, out, S);
   STY_CHECK_LAUNCH("istft_head");
   return STY_OK;
+}
+
+extern "C" int sty_istft_head_fwd(const float* logamp, int64_t logamp_bs, const float* real,
+                                  const float* imag, int64_t ri_bs, const float* basis_re,
+                                  const float* basis_im, float* out, int B, int S, int bins,
+                                  int n_fft, int hop, sty_stream_t stream) {
+  return sty_istft_head_pitched_fwd(logamp, logamp_bs, S, real, imag, ri_bs, S, basis_re, basis_im, out, B, S,
+                                    bins, n_fft, hop, stream);
 }

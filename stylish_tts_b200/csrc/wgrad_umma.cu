@@ -269,7 +269,7 @@ conv1d_wgrad_umma_kernel(const sty_conv1d_wgrad_args p, const WgPlan pl) {
       const uint32_t s = it % (uint32_t)pl.stages;
       mbar_wait(&full[s], (it / (uint32_t)pl.stages) & 1u);
       tc_fence_after();
-      if (lane == 0) {
+      if (elect_one()) {
         const uint4* Ms = stage0 + (size_t)s * pl.stage_u4;
         const uint32_t m_addr = smem_u32(Ms), n_addr = smem_u32(Ms + 2 * m_plane);
         // blocked sides: K blocks are n_groups (m_groups) core matrices apart, groups adjacent (LBO = 8*groups, SBO = 8)

@@ -27,6 +27,14 @@ UMMA_MIN_T = 64
 FUSE_STATS = os.environ.get("STYLISH_B200_FUSE_STATS", "1") != "0"
 
 
+def empty_bct(B: int, C: int, T: int, device) -> torch.Tensor:
+    """(B,C,T) fp32 activation whose rows start on 16-byte boundaries (row pitch = T rounded up to 4 floats):
+    what the TMA loads of the tensor-core convs need (`cp.async.bulk.tensor`: base and strides multiples of
+    16 bytes).  T = 75 * frames is odd for an odd frame count (60 225 at the BASELINE shapes)."""
+    Tp = (T + 3) & ~3
+    return torch.empty((B, C, Tp), device=device, dtype=torch.float32)[:, :, :T]
+
+
 def split_bf16(w_oik: torch.Tensor) -> torch.Tensor:
     """(CO,CI,K) fp32 -> bf16 (hi, lo) pair in the UMMA K-major layout [K][2][CI/8][CO][8]."""
     co, ci, k = w_oik.shape
@@ -64,8 +72,9 @@ def conv1d(x, cw: ConvW, *, dil=1, out=None, res=None, in_scale=None, in_shift=N
     assert CI == cw.CI, (CI, cw.CI)
     x_bs, x_cs = L._bct(x, "x")
     s = shuffle if shuffle > 1 else 1
-    if out is None:
-        out = torch.empty((B, cw.CO // s, T * s), device=x.device, dtype=torch.float32)
+    if out is None:  # same row pitch policy as the input: pitch-padded in, pitch-padded out
+        alloc = empty_bct if x_cs != T else (lambda *a: torch.empty(a[:3], device=a[3], dtype=torch.float32))
+        out = alloc(B, cw.CO // s, T * s, x.device)
     assert out.shape == (B, cw.CO // s, T * s), (out.shape, (B, cw.CO // s, T * s))
     y_bs, y_cs = L._bct(out, "out")
     a = ConvArgs()
@@ -99,16 +108,20 @@ def chan_layernorm(x, gamma, beta, *, eps, res=None, g_bs=0, plus_one=False, out
                    act=ACT_NONE):
     B, Cc, T = x.shape
     x_bs, x_cs = L._bct(x, "x")
-    assert x_cs == T
     if res is not None:
         assert res.stride() == x.stride()
     if out is None:
-        out = torch.empty((B, Cc, T), device=x.device, dtype=torch.float32)
+        out = empty_bct(B, Cc, T, x.device) if x_cs != T else torch.empty((B, Cc, T), device=x.device,
+                                                                          dtype=torch.float32)
     y_bs, y_cs = L._bct(out, "out")
-    assert y_cs == T
-    L.call("sty_chan_layernorm_fwd", x.data_ptr(), L.ptr(res), x_bs, gamma.data_ptr(),
-           beta.data_ptr(), g_bs, int(plus_one), out.data_ptr(), y_bs, L.ptr(mask), B, Cc, T,
-           eps, act, L.stream_ptr())
+    if x_cs == T and y_cs == T:
+        L.call("sty_chan_layernorm_fwd", x.data_ptr(), L.ptr(res), x_bs, gamma.data_ptr(),
+               beta.data_ptr(), g_bs, int(plus_one), out.data_ptr(), y_bs, L.ptr(mask), B, Cc, T,
+               eps, act, L.stream_ptr())
+    else:  # pitch-padded rows
+        L.call("sty_chan_layernorm_pitched_fwd", x.data_ptr(), L.ptr(res), x_bs, x_cs, gamma.data_ptr(),
+               beta.data_ptr(), g_bs, int(plus_one), out.data_ptr(), y_bs, y_cs, L.ptr(mask), B, Cc, T,
+               eps, act, L.stream_ptr())
     return out
 
 
@@ -474,7 +487,7 @@ class SpeechEngine:
         inter = blk["pw1"].CO
         sumsq = torch.zeros((B, inter), device=x.device, dtype=torch.float32)
         fused_front = (USE_UMMA and blk["pw1"].split is not None and Cc <= 64 and Cc % 16 == 0
-                       and T >= UMMA_MIN_T and x.stride(1) == T)
+                       and T >= UMMA_MIN_T and x.stride(2) == 1)
         if fused_front:  # depthwise k7 + LN + AdaLN computed by the pointwise conv's producer warps
             hb = conv1d(x, blk["pw1"], out_act=ACT_SNAKE, out_alpha=blk["snake"], out_sumsq=sumsq,
                         dwln=(blk["dw_w"], blk["dw_b"], gb, J, 1e-6))
@@ -534,10 +547,11 @@ class SpeechEngine:
                H, float(mc.sample_rate), 0.1, 0.003, 10.0, L.stream_ptr())
         hop_s = hop // 75
         S = Lw // hop_s
-        spec = torch.empty((B, P.hidden_s, S), device=dev, dtype=torch.float32)
-        phase = torch.empty_like(spec)
-        L.call("sty_stft_fwd", wave.data_ptr(), P.stft_f_re.data_ptr(), P.stft_f_im.data_ptr(),
-               spec.data_ptr(), phase.data_ptr(), B, Lw, 64, hop_s, P.hidden_s, L.stream_ptr())
+        spec = empty_bct(B, P.hidden_s, S, dev)
+        phase = empty_bct(B, P.hidden_s, S, dev)
+        L.call("sty_stft_pitched_fwd", wave.data_ptr(), P.stft_f_re.data_ptr(), P.stft_f_im.data_ptr(),
+               spec.data_ptr(), phase.data_ptr(), spec.stride(0), spec.stride(1), B, Lw, 64, hop_s, P.hidden_s,
+               L.stream_ptr())
         if taps is not None:
             taps["prior_wave"] = wave
         return spec, phase
@@ -554,14 +568,14 @@ class SpeechEngine:
             taps["conformer"] = x.clone()
         if prior is None:
             har_spec, har_phase = self.harmonic_prior(P, pitch, voiced, noise, taps)
-        else:
-            har_spec, har_phase = prior
+        else:  # injected (parity tests): same pitch-padded layout as the computed prior
+            har_spec, har_phase = (empty_bct(*t.shape, dev).copy_(t) for t in prior)
         if taps is not None:
             taps["har_spec"], taps["har_phase"] = har_spec, har_phase
         S = har_spec.shape[2]
         Hs = P.hidden_s
         # phase-head input: [upsampled mel | logamp prior | phase prior] in one buffer
-        pin = torch.empty((B, 3 * Hs, S), device=dev, dtype=torch.float32)
+        pin = empty_bct(B, 3 * Hs, S, dev)
         mom = torch.zeros((2, 2, B, Hs), device=dev, dtype=torch.float32)
         lp = conv1d(har_spec, P.amp_prior_conv, out=pin[:, Hs:2 * Hs], out_sum=mom[0, 0], out_sumsq=mom[0, 1])
         self.gen_block(P, P.amp_prior_block, lp, h, mom[0])
@@ -592,8 +606,8 @@ class SpeechEngine:
             taps["logamp"], taps["real"], taps["imag"] = logamp, ri[:, :Hs], ri[:, Hs:]
         hop_s = P.mc.hop_length // 75
         audio = torch.empty((B, 1, S * hop_s), device=dev, dtype=torch.float32)
-        L.call("sty_istft_head_fwd", logamp.data_ptr(), logamp.stride(0), ri.data_ptr(),
-               ri.data_ptr() + 4 * Hs * S, ri.stride(0), P.stft_b_re.data_ptr(),
+        L.call("sty_istft_head_pitched_fwd", logamp.data_ptr(), logamp.stride(0), logamp.stride(1), ri.data_ptr(),
+               ri[:, Hs:].data_ptr(), ri.stride(0), ri.stride(1), P.stft_b_re.data_ptr(),
                P.stft_b_im.data_ptr(), audio.data_ptr(), B, S, Hs, 64, hop_s, L.stream_ptr())
         return audio
 

@@ -51,7 +51,7 @@ def test_forward_plumbing(recorder, monkeypatch):
     cnt = collections.Counter(recorder)
     # 8 encoder layers x (qkv, o, ffn1, ffn2) + prenet 3 + proj + proj_m ...
     assert cnt["sty_attention_fwd"] == 8 + 1
-    assert cnt["sty_source_fwd"] == 1 and cnt["sty_stft_fwd"] == 1 and cnt["sty_istft_head_fwd"] == 1
+    assert cnt["sty_source_fwd"] == 1 and cnt["sty_stft_pitched_fwd"] == 1 and cnt["sty_istft_head_pitched_fwd"] == 1
     # C<=64 ConvNeXt fronts are fused into the pointwise conv (tensor-core path) when T >= 128
     assert cnt["sty_dwconv_ln_fwd"] == 5 + 1
     assert cnt["sty_grn_scale_fwd"] == 16

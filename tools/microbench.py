@@ -16,7 +16,7 @@ d = torch.device("cuda:0")
 
 
 def conv_case(ci, co, k, dil=1, T=S, pro=None, out_act=0, ssq=False, res=False, shuffle=0, dwln=False):
-    x = torch.randn(B, ci, T, device=d)
+    x = E.empty_bct(B, ci, T, d).normal_()  # pitch-padded rows, like the engine's S-rate activations (TMA path)
     w = E.ConvW(torch.randn(co, ci, k, device=d) / math.sqrt(ci * k), torch.randn(co, device=d))
     kw = {}
     if pro:
@@ -36,9 +36,9 @@ def conv_case(ci, co, k, dil=1, T=S, pro=None, out_act=0, ssq=False, res=False, 
         kw["dwln"] = (torch.randn(ci, 7, device=d) * 0.3, torch.randn(ci, device=d) * 0.1,
                       torch.randn(B, 2 * ci, device=d) * 0.3, 2 * ci, 1e-6)
     s = shuffle if shuffle > 1 else 1
-    out = torch.empty(B, co // s, T * s, device=d)
+    out = E.empty_bct(B, co // s, T * s, d)
     if res:
-        kw["res"] = torch.randn_like(out)
+        kw["res"] = E.empty_bct(B, co // s, T * s, d).normal_()
     flops = 2.0 * B * T * ci * co * k
     byts = 4.0 * B * T * (ci + co + (co if res else 0))
     return (lambda: E.conv1d(x, w, dil=dil, out=out, out_act=out_act, shuffle=shuffle, **kw)), flops, byts
