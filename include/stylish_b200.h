@@ -136,6 +136,20 @@ STY_API int sty_dwconv_ln_fwd(const float* x, int64_t x_bs, const float* w, cons
                               const float* gb, int64_t gb_bs, float* y, int64_t y_bs, int B, int C,
                               int T, float eps, sty_stream_t stream);
 
+/* ---- GeneratorConvNeXtBlock, fused, without the 4C-wide intermediate ------------------------------
+ * y = x + W2 ( gs[b,:] * Snake(W1 AdaLN(LN_C(dwconv7(x))) + b1) ) + b2      (conv_next.py:80-93, GRN :7-18;
+ * gs = 1 + grn_gamma * ||h||_t / (mean_j ||h||_t + 1e-6); GRN beta is folded into b2 by the caller).
+ * Two passes over x (statistics, then output) on the tensor cores, fed by TMA: HBM traffic = read x twice +
+ * write y.  Requirements: C = 32, J = 4C = 128, T >= 512, y != x, x / y rows 16-byte aligned with a pitch
+ * >= T rounded up to 4 (x_cs, y_cs, x_bs, y_bs multiples of 4).  w1_split / w2_split: bf16 (hi, lo) packs in
+ * the layout of sty_conv1d_args.w_split for K = 1 ([2][C/8][J][8] and [2][J/8][C][8]); gb: gamma | beta rows
+ * of the AdaLN (B rows, stride gb_bs); sumsq, gs: (B, J) workspaces owned by the caller. */
+STY_API int sty_convnext_fused_fwd(const float* x, int64_t x_bs, int64_t x_cs, float* y, int64_t y_bs, int64_t y_cs,
+                                   const float* dw_w, const float* dw_b, const float* gb, int64_t gb_bs, float eps,
+                                   const void* w1_split, const float* b1, const float* alpha,
+                                   const float* grn_gamma, const void* w2_split, const float* b2, float* sumsq,
+                                   float* gs, int B, int C, int J, int T, sty_stream_t stream);
+
 /* ---- LayerNorm over the channel axis of (B,C,T) --------------------------
  * v = x (+ res);  n = (v-mean_c)/sqrt(var_c+eps)
  * y = act( (g_plus_one ? 1+g : g) * n + b ) * mask[b,t]

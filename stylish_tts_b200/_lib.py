@@ -72,6 +72,8 @@ _SIGNATURES = {
                           _f32, _f32p],
     "sty_chan_layernorm_fwd": [_f32p, _f32p, _i64, _f32p, _f32p, _i64, _i32, _f32p, _i64, _f32p,
                                _i32, _i32, _i32, _f32, _i32, _f32p],
+    "sty_convnext_fused_fwd": [_f32p, _i64, _i64, _f32p, _i64, _i64, _f32p, _f32p, _f32p, _i64, _f32, _f32p, _f32p,
+                               _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, _i32, _i32, _i32, _i32, _f32p],
     "sty_chan_layernorm_pitched_fwd": [_f32p, _f32p, _i64, _i64, _f32p, _f32p, _i64, _i32, _f32p, _i64, _i64,
                                        _f32p, _i32, _i32, _i32, _f32, _i32, _f32p],
     "sty_instnorm_affine_fwd": [_f32p, _i64, _i64, _f32p, _i64, _f32p, _f32p, _i32, _i32, _i32,
@@ -240,7 +242,7 @@ def _signature(name: str, args) -> str:
             extra += "+dwln"
         return f"conv1d[ci={a.CI},co={a.CO},k={a.K},d={a.dil},B={a.B},T={a.T}{extra}]"
     pos = {"sty_dwconv_ln_fwd": (9, 10), "sty_chan_layernorm_fwd": (11, 12),
-           "sty_chan_layernorm_pitched_fwd": (13, 14),
+           "sty_chan_layernorm_pitched_fwd": (13, 14), "sty_convnext_fused_fwd": (20, 22),
            "sty_instnorm_affine_fwd": (8, 9), "sty_attention_fwd": (12, 13)}.get(name)
     if pos:
         return f"{name[4:]}[c={args[pos[0]]},T={args[pos[1]]}]"
@@ -250,7 +252,8 @@ def _signature(name: str, args) -> str:
 def call(name: str, *args) -> None:
     global launches
     lib = load()
-    launches += 2 if name == "sty_source_fwd" else 1  # source = phase + wave kernels
+    # kernels per call: source = phase + wave; fused ConvNeXt block = pass 1 + GRN scale + pass 2
+    launches += 2 if name == "sty_source_fwd" else 3 if name == "sty_convnext_fused_fwd" else 1
     if profile_log is not None:
         e0 = torch.cuda.Event(enable_timing=True)
         e1 = torch.cuda.Event(enable_timing=True)

@@ -25,6 +25,8 @@ USE_UMMA = os.environ.get("STYLISH_B200_UMMA", "1") != "0"
 UMMA_MIN_T = 64
 # InstanceNorm statistics of the S-rate AdaINs accumulated in the producing conv's epilogue (one pass less)
 FUSE_STATS = os.environ.get("STYLISH_B200_FUSE_STATS", "1") != "0"
+# output-rate ConvNeXt blocks as one fused two-pass kernel that never stores the 4C-wide intermediate
+FUSE_CONVNEXT = os.environ.get("STYLISH_B200_FUSE_CONVNEXT", "1") != "0"
 
 
 def empty_bct(B: int, C: int, T: int, device) -> torch.Tensor:
@@ -33,6 +35,12 @@ def empty_bct(B: int, C: int, T: int, device) -> torch.Tensor:
     16 bytes).  T = 75 * frames is odd for an odd frame count (60 225 at the BASELINE shapes)."""
     Tp = (T + 3) & ~3
     return torch.empty((B, C, Tp), device=device, dtype=torch.float32)[:, :, :T]
+
+
+def _rows_aligned(t: torch.Tensor) -> bool:
+    """TMA-compatible (B,C,T) view: 16-byte aligned base, strides multiples of 4 floats, row pitch >= T rounded up to 4"""
+    return (t.stride(2) == 1 and t.data_ptr() % 16 == 0 and t.stride(0) % 4 == 0 and t.stride(1) % 4 == 0
+            and t.stride(1) >= ((t.shape[2] + 3) & ~3))
 
 
 def split_bf16(w_oik: torch.Tensor) -> torch.Tensor:
@@ -479,12 +487,28 @@ class SpeechEngine:
         x4 = ff(cf["ff2"], x3)
         return self._ada_ln(P, x4, h, cf["post_norm"], 1e-5)
 
-    def convnext(self, P: Packed, blk, x, h):
-        """GeneratorConvNeXtBlock, in place on x (B,C,T) (conv_next.py:80-93)."""
+    def convnext(self, P: Packed, blk, x, h, out=None):
+        """GeneratorConvNeXtBlock (conv_next.py:80-93) -> (B,C,T).  At the output rate (C = 32, pitch-padded rows)
+        the whole block is ONE C-ABI call that never stores the 4C-wide intermediate (csrc/convnext_fused.cu) and
+        writes a new tensor (`out`, or a fresh pitch-padded one); elsewhere the block runs in place on x."""
         B, Cc, T = x.shape
         J = P.fc_rows
         gb = self._gb(P, h, blk["norm"])
         inter = blk["pw1"].CO
+        if (FUSE_CONVNEXT and USE_UMMA and Cc == 32 and inter == 128 and T >= 512 and blk["pw1"].split is not None
+                and blk["pw2"].split is not None and _rows_aligned(x)):
+            y = out if out is not None else empty_bct(B, Cc, T, x.device)
+            assert _rows_aligned(y) and y.data_ptr() != x.data_ptr()
+            ws = torch.empty((2, B, inter), device=x.device, dtype=torch.float32)
+            L.call("sty_convnext_fused_fwd", x.data_ptr(), x.stride(0), x.stride(1), y.data_ptr(), y.stride(0),
+                   y.stride(1), blk["dw_w"].data_ptr(), blk["dw_b"].data_ptr(), gb.data_ptr(), J, 1e-6,
+                   blk["pw1"].split.data_ptr(), blk["pw1"].bias.data_ptr(), blk["snake"].data_ptr(),
+                   blk["grn_gamma"].data_ptr(), blk["pw2"].split.data_ptr(), blk["pw2"].bias.data_ptr(),
+                   ws[0].data_ptr(), ws[1].data_ptr(), B, Cc, inter, T, L.stream_ptr())
+            return y
+        if out is not None:  # unfused path works in place: start from a copy in the caller's buffer
+            out.copy_(x)
+            x = out
         sumsq = torch.zeros((B, inter), device=x.device, dtype=torch.float32)
         fused_front = (USE_UMMA and blk["pw1"].split is not None and Cc <= 64 and Cc % 16 == 0
                        and T >= UMMA_MIN_T and x.stride(2) == 1)
@@ -589,9 +613,12 @@ class SpeechEngine:
             taps["amp_convnext"] = x.clone()
         for i, (cw, blk, r) in enumerate(zip(P.upconvs, P.upblocks, P.rates)):
             last = i == len(P.rates) - 1
-            out = pin[:, :Hs] if last else None
-            x = conv1d(x, cw, shuffle=r, out=out)
-            x = self.convnext(P, blk, x, h)
+            if last:  # output rate: pitch-padded rows, the block writes straight into the phase-head input
+                x = conv1d(x, cw, shuffle=r, out=empty_bct(B, cw.CO // r, x.shape[2] * r, dev))
+                x = self.convnext(P, blk, x, h, out=pin[:, :Hs])
+            else:
+                x = conv1d(x, cw, shuffle=r)
+                x = self.convnext(P, blk, x, h)
         if taps is not None:
             taps["upsampled"] = x.clone()
         la = chan_layernorm(x, *P.amp_final_ln, eps=1e-6)

@@ -394,3 +394,59 @@ def test_conv1d_epilogue_moments_feed_adain(umma):
     sc, sh = E.moments_affine(mom, gb.to(dev()), 2 * co, T)
     sc2, sh2 = E.instnorm_affine(y, gb.to(dev()), 2 * co)
     assert rel_l2(sc, sc2) < 2e-5 and rel_l2(sh, sh2) < 5e-5
+
+
+@pytest.mark.parametrize("T,B", [(1000, 2), (2301, 3), (60225, 2)])
+def test_convnext_block_fused_no_intermediate(T, B):
+    """The whole GeneratorConvNeXtBlock (conv_next.py:80-93, GRN :7-18) as ONE call that never stores the
+    4C-wide intermediate (csrc/convnext_fused.cu: TMA-fed, two passes) against the fp64 oracle block; odd
+    lengths (pitch-padded rows, partial last tile), several tiles per CTA at T = 60 225, and the output written
+    into a channel slice of a wider buffer like the engine does."""
+    gen = g(T + B)
+    Cc, inter, sdim = 32, 128, 64
+    p = "blk"
+    sd = {
+        p + ".dwconv.weight": torch.randn(Cc, 1, 7, generator=gen) * 0.4,
+        p + ".dwconv.bias": torch.randn(Cc, generator=gen) * 0.1,
+        p + ".norm.fc.weight": torch.randn(2 * Cc, sdim, generator=gen) * 0.05,
+        p + ".norm.fc.bias": torch.randn(2 * Cc, generator=gen) * 0.1,
+        p + ".pwconv1.weight": torch.randn(inter, Cc, generator=gen) / math.sqrt(Cc),
+        p + ".pwconv1.bias": torch.randn(inter, generator=gen) * 0.1,
+        p + ".snake": 0.75 + 0.5 * torch.rand(1, 1, inter, generator=gen),
+        p + ".grn.gamma": torch.randn(1, 1, inter, generator=gen) * 0.3,
+        p + ".grn.beta": torch.randn(1, 1, inter, generator=gen) * 0.1,
+        p + ".pwconv2.weight": torch.randn(Cc, inter, generator=gen) / math.sqrt(inter),
+        p + ".pwconv2.bias": torch.randn(Cc, generator=gen) * 0.1,
+    }
+    x = torch.randn(B, Cc, T, generator=gen)
+    style = torch.randn(B, sdim, generator=gen)
+    ref = so.convnext_block({k: v.double() for k, v in sd.items()}, p, x.double(), style.double())
+    dv = dev()
+    w2 = sd[p + ".pwconv2.weight"]
+    blk = dict(dw_w=sd[p + ".dwconv.weight"].reshape(Cc, 7).contiguous().to(dv), dw_b=sd[p + ".dwconv.bias"].to(dv),
+               norm="n", pw1=E.ConvW(sd[p + ".pwconv1.weight"].unsqueeze(-1).to(dv), sd[p + ".pwconv1.bias"].to(dv)),
+               snake=sd[p + ".snake"].reshape(-1).contiguous().to(dv),
+               grn_gamma=sd[p + ".grn.gamma"].reshape(-1).contiguous().to(dv),
+               pw2=E.ConvW(w2.unsqueeze(-1).to(dv),
+                           (sd[p + ".pwconv2.bias"] + w2 @ sd[p + ".grn.beta"].reshape(-1)).to(dv)))
+    hfc = (style @ sd[p + ".norm.fc.weight"].t() + sd[p + ".norm.fc.bias"]).to(dv).contiguous()  # gamma | beta rows
+    P = type("P", (), dict(fc_rows=2 * Cc, fc_off={"n": 0}))()
+    eng = E.SpeechEngine.__new__(E.SpeechEngine)
+    xd = E.empty_bct(B, Cc, T, dv).copy_(x.to(dv))
+    wide = E.empty_bct(B, 3 * Cc, T, dv).fill_(7.0)
+    calls = []
+    orig = L.call
+    L.call = lambda name, *a: (calls.append(name), orig(name, *a))[1]
+    try:
+        y = eng.convnext(P, blk, xd, hfc, out=wide[:, Cc:2 * Cc])
+    finally:
+        L.call = orig
+    assert calls == ["sty_convnext_fused_fwd"], calls
+    assert y.data_ptr() == wide[:, Cc:2 * Cc].data_ptr()
+    assert rel_l2(y, ref) < 5e-5, rel_l2(y, ref)
+    assert float((wide[:, :Cc] - 7.0).abs().max()) == 0.0 and float((wide[:, 2 * Cc:] - 7.0).abs().max()) == 0.0
+    assert rel_l2(xd, x) == 0.0  # the input is not modified
+    # and the two-kernel path (in place) agrees
+    y2 = eng.convnext(P, blk, x.to(dv).contiguous().clone(), hfc) if T % 4 else None
+    if y2 is not None:
+        assert rel_l2(y2, ref) < 5e-5
