@@ -35,7 +35,7 @@ namespace {
 
 constexpr int kC = 32, kJ = 128, kMT = 128;
 constexpr int kRawW = 136;  // box: steps t0-4 .. t0+131 (the box must start on a 16-byte boundary)
-constexpr int kRawStages = 3;
+constexpr int kRawStages = 4;  // pass 2 keeps a stage until the output epilogue has read the residual from it
 constexpr int kRawFloats = kC * kRawW;
 constexpr int kMmaWarp = 1, kFrontWarp0 = 4, kEpi1Warp0 = 8, kEpi2Warp0 = 16;
 constexpr int kThreads1 = 16 * 32, kThreads2 = 18 * 32;
@@ -75,17 +75,17 @@ convnext_fused_kernel(const Args p, const __grid_constant__ CUtensorMap tmap) {
   float* dwp = reinterpret_cast<float*>(smem + kOffPrm);  // [32][8]
   float* gbs = dwp + kC * 8;                              // [2][64]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBars);
-  uint64_t* raw_full = bars;        // [3]
-  uint64_t* raw_empty = bars + 3;   // [3]
-  uint64_t* x_full = bars + 6;      // [2]
-  uint64_t* x_empty = bars + 8;     // [2]
-  uint64_t* acc1_full = bars + 10;  // [2]
-  uint64_t* acc1_empty = bars + 12; // [2]
-  uint64_t* h_full = bars + 14;
-  uint64_t* h_empty = bars + 15;
-  uint64_t* acc2_full = bars + 16;  // [2]
-  uint64_t* acc2_empty = bars + 18; // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+  uint64_t* raw_full = bars;        // [4]
+  uint64_t* raw_empty = bars + 4;   // [4]
+  uint64_t* x_full = bars + 8;      // [2]
+  uint64_t* x_empty = bars + 10;    // [2]
+  uint64_t* acc1_full = bars + 12;  // [2]
+  uint64_t* acc1_empty = bars + 14; // [2]
+  uint64_t* h_full = bars + 16;     // [2] half tiles of 64 steps: GEMM 2 of one half overlaps the Snake of the next
+  uint64_t* h_empty = bars + 18;    // [2]
+  uint64_t* acc2_full = bars + 20;  // [2]
+  uint64_t* acc2_ready = bars + 22; // [2] accumulator stage initialised with the residual (see the output epilogue)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
   uint4* W2s = reinterpret_cast<uint4*>(smem + kOffW2);
   uint4* Hs = reinterpret_cast<uint4*>(smem + kOffH);
 
@@ -96,7 +96,7 @@ convnext_fused_kernel(const Args p, const __grid_constant__ CUtensorMap tmap) {
   if (tid == 0) {
     for (int i = 0; i < kRawStages; ++i) {
       mbar_init(&raw_full[i], 1);
-      mbar_init(&raw_empty[i], 64);
+      mbar_init(&raw_empty[i], PASS == 1 ? 64 : 128);  // front group (+ output epilogue: residual)
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&x_full[i], 64);
@@ -104,10 +104,12 @@ convnext_fused_kernel(const Args p, const __grid_constant__ CUtensorMap tmap) {
       mbar_init(&acc1_full[i], 1);
       mbar_init(&acc1_empty[i], 256);
       mbar_init(&acc2_full[i], 1);
-      mbar_init(&acc2_empty[i], 64);
+      mbar_init(&acc2_ready[i], 64);
     }
-    mbar_init(h_full, 256);
-    mbar_init(h_empty, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&h_full[i], 256);
+      mbar_init(&h_empty[i], 1);
+    }
     fence_barrier_init();
   }
   for (int i = tid; i < 2 * 4 * kJ; i += NT) W1s[i] = p.w1s[i];
@@ -148,8 +150,8 @@ convnext_fused_kernel(const Args p, const __grid_constant__ CUtensorMap tmap) {
   } else if (warp == kMmaWarp) {
     // =========================== MMA issuer: GEMM 1 of tile it+1 is issued before GEMM 2 of tile it
     const uint32_t idesc1 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kMT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-    const uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(kMT >> 3) << 17) |
-                            ((uint32_t)(64 >> 4) << 24);
+    const uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(64 >> 3) << 17) |
+                            ((uint32_t)(64 >> 4) << 24);  // M = 64 (32 output channels used), N = 64 steps, B MN-major
     const uint64_t a1d = make_desc(smem_u32(W1s), 128u, 8u);
     const uint64_t a2d = make_desc(smem_u32(W2s), 64u, 8u);
     const uint64_t b2d = make_desc(smem_u32(Hs), 8u, 128u);
@@ -177,24 +179,28 @@ convnext_fused_kernel(const Args p, const __grid_constant__ CUtensorMap tmap) {
     };
     auto gemm2 = [&](int it) {
       const uint32_t s = (uint32_t)it & 1u, ph = ((uint32_t)it >> 1) & 1u;
-      mbar_wait(h_full, (uint32_t)it & 1u);
-      mbar_wait(&acc2_empty[s], ph ^ 1u);
-      tc_fence_after();
-      if (elect_one()) {
-        const uint32_t ah = (uint32_t)(a2d >> 32), bh = (uint32_t)(b2d >> 32);
-        const uint32_t al = (uint32_t)a2d, bl = (uint32_t)b2d;
-        const uint32_t d = tmem_base + 256u + s * 128u;
+      const uint32_t ah = (uint32_t)(a2d >> 32), bh = (uint32_t)(b2d >> 32);
+      const uint32_t al = (uint32_t)a2d;
+#pragma unroll 1
+      for (uint32_t hh = 0; hh < 2; ++hh) {  // the two 64-step halves of the tile
+        mbar_wait(&h_full[hh], (uint32_t)it & 1u);
+        if (hh == 0) mbar_wait(&acc2_ready[s], ph);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t bl = (uint32_t)b2d + hh * 2048u;  // half stage: [2 split][8 tg][128 j] 16-byte units
+          const uint32_t d = tmem_base + 256u + s * 128u + hh * 64u;
 #pragma unroll
-        for (uint32_t ks = 0; ks < 8; ++ks) {
-          const uint32_t ak = al + ks * 128u, bk = bl + ks * 16u;
-          umma_bf16_w(d, ak, ah, bk, bh, idesc2, ks);            // W2 hi * h hi
-          umma_bf16_w(d, ak + 1024u, ah, bk, bh, idesc2, 1u);    // W2 lo * h hi
-          umma_bf16_w(d, ak, ah, bk + 2048u, bh, idesc2, 1u);    // W2 hi * h lo
+          for (uint32_t ks = 0; ks < 8; ++ks) {
+            const uint32_t ak = al + ks * 128u, bk = bl + ks * 16u;
+            umma_bf16_w(d, ak, ah, bk, bh, idesc2, 1u);            // W2 hi * h hi (on top of the residual)
+            umma_bf16_w(d, ak + 1024u, ah, bk, bh, idesc2, 1u);    // W2 lo * h hi
+            umma_bf16_w(d, ak, ah, bk + 1024u, bh, idesc2, 1u);    // W2 hi * h lo
+          }
+          umma_commit(&h_empty[hh]);
+          if (hh == 1) umma_commit(&acc2_full[s]);
         }
-        umma_commit(h_empty);
-        umma_commit(&acc2_full[s]);
+        __syncwarp();
       }
-      __syncwarp();
     };
     if (n_local > 0) gemm1(0);
     for (int it = 0; it < n_local; ++it) {
@@ -291,7 +297,7 @@ convnext_fused_kernel(const Args p, const __grid_constant__ CUtensorMap tmap) {
     const int j = q * 32 + lane;
     const float al = p.alpha[j], ia = 1.0f / al;
     const float bp = p.b1[j] + 0.5f * ia, a2 = 2.0f * al, nh = -0.5f * ia;
-    const uint32_t lane_addr = ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 64);
+    const uint32_t lane_addr = ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 32);
     float ss = 0.f, gsv = 1.f;
     int cur_b = -1;
     for (int it = 0; it < n_local; ++it) {
@@ -309,13 +315,13 @@ convnext_fused_kernel(const Args p, const __grid_constant__ CUtensorMap tmap) {
       const uint32_t s = (uint32_t)it & 1u, ph = ((uint32_t)it >> 1) & 1u;
       mbar_wait_sleep(&acc1_full[s], ph);
       tc_fence_after();
-      const int col0 = half * 64;
-      const int valid = p.T - t0 - col0;  // columns [0, valid) of this thread's 64 are real time steps
 #pragma unroll
-      for (int ch = 0; ch < 2; ++ch) {
+      for (int hh = 0; hh < 2; ++hh) {  // this warp's 32 columns of each 64-step half of the tile
+        const int col0 = hh * 64 + half * 32;
+        const int valid = p.T - t0 - col0;  // columns [0, valid) are real time steps
         float r[32];
-        tmem_ld32(tmem_base + s * 128u + lane_addr + (uint32_t)(ch * 32), r);
-        if (ch == 1) {  // both chunks are in registers: the accumulator stage may be overwritten
+        tmem_ld32(tmem_base + s * 128u + lane_addr + (uint32_t)(hh * 64), r);
+        if (hh == 1) {  // both chunks are in registers: the accumulator stage may be overwritten
           tc_fence_before();
           mbar_arrive(&acc1_empty[s]);
         }
@@ -326,34 +332,33 @@ convnext_fused_kernel(const Args p, const __grid_constant__ CUtensorMap tmap) {
           r[i] = fmaf(c, nh, w);
         }
         if (PASS == 1) {
-          if (valid >= ch * 32 + 32) {
+          if (valid >= 32) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) ss = fmaf(r[i], r[i], ss);
           } else {
 #pragma unroll
             for (int i = 0; i < 32; ++i)
-              if (ch * 32 + i < valid) ss = fmaf(r[i], r[i], ss);
+              if (i < valid) ss = fmaf(r[i], r[i], ss);
           }
         } else {
-          if (ch == 0) mbar_wait(h_empty, ((uint32_t)it & 1u) ^ 1u);  // GEMM 2 of the previous tile has read Hs
+          uint4* Hh = Hs + hh * 2048;  // half stage [2 split][8 tg][128 j]
+          mbar_wait(&h_empty[hh], ((uint32_t)it & 1u) ^ 1u);  // GEMM 2 of the previous tile has read this half
 #pragma unroll
           for (int g8 = 0; g8 < 4; ++g8) {
-            uint32_t hh[4], ll[4];
+            uint32_t hv[4], lv[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const float v0 = r[g8 * 8 + 2 * e] * gsv, v1 = r[g8 * 8 + 2 * e + 1] * gsv;
-              hh[e] = pack_bf16(v0, v1);
-              ll[e] = pack_bf16(v0 - __uint_as_float(hh[e] << 16), v1 - __uint_as_float(hh[e] & 0xffff0000u));
+              hv[e] = pack_bf16(v0, v1);
+              lv[e] = pack_bf16(v0 - __uint_as_float(hv[e] << 16), v1 - __uint_as_float(hv[e] & 0xffff0000u));
             }
-            const int tg = (col0 + ch * 32) / 8 + g8;
-            Hs[(0 * 16 + tg) * kJ + j] = make_uint4(hh[0], hh[1], hh[2], hh[3]);
-            Hs[(1 * 16 + tg) * kJ + j] = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+            const int tg = half * 4 + g8;
+            Hh[(0 * 8 + tg) * kJ + j] = make_uint4(hv[0], hv[1], hv[2], hv[3]);
+            Hh[(1 * 8 + tg) * kJ + j] = make_uint4(lv[0], lv[1], lv[2], lv[3]);
           }
+          fence_proxy_async_smem();
+          mbar_arrive(&h_full[hh]);
         }
-      }
-      if (PASS == 2) {
-        fence_proxy_async_smem();
-        mbar_arrive(h_full);
       }
     }
     if (PASS == 1 && cur_b >= 0) atomicAdd(p.sumsq + (int64_t)cur_b * kJ + j, ss);
@@ -364,41 +369,57 @@ convnext_fused_kernel(const Args p, const __grid_constant__ CUtensorMap tmap) {
     const bool has = lane < 16;
     const float b2 = p.b2[co];
     const uint32_t lane_addr = ((uint32_t)(q * 32) << 16);
+    // The residual is ADDED BY THE TENSOR CORE: this role initialises accumulator stage it & 1 with the block input
+    // of tile it (from the raw TMA stage, as soon as it has landed), GEMM 2 then accumulates on top of it.  The raw
+    // stage is released two tiles before the output of its tile is written, so the loader stays ahead.
+    auto prefill = [&](int it2) {
+      if (it2 >= n_local) return;
+      const uint32_t s2 = (uint32_t)it2 & 1u, rs = (uint32_t)it2 % kRawStages, rph = ((uint32_t)it2 / kRawStages) & 1u;
+      mbar_wait(&raw_full[rs], rph);
+      const float* xr = raw0 + rs * kRawFloats + co * kRawW + 4;  // column 4 = step t0 (zeros past the end)
+#pragma unroll 1
+      for (int ch = 0; ch < 4; ++ch) {
+        float r[32];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 v = *reinterpret_cast<const float4*>(xr + ch * 32 + 4 * i);
+          r[4 * i] = v.x, r[4 * i + 1] = v.y, r[4 * i + 2] = v.z, r[4 * i + 3] = v.w;
+        }
+        tmem_st32(tmem_base + 256u + s2 * 128u + lane_addr + (uint32_t)(ch * 32), r);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&acc2_ready[s2]);
+      mbar_arrive(&raw_empty[rs]);  // second reader of the raw stage (after the front group)
+    };
+    prefill(0);
+    prefill(1);
     for (int it = 0; it < n_local; ++it) {
       const int tile = tile_begin + it;
       const int b = tile / p.tiles_per_b, t0 = (tile - b * p.tiles_per_b) * kMT;
       const uint32_t s = (uint32_t)it & 1u, ph = ((uint32_t)it >> 1) & 1u;
-      const float* __restrict__ xr = p.x + (int64_t)b * p.x_bs + (int64_t)co * p.x_cs + t0;
       float* __restrict__ yr = p.y + (int64_t)b * p.y_bs + (int64_t)co * p.y_cs + t0;
       mbar_wait_sleep(&acc2_full[s], ph);
       tc_fence_after();
 #pragma unroll 1
       for (int ch = 0; ch < 4; ++ch) {
-        float4 res[8];
         const int tc = t0 + ch * 32;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {  // residual: the block input (L2-resident, this CTA fetched it a tile ago)
-          const bool ok = has && (tc + 4 * i < p.T);
-          res[i] = ok ? *reinterpret_cast<const float4*>(xr + ch * 32 + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
         float r[32];
         tmem_ld32(tmem_base + 256u + s * 128u + lane_addr + (uint32_t)(ch * 32), r);
-        if (ch == 3) {
-          tc_fence_before();
-          mbar_arrive(&acc2_empty[s]);
-        }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           if (has && (tc + 4 * i < p.T)) {
             float4 o;
-            o.x = r[4 * i] + b2 + res[i].x;
-            o.y = r[4 * i + 1] + b2 + res[i].y;
-            o.z = r[4 * i + 2] + b2 + res[i].z;
-            o.w = r[4 * i + 3] + b2 + res[i].w;
+            o.x = r[4 * i] + b2;
+            o.y = r[4 * i + 1] + b2;
+            o.z = r[4 * i + 2] + b2;
+            o.w = r[4 * i + 3] + b2;
             *reinterpret_cast<float4*>(yr + ch * 32 + 4 * i) = o;  // the last group may spill into the row padding
           }
         }
       }
+      tc_fence_before();
+      prefill(it + 2);  // same accumulator stage
     }
   }
   tc_fence_before();
