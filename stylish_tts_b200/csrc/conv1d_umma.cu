@@ -80,6 +80,40 @@ __device__ __forceinline__ float warp_colsum16(float (&v)[16], int lane) {
   return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 16);
 }
 
+// MMAs of one staged chunk (all taps, all 16-channel K blocks), issued by the elected thread.  Only the first MMA
+// carries the run-time accumulate flag; everything else is branch-free so that the issuing thread — the kernel's
+// critical path for K = 11 / 21 (one thread feeds the tensor pipe) — executes a handful of uniform instructions
+// per MMA.  DUAL: hi*hi and hi*lo come from ONE MMA against [W_hi | W_lo] (N = 2*NT).
+template <bool DUAL>
+__device__ __forceinline__ void issue_chunk(uint32_t d_tmem, uint32_t a0, uint32_t a_hi, uint32_t b0, uint32_t b_hi,
+                                            uint32_t idesc, uint32_t idesc2, int K, uint32_t dil, int kblocks,
+                                            uint32_t a_kstep, uint32_t b_kstep, uint32_t a_lo_off, uint32_t b_lo_off,
+                                            uint32_t b_tstep, uint32_t acc0) {
+  auto block = [&](uint32_t ak, uint32_t bk, uint32_t acc) {
+    if constexpr (DUAL) {
+      umma_bf16_w(d_tmem, ak, a_hi, bk, b_hi, idesc2, acc);            // hi * [hi | lo]
+      umma_bf16_w(d_tmem, ak + a_lo_off, a_hi, bk, b_hi, idesc, 1u);   // lo * hi -> cols [0,NT)
+    } else {
+      umma_bf16_w(d_tmem, ak, a_hi, bk, b_hi, idesc, acc);             // hi * hi
+      umma_bf16_w(d_tmem, ak + a_lo_off, a_hi, bk, b_hi, idesc, 1u);   // lo * hi
+      umma_bf16_w(d_tmem, ak, a_hi, bk + b_lo_off, b_hi, idesc, 1u);   // hi * lo
+    }
+  };
+  block(a0, b0, acc0);
+  {
+    uint32_t ak = a0 + a_kstep, bk = b0 + b_kstep;
+#pragma unroll 2
+    for (int kb = 1; kb < kblocks; ++kb, ak += a_kstep, bk += b_kstep) block(ak, bk, 1u);
+  }
+  uint32_t a_t = a0 + dil, b_t = b0 + b_tstep;
+#pragma unroll 1
+  for (int tap = 1; tap < K; ++tap, a_t += dil, b_t += b_tstep) {
+    uint32_t ak = a_t, bk = b_t;
+#pragma unroll 2
+    for (int kb = 0; kb < kblocks; ++kb, ak += a_kstep, bk += b_kstep) block(ak, bk, 1u);
+  }
+}
+
 // IN_MODE : 0 no prologue | 1 mask/affine | 2 mask/affine + LeakyReLU(0.2) | 3 mask/affine + Snake
 //           4 ConvNeXt front: depthwise k7 conv + LayerNorm over channels + adaptive affine (K=1 only)
 // OUT_MODE: 0 none | 1 Snake | 2 ReLU | 3 Swish          (compile-time: keeps each role's loop small
@@ -474,23 +508,12 @@ conv1d_umma_kernel(const sty_conv1d_args p, const UmmaPlan pl, const __grid_cons
           const uint32_t a_kstep = 2 * rows, b_kstep = dual ? 4 * NT : 2 * NT;
           const uint32_t idesc2 = (idesc & ~(0x3Fu << 17)) | ((uint32_t)((2 * NT) >> 3) << 17);  // N = 2*NT
           const uint32_t b_tstep = 2 * wc8 * NT;                // per tap (hi and lo blocks)
-          uint32_t accumulate = ch > 0 ? 1u : 0u;
-#pragma unroll 1
-          for (int tap = 0; tap < K; ++tap, a_t += (uint32_t)dil, b_t += b_tstep) {
-            uint32_t ak = a_t, bk = b_t;
-#pragma unroll 2
-            for (int kb = 0; kb < kblocks; ++kb, ak += a_kstep, bk += b_kstep) {
-              if (dual) {
-                umma_bf16_w(d_tmem, ak, a_hi32, bk, b_hi32, idesc2, accumulate);          // hi * [hi | lo]
-                umma_bf16_w(d_tmem, ak + a_lo_off, a_hi32, bk, b_hi32, idesc, 1u);        // lo * hi -> cols [0,NT)
-              } else {
-                umma_bf16_w(d_tmem, ak, a_hi32, bk, b_hi32, idesc, accumulate);           // hi * hi
-                umma_bf16_w(d_tmem, ak + a_lo_off, a_hi32, bk, b_hi32, idesc, 1u);        // lo * hi
-                umma_bf16_w(d_tmem, ak, a_hi32, bk + b_lo_off, b_hi32, idesc, 1u);        // hi * lo
-              }
-              accumulate = 1;
-            }
-          }
+          if (dual)
+            issue_chunk<true>(d_tmem, a_t, a_hi32, b_t, b_hi32, idesc, idesc2, K, (uint32_t)dil, kblocks, a_kstep,
+                              b_kstep, a_lo_off, b_lo_off, b_tstep, ch > 0 ? 1u : 0u);
+          else
+            issue_chunk<false>(d_tmem, a_t, a_hi32, b_t, b_hi32, idesc, idesc2, K, (uint32_t)dil, kblocks, a_kstep,
+                               b_kstep, a_lo_off, b_lo_off, b_tstep, ch > 0 ? 1u : 0u);
           umma_commit(&x_empty[s]);                               // stage free once read
           if (ch == pl.n_chunks - 1) umma_commit(&acc_full[a]);  // accumulator complete
         }
