@@ -264,6 +264,8 @@ def call(name: str, *args) -> None:
         if name == "sty_conv1d_fwd":
             a = args[0]._obj
             info = dict(B=a.B, CI=a.CI, CO=a.CO, K=a.K, T=a.T, res=bool(a.res))
+        elif name == "sty_convnext_fused_fwd":
+            info = dict(kind="convnext_fused", B=args[19], C=args[20], J=args[21], T=args[22])
         profile_log.append((_signature(name, args), e0, e1, info))
         check(rc, name)
         return
