@@ -51,6 +51,18 @@ class FlatAdamW:
         self.lr = lr
         self.hyper[0] = lr
 
+    def schedule(self, step: int, step_limit: int, base_lr: Optional[float] = None) -> float:
+        """the reference's per-batch scheduler call (batch_manager.py:239 -> optimizers.py:96-103): cosine on the
+        10 000-logical-step clock with the 90 % plateau, from the stage's base rate (the constructor's `lr` unless
+        given); the new rate is written into the device cell the update kernel reads"""
+        if base_lr is not None:
+            self.base_lr = base_lr
+        elif not hasattr(self, "base_lr"):
+            self.base_lr = self.lr
+        lr = cosine_lr(self.base_lr, step, step_limit)
+        self.set_lr(lr)
+        return lr
+
     # -- gradient plumbing (works on any device; the gloo tests exercise it on CPU) --------------
     def pack_gradients(self) -> torch.Tensor:
         """copy the per-parameter ``.grad`` tensors into the flat arena (missing gradients = 0, like
@@ -98,3 +110,52 @@ def acoustic_losses(audio_pred, audio_target, multi_spectrogram, stft_loss, *, w
     ph = multi_phase_loss(p_ph, t_ph)
     total = w_mel * mel / (mel.detach() + 1e-9) + w_phase * ph / (ph.detach() + 1e-9)
     return total, mel, ph
+
+
+# ---------------------------------------------------------------------------------------------------------
+# learning-rate policy of the reference (optimizers.py:54-65,96-103; losses.py:229-250)
+# ---------------------------------------------------------------------------------------------------------
+LOGICAL_STEP_LIMIT = 10000  # optimizers.py:10: every stage is mapped onto a 10 000-"logical-step" cosine
+PLATEAU = 0.9               # optimizers.py:98: the cosine stops decaying after 90 % of the stage
+
+
+def cosine_lr(base_lr: float, step: int, step_limit: int) -> float:
+    """MultiOptimizer.scheduler (optimizers.py:96-103) + transformers.get_cosine_schedule_with_warmup(0 warm-up,
+    10 000 steps, half a cycle): the stage's `step` of `step_limit` is mapped to a logical step, capped at the
+    plateau, and the scheduler is evaluated one past it (``scheduler.step()`` increments before it evaluates)."""
+    import math
+
+    logical = step * LOGICAL_STEP_LIMIT // step_limit
+    logical = min(logical, LOGICAL_STEP_LIMIT * PLATEAU)
+    progress = float(logical + 1) / float(max(1, LOGICAL_STEP_LIMIT))
+    return base_lr * max(0.0, 0.5 * (1.0 + math.cos(math.pi * progress)))
+
+
+class DiscriminatorLR:
+    """Gap-aware discriminator learning rate (DiscriminatorLossHelper, losses.py:229-250; applied by
+    MultiOptimizer.step_discriminator_schedulers, optimizers.py:54-65): lr_disc = lr_gen * f(last_loss) with
+    ``last_loss`` an exponential moving average of the LSGAN discriminator loss.  Everything lives in DEVICE
+    tensors (no ``.item()`` like losses.py:287), so it can sit inside a captured training iteration:
+    ``update(loss)`` folds a new loss in, ``apply(gen_opt, disc_opt)`` writes the discriminator's learning rate
+    into its ``FlatAdamW.hyper`` cell."""
+
+    def __init__(self, sub_count: int, device="cpu"):
+        self.ideal = 0.5 * sub_count
+        self.f_max, self.h_min = 4.0, 0.01
+        self.x_max = self.x_min = 0.05 * sub_count
+        self.last_loss = torch.full((), self.ideal, device=device, dtype=torch.float32)
+
+    def update(self, disc_loss: torch.Tensor) -> None:
+        self.last_loss.mul_(0.95).add_(disc_loss.detach().to(self.last_loss.dtype), alpha=0.05)
+
+    def multiplier(self) -> torch.Tensor:
+        last, ideal = self.last_loss, self.ideal
+        x = (last - ideal).abs()
+        up = torch.clamp(torch.pow(torch.full_like(x, self.f_max), x / self.x_max), max=self.f_max)
+        down = torch.clamp(torch.pow(torch.full_like(x, self.h_min), x / self.x_min), min=self.h_min)
+        mid = torch.where(last > ideal, up, down)
+        return torch.where(last > ideal + self.x_max, torch.full_like(x, self.f_max),
+                           torch.where(last < ideal - self.x_min, torch.full_like(x, self.h_min), mid))
+
+    def apply(self, gen_opt: "FlatAdamW", disc_opt: "FlatAdamW") -> None:
+        disc_opt.hyper[0:1].copy_(gen_opt.hyper[0:1] * self.multiplier())
