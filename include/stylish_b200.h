@@ -150,6 +150,26 @@ STY_API int sty_convnext_fused_fwd(const float* x, int64_t x_bs, int64_t x_cs, f
                                    const float* grn_gamma, const void* w2_split, const float* b2, float* sumsq,
                                    float* gs, int B, int C, int J, int T, sty_stream_t stream);
 
+/* ---- adversarial losses: discriminators.py:13-69, losses.py:166-373 -----------------
+ * sty_leaky_s2d: y[n, c*s + p, u] = LeakyReLU_slope(x[n, c, s*u + p]) (0 past the end), x (N,C,W) -> y (N,C*s,ceil(W/s)):
+ * the activation between the discriminator convs, fused with the space-to-depth rearrangement that turns a
+ * stride-s convolution into a stride-1 one on s*C channels (s = 1: plain LeakyReLU).  _bwd: its gradient.
+ * sty_sqdiff_sum_fwd: out[0] += sum_i (c - x[i])^2  (LSGAN terms).
+ * sty_tprls_fwd: truncated pointwise relativistic least squares statistics of d = a - b:
+ *   median = lower median of d (radix select, torch.median semantics), sums = [sum_mask (d-m)^2, count, sum_mask (d-m)]
+ *   over the elements with a < b + m; no host synchronisation.  workspace: sty_tprls_workspace_bytes().
+ * sty_tprls_bwd: da = coef[0]*mask*(d-m) + [d == m, one element]*coef[1], db = -da  (either may be NULL). */
+STY_API int sty_leaky_s2d_fwd(const float* x, float* y, int64_t N, int C, int W, int s, float slope,
+                              sty_stream_t stream);
+STY_API int sty_leaky_s2d_bwd(const float* dy, const float* x, float* dx, int64_t N, int C, int W, int s, float slope,
+                              sty_stream_t stream);
+STY_API int sty_sqdiff_sum_fwd(const float* x, int64_t n, float c, float* out, sty_stream_t stream);
+STY_API int64_t sty_tprls_workspace_bytes(void);
+STY_API int sty_tprls_fwd(const float* a, const float* b, int64_t n, void* workspace, float* sums, float* median,
+                          sty_stream_t stream);
+STY_API int sty_tprls_bwd(const float* a, const float* b, int64_t n, const float* median, const float* coef, float* da,
+                          float* db, int* flag, sty_stream_t stream);
+
 /* ---- LayerNorm over the channel axis of (B,C,T) --------------------------
  * v = x (+ res);  n = (v-mean_c)/sqrt(var_c+eps)
  * y = act( (g_plus_one ? 1+g : g) * n + b ) * mask[b,t]

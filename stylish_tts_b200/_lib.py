@@ -158,11 +158,18 @@ _SIGNATURES = {
                                _f32p, _f32p, _f32p, _i64, _f32p, _i32, _i32, _i32, _i32, _f32,
                                C.POINTER(Dropout), _f32p],
     "sty_stft_loss_finalize": [_f32p, _f32p, _f32p, _i32, _f32, _f32, _i32, _f32p, _f32p],
+    # adversarial losses (spectrogram discriminators, LSGAN / TPRLS)
+    "sty_leaky_s2d_fwd": [_f32p, _f32p, _i64, _i32, _i32, _i32, _f32, _f32p],
+    "sty_leaky_s2d_bwd": [_f32p, _f32p, _f32p, _i64, _i32, _i32, _i32, _f32, _f32p],
+    "sty_sqdiff_sum_fwd": [_f32p, _i64, _f32, _f32p, _f32p],
+    "sty_tprls_fwd": [_f32p, _f32p, _i64, _f32p, _f32p, _f32p, _f32p],
+    "sty_tprls_bwd": [_f32p, _f32p, _i64, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p],
 }
 _SPECIAL = {
     "sty_version": ([], C.c_int),
     "sty_last_error": ([], C.c_char_p),
     "sty_device_sm_count": ([], C.c_int),
+    "sty_tprls_workspace_bytes": ([], C.c_int64),
 }
 EXPORTED = tuple(_SIGNATURES) + tuple(_SPECIAL)
 

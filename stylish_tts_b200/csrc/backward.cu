@@ -825,10 +825,11 @@ extern "C" int sty_conv1d_wgrad(const sty_conv1d_wgrad_args* a, sty_stream_t str
     case 3: return launch_wgrad<3, 8>(*a, st);
     case 5: return launch_wgrad<5, 4>(*a, st);
     case 7: return launch_wgrad<7, 4>(*a, st);
+    case 9: return launch_wgrad<9, 4>(*a, st);  // first layer of the spectrogram discriminators (3x9)
     case 11: return launch_wgrad<11, 4>(*a, st);
     case 21: return launch_wgrad<21, 4>(*a, st);
     default:
-      set_error("conv1d_wgrad: kernel size %d not built (1,3,5,7,11,21)", a->K);
+      set_error("conv1d_wgrad: kernel size %d not built (1,3,5,7,9,11,21)", a->K);
       return STY_ERR_BAD_ARG;
   }
 }

@@ -1,0 +1,254 @@
+"""Spectrogram discriminators and the adversarial losses of the acoustic stage on the sm_100a kernels
+(SURVEY 8f rank 1).
+
+``SpecDiscriminator`` is the drop-in for the reference's ``mrd0 / mrd1 / mrd2`` (train/models/discriminator.py:13-69,
+built at models.py:44-46): same constructor, same state-dict keys (``discriminators.{i}`` / ``out.{i}``,
+``parametrizations.weight.original0/1`` + ``bias``), ``forward(y (B,1,bins,frames)) -> (five flattened score maps, [])``.
+Images are row-channel (B, bins+2, C, frames) like the style encoder's, so each 3xK Conv2d is the stride-1
+Conv1d kernel over three stacked rows (tcgen05 path for the 32 -> 32 layers); the stride-(1,2) layers run on the
+space-to-depth rearrangement of their input (2C channels, 5 taps: no wasted MACs), which the LeakyReLU(0.1)
+kernel produces in the same pass (``sty_leaky_s2d``).
+
+``GeneratorLoss`` / ``DiscriminatorLoss`` mirror train/losses.py:166-373 for the spectrogram discriminators:
+LSGAN terms + TPRLS (median by radix select on the device, masked sums; no ``.item()``, no boolean-mask gather),
+the moving average that drives the discriminator learning rate stays in device memory (``optim.DiscriminatorLR``).
+The waveform discriminator (``disc``: ContextFreeDiscriminator) is accepted as an optional external module — it is
+not re-implemented here (out-of-scope table).
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+from torch import nn
+from torch.autograd import Function
+from torch.nn.utils.parametrizations import weight_norm
+
+from . import _lib as L
+from .optim import DiscriminatorLR
+from .style_encoder import RowConvFn
+
+DISC_WEIGHT = 3.0  # losses.py:14
+TAU = 0.04         # losses.py:270,359
+
+
+class LeakyS2dFn(Function):
+    """(N,C,W) -> (N, C*s, ceil(W/s)): LeakyReLU(slope) + space-to-depth by s along W (s = 1: activation only)"""
+
+    @staticmethod
+    def forward(ctx, x, s, slope):
+        x = x.contiguous()
+        N, Cc, W = x.shape
+        y = torch.empty((N, Cc * s, (W + s - 1) // s), device=x.device, dtype=torch.float32)
+        L.call("sty_leaky_s2d_fwd", x.data_ptr(), y.data_ptr(), N, Cc, W, s, slope, L.stream_ptr())
+        ctx.save_for_backward(x)
+        ctx.s, ctx.slope = s, slope
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        N, Cc, W = x.shape
+        dx = torch.empty_like(x)
+        L.call("sty_leaky_s2d_bwd", dy.contiguous().data_ptr(), x.data_ptr(), dx.data_ptr(), N, Cc, W, ctx.s, ctx.slope,
+               L.stream_ptr())
+        return dx, None, None
+
+
+def leaky_image(img, s=1, slope=0.1):
+    """row-channel image (B,Hp,C,W) -> (B,Hp,C*s,ceil(W/s))"""
+    B, Hp, Cc, W = img.shape
+    y = LeakyS2dFn.apply(img.reshape(B * Hp, Cc, W), s, slope)
+    return y.view(B, Hp, Cc * s, y.shape[2])
+
+
+def stride2_weight(w4: torch.Tensor) -> torch.Tensor:
+    """(Co,Ci,3,9) stride-(1,2) pad-(1,4) kernel -> (Co,2Ci,3,5) stride-1 pad-(1,2) kernel on the space-to-depth
+    input: y[w'] = sum_k w[k] x[2w'+k-4] = sum_{j,p} w[2j+p] xs[p][w'+j-2]; tap k = 9 does not exist (zero).
+    Plain tensor ops on the weight, so autograd carries the gradient back to the 3x9 parameter."""
+    Co, Ci, R, K = w4.shape
+    assert K == 9
+    wp = torch.nn.functional.pad(w4, (0, 1))                      # k = 0..9
+    return wp.reshape(Co, Ci, R, 5, 2).permute(0, 1, 4, 2, 3).reshape(Co, Ci * 2, R, 5)
+
+
+class SpecDiscriminator(nn.Module):
+    """Drop-in for reference SpecDiscriminator (discriminator.py:13-69)."""
+
+    def __init__(self):
+        super().__init__()
+        c2 = lambda ci, co, k, stride, pad: weight_norm(nn.Conv2d(ci, co, kernel_size=k, stride=stride, padding=pad))
+        self.discriminators = nn.ModuleList([
+            c2(1, 32, (3, 9), 1, (1, 4)), c2(32, 32, (3, 9), (1, 2), (1, 4)), c2(32, 32, (3, 9), (1, 2), (1, 4)),
+            c2(32, 32, (3, 9), (1, 2), (1, 4)), c2(32, 32, (3, 3), 1, (1, 1))])
+        self.out = nn.ModuleList([c2(32, 1, 3, 1, 1) for _ in range(5)])
+        self._masks = {}
+
+    def _row_mask(self, B, Hp, W, device):
+        key = (B, Hp, W, str(device))
+        if key not in self._masks:
+            n = torch.arange(B * Hp - 2, device=device)
+            self._masks[key] = ((n % Hp) < (Hp - 2)).float()[:, None].expand(-1, W).contiguous()
+        return self._masks[key]
+
+    @staticmethod
+    def _w(conv):
+        p = conv.parametrizations.weight
+        return torch._weight_norm(p.original1, p.original0, 0)
+
+    def forward(self, y):
+        if not y.is_cuda:
+            raise RuntimeError("stylish_tts_b200: SpecDiscriminator needs CUDA tensors (no CPU fallback)")
+        B, one, K, N = y.shape
+        assert one == 1
+        Hp = K + 2
+        img = torch.zeros((B, Hp, 1, N), device=y.device, dtype=torch.float32)
+        img[:, 1:K + 1, 0, :] = y[:, 0].to(torch.float32)
+        conv = lambda t, w4, b: RowConvFn.apply(t, w4, b, None,
+                                                dict(row_mask=self._row_mask(t.shape[0], t.shape[1], t.shape[3], t.device)))
+        result: List[torch.Tensor] = []
+        h = conv(img, self._w(self.discriminators[0]), self.discriminators[0].bias)
+        for i in range(5):
+            a = leaky_image(h)                                   # LeakyReLU(0.1), discriminator.py:59
+            o = conv(a, self._w(self.out[i]), self.out[i].bias)  # (B,Hp,1,W)
+            result.append(o[:, 1:K + 1, 0, :].reshape(B, -1))    # torch.flatten(out, 1, -1)
+            if i == 4:
+                break
+            d = self.discriminators[i + 1]
+            if i < 3:   # stride (1,2): space-to-depth of the SAME activation, 5-tap stride-1 conv
+                h = conv(leaky_image(h, s=2), stride2_weight(self._w(d)), d.bias)
+            else:
+                h = conv(a, self._w(d), d.bias)
+        return result, []
+
+
+# ---------------------------------------------------------------------------------------------- losses
+class _SqMeanFn(Function):
+    """mean((c - x)^2) with the reduction on the device kernel (losses.py:257-259,341)"""
+
+    @staticmethod
+    def forward(ctx, x, c):
+        x = x.contiguous()
+        out = torch.zeros((), device=x.device, dtype=torch.float32)
+        L.call("sty_sqdiff_sum_fwd", x.data_ptr(), x.numel(), float(c), out.data_ptr(), L.stream_ptr())
+        ctx.save_for_backward(x)
+        ctx.c = c
+        return out / x.numel()
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        return (x - ctx.c) * (g * (2.0 / x.numel())), None
+
+
+class _TprlsFn(Function):
+    """tau - relu(tau - l_rel), l_rel = sum_{a < b + m} ((a-b) - m)^2 / (count + eps), m = median(a - b)
+    (losses.py:264-278 with eps = 1e-9; :356-363 with the plain mean, eps = 0)."""
+
+    @staticmethod
+    def forward(ctx, a, b, eps):
+        a, b = a.contiguous(), b.contiguous()
+        n = a.numel()
+        ws = torch.empty(int(L.load().sty_tprls_workspace_bytes()) // 4 + 4, device=a.device, dtype=torch.int32)
+        sums = torch.empty(3, device=a.device, dtype=torch.float32)
+        med = torch.empty(1, device=a.device, dtype=torch.float32)
+        L.call("sty_tprls_fwd", a.data_ptr(), b.data_ptr(), n, ws.data_ptr(), sums.data_ptr(), med.data_ptr(),
+               L.stream_ptr())
+        l_rel = sums[0] / (sums[1] + eps)
+        ctx.save_for_backward(a, b, sums, med, l_rel)
+        ctx.eps = eps
+        return TAU - torch.relu(TAU - l_rel)
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b, sums, med, l_rel = ctx.saved_tensors
+        gate = (l_rel < TAU).to(torch.float32) * g   # d/dl [tau - relu(tau - l)]
+        denom = sums[1] + ctx.eps
+        coef = torch.stack([gate * 2.0 / denom, gate * (-2.0) * sums[2] / denom]).contiguous()
+        need_a, need_b = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        da = torch.empty_like(a) if need_a else None
+        db = torch.empty_like(b) if need_b else None
+        flag = torch.empty(1, device=a.device, dtype=torch.int32)
+        L.call("sty_tprls_bwd", a.data_ptr(), b.data_ptr(), a.numel(), med.data_ptr(), coef.data_ptr(), L.ptr(da),
+               L.ptr(db), flag.data_ptr(), L.stream_ptr())
+        return da, db, None
+
+
+def lsgan_discriminator(real: List[torch.Tensor], gen: List[torch.Tensor]):
+    """losses.py:251-262"""
+    return sum(_SqMeanFn.apply(dr, 1.0) + _SqMeanFn.apply(dg, 0.0) for dr, dg in zip(real, gen))
+
+
+def lsgan_generator(gen: List[torch.Tensor]):
+    """losses.py:339-343"""
+    return sum(_SqMeanFn.apply(dg, 1.0) for dg in gen)
+
+
+def tprls_discriminator(real, gen):
+    """losses.py:264-278"""
+    return sum(_TprlsFn.apply(dr, dg, 1e-9) for dr, dg in zip(real, gen))
+
+
+def tprls_generator(real, gen):
+    """losses.py:356-363 — the reference zips (real, gen) into the names (dg, dr): inside its loop 'dr' is the
+    GENERATED score; restated literally (median of gen - real, mask gen < real + m, plain mean)"""
+    return sum(_TprlsFn.apply(dg_gen, dr_real, 0.0) for dr_real, dg_gen in zip(real, gen))
+
+
+class GeneratorLoss(nn.Module):
+    """GeneratorLoss.forward with used = the acoustic set (losses.py:316-327): sum over mrd0..2 of
+    [LSGAN + TPRLS on the generated / real scores] (+ disc_weight x the same on the waveform discriminator when
+    one is supplied).  Gradients flow into `pred_list` only; the discriminators' parameters are treated as constants
+    (the reference computes their gradients here and discards them with zero_grad, stage.py:127)."""
+
+    def __init__(self, *, mrd0, mrd1, mrd2, disc: Optional[nn.Module] = None):
+        super().__init__()
+        self.mrd = nn.ModuleList([mrd0, mrd1, mrd2])
+        self.disc = disc
+
+    @staticmethod
+    def _one(model, target, pred):
+        with torch.no_grad():
+            real, _ = model(target)
+        gen, _ = model(pred)
+        return lsgan_generator(gen) + tprls_generator(real, gen)
+
+    def forward(self, *, target_list, pred_list, target_audio=None, pred_audio=None):
+        req = [p.requires_grad for m in self.mrd for p in m.parameters()]
+        for m in self.mrd:
+            m.requires_grad_(False)
+        try:
+            loss = sum(self._one(m, t, p) for m, t, p in zip(self.mrd, target_list, pred_list))
+        finally:
+            it = iter(req)
+            for m in self.mrd:
+                for p in m.parameters():
+                    p.requires_grad_(next(it))
+        if self.disc is not None:
+            loss = loss + DISC_WEIGHT * self._one(self.disc, target_audio, pred_audio)
+        return loss
+
+
+class DiscriminatorLoss(nn.Module):
+    """DiscriminatorLoss.forward, acoustic set (losses.py:196-207) on DETACHED spectrograms, plus the moving
+    average of the plain LSGAN part per discriminator that drives its learning rate (losses.py:280-288)."""
+
+    def __init__(self, *, mrd0, mrd1, mrd2, disc: Optional[nn.Module] = None, device="cuda"):
+        super().__init__()
+        self.mrd = nn.ModuleList([mrd0, mrd1, mrd2])
+        self.disc = disc
+        self.lr_control = {f"mrd{i}": DiscriminatorLR(5, device) for i in range(3)}
+        self.lr_control["disc"] = DiscriminatorLR(1, device)
+
+    def _one(self, key, model, target, pred):
+        real, _ = model(target.detach())
+        gen, _ = model(pred.detach())
+        d = lsgan_discriminator(real, gen)
+        self.lr_control[key].update(d)
+        return d + tprls_discriminator(real, gen)
+
+    def forward(self, *, target_list, pred_list, target_audio=None, pred_audio=None):
+        loss = sum(self._one(f"mrd{i}", m, t, p) for i, (m, t, p) in enumerate(zip(self.mrd, target_list, pred_list)))
+        if self.disc is not None:
+            loss = loss + DISC_WEIGHT * self._one("disc", self.disc, target_audio, pred_audio)
+        return loss

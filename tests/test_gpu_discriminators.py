@@ -1,0 +1,179 @@
+"""Spectrogram discriminators and adversarial losses on the device through the C ABI:
+
+* ``SpecDiscriminator`` (drop-in for mrd0-2, discriminator.py:13-69) against the golden outputs of the UNMODIFIED
+  reference (tests/golden/discriminators.npz) and, at a size that takes the tensor-core path (frames >= 64 after
+  three stride-2 layers), against the fp64 oracle — scores, input gradient and every parameter gradient;
+* LSGAN + TPRLS generator / discriminator losses (losses.py:251-278,339-363) incl. the radix-select median, against
+  the oracle formulas (which tests/test_disc_oracle.py pins to the reference);
+* the device-resident moving average / learning-rate multiplier.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import disc_oracle as do
+from stylish_tts_b200 import _lib as L
+from stylish_tts_b200 import discriminator as D
+from tests import util
+from tests.golden.make_disc_golden import inputs, state_dict_from_table
+from tests.util import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def gold():
+    z = np.load(util.GOLDEN_DIR + "/discriminators.npz")
+    return {k: z[k] for k in z.files}
+
+
+def test_spec_discriminator_vs_reference_golden():
+    g = gold()
+    tf, _, _, _ = inputs()
+    for i in range(3):
+        m = D.SpecDiscriminator()
+        m.load_state_dict(state_dict_from_table(g[f"mrd{i}_names"], g[f"mrd{i}_shapes"]), strict=True)
+        m = m.to(dev())
+        with torch.no_grad():
+            outs, fmaps = m(tf[i].to(dev()))
+        assert fmaps == [] and len(outs) == 5
+        for j, o in enumerate(outs):
+            ref = torch.from_numpy(g[f"mrd{i}_out{j}"])
+            assert o.shape == ref.shape, (i, j, o.shape, ref.shape)
+            assert rel_l2(o, ref) < 3e-5, (i, j, rel_l2(o, ref))
+
+
+def _seeded_disc(seed):
+    torch.manual_seed(seed)
+    m = D.SpecDiscriminator()
+    with torch.no_grad():
+        for p in m.parameters():
+            if p.dim() > 1 and p.shape[1:] != (1, 1, 1):
+                p.copy_(torch.randn(p.shape) / np.sqrt(p[0].numel()))
+            elif p.dim() == 1:
+                p.copy_(0.1 * torch.randn(p.shape))
+    return m
+
+
+@pytest.mark.parametrize("tensor_cores", [True, False])
+@pytest.mark.parametrize("bins,frames", [(65, 523), (33, 1030)])
+def test_spec_discriminator_tensor_core_path_vs_fp64_oracle(bins, frames, tensor_cores, monkeypatch):
+    from stylish_tts_b200 import engine as E
+
+    monkeypatch.setattr(E, "USE_UMMA", tensor_cores)
+    m = _seeded_disc(bins)
+    sd64 = {k: v.detach().double().requires_grad_(True) for k, v in m.state_dict().items()}
+    gen = torch.Generator().manual_seed(frames)
+    y = torch.rand(2, 1, bins, frames, generator=gen) * 3
+    y64 = y.double().requires_grad_(True)
+    outs_ref = do.spec_discriminator(sd64, y64)
+    cots = [torch.randn(o.shape, generator=gen).double() for o in outs_ref]
+    sum((o * c).sum() for o, c in zip(outs_ref, cots)).backward()
+    md = m.to(dev())
+    yd = y.to(dev()).requires_grad_(True)
+    calls = []
+    orig = L.call
+    L.call = lambda name, *a: (calls.append((name, a)), orig(name, *a))[1]
+    try:
+        outs, _ = md(yd)
+    finally:
+        L.call = orig
+    umma = [a[0]._obj for n, a in calls if n == "sty_conv1d_fwd" and a[0]._obj.w_split]
+    if tensor_cores:  # the space-to-depth convs and the last 3x3 conv run on tcgen05
+        assert len(umma) >= 4 and {(c.CI, c.K) for c in umma} >= {(192, 5), (96, 3)}
+    else:
+        assert not umma
+    sum((o * c.float().to(dev())).sum() for o, c in zip(outs, cots)).backward()
+    torch.cuda.synchronize()
+    for j, (o, r) in enumerate(zip(outs, outs_ref)):
+        assert o.shape == r.shape and rel_l2(o, r) < 1e-4, (j, rel_l2(o, r))
+    # LeakyReLU(0.1) has a kink at 0: a forward difference of 1e-5 (bf16x3) / 1e-6 (fp32 FMA) flips the slope of the
+    # pre-activations that close to zero, and the gradient error goes like the square root of that fraction
+    tol = 8e-3 if tensor_cores else 1e-3  # measured 3.9e-3 / 5.1e-4; the conv primitives themselves hold 6e-6 (test_style_encoder)
+    print("d(input)", rel_l2(yd.grad, y64.grad))
+    assert rel_l2(yd.grad, y64.grad) < tol, rel_l2(yd.grad, y64.grad)
+    params = dict(md.named_parameters())
+    worst = 0.0
+    for k, v in sd64.items():
+        assert params[k].grad is not None, k
+        e = rel_l2(params[k].grad, v.grad)
+        worst = max(worst, e)
+        assert e < tol, (k, e)
+    print("worst parameter gradient", worst)
+
+
+@pytest.mark.parametrize("n", [1, 2, 7, 1000, 65537, 300001])
+def test_tprls_kernels_vs_torch(n):
+    gen = torch.Generator().manual_seed(n)
+    a = torch.randn(n, generator=gen)
+    b = torch.randn(n, generator=gen) * 0.7 + 0.1
+    for eps, fn in ((1e-9, lambda r, g_: do.tprls_discriminator([r], [g_])), (0.0, None)):
+        a64, b64 = a.double().requires_grad_(True), b.double().requires_grad_(True)
+        if fn is None:  # generator form on (gen=a, real=b): do.tprls_generator(real, gen)
+            ref = do.tprls_generator([b64], [a64])
+        else:
+            ref = fn(a64, b64)
+        ad, bd = a.to(dev()).requires_grad_(True), b.to(dev()).requires_grad_(True)
+        out = D._TprlsFn.apply(ad, bd, eps)
+        if not torch.isfinite(ref):
+            assert not torch.isfinite(out)  # empty selection: NaN in the reference formula too
+            continue
+        assert float(out) == pytest.approx(float(ref), rel=2e-5, abs=1e-7), (n, eps)
+        ref.backward()
+        out.backward()
+        if float(a64.grad.abs().sum()) > 0:
+            assert rel_l2(ad.grad, a64.grad) < 1e-4 and rel_l2(bd.grad, b64.grad) < 1e-4
+        else:
+            assert float(ad.grad.abs().sum()) == 0.0
+
+
+def test_adversarial_losses_vs_oracle_and_lr_control():
+    g = gold()
+    tf, pf, _, _ = inputs()
+    # frames >= 8 so that every scale has several elements; the golden's own sizes
+    mods = []
+    for i in range(3):
+        m = D.SpecDiscriminator()
+        m.load_state_dict(state_dict_from_table(g[f"mrd{i}_names"], g[f"mrd{i}_shapes"]), strict=True)
+        mods.append(m.to(dev()))
+    sds = {f"mrd{i}": {k: v.detach().cpu().double().requires_grad_(True) for k, v in mods[i].state_dict().items()}
+           for i in range(3)}
+    tfd, pfd = [t.to(dev()) for t in tf], [p.to(dev()).requires_grad_(True) for p in pf]
+    pf64 = [p.double().requires_grad_(True) for p in pf]
+    tf64 = [t.double() for t in tf]
+    # generator side
+    gl = D.GeneratorLoss(mrd0=mods[0], mrd1=mods[1], mrd2=mods[2])
+    loss = gl(target_list=tfd, pred_list=pfd)
+    ref = sum(do.helper_generator(lambda y, i=i: do.spec_discriminator(sds[f"mrd{i}"], y), tf64[i], pf64[i])
+              for i in range(3))
+    assert float(loss) == pytest.approx(float(ref), rel=1e-4)
+    loss.backward()
+    ref.backward()
+    for i in range(3):
+        assert rel_l2(pfd[i].grad, pf64[i].grad) < 1e-3, (i, rel_l2(pfd[i].grad, pf64[i].grad))
+    assert all(p.grad is None for m in mods for p in m.parameters())  # constants of the generator step
+    assert all(p.requires_grad for m in mods for p in m.parameters())
+    # discriminator side
+    for sd in sds.values():
+        for v in sd.values():
+            v.grad = None
+    dl = D.DiscriminatorLoss(mrd0=mods[0], mrd1=mods[1], mrd2=mods[2], device=dev())
+    dloss = dl(target_list=tfd, pred_list=[p.detach() for p in pfd])
+    parts = [do.helper_discriminator(lambda y, i=i: do.spec_discriminator(sds[f"mrd{i}"], y), tf64[i],
+                                     pf64[i].detach()) for i in range(3)]
+    dref = sum(p[0] for p in parts)
+    assert float(dloss) == pytest.approx(float(dref), rel=1e-4)
+    dloss.backward()
+    dref.backward()
+    for i in range(3):
+        for k, p in mods[i].named_parameters():
+            e = rel_l2(p.grad, sds[f"mrd{i}"][k].grad)
+            assert e < 2e-3, (i, k, e)
+    # moving average of the plain LSGAN part and the resulting learning-rate multiplier (losses.py:237-249,287)
+    last = 0.5 * 5 * 0.95 + float(parts[0][1]) * 0.05
+    assert float(dl.lr_control["mrd0"].last_loss) == pytest.approx(last, rel=1e-5)
+    assert float(dl.lr_control["mrd0"].last_loss) == pytest.approx(float(g["last_loss_mrd0"]), rel=1e-4)
+    assert float(dl.lr_control["mrd0"].multiplier()) == pytest.approx(float(g["lr_mult_mrd0"]), rel=1e-3)
