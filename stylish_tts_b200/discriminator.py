@@ -122,6 +122,32 @@ class SpecDiscriminator(nn.Module):
         return result, []
 
 
+class PitchDiscriminator(nn.Module):
+    """Drop-in for reference PitchDiscriminator (pitch_discriminator.py:6-68; ``pitch_disc`` = (2, 64, k21),
+    ``dur_disc`` = (1, 64, k5), models.py:78-83): five weight-normed 'same' Conv1d + LeakyReLU(0.1), each with its
+    own k-tap score conv; forward(y (B,dim_in,T)) -> (five (B,T) score maps, [])."""
+
+    def __init__(self, *, dim_in, dim_hidden, kernel):
+        super().__init__()
+        pad = kernel // 2
+        c1 = lambda ci, co: weight_norm(nn.Conv1d(ci, co, kernel_size=kernel, padding=pad))
+        self.discriminators = nn.ModuleList([c1(dim_in, dim_hidden)] + [c1(dim_hidden, dim_hidden) for _ in range(4)])
+        self.out = nn.ModuleList([c1(dim_hidden, 1) for _ in range(5)])
+
+    def forward(self, y):
+        from . import train_ops as T
+
+        if not y.is_cuda:
+            raise RuntimeError("stylish_tts_b200: PitchDiscriminator needs CUDA tensors (no CPU fallback)")
+        w = SpecDiscriminator._w
+        result = []
+        h = y.to(torch.float32).contiguous()
+        for i, d in enumerate(self.discriminators):
+            h = LeakyS2dFn.apply(T.conv(h, w(d), d.bias), 1, 0.1)
+            result.append(T.conv(h, w(self.out[i]), self.out[i].bias).flatten(1))
+        return result, []
+
+
 # ---------------------------------------------------------------------------------------------- losses
 class _SqMeanFn(Function):
     """mean((c - x)^2) with the reduction on the device kernel (losses.py:257-259,341)"""

@@ -100,15 +100,19 @@ class FlatAdamW:
         L.param_epoch += 1  # the arena changed under the views: invalidates the engines' packed weights
 
 
-def acoustic_losses(audio_pred, audio_target, multi_spectrogram, stft_loss, *, w_mel=5.0, w_phase=8.0):
+def acoustic_losses(audio_pred, audio_target, multi_spectrogram, stft_loss, *, w_mel=5.0, w_phase=8.0,
+                    return_fft=False):
     """mel + multi_phase terms of the acoustic stage with LossLog.backwards_loss normalisation
-    (stage_type.py:170-193, loss_log.py:82-94, weights config.yml:73-107).  -> (total, mel, phase)"""
+    (stage_type.py:170-193, loss_log.py:82-94, weights config.yml:73-107).  -> (total, mel, phase)
+    [+ (target |X| list, predicted |X| list) — the discriminators' inputs, stage_type.py:208-219]"""
     from .spectral import multi_phase_loss
 
-    t_spec, p_spec, t_ph, p_ph, _, _ = multi_spectrogram(target=audio_target, pred=audio_pred)
+    t_spec, p_spec, t_ph, p_ph, t_fft, p_fft = multi_spectrogram(target=audio_target, pred=audio_pred)
     mel = stft_loss(target_list=t_spec, pred_list=p_spec)
     ph = multi_phase_loss(p_ph, t_ph)
     total = w_mel * mel / (mel.detach() + 1e-9) + w_phase * ph / (ph.detach() + 1e-9)
+    if return_fft:
+        return total, mel, ph, t_fft, p_fft
     return total, mel, ph
 
 

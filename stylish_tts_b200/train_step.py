@@ -50,7 +50,8 @@ def alignment_from_durations(durations: torch.Tensor, frames: int = 0, multiplie
     return al
 
 
-def acoustic_step(batch, nets, fe: FrontEnd, *, w_mel=5.0, w_phase=8.0, source_draws=None, prior=None):
+def acoustic_step(batch, nets, fe: FrontEnd, *, w_mel=5.0, w_phase=8.0, source_draws=None, prior=None,
+                  generator_loss=None, w_generator=1.0):
     """batch: audio_gt (B,L), text (B,T), text_length (B,), pitch (B,F), alignment (B,1,T) integer durations
     (the reference's collated batch, stage_type.py:61-106).  Returns total / mel / multi_phase losses and
     the prediction.  `prior` = (har_spec, har_phase) injects the harmonic prior (parity tests)."""
@@ -67,7 +68,36 @@ def acoustic_step(batch, nets, fe: FrontEnd, *, w_mel=5.0, w_phase=8.0, source_d
     style = nets.speech_style_encoder(style_mel.unsqueeze(1))
     pred = nets.speech_predictor(batch.text, batch.text_length, alignment, pitch, energy, voiced, style, pitch,
                                  source_draws=source_draws, prior=prior)
-    total, mel_loss, phase_loss = acoustic_losses(pred.audio.squeeze(1), audio_gt, fe.multi_spectrogram,
-                                                  fe.stft_loss, w_mel=w_mel, w_phase=w_phase)
-    return SimpleNamespace(total=total, mel=mel_loss, multi_phase=phase_loss, pred=pred, style=style,
-                           energy=energy, mel_target=mel)
+    total, mel_loss, phase_loss, t_fft, p_fft = acoustic_losses(pred.audio.squeeze(1), audio_gt, fe.multi_spectrogram,
+                                                                fe.stft_loss, w_mel=w_mel, w_phase=w_phase,
+                                                                return_fft=True)
+    gen_loss = None
+    if generator_loss is not None:
+        # step.generator_loss (stage_type.py:208-219): the adversarial term enters backwards_loss RAW (loss_log.py:85-86)
+        gen_loss = generator_loss(target_list=t_fft, pred_list=p_fft, target_audio=audio_gt,
+                                  pred_audio=pred.audio.squeeze(1))
+        total = total + w_generator * gen_loss
+    return SimpleNamespace(total=total, mel=mel_loss, multi_phase=phase_loss, generator=gen_loss, pred=pred,
+                           style=style, energy=energy, mel_target=mel, target_fft=t_fft, pred_fft=p_fft)
+
+
+def discriminator_step(out, batch, discriminator_loss, optimizers, *, disc_index: int, lr_source=None):
+    """The second half of Stage.train_batch (stage.py:125-146): discriminator loss on the DETACHED spectrograms of
+    the step just taken, backward of d_loss * sqrt(B), optimizer step of ``mrd{disc_index}`` (and ``disc`` when the
+    loss carries a waveform discriminator).  `optimizers`: dict key -> FlatAdamW.  `lr_source`: the generator's
+    FlatAdamW — when given, each stepped discriminator's learning rate is lr_gen x its gap-aware multiplier first
+    (optimizers.py:54-65), all on the device."""
+    import math
+
+    d_loss = discriminator_loss(target_list=[t.detach() for t in out.target_fft],
+                                pred_list=[p.detach() for p in out.pred_fft], target_audio=batch.audio_gt,
+                                pred_audio=out.pred.audio.detach().squeeze(1))
+    (d_loss * math.sqrt(batch.text.shape[0])).backward()
+    keys = [f"mrd{disc_index}"] + (["disc"] if "disc" in optimizers else [])
+    for k in keys:
+        if lr_source is not None:
+            discriminator_loss.lr_control[k].apply(lr_source, optimizers[k])
+        optimizers[k].step()
+    for opt in optimizers.values():
+        opt.zero_grad()
+    return d_loss.detach()

@@ -54,7 +54,9 @@ def test_forward_plumbing(recorder, monkeypatch):
     assert cnt["sty_source_fwd"] == 1 and cnt["sty_stft_pitched_fwd"] == 1 and cnt["sty_istft_head_pitched_fwd"] == 1
     # C<=64 ConvNeXt fronts are fused into the pointwise conv (tensor-core path) when T >= 128
     assert cnt["sty_dwconv_ln_fwd"] == 5 + 1
-    assert cnt["sty_grn_scale_fwd"] == 16
+    # the 9 output-rate ConvNeXt blocks are one fused call each (pass 1 + GRN scale + pass 2 inside the library)
+    assert cnt["sty_convnext_fused_fwd"] == 9
+    assert cnt["sty_grn_scale_fwd"] == 16 - 9
     # decoder AdaINs keep the two-pass statistics kernel; the 12 S-rate AdaINs of the two generator blocks
     # take their statistics from the producing conv's epilogue (out_sum / out_sumsq -> moments_affine)
     assert cnt["sty_instnorm_affine_fwd"] == 2 * 5

@@ -177,3 +177,60 @@ def test_adversarial_losses_vs_oracle_and_lr_control():
     assert float(dl.lr_control["mrd0"].last_loss) == pytest.approx(last, rel=1e-5)
     assert float(dl.lr_control["mrd0"].last_loss) == pytest.approx(float(g["last_loss_mrd0"]), rel=1e-4)
     assert float(dl.lr_control["mrd0"].multiplier()) == pytest.approx(float(g["lr_mult_mrd0"]), rel=1e-3)
+
+
+def test_acoustic_step_with_adversarial_terms_and_discriminator_step():
+    """configs[2] "full train step": AcousticStep forward + mel / multi-phase / generator (mrd0-2) terms, backward,
+    AdamW on speech_predictor + speech_style_encoder, then the discriminator half of Stage.train_batch
+    (stage.py:125-146): detached spectrograms, d_loss * sqrt(B), one mrd optimizer stepped at lr_gen x multiplier."""
+    from types import SimpleNamespace
+    import stylish_tts_b200 as st
+    from stylish_tts_b200 import optim, synth, train_step as ts
+
+    d = dev()
+    mc = st.default_model_config()
+    nets = st.build_model(mc)
+    assert {"mrd0", "mrd1", "mrd2", "pitch_disc", "dur_disc"} <= set(nets)
+    synth.randomize_(nets.speech_predictor, 0)
+    synth.converge_spectral_(nets.speech_style_encoder)
+    for k in list(nets):
+        nets[k] = nets[k].to(d)
+    sp, se = nets.speech_predictor.train(), nets.speech_style_encoder.train()
+    sp.regularisers = False
+    B, Tn = 2, 18
+    inp = synth.speech_inputs(B, Tn, seed=4)
+    dur = torch.full((B, Tn), 3.0)
+    dur[:, ::9] += 1.0
+    frames = int(dur[0].sum())
+    g = torch.Generator().manual_seed(8)
+    batch = SimpleNamespace(audio_gt=(0.1 * torch.randn(B, frames * 300, generator=g)).to(d),
+                            text=inp["texts"].to(d), text_length=inp["text_lengths"].to(d),
+                            pitch=inp["pitch"].to(d), alignment=dur.unsqueeze(1).to(d))
+    fe = ts.FrontEnd(mc)
+    gen_opt = optim.FlatAdamW(list(sp.parameters()) + list(se.parameters()), lr=1e-4, betas=(0.85, 0.99), eps=1e-9,
+                              weight_decay=1e-4, world_size=1)
+    disc_opts = {f"mrd{i}": optim.FlatAdamW(nets[f"mrd{i}"].parameters(), lr=1e-4, betas=(0.85, 0.99), eps=1e-9,
+                                            weight_decay=1e-4, world_size=1) for i in range(3)}
+    gl = D.GeneratorLoss(mrd0=nets.mrd0, mrd1=nets.mrd1, mrd2=nets.mrd2)
+    dl = D.DiscriminatorLoss(mrd0=nets.mrd0, mrd1=nets.mrd1, mrd2=nets.mrd2, device=d)
+    draws = {"noise": inp["draws"]["noise"].to(d)}
+    before = {k: o.flat.clone() for k, o in disc_opts.items()}
+    out = ts.acoustic_step(batch, nets, fe, source_draws=draws, generator_loss=gl)
+    assert out.generator is not None and torch.isfinite(out.generator)
+    plain = ts.acoustic_step(batch, nets, fe, source_draws=draws)
+    assert float(out.total) == pytest.approx(float(plain.total) + float(out.generator), rel=1e-5)
+    out.total.backward()
+    for n, p in list(sp.named_parameters()) + list(se.named_parameters()):
+        if "m_source" not in n:
+            assert p.grad is not None and torch.isfinite(p.grad).all(), n
+    assert all(p.grad is None for i in range(3) for p in nets[f"mrd{i}"].parameters())
+    gen_opt.step()
+    gen_opt.zero_grad()
+    d_loss = ts.discriminator_step(out, batch, dl, disc_opts, disc_index=1, lr_source=gen_opt)
+    torch.cuda.synchronize()
+    assert torch.isfinite(d_loss)
+    assert float((disc_opts["mrd1"].flat - before["mrd1"]).abs().max()) > 0      # stepped
+    assert float((disc_opts["mrd0"].flat - before["mrd0"]).abs().max()) == 0     # not this index
+    mult = float(dl.lr_control["mrd1"].multiplier())
+    assert float(disc_opts["mrd1"].hyper[0]) == pytest.approx(1e-4 * mult, rel=1e-5)
+    assert all(p.grad is None for i in range(3) for p in nets[f"mrd{i}"].parameters())
