@@ -357,6 +357,16 @@ def measure_train(args, dev, world, rank, barrier, steps, warmup, batch):
     opt = optim.FlatAdamW(list(sp.parameters()) + list(se.parameters()), lr=1e-4, betas=(0.85, 0.99), eps=1e-9,
                           weight_decay=1e-4, world_size=world)
     fe = ts.FrontEnd(mc)
+    adversarial = None
+    if getattr(args, "adversarial", False):
+        # the adversarial half of configs[2]: generator term on mrd0-2 + one discriminator stepped per batch
+        # (the waveform discriminator `disc` of the reference is not re-implemented: DESIGN.md)
+        from stylish_tts_b200 import discriminator as D
+        mrd = [nets[f"mrd{i}"].to(dev).train() for i in range(3)]
+        disc_opts = {f"mrd{i}": optim.FlatAdamW(mrd[i].parameters(), lr=1e-4, betas=(0.85, 0.99), eps=1e-9,
+                                                weight_decay=1e-4, world_size=world) for i in range(3)}
+        adversarial = (D.GeneratorLoss(mrd0=mrd[0], mrd1=mrd[1], mrd2=mrd[2]),
+                       D.DiscriminatorLoss(mrd0=mrd[0], mrd1=mrd[1], mrd2=mrd[2], device=dev), disc_opts)
     host = synth.speech_inputs(batch, args.tokens, seed=11 + rank)
     dur = torch.full((batch, args.tokens), 3.0)
     dur[:, ::9] += 1.0  # the durations synth.speech_inputs builds its alignment from
@@ -374,17 +384,22 @@ def measure_train(args, dev, world, rank, barrier, steps, warmup, batch):
     loss_host = torch.empty(3, dtype=torch.float32).pin_memory()
 
     def train_step(b):
-        out = ts.acoustic_step(SimpleNamespace(**b), nets, fe)  # source noise drawn on the device (reference too)
-        out.total.backward()
+        import random
+        bb = SimpleNamespace(**b)
+        out = ts.acoustic_step(bb, nets, fe, generator_loss=adversarial[0] if adversarial else None)
+        out.total.backward()  # source noise drawn on the device (reference too)
         opt.step()
         opt.zero_grad()
+        if adversarial:
+            ts.discriminator_step(out, bb, adversarial[1], adversarial[2], disc_index=random.randrange(3),
+                                  lr_source=opt)
         return torch.stack([out.total.detach(), out.mel.detach(), out.multi_phase.detach()])
 
     graphed = None
     if not args.no_graph:
         try:  # the whole iteration (fwd, losses, bwd, all-reduce, AdamW) as one CUDA graph
             from stylish_tts_b200.runtime import GraphedAcousticStep
-            graphed = GraphedAcousticStep(nets, fe, opt, SimpleNamespace(**resident))
+            graphed = GraphedAcousticStep(nets, fe, opt, SimpleNamespace(**resident), adversarial=adversarial)
         except Exception as e:  # still our kernels, launched eagerly
             log(f"[bench] train-step graph capture failed ({type(e).__name__}: {e}); eager launches")
             graphed = None
@@ -396,7 +411,7 @@ def measure_train(args, dev, world, rank, barrier, steps, warmup, batch):
 
     def step_e2e():
         if graphed is not None:
-            loss_host.copy_(graphed(SimpleNamespace(**pinned)), non_blocking=True)
+            loss_host.copy_(graphed(SimpleNamespace(**pinned))[:3], non_blocking=True)
         else:
             loss_host.copy_(train_step({k: v.to(dev, non_blocking=True) for k, v in pinned.items()}),
                             non_blocking=True)
@@ -434,6 +449,9 @@ def measure_train(args, dev, world, rank, barrier, steps, warmup, batch):
         "grad_allreduce_bytes": opt.numel * 4 if world > 1 else 0,
         "params": opt.numel, "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 1e9, 1),
         "loss": [round(float(x), 5) for x in loss_host.tolist()],
+        "adversarial": ("generator term on mrd0-2 (LSGAN + TPRLS) + discriminator half-step (one of mrd0-2 per batch, "
+                        "sqrt(B) scaling, gap-aware lr); waveform discriminator `disc` not included") if adversarial
+        else "off",
         "scope": "AcousticStep(use_predicted_pe=False, predict_audio=True): calculate_mel x2 + energy + alignment "
                  "+ speech_style_encoder + speech_predictor (train() mode: batch-stat BN, dropout sites and decoder box smoothing live) + "
                  "MultiSpectrogram x3 + mel & multi-phase losses (backwards_loss normalisation) + backward of "
@@ -771,6 +789,8 @@ def main():
                          "train: configs[2]/[4] as the line itself")
     ap.add_argument("--train-batch", type=int, default=32)
     ap.add_argument("--no-train", action="store_true", help="skip the train sub-measurement of --mode fwd")
+    ap.add_argument("--adversarial", action="store_true",
+                    help="train measurement with the adversarial terms (spectrogram discriminators mrd0-2)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -54,9 +54,15 @@ class GraphedAcousticStep:
     static buffers; the learning rate / step count live in device memory (`FlatAdamW.hyper`), so replays keep
     advancing the optimizer.  Shapes are fixed at capture time."""
 
-    def __init__(self, nets, frontend, optimizer, example_batch, *, warmup: int = 3, source_draws=None):
+    def __init__(self, nets, frontend, optimizer, example_batch, *, warmup: int = 3, source_draws=None,
+                 adversarial=None):
+        """adversarial = (GeneratorLoss, DiscriminatorLoss, {key: FlatAdamW of mrd0..2}): the iteration then also
+        carries the generator's adversarial term and the discriminator half-step (stage.py:116-146).  The reference
+        draws the stepped discriminator with random.randrange(3) per batch, so one graph per index is captured
+        (shared memory pool) and picked at replay."""
+        import random
         from types import SimpleNamespace
-        from .train_step import acoustic_step
+        from .train_step import acoustic_step, discriminator_step
 
         self.static = {k: v.clone() for k, v in vars(example_batch).items()}
         self.opt = optimizer
@@ -67,12 +73,23 @@ class GraphedAcousticStep:
         for g in self.train_graphs:
             g.auto_step = False
 
-        def iteration():
-            out = acoustic_step(batch, nets, frontend, source_draws=source_draws)
+        self.adversarial = adversarial
+        self._random = random
+
+        def iteration(disc_index=0):
+            if adversarial is None:
+                out = acoustic_step(batch, nets, frontend, source_draws=source_draws)
+            else:
+                out = acoustic_step(batch, nets, frontend, source_draws=source_draws, generator_loss=adversarial[0])
             out.total.backward()
             optimizer.step()
             optimizer.zero_grad()
-            return torch.stack([out.total.detach(), out.mel.detach(), out.multi_phase.detach()])
+            terms = [out.total.detach(), out.mel.detach(), out.multi_phase.detach()]
+            if adversarial is not None:
+                terms.append(out.generator.detach())
+                terms.append(discriminator_step(out, batch, adversarial[1], adversarial[2], disc_index=disc_index,
+                                                lr_source=optimizer))
+            return torch.stack(terms)
 
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -82,14 +99,29 @@ class GraphedAcousticStep:
                 iteration()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        torch.cuda.empty_cache()  # the warm-up's activations go back to the driver before the graph pool grows
         self.begin_step()
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
         before = L.launches
         with torch.cuda.graph(self.graph):
-            self.losses = iteration()
+            self.losses = iteration(0)
         self.launches_per_replay = L.launches - before
         optimizer.step_count -= 1  # capturing launches nothing: only the warm-up iterations were real updates
+        self.graphs, self.loss_bufs = [self.graph], [self.losses]
+        if adversarial is not None:
+            adversarial[2]["mrd0"].step_count -= 1
+            for idx in (1, 2):  # one graph per stepped discriminator, same memory pool (replayed one at a time);
+                # nothing index-specific is allocated lazily (all three discriminators run in every iteration)
+                self.begin_step()
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, pool=self.graph.pool()):
+                    buf = iteration(idx)
+                optimizer.step_count -= 1
+                adversarial[2][f"mrd{idx}"].step_count -= 1
+                self.graphs.append(g)
+                self.loss_bufs.append(buf)
 
     def begin_step(self):
         for g in self.train_graphs:
@@ -101,7 +133,10 @@ class GraphedAcousticStep:
         if batch is not None:
             for k, v in vars(batch).items():
                 self.static[k].copy_(v, non_blocking=True)
-        self.graph.replay()
+        idx = self._random.randrange(3) if self.adversarial is not None else 0  # stage.py:119
+        self.graphs[idx].replay()
         self.opt.step_count += 1
+        if self.adversarial is not None:
+            self.adversarial[2][f"mrd{idx}"].step_count += 1
         L.param_epoch += 1
-        return self.losses
+        return self.loss_bufs[idx]
