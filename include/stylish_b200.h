@@ -170,6 +170,27 @@ STY_API int sty_tprls_fwd(const float* a, const float* b, int64_t n, void* works
 STY_API int sty_tprls_bwd(const float* a, const float* b, int64_t n, const float* median, const float* coef, float* da,
                           float* db, int* flag, sty_stream_t stream);
 
+/* ---- style-diffusion denoiser (BASELINE configs[3]; absent from the reference) ----
+ * Token-major (rows = tokens) dense layers on TMA-fed tcgen05 GEMMs with bf16 hi|lo operand planes:
+ * sty_split_planes_fwd : fp32 (n) -> bf16 planes out[0..n) = hi, out[n..2n) = lo   (weights, inputs)
+ * sty_gemm_split_fwd   : C[M,N] = act(A W^T + bias) (+ res); A = planes [2][M][K], W = planes [2][N][K];
+ *                        out fp32 (M,N) and / or out_split planes [2][M][N]; M, N % 128 == 0, K % 64 == 0
+ * sty_build_tokens_fwd : tok[b*T+t] = [scale * x[b] (Cx) | emb[b,t] (Ce)], rows >= B*T zero
+ * sty_row_ln_split_fwd : hm = h + add[b] (written when hm != NULL); planes of LayerNorm_C(hm)*gamma+beta; C = 1024
+ * sty_token_mean_fwd   : out[b] = mean_t x[b*T+t]
+ * sty_attention_tokens_fwd : softmax(q k^T * scale) v per (batch, 64-wide head) on token-major q|k|v rows,
+ *                        result as planes [2][M_pad][H*64] */
+STY_API int sty_split_planes_fwd(const float* x, void* out, int64_t n, sty_stream_t stream);
+STY_API int sty_gemm_split_fwd(const void* a_split, const void* w_split, const float* bias, const float* res,
+                               float* out, void* out_split, int M, int N, int K, int act, sty_stream_t stream);
+STY_API int sty_build_tokens_fwd(const float* x, const float* emb, float scale, float* tok, int B, int T, int Cx, int Ce,
+                                 int M, sty_stream_t stream);
+STY_API int sty_row_ln_split_fwd(const float* h, const float* add, const float* gamma, const float* beta, float eps,
+                                 float* hm, void* out_split, int M, int M_real, int T, int C, sty_stream_t stream);
+STY_API int sty_token_mean_fwd(const float* x, float* out, int B, int T, int C, sty_stream_t stream);
+STY_API int sty_attention_tokens_fwd(const float* qkv, int64_t ld, void* out_split, int64_t M_pad, int B, int H, int T,
+                                     float scale, sty_stream_t stream);
+
 /* ---- LayerNorm over the channel axis of (B,C,T) --------------------------
  * v = x (+ res);  n = (v-mean_c)/sqrt(var_c+eps)
  * y = act( (g_plus_one ? 1+g : g) * n + b ) * mask[b,t]

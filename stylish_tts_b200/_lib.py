@@ -158,6 +158,13 @@ _SIGNATURES = {
                                _f32p, _f32p, _f32p, _i64, _f32p, _i32, _i32, _i32, _i32, _f32,
                                C.POINTER(Dropout), _f32p],
     "sty_stft_loss_finalize": [_f32p, _f32p, _f32p, _i32, _f32, _f32, _i32, _f32p, _f32p],
+    # style-diffusion denoiser (token-major TMA-fed GEMMs)
+    "sty_split_planes_fwd": [_f32p, _f32p, _i64, _f32p],
+    "sty_gemm_split_fwd": [_f32p, _f32p, _f32p, _f32p, _f32p, _f32p, _i32, _i32, _i32, _i32, _f32p],
+    "sty_build_tokens_fwd": [_f32p, _f32p, _f32, _f32p, _i32, _i32, _i32, _i32, _i32, _f32p],
+    "sty_row_ln_split_fwd": [_f32p, _f32p, _f32p, _f32p, _f32, _f32p, _f32p, _i32, _i32, _i32, _i32, _f32p],
+    "sty_token_mean_fwd": [_f32p, _f32p, _i32, _i32, _i32, _f32p],
+    "sty_attention_tokens_fwd": [_f32p, _i64, _f32p, _i64, _i32, _i32, _i32, _f32, _f32p],
     # adversarial losses (spectrogram discriminators, LSGAN / TPRLS)
     "sty_leaky_s2d_fwd": [_f32p, _f32p, _i64, _i32, _i32, _i32, _f32, _f32p],
     "sty_leaky_s2d_bwd": [_f32p, _f32p, _f32p, _i64, _i32, _i32, _i32, _f32, _f32p],

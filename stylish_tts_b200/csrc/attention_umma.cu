@@ -53,6 +53,35 @@ __device__ __forceinline__ void stage_head(uint4* __restrict__ dst, const float*
   }
 }
 
+// token-major source: row t holds the 64 features of this head contiguously, rows `ld` floats apart
+__device__ __forceinline__ void stage_head_tm(uint4* __restrict__ dst, const float* __restrict__ src, int64_t ld, int T,
+                                              int t0, int rows, float mul, int tid) {
+  const int n_items = 8 * rows;  // (row, d8): d8 fastest so that a warp reads whole 256-byte rows
+  for (int item = tid; item < n_items; item += kAThreads) {
+    const int row = item >> 3, d8 = item & 7;
+    const int t = t0 + row;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    if (t < T) {
+      const float* sp = src + (int64_t)t * ld + d8 * 8;
+      a = *reinterpret_cast<const float4*>(sp);
+      b = *reinterpret_cast<const float4*>(sp + 4);
+    }
+    const float v[8] = {a.x * mul, a.y * mul, a.z * mul, a.w * mul, b.x * mul, b.y * mul, b.z * mul, b.w * mul};
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      h[j] = pack_bf16(v[2 * j], v[2 * j + 1]);
+      l[j] = pack_bf16(v[2 * j] - __uint_as_float(h[j] << 16), v[2 * j + 1] - __uint_as_float(h[j] & 0xffff0000u));
+    }
+    dst[(0 * 8 + d8) * rows + row] = make_uint4(h[0], h[1], h[2], h[3]);
+    dst[(1 * 8 + d8) * rows + row] = make_uint4(l[0], l[1], l[2], l[3]);
+  }
+}
+
+// TM = false: q, k, v channel-major (B, H*64, T) fp32, output channel-major fp32 (the conformer).
+// TM = true : q, k, v token-major rows of `qkv_bs` floats ([B*T, ld], head h at columns h*64 of each pointer),
+//             output = bf16 hi | lo planes [2][o_bs rows][H*64] (the next GEMM's operand; o_bs = padded row count).
+template <bool TM>
 __global__ void __launch_bounds__(kAThreads, 2)
 attention_umma_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
                       int64_t qkv_bs, float* __restrict__ o, int64_t o_bs, int T, float scale,
@@ -66,10 +95,10 @@ attention_umma_kernel(const float* __restrict__ q, const float* __restrict__ k, 
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * kAQ;
-  const int64_t hoff = (int64_t)h * kAD * T;
-  const float* __restrict__ qb = q + (int64_t)b * qkv_bs + hoff;
-  const float* __restrict__ kb = k + (int64_t)b * qkv_bs + hoff;
-  const float* __restrict__ vb = v + (int64_t)b * qkv_bs + hoff;
+  const int64_t hoff = TM ? (int64_t)b * T * qkv_bs + (int64_t)h * kAD : (int64_t)b * qkv_bs + (int64_t)h * kAD * T;
+  const float* __restrict__ qb = q + hoff;
+  const float* __restrict__ kb = k + hoff;
+  const float* __restrict__ vb = v + hoff;
 
   if (warp == 0) tmem_alloc(tmem_slot, 128);
   if (tid == 0) {
@@ -77,7 +106,8 @@ attention_umma_kernel(const float* __restrict__ q, const float* __restrict__ k, 
     mbar_init(&bars[1], 1);
     fence_barrier_init();
   }
-  stage_head(Qs, qb, T, q0, kAQ, scale, tid);
+  if (TM) stage_head_tm(Qs, qb, qkv_bs, T, q0, kAQ, scale, tid);
+  else stage_head(Qs, qb, T, q0, kAQ, scale, tid);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -96,8 +126,13 @@ attention_umma_kernel(const float* __restrict__ q, const float* __restrict__ k, 
   for (int kt = 0; kt < n_tiles; ++kt) {
     const int k0 = kt * kAK;
     // the previous tile's MMAs have completed (waited below), so K/V/P buffers are free
-    stage_head(Ks, kb, T, k0, kAK, 1.f, tid);
-    stage_head(Vs, vb, T, k0, kAK, 1.f, tid);
+    if (TM) {
+      stage_head_tm(Ks, kb, qkv_bs, T, k0, kAK, 1.f, tid);
+      stage_head_tm(Vs, vb, qkv_bs, T, k0, kAK, 1.f, tid);
+    } else {
+      stage_head(Ks, kb, T, k0, kAK, 1.f, tid);
+      stage_head(Vs, vb, T, k0, kAK, 1.f, tid);
+    }
     fence_proxy_async_smem();
     __syncthreads();
     if (tid == 0) {
@@ -182,10 +217,30 @@ attention_umma_kernel(const float* __restrict__ q, const float* __restrict__ k, 
   const int tq = q0 + tid;
   if (tq < T) {
     const float inv = 1.0f / l_run;
-    float* __restrict__ ob = o + (int64_t)b * o_bs + hoff;
+    if constexpr (TM) {
+      const int C = gridDim.y * kAD;
+      const int64_t row = (int64_t)b * T + tq;
+      __nv_bfloat16* os = reinterpret_cast<__nv_bfloat16*>(o);
+      uint4* oh = reinterpret_cast<uint4*>(os + row * C + h * kAD);
+      uint4* ol = reinterpret_cast<uint4*>(os + (o_bs + row) * C + h * kAD);
 #pragma unroll
-    for (int j = 0; j < kAD; ++j) ob[(int64_t)j * T + tq] = acc[j] * inv;
-    if (lse) lse[((int64_t)b * gridDim.y + h) * T + tq] = m_run + logf(l_run);
+      for (int g = 0; g < kAD / 8; ++g) {
+        uint32_t hh[4], ll[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float v0 = acc[g * 8 + 2 * e] * inv, v1 = acc[g * 8 + 2 * e + 1] * inv;
+          hh[e] = pack_bf16(v0, v1);
+          ll[e] = pack_bf16(v0 - __uint_as_float(hh[e] << 16), v1 - __uint_as_float(hh[e] & 0xffff0000u));
+        }
+        oh[g] = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+        ol[g] = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+      }
+    } else {
+      float* __restrict__ ob = o + hoff;
+#pragma unroll
+      for (int j = 0; j < kAD; ++j) ob[(int64_t)j * T + tq] = acc[j] * inv;
+      if (lse) lse[((int64_t)b * gridDim.y + h) * T + tq] = m_run + logf(l_run);
+    }
   }
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_s, 128);
@@ -196,11 +251,31 @@ attention_umma_kernel(const float* __restrict__ q, const float* __restrict__ k, 
 int attention_umma_launch(const float* q, const float* k, const float* v, int64_t qkv_bs, float* o, int64_t o_bs,
                           int B, int H, int T, float scale, float* lse, cudaStream_t st) {
   const size_t smem = (size_t)(2 * 8 * kAQ + 2 * 2 * 8 * kAK + 2 * (kAK / 8) * kAQ) * 16 + 64;
-  cudaFuncSetAttribute(attention_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaFuncSetAttribute(attention_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   dim3 grid(cdiv(T, kAQ), H, B);
-  attention_umma_kernel<<<grid, kAThreads, smem, st>>>(q, k, v, qkv_bs, o, o_bs, T, scale, lse);
+  attention_umma_kernel<false><<<grid, kAThreads, smem, st>>>(q, k, v, qkv_bs, o, o_bs, T, scale, lse);
   STY_CHECK_LAUNCH("attention_umma");
   return STY_OK;
 }
+
+}  // namespace sty
+
+// token-major 64-wide attention of the diffusion denoiser (no mask): qkv rows [B*T, ld] fp32 with q | k | v at
+// column offsets 0 / H*64 / 2*H*64; output bf16 hi | lo planes [2][M_pad][H*64]
+extern "C" int sty_attention_tokens_fwd(const float* qkv, int64_t ld, void* out_split, int64_t M_pad, int B, int H,
+                                        int T, float scale, sty_stream_t stream) {
+  using namespace sty;
+  STY_REQUIRE(qkv && out_split && B > 0 && H > 0 && T > 0 && ld >= 3 * H * kAD && (ld & 3) == 0 &&
+                  M_pad >= (int64_t)B * T, "attention_tokens: bad argument");
+  const size_t smem = (size_t)(2 * 8 * kAQ + 2 * 2 * 8 * kAK + 2 * (kAK / 8) * kAQ) * 16 + 64;
+  cudaFuncSetAttribute(attention_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  dim3 grid(cdiv(T, kAQ), H, B);
+  attention_umma_kernel<true><<<grid, kAThreads, smem, as_stream(stream)>>>(
+      qkv, qkv + H * kAD, qkv + 2 * H * kAD, ld, reinterpret_cast<float*>(out_split), M_pad, T, scale, nullptr);
+  STY_CHECK_LAUNCH("attention_tokens");
+  return STY_OK;
+}
+
+namespace sty {
 
 }  // namespace sty
