@@ -174,7 +174,7 @@ STY_API int sty_tprls_bwd(const float* a, const float* b, int64_t n, const float
  * Token-major (rows = tokens) dense layers on TMA-fed tcgen05 GEMMs with bf16 hi|lo operand planes:
  * sty_split_planes_fwd : fp32 (n) -> bf16 planes out[0..n) = hi, out[n..2n) = lo   (weights, inputs)
  * sty_gemm_split_fwd   : C[M,N] = act(A W^T + bias) (+ res); A = planes [2][M][K], W = planes [2][N][K];
- *                        out fp32 (M,N) and / or out_split planes [2][M][N]; M, N % 128 == 0, K % 64 == 0
+ *                        out fp32 (M,N) and / or out_split planes [2][M][N]; M % 128, N % 256, K % 64 == 0
  * sty_build_tokens_fwd : tok[b*T+t] = [scale * x[b] (Cx) | emb[b,t] (Ce)], rows >= B*T zero
  * sty_row_ln_split_fwd : hm = h + add[b] (written when hm != NULL); planes of LayerNorm_C(hm)*gamma+beta; C = 1024
  * sty_token_mean_fwd   : out[b] = mean_t x[b*T+t]

@@ -4,12 +4,14 @@
 // Precision: "bf16x3" like the convolutions — every fp32 operand is kept in memory as TWO bf16 planes (hi, lo) and
 // three MMAs (hi*hi + lo*hi + hi*lo) accumulate in fp32 in TMEM.  Because the planes are produced by the epilogue
 // of the PREVIOUS kernel (GEMM, LayerNorm, attention), the operand tiles go global -> shared by cp.async.bulk.tensor
-// straight into the UMMA K-major / no-swizzle layout ([K/8][row][8 bf16]: the tensor map views a row-major
-// [rows, K] plane as (8, rows, K/8)), and the MMA warp consumes them with no thread ever touching the data.
+// straight into the UMMA K-major SWIZZLE_128B layout, and the MMA warp consumes them with no thread ever touching
+// the data.
 //
-// CTA: 128 x 128 output tile, K blocks of 64, 3-stage ring (64 KB per stage: A hi, A lo, W hi, W lo), persistent.
+// CTA: 128 x 256 output tile (N = 256 makes the MMA tensor-bound: 128 cycles vs 96 of shared-memory operand reads),
+// K blocks of 64 (= one 128-byte swizzle atom per row), 2-stage ring of 96 KB (A hi, A lo: 128 rows; W hi, W lo: 256
+// rows), tiles in the canonical SWIZZLE_128B K-major layout written by TMA with full 128-byte rows, persistent.
 // warp 0: TMA loader | warp 1: MMA issuer (elect.sync, 12 MMAs per K block) | warps 2-5: epilogue (TMEM -> bias /
-// GELU / residual -> fp32 rows and / or bf16 hi|lo planes), 2 accumulator stages of 128 TMEM columns.
+// GELU / residual -> fp32 rows and / or bf16 hi|lo planes), 2 accumulator stages of 256 TMEM columns.
 #include <string.h>
 
 #include "tma.cuh"
@@ -17,10 +19,19 @@
 namespace sty {
 namespace {
 
-constexpr int kBM = 128, kBN = 128, kBK = 64;
-constexpr int kStages = 3;
-constexpr int kPlaneU4 = kBM * (kBK / 8);  // uint4 per operand plane tile: [8 k8][128 rows]
-constexpr int kStageBytes = 4 * kPlaneU4 * 16;
+constexpr int kBM = 128, kBN = 256, kBK = 64;
+constexpr int kStages = 2;
+constexpr int kAU4 = kBM * (kBK / 8);  // uint4 per A plane tile: 128 rows x 128 bytes
+constexpr int kWU4 = kBN * (kBK / 8);  // uint4 per W plane tile: 256 rows x 128 bytes
+constexpr int kStageU4 = 2 * kAU4 + 2 * kWU4;
+constexpr int kStageBytes = kStageU4 * 16;
+constexpr int kAccCols = kBN;
+
+// shared-memory matrix descriptor, K-major, SWIZZLE_128B: 8-row groups 1024 bytes apart, sm_100 version bit
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
+         (2ull << 61);
+}
 constexpr int kGemmThreads = 6 * 32;
 
 struct GemmArgs {
@@ -37,14 +48,14 @@ gemm_bf16x3_kernel(const GemmArgs p, const __grid_constant__ CUtensorMap tmA, co
   extern __shared__ __align__(1024) uint8_t smem[];
   uint4* stage0 = reinterpret_cast<uint4*>(smem);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
-  uint64_t* full = bars;                 // [3]
-  uint64_t* empty = bars + kStages;      // [3]
+  uint64_t* full = bars;                 // [kStages]
+  uint64_t* empty = bars + kStages;      // [kStages]
   uint64_t* acc_full = bars + 2 * kStages;   // [2]
   uint64_t* acc_empty = acc_full + 2;        // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-  if (warp == 1) tmem_alloc(tmem_slot, 256);
+  if (warp == 1) tmem_alloc(tmem_slot, 2 * kAccCols);
   if (tid == 0) {
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&full[i], 1);
@@ -75,12 +86,12 @@ gemm_bf16x3_kernel(const GemmArgs p, const __grid_constant__ CUtensorMap tmA, co
           const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
           mbar_wait_sleep(&empty[s], ph ^ 1u);
           mbar_arrive_expect_tx(&full[s], kStageBytes);
-          uint4* st = stage0 + (size_t)s * 4 * kPlaneU4;
+          uint4* st = stage0 + (size_t)s * kStageU4;
           // planes are stacked along the row axis of the tensor map: rows [0, M) = hi, [M, 2M) = lo
-          tma_load_3d(st, &tmA, &full[s], 0, m0, kb * (kBK / 8));
-          tma_load_3d(st + kPlaneU4, &tmA, &full[s], 0, p.M + m0, kb * (kBK / 8));
-          tma_load_3d(st + 2 * kPlaneU4, &tmW, &full[s], 0, n0, kb * (kBK / 8));
-          tma_load_3d(st + 3 * kPlaneU4, &tmW, &full[s], 0, p.N + n0, kb * (kBK / 8));
+          tma_load_2d(st, &tmA, &full[s], kb * kBK, m0);
+          tma_load_2d(st + kAU4, &tmA, &full[s], kb * kBK, p.M + m0);
+          tma_load_2d(st + 2 * kAU4, &tmW, &full[s], kb * kBK, n0);
+          tma_load_2d(st + 2 * kAU4 + kWU4, &tmW, &full[s], kb * kBK, p.N + n0);
         }
       }
     }
@@ -92,23 +103,23 @@ gemm_bf16x3_kernel(const GemmArgs p, const __grid_constant__ CUtensorMap tmA, co
       const uint32_t a = j & 1u;
       mbar_wait(&acc_empty[a], ((j >> 1) & 1u) ^ 1u);
       tc_fence_after();
-      const uint32_t d = tmem_base + a * 128u;
+      const uint32_t d = tmem_base + a * (uint32_t)kAccCols;
       for (int kb = 0; kb < kblocks; ++kb, ++it) {
         const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
         mbar_wait(&full[s], ph);
         tc_fence_after();
         if (elect_one()) {
-          const uint4* st = stage0 + (size_t)s * 4 * kPlaneU4;
-          const uint64_t ad = make_desc(smem_u32(st), (uint32_t)kBM, 8u);
-          const uint64_t wd = make_desc(smem_u32(st + 2 * kPlaneU4), (uint32_t)kBN, 8u);
+          const uint4* st = stage0 + (size_t)s * kStageU4;
+          const uint64_t ad = make_desc_sw128(smem_u32(st));
+          const uint64_t wd = make_desc_sw128(smem_u32(st + 2 * kAU4));
           const uint32_t ah = (uint32_t)(ad >> 32), wh = (uint32_t)(wd >> 32);
           const uint32_t al = (uint32_t)ad, wl = (uint32_t)wd;
 #pragma unroll
-          for (uint32_t ks = 0; ks < kBK / 16; ++ks) {
-            const uint32_t ak = al + ks * 2u * kBM, wk = wl + ks * 2u * kBN;
+          for (uint32_t ks = 0; ks < kBK / 16; ++ks) {  // a 16-element K step = 32 bytes inside the swizzle atom
+            const uint32_t ak = al + ks * 2u, wk = wl + ks * 2u;
             umma_bf16_w(d, ak, ah, wk, wh, idesc, (kb | (int)ks) ? 1u : 0u);   // A hi * W hi
-            umma_bf16_w(d, ak + kPlaneU4, ah, wk, wh, idesc, 1u);               // A lo * W hi
-            umma_bf16_w(d, ak, ah, wk + kPlaneU4, wh, idesc, 1u);               // A hi * W lo
+            umma_bf16_w(d, ak + kAU4, ah, wk, wh, idesc, 1u);                   // A lo * W hi
+            umma_bf16_w(d, ak, ah, wk + kWU4, wh, idesc, 1u);                   // A hi * W lo
           }
           umma_commit(&empty[s]);
           if (kb == kblocks - 1) umma_commit(&acc_full[a]);
@@ -127,10 +138,10 @@ gemm_bf16x3_kernel(const GemmArgs p, const __grid_constant__ CUtensorMap tmA, co
       mbar_wait_sleep(&acc_full[a], (j >> 1) & 1u);
       tc_fence_after();
 #pragma unroll 1
-      for (int ch = 0; ch < 4; ++ch) {
+      for (int ch = 0; ch < kBN / 32; ++ch) {
         float r[32];
-        tmem_ld32(tmem_base + a * 128u + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 32), r);
-        if (ch == 3) {
+        tmem_ld32(tmem_base + a * (uint32_t)kAccCols + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 32), r);
+        if (ch == kBN / 32 - 1) {
           tc_fence_before();
           mbar_arrive(&acc_empty[a]);
         }
@@ -180,7 +191,7 @@ gemm_bf16x3_kernel(const GemmArgs p, const __grid_constant__ CUtensorMap tmA, co
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 256);
+  if (warp == 1) tmem_dealloc(tmem_base, 2 * kAccCols);
 }
 
 // ---- small token-rate helpers --------------------------------------------------------------------------------
@@ -273,8 +284,8 @@ __global__ void token_mean_kernel(const float* __restrict__ x, float* __restrict
   out[(int64_t)b * C + c] = s / (float)T;
 }
 
-bool make_tmap_planes(CUtensorMap* out, const void* base, int64_t rows, int64_t K) {
-  // row-major bf16 [rows, K] seen as (8, rows, K/8): box (8, 128, 8) lands in shared memory as [k8][row][8]
+bool make_tmap_planes(CUtensorMap* out, const void* base, int64_t rows, int64_t K, int box_rows) {
+  // row-major bf16 [rows, K]: box (64 K-elements = 128 bytes, box_rows), SWIZZLE_128B
   typedef CUresult (*Fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                          const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                          CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -287,12 +298,12 @@ bool make_tmap_planes(CUtensorMap* out, const void* base, int64_t rows, int64_t 
       return false;
     fn = reinterpret_cast<Fn>(ptr);
   }
-  cuuint64_t dims[3] = {8, (cuuint64_t)rows, (cuuint64_t)(K / 8)};
-  cuuint64_t strides[2] = {(cuuint64_t)K * 2, 16};
-  cuuint32_t box[3] = {8, 128, 8};
-  cuuint32_t es[3] = {1, 1, 1};
-  return fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, es,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+  cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)box_rows};
+  cuuint32_t es[2] = {1, 1};
+  return fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
@@ -314,10 +325,11 @@ extern "C" int sty_gemm_split_fwd(const void* a_split, const void* w_split, cons
                                   float* out, void* out_split, int M, int N, int K, int act, sty_stream_t stream) {
   STY_REQUIRE(a_split && w_split && (out || out_split), "gemm_split: null pointer");
   STY_REQUIRE(M > 0 && M % kBM == 0 && N > 0 && N % kBN == 0 && K > 0 && K % kBK == 0,
-              "gemm_split: M, N multiples of 128 and K a multiple of 64 required (got %d %d %d)", M, N, K);
+              "gemm_split: M %% 128, N %% 256, K %% 64 == 0 required (got %d %d %d)", M, N, K);
   STY_REQUIRE(act == STY_ACT_NONE || act == STY_ACT_GELU, "gemm_split: activation not supported");
   CUtensorMap tmA, tmW;
-  STY_REQUIRE(make_tmap_planes(&tmA, a_split, 2 * (int64_t)M, K) && make_tmap_planes(&tmW, w_split, 2 * (int64_t)N, K),
+  STY_REQUIRE(make_tmap_planes(&tmA, a_split, 2 * (int64_t)M, K, kBM) &&
+                  make_tmap_planes(&tmW, w_split, 2 * (int64_t)N, K, kBN),
               "gemm_split: tensor map encoding failed");
   GemmArgs g;
   g.bias = bias; g.res = res; g.out = out; g.out_split = reinterpret_cast<__nv_bfloat16*>(out_split);

@@ -23,7 +23,7 @@ def planes(x):
     return DF._planes(x)
 
 
-@pytest.mark.parametrize("M,N,K,act,res", [(128, 128, 64, 0, False), (256, 384, 192, 5, False), (384, 128, 1024, 0, True),
+@pytest.mark.parametrize("M,N,K,act,res", [(128, 256, 64, 0, False), (256, 768, 192, 5, False), (384, 256, 1024, 0, True),
                                            (16512, 1536, 1024, 0, False)])
 def test_gemm_split_vs_fp64(M, N, K, act, res):
     g = torch.Generator().manual_seed(M + N + K)
