@@ -228,6 +228,19 @@ def config0_text_to_wav(dev, cpu=True):
     return out
 
 
+def diffusion_sampler_bench(dev, iters=3):
+    """BASELINE configs[3] (kernel isolation): 10-step diffusion style sampler, batch 64 styles, 258-token context.
+    Restatement, parity unpinned (the reference has no implementation: SURVEY F2); CUDA-graph replay, CUDA events."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_diffusion", os.path.join(ROOT, "tools", "bench_diffusion.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    r = mod.measure(B=64, T=258, steps=10, iters=iters, graph=True, dev=dev)
+    r["tensor_pipe_note"] = ("sm__pipe_tensor_cycles_active of the GEMM launches: 72-74 % (q|kv, FF1, FF2), 28 % "
+                             "(out-proj, K=512 with residual + two outputs): profiles/r02_ncu_full_gemm_split.txt")
+    return r
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU implementation (oracle port) on host threads."""
     rank = int(os.environ.get("RANK", "0"))
@@ -657,6 +670,13 @@ def run_ours(args):
         except Exception as e:
             log(f"[bench] configs[0] failed: {type(e).__name__}: {e}")
         torch.cuda.empty_cache()
+    diffusion = None
+    if rank == 0 and world == 1:
+        try:
+            diffusion = diffusion_sampler_bench(dev)
+        except Exception as e:
+            log(f"[bench] configs[3] failed: {type(e).__name__}: {e}")
+        torch.cuda.empty_cache()
 
     train = None
     had_graph = graph is not None
@@ -688,6 +708,9 @@ def run_ours(args):
                              config0_cpu_audio_s_per_s=round(config0.get("cpu_audio_s_per_s", 0.0), 2))
         if cpu is not None and "eager_gpu" in cpu:
             extra_cfg["eager_gpu_audio_s_per_s"] = round(cpu["eager_gpu"]["value"], 1)
+        if diffusion is not None:
+            extra_cfg.update(config3_diffusion_ms_per_64_styles=round(diffusion["ms_per_sample_batch"], 2),
+                             config3_diffusion_mma_tflops=round(diffusion["mma_tflops_bf16x3"], 1))
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -709,6 +732,7 @@ def run_ours(args):
             "top_kernels": top,
             "train": train,
             "config0": config0,
+            "diffusion": diffusion,
         }), flush=True)
     if world > 1:
         dist.destroy_process_group()
