@@ -378,8 +378,12 @@ def measure_train(args, dev, world, rank, barrier, steps, warmup, batch):
         mrd = [nets[f"mrd{i}"].to(dev).train() for i in range(3)]
         disc_opts = {f"mrd{i}": optim.FlatAdamW(mrd[i].parameters(), lr=1e-4, betas=(0.85, 0.99), eps=1e-9,
                                                 weight_decay=1e-4, world_size=world) for i in range(3)}
-        adversarial = (D.GeneratorLoss(mrd0=mrd[0], mrd1=mrd[1], mrd2=mrd[2]),
-                       D.DiscriminatorLoss(mrd0=mrd[0], mrd1=mrd[1], mrd2=mrd[2], device=dev), disc_opts)
+        if getattr(args, "adversarial_two_pass", False):  # the reference's literal schedule: 2 evaluations per batch
+            adversarial = (D.GeneratorLoss(mrd0=mrd[0], mrd1=mrd[1], mrd2=mrd[2]),
+                           D.DiscriminatorLoss(mrd0=mrd[0], mrd1=mrd[1], mrd2=mrd[2], device=dev), disc_opts)
+        else:  # one evaluation of mrd0-2 per batch feeds both halves (same numbers: tests/test_gpu_discriminators.py)
+            adv = D.AdversarialTerms(mrd0=mrd[0], mrd1=mrd[1], mrd2=mrd[2], device=dev)
+            adversarial = (adv, adv, disc_opts)
     host = synth.speech_inputs(batch, args.tokens, seed=11 + rank)
     dur = torch.full((batch, args.tokens), 3.0)
     dur[:, ::9] += 1.0  # the durations synth.speech_inputs builds its alignment from
@@ -813,6 +817,8 @@ def main():
                          "train: configs[2]/[4] as the line itself")
     ap.add_argument("--train-batch", type=int, default=32)
     ap.add_argument("--no-train", action="store_true", help="skip the train sub-measurement of --mode fwd")
+    ap.add_argument("--adversarial-two-pass", action="store_true",
+                    help="with --adversarial: evaluate the discriminators twice per batch like the reference's schedule")
     ap.add_argument("--adversarial", action="store_true",
                     help="train measurement with the adversarial terms (spectrogram discriminators mrd0-2)")
     args = ap.parse_args()

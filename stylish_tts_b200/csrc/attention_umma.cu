@@ -236,7 +236,7 @@ attention_umma_kernel(const float* __restrict__ q, const float* __restrict__ k, 
         ol[g] = make_uint4(ll[0], ll[1], ll[2], ll[3]);
       }
     } else {
-      float* __restrict__ ob = o + hoff;
+      float* __restrict__ ob = o + (int64_t)b * o_bs + (int64_t)h * kAD * T;  // o_bs may differ from qkv_bs
 #pragma unroll
       for (int j = 0; j < kAD; ++j) ob[(int64_t)j * T + tq] = acc[j] * inv;
       if (lse) lse[((int64_t)b * gridDim.y + h) * T + tq] = m_run + logf(l_run);

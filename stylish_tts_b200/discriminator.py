@@ -72,11 +72,37 @@ def stride2_weight(w4: torch.Tensor) -> torch.Tensor:
     return wp.reshape(Co, Ci, R, 5, 2).permute(0, 1, 4, 2, 3).reshape(Co, Ci * 2, R, 5)
 
 
+class BackwardMode:
+    """Which gradients a backward pass through a discriminator is run for.  The reference evaluates every
+    discriminator twice per batch on the same inputs with the same weights — once inside ``GeneratorLoss`` (weight
+    gradients computed and thrown away by ``zero_grad``, stage.py:127) and once inside ``DiscriminatorLoss``
+    (detached inputs).  ``AdversarialTerms`` keeps ONE forward and walks its tape twice; this switch tells the conv
+    backward which half of its work the current walk needs."""
+
+    def __init__(self):
+        self.weights = True       # weight / bias gradients
+        self.first_input = True   # gradient w.r.t. the spectrogram itself (first layer's data gradient)
+
+    def set(self, *, weights=True, first_input=True):
+        mode = self
+
+        class _Ctx:
+            def __enter__(self):
+                self.saved = (mode.weights, mode.first_input)
+                mode.weights, mode.first_input = weights, first_input
+
+            def __exit__(self, *exc):
+                mode.weights, mode.first_input = self.saved
+
+        return _Ctx()
+
+
 class SpecDiscriminator(nn.Module):
     """Drop-in for reference SpecDiscriminator (discriminator.py:13-69)."""
 
     def __init__(self):
         super().__init__()
+        self.backward_mode = BackwardMode()
         c2 = lambda ci, co, k, stride, pad: weight_norm(nn.Conv2d(ci, co, kernel_size=k, stride=stride, padding=pad))
         self.discriminators = nn.ModuleList([
             c2(1, 32, (3, 9), 1, (1, 4)), c2(32, 32, (3, 9), (1, 2), (1, 4)), c2(32, 32, (3, 9), (1, 2), (1, 4)),
@@ -104,10 +130,11 @@ class SpecDiscriminator(nn.Module):
         Hp = K + 2
         img = torch.zeros((B, Hp, 1, N), device=y.device, dtype=torch.float32)
         img[:, 1:K + 1, 0, :] = y[:, 0].to(torch.float32)
-        conv = lambda t, w4, b: RowConvFn.apply(t, w4, b, None,
-                                                dict(row_mask=self._row_mask(t.shape[0], t.shape[1], t.shape[3], t.device)))
+        conv = lambda t, w4, b, first=False: RowConvFn.apply(
+            t, w4, b, None, dict(row_mask=self._row_mask(t.shape[0], t.shape[1], t.shape[3], t.device),
+                                 mode=self.backward_mode, first=first))
         result: List[torch.Tensor] = []
-        h = conv(img, self._w(self.discriminators[0]), self.discriminators[0].bias)
+        h = conv(img, self._w(self.discriminators[0]), self.discriminators[0].bias, True)
         for i in range(5):
             a = leaky_image(h)                                   # LeakyReLU(0.1), discriminator.py:59
             # score conv 32 -> 1: zero-padded to 16 output channels so that forward, data gradient and weight
@@ -283,3 +310,107 @@ class DiscriminatorLoss(nn.Module):
         if self.disc is not None:
             loss = loss + DISC_WEIGHT * self._one("disc", self.disc, target_audio, pred_audio)
         return loss
+
+
+class AdversarialTerms(nn.Module):
+    """Both adversarial halves of an acoustic batch from ONE evaluation of the discriminators.
+
+    Stage.train_batch (stage.py:104-146) runs ``GeneratorLoss`` (inside the generator's backward) and then
+    ``DiscriminatorLoss`` on the detached spectrograms; between the two only the generator's parameters change, so
+    both see the same discriminator outputs for the same (target, prediction) pair.  Here the discriminators run
+    once per batch with their tape kept:
+
+    * ``generator_loss(...)`` (same keywords as ``GeneratorLoss.forward``) returns the generator term; its backward
+      walks the tape for the gradient w.r.t. the predicted spectrograms only (no weight gradients — the reference
+      computes and discards them);
+    * ``discriminator_backward(index, scale)`` evaluates ``DiscriminatorLoss`` from the stored scores (value of all
+      three + moving averages, losses.py:196-207,280-288) and back-propagates ``scale x`` the term of the ONE
+      discriminator that is stepped (``mrd{index}``, stage.py:141-143; the others' gradients are zeroed unused in
+      the reference), without the data gradient of the first layer.
+
+    5.3 discriminator-forward equivalents per batch instead of 9 + 2 discarded weight-gradient passes; the numbers
+    are identical to the two-evaluation classes above (tests/test_gpu_discriminators.py)."""
+
+    def __init__(self, *, mrd0, mrd1, mrd2, disc: Optional[nn.Module] = None, device="cuda"):
+        super().__init__()
+        self.mrd = nn.ModuleList([mrd0, mrd1, mrd2])
+        self.disc = disc
+        self.lr_control = {f"mrd{i}": DiscriminatorLR(5, device) for i in range(3)}
+        self.lr_control["disc"] = DiscriminatorLR(1, device)
+        self._state = None
+
+    def _models(self):
+        return list(self.mrd) + ([self.disc] if self.disc is not None else [])
+
+    def _modes(self, **kw):
+        import contextlib
+        stack = contextlib.ExitStack()
+        for m in self._models():
+            mode = getattr(m, "backward_mode", None)
+            if mode is not None:
+                stack.enter_context(mode.set(**kw))
+        return stack
+
+    class _GeneratorTermFn(Function):
+        @staticmethod
+        def forward(ctx, owner, targets, *preds):
+            models = owner._models()
+            with torch.enable_grad():
+                leafs = [p.detach().requires_grad_(True) for p in preds]
+                real, gen, total = [], [], 0.0
+                for k, (m, t, p) in enumerate(zip(models, targets, leafs)):
+                    r, _ = m(t.detach())
+                    g, _ = m(p)
+                    term = lsgan_generator(g) + tprls_generator([x.detach() for x in r], g)
+                    total = total + (term if k < 3 else DISC_WEIGHT * term)
+                    real.append(r)
+                    gen.append(g)
+            owner._state = SimpleState(leafs=leafs, real=real, gen=gen, gen_loss=total)
+            ctx.owner = owner
+            return total.detach().clone()
+
+        @staticmethod
+        def backward(ctx, g):
+            st = ctx.owner._state
+            if st is None:
+                raise RuntimeError("AdversarialTerms: generator backward after discriminator_backward released the tape")
+            with ctx.owner._modes(weights=False):
+                grads = torch.autograd.grad(st.gen_loss, st.leafs, retain_graph=True)
+            return (None, None) + tuple(x * g for x in grads)
+
+    def generator_loss(self, *, target_list, pred_list, target_audio=None, pred_audio=None):
+        targets, preds = list(target_list), list(pred_list)
+        if self.disc is not None:
+            targets.append(target_audio)
+            preds.append(pred_audio)
+        return self._GeneratorTermFn.apply(self, targets, *preds)
+
+    forward = generator_loss
+
+    def discriminator_backward(self, index: int, scale: float = 1.0) -> torch.Tensor:
+        st = self._state
+        if st is None:
+            raise RuntimeError("AdversarialTerms: discriminator_backward needs the generator_loss of the same batch")
+        keys = [f"mrd{i}" for i in range(3)] + (["disc"] if self.disc is not None else [])
+        models = self._models()
+        stepped = {index} | ({3} if self.disc is not None else set())
+        total, back = 0.0, 0.0
+        for k, key in enumerate(keys):
+            with torch.set_grad_enabled(k in stepped):
+                d = lsgan_discriminator(st.real[k], st.gen[k])
+                self.lr_control[key].update(d)
+                term = d + tprls_discriminator(st.real[k], st.gen[k])
+                term = term if k < 3 else DISC_WEIGHT * term
+            total = total + term.detach()
+            if k in stepped:
+                back = back + term
+        params = [p for k in sorted(stepped) for p in models[k].parameters()]
+        with self._modes(first_input=False):
+            torch.autograd.backward(back * scale, inputs=params)
+        self._state = None
+        return total
+
+
+class SimpleState:
+    def __init__(self, **kw):
+        self.__dict__.update(kw)

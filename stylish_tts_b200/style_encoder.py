@@ -79,7 +79,13 @@ class RowConvFn(Function):
         gv = dy.as_strided((N, Co, W), (Co * W, W, 1), ctx.off * Co * W)
         xv = x.as_strided((N, R * Cc, W), (Cc * W, W, 1))
         w3 = w4.detach().permute(0, 2, 1, 3).reshape(Co, R * Cc, K)
-        need = ctx.needs_input_grad
+        need = list(ctx.needs_input_grad)
+        mode = cfg.get("mode")  # discriminator.BackwardMode: which gradients THIS backward pass is run for
+        if mode is not None:
+            if not mode.weights:
+                need[1] = need[2] = False
+            if cfg.get("first") and not mode.first_input:
+                need[0] = False
         d_res = (dy * res_scale if res_scale != 1.0 else dy) if (ctx.has_res and need[3]) else None
         d_bias = T.channel_sum(gv, mask, out_scale) if (ctx.has_bias and need[2]) else None
         d_w4 = None

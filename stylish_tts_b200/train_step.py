@@ -89,10 +89,16 @@ def discriminator_step(out, batch, discriminator_loss, optimizers, *, disc_index
     (optimizers.py:54-65), all on the device."""
     import math
 
-    d_loss = discriminator_loss(target_list=[t.detach() for t in out.target_fft],
-                                pred_list=[p.detach() for p in out.pred_fft], target_audio=batch.audio_gt,
-                                pred_audio=out.pred.audio.detach().squeeze(1))
-    (d_loss * math.sqrt(batch.text.shape[0])).backward()
+    scale = math.sqrt(batch.text.shape[0])
+    if hasattr(discriminator_loss, "discriminator_backward"):
+        # discriminator.AdversarialTerms: the scores of this batch are already on its tape (one evaluation serves
+        # the generator term and this loss); only the stepped discriminator is back-propagated
+        d_loss = discriminator_loss.discriminator_backward(disc_index, scale)
+    else:
+        d_loss = discriminator_loss(target_list=[t.detach() for t in out.target_fft],
+                                    pred_list=[p.detach() for p in out.pred_fft], target_audio=batch.audio_gt,
+                                    pred_audio=out.pred.audio.detach().squeeze(1))
+        (d_loss * scale).backward()
     keys = [f"mrd{disc_index}"] + (["disc"] if "disc" in optimizers else [])
     for k in keys:
         if lr_source is not None:

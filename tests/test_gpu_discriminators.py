@@ -234,3 +234,52 @@ def test_acoustic_step_with_adversarial_terms_and_discriminator_step():
     mult = float(dl.lr_control["mrd1"].multiplier())
     assert float(disc_opts["mrd1"].hyper[0]) == pytest.approx(1e-4 * mult, rel=1e-5)
     assert all(p.grad is None for i in range(3) for p in nets[f"mrd{i}"].parameters())
+
+
+def test_shared_evaluation_matches_the_two_evaluation_losses():
+    """AdversarialTerms (one discriminator evaluation per batch) against GeneratorLoss + DiscriminatorLoss (the
+    reference's two evaluations, pinned to the oracle above): generator term and its gradient w.r.t. the predicted
+    spectrograms, discriminator loss value, moving averages, and the stepped discriminator's parameter gradients
+    (x sqrt(B)); the discriminators that are not stepped get no gradient at all."""
+    import math
+
+    tf, pf, _, _ = inputs()
+    mods = [_seeded_disc(10 + i).to(dev()) for i in range(3)]
+    tfd = [t.to(dev()) for t in tf]
+    scale = math.sqrt(tf[0].shape[0])
+    # reference schedule
+    pa = [p.to(dev()).requires_grad_(True) for p in pf]
+    gl = D.GeneratorLoss(mrd0=mods[0], mrd1=mods[1], mrd2=mods[2])
+    la = gl(target_list=tfd, pred_list=pa)
+    (2.5 * la).backward()
+    dl = D.DiscriminatorLoss(mrd0=mods[0], mrd1=mods[1], mrd2=mods[2], device=dev())
+    da = dl(target_list=tfd, pred_list=[p.detach() for p in pa])
+    (da * scale).backward()
+    grads_a = [{k: p.grad.clone() for k, p in m.named_parameters()} for m in mods]
+    for m in mods:
+        m.zero_grad(set_to_none=True)
+    # shared evaluation
+    for index in (0, 2):
+        pb = [p.to(dev()).requires_grad_(True) for p in pf]
+        adv = D.AdversarialTerms(mrd0=mods[0], mrd1=mods[1], mrd2=mods[2], device=dev())
+        lb = adv(target_list=tfd, pred_list=pb)
+        assert float(lb) == pytest.approx(float(la), rel=1e-6)
+        (2.5 * lb).backward()
+        assert all(p.grad is None for m in mods for p in m.parameters())  # constants of the generator step
+        for i in range(3):
+            assert rel_l2(pb[i].grad, pa[i].grad) < 1e-6, (i, rel_l2(pb[i].grad, pa[i].grad))
+        db = adv.discriminator_backward(index, scale)
+        assert float(db) == pytest.approx(float(da), rel=1e-6)
+        for i in range(3):
+            assert float(adv.lr_control[f"mrd{i}"].last_loss) == pytest.approx(float(dl.lr_control[f"mrd{i}"].last_loss),
+                                                                               rel=1e-6)
+            for k, p in mods[i].named_parameters():
+                if i == index:
+                    assert rel_l2(p.grad, grads_a[i][k]) < 1e-5, (i, k, rel_l2(p.grad, grads_a[i][k]))
+                else:
+                    assert p.grad is None, (i, k)
+        assert all(p.grad.abs().max() == pa[i].grad.abs().max() for i, p in enumerate(pb))  # untouched by the 2nd walk
+        with pytest.raises(RuntimeError):
+            adv.discriminator_backward(index, scale)  # the tape is released after the discriminator half
+        for m in mods:
+            m.zero_grad(set_to_none=True)

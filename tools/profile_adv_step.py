@@ -33,5 +33,5 @@ for sig, a, b, info in L.profile_log:
 L.profile_log = None
 tot = sum(v[0] for v in agg.values())
 print(f"sum of C-ABI kernel time {tot:.1f} ms")
-for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])[:25]:
+for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])[:int(os.environ.get("TOPN", "25"))]:
     print(f"  {v[0]:8.2f} ms  n={v[1]:3d}  {k}")
