@@ -170,6 +170,29 @@ STY_API int sty_tprls_fwd(const float* a, const float* b, int64_t n, void* works
 STY_API int sty_tprls_bwd(const float* a, const float* b, int64_t n, const float* median, const float* coef, float* da,
                           float* db, int* flag, sty_stream_t stream);
 
+/* ---- spectrogram discriminator, non-tensor-core layers (discriminator.py:13-69) ---------------------------------
+ * Row-channel images (B, Hp = bins + 2, C, W) with zero border rows, 32 hidden channels, LeakyReLU slope 0.1.
+ * sty_disc_first_fwd  : h = Conv2d(1 -> 32, 3x9, pad (1,4))(y), y (B,bins,W) -> h (B,Hp,32,W) (border rows written 0);
+ *                       w (32,1,3,9), bias (32) in the reference layout.  _dgrad: dy (B,bins,W) from dh (zero borders);
+ *                       _wgrad: dw (32*27), db (32) (zeroed by the call, accumulated with atomics).
+ * sty_disc_tail_fwd   : a = LeakyReLU(h); score (B,bins,W) = Conv2d(32 -> 1, 3x3, pad 1)(a) + b_score;
+ *                       next_kind 0: nothing else | 1: next = a (B,Hp,32,W) | 2: next = space-to-depth of a along W,
+ *                       (B,Hp,64,ceil(W/2)), channel 2c+p = a[c, 2u+p] (input of the following stride-(1,2) layer).
+ * sty_disc_tail_bwd   : dh = LeakyReLU'(h) * (data gradient of the score conv from dscore (may be NULL) + d(next)),
+ *                       border rows written 0.
+ * sty_disc_score_wgrad: dw (32*9), db (1) of the score conv (zeroed by the call). */
+STY_API int sty_disc_first_fwd(const float* y, const float* w, const float* bias, float* h, int B, int bins, int W,
+                               sty_stream_t stream);
+STY_API int sty_disc_first_dgrad(const float* dh, const float* w, float* dy, int B, int bins, int W, sty_stream_t stream);
+STY_API int sty_disc_first_wgrad(const float* y, const float* dh, float* dw, float* db, int B, int bins, int W,
+                                 sty_stream_t stream);
+STY_API int sty_disc_tail_fwd(const float* h, const float* w_score, const float* b_score, float* score, float* next,
+                              int next_kind, int B, int Hp, int W, sty_stream_t stream);
+STY_API int sty_disc_tail_bwd(const float* h, const float* w_score, const float* dscore, const float* dnext, float* dh,
+                              int next_kind, int B, int Hp, int W, sty_stream_t stream);
+STY_API int sty_disc_score_wgrad(const float* h, const float* dscore, float* dw, float* db, int B, int Hp, int W,
+                                 sty_stream_t stream);
+
 /* ---- style-diffusion denoiser (BASELINE configs[3]; absent from the reference) ----
  * Token-major (rows = tokens) dense layers on TMA-fed tcgen05 GEMMs with bf16 hi|lo operand planes:
  * sty_split_planes_fwd : fp32 (n) -> bf16 planes out[0..n) = hi, out[n..2n) = lo   (weights, inputs)

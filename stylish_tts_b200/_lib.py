@@ -171,6 +171,12 @@ _SIGNATURES = {
     "sty_sqdiff_sum_fwd": [_f32p, _i64, _f32, _f32p, _f32p],
     "sty_tprls_fwd": [_f32p, _f32p, _i64, _f32p, _f32p, _f32p, _f32p],
     "sty_tprls_bwd": [_f32p, _f32p, _i64, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p],
+    "sty_disc_first_fwd": [_f32p, _f32p, _f32p, _f32p, _i32, _i32, _i32, _f32p],
+    "sty_disc_first_dgrad": [_f32p, _f32p, _f32p, _i32, _i32, _i32, _f32p],
+    "sty_disc_first_wgrad": [_f32p, _f32p, _f32p, _f32p, _i32, _i32, _i32, _f32p],
+    "sty_disc_tail_fwd": [_f32p, _f32p, _f32p, _f32p, _f32p, _i32, _i32, _i32, _i32, _f32p],
+    "sty_disc_tail_bwd": [_f32p, _f32p, _f32p, _f32p, _f32p, _i32, _i32, _i32, _i32, _f32p],
+    "sty_disc_score_wgrad": [_f32p, _f32p, _f32p, _f32p, _i32, _i32, _i32, _f32p],
 }
 _SPECIAL = {
     "sty_version": ([], C.c_int),

@@ -62,6 +62,92 @@ def leaky_image(img, s=1, slope=0.1):
     return y.view(B, Hp, Cc * s, y.shape[2])
 
 
+def _skip(mode, what):
+    return mode is not None and not getattr(mode, what)
+
+
+class FirstConvFn(Function):
+    """Conv2d(1 -> 32, 3x9, pad (1,4)) of the raw spectrogram: y (B,bins,W) -> row-channel h (B,bins+2,32,W).
+    864 FMAs per pixel against a 128-byte output write: fp32 FMA kernels (csrc/disc_ops.cu), output-bound."""
+
+    @staticmethod
+    def forward(ctx, y, w4, bias, mode):
+        y = y.contiguous()
+        B, bins, W = y.shape
+        w = w4.detach().contiguous()
+        h = torch.empty((B, bins + 2, 32, W), device=y.device, dtype=torch.float32)
+        L.call("sty_disc_first_fwd", y.data_ptr(), w.data_ptr(), bias.detach().contiguous().data_ptr(), h.data_ptr(),
+               B, bins, W, L.stream_ptr())
+        ctx.save_for_backward(y, w)
+        ctx.mode = mode
+        return h
+
+    @staticmethod
+    def backward(ctx, dh):
+        y, w = ctx.saved_tensors
+        B, bins, W = y.shape
+        dh = dh.contiguous()
+        dy = dw = db = None
+        if ctx.needs_input_grad[0] and not _skip(ctx.mode, "first_input"):
+            dy = torch.empty_like(y)
+            L.call("sty_disc_first_dgrad", dh.data_ptr(), w.data_ptr(), dy.data_ptr(), B, bins, W, L.stream_ptr())
+        if ctx.needs_input_grad[1] and not _skip(ctx.mode, "weights"):
+            dw = torch.empty((32, 1, 3, 9), device=y.device, dtype=torch.float32)
+            db = torch.empty((32,), device=y.device, dtype=torch.float32)
+            L.call("sty_disc_first_wgrad", y.data_ptr(), dh.data_ptr(), dw.data_ptr(), db.data_ptr(), B, bins, W,
+                   L.stream_ptr())
+        return dy, dw, db, None
+
+
+class TailFn(Function):
+    """What hangs off a pre-activation h (B,Hp,32,W) besides the next 32 -> 32 conv, in one pass:
+    a = LeakyReLU_0.1(h) (discriminator.py:59), score = Conv2d(32 -> 1, 3x3)(a) (:60-61), and the next layer's input
+    (kind 1: a itself; kind 2: its space-to-depth along W for a stride-(1,2) layer; kind 0: none).  The backward is one
+    pass too: dh = leaky'(h) * (score-conv data gradient + d(next))."""
+
+    @staticmethod
+    def forward(ctx, h, ws4, bs, kind, mode):
+        h = h.contiguous()
+        B, Hp, Cc, W = h.shape
+        assert Cc == 32
+        w = ws4.detach().contiguous()
+        score = torch.empty((B, Hp - 2, W), device=h.device, dtype=torch.float32)
+        nxt = None
+        if kind == 1:
+            nxt = torch.empty_like(h)
+        elif kind == 2:
+            nxt = torch.empty((B, Hp, 64, (W + 1) // 2), device=h.device, dtype=torch.float32)
+        L.call("sty_disc_tail_fwd", h.data_ptr(), w.data_ptr(), bs.detach().contiguous().data_ptr(), score.data_ptr(),
+               L.ptr(nxt), kind, B, Hp, W, L.stream_ptr())
+        ctx.save_for_backward(h, w)
+        ctx.kind, ctx.mode = kind, mode
+        if nxt is None:
+            nxt = score.new_zeros(())  # placeholder output
+            ctx.mark_non_differentiable(nxt)
+        return score, nxt
+
+    @staticmethod
+    def backward(ctx, dscore, dnext):
+        h, w = ctx.saved_tensors
+        B, Hp, _, W = h.shape
+        kind = ctx.kind
+        dscore = None if dscore is None else dscore.contiguous()
+        if kind != 0 and dnext is None:
+            dnext = torch.zeros((B, Hp, 32, W) if kind == 1 else (B, Hp, 64, (W + 1) // 2), device=h.device)
+        dh = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dh = torch.empty_like(h)
+            L.call("sty_disc_tail_bwd", h.data_ptr(), w.data_ptr(), L.ptr(dscore),
+                   L.ptr(dnext.contiguous() if kind != 0 else None), dh.data_ptr(), kind, B, Hp, W, L.stream_ptr())
+        if ctx.needs_input_grad[1] and not _skip(ctx.mode, "weights"):
+            dw = torch.zeros((1, 32, 3, 3), device=h.device, dtype=torch.float32)
+            db = torch.zeros((1,), device=h.device, dtype=torch.float32)
+            if dscore is not None:
+                L.call("sty_disc_score_wgrad", h.data_ptr(), dscore.data_ptr(), dw.data_ptr(), db.data_ptr(), B, Hp, W,
+                       L.stream_ptr())
+        return dh, dw, db, None, None
+
+
 def stride2_weight(w4: torch.Tensor) -> torch.Tensor:
     """(Co,Ci,3,9) stride-(1,2) pad-(1,4) kernel -> (Co,2Ci,3,5) stride-1 pad-(1,2) kernel on the space-to-depth
     input: y[w'] = sum_k w[k] x[2w'+k-4] = sum_{j,p} w[2j+p] xs[p][w'+j-2]; tap k = 9 does not exist (zero).
@@ -122,9 +208,33 @@ class SpecDiscriminator(nn.Module):
         p = conv.parametrizations.weight
         return torch._weight_norm(p.original1, p.original0, 0)
 
+    fused = True  # False: the first version (generic conv kernels for every layer); kept for A/B tests
+
     def forward(self, y):
         if not y.is_cuda:
             raise RuntimeError("stylish_tts_b200: SpecDiscriminator needs CUDA tensors (no CPU fallback)")
+        if not self.fused:
+            return self._forward_generic(y)
+        B, one, K, N = y.shape
+        assert one == 1
+        mode = self.backward_mode
+        conv = lambda t, w4, b: RowConvFn.apply(
+            t, w4, b, None, dict(row_mask=self._row_mask(t.shape[0], t.shape[1], t.shape[3], t.device), mode=mode,
+                                 fold_free=True, wide=True))
+        result: List[torch.Tensor] = []
+        d0 = self.discriminators[0]
+        h = FirstConvFn.apply(y[:, 0].to(torch.float32), self._w(d0), d0.bias, mode)
+        for i in range(5):
+            kind = 2 if i < 3 else (1 if i == 3 else 0)   # layers 1-3 are stride (1,2): space-to-depth input
+            score, nxt = TailFn.apply(h, self._w(self.out[i]), self.out[i].bias, kind, mode)
+            result.append(score.reshape(B, -1))               # torch.flatten(out, 1, -1), discriminator.py:61
+            if i == 4:
+                break
+            d = self.discriminators[i + 1]
+            h = conv(nxt, stride2_weight(self._w(d)) if i < 3 else self._w(d), d.bias)
+        return result, []
+
+    def _forward_generic(self, y):
         B, one, K, N = y.shape
         assert one == 1
         Hp = K + 2
@@ -138,8 +248,7 @@ class SpecDiscriminator(nn.Module):
         for i in range(5):
             a = leaky_image(h)                                   # LeakyReLU(0.1), discriminator.py:59
             # score conv 32 -> 1: zero-padded to 16 output channels so that forward, data gradient and weight
-            # gradient all take the tensor-core kernels (a 1-channel conv on the fp32 FMA kernel was 10x slower
-            # than the 32 -> 32 layer it follows); channel 0 is the score map
+            # gradient all take the tensor-core kernels; channel 0 is the score map
             wo = torch.nn.functional.pad(self._w(self.out[i]), (0, 0, 0, 0, 0, 0, 0, 15))
             bo = torch.nn.functional.pad(self.out[i].bias, (0, 15))
             o = conv(a, wo, bo)                                  # (B,Hp,16,W)

@@ -23,6 +23,7 @@ INV_SQRT2 = 1.0 / math.sqrt(2.0)
 # tensor-core (tcgen05, bf16x3) path for eligible convs; STYLISH_B200_UMMA=0 forces fp32 FMA
 USE_UMMA = os.environ.get("STYLISH_B200_UMMA", "1") != "0"
 UMMA_MIN_T = 64
+WIDE_MIN_ELEMS = 65536  # conv1d(wide=True): rows x steps from which short rows still go to the tensor cores
 # InstanceNorm statistics of the S-rate AdaINs accumulated in the producing conv's epilogue (one pass less)
 FUSE_STATS = os.environ.get("STYLISH_B200_FUSE_STATS", "1") != "0"
 # output-rate ConvNeXt blocks as one fused two-pass kernel that never stores the 4C-wide intermediate
@@ -75,7 +76,7 @@ class ConvW:
 def conv1d(x, cw: ConvW, *, dil=1, out=None, res=None, in_scale=None, in_shift=None,
            in_alpha=None, in_act=ACT_NONE, in_mask=None, out_mask=None, out_act=ACT_NONE,
            out_alpha=None, out_sumsq=None, out_sum=None, shuffle=0, out_scale=1.0, res_scale=1.0, umma=True,
-           dwln=None):
+           dwln=None, wide=False):
     B, CI, T = x.shape
     assert CI == cw.CI, (CI, cw.CI)
     x_bs, x_cs = L._bct(x, "x")
@@ -102,7 +103,8 @@ def conv1d(x, cw: ConvW, *, dil=1, out=None, res=None, in_scale=None, in_shift=N
     a.pad = (cw.K - 1) * dil // 2
     a.in_act, a.out_act, a.shuffle = in_act, out_act, shuffle
     a.out_scale, a.res_scale = out_scale, res_scale
-    if umma and USE_UMMA and cw.split is not None and T >= UMMA_MIN_T:
+    # `wide`: thousands of short rows (row-stacked images) — the tensor-core kernel wins below UMMA_MIN_T too
+    if umma and USE_UMMA and cw.split is not None and (T >= UMMA_MIN_T or (wide and T >= 16 and B * T >= WIDE_MIN_ELEMS)):
         a.w_split = cw.split.data_ptr()
     if dwln is not None:  # fused ConvNeXt front (dw_w, dw_b, gamma|beta rows, row stride, eps)
         assert a.w_split, "fused ConvNeXt front needs the tensor-core path"

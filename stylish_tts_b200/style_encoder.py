@@ -53,7 +53,13 @@ class RowConvFn(Function):
         xv = x.as_strided((N, R * Cc, W), (Cc * W, W, 1))
         w3 = w4.detach().permute(0, 2, 1, 3).reshape(Co, R * Cc, K)
         off = cfg.get("out_off", (R - 1) // 2)
-        y = torch.zeros((B, Hp, Co, W), device=x.device, dtype=torch.float32)
+        if cfg.get("fold_free") and cfg.get("row_mask") is not None and off == 1 and R == 3:
+            # the masked windows write every row but the first and the last one of the stack
+            y = torch.empty((B, Hp, Co, W), device=x.device, dtype=torch.float32)
+            y[0, 0].zero_()
+            y[B - 1, Hp - 1].zero_()
+        else:
+            y = torch.zeros((B, Hp, Co, W), device=x.device, dtype=torch.float32)
         yv = y.as_strided((N, Co, W), (Co * W, W, 1), off * Co * W)
         resv = None
         if res is not None:
@@ -61,7 +67,7 @@ class RowConvFn(Function):
             resv = res.as_strided((N, Co, W), (Co * W, W, 1), off * Co * W)
         conv1d(xv, ConvW(w3, None if bias is None else bias.detach()), in_act=cfg.get("in_act", ACT_NONE),
                out_mask=cfg.get("row_mask"), res=resv, out=yv, out_scale=cfg.get("out_scale", 1.0),
-               res_scale=cfg.get("res_scale", 1.0), umma=cfg.get("umma", True))
+               res_scale=cfg.get("res_scale", 1.0), umma=cfg.get("umma", True), wide=cfg.get("wide", False))
         ctx.save_for_backward(x, w4)
         ctx.cfg, ctx.has_bias, ctx.has_res, ctx.off = cfg, bias is not None, res is not None, off
         return y
@@ -93,7 +99,20 @@ class RowConvFn(Function):
             d_w3 = T.wgrad(xv, gv, K, 1, in_act=in_act, out_mask=mask, out_scale=out_scale, umma=umma)
             d_w4 = d_w3.reshape(Co, R, Cc, K).permute(0, 2, 1, 3)
         d_x = None
-        if need[0]:
+        if need[0] and cfg.get("fold_free"):
+            # the adjoint of an R x K 'same' conv is the R x K conv of dy with the taps reversed along both axes and
+            # the channel roles swapped — the same row-stacked kernel, no (N, R*C, W) intermediate and no fold pass.
+            # Needs zero border rows in dy, which every producer of the discriminator chain guarantees
+            # (TailFn / this function write them as zeros).
+            assert in_act == ACT_NONE and out_scale == 1.0 and R == 3 and ctx.off == 1 and mask is not None
+            wt = w4.detach().flip(2, 3).permute(1, 2, 0, 3).reshape(Cc, R * Co, K)
+            gx = dy.as_strided((N, R * Co, W), (Co * W, W, 1))
+            d_x = torch.empty((B, Hp, Cc, W), device=x.device, dtype=torch.float32)
+            d_x[0, 0].zero_()
+            d_x[B - 1, Hp - 1].zero_()
+            conv1d(gx, ConvW(wt, None), out_mask=mask, out=d_x.as_strided((N, Cc, W), (Cc * W, W, 1), Cc * W),
+                   umma=umma, wide=cfg.get("wide", False))
+        elif need[0]:
             dxp = conv1d(gv, T.transposed_weight(w3), in_mask=mask, out_scale=out_scale, umma=umma)  # (N,R*C,W)
             folded = _new((B, Hp, Cc, W), x)
             L.call("sty_fold_rows", dxp.data_ptr(), folded.data_ptr(), R, B, Hp, Cc, W, L.stream_ptr())

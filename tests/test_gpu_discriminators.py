@@ -58,12 +58,20 @@ def _seeded_disc(seed):
     return m
 
 
+@pytest.mark.parametrize("fused", [True, False])
 @pytest.mark.parametrize("tensor_cores", [True, False])
-@pytest.mark.parametrize("bins,frames", [(65, 523), (33, 1030)])
-def test_spec_discriminator_tensor_core_path_vs_fp64_oracle(bins, frames, tensor_cores, monkeypatch):
+@pytest.mark.parametrize("bins,frames", [(65, 523), (33, 1030), (20, 333)])
+def test_spec_discriminator_tensor_core_path_vs_fp64_oracle(bins, frames, tensor_cores, fused, monkeypatch):
+    """fused = the production path (first-layer / tail kernels of csrc/disc_ops.cu + fold-free data gradients);
+    fused = False = every layer through the generic conv kernels.  (20, 333): 333 -> 167 -> 84 -> 42 frames, the
+    last two layers run below UMMA_MIN_T and take the `wide` tensor-core rule (threshold lowered for the test)."""
     from stylish_tts_b200 import engine as E
 
+    if not fused and frames == 333:
+        pytest.skip("wide rule belongs to the fused path")
     monkeypatch.setattr(E, "USE_UMMA", tensor_cores)
+    monkeypatch.setattr(E, "WIDE_MIN_ELEMS", 0)
+    monkeypatch.setattr(D.SpecDiscriminator, "fused", fused)
     m = _seeded_disc(bins)
     sd64 = {k: v.detach().double().requires_grad_(True) for k, v in m.state_dict().items()}
     gen = torch.Generator().manual_seed(frames)
@@ -268,6 +276,7 @@ def test_shared_evaluation_matches_the_two_evaluation_losses():
         assert all(p.grad is None for m in mods for p in m.parameters())  # constants of the generator step
         for i in range(3):
             assert rel_l2(pb[i].grad, pa[i].grad) < 1e-6, (i, rel_l2(pb[i].grad, pa[i].grad))
+        before = [p.grad.clone() for p in pb]
         db = adv.discriminator_backward(index, scale)
         assert float(db) == pytest.approx(float(da), rel=1e-6)
         for i in range(3):
@@ -275,11 +284,81 @@ def test_shared_evaluation_matches_the_two_evaluation_losses():
                                                                                rel=1e-6)
             for k, p in mods[i].named_parameters():
                 if i == index:
-                    assert rel_l2(p.grad, grads_a[i][k]) < 1e-5, (i, k, rel_l2(p.grad, grads_a[i][k]))
+                    assert rel_l2(p.grad, grads_a[i][k]) < 1e-4, (i, k, rel_l2(p.grad, grads_a[i][k]))  # fp32 sums in another order
                 else:
                     assert p.grad is None, (i, k)
-        assert all(p.grad.abs().max() == pa[i].grad.abs().max() for i, p in enumerate(pb))  # untouched by the 2nd walk
+        assert all(torch.equal(p.grad, g0) for p, g0 in zip(pb, before))  # untouched by the second walk
         with pytest.raises(RuntimeError):
             adv.discriminator_backward(index, scale)  # the tape is released after the discriminator half
         for m in mods:
             m.zero_grad(set_to_none=True)
+
+
+def _conv2d_ref(x, w, b, stride=(1, 1), pad=(1, 4)):
+    return torch.nn.functional.conv2d(x, w, b, stride=stride, padding=pad)
+
+
+@pytest.mark.parametrize("B,bins,W", [(2, 17, 600), (1, 5, 37), (3, 9, 513)])
+def test_first_layer_kernels_vs_torch_fp64(B, bins, W):
+    """sty_disc_first_{fwd,dgrad,wgrad}: Conv2d(1 -> 32, 3x9, pad (1,4)) and both gradients against torch fp64"""
+    g = torch.Generator().manual_seed(bins * W)
+    y = torch.randn(B, bins, W, generator=g)
+    w = torch.randn(32, 1, 3, 9, generator=g) / 5
+    b = torch.randn(32, generator=g)
+    cot = torch.randn(B, 32, bins, W, generator=g)
+    y64, w64, b64 = (t.double().requires_grad_(True) for t in (y, w, b))
+    ref = _conv2d_ref(y64[:, None], w64, b64)
+    (ref * cot.double()).sum().backward()
+    yd, wd, bd = (t.to(dev()).requires_grad_(True) for t in (y, w, b))
+    h = D.FirstConvFn.apply(yd, wd, bd, None)                         # (B, bins+2, 32, W)
+    assert float(h[:, 0].abs().max()) == 0 and float(h[:, -1].abs().max()) == 0
+    assert rel_l2(h[:, 1:-1].permute(0, 2, 1, 3), ref) < 2e-6
+    coth = torch.zeros_like(h)
+    coth[:, 1:-1] = cot.to(dev()).permute(0, 2, 1, 3)
+    (h * coth).sum().backward()
+    assert rel_l2(yd.grad, y64.grad) < 2e-6, rel_l2(yd.grad, y64.grad)
+    assert rel_l2(wd.grad, w64.grad) < 5e-6, rel_l2(wd.grad, w64.grad)
+    assert rel_l2(bd.grad, b64.grad) < 5e-6, rel_l2(bd.grad, b64.grad)
+
+
+@pytest.mark.parametrize("kind", [0, 1, 2])
+@pytest.mark.parametrize("B,bins,W", [(2, 19, 300), (1, 6, 131), (2, 8, 58)])
+def test_tail_kernels_vs_torch_fp64(B, bins, W, kind):
+    """sty_disc_tail_{fwd,bwd} + sty_disc_score_wgrad: LeakyReLU(0.1) -> (score conv 32 -> 1 3x3 | identity |
+    space-to-depth) and the single-pass backward, against torch fp64"""
+    g = torch.Generator().manual_seed(bins * W + kind)
+    Hp = bins + 2
+    h = torch.zeros(B, Hp, 32, W)
+    h[:, 1:-1] = torch.randn(B, bins, 32, W, generator=g)
+    ws = torch.randn(1, 32, 3, 3, generator=g) / 8
+    bs = torch.randn(1, generator=g)
+    h64, w64, b64 = (t.double().requires_grad_(True) for t in (h, ws, bs))
+    a64 = torch.nn.functional.leaky_relu(h64, 0.1)                   # (B,Hp,32,W), zero border rows stay zero
+    score64 = _conv2d_ref(a64[:, 1:-1].permute(0, 2, 1, 3), w64, b64, pad=(1, 1))[:, 0]   # (B,bins,W)
+    W2 = (W + 1) // 2
+    if kind == 1:
+        next64 = a64
+    elif kind == 2:
+        ap = torch.nn.functional.pad(a64, (0, 2 * W2 - W))
+        next64 = ap.reshape(B, Hp, 32, W2, 2).permute(0, 1, 2, 4, 3).reshape(B, Hp, 64, W2)
+    cs = torch.randn(score64.shape, generator=g)
+    loss = (score64 * cs.double()).sum()
+    cn = None
+    if kind:
+        cn = torch.randn(next64.shape, generator=g)
+        cn[:, 0] = 0
+        cn[:, -1] = 0          # consumers never send gradient into the border rows
+        loss = loss + (next64 * cn.double()).sum()
+    loss.backward()
+    hd, wd, bd = (t.to(dev()).requires_grad_(True) for t in (h, ws, bs))
+    score, nxt = D.TailFn.apply(hd, wd, bd, kind, None)
+    assert rel_l2(score, score64) < 2e-6, rel_l2(score, score64)
+    lossd = (score * cs.to(dev())).sum()
+    if kind:
+        assert nxt.shape == next64.shape and rel_l2(nxt, next64) < 1e-7
+        lossd = lossd + (nxt * cn.to(dev())).sum()
+    lossd.backward()
+    assert float(hd.grad[:, 0].abs().max()) == 0 and float(hd.grad[:, -1].abs().max()) == 0
+    assert rel_l2(hd.grad[:, 1:-1], h64.grad[:, 1:-1]) < 2e-6, rel_l2(hd.grad[:, 1:-1], h64.grad[:, 1:-1])
+    assert rel_l2(wd.grad, w64.grad) < 5e-6, rel_l2(wd.grad, w64.grad)
+    assert rel_l2(bd.grad, b64.grad) < 5e-6, rel_l2(bd.grad, b64.grad)

@@ -11,14 +11,15 @@ g = torch.Generator(device=d).manual_seed(0)
 shapes = [(257, 1876), (513, 938), (1025, 469)]
 tf = [torch.rand(B, 1, k, n, device=d, generator=g) for k, n in shapes]
 pf = [(t * 0.9).requires_grad_(True) for t in tf]
-gl = D.GeneratorLoss(mrd0=mrd[0], mrd1=mrd[1], mrd2=mrd[2])
-dl = D.DiscriminatorLoss(mrd0=mrd[0], mrd1=mrd[1], mrd2=mrd[2], device=d)
+import math, random
+adv = D.AdversarialTerms(mrd0=mrd[0], mrd1=mrd[1], mrd2=mrd[2], device=d)
 
 def step():
-    loss = gl(target_list=tf, pred_list=pf)
+    # one evaluation of mrd0-2 on (target, prediction): generator term + backward to the spectrograms, then the
+    # discriminator loss from the same scores and the backward of the stepped discriminator
+    loss = adv(target_list=tf, pred_list=pf)
     loss.backward()
-    dloss = dl(target_list=tf, pred_list=[p.detach() for p in pf])
-    dloss.backward()
+    adv.discriminator_backward(random.randrange(3), math.sqrt(B))
     for m in mrd:
         m.zero_grad()
 step(); torch.cuda.synchronize()
