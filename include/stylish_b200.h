@@ -170,6 +170,21 @@ STY_API int sty_tprls_fwd(const float* a, const float* b, int64_t n, void* works
 STY_API int sty_tprls_bwd(const float* a, const float* b, int64_t n, const float* median, const float* coef, float* da,
                           float* db, int* flag, sty_stream_t stream);
 
+/* ---- 64-wide attention, second generation (conformer.py:112-131; Transformer1d blocks of the style denoiser) --------
+ * No mask / RoPE / dropout, head dim 64.  One pre-pass splits q (scaled), k, v into bf16 hi | lo planes stored as the
+ * shared-memory image of each tile; the attention kernel then moves tiles with cp.async.bulk and issues the next tile's
+ * S = Q K^T behind the current P V (tcgen05, bf16x3).  `workspace`: sty_attention64_workspace_bytes(B,H,T) bytes,
+ * 16-byte aligned, owned by the caller (contents are scratch).
+ * sty_attention64_fwd       : q, k, v (B, H*64, T) fp32 channel-major, batch stride qkv_bs; o (B, H*64, T), batch
+ *                             stride o_bs; lse (B,H,T) log-sum-exp per query or NULL.
+ * sty_attention64_tokens_fwd: qkv token-major rows [B*T, ld] (q | k | v at columns 0 / H*64 / 2*H*64); output bf16
+ *                             hi | lo planes [2][M_pad][H*64] (rows >= B*T untouched). */
+STY_API int64_t sty_attention64_workspace_bytes(int B, int H, int T);
+STY_API int sty_attention64_fwd(const float* q, const float* k, const float* v, int64_t qkv_bs, float* o, int64_t o_bs,
+                                int B, int H, int T, float scale, float* lse, void* workspace, sty_stream_t stream);
+STY_API int sty_attention64_tokens_fwd(const float* qkv, int64_t ld, void* out_split, int64_t M_pad, int B, int H, int T,
+                                       float scale, void* workspace, sty_stream_t stream);
+
 /* ---- spectrogram discriminator, non-tensor-core layers (discriminator.py:13-69) ---------------------------------
  * Row-channel images (B, Hp = bins + 2, C, W) with zero border rows, 32 hidden channels, LeakyReLU slope 0.1.
  * sty_disc_first_fwd  : h = Conv2d(1 -> 32, 3x9, pad (1,4))(y), y (B,bins,W) -> h (B,Hp,32,W) (border rows written 0);

@@ -171,6 +171,8 @@ _SIGNATURES = {
     "sty_sqdiff_sum_fwd": [_f32p, _i64, _f32, _f32p, _f32p],
     "sty_tprls_fwd": [_f32p, _f32p, _i64, _f32p, _f32p, _f32p, _f32p],
     "sty_tprls_bwd": [_f32p, _f32p, _i64, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p],
+    "sty_attention64_fwd": [_f32p, _f32p, _f32p, _i64, _f32p, _i64, _i32, _i32, _i32, _f32, _f32p, _f32p, _f32p],
+    "sty_attention64_tokens_fwd": [_f32p, _i64, _f32p, _i64, _i32, _i32, _i32, _f32, _f32p, _f32p],
     "sty_disc_first_fwd": [_f32p, _f32p, _f32p, _f32p, _i32, _i32, _i32, _f32p],
     "sty_disc_first_dgrad": [_f32p, _f32p, _f32p, _i32, _i32, _i32, _f32p],
     "sty_disc_first_wgrad": [_f32p, _f32p, _f32p, _f32p, _i32, _i32, _i32, _f32p],
@@ -183,6 +185,7 @@ _SPECIAL = {
     "sty_last_error": ([], C.c_char_p),
     "sty_device_sm_count": ([], C.c_int),
     "sty_tprls_workspace_bytes": ([], C.c_int64),
+    "sty_attention64_workspace_bytes": ([_i32, _i32, _i32], C.c_int64),
 }
 EXPORTED = tuple(_SIGNATURES) + tuple(_SPECIAL)
 
@@ -264,6 +267,8 @@ def _signature(name: str, args) -> str:
     pos = {"sty_dwconv_ln_fwd": (9, 10), "sty_chan_layernorm_fwd": (11, 12),
            "sty_chan_layernorm_pitched_fwd": (13, 14), "sty_convnext_fused_fwd": (20, 22),
            "sty_instnorm_affine_fwd": (8, 9), "sty_attention_fwd": (12, 13)}.get(name)
+    if name == "sty_attention64_fwd":
+        return f"attention64_fwd[c=64,T={args[8]}]"
     if pos:
         return f"{name[4:]}[c={args[pos[0]]},T={args[pos[1]]}]"
     return name[4:]
@@ -273,7 +278,8 @@ def call(name: str, *args) -> None:
     global launches
     lib = load()
     # kernels per call: source = phase + wave; fused ConvNeXt block = pass 1 + GRN scale + pass 2
-    launches += 2 if name == "sty_source_fwd" else 3 if name == "sty_convnext_fused_fwd" else 1
+    launches += (2 if name in ("sty_source_fwd", "sty_attention64_fwd", "sty_attention64_tokens_fwd")
+                 else 3 if name == "sty_convnext_fused_fwd" else 1)
     if profile_log is not None:
         e0 = torch.cuda.Event(enable_timing=True)
         e1 = torch.cuda.Event(enable_timing=True)

@@ -14,7 +14,7 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SOURCES = ["err.cu", "tma.cu", "spectral.cu", "backward.cu", "wgrad_umma.cu", "attention_bwd.cu", "image_ops.cu", "conv1d.cu", "conv1d_umma.cu", "convnext_fused.cu", "gan_ops.cu", "disc_ops.cu", "gemm_split.cu", "norms.cu", "attention.cu", "attention_umma.cu", "source_stft.cu", "misc.cu", "seq_ops.cu", "dropout.cu"]
+SOURCES = ["err.cu", "tma.cu", "spectral.cu", "backward.cu", "wgrad_umma.cu", "attention_bwd.cu", "image_ops.cu", "conv1d.cu", "conv1d_umma.cu", "convnext_fused.cu", "gan_ops.cu", "disc_ops.cu", "gemm_split.cu", "norms.cu", "attention.cu", "attention_umma.cu", "attention64.cu", "source_stft.cu", "misc.cu", "seq_ops.cu", "dropout.cu"]
 LIB = os.path.join(HERE, "libstylish_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -116,8 +116,9 @@ class StyleDenoiser(nn.Module):
             qkv, _ = self._gemm(n_pl, P[f"{i}.qkv"], None, None, Mp, 3 * HD, C)
             att_pl = torch.zeros((2, Mp, HD), device=dev, dtype=torch.bfloat16) if Mp != M else \
                 torch.empty((2, Mp, HD), device=dev, dtype=torch.bfloat16)
-            L.call("sty_attention_tokens_fwd", qkv.data_ptr(), 3 * HD, att_pl.data_ptr(), Mp, B, HEADS, T,
-                   HEAD_DIM ** -0.5, L.stream_ptr())
+            ws = torch.empty(int(L.load().sty_attention64_workspace_bytes(B, HEADS, T)), device=dev, dtype=torch.uint8)
+            L.call("sty_attention64_tokens_fwd", qkv.data_ptr(), 3 * HD, att_pl.data_ptr(), Mp, B, HEADS, T,
+                   HEAD_DIM ** -0.5, ws.data_ptr(), L.stream_ptr())
             h1, h1_pl = self._gemm(att_pl, P[f"{i}.out"], blk.to_out.bias, hm, Mp, C, HD, want_planes=True)
             ff0, ff1 = getattr(blk.ff, "0"), getattr(blk.ff, "1")
             _, f_pl = self._gemm(h1_pl, P[f"{i}.ff0"], ff0.bias, None, Mp, 2 * C, C, act=ACT_GELU, want_f32=False,

@@ -165,6 +165,18 @@ def dwconv1d(x, w, bias, *, K, pad_left, out, post_scale=None, post_shift=None, 
     return out
 
 
+# 64-wide unmasked attention through the pre-split / bulk-copy kernel (csrc/attention64.cu); 0 = first-generation kernel
+ATTENTION64 = os.environ.get("STYLISH_B200_ATTENTION64", "1") != "0"
+
+
+def attention64(q_ptr, k_ptr, v_ptr, qkv_bs, out, B, H, T, scale, lse=None):
+    """q, k, v: device pointers of (B, H*64, T) fp32 tensors with batch stride qkv_bs -> out (B, H*64, T)"""
+    ws = torch.empty(int(L.load().sty_attention64_workspace_bytes(B, H, T)), device=out.device, dtype=torch.uint8)
+    L.call("sty_attention64_fwd", q_ptr, k_ptr, v_ptr, qkv_bs, out.data_ptr(), out.stride(0), B, H, T, scale,
+           L.ptr(lse), ws.data_ptr(), L.stream_ptr())
+    return out
+
+
 def attention(qkv, n_q, n_k, n_v, *, H, D, lengths=None, rope=None, scale):
     """qkv: (B, n_q+n_k+n_v, T) fused projection output."""
     B, _, T = qkv.shape
@@ -174,6 +186,9 @@ def attention(qkv, n_q, n_k, n_v, *, H, D, lengths=None, rope=None, scale):
     q = qkv.data_ptr()
     k = q + 4 * n_q * T
     v = k + 4 * n_k * T
+    if D == 64 and rope is None and lengths is None and T >= 64 and ATTENTION64:
+        attention64(q, k, v, bs, out, B, H, T, scale)
+        return out
     rc, rs, d_rot = (None, None, 0) if rope is None else (rope[0].data_ptr(), rope[1].data_ptr(),
                                                           rope[2])
     L.call("sty_attention_fwd", q, k, v, bs, out.data_ptr(), out.stride(0), L.ptr(lengths), rc, rs,

@@ -468,6 +468,11 @@ class _NullRng:
 _NULL_RNG = _NullRng()
 
 
+def _engine():
+    from . import engine
+    return engine
+
+
 class AttentionFn(Function):
     """attention core on a fused (B, 3*H*D, T) q|k|v tensor (text_encoder.py:233-272, conformer.py:112-131);
     ``drop`` = (DropoutRng, site, p) puts SDPA's dropout on the probabilities."""
@@ -486,6 +491,9 @@ class AttentionFn(Function):
             L.call("sty_attention_drop_fwd", q, q + 4 * n * T, q + 8 * n * T, qkv.stride(0), out.data_ptr(),
                    out.stride(0), L.ptr(lengths), rc, rs, d_rot, B, H, D, T, scale, lse.data_ptr(), C.byref(spec),
                    L.stream_ptr())
+        elif D == 64 and rope is None and lengths is None and T >= 64 and _engine().ATTENTION64:
+            drop = None
+            _engine().attention64(q, q + 4 * n * T, q + 8 * n * T, qkv.stride(0), out, B, H, T, scale, lse=lse)
         else:
             drop = None
             L.call("sty_attention_lse_fwd", q, q + 4 * n * T, q + 8 * n * T, qkv.stride(0), out.data_ptr(),

@@ -234,9 +234,12 @@ def test_attention_text(T, lens):
     assert rel_l2(out, ref) < 5e-5
 
 
-@pytest.mark.parametrize("T", [203, 803, 64, 129])
-def test_attention_conformer(T):
-    """8 heads x 64, no mask: the tcgen05 flash kernel (bf16x3) against fp64 softmax attention"""
+@pytest.mark.parametrize("second_gen", [True, False])
+@pytest.mark.parametrize("T", [203, 803, 64, 129, 258, 1030])
+def test_attention_conformer(T, second_gen, monkeypatch):
+    """8 heads x 64, no mask: the tcgen05 flash kernels (bf16x3) against fp64 softmax attention.
+    second_gen: pre-split operands + cp.async.bulk tiles (csrc/attention64.cu); else the first kernel."""
+    monkeypatch.setattr(E, "ATTENTION64", second_gen)
     gen = g(64)
     B, H, D = 2, 8, 64
     qkv = torch.randn(B, 3 * H * D, T, generator=gen) * 1.5
