@@ -466,13 +466,15 @@ def measure_train(args, dev, world, rank, barrier, steps, warmup, batch):
         "grad_allreduce_bytes": opt.numel * 4 if world > 1 else 0,
         "params": opt.numel, "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 1e9, 1),
         "loss": [round(float(x), 5) for x in loss_host.tolist()],
-        "adversarial": ("generator term on mrd0-2 (LSGAN + TPRLS) + discriminator half-step (one of mrd0-2 per batch, "
-                        "sqrt(B) scaling, gap-aware lr); waveform discriminator `disc` not included") if adversarial
-        else "off",
+        "adversarial": ("generator term on mrd0-2 (LSGAN + TPRLS) + discriminator half-step (loss of all three, "
+                        "mrd{random index} stepped, sqrt(B) scaling, gap-aware lr) from ONE evaluation of the "
+                        "discriminators per batch (discriminator.AdversarialTerms); waveform discriminator `disc` "
+                        "not included") if adversarial else "off",
         "scope": "AcousticStep(use_predicted_pe=False, predict_audio=True): calculate_mel x2 + energy + alignment "
                  "+ speech_style_encoder + speech_predictor (train() mode: batch-stat BN, dropout sites and decoder box smoothing live) + "
                  "MultiSpectrogram x3 + mel & multi-phase losses (backwards_loss normalisation) + backward of "
-                 "both modules + fused AdamW; adversarial / SLM terms out of scope (SURVEY 8f)",
+                 "both modules + fused AdamW" + ("; + adversarial terms (stage.py:104-146)" if adversarial
+                                                 else "; adversarial terms measured separately (train_adversarial)"),
     }
     del graphed, opt, sp, se, nets
     torch.cuda.empty_cache()
@@ -682,7 +684,7 @@ def run_ours(args):
             log(f"[bench] configs[3] failed: {type(e).__name__}: {e}")
         torch.cuda.empty_cache()
 
-    train = None
+    train = train_adv = None
     had_graph = graph is not None
     if not args.no_train:
         had_graph, graph = graph is not None, None  # free the captured graph's memory pool first
@@ -692,6 +694,14 @@ def run_ours(args):
                                   args.train_batch)
         except Exception as e:
             log(f"[bench] train measurement failed: {type(e).__name__}: {e}")
+        try:  # the same step with the adversarial terms of the acoustic stage (mrd0-2)
+            import copy
+            adv_args = copy.copy(args)
+            adv_args.adversarial = True
+            torch.cuda.empty_cache()
+            train_adv = measure_train(adv_args, dev, world, rank, barrier, 3, 3, args.train_batch)
+        except Exception as e:
+            log(f"[bench] adversarial train measurement failed: {type(e).__name__}: {e}")
 
     if rank == 0:
         peak_hbm, _ = measured_peaks()
@@ -707,6 +717,9 @@ def run_ours(args):
                              train_global_batch=train["global_batch"],
                              train_grad_allreduce_bytes=train["grad_allreduce_bytes"],
                              train_e2e_ms_per_step=round(train["e2e"]["ms_per_step"], 3))
+        if train_adv is not None:
+            extra_cfg.update(train_adversarial_ms_per_step=round(train_adv["ms_per_step"], 3),
+                             train_adversarial_steps_per_s=round(train_adv["steps_per_s"], 4))
         if config0 is not None:
             extra_cfg.update(config0_ours_audio_s_per_s=round(config0["ours_audio_s_per_s"], 1),
                              config0_cpu_audio_s_per_s=round(config0.get("cpu_audio_s_per_s", 0.0), 2))
@@ -735,6 +748,7 @@ def run_ours(args):
             "cpu_baseline": cpu,
             "top_kernels": top,
             "train": train,
+            "train_adversarial": train_adv,
             "config0": config0,
             "diffusion": diffusion,
         }), flush=True)

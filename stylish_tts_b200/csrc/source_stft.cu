@@ -164,80 +164,111 @@ stft_kernel(const float* __restrict__ wave, const float* __restrict__ basis_re,
 }
 
 // ---------------------------------------------------------------- iSTFT head
-// thread = HOP consecutive output samples.  R = NFFT/HOP frames overlap each sample.
-template <int NFFT, int HOP, int BINS, int MT>
+// out[4 mo + r] = tanh( sum_{fr < 16} sum_{kb < 32}  re[kb, f] * Br[kb][4 (15 - fr) + r] - im[kb, f] * Bi[kb][...] ),
+// f = mo - 7 + fr: a 16-tap, 64 -> 4 channel contraction per S-rate step (4096 FMAs per step, 3.9 GFMA per call at
+// config 2).  Register-tiled: a thread owns G = 8 consecutive output groups (32 samples); per bin it loads its 23
+// frames of re / im (12 LDS.128) and the 2 x 64 basis taps (32 broadcast LDS.128) for 1024 FMAs, so the loop is bound
+// by the FMA pipe and not by shared-memory loads (the first version did 4 loads per 8 FMAs).  The head math
+// (exp(logamp), cos / sin of atan2(imag, real) without the transcendental: one rsqrt) is done while staging.
+template <int NFFT, int HOP, int BINS, int MT, int G, int KC>
 __global__ void __launch_bounds__(MT)
 istft_head_kernel(const float* __restrict__ logamp, int64_t logamp_bs, int64_t logamp_cs,
                   const float* __restrict__ real, const float* __restrict__ imag, int64_t ri_bs, int64_t ri_cs,
                   const float* __restrict__ basis_re, const float* __restrict__ basis_im,
                   float* __restrict__ out, int S) {
-  static_assert(HOP == 4, "vectorised basis loads assume hop 4");
-  constexpr int R = NFFT / HOP;
-  constexpr int FT = MT + R - 1;
+  static_assert(HOP == 4 && NFFT == 64 && G == 8, "register tiling assumes hop 4, n_fft 64, 8 groups per thread");
+  constexpr int R = NFFT / HOP;          // 16 frames overlap each sample
+  constexpr int FT = MT * G + R - 1;     // frames staged per block
   constexpr int FTP = (FT + 3) & ~3;
+  constexpr int NF = G + R - 1;          // 23 frames per thread
   extern __shared__ __align__(16) float sm[];
-  float* bre = sm;                // [BINS][NFFT]
-  float* bim = bre + BINS * NFFT; // [BINS][NFFT]
-  float* res = bim + BINS * NFFT; // [BINS][FTP]
-  float* ims = res + BINS * FTP;  // [BINS][FTP]
+  float* bre = sm;                 // [BINS][NFFT]
+  float* bim = bre + BINS * NFFT;  // [BINS][NFFT]
+  float* res = bim + BINS * NFFT;  // [KC][FTP]
+  float* ims = res + KC * FTP;     // [KC][FTP]
   const int b = blockIdx.y;
   const int tid = threadIdx.x;
-  const int mo0 = blockIdx.x * MT;  // first output group of this CTA
-  // output group mo covers padded samples n' = HOP*(mo + R/2) + r; frames f with
-  // 0 <= n' - HOP*f < NFFT  <=>  f in [mo + R/2 - (R-1), mo + R/2]
+  const int mo0 = blockIdx.x * MT * G;  // first output group of this CTA
   const int fbase = mo0 + R / 2 - (R - 1);
   for (int i = tid; i < BINS * NFFT; i += MT) {
     bre[i] = basis_re[i];
     bim[i] = basis_im[i];
   }
-  for (int idx = tid; idx < BINS * FTP; idx += MT) {
-    const int kb = idx / FTP, fl = idx - kb * FTP;
-    const int f = fbase + fl;
-    float re = 0.f, im = 0.f;
-    if (fl < FT && f >= 0 && f <= S) {
-      const int fs = min(f, S - 1);  // replicate-pad of one frame (generator.py:784-785)
-      const int64_t o = (int64_t)kb * ri_cs + fs;
-      const float mag = expf(logamp[(int64_t)b * logamp_bs + (int64_t)kb * logamp_cs + fs]);
-      // cos(atan2(y, x)) = x/|z|, sin(atan2(y, x)) = y/|z| (atan2(0, 0) = 0 -> cos 1, sin 0): one rsqrt
-      // instead of atan2f + cosf + sinf; the operands are scaled first so x^2 + y^2 cannot over/underflow
-      const float xr = real[(int64_t)b * ri_bs + o], yi = imag[(int64_t)b * ri_bs + o];
-      const float big = fmaxf(fabsf(xr), fabsf(yi));
-      float c = 1.f, sn = 0.f;
-      if (big > 0.f) {
-        const float inv = 1.0f / big;
-        const float xs = xr * inv, ys = yi * inv;
-        const float rn = rsqrtf(fmaf(xs, xs, ys * ys));
-        c = xs * rn;
-        sn = ys * rn;
+  float acc[G][HOP];
+#pragma unroll
+  for (int g = 0; g < G; ++g)
+#pragma unroll
+    for (int r = 0; r < HOP; ++r) acc[g][r] = 0.f;
+
+  for (int kb0 = 0; kb0 < BINS; kb0 += KC) {
+    __syncthreads();  // previous chunk consumed (and, the first time, nothing to wait for but the basis stores)
+#pragma unroll 1
+    for (int kc = 0; kc < KC; ++kc) {
+      const int kb = kb0 + kc;
+      const float* __restrict__ la = logamp + (int64_t)b * logamp_bs + (int64_t)kb * logamp_cs;
+      const float* __restrict__ xr_ = real + (int64_t)b * ri_bs + (int64_t)kb * ri_cs;
+      const float* __restrict__ yi_ = imag + (int64_t)b * ri_bs + (int64_t)kb * ri_cs;
+      for (int fl = tid; fl < FTP; fl += MT) {
+        const int f = fbase + fl;
+        float re = 0.f, im = 0.f;
+        if (fl < FT && f >= 0 && f <= S) {
+          const int fs = min(f, S - 1);  // replicate-pad of one frame (generator.py:784-785)
+          const float mag = expf(la[fs]);
+          // cos(atan2(y, x)) = x/|z|, sin(atan2(y, x)) = y/|z| (atan2(0, 0) = 0 -> cos 1, sin 0): one rsqrt
+          // instead of atan2f + cosf + sinf; the operands are scaled first so x^2 + y^2 cannot over/underflow
+          const float xr = xr_[fs], yi = yi_[fs];
+          const float big = fmaxf(fabsf(xr), fabsf(yi));
+          float c = 1.f, sn = 0.f;
+          if (big > 0.f) {
+            const float inv = 1.0f / big;
+            const float xs = xr * inv, ys = yi * inv;
+            const float rn = rsqrtf(fmaf(xs, xs, ys * ys));
+            c = xs * rn;
+            sn = ys * rn;
+          }
+          re = mag * c;
+          im = mag * sn;
+        }
+        res[kc * FTP + fl] = re;
+        ims[kc * FTP + fl] = -im;  // sign folded here: acc += re * Br + (-im) * Bi
       }
-      re = mag * c;
-      im = mag * sn;
     }
-    res[idx] = re;
-    ims[idx] = im;
-  }
-  __syncthreads();
-  const int mo = mo0 + tid;
-  if (mo >= S) return;
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll 4
-  for (int fr = 0; fr < R; ++fr) {
-    const int tap = HOP * (R - 1 - fr);
-    const float* __restrict__ rr = res + tid + fr;
-    const float* __restrict__ ii = ims + tid + fr;
-#pragma unroll 8
-    for (int kb = 0; kb < BINS; ++kb) {
-      const float re = rr[kb * FTP], im = ii[kb * FTP];
-      const float4 cr = *reinterpret_cast<const float4*>(bre + kb * NFFT + tap);
-      const float4 ci = *reinterpret_cast<const float4*>(bim + kb * NFFT + tap);
-      a0 = fmaf(re, cr.x, a0); a0 = fmaf(-im, ci.x, a0);
-      a1 = fmaf(re, cr.y, a1); a1 = fmaf(-im, ci.y, a1);
-      a2 = fmaf(re, cr.z, a2); a2 = fmaf(-im, ci.z, a2);
-      a3 = fmaf(re, cr.w, a3); a3 = fmaf(-im, ci.w, a3);
+    __syncthreads();
+#pragma unroll 1
+    for (int kc = 0; kc < KC; ++kc) {
+      float xr[NF + 1], xi[NF + 1];
+      const float4* rp = reinterpret_cast<const float4*>(res + kc * FTP + tid * G);
+      const float4* ip = reinterpret_cast<const float4*>(ims + kc * FTP + tid * G);
+#pragma unroll
+      for (int q = 0; q < (NF + 1) / 4; ++q) {
+        const float4 a = rp[q], c = ip[q];
+        xr[4 * q] = a.x; xr[4 * q + 1] = a.y; xr[4 * q + 2] = a.z; xr[4 * q + 3] = a.w;
+        xi[4 * q] = c.x; xi[4 * q + 1] = c.y; xi[4 * q + 2] = c.z; xi[4 * q + 3] = c.w;
+      }
+      const float4* cr4 = reinterpret_cast<const float4*>(bre + (kb0 + kc) * NFFT);
+      const float4* ci4 = reinterpret_cast<const float4*>(bim + (kb0 + kc) * NFFT);
+#pragma unroll
+      for (int fr = 0; fr < R; ++fr) {
+        const float4 cr = cr4[R - 1 - fr], ci = ci4[R - 1 - fr];  // taps 4 (15 - fr) .. + 3
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          const float re = xr[g + fr], im = xi[g + fr];
+          acc[g][0] = fmaf(re, cr.x, acc[g][0]); acc[g][0] = fmaf(im, ci.x, acc[g][0]);
+          acc[g][1] = fmaf(re, cr.y, acc[g][1]); acc[g][1] = fmaf(im, ci.y, acc[g][1]);
+          acc[g][2] = fmaf(re, cr.z, acc[g][2]); acc[g][2] = fmaf(im, ci.z, acc[g][2]);
+          acc[g][3] = fmaf(re, cr.w, acc[g][3]); acc[g][3] = fmaf(im, ci.w, acc[g][3]);
+        }
+      }
     }
   }
-  float4 o4 = make_float4(tanhf(a0), tanhf(a1), tanhf(a2), tanhf(a3));
-  *reinterpret_cast<float4*>(out + (int64_t)b * S * HOP + (int64_t)mo * HOP) = o4;
+  float* __restrict__ ob = out + (int64_t)b * S * HOP;
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    const int mo = mo0 + tid * G + g;
+    if (mo < S)
+      *reinterpret_cast<float4*>(ob + (int64_t)mo * HOP) =
+          make_float4(tanhf(acc[g][0]), tanhf(acc[g][1]), tanhf(acc[g][2]), tanhf(acc[g][3]));
+  }
 }
 
 }  // namespace sty
@@ -294,15 +325,15 @@ extern "C" int sty_istft_head_pitched_fwd(const float* logamp, int64_t logamp_bs
   STY_REQUIRE(n_fft == 64 && hop == 4 && bins == 32,
               "istft_head: built for n_fft=64 hop=4 bins=32 (got %d %d %d)", n_fft, hop, bins);
   STY_REQUIRE(B > 0 && S > 0 && logamp_cs >= S && ri_cs >= S, "istft_head: bad shape");
-  constexpr int MT = 128, R = 16, FTP = (MT + R - 1 + 3) & ~3;
-  const size_t smem = ((size_t)2 * 32 * 64 + 2 * 32 * FTP) * sizeof(float);
-  auto kern = istft_head_kernel<64, 4, 32, MT>;
+  constexpr int MT = 128, G = 8, KC = 4, R = 16, FTP = (MT * G + R - 1 + 3) & ~3;
+  const size_t smem = ((size_t)2 * 32 * 64 + 2 * KC * FTP) * sizeof(float);
+  auto kern = istft_head_kernel<64, 4, 32, MT, G, KC>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr_set = true;
   }
-  dim3 grid(cdiv(S, MT), B);
+  dim3 grid(cdiv(S, MT * G), B);
   kern<<<grid, MT, smem, as_stream(stream)>>>(logamp, logamp_bs, logamp_cs, real, imag, ri_bs, ri_cs, basis_re,
                                               basis_im, out, S);
   STY_CHECK_LAUNCH("istft_head");
