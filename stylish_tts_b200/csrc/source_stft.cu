@@ -182,18 +182,14 @@ istft_head_kernel(const float* __restrict__ logamp, int64_t logamp_bs, int64_t l
   constexpr int FTP = (FT + 3) & ~3;
   constexpr int NF = G + R - 1;          // 23 frames per thread
   extern __shared__ __align__(16) float sm[];
-  float* bre = sm;                 // [BINS][NFFT]
-  float* bim = bre + BINS * NFFT;  // [BINS][NFFT]
-  float* res = bim + BINS * NFFT;  // [KC][FTP]
-  float* ims = res + KC * FTP;     // [KC][FTP]
+  float* bre = sm;               // [KC][NFFT]  basis rows of the current chunk of bins
+  float* bim = bre + KC * NFFT;  // [KC][NFFT]
+  float* res = bim + KC * NFFT;  // [KC][FTP]
+  float* ims = res + KC * FTP;   // [KC][FTP]
   const int b = blockIdx.y;
   const int tid = threadIdx.x;
   const int mo0 = blockIdx.x * MT * G;  // first output group of this CTA
   const int fbase = mo0 + R / 2 - (R - 1);
-  for (int i = tid; i < BINS * NFFT; i += MT) {
-    bre[i] = basis_re[i];
-    bim[i] = basis_im[i];
-  }
   float acc[G][HOP];
 #pragma unroll
   for (int g = 0; g < G; ++g)
@@ -201,27 +197,47 @@ istft_head_kernel(const float* __restrict__ logamp, int64_t logamp_bs, int64_t l
     for (int r = 0; r < HOP; ++r) acc[g][r] = 0.f;
 
   for (int kb0 = 0; kb0 < BINS; kb0 += KC) {
-    __syncthreads();  // previous chunk consumed (and, the first time, nothing to wait for but the basis stores)
+    __syncthreads();  // previous chunk consumed
+    for (int i = tid; i < KC * NFFT; i += MT) {
+      bre[i] = basis_re[kb0 * NFFT + i];
+      bim[i] = basis_im[kb0 * NFFT + i];
+    }
+    // staging: KC bins x FTP frames, several independent global loads in flight per thread
+    const float* __restrict__ la = logamp + (int64_t)b * logamp_bs + (int64_t)kb0 * logamp_cs;
+    const float* __restrict__ xr_ = real + (int64_t)b * ri_bs + (int64_t)kb0 * ri_cs;
+    const float* __restrict__ yi_ = imag + (int64_t)b * ri_bs + (int64_t)kb0 * ri_cs;
+    constexpr int NIT = (KC * FTP + MT - 1) / MT;
+    constexpr int UN = (NIT % 6 == 0) ? 6 : (NIT % 5 == 0 ? 5 : 4);
 #pragma unroll 1
-    for (int kc = 0; kc < KC; ++kc) {
-      const int kb = kb0 + kc;
-      const float* __restrict__ la = logamp + (int64_t)b * logamp_bs + (int64_t)kb * logamp_cs;
-      const float* __restrict__ xr_ = real + (int64_t)b * ri_bs + (int64_t)kb * ri_cs;
-      const float* __restrict__ yi_ = imag + (int64_t)b * ri_bs + (int64_t)kb * ri_cs;
-      for (int fl = tid; fl < FTP; fl += MT) {
+    for (int it0 = 0; it0 < NIT; it0 += UN) {
+      float lg[UN], vx[UN], vy[UN];
+      bool ok[UN];
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+        const int i = (it0 + u) * MT + tid;
+        const int kc = i / FTP, fl = i - kc * FTP;
         const int f = fbase + fl;
+        ok[u] = i < KC * FTP && fl < FT && f >= 0 && f <= S;
+        const int fs = min(max(f, 0), S - 1);  // replicate-pad of one frame (generator.py:784-785)
+        const int kcc = min(kc, KC - 1);
+        lg[u] = ok[u] ? la[(int64_t)kcc * logamp_cs + fs] : 0.f;
+        vx[u] = ok[u] ? xr_[(int64_t)kcc * ri_cs + fs] : 0.f;
+        vy[u] = ok[u] ? yi_[(int64_t)kcc * ri_cs + fs] : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+        const int i = (it0 + u) * MT + tid;
+        if (i >= KC * FTP) continue;
         float re = 0.f, im = 0.f;
-        if (fl < FT && f >= 0 && f <= S) {
-          const int fs = min(f, S - 1);  // replicate-pad of one frame (generator.py:784-785)
-          const float mag = expf(la[fs]);
+        if (ok[u]) {
+          const float mag = expf(lg[u]);
           // cos(atan2(y, x)) = x/|z|, sin(atan2(y, x)) = y/|z| (atan2(0, 0) = 0 -> cos 1, sin 0): one rsqrt
           // instead of atan2f + cosf + sinf; the operands are scaled first so x^2 + y^2 cannot over/underflow
-          const float xr = xr_[fs], yi = yi_[fs];
-          const float big = fmaxf(fabsf(xr), fabsf(yi));
+          const float big = fmaxf(fabsf(vx[u]), fabsf(vy[u]));
           float c = 1.f, sn = 0.f;
           if (big > 0.f) {
             const float inv = 1.0f / big;
-            const float xs = xr * inv, ys = yi * inv;
+            const float xs = vx[u] * inv, ys = vy[u] * inv;
             const float rn = rsqrtf(fmaf(xs, xs, ys * ys));
             c = xs * rn;
             sn = ys * rn;
@@ -229,8 +245,8 @@ istft_head_kernel(const float* __restrict__ logamp, int64_t logamp_bs, int64_t l
           re = mag * c;
           im = mag * sn;
         }
-        res[kc * FTP + fl] = re;
-        ims[kc * FTP + fl] = -im;  // sign folded here: acc += re * Br + (-im) * Bi
+        res[i] = re;      // i = kc * FTP + fl
+        ims[i] = -im;     // sign folded here: acc += re * Br + (-im) * Bi
       }
     }
     __syncthreads();
@@ -245,8 +261,8 @@ istft_head_kernel(const float* __restrict__ logamp, int64_t logamp_bs, int64_t l
         xr[4 * q] = a.x; xr[4 * q + 1] = a.y; xr[4 * q + 2] = a.z; xr[4 * q + 3] = a.w;
         xi[4 * q] = c.x; xi[4 * q + 1] = c.y; xi[4 * q + 2] = c.z; xi[4 * q + 3] = c.w;
       }
-      const float4* cr4 = reinterpret_cast<const float4*>(bre + (kb0 + kc) * NFFT);
-      const float4* ci4 = reinterpret_cast<const float4*>(bim + (kb0 + kc) * NFFT);
+      const float4* cr4 = reinterpret_cast<const float4*>(bre + kc * NFFT);
+      const float4* ci4 = reinterpret_cast<const float4*>(bim + kc * NFFT);
 #pragma unroll
       for (int fr = 0; fr < R; ++fr) {
         const float4 cr = cr4[R - 1 - fr], ci = ci4[R - 1 - fr];  // taps 4 (15 - fr) .. + 3
@@ -325,8 +341,8 @@ extern "C" int sty_istft_head_pitched_fwd(const float* logamp, int64_t logamp_bs
   STY_REQUIRE(n_fft == 64 && hop == 4 && bins == 32,
               "istft_head: built for n_fft=64 hop=4 bins=32 (got %d %d %d)", n_fft, hop, bins);
   STY_REQUIRE(B > 0 && S > 0 && logamp_cs >= S && ri_cs >= S, "istft_head: bad shape");
-  constexpr int MT = 128, G = 8, KC = 4, R = 16, FTP = (MT * G + R - 1 + 3) & ~3;
-  const size_t smem = ((size_t)2 * 32 * 64 + 2 * KC * FTP) * sizeof(float);
+  constexpr int MT = 128, G = 8, KC = 2, R = 16, FTP = (MT * G + R - 1 + 3) & ~3;  // 17.7 KB: 7 CTAs per SM
+  const size_t smem = ((size_t)2 * KC * 64 + 2 * KC * FTP) * sizeof(float);
   auto kern = istft_head_kernel<64, 4, 32, MT, G, KC>;
   static bool attr_set = false;
   if (!attr_set) {

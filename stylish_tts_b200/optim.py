@@ -40,12 +40,31 @@ class FlatAdamW:
             for p, o in zip(self.params, self.offsets):  # re-home the parameters inside the arena
                 self.flat[o:o + p.numel()].copy_(p.detach().reshape(-1))
                 p.data = self.flat[o:o + p.numel()].view(p.shape)
+        if self.world > 1:
+            # DDP broadcasts rank 0's parameters when it wraps a module (train_context.py:94-104 via accelerate);
+            # here the arena IS the parameters, so one broadcast keeps the replicas identical from step 0
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                dist.broadcast(self.flat, src=0 if process_group is None else dist.get_global_rank(process_group, 0),
+                               group=process_group)
         self.grad = torch.zeros(n, device=dev, dtype=torch.float32)
         self.m = torch.zeros(n, device=dev, dtype=torch.float32)
         self.v = torch.zeros(n, device=dev, dtype=torch.float32)
         self.step_count = 0
         # [lr, step] on the device: read by the update kernel, so a captured step keeps advancing (CUDA graphs)
         self.hyper = torch.tensor([lr, 0.0], device=dev, dtype=torch.float32)
+
+    def state_snapshot(self):
+        """copies of everything a step changes (parameters, moments, step / lr cell) — used to undo warm-up steps"""
+        return (self.flat.clone(), self.m.clone(), self.v.clone(), self.hyper.clone(), self.step_count)
+
+    def state_restore(self, snap):
+        flat, m, v, hyper, self.step_count = snap
+        self.flat.copy_(flat)
+        self.m.copy_(m)
+        self.v.copy_(v)
+        self.hyper.copy_(hyper)
+        L.param_epoch += 1
 
     def set_lr(self, lr: float):
         self.lr = lr

@@ -91,6 +91,16 @@ class GraphedAcousticStep:
                                                 lr_source=optimizer))
             return torch.stack(terms)
 
+        # the warm-up iterations are real launches (they fill the device-constant caches and size the allocator), but
+        # constructing the graph must not train: parameters, Adam moments, step / lr cells, module buffers (BatchNorm
+        # running statistics, spectral-norm u / v) and the discriminators' moving averages are restored afterwards
+        opts = [optimizer] + (list(adversarial[2].values()) if adversarial is not None else [])
+        snaps = [o.state_snapshot() for o in opts]
+        mods = [m for m in nets.values() if isinstance(m, torch.nn.Module)] if hasattr(nets, "values") else []
+        bufs = [(b, b.detach().clone()) for m in mods for b in m.buffers()]
+        ctl = getattr(adversarial[1], "lr_control", {}) if adversarial is not None else {}
+        ctl_snap = {k: c.last_loss.clone() for k, c in ctl.items()}
+        py_state = random.getstate()
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):  # also fills the device-constant caches: no host copies while capturing
@@ -98,6 +108,15 @@ class GraphedAcousticStep:
                 self.begin_step()
                 iteration()
         torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        with torch.no_grad():
+            for o, sn in zip(opts, snaps):
+                o.state_restore(sn)
+            for b, c in bufs:
+                b.copy_(c)
+            for k, c in ctl.items():
+                c.last_loss.copy_(ctl_snap[k])
+        random.setstate(py_state)
         torch.cuda.synchronize()
         torch.cuda.empty_cache()  # the warm-up's activations go back to the driver before the graph pool grows
         self.begin_step()
