@@ -341,9 +341,17 @@ def test_graphed_acoustic_step_matches_eager():
         opt = optim.FlatAdamW(list(sp.parameters()) + list(se.parameters()), lr=1e-4, world_size=1)
         losses = []
         if graphed:
-            step = GraphedAcousticStep(nets, fe, opt, batch, warmup=1, source_draws=draws)  # warm-up = iteration 1
-            for _ in range(3):
-                losses.append(step(batch).clone())
+            before = opt.flat.clone()
+            stats = [b.clone() for b in sp.buffers()]
+            step = GraphedAcousticStep(nets, fe, opt, batch, warmup=1, source_draws=draws)
+            # constructing the graph runs warm-up iterations but must not train: parameters, moments,
+            # step counter and module buffers are back where they were
+            assert torch.equal(opt.flat, before) and opt.step_count == 0 and int(opt.hyper[1].item()) == 0
+            assert float(opt.m.abs().max()) == 0 and all(torch.equal(a, b) for a, b in zip(stats, sp.buffers()))
+            for i in range(4):
+                loss = step(batch).clone()
+                if i >= 1:
+                    losses.append(loss)
         else:
             for i in range(4):
                 out = ts.acoustic_step(batch, nets, fe, source_draws=draws)
