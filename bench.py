@@ -373,16 +373,21 @@ def measure_train(args, dev, world, rank, barrier, steps, warmup, batch):
     adversarial = None
     if getattr(args, "adversarial", False):
         # the adversarial half of configs[2]: generator term on mrd0-2 + one discriminator stepped per batch
-        # (the waveform discriminator `disc` of the reference is not re-implemented: DESIGN.md)
         from stylish_tts_b200 import discriminator as D
         mrd = [nets[f"mrd{i}"].to(dev).train() for i in range(3)]
         disc_opts = {f"mrd{i}": optim.FlatAdamW(mrd[i].parameters(), lr=1e-4, betas=(0.85, 0.99), eps=1e-9,
                                                 weight_decay=1e-4, world_size=world) for i in range(3)}
+        wave_disc = None
+        if not getattr(args, "no_wave_disc", False):  # `disc`: ContextFreeDiscriminator on 1024-sample windows
+            wave_disc = nets["disc"].to(dev).train()
+            disc_opts["disc"] = optim.FlatAdamW(wave_disc.parameters(), lr=1e-4, betas=(0.85, 0.99), eps=1e-9,
+                                                weight_decay=1e-4, world_size=world)
         if getattr(args, "adversarial_two_pass", False):  # the reference's literal schedule: 2 evaluations per batch
-            adversarial = (D.GeneratorLoss(mrd0=mrd[0], mrd1=mrd[1], mrd2=mrd[2]),
-                           D.DiscriminatorLoss(mrd0=mrd[0], mrd1=mrd[1], mrd2=mrd[2], device=dev), disc_opts)
+            adversarial = (D.GeneratorLoss(mrd0=mrd[0], mrd1=mrd[1], mrd2=mrd[2], disc=wave_disc),
+                           D.DiscriminatorLoss(mrd0=mrd[0], mrd1=mrd[1], mrd2=mrd[2], disc=wave_disc, device=dev),
+                           disc_opts)
         else:  # one evaluation of mrd0-2 per batch feeds both halves (same numbers: tests/test_gpu_discriminators.py)
-            adv = D.AdversarialTerms(mrd0=mrd[0], mrd1=mrd[1], mrd2=mrd[2], device=dev)
+            adv = D.AdversarialTerms(mrd0=mrd[0], mrd1=mrd[1], mrd2=mrd[2], disc=wave_disc, device=dev)
             adversarial = (adv, adv, disc_opts)
     host = synth.speech_inputs(batch, args.tokens, seed=11 + rank)
     dur = torch.full((batch, args.tokens), 3.0)
@@ -469,7 +474,8 @@ def measure_train(args, dev, world, rank, barrier, steps, warmup, batch):
         "adversarial": ("generator term on mrd0-2 (LSGAN + TPRLS) + discriminator half-step (loss of all three, "
                         "mrd{random index} stepped, sqrt(B) scaling, gap-aware lr) from ONE evaluation of the "
                         "discriminators per batch (discriminator.AdversarialTerms); waveform discriminator `disc` "
-                        "not included") if adversarial else "off",
+                        + ("included (disc_weight 3, stepped every batch)" if "disc" in adversarial[2] else "not included"))
+        if adversarial else "off",
         "scope": "AcousticStep(use_predicted_pe=False, predict_audio=True): calculate_mel x2 + energy + alignment "
                  "+ speech_style_encoder + speech_predictor (train() mode: batch-stat BN, dropout sites and decoder box smoothing live) + "
                  "MultiSpectrogram x3 + mel & multi-phase losses (backwards_loss normalisation) + backward of "
@@ -831,6 +837,8 @@ def main():
                          "train: configs[2]/[4] as the line itself")
     ap.add_argument("--train-batch", type=int, default=32)
     ap.add_argument("--no-train", action="store_true", help="skip the train sub-measurement of --mode fwd")
+    ap.add_argument("--no-wave-disc", action="store_true",
+                    help="with --adversarial: leave the waveform discriminator `disc` out (mrd0-2 only)")
     ap.add_argument("--adversarial-two-pass", action="store_true",
                     help="with --adversarial: evaluate the discriminators twice per batch like the reference's schedule")
     ap.add_argument("--adversarial", action="store_true",

@@ -93,7 +93,8 @@ typedef struct sty_conv1d_args {
   const float* in_scale; /* (B,CI) or NULL */
   const float* in_shift; /* (B,CI) or NULL */
   const float* in_alpha; /* (CI): snake alpha of the prologue activation */
-  const float* in_mask;  /* (B,T) or NULL */
+  const float* in_mask;  /* (B,T) or NULL: x is multiplied by it BEFORE scale / shift / activation; a NEGATIVE value
+                            instead forces the activated value to 0 (zero gaps of end-to-end window layouts) */
   const float* out_mask; /* (B,T) or NULL */
   const float* out_alpha; /* (CO): snake alpha of the epilogue activation */
   float* out_sumsq;       /* (B,CO) accumulated with atomics, or NULL */
@@ -163,6 +164,13 @@ STY_API int sty_leaky_s2d_fwd(const float* x, float* y, int64_t N, int C, int W,
                               sty_stream_t stream);
 STY_API int sty_leaky_s2d_bwd(const float* dy, const float* x, float* dx, int64_t N, int C, int W, int s, float slope,
                               sty_stream_t stream);
+/* y[r, t] = (x ? x[r, t] : 1) * g[r] * mul over `rows` rows of T values (gate of ContextFreeDiscriminator,
+ * discriminator.py:167-168; with x = NULL the broadcast of a per-row value) */
+STY_API int sty_row_scale_fwd(const float* x, const float* g, float* y, int64_t rows, int T, float mul,
+                              sty_stream_t stream);
+/* y[r] = mul * sum_{j < P} x[r*P + j]  (P % 4 == 0): pooled value per window of the gapped waveform-discriminator
+ * layout (AdaptiveAvgPool1d(1), discriminator.py:139) */
+STY_API int sty_segment_sum_fwd(const float* x, float* y, int64_t rows, int P, float mul, sty_stream_t stream);
 STY_API int sty_sqdiff_sum_fwd(const float* x, int64_t n, float c, float* out, sty_stream_t stream);
 STY_API int64_t sty_tprls_workspace_bytes(void);
 STY_API int sty_tprls_fwd(const float* a, const float* b, int64_t n, void* workspace, float* sums, float* median,

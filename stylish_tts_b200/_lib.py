@@ -168,6 +168,8 @@ _SIGNATURES = {
     # adversarial losses (spectrogram discriminators, LSGAN / TPRLS)
     "sty_leaky_s2d_fwd": [_f32p, _f32p, _i64, _i32, _i32, _i32, _f32, _f32p],
     "sty_leaky_s2d_bwd": [_f32p, _f32p, _f32p, _i64, _i32, _i32, _i32, _f32, _f32p],
+    "sty_row_scale_fwd": [_f32p, _f32p, _f32p, _i64, _i32, _f32, _f32p],
+    "sty_segment_sum_fwd": [_f32p, _f32p, _i64, _i32, _f32, _f32p],
     "sty_sqdiff_sum_fwd": [_f32p, _i64, _f32, _f32p, _f32p],
     "sty_tprls_fwd": [_f32p, _f32p, _i64, _f32p, _f32p, _f32p, _f32p],
     "sty_tprls_bwd": [_f32p, _f32p, _i64, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p],

@@ -49,6 +49,7 @@ __device__ __forceinline__ float snake_dalpha(float a, float inv_alpha, const Sn
 }
 
 __device__ __forceinline__ float prologue_value(float xv, float m, float sc, float sh, int act, float al) {
+  if (m < 0.f) return 0.f;  // negative mask value: zero AFTER the prologue (gapped layouts)
   float w = fmaf(xv * m, sc, sh);
   if (act == STY_ACT_SNAKE) return fmaf(1.f / al, sin_sq(al * w), w);
   return act_apply(w, act);

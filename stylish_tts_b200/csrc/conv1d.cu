@@ -88,7 +88,7 @@ conv1d_kernel(const sty_conv1d_args p, const int ci_chunk, const int xtp) {
             } else if (in_act != STY_ACT_NONE) {
               w = act_apply(w, in_act);
             }
-            v[u] = ok ? w : 0.f;
+            v[u] = (ok && m >= 0.f) ? w : 0.f;  // negative mask value: zero AFTER the prologue
           }
         }
 #pragma unroll

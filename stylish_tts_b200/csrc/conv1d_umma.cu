@@ -452,7 +452,7 @@ conv1d_umma_kernel(const sty_conv1d_args p, const UmmaPlan pl, const __grid_cons
                   } else if constexpr (IN_MODE == 2) {
                     w = w > 0.f ? w : 0.2f * w;
                   }
-                  v[u][j] = ok ? w : 0.f;
+                  v[u][j] = (ok && m >= 0.f) ? w : 0.f;  // negative mask value: zero AFTER the prologue
                 }
               }
               uint32_t h[4], l[4];

@@ -36,6 +36,30 @@ __global__ void leaky_s2d_bwd_kernel(const float* __restrict__ dy, const float* 
   }
 }
 
+// y[r, t] = (x ? x[r, t] : 1) * g[r] * mul  — the squeeze-excite style gate of ContextFreeDiscriminator
+// (discriminator.py:167-168: x * attn) and the broadcast of a per-row gradient
+__global__ void row_scale_kernel(const float* __restrict__ x, const float* __restrict__ g, float* __restrict__ y,
+                                 int64_t total, int T, float mul) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const float s = g[i / T] * mul;
+    y[i] = x ? x[i] * s : s;
+  }
+}
+
+// y[r] = mul * sum_{j < P} x[r*P + j]: pooled value of short segments (AdaptiveAvgPool1d over one window of the
+// gapped waveform-discriminator layout); one thread per segment, P % 4 == 0
+__global__ void segment_sum_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t rows, int P, float mul) {
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x) {
+    const float4* p = reinterpret_cast<const float4*>(x + r * P);
+    float acc = 0.f;
+    for (int j = 0; j < P / 4; ++j) {
+      const float4 v = p[j];
+      acc += (v.x + v.y) + (v.z + v.w);
+    }
+    y[r] = acc * mul;
+  }
+}
+
 // ---- sums of squares: out[0] += sum (c - x)^2
 __global__ void sqdiff_sum_kernel(const float* __restrict__ x, int64_t n, float c, float* __restrict__ out) {
   float acc = 0.f;
@@ -175,6 +199,23 @@ extern "C" int sty_leaky_s2d_bwd(const float* dy, const float* x, float* dx, int
   const int64_t total = N * C * W;
   leaky_s2d_bwd_kernel<<<blocks_for(total), 256, 0, as_stream(stream)>>>(dy, x, dx, total, C, W, W2, s, slope);
   STY_CHECK_LAUNCH("leaky_s2d_bwd");
+  return STY_OK;
+}
+
+extern "C" int sty_row_scale_fwd(const float* x, const float* g, float* y, int64_t rows, int T, float mul,
+                                 sty_stream_t stream) {
+  STY_REQUIRE(g && y && rows > 0 && T > 0, "row_scale: bad argument");
+  const int64_t total = rows * T;
+  row_scale_kernel<<<blocks_for(total), 256, 0, as_stream(stream)>>>(x, g, y, total, T, mul);
+  STY_CHECK_LAUNCH("row_scale");
+  return STY_OK;
+}
+
+extern "C" int sty_segment_sum_fwd(const float* x, float* y, int64_t rows, int P, float mul, sty_stream_t stream) {
+  STY_REQUIRE(x && y && rows > 0 && P > 0 && P % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0,
+              "segment_sum: bad argument (P %% 4 == 0, 16-byte aligned rows)");
+  segment_sum_kernel<<<blocks_for(rows), 256, 0, as_stream(stream)>>>(x, y, rows, P, mul);
+  STY_CHECK_LAUNCH("segment_sum");
   return STY_OK;
 }
 

@@ -120,7 +120,7 @@ __device__ __forceinline__ void stage_side_t(const SideDesc& S, const sty_conv1d
           } else if (act != STY_ACT_NONE) {
             w = act_apply(w, act);
           }
-          v[u][j] = (ok && (chan_full || S.c0 + cl + j < S.C)) ? w : 0.f;
+          v[u][j] = (ok && m >= 0.f && (chan_full || S.c0 + cl + j < S.C)) ? w : 0.f;  // m < 0: zero after the prologue
         }
       } else {
         const float mm = m * p.out_scale;

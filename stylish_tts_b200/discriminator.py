@@ -12,8 +12,7 @@ kernel produces in the same pass (``sty_leaky_s2d``).
 ``GeneratorLoss`` / ``DiscriminatorLoss`` mirror train/losses.py:166-373 for the spectrogram discriminators:
 LSGAN terms + TPRLS (median by radix select on the device, masked sums; no ``.item()``, no boolean-mask gather),
 the moving average that drives the discriminator learning rate stays in device memory (``optim.DiscriminatorLR``).
-The waveform discriminator (``disc``: ContextFreeDiscriminator) is accepted as an optional external module — it is
-not re-implemented here (out-of-scope table).
+``ContextFreeDiscriminator`` is the drop-in for the waveform discriminator ``disc`` (discriminator.py:119-175).
 """
 from __future__ import annotations
 
@@ -289,6 +288,188 @@ class PitchDiscriminator(nn.Module):
         return result, []
 
 
+# ------------------------------------------------------------------------------ waveform discriminator (`disc`)
+class SegmentScaleFn(Function):
+    """y[b, c, w*P + j] = x[b, c, w*P + j] * g[b, c, w]  (the gate of ContextFreeDiscriminator, discriminator.py:167-168,
+    on windows laid end to end with pitch P)"""
+
+    @staticmethod
+    def forward(ctx, x, g, P):
+        x, g = x.contiguous(), g.contiguous()
+        y = torch.empty_like(x)
+        L.call("sty_row_scale_fwd", x.data_ptr(), g.data_ptr(), y.data_ptr(), g.numel(), P, 1.0, L.stream_ptr())
+        ctx.save_for_backward(x, g)
+        ctx.P = P
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, g = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = dg = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            L.call("sty_row_scale_fwd", dy.data_ptr(), g.data_ptr(), dx.data_ptr(), g.numel(), ctx.P, 1.0, L.stream_ptr())
+        if ctx.needs_input_grad[1]:
+            dg = torch.empty_like(g)
+            L.call("sty_row_dot", dy.data_ptr(), x.data_ptr(), dg.data_ptr(), g.numel(), ctx.P, L.stream_ptr())
+        return dx, dg, None
+
+
+class SegmentMeanFn(Function):
+    """(B, C, W*P) with Tw data positions per window (zeros in the gaps) -> per-window mean (B, C, W)
+    (AdaptiveAvgPool1d(1), discriminator.py:139)"""
+
+    @staticmethod
+    def forward(ctx, x, P, Tw):
+        x = x.contiguous()
+        B, Cc, T_ = x.shape
+        y = torch.empty((B, Cc, T_ // P), device=x.device, dtype=torch.float32)
+        L.call("sty_segment_sum_fwd", x.data_ptr(), y.data_ptr(), y.numel(), P, 1.0 / Tw, L.stream_ptr())
+        ctx.meta = (x.shape, P, Tw)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        shape, P, Tw = ctx.meta
+        g = g.contiguous()
+        dx = torch.empty(shape, device=g.device, dtype=torch.float32)  # gap positions: ignored by the masked producer
+        L.call("sty_row_scale_fwd", None, g.data_ptr(), dx.data_ptr(), g.numel(), P, 1.0 / Tw, L.stream_ptr())
+        return dx, None, None
+
+
+def strided_weight(w: torch.Tensor, s: int) -> torch.Tensor:
+    """(Co, C, K) stride-s pad-K//2 Conv1d kernel -> (Co, C*s, K') stride-1 'same' kernel on the space-to-depth input
+    xs[c*s + p][u] = x[c][s*u + p]:  y[u] = sum_k w[k] x[s*u + k - pad] with k - pad = s*j + p, |j| <= J = ceil(pad/s).
+    Plain tensor ops, so autograd carries the gradient back to the (Co, C, K) parameter."""
+    if s == 1:
+        return w
+    Co, Cc, K = w.shape
+    pad = K // 2
+    J = -(-pad // s)
+    Kp = 2 * J + 1
+    left = s * J - pad
+    wp = torch.nn.functional.pad(w, (left, s * Kp - K - left))
+    return wp.reshape(Co, Cc, Kp, s).permute(0, 1, 3, 2).reshape(Co, Cc * s, Kp)
+
+
+def grouped_as_dense(w: torch.Tensor, groups: int) -> torch.Tensor:
+    """(Co, Ci/g, K) grouped kernel -> block-diagonal (Co, Ci, K): the grouped layers are 1-8 % of the discriminator's
+    MACs, so they run as dense tensor-core convs on a weight with zero off-diagonal blocks"""
+    if groups == 1:
+        return w
+    Co, Cg, K = w.shape
+    eye = torch.eye(groups, device=w.device, dtype=w.dtype).view(groups, 1, groups, 1, 1)
+    return (w.view(groups, Co // groups, 1, Cg, K) * eye).reshape(Co, groups * Cg, K)
+
+
+class _CFBlock(nn.Module):
+    """parameter holder with the reference's names (ContextFreeBlock, discriminator.py:94-116: net.0 conv, net.1 BN)"""
+
+    def __init__(self, ci, co, *, kernel, stride=1, groups=1, bias=False):
+        super().__init__()
+        self.net = nn.Sequential(nn.Conv1d(ci, co, kernel, stride, kernel // 2, groups=groups, bias=bias),
+                                 nn.BatchNorm1d(co), nn.GELU())
+        self.kernel, self.stride, self.groups = kernel, stride, groups
+
+
+class ContextFreeDiscriminator(nn.Module):
+    """Drop-in for the reference's waveform discriminator `disc` (discriminator.py:119-175): 1024-sample windows (hop
+    512) -> four strided Conv1d + BatchNorm + GELU blocks -> squeeze-excite gate -> temporal (k7, k3; 8 groups) and
+    'spectral' (k1; 8 groups) branches -> fusion -> 1x1 head; forward(x (B, L)) -> ([(B, windows*16)], []).
+
+    Every block is `conv -> BN -> GELU`; BN + GELU run as the PROLOGUE of the consuming convolution (batch statistics
+    from `sty_row_moments`, their backward terms from `sty_prologue_bwd_*`), strided layers run as stride-1
+    tensor-core convs on the space-to-depth input with phase-pooled BatchNorm statistics, grouped layers as
+    block-diagonal dense convs.  The torch children only own the parameters / buffers (same state-dict keys).
+
+    Layout: the reference folds the windows into the batch axis — (B*470, C, 16) at the last level, millions of
+    16-element rows.  Here the windows of an utterance lie END TO END on the time axis with a zero gap after each one
+    (pitch 1280 / 320 / 80 / 40 / 20 for 1024 / 256 / 64 / 32 / 16 data positions: the pitch divides by every stride, so
+    space-to-depth keeps windows aligned, and the gap is wider than every kernel's reach), i.e. (B, C, 470*pitch): the
+    long-row regime all conv / norm kernels are built for.  Producers keep the gaps zero (`out_mask`), consumers mask
+    their prologue (`in_mask`), BatchNorm counts only the data positions (`bn_frac` = 0.8)."""
+
+    PITCH = (1280, 320, 80, 40, 20)
+    DATA = (1024, 256, 64, 32, 16)
+
+    def __init__(self):
+        super().__init__()
+        d = 64
+        self.conv = nn.ModuleList([_CFBlock(1, d, kernel=11, stride=4), _CFBlock(d, 2 * d, kernel=11, stride=4),
+                                   _CFBlock(2 * d, 4 * d, kernel=7, stride=2), _CFBlock(4 * d, 4 * d, kernel=5, stride=2)])
+        self.attn = nn.Sequential(nn.AdaptiveAvgPool1d(1), nn.Conv1d(4 * d, 4 * d, 1), nn.Sigmoid())
+        self.temporal = nn.Sequential(_CFBlock(4 * d, 4 * d, kernel=7, groups=8, bias=True),
+                                      _CFBlock(4 * d, 4 * d, kernel=3, groups=8, bias=True))
+        self.spectral = nn.Sequential(_CFBlock(4 * d, 12 * d, kernel=1, groups=8, bias=True),
+                                      _CFBlock(12 * d, 4 * d, kernel=1, groups=8, bias=True))
+        self.fusion = _CFBlock(8 * d, 4 * d, kernel=1, bias=True)
+        self.last = nn.Sequential(nn.Conv1d(4 * d, 8 * d, 1, 1), nn.ReLU(), nn.Conv1d(8 * d, 1, 1))
+        self._masks = {}
+
+    def _mask(self, B, windows, level, device):
+        key = (B, windows, level, str(device))
+        if key not in self._masks:
+            pos = torch.arange(windows * self.PITCH[level], device=device) % self.PITCH[level]
+            self._masks[key] = (pos < self.DATA[level]).float().unsqueeze(0).expand(B, -1).contiguous()
+        return self._masks[key]
+
+    def _bn(self, *blocks, group=1):
+        """prologue arguments: BatchNorm + GELU of `blocks` (side by side on the channel axis) ahead of the next conv"""
+        from ._lib import ACT_GELU
+
+        bns = [b.net[1] for b in blocks]
+        if self.training:
+            with torch.no_grad():
+                for bn in bns:
+                    bn.num_batches_tracked += 1
+        cat = lambda ts: ts[0] if len(ts) == 1 else torch.cat(ts)
+        return dict(bn_w=cat([bn.weight for bn in bns]), bn_b=cat([bn.bias for bn in bns]), norm="batch",
+                    in_act=ACT_GELU, bn_group=group, bn_eval=not self.training, eps=bns[0].eps,
+                    bn_frac=self.DATA[0] / self.PITCH[0],
+                    bn_buffers=[(bn.running_mean, bn.running_var) for bn in bns])
+
+    def forward(self, x):
+        from . import train_ops as T
+        from ._lib import ACT_RELU
+
+        if not x.is_cuda:
+            raise RuntimeError("stylish_tts_b200: ContextFreeDiscriminator needs CUDA tensors (no CPU fallback)")
+        B = x.shape[0]
+        win = x.to(torch.float32).unfold(1, 1024, 512)                       # (B, W, 1024), discriminator.py:160
+        W = win.shape[1]
+        h = torch.nn.functional.pad(win, (0, self.PITCH[0] - self.DATA[0])).reshape(B, 1, W * self.PITCH[0])
+        prev = None
+        for lvl, blk in enumerate(self.conv, start=1):                        # conv -> BN -> GELU, strides 4 4 2 2
+            s, m = blk.stride, self._mask(B, W, lvl, x.device)
+            xs = LeakyS2dFn.apply(h, s, 1.0)                                   # space-to-depth only (slope 1)
+            w = strided_weight(blk.net[0].weight, s)
+            if prev is None:
+                h = T.conv(xs, w, None, out_mask=m)
+            else:
+                h = T.conv(xs, w, None, in_mask=m, in_mask_post=True, out_mask=m, **self._bn(prev, group=s))
+            prev = blk
+        m = self._mask(B, W, 4, x.device)
+        P, Tw = self.PITCH[4], self.DATA[4]
+        mk = dict(in_mask=m, in_mask_post=True, out_mask=m)
+        # x3 = GELU(BN(h)) is needed as a tensor (pooled, gated, read by two branches): identity 1x1 conv carries it
+        eye = torch.eye(h.shape[1], device=h.device, dtype=torch.float32).unsqueeze(-1)
+        x3 = T.conv(h, eye, None, **mk, **self._bn(prev))
+        gate = torch.sigmoid(T.conv(SegmentMeanFn.apply(x3, P, Tw), self.attn[1].weight, self.attn[1].bias))
+        xg = SegmentScaleFn.apply(x3, gate, P)                                 # discriminator.py:167-168
+        branches = []
+        for seq in (self.temporal, self.spectral):
+            b0, b1 = seq[0], seq[1]
+            y0 = T.conv(xg, grouped_as_dense(b0.net[0].weight, b0.groups), b0.net[0].bias, out_mask=m)
+            branches.append(T.conv(y0, grouped_as_dense(b1.net[0].weight, b1.groups), b1.net[0].bias, **mk,
+                                   **self._bn(b0)))
+        f = T.conv(torch.cat(branches, 1), self.fusion.net[0].weight, self.fusion.net[0].bias, **mk,
+                   **self._bn(self.temporal[1], self.spectral[1]))
+        l0 = T.conv(f, self.last[0].weight, self.last[0].bias, **mk, **self._bn(self.fusion))
+        out = T.conv(l0, self.last[2].weight, self.last[2].bias, in_act=ACT_RELU)     # (B, 1, W*P)
+        return [out.view(B, W, P)[:, :, :Tw].reshape(B, -1)], []               # "(b t) c f -> b (t c f)"
+
+
 # ---------------------------------------------------------------------------------------------- losses
 class _SqMeanFn(Function):
     """mean((c - x)^2) with the reduction on the device kernel (losses.py:257-259,341)"""
@@ -381,18 +562,19 @@ class GeneratorLoss(nn.Module):
         return lsgan_generator(gen) + tprls_generator(real, gen)
 
     def forward(self, *, target_list, pred_list, target_audio=None, pred_audio=None):
-        req = [p.requires_grad for m in self.mrd for p in m.parameters()]
-        for m in self.mrd:
+        models = list(self.mrd) + ([self.disc] if self.disc is not None else [])
+        req = [p.requires_grad for m in models for p in m.parameters()]
+        for m in models:
             m.requires_grad_(False)
         try:
             loss = sum(self._one(m, t, p) for m, t, p in zip(self.mrd, target_list, pred_list))
+            if self.disc is not None:
+                loss = loss + DISC_WEIGHT * self._one(self.disc, target_audio, pred_audio)
         finally:
             it = iter(req)
-            for m in self.mrd:
+            for m in models:
                 for p in m.parameters():
                     p.requires_grad_(next(it))
-        if self.disc is not None:
-            loss = loss + DISC_WEIGHT * self._one(self.disc, target_audio, pred_audio)
         return loss
 
 

@@ -537,7 +537,7 @@ class Synthesizer(nn.Module):
 
 
 HOT_PATH_KEYS = ("speech_predictor", "duration_predictor", "pitch_energy_predictor", "speech_style_encoder",
-                 "pe_style_encoder", "duration_style_encoder", "mrd0", "mrd1", "mrd2", "pitch_disc", "dur_disc")
+                 "pe_style_encoder", "duration_style_encoder", "disc", "mrd0", "mrd1", "mrd2", "pitch_disc", "dur_disc")
 ALL_KEYS = ("text_aligner", "duration_predictor", "pitch_energy_predictor", "speech_predictor",
             "disc", "mrd0", "mrd1", "mrd2", "speech_style_encoder", "pe_style_encoder",
             "duration_style_encoder", "pitch_disc", "dur_disc")
@@ -576,10 +576,11 @@ def build_model(model_config, *, extra: Dict[str, nn.Module] | None = None) -> M
     nets["pe_style_encoder"] = PitchStyleEncoder(se.n_mels, model_config.style_dim, se.max_channels,
                                                  se.skip_downsample,
                                                  coarse_multiplier=model_config.coarse_multiplier)
-    # discriminators of the adversarial terms (models.py:44-46,78-83).  `disc` (ContextFreeDiscriminator, waveform
-    # windows) and `text_aligner` are not re-implemented: pass them through `extra` when needed.
-    from .discriminator import PitchDiscriminator, SpecDiscriminator
+    # discriminators of the adversarial terms (models.py:43-46,78-83).  `text_aligner` is not re-implemented: pass it
+    # through `extra` when needed.
+    from .discriminator import ContextFreeDiscriminator, PitchDiscriminator, SpecDiscriminator
 
+    nets["disc"] = ContextFreeDiscriminator()
     for key in ("mrd0", "mrd1", "mrd2"):
         nets[key] = SpecDiscriminator()
     nets["pitch_disc"] = PitchDiscriminator(dim_in=2, dim_hidden=64, kernel=21)

@@ -129,7 +129,10 @@ class GraphedAcousticStep:
         optimizer.step_count -= 1  # capturing launches nothing: only the warm-up iterations were real updates
         self.graphs, self.loss_bufs = [self.graph], [self.losses]
         if adversarial is not None:
+            always = [adversarial[2]["disc"]] if "disc" in adversarial[2] else []  # `disc` is stepped with every index
             adversarial[2]["mrd0"].step_count -= 1
+            for o in always:
+                o.step_count -= 1
             for idx in (1, 2):  # one graph per stepped discriminator, same memory pool (replayed one at a time);
                 # nothing index-specific is allocated lazily (all three discriminators run in every iteration)
                 self.begin_step()
@@ -139,6 +142,8 @@ class GraphedAcousticStep:
                     buf = iteration(idx)
                 optimizer.step_count -= 1
                 adversarial[2][f"mrd{idx}"].step_count -= 1
+                for o in always:
+                    o.step_count -= 1
                 self.graphs.append(g)
                 self.loss_bufs.append(buf)
 
@@ -157,5 +162,7 @@ class GraphedAcousticStep:
         self.opt.step_count += 1
         if self.adversarial is not None:
             self.adversarial[2][f"mrd{idx}"].step_count += 1
+            if "disc" in self.adversarial[2]:
+                self.adversarial[2]["disc"].step_count += 1
         L.param_epoch += 1
         return self.loss_bufs[idx]

@@ -98,6 +98,25 @@ def prologue_bwd(dxp, x, *, scale, shift, alpha, mask, act, center=None, want_su
     return sums, dx
 
 
+_POST_MASKS = {}
+
+
+def _post_mask(mask):
+    """binary (B,T) mask -> the kernels' "zero AFTER the prologue" encoding (1 keep, -1 force 0).  The backward keeps
+    using the binary mask: for 0/1 masks d/dx [m act(s x + b)] and d/dx [act(s m x + b)] coincide wherever m = 1 and
+    are both 0 wherever m = 0."""
+    if mask is None:
+        return None
+    key = (mask.data_ptr(), tuple(mask.shape))
+    hit = _POST_MASKS.get(key)
+    if hit is None or hit[0] is not mask:
+        if len(_POST_MASKS) > 64:
+            _POST_MASKS.clear()
+        hit = (mask, (2.0 * mask - 1.0).contiguous())
+        _POST_MASKS[key] = hit
+    return hit[1]
+
+
 class ConvFn(Function):
     """Conv1d / Linear with the fused prologue (mask, InstanceNorm- or BatchNorm-affine, activation) and
     epilogue (bias, mask, residual, pixel shuffle) of ``sty_conv1d_fwd``.
@@ -124,32 +143,54 @@ class ConvFn(Function):
             scale = ((1.0 + gb[:, :CI]) * rstd).contiguous()
             shift = (gb[:, CI:] - mean * scale).contiguous()
         elif norm == "batch":
+            # bn_group = s: the conv input is a space-to-depth view (channel c*s + p = phase p of channel c), the
+            # BatchNorm it carries belongs to the original channels — statistics are pooled over the s phases and
+            # bn_w / bn_b / the running buffers have CI / s entries
+            # bn_frac < 1: only that fraction of the T positions is data (zero gaps between windows laid end to end,
+            # kept zero by the producers' out_mask): sums run over everything, counts over the valid positions
+            grp, frac = cfg.get("bn_group", 1), cfg.get("bn_frac", 1.0)
             stats = cfg.get("bn_buffers")
+            if stats is not None and not isinstance(stats, list):
+                stats = [stats]  # several BatchNorm modules side by side (concatenated channels)
             if cfg.get("bn_eval"):
                 # module.eval() under autograd: nn.BatchNorm1d normalises with the running statistics and
                 # leaves them untouched; they are constants of the backward (no batch-statistics terms)
-                mean_c, var_c = stats[0].detach().clone(), stats[1].detach().clone()
+                mean_c = torch.cat([st[0].detach() for st in stats]).clone()
+                var_c = torch.cat([st[1].detach() for st in stats]).clone()
                 stats = None
             else:
                 m_bc, v_bc = row_moments(x)
                 mean_c = m_bc.mean(0)
-                var_c = (v_bc + m_bc * m_bc).mean(0) - mean_c * mean_c
+                ex2_c = (v_bc + m_bc * m_bc).mean(0)
+                if grp > 1:
+                    mean_c = mean_c.view(-1, grp).mean(1)
+                    ex2_c = ex2_c.view(-1, grp).mean(1)
+                if frac != 1.0:
+                    mean_c, ex2_c = mean_c / frac, ex2_c / frac
+                var_c = ex2_c - mean_c * mean_c
+            if stats is not None:  # running statistics, momentum 0.1, unbiased variance (nn.BatchNorm1d)
+                n = B * T * grp * frac
+                o = 0
+                for rm, rv in stats:
+                    k = rm.numel()
+                    rm.mul_(0.9).add_(mean_c[o:o + k], alpha=0.1)
+                    rv.mul_(0.9).add_(var_c[o:o + k] * (n / max(n - 1, 1)), alpha=0.1)
+                    o += k
             rstd_c = torch.rsqrt(var_c + eps)
             sc = bn_w * rstd_c
+            sh = bn_b - mean_c * sc
+            if grp > 1:
+                mean_c, rstd_c, sc, sh = (t.repeat_interleave(grp) for t in (mean_c, rstd_c, sc, sh))
             scale = sc.unsqueeze(0).expand(B, CI).contiguous()
-            shift = (bn_b - mean_c * sc).unsqueeze(0).expand(B, CI).contiguous()
+            shift = sh.unsqueeze(0).expand(B, CI).contiguous()
             mean, rstd = mean_c.unsqueeze(0).expand(B, CI).contiguous(), rstd_c
-            if stats is not None:  # running statistics, momentum 0.1, unbiased variance (nn.BatchNorm1d)
-                n = B * T
-                stats[0].mul_(0.9).add_(mean_c, alpha=0.1)
-                stats[1].mul_(0.9).add_(var_c * (n / max(n - 1, 1)), alpha=0.1)
         elif cfg.get("in_scale") is not None:
             raise ValueError("ConvFn: constant in_scale is not supported; use a norm mode")
         cw = ConvW(w.detach(), None if bias is None else bias.detach())
         al = None if alpha is None else alpha.detach().contiguous()
         y = conv1d(x, cw, dil=dil, res=res, in_scale=scale, in_shift=shift, in_alpha=al, in_act=in_act,
-                   in_mask=in_mask, out_mask=out_mask, shuffle=shuffle, out_scale=out_scale,
-                   res_scale=res_scale, umma=umma)
+                   in_mask=_post_mask(in_mask) if cfg.get("in_mask_post") else in_mask, out_mask=out_mask, shuffle=shuffle, out_scale=out_scale,
+                   res_scale=res_scale, umma=umma, wide=cfg.get("wide", False))
         ctx.save_for_backward(x, w, gb, al, scale, shift, mean, rstd, bn_w)
         ctx.cfg, ctx.has_bias, ctx.has_res = cfg, bias is not None, res is not None
         return y
@@ -175,11 +216,15 @@ class ConvFn(Function):
         d_w = None
         if need[1]:
             d_w = wgrad(x, g, K, dil, in_scale=scale, in_shift=shift, in_alpha=al, in_act=in_act,
-                        in_mask=in_mask, out_mask=out_mask, out_scale=out_scale, umma=umma)
+                        in_mask=_post_mask(in_mask) if cfg.get("in_mask_post") else in_mask, out_mask=out_mask,
+                        out_scale=out_scale, umma=umma)
         d_x = d_gb = d_alpha = d_bnw = d_bnb = None
         want_stats = norm is not None or (al is not None and need[4])
         if need[0] or want_stats:
-            dxp = conv1d(g, transposed_weight(w), dil=dil, in_mask=out_mask, out_scale=out_scale, umma=umma)
+            # in_mask_post: y = m * act(s x + b), so the shift / scale statistics only see the data positions — the
+            # data gradient is zeroed in the gaps before the prologue backward sums it
+            dxp = conv1d(g, transposed_weight(w), dil=dil, in_mask=out_mask, out_scale=out_scale, umma=umma,
+                         out_mask=in_mask if cfg.get("in_mask_post") else None, wide=cfg.get("wide", False))
             plain = scale is None and in_mask is None and in_act == ACT_NONE
             if plain:
                 d_x = dxp
@@ -196,9 +241,15 @@ class ConvFn(Function):
                     c0 = (-scale * s0 / T - c1 * mean).contiguous()
                 elif norm == "batch":
                     s0, s1 = sums[:, :, 0].sum(0), sums[:, :, 1].sum(0)
+                    grp = cfg.get("bn_group", 1)
+                    if grp > 1:  # pooled statistics: the sums of a channel's phases belong together
+                        s0 = s0.view(-1, grp).sum(1).repeat_interleave(grp)
+                        s1 = s1.view(-1, grp).sum(1).repeat_interleave(grp)
                     d_bnw, d_bnb = s1 * rstd, s0
+                    if grp > 1:
+                        d_bnw, d_bnb = d_bnw.view(-1, grp)[:, 0].contiguous(), d_bnb.view(-1, grp)[:, 0].contiguous()
                     if not cfg.get("bn_eval"):
-                        n = B * T
+                        n = B * T * grp * cfg.get("bn_frac", 1.0)
                         sc = scale[0]
                         c1c = -(sc * rstd * rstd) * s1 / n
                         c0c = -sc * s0 / n - c1c * mean[0]

@@ -362,3 +362,127 @@ def test_tail_kernels_vs_torch_fp64(B, bins, W, kind):
     assert rel_l2(hd.grad[:, 1:-1], h64.grad[:, 1:-1]) < 2e-6, rel_l2(hd.grad[:, 1:-1], h64.grad[:, 1:-1])
     assert rel_l2(wd.grad, w64.grad) < 5e-6, rel_l2(wd.grad, w64.grad)
     assert rel_l2(bd.grad, b64.grad) < 5e-6, rel_l2(bd.grad, b64.grad)
+
+
+def _cfd(seed=0):
+    g = gold()
+    m = D.ContextFreeDiscriminator()
+    m.load_state_dict(state_dict_from_table(g["disc_names"], g["disc_shapes"]), strict=True)
+    return m
+
+
+def test_context_free_discriminator_vs_reference_golden():
+    """`disc` (ContextFreeDiscriminator, discriminator.py:119-175) against the output of the UNMODIFIED reference in
+    train() mode (batch-statistics BatchNorm), same state dict"""
+    g = gold()
+    _, _, ta, _ = inputs()
+    m = _cfd().to(dev()).train()
+    with torch.no_grad():
+        outs, fmaps = m(ta.to(dev()))
+    assert fmaps == [] and len(outs) == 1
+    ref = torch.from_numpy(g["disc_out"])
+    assert outs[0].shape == ref.shape and rel_l2(outs[0], ref) < 2e-4, rel_l2(outs[0], ref)
+
+
+@pytest.mark.parametrize("tensor_cores", [True, False])
+@pytest.mark.parametrize("training", [True, False])
+def test_context_free_discriminator_vs_fp64_oracle(tensor_cores, training, monkeypatch):
+    """scores, input gradient and every parameter gradient against oracle/disc_oracle.py in fp64; train() mode
+    (batch statistics, running buffers updated like nn.BatchNorm1d) and eval() mode (running statistics)"""
+    from stylish_tts_b200 import engine as E
+
+    monkeypatch.setattr(E, "USE_UMMA", tensor_cores)
+    pass
+    m = _cfd()
+    with torch.no_grad():  # non-trivial running statistics for the eval() case
+        for k, b in m.named_buffers():
+            if k.endswith("running_mean"):
+                b.copy_(0.05 * torch.randn(b.shape, generator=torch.Generator().manual_seed(len(k))))
+            if k.endswith("running_var"):
+                b.copy_(0.5 + torch.rand(b.shape, generator=torch.Generator().manual_seed(len(k) + 1)))
+    gen = torch.Generator().manual_seed(3)
+    x = 0.2 * torch.randn(3, 1024 + 512 * 6, generator=gen)
+    names = {k for k, _ in m.named_parameters()}
+    sd64 = {k: (v.detach().double().requires_grad_(True) if k in names else v.detach().double().clone()
+                if v.is_floating_point() else v.clone()) for k, v in m.state_dict().items()}
+    x64 = x.double().requires_grad_(True)
+    ref = do.context_free_discriminator(sd64, x64, bn_training=training)[0]
+    cot = torch.randn(ref.shape, generator=gen).double()
+    (ref * cot).sum().backward()
+    md = m.to(dev())
+    md.train(training)
+    before = {k: b.clone() for k, b in md.named_buffers()}
+    xd = x.to(dev()).requires_grad_(True)
+    out = md(xd)[0][0]
+    assert out.shape == ref.shape and rel_l2(out, ref) < 2e-4, rel_l2(out, ref)
+    (out * cot.float().to(dev())).sum().backward()
+    torch.cuda.synchronize()
+    # GELU / ReLU kinks + 9 BatchNorm layers amplify the bf16x3 forward difference in a handful of elements
+    tol = 5e-3 if tensor_cores else 1e-3
+    assert rel_l2(xd.grad, x64.grad) < tol, rel_l2(xd.grad, x64.grad)
+    worst = 0.0
+    for k, p in md.named_parameters():
+        assert p.grad is not None, k
+        r = sd64[k].grad
+        if training and float(r.norm()) < 1e-10 * max(float(sd64[k].detach().norm()), 1.0):
+            # a bias straight in front of a batch-statistics BatchNorm has NO gradient (the mean removes it): the fp64
+            # value is rounding noise, ours must be noise of fp32 size
+            assert float(p.grad.norm()) < 1e-5, (k, float(p.grad.norm()))
+            continue
+        e = rel_l2(p.grad, r)
+        worst = max(worst, e)
+        assert e < tol, (k, e)
+    print("worst parameter gradient", worst)
+    after = dict(md.named_buffers())
+    if not training:
+        assert all(torch.equal(before[k], after[k]) for k in before)
+    else:
+        # first BatchNorm: running statistics follow nn.BatchNorm1d (momentum 0.1, unbiased variance)
+        h0 = torch.nn.functional.conv1d(x.double().unfold(1, 1024, 512).reshape(-1, 1, 1024),
+                                        sd64["conv.0.net.0.weight"].detach(), stride=4, padding=5)
+        mean, var = h0.mean((0, 2)), h0.var((0, 2), unbiased=True)
+        rm = 0.9 * before["conv.0.net.1.running_mean"].double().cpu() + 0.1 * mean
+        rv = 0.9 * before["conv.0.net.1.running_var"].double().cpu() + 0.1 * var
+        assert rel_l2(after["conv.0.net.1.running_mean"], rm) < 1e-5
+        assert rel_l2(after["conv.0.net.1.running_var"], rv) < 1e-5
+        assert int(after["conv.0.net.1.num_batches_tracked"]) == 1
+
+
+def test_adversarial_terms_with_waveform_discriminator():
+    """AdversarialTerms with `disc`: generator term = sum over mrd0-2 + disc_weight x disc (losses.py:316-327), the
+    discriminator half steps mrd{index} AND disc (stage.py:141-143); against the two-evaluation classes"""
+    import math
+
+    tf, pf, ta, pa = inputs()
+    mods = [_seeded_disc(20 + i).to(dev()) for i in range(3)]
+    disc = _cfd().to(dev()).train()
+    tfd, tad = [t.to(dev()) for t in tf], ta.to(dev())
+    scale = math.sqrt(2)
+    pfa = [p.to(dev()).requires_grad_(True) for p in pf]
+    paa = pa.to(dev()).requires_grad_(True)
+    gl = D.GeneratorLoss(mrd0=mods[0], mrd1=mods[1], mrd2=mods[2], disc=disc)
+    la = gl(target_list=tfd, pred_list=pfa, target_audio=tad, pred_audio=paa)
+    la.backward()
+    dl = D.DiscriminatorLoss(mrd0=mods[0], mrd1=mods[1], mrd2=mods[2], disc=disc, device=dev())
+    da = dl(target_list=tfd, pred_list=[p.detach() for p in pfa], target_audio=tad, pred_audio=paa.detach())
+    (da * scale).backward()
+    grads_disc = {k: p.grad.clone() for k, p in disc.named_parameters()}
+    grads_m1 = {k: p.grad.clone() for k, p in mods[1].named_parameters()}
+    for m in mods + [disc]:
+        m.zero_grad(set_to_none=True)
+    pfb = [p.to(dev()).requires_grad_(True) for p in pf]
+    pab = pa.to(dev()).requires_grad_(True)
+    adv = D.AdversarialTerms(mrd0=mods[0], mrd1=mods[1], mrd2=mods[2], disc=disc, device=dev())
+    lb = adv(target_list=tfd, pred_list=pfb, target_audio=tad, pred_audio=pab)
+    assert float(lb) == pytest.approx(float(la), rel=1e-5)
+    lb.backward()
+    assert rel_l2(pab.grad, paa.grad) < 1e-4, rel_l2(pab.grad, paa.grad)
+    db = adv.discriminator_backward(1, scale)
+    assert float(db) == pytest.approx(float(da), rel=1e-5)
+    for k, p in disc.named_parameters():
+        if float(grads_disc[k].norm()) < 1e-6 and float(p.grad.norm()) < 1e-6:
+            continue  # bias in front of a batch-statistics BatchNorm: zero gradient, both sides are rounding noise
+        assert rel_l2(p.grad, grads_disc[k]) < 1e-3, (k, rel_l2(p.grad, grads_disc[k]))
+    for k, p in mods[1].named_parameters():
+        assert rel_l2(p.grad, grads_m1[k]) < 1e-4, (k, rel_l2(p.grad, grads_m1[k]))
+    assert all(p.grad is None for i in (0, 2) for p in mods[i].parameters())
