@@ -114,7 +114,8 @@ __device__ __forceinline__ void issue_chunk(uint32_t d_tmem, uint32_t a0, uint32
   }
 }
 
-// IN_MODE : 0 no prologue | 1 mask/affine | 2 mask/affine + LeakyReLU(0.2) | 3 mask/affine + Snake
+// IN_MODE : 0 no prologue | 1 mask/affine | 2 mask/affine + LeakyReLU(0.2) | 3 mask/affine + Snake | 5 mask/affine + any
+//           other activation (act_apply: GELU, ReLU, Swish)
 //           4 ConvNeXt front: depthwise k7 conv + LayerNorm over channels + adaptive affine (K=1 only)
 // OUT_MODE: 0 none | 1 Snake | 2 ReLU | 3 Swish          (compile-time: keeps each role's loop small
 // enough for the instruction cache — three roles run different code on one SM)
@@ -130,7 +131,7 @@ template <int IN_MODE, int OUT_MODE, int EPI = 0, bool TMA = false>
 __global__ void __launch_bounds__(TMA ? kThreadsTma : kThreads, 1)
 conv1d_umma_kernel(const sty_conv1d_args p, const UmmaPlan pl, const __grid_constant__ CUtensorMap tmap) {
   static_assert(!(TMA && IN_MODE == 4), "the fused ConvNeXt front has its own kernel for TMA");
-  constexpr bool PRO = IN_MODE >= 1 && IN_MODE <= 3;
+  constexpr bool PRO = (IN_MODE >= 1 && IN_MODE <= 3) || IN_MODE == 5;
   constexpr int MT = 128;
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const int K = p.K, dil = p.dil, CO = p.CO, CI = p.CI, NT = pl.NT, rows = pl.rows;
@@ -451,6 +452,8 @@ conv1d_umma_kernel(const sty_conv1d_args p, const UmmaPlan pl, const __grid_cons
                     w = fmaf(ial[j], sin_sq(al[j] * w), w);
                   } else if constexpr (IN_MODE == 2) {
                     w = w > 0.f ? w : 0.2f * w;
+                  } else if constexpr (IN_MODE == 5) {
+                    w = act_apply(w, p.in_act);
                   }
                   v[u][j] = (ok && m >= 0.f) ? w : 0.f;  // negative mask value: zero AFTER the prologue
                 }
@@ -760,7 +763,7 @@ static int umma_in_mode(const sty_conv1d_args& a) {
   }
   if (a.in_act == STY_ACT_SNAKE) return 3;
   if (a.in_act == STY_ACT_LEAKY02) return 2;
-  if (a.in_act != STY_ACT_NONE) return -1;
+  if (a.in_act != STY_ACT_NONE) return 5;  // any other activation (GELU, ReLU, Swish): generic prologue, plain epilogue only
   return (a.in_scale || a.in_shift || a.in_mask) ? 1 : 0;
 }
 static int umma_out_mode(const sty_conv1d_args& a) {
@@ -776,6 +779,7 @@ static int umma_out_mode(const sty_conv1d_args& a) {
 bool conv1d_umma_eligible(const sty_conv1d_args& a) {
   if (!a.w_split || a.w_bs != 0 || a.T < 64) return false;
   if (umma_in_mode(a) < 0 || umma_out_mode(a) < 0) return false;
+  if (umma_in_mode(a) == 5 && umma_out_mode(a) != 0) return false;
   if (a.out_sum && a.CO > 64) return false;
   UmmaPlan pl;
   return make_plan(a, pl);
@@ -845,6 +849,7 @@ static KernPtr pick_kernel(const sty_conv1d_args& a) {
       {conv1d_umma_kernel<3, 0, 0, TMA>, conv1d_umma_kernel<3, 1, 0, TMA>, conv1d_umma_kernel<3, 2, 0, TMA>,
        conv1d_umma_kernel<3, 3, 0, TMA>}};
   if (im >= 0 && im < 4) return table[im][om];
+  if (im == 5 && om == 0) return conv1d_umma_kernel<5, 0, 0, TMA>;  // BatchNorm + GELU prologues (waveform discriminator)
   return nullptr;
 }
 

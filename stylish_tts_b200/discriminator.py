@@ -406,6 +406,7 @@ class ContextFreeDiscriminator(nn.Module):
         self.fusion = _CFBlock(8 * d, 4 * d, kernel=1, bias=True)
         self.last = nn.Sequential(nn.Conv1d(4 * d, 8 * d, 1, 1), nn.ReLU(), nn.Conv1d(8 * d, 1, 1))
         self._masks = {}
+        self.backward_mode = BackwardMode()
 
     def _mask(self, B, windows, level, device):
         key = (B, windows, level, str(device))
@@ -436,6 +437,7 @@ class ContextFreeDiscriminator(nn.Module):
         if not x.is_cuda:
             raise RuntimeError("stylish_tts_b200: ContextFreeDiscriminator needs CUDA tensors (no CPU fallback)")
         B = x.shape[0]
+        conv = lambda *a, **kw: T.conv(*a, mode=self.backward_mode, **kw)
         win = x.to(torch.float32).unfold(1, 1024, 512)                       # (B, W, 1024), discriminator.py:160
         W = win.shape[1]
         h = torch.nn.functional.pad(win, (0, self.PITCH[0] - self.DATA[0])).reshape(B, 1, W * self.PITCH[0])
@@ -445,28 +447,28 @@ class ContextFreeDiscriminator(nn.Module):
             xs = LeakyS2dFn.apply(h, s, 1.0)                                   # space-to-depth only (slope 1)
             w = strided_weight(blk.net[0].weight, s)
             if prev is None:
-                h = T.conv(xs, w, None, out_mask=m)
+                h = conv(xs, w, None, out_mask=m, first=True)
             else:
-                h = T.conv(xs, w, None, in_mask=m, in_mask_post=True, out_mask=m, **self._bn(prev, group=s))
+                h = conv(xs, w, None, in_mask=m, in_mask_post=True, out_mask=m, **self._bn(prev, group=s))
             prev = blk
         m = self._mask(B, W, 4, x.device)
         P, Tw = self.PITCH[4], self.DATA[4]
         mk = dict(in_mask=m, in_mask_post=True, out_mask=m)
         # x3 = GELU(BN(h)) is needed as a tensor (pooled, gated, read by two branches): identity 1x1 conv carries it
         eye = torch.eye(h.shape[1], device=h.device, dtype=torch.float32).unsqueeze(-1)
-        x3 = T.conv(h, eye, None, **mk, **self._bn(prev))
-        gate = torch.sigmoid(T.conv(SegmentMeanFn.apply(x3, P, Tw), self.attn[1].weight, self.attn[1].bias))
+        x3 = conv(h, eye, None, **mk, **self._bn(prev))
+        gate = torch.sigmoid(conv(SegmentMeanFn.apply(x3, P, Tw), self.attn[1].weight, self.attn[1].bias))
         xg = SegmentScaleFn.apply(x3, gate, P)                                 # discriminator.py:167-168
         branches = []
         for seq in (self.temporal, self.spectral):
             b0, b1 = seq[0], seq[1]
-            y0 = T.conv(xg, grouped_as_dense(b0.net[0].weight, b0.groups), b0.net[0].bias, out_mask=m)
-            branches.append(T.conv(y0, grouped_as_dense(b1.net[0].weight, b1.groups), b1.net[0].bias, **mk,
+            y0 = conv(xg, grouped_as_dense(b0.net[0].weight, b0.groups), b0.net[0].bias, out_mask=m)
+            branches.append(conv(y0, grouped_as_dense(b1.net[0].weight, b1.groups), b1.net[0].bias, **mk,
                                    **self._bn(b0)))
-        f = T.conv(torch.cat(branches, 1), self.fusion.net[0].weight, self.fusion.net[0].bias, **mk,
+        f = conv(torch.cat(branches, 1), self.fusion.net[0].weight, self.fusion.net[0].bias, **mk,
                    **self._bn(self.temporal[1], self.spectral[1]))
-        l0 = T.conv(f, self.last[0].weight, self.last[0].bias, **mk, **self._bn(self.fusion))
-        out = T.conv(l0, self.last[2].weight, self.last[2].bias, in_act=ACT_RELU)     # (B, 1, W*P)
+        l0 = conv(f, self.last[0].weight, self.last[0].bias, **mk, **self._bn(self.fusion))
+        out = conv(l0, self.last[2].weight, self.last[2].bias, in_act=ACT_RELU)     # (B, 1, W*P)
         return [out.view(B, W, P)[:, :, :Tw].reshape(B, -1)], []               # "(b t) c f -> b (t c f)"
 
 

@@ -206,7 +206,13 @@ class ConvFn(Function):
         in_mask, out_mask = cfg.get("in_mask"), cfg.get("out_mask")
         shuffle, umma = cfg.get("shuffle", 0), cfg.get("umma", True)
         out_scale, res_scale = cfg.get("out_scale", 1.0), cfg.get("res_scale", 1.0)
-        need = ctx.needs_input_grad
+        need = list(ctx.needs_input_grad)
+        mode = cfg.get("mode")  # discriminator.BackwardMode: which gradients THIS walk of the tape is run for
+        if mode is not None:
+            if not mode.weights:
+                need[1] = need[2] = False
+            if cfg.get("first") and not mode.first_input:
+                need[0] = False
         dy = dy.contiguous()
         d_res = None
         if ctx.has_res and need[5]:

@@ -377,6 +377,36 @@ def test_convnext_front_fused_into_pointwise_conv(Cc, T):
     assert rel_l2(ssq, (h ** 2).sum(2)) < 3e-5
 
 
+@pytest.mark.parametrize("T", [900, 1504])
+def test_conv1d_tensor_core_gelu_prologue_and_post_mask(T):
+    """generic-activation prologue (IN_MODE 5: affine + GELU) on the tcgen05 path, with the "negative mask value =
+    zero AFTER the prologue" convention of end-to-end window layouts (waveform discriminator) and an output mask;
+    T = 1504 has 16-byte aligned rows (TMA producers), 900 takes the load path as well (T < 512 rule aside)"""
+    gen = g(78)
+    B, ci, co, k = 2, 64, 48, 5
+    x = torch.randn(B, ci, T, generator=gen)
+    w = torch.randn(co, ci, k, generator=gen) / math.sqrt(ci * k)
+    bias = torch.randn(co, generator=gen)
+    sc, sh = torch.randn(B, ci, generator=gen), torch.randn(B, ci, generator=gen)
+    keep = ((torch.arange(T) % 20) < 16).float().unsqueeze(0).expand(B, -1).contiguous()
+    xin = F.gelu(sc[:, :, None] * x.double() + sh[:, :, None]) * keep[:, None, :]
+    ref = F.conv1d(xin, w.double(), bias.double(), padding=k // 2) * keep[:, None, :]
+    d = dev()
+    calls = []
+    orig = L.call
+    L.call = lambda name, *a: (calls.append((name, a)), orig(name, *a))[1]
+    try:
+        out = E.conv1d(x.to(d), E.ConvW(w.to(d), bias.to(d)), in_scale=sc.to(d), in_shift=sh.to(d),
+                       in_act=L.ACT_GELU, in_mask=(2 * keep - 1).to(d), out_mask=keep.to(d))
+    finally:
+        L.call = orig
+    assert calls[0][1][0]._obj.w_split  # tensor-core path requested (and taken: same result on the FMA path below)
+    assert rel_l2(out, ref) < 3e-5, rel_l2(out, ref)
+    out_fma = E.conv1d(x.to(d), E.ConvW(w.to(d), bias.to(d)), in_scale=sc.to(d), in_shift=sh.to(d),
+                       in_act=L.ACT_GELU, in_mask=(2 * keep - 1).to(d), out_mask=keep.to(d), umma=False)
+    assert rel_l2(out_fma, ref) < 2e-6, rel_l2(out_fma, ref)
+
+
 @pytest.mark.parametrize("umma", [True, False])
 def test_conv1d_epilogue_moments_feed_adain(umma):
     """out_sum / out_sumsq accumulated by the producing conv + sty_moments_affine_fwd == the two-pass
