@@ -167,6 +167,8 @@ def dwconv1d(x, w, bias, *, K, pad_left, out, post_scale=None, post_shift=None, 
 
 # 64-wide unmasked attention through the pre-split / bulk-copy kernel (csrc/attention64.cu); 0 = first-generation kernel
 ATTENTION64 = os.environ.get("STYLISH_B200_ATTENTION64", "1") != "0"
+# harmonic-prior branch of the generator on a side stream, concurrent with the text encoder / decoder / conformer
+OVERLAP_PRIOR = os.environ.get("STYLISH_B200_OVERLAP_PRIOR", "1") != "0"
 
 
 def attention64(q_ptr, k_ptr, v_ptr, qkv_bs, out, B, H, T, scale, lse=None):
@@ -383,6 +385,7 @@ class SpeechEngine:
         self.module = module
         self._packed: Optional[Packed] = None
         self._packed_key = None
+        self._side_streams = {}
 
     # parameters are repacked when any of them changed (optimizer step, load_state_dict)
     def packed(self, device) -> Packed:
@@ -597,7 +600,29 @@ class SpeechEngine:
             taps["prior_wave"] = wave
         return spec, phase
 
-    def generator(self, P: Packed, mel, h, pitch, voiced, noise, prior=None, taps=None):
+    def prior_branch(self, P: Packed, pin, h, pitch, voiced, noise, prior=None, taps=None):
+        """harmonic source -> STFT -> the two prior convs + AdaptiveGeneratorBlocks, written into channels [Hs, 3 Hs)
+        of the phase-head input `pin`.  Depends on pitch / voiced / style only (generator.py:719-760), so forward()
+        runs it on a side stream next to the text encoder / decoder / conformer."""
+        dev = pin.device
+        B, Hs = pin.shape[0], P.hidden_s
+        if prior is None:
+            har_spec, har_phase = self.harmonic_prior(P, pitch, voiced, noise, taps)
+        else:  # injected (parity tests): same pitch-padded layout as the computed prior
+            har_spec, har_phase = (empty_bct(*t.shape, dev).copy_(t) for t in prior)
+        if taps is not None:
+            taps["har_spec"], taps["har_phase"] = har_spec, har_phase
+        mom = torch.zeros((2, 2, B, Hs), device=dev, dtype=torch.float32)
+        lp = conv1d(har_spec, P.amp_prior_conv, out=pin[:, Hs:2 * Hs], out_sum=mom[0, 0], out_sumsq=mom[0, 1])
+        self.gen_block(P, P.amp_prior_block, lp, h, mom[0])
+        pp = conv1d(har_phase, P.phase_prior_conv, out=pin[:, 2 * Hs:], out_sum=mom[1, 0], out_sumsq=mom[1, 1])
+        self.gen_block(P, P.phase_prior_block, pp, h, mom[1])
+        if taps is not None:
+            taps["logamp_prior"], taps["phase_prior"] = lp.clone(), pp.clone()
+
+    def generator(self, P: Packed, mel, h, pitch, voiced, noise, prior=None, taps=None, pin=None, join=None):
+        """pin / join: the phase-head input whose prior channels forward() is already filling on a side stream, and
+        the callable that makes the current stream wait for it"""
         B, _, Fr = mel.shape
         dev = mel.device
         x = conv1d(mel, P.amp_input)
@@ -607,23 +632,12 @@ class SpeechEngine:
         x = self.conformer(P, x, h)
         if taps is not None:
             taps["conformer"] = x.clone()
-        if prior is None:
-            har_spec, har_phase = self.harmonic_prior(P, pitch, voiced, noise, taps)
-        else:  # injected (parity tests): same pitch-padded layout as the computed prior
-            har_spec, har_phase = (empty_bct(*t.shape, dev).copy_(t) for t in prior)
-        if taps is not None:
-            taps["har_spec"], taps["har_phase"] = har_spec, har_phase
-        S = har_spec.shape[2]
         Hs = P.hidden_s
-        # phase-head input: [upsampled mel | logamp prior | phase prior] in one buffer
-        pin = empty_bct(B, 3 * Hs, S, dev)
-        mom = torch.zeros((2, 2, B, Hs), device=dev, dtype=torch.float32)
-        lp = conv1d(har_spec, P.amp_prior_conv, out=pin[:, Hs:2 * Hs], out_sum=mom[0, 0], out_sumsq=mom[0, 1])
-        self.gen_block(P, P.amp_prior_block, lp, h, mom[0])
-        pp = conv1d(har_phase, P.phase_prior_conv, out=pin[:, 2 * Hs:], out_sum=mom[1, 0], out_sumsq=mom[1, 1])
-        self.gen_block(P, P.phase_prior_block, pp, h, mom[1])
-        if taps is not None:
-            taps["logamp_prior"], taps["phase_prior"] = lp.clone(), pp.clone()
+        S = Fr * P.mc.hop_length // (P.mc.hop_length // 75)
+        if pin is None:
+            # phase-head input: [upsampled mel | logamp prior | phase prior] in one buffer
+            pin = empty_bct(B, 3 * Hs, S, dev)
+            self.prior_branch(P, pin, h, pitch, voiced, noise, prior, taps)
         for blk in P.amp_convnext:
             x = self.convnext(P, blk, x, h)
         if taps is not None:
@@ -640,6 +654,8 @@ class SpeechEngine:
             taps["upsampled"] = x.clone()
         la = chan_layernorm(x, *P.amp_final_ln, eps=1e-6)
         logamp = conv1d(la, P.amp_output)
+        if join is not None:
+            join()  # the prior channels of `pin` are complete
         ph = conv1d(pin, P.phase_input)
         ph = chan_layernorm(ph, *P.phase_norm, eps=1e-6, out=ph)
         for blk in P.phase_convnext:
@@ -673,16 +689,30 @@ class SpeechEngine:
         h = torch.empty((B, P.fc_rows), device=dev, dtype=torch.float32)
         L.call("sty_linear_rows_fwd", style.data_ptr(), P.fc_w.data_ptr(), P.fc_b.data_ptr(),
                h.data_ptr(), B, style.shape[1], P.fc_rows, L.stream_ptr())
+        noise = None
+        if source_draws is not None:
+            noise = f32(source_draws["noise"])
+        pin = join = None
+        if OVERLAP_PRIOR and taps is None and prior is None:
+            # the harmonic-prior branch (source, STFT, 2 x (k21 conv + AdaptiveGeneratorBlock): S-rate kernels that fill
+            # the GPU) has no dependence on the text: it runs on a side stream while the text encoder, decoder and
+            # conformer (frame-rate kernels with small grids) leave most SMs idle.  Captured graphs keep the fork / join.
+            main = torch.cuda.current_stream()
+            side = self._side_streams.get(dev)
+            if side is None:
+                side = self._side_streams[dev] = torch.cuda.Stream(device=dev)
+            pin = empty_bct(B, 3 * P.hidden_s, pitch.shape[1] * P.mc.hop_length // (P.mc.hop_length // 75), dev)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                self.prior_branch(P, pin, h, denormal_pitch, voiced, noise)
+            join = lambda: main.wait_stream(side)
         mu, _, _ = self.text_encoder(P, texts, text_lengths, taps)
         if taps is not None:
             taps["text_encoding"] = mu
         mel = self.decoder(P, mu, alignment, pitch, energy, voiced, h, taps)
         if taps is not None:
             taps["decoder"] = mel
-        noise = None
-        if source_draws is not None:
-            noise = f32(source_draws["noise"])
-        return self.generator(P, mel, h, denormal_pitch, voiced, noise, prior=prior, taps=taps)
+        return self.generator(P, mel, h, denormal_pitch, voiced, noise, prior=prior, taps=taps, pin=pin, join=join)
 
 
 # ==========================================================================
