@@ -32,6 +32,8 @@ from .modules import Node
 from . import train_ops as T
 
 INV_SQRT2 = 1.0 / math.sqrt(2.0)
+# data gradient of the 3x3 convs as the row-stacked conv of dy with reversed taps (no (N, 3C, W) intermediate, no fold)
+FOLD_FREE = True
 
 
 def _new(shape, like):
@@ -102,16 +104,26 @@ class RowConvFn(Function):
         if need[0] and cfg.get("fold_free"):
             # the adjoint of an R x K 'same' conv is the R x K conv of dy with the taps reversed along both axes and
             # the channel roles swapped — the same row-stacked kernel, no (N, R*C, W) intermediate and no fold pass.
-            # Needs zero border rows in dy, which every producer of the discriminator chain guarantees
-            # (TailFn / this function write them as zeros).
-            assert in_act == ACT_NONE and out_scale == 1.0 and R == 3 and ctx.off == 1 and mask is not None
+            # It reads dy's border rows as padding: gradients that arrive there (w.r.t. the zero padding rows, from a
+            # pooling / strided / valid-conv consumer) carry no meaning for any op of these image stacks, so they are
+            # cleared in place first.
+            assert R == 3 and ctx.off == 1 and mask is not None
+            dy[:, 0].zero_()
+            dy[:, Hp - 1].zero_()
             wt = w4.detach().flip(2, 3).permute(1, 2, 0, 3).reshape(Cc, R * Co, K)
             gx = dy.as_strided((N, R * Co, W), (Co * W, W, 1))
-            d_x = torch.empty((B, Hp, Cc, W), device=x.device, dtype=torch.float32)
-            d_x[0, 0].zero_()
-            d_x[B - 1, Hp - 1].zero_()
-            conv1d(gx, ConvW(wt, None), out_mask=mask, out=d_x.as_strided((N, Cc, W), (Cc * W, W, 1), Cc * W),
-                   umma=umma, wide=cfg.get("wide", False))
+            folded = torch.empty((B, Hp, Cc, W), device=x.device, dtype=torch.float32)
+            folded[0, 0].zero_()
+            folded[B - 1, Hp - 1].zero_()
+            conv1d(gx, ConvW(wt, None), out_mask=mask, out=folded.as_strided((N, Cc, W), (Cc * W, W, 1), Cc * W),
+                   out_scale=out_scale, umma=umma, wide=cfg.get("wide", False))
+            if in_act != ACT_NONE:  # act is elementwise on x: one act' pass on the image
+                x3 = x.view(B * Hp, Cc, W)
+                _, d_x3 = T.prologue_bwd(folded.view(B * Hp, Cc, W), x3, scale=None, shift=None, alpha=None,
+                                         mask=None, act=in_act, want_sums=False)
+                d_x = d_x3.view(B, Hp, Cc, W)
+            else:
+                d_x = folded
         elif need[0]:
             dxp = conv1d(gv, T.transposed_weight(w3), in_mask=mask, out_scale=out_scale, umma=umma)  # (N,R*C,W)
             folded = _new((B, Hp, Cc, W), x)
@@ -267,7 +279,7 @@ class MelStyleEncoder(nn.Module):
         img[:, 1:H + 1, 0, :] = mel.to(torch.float32)
         conv3 = lambda t, pre, **kw: RowConvFn.apply(
             t, self._weight(P, Bf, pre), P.get(pre + ".bias"), kw.pop("res", None),
-            dict(row_mask=self._row_mask(t.shape[0], t.shape[1], t.shape[3], 3, dev), **kw))
+            dict(row_mask=self._row_mask(t.shape[0], t.shape[1], t.shape[3], 3, dev), fold_free=FOLD_FREE, **kw))
         h = conv3(img, "shared.0")
         for pre, d_in, d_out, down in self.blocks:
             r = conv3(h, pre + ".conv1", in_act=ACT_LEAKY02)
