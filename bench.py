@@ -482,6 +482,43 @@ def measure_train(args, dev, world, rank, barrier, steps, warmup, batch):
                  "both modules + fused AdamW" + ("; + adversarial terms (stage.py:104-146)" if adversarial
                                                  else "; adversarial terms measured separately (train_adversarial)"),
     }
+    if rank == 0 and not adversarial:
+        # one event-profiled EAGER step: per-kernel device time of the training step and the roofline of its
+        # dominant convolution call (the graph replays above are what `ms_per_step` measures)
+        try:
+            train_step(resident)
+            torch.cuda.synchronize()
+            _lib.profile_log = []
+            train_step(resident)
+            torch.cuda.synchronize()
+            agg = {}
+            for sig, e0, e1, info in _lib.profile_log:
+                d = agg.setdefault(sig, {"ms": 0.0, "n": 0, "info": info})
+                d["ms"] += e0.elapsed_time(e1)
+                d["n"] += 1
+            _lib.profile_log = None
+            total = sum(d["ms"] for d in agg.values())
+            ranked = sorted(agg.items(), key=lambda kv: -kv[1]["ms"])
+            res["top_kernels"] = [{"kernel": k, "share": round(v["ms"] / total, 4), "launches_per_step": v["n"],
+                                   "avg_ms": round(v["ms"] / v["n"], 4)} for k, v in ranked[:12]]
+            peak, how = measured_peaks()
+            with_info = [(k, v) for k, v in ranked if v["info"] is not None]
+            if with_info:
+                k, v = with_info[0]
+                avg_s = v["ms"] / v["n"] / 1e3
+                byts = conv_alg_bytes(v["info"])
+                res["roofline"] = {
+                    "bound": "hbm", "kernel": k, "achieved": round(byts / avg_s / 1e9, 1), "peak": peak, "unit": "GB/s",
+                    "frac": round(byts / avg_s / 1e9 / peak, 4), "traffic": None, "peak_source": how,
+                    "alg_bytes_per_launch": byts, "avg_launch_ms": round(avg_s * 1e3, 4),
+                    "share_of_step": round(v["ms"] / total, 4),
+                    "note": "dominant convolution call of one eager training step (input + output (+ residual) bytes / "
+                            "CUDA-event time); the step's device time is spread over ~940 C-ABI calls, the largest "
+                            "single kernel is the SIMT attention backward of the conformer (top_kernels)"}
+        except Exception as e:
+            _lib.profile_log = None
+            log(f"[bench] train-step kernel profile failed: {type(e).__name__}: {e}")
+            torch.cuda.synchronize()
     del graphed, opt, sp, se, nets
     torch.cuda.empty_cache()
     return res
