@@ -190,6 +190,13 @@ STY_API int sty_tprls_bwd(const float* a, const float* b, int64_t n, const float
 STY_API int64_t sty_attention64_workspace_bytes(int B, int H, int T);
 STY_API int sty_attention64_fwd(const float* q, const float* k, const float* v, int64_t qkv_bs, float* o, int64_t o_bs,
                                 int B, int H, int T, float scale, float* lse, void* workspace, sty_stream_t stream);
+/* backward of sty_attention64_fwd (needs its o and lse): two tcgen05 kernels over pre-split tiles — dQ (128 queries per
+ * CTA, dQ accumulated in TMEM over all key tiles) and dK / dV (128 keys per CTA); dq, dk, dv (B, H*64, T) with batch
+ * stride dqkv_bs.  workspace: sty_attention64_bwd_workspace_bytes(B,H,T), 16-byte aligned. */
+STY_API int64_t sty_attention64_bwd_workspace_bytes(int B, int H, int T);
+STY_API int sty_attention64_bwd(const float* q, const float* k, const float* v, int64_t qkv_bs, const float* o,
+                                const float* d_o, int64_t o_bs, const float* lse, float* dq, float* dk, float* dv,
+                                int64_t dqkv_bs, int B, int H, int T, float scale, void* workspace, sty_stream_t stream);
 STY_API int sty_attention64_tokens_fwd(const float* qkv, int64_t ld, void* out_split, int64_t M_pad, int B, int H, int T,
                                        float scale, void* workspace, sty_stream_t stream);
 

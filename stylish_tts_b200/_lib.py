@@ -174,6 +174,8 @@ _SIGNATURES = {
     "sty_tprls_fwd": [_f32p, _f32p, _i64, _f32p, _f32p, _f32p, _f32p],
     "sty_tprls_bwd": [_f32p, _f32p, _i64, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p],
     "sty_attention64_fwd": [_f32p, _f32p, _f32p, _i64, _f32p, _i64, _i32, _i32, _i32, _f32, _f32p, _f32p, _f32p],
+    "sty_attention64_bwd": [_f32p, _f32p, _f32p, _i64, _f32p, _f32p, _i64, _f32p, _f32p, _f32p, _f32p, _i64, _i32, _i32,
+                            _i32, _f32, _f32p, _f32p],
     "sty_attention64_tokens_fwd": [_f32p, _i64, _f32p, _i64, _i32, _i32, _i32, _f32, _f32p, _f32p],
     "sty_disc_first_fwd": [_f32p, _f32p, _f32p, _f32p, _i32, _i32, _i32, _f32p],
     "sty_disc_first_dgrad": [_f32p, _f32p, _f32p, _i32, _i32, _i32, _f32p],
@@ -188,6 +190,7 @@ _SPECIAL = {
     "sty_device_sm_count": ([], C.c_int),
     "sty_tprls_workspace_bytes": ([], C.c_int64),
     "sty_attention64_workspace_bytes": ([_i32, _i32, _i32], C.c_int64),
+    "sty_attention64_bwd_workspace_bytes": ([_i32, _i32, _i32], C.c_int64),
 }
 EXPORTED = tuple(_SIGNATURES) + tuple(_SPECIAL)
 
@@ -281,6 +284,7 @@ def call(name: str, *args) -> None:
     lib = load()
     # kernels per call: source = phase + wave; fused ConvNeXt block = pass 1 + GRN scale + pass 2
     launches += (2 if name in ("sty_source_fwd", "sty_attention64_fwd", "sty_attention64_tokens_fwd")
+                 else 3 if name == "sty_attention64_bwd"
                  else 3 if name == "sty_convnext_fused_fwd" else 1)
     if profile_log is not None:
         e0 = torch.cuda.Event(enable_timing=True)

@@ -296,6 +296,347 @@ attn64_kernel_impl(const uint4* __restrict__ Qw, const uint4* __restrict__ Kw, c
   if (warp == 0) tmem_dealloc(tmem_s, 128);
 }
 
+// =====================================================================================================================
+// Backward (no mask / RoPE / dropout, head dim 64), two tensor-core kernels over pre-split operand tiles:
+//   s = scale q k^T, P = exp(s - lse), dP = dO V^T, delta_i = sum_d dO_id O_id, dS = P o (dP - delta)
+//   dQ = scale dS K          dK = scale dS^T Q          dV = P^T dO
+// dQ kernel : CTA = 128 queries, streams 128-key tiles: S = Q K^T and dP = dO V^T (M=128, N=128, K=64) into TMEM, the
+//             threads form dS (2 threads per query row, lse / delta in registers) and re-stage it as bf16 hi|lo,
+//             dQ += dS K (M=128, N=64, K=128) accumulates in TMEM over ALL tiles (no rescaling: lse is known).
+// dKV kernel: CTA = 128 keys, streams 64-query tiles: S^T = K Q^T, dP^T = V dO^T (M=128 keys, N=64), the threads form
+//             P^T and dS^T (lse / delta per COLUMN from shared memory), dV += P^T dO and dK += dS^T Q accumulate in TMEM.
+// q arrives scaled by scale*log2(e) in the tiles: P = ex2(S - lse*log2e); dS is staged * scale (dQ kernel, K unscaled)
+// or * ln2 (dKV kernel, against the scaled Q tiles).  bf16x3 everywhere.
+constexpr int kBT = 128;                       // rows per owner / stream tile of the dQ kernel
+constexpr int kT128U4 = 2 * 8 * 128, kT64U4 = 2 * 8 * 64;
+
+// one (b, h, 64-row block): q (scaled), k, v, dO -> 128-row tile images (half of one) + q, dO 64-row tile images;
+// delta = rowsum(dO o O), lse2 = lse * log2e (+inf for rows >= T: P = 0 there)
+__global__ void __launch_bounds__(256)
+attn64_bwd_prepare_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
+                          int64_t qkv_bs, const float* __restrict__ o, const float* __restrict__ d_o, int64_t o_bs,
+                          const float* __restrict__ lse, uint4* __restrict__ Q128, uint4* __restrict__ K128,
+                          uint4* __restrict__ V128, uint4* __restrict__ G128, uint4* __restrict__ Q64,
+                          uint4* __restrict__ G64, float* __restrict__ delta, float* __restrict__ lse2, int T,
+                          int n128, int n64, float qmul) {
+  const int tile = blockIdx.x, h = blockIdx.y, b = blockIdx.z, H = gridDim.y;
+  const int t0 = tile * 64;
+  const int64_t bh = (int64_t)b * H + h;
+  const int64_t off_qkv = (int64_t)b * qkv_bs + (int64_t)h * kD * T, off_o = (int64_t)b * o_bs + (int64_t)h * kD * T;
+  const int64_t t128 = (bh * n128 + (tile >> 1)) * kT128U4 + (tile & 1) * 64;
+  const int64_t t64 = (bh * n64 + tile) * kT64U4;
+  __shared__ float dsum[8][64];
+  for (int item = threadIdx.x; item < 4 * 512; item += 256) {
+    const int which = item >> 9, r = item & 511;
+    const int d8 = r >> 6, row = r & 63, t = t0 + row;
+    const float* __restrict__ src = which == 0 ? q + off_qkv : which == 1 ? k + off_qkv : which == 2 ? v + off_qkv
+                                                                                                      : d_o + off_o;
+    float x[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[j] = t < T ? src[(int64_t)(d8 * 8 + j) * T + t] : 0.f;
+    if (which == 3) {  // delta partial over this thread's 8 features
+      float acc = 0.f;
+      if (t < T)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc = fmaf(x[j], o[off_o + (int64_t)(d8 * 8 + j) * T + t], acc);
+      dsum[d8][row] = acc;
+    }
+    if (which == 0)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[j] *= qmul;
+    uint4 hi, lo;
+    split8(x, hi, lo);
+    uint4* big = which == 0 ? Q128 : which == 1 ? K128 : which == 2 ? V128 : G128;
+    big[t128 + (0 * 8 + d8) * 128 + row] = hi;
+    big[t128 + (1 * 8 + d8) * 128 + row] = lo;
+    if ((which == 0 || which == 3) && tile < n64) {
+      uint4* sm = which == 0 ? Q64 : G64;
+      sm[t64 + (0 * 8 + d8) * 64 + row] = hi;
+      sm[t64 + (1 * 8 + d8) * 64 + row] = lo;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    const int row = threadIdx.x, t = t0 + row;
+    float a = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a += dsum[j][row];
+    const int64_t idx = bh * ((int64_t)n128 * 128) + t;  // padded to whole 128-row tiles
+    if (t < n128 * 128) {
+      delta[idx] = t < T ? a : 0.f;
+      lse2[idx] = t < T ? lse[bh * T + t] * 1.4426950408889634f : INFINITY;
+    }
+  }
+}
+
+// generic bf16x3 MMA group: D (+)= A B over n_k K-steps; descriptors as (lo, hi) words, lo words advanced per K-step
+__device__ __forceinline__ void mma_x3(uint32_t tmem_d, uint64_t ad, uint64_t bd, uint32_t a_kstep, uint32_t b_kstep,
+                                       uint32_t a_lo_off, uint32_t b_lo_off, uint32_t idesc, int n_k, uint32_t acc0) {
+  const uint32_t a_hi = (uint32_t)(ad >> 32), b_hi = (uint32_t)(bd >> 32);
+  uint32_t ak = (uint32_t)ad, bk = (uint32_t)bd;
+#pragma unroll 1
+  for (int ks = 0; ks < n_k; ++ks, ak += a_kstep, bk += b_kstep) {
+    umma_bf16_w(tmem_d, ak, a_hi, bk, b_hi, idesc, ks == 0 ? acc0 : 1u);
+    umma_bf16_w(tmem_d, ak + a_lo_off, a_hi, bk, b_hi, idesc, 1u);  // lo * hi
+    umma_bf16_w(tmem_d, ak, a_hi, bk + b_lo_off, b_hi, idesc, 1u);  // hi * lo
+  }
+}
+
+__host__ __device__ constexpr uint32_t idesc_mn(int N, bool b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (b_mn_major ? (1u << 16) : 0u) | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(128 >> 4) << 24);
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+attn64_bwd_dq_kernel(const uint4* __restrict__ Q128, const uint4* __restrict__ K128, const uint4* __restrict__ V128,
+                     const uint4* __restrict__ G128, const float* __restrict__ delta, const float* __restrict__ lse2,
+                     float* __restrict__ dq, int64_t dq_bs, int T, int n128, float scale) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  uint4* Qs = reinterpret_cast<uint4*>(smem_raw);   // [2][8][128]
+  uint4* Gs = Qs + kT128U4;                         // dO
+  uint4* Ks = Gs + kT128U4;
+  uint4* Vs = Ks + kT128U4;
+  uint4* Ds = Vs + kT128U4;                         // dS [2][16 key groups][128 rows]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(Ds + 2 * 16 * 128);
+  uint64_t *bar_own = bars, *bar_k = bars + 1, *bar_v = bars + 2, *bar_s = bars + 3, *bar_dp = bars + 4,
+           *bar_ds = bars + 5, *bar_dq = bars + 6;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int quad = warp & 3, half = warp >> 2, row = quad * 32 + lane;
+  const int b = blockIdx.z, h = blockIdx.y, qb = blockIdx.x, H = gridDim.y;
+  const int64_t bh = (int64_t)b * H + h;
+  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  if (tid == 0) {
+    for (int i = 0; i < 7; ++i) mbar_init(&bars[i], i == 5 ? 256u : 1u);
+    fence_barrier_init();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tm_s = *tmem_slot, tm_dp = tm_s + 128, tm_dq = tm_s + 256;
+  const uint4* kt_src = K128 + bh * n128 * kT128U4;
+  const uint4* vt_src = V128 + bh * n128 * kT128U4;
+  constexpr uint32_t TILE_B = kT128U4 * 16;
+
+  if (warp == kIssuerWarp) {
+    if (elect_one()) {
+      mbar_arrive_expect_tx(bar_own, 2 * TILE_B);
+      bulk_load(Qs, Q128 + (bh * n128 + qb) * kT128U4, TILE_B, bar_own);
+      bulk_load(Gs, G128 + (bh * n128 + qb) * kT128U4, TILE_B, bar_own);
+      mbar_arrive_expect_tx(bar_k, TILE_B);
+      bulk_load(Ks, kt_src, TILE_B, bar_k);
+      mbar_arrive_expect_tx(bar_v, TILE_B);
+      bulk_load(Vs, vt_src, TILE_B, bar_v);
+      mbar_wait(bar_own, 0);
+      const uint64_t q_d = make_desc(smem_u32(Qs), 128u, 8u), g_d = make_desc(smem_u32(Gs), 128u, 8u);
+      const uint64_t k_d = make_desc(smem_u32(Ks), 128u, 8u), v_d = make_desc(smem_u32(Vs), 128u, 8u);
+      const uint64_t ds_d = make_desc(smem_u32(Ds), 128u, 8u);           // A: K-major, 16 key groups
+      const uint64_t kmn_d = make_desc(smem_u32(Ks), 8u, 128u);          // B: MN-major (N = d, K = keys)
+      for (int kt = 0; kt < n128; ++kt) {
+        const uint32_t ph = (uint32_t)(kt & 1);
+        mbar_wait(bar_k, ph);
+        tc_fence_after();
+        mma_x3(tm_s, q_d, k_d, 256u, 256u, 8u * 128u, 8u * 128u, idesc_mn(128, false), 4, 0u);
+        umma_commit(bar_s);
+        mbar_wait(bar_v, ph);
+        mma_x3(tm_dp, g_d, v_d, 256u, 256u, 8u * 128u, 8u * 128u, idesc_mn(128, false), 4, 0u);
+        umma_commit(bar_dp);
+        mbar_wait(bar_dp, ph);  // V is free
+        if (kt + 1 < n128) {
+          mbar_arrive_expect_tx(bar_v, TILE_B);
+          bulk_load(Vs, vt_src + (int64_t)(kt + 1) * kT128U4, TILE_B, bar_v);
+        }
+        mbar_wait(bar_ds, ph);  // dS staged, S / dP read
+        tc_fence_after();
+        mma_x3(tm_dq, ds_d, kmn_d, 256u, 16u, 16u * 128u, 8u * 128u, idesc_mn(64, true), 8, kt == 0 ? 0u : 1u);
+        umma_commit(bar_dq);
+        mbar_wait(bar_dq, ph);  // K and dS buffers are free
+        if (kt + 1 < n128) {
+          mbar_arrive_expect_tx(bar_k, TILE_B);
+          bulk_load(Ks, kt_src + (int64_t)(kt + 1) * kT128U4, TILE_B, bar_k);
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    const int64_t ridx = bh * ((int64_t)n128 * 128) + qb * 128 + row;
+    const float my_lse = lse2[ridx], my_delta = delta[ridx];
+    const uint32_t t_addr = ((uint32_t)(quad * 32) << 16) + (uint32_t)(half * 64);
+    for (int kt = 0; kt < n128; ++kt) {
+      const uint32_t ph = (uint32_t)(kt & 1);
+      const int k0 = kt * 128 + half * 64;
+      mbar_wait(bar_s, ph);
+      mbar_wait(bar_dp, ph);
+      tc_fence_after();
+      if (kt > 0) mbar_wait(bar_dq, ph ^ 1u);  // the previous tile's dQ MMAs have read the dS buffer
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        float s[32], dp[32];
+        tmem_ld32(tm_s + t_addr + 32u * c, s);
+        tmem_ld32(tm_dp + t_addr + 32u * c, dp);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float p = (k0 + 32 * c + j < T) ? ex2_approx(s[j] - my_lse) : 0.f;
+          s[j] = p * (dp[j] - my_delta) * scale;
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 hi, lo;
+          split8(s + g * 8, hi, lo);
+          const int kg = half * 8 + c * 4 + g;
+          Ds[(0 * 16 + kg) * 128 + row] = hi;
+          Ds[(1 * 16 + kg) * 128 + row] = lo;
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(bar_ds);
+    }
+    mbar_wait(bar_dq, (uint32_t)((n128 - 1) & 1));
+    tc_fence_after();
+    const int tq = qb * 128 + row;
+    float acc[32];
+    tmem_ld32(tm_dq + ((uint32_t)(quad * 32) << 16) + (uint32_t)(half * 32), acc);
+    if (tq < T) {
+      float* __restrict__ ob = dq + (int64_t)b * dq_bs + ((int64_t)h * kD + half * 32) * T;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) ob[(int64_t)j * T + tq] = acc[j];
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tm_s, 512);
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+attn64_bwd_dkv_kernel(const uint4* __restrict__ K128, const uint4* __restrict__ V128, const uint4* __restrict__ Q64,
+                      const uint4* __restrict__ G64, const float* __restrict__ delta, const float* __restrict__ lse2,
+                      float* __restrict__ dk, float* __restrict__ dv, int64_t d_bs, int T, int n128, int n64) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  uint4* Ks = reinterpret_cast<uint4*>(smem_raw);   // [2][8][128] owner keys
+  uint4* Vs = Ks + kT128U4;
+  uint4* Qs = Vs + kT128U4;                         // [2][8][64] streamed queries
+  uint4* Gs = Qs + kT64U4;                          // dO
+  uint4* Ps = Gs + kT64U4;                          // P^T  [2][8 query groups][128 keys]
+  uint4* Ds = Ps + 2 * 8 * 128;                     // dS^T
+  float* col = reinterpret_cast<float*>(Ds + 2 * 8 * 128);  // [2 parity][lse2 | delta][64]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(col + 2 * 2 * 64);
+  uint64_t *bar_own = bars, *bar_q = bars + 1, *bar_s = bars + 2, *bar_dp = bars + 3, *bar_pd = bars + 4,
+           *bar_acc = bars + 5;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int quad = warp & 3, half = warp >> 2, row = quad * 32 + lane;
+  const int b = blockIdx.z, h = blockIdx.y, kb = blockIdx.x, H = gridDim.y;
+  const int64_t bh = (int64_t)b * H + h;
+  if (warp == 0) tmem_alloc(tmem_slot, 256);
+  if (tid == 0) {
+    for (int i = 0; i < 6; ++i) mbar_init(&bars[i], i == 4 ? 256u : 1u);
+    fence_barrier_init();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tm_s = *tmem_slot, tm_dp = tm_s + 64, tm_dv = tm_s + 128, tm_dk = tm_s + 192;
+  const uint4* q_src = Q64 + bh * n64 * kT64U4;
+  const uint4* g_src = G64 + bh * n64 * kT64U4;
+  const float* lse_src = lse2 + bh * ((int64_t)n128 * 128);
+  const float* del_src = delta + bh * ((int64_t)n128 * 128);
+  constexpr uint32_t OWN_B = kT128U4 * 16, STR_B = kT64U4 * 16;
+
+  if (warp == kIssuerWarp) {
+    if (elect_one()) {
+      mbar_arrive_expect_tx(bar_own, 2 * OWN_B);
+      bulk_load(Ks, K128 + (bh * n128 + kb) * kT128U4, OWN_B, bar_own);
+      bulk_load(Vs, V128 + (bh * n128 + kb) * kT128U4, OWN_B, bar_own);
+      mbar_arrive_expect_tx(bar_q, 2 * STR_B);
+      bulk_load(Qs, q_src, STR_B, bar_q);
+      bulk_load(Gs, g_src, STR_B, bar_q);
+      mbar_wait(bar_own, 0);
+      const uint64_t k_d = make_desc(smem_u32(Ks), 128u, 8u), v_d = make_desc(smem_u32(Vs), 128u, 8u);
+      const uint64_t q_d = make_desc(smem_u32(Qs), 64u, 8u), g_d = make_desc(smem_u32(Gs), 64u, 8u);
+      const uint64_t p_d = make_desc(smem_u32(Ps), 128u, 8u), ds_d = make_desc(smem_u32(Ds), 128u, 8u);
+      const uint64_t qmn_d = make_desc(smem_u32(Qs), 8u, 64u), gmn_d = make_desc(smem_u32(Gs), 8u, 64u);
+      for (int qt = 0; qt < n64; ++qt) {
+        const uint32_t ph = (uint32_t)(qt & 1);
+        mbar_wait(bar_q, ph);
+        tc_fence_after();
+        mma_x3(tm_s, k_d, q_d, 256u, 128u, 8u * 128u, 8u * 64u, idesc_mn(64, false), 4, 0u);
+        umma_commit(bar_s);
+        mma_x3(tm_dp, v_d, g_d, 256u, 128u, 8u * 128u, 8u * 64u, idesc_mn(64, false), 4, 0u);
+        umma_commit(bar_dp);
+        mbar_wait(bar_pd, ph);  // P^T and dS^T staged, S^T / dP^T read
+        tc_fence_after();
+        mma_x3(tm_dv, p_d, gmn_d, 256u, 16u, 8u * 128u, 8u * 64u, idesc_mn(64, true), 4, qt == 0 ? 0u : 1u);
+        mma_x3(tm_dk, ds_d, qmn_d, 256u, 16u, 8u * 128u, 8u * 64u, idesc_mn(64, true), 4, qt == 0 ? 0u : 1u);
+        umma_commit(bar_acc);
+        mbar_wait(bar_acc, ph);  // Q / dO tiles and the P^T / dS^T buffers are free
+        if (qt + 1 < n64) {
+          mbar_arrive_expect_tx(bar_q, 2 * STR_B);
+          bulk_load(Qs, q_src + (int64_t)(qt + 1) * kT64U4, STR_B, bar_q);
+          bulk_load(Gs, g_src + (int64_t)(qt + 1) * kT64U4, STR_B, bar_q);
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    const uint32_t t_addr = ((uint32_t)(quad * 32) << 16) + (uint32_t)(half * 32);
+    for (int qt = 0; qt < n64; ++qt) {
+      const uint32_t ph = (uint32_t)(qt & 1);
+      float* cs = col + ph * 128;
+      if (tid < 64) {  // per-column (query) constants of this tile
+        cs[tid] = lse_src[qt * 64 + tid];
+        cs[64 + tid] = del_src[qt * 64 + tid];
+      }
+      mbar_wait(bar_s, ph);
+      mbar_wait(bar_dp, ph);
+      tc_fence_after();
+      if (qt > 0) mbar_wait(bar_acc, ph ^ 1u);  // previous dV / dK MMAs have read the staging buffers
+      asm volatile("bar.sync 1, 256;" ::: "memory");  // column constants visible (the 8 softmax warps only)
+      float s[32], dp[32];
+      tmem_ld32(tm_s + t_addr, s);
+      tmem_ld32(tm_dp + t_addr, dp);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float p = ex2_approx(s[j] - cs[half * 32 + j]);  // lse2 = +inf for padded queries: p = 0
+        dp[j] = p * (dp[j] - cs[64 + half * 32 + j]) * 0.69314718055994531f;
+        s[j] = p;
+      }
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        uint4 hi, lo;
+        split8(s + g * 8, hi, lo);
+        Ps[(0 * 8 + half * 4 + g) * 128 + row] = hi;
+        Ps[(1 * 8 + half * 4 + g) * 128 + row] = lo;
+        split8(dp + g * 8, hi, lo);
+        Ds[(0 * 8 + half * 4 + g) * 128 + row] = hi;
+        Ds[(1 * 8 + half * 4 + g) * 128 + row] = lo;
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(bar_pd);
+    }
+    mbar_wait(bar_acc, (uint32_t)((n64 - 1) & 1));
+    tc_fence_after();
+    const int tk = kb * 128 + row;
+    float a[32];
+    tmem_ld32(tm_dv + t_addr, a);
+    if (tk < T) {
+      float* __restrict__ ob = dv + (int64_t)b * d_bs + ((int64_t)h * kD + half * 32) * T;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) ob[(int64_t)j * T + tk] = a[j];
+    }
+    tmem_ld32(tm_dk + t_addr, a);
+    if (tk < T) {
+      float* __restrict__ ob = dk + (int64_t)b * d_bs + ((int64_t)h * kD + half * 32) * T;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) ob[(int64_t)j * T + tk] = a[j];
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tm_s, 256);
+}
+
 struct Plan {
   int n_qb, n_kt;
   int64_t q_u4, kv_u4;
@@ -357,5 +698,49 @@ extern "C" int sty_attention64_tokens_fwd(const float* qkv, int64_t ld, void* ou
   launch<true, true>(qkv, qkv + H * kD, qkv + 2 * H * kD, ld, reinterpret_cast<float*>(out_split), M_pad, B, H, T,
                      scale, nullptr, workspace, as_stream(stream));
   STY_CHECK_LAUNCH("attention64_tokens");
+  return STY_OK;
+}
+
+extern "C" int64_t sty_attention64_bwd_workspace_bytes(int B, int H, int T) {
+  if (B <= 0 || H <= 0 || T <= 0) return 0;
+  const int64_t n128 = cdiv(T, 128), n64 = cdiv(T, 64), bh = (int64_t)B * H;
+  return (bh * n128 * kT128U4 * 4 + bh * n64 * kT64U4 * 2) * 16 + bh * n128 * 128 * 2 * (int64_t)sizeof(float);
+}
+
+extern "C" int sty_attention64_bwd(const float* q, const float* k, const float* v, int64_t qkv_bs, const float* o,
+                                   const float* d_o, int64_t o_bs, const float* lse, float* dq, float* dk, float* dv,
+                                   int64_t dqkv_bs, int B, int H, int T, float scale, void* workspace,
+                                   sty_stream_t stream) {
+  STY_REQUIRE(q && k && v && o && d_o && lse && dq && dk && dv && workspace && B > 0 && H > 0 && T >= 64 &&
+                  H <= 65535 && B <= 65535,
+              "attention64_bwd: bad argument");
+  STY_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "attention64_bwd: workspace must be 16-byte aligned");
+  cudaStream_t st = as_stream(stream);
+  const int n128 = cdiv(T, 128), n64 = cdiv(T, 64);
+  const int64_t bh = (int64_t)B * H;
+  uint4* Q128 = reinterpret_cast<uint4*>(workspace);
+  uint4* K128 = Q128 + bh * n128 * kT128U4;
+  uint4* V128 = K128 + bh * n128 * kT128U4;
+  uint4* G128 = V128 + bh * n128 * kT128U4;
+  uint4* Q64 = G128 + bh * n128 * kT128U4;
+  uint4* G64 = Q64 + bh * n64 * kT64U4;
+  float* delta = reinterpret_cast<float*>(G64 + bh * n64 * kT64U4);
+  float* lse2 = delta + bh * n128 * 128;
+  attn64_bwd_prepare_kernel<<<dim3(2 * n128, H, B), 256, 0, st>>>(q, k, v, qkv_bs, o, d_o, o_bs, lse, Q128, K128, V128,
+                                                                  G128, Q64, G64, delta, lse2, T, n128, n64,
+                                                                  scale * 1.4426950408889634f);
+  {
+    const size_t smem = (size_t)(4 * kT128U4 + 2 * 16 * 128) * 16 + 128;
+    cudaFuncSetAttribute(attn64_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attn64_bwd_dq_kernel<<<dim3(n128, H, B), kThreads, smem, st>>>(Q128, K128, V128, G128, delta, lse2, dq, dqkv_bs, T,
+                                                                   n128, scale);
+  }
+  {
+    const size_t smem = (size_t)(2 * kT128U4 + 2 * kT64U4 + 2 * 2 * 8 * 128) * 16 + 2 * 2 * 64 * sizeof(float) + 128;
+    cudaFuncSetAttribute(attn64_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attn64_bwd_dkv_kernel<<<dim3(n128, H, B), kThreads, smem, st>>>(K128, V128, Q64, G64, delta, lse2, dk, dv, dqkv_bs,
+                                                                    T, n128, n64);
+  }
+  STY_CHECK_LAUNCH("attention64_bwd");
   return STY_OK;
 }

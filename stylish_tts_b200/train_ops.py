@@ -577,6 +577,13 @@ class AttentionFn(Function):
         if drop is not None:
             spec = drop[0].spec(drop[1], drop[2])
             L.call("sty_attention_drop_bwd", *args, C.byref(spec), L.stream_ptr())
+        elif D == 64 and rope is None and lengths is None and T >= 64 and _engine().ATTENTION64:
+            # tcgen05 backward over pre-split tiles (csrc/attention64.cu): dQ kernel + dK/dV kernel
+            ws = torch.empty(int(L.load().sty_attention64_bwd_workspace_bytes(B, H, T)), device=qkv.device,
+                             dtype=torch.uint8)
+            L.call("sty_attention64_bwd", q, q + 4 * n * T, q + 8 * n * T, qkv.stride(0), out.data_ptr(),
+                   d_out.data_ptr(), out.stride(0), lse.data_ptr(), dq, dq + 4 * n * T, dq + 8 * n * T,
+                   d_qkv.stride(0), B, H, T, scale, ws.data_ptr(), L.stream_ptr())
         else:
             L.call("sty_attention_bwd", *args, L.stream_ptr())
         return d_qkv, None, None, None, None, None, None

@@ -187,8 +187,11 @@ def test_dwconv(Cc, K, T_):
 
 
 @pytest.mark.parametrize("H,D,T_,lens,use_rope", [(8, 16, 258, [258, 200], True), (8, 16, 40, [40, 17], True),
-                                                  (8, 64, 203, None, False)])
+                                                  (8, 64, 203, None, False), (8, 64, 804, None, False),
+                                                  (4, 64, 64, None, False), (2, 64, 385, None, False)])
 def test_attention(H, D, T_, lens, use_rope):
+    """forward + backward against torch SDPA autograd in fp64; the 64-wide unmasked cases take the tcgen05 forward
+    and the tcgen05 backward (dQ kernel + dK/dV kernel, csrc/attention64.cu)"""
     gen = g(9)
     B, n = 2, H * D
     qkv = rn(gen, B, 3 * n, T_)

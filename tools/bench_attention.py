@@ -22,3 +22,21 @@ for B, T in ((16, 803), (64, 258), (32, 804)):
         ms = e0.elapsed_time(e1) / 20
         fl = 4.0 * B * 8 * T * T * 64
         print(f"B={B} T={T} gen{2 if gen2 else 1}: {ms:.4f} ms  {fl / ms / 1e9:.1f} TFLOP/s logical ({3 * fl / ms / 1e9:.0f} bf16 MMA)")
+
+# backward (B=32, T=804: the conformer attention of the training step)
+from stylish_tts_b200 import train_ops as TO
+for gen2 in (False, True):
+    E.ATTENTION64 = gen2
+    qkv = torch.randn(32, 3 * 512, 804, device=d, requires_grad=True)
+    out = TO.AttentionFn.apply(qkv, 8, 64, None, None, 0.125)
+    g = torch.randn_like(out)
+    for _ in range(2):
+        out.backward(g, retain_graph=True)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        out.backward(g, retain_graph=True)
+    e1.record()
+    torch.cuda.synchronize()
+    print(f"backward B=32 T=804 gen{2 if gen2 else 1}: {e0.elapsed_time(e1) / 5:.3f} ms")
