@@ -482,22 +482,24 @@ def measure_train(args, dev, world, rank, barrier, steps, warmup, batch):
                  "both modules + fused AdamW" + ("; + adversarial terms (stage.py:104-146)" if adversarial
                                                  else "; adversarial terms measured separately (train_adversarial)"),
     }
-    if rank == 0 and not adversarial:
+    if not adversarial:
         # one event-profiled EAGER step: per-kernel device time of the training step and the roofline of its
-        # dominant convolution call (the graph replays above are what `ms_per_step` measures)
+        # dominant convolution call (the graph replays above are what `ms_per_step` measures).  EVERY rank runs the
+        # two steps (they contain the gradient all-reduce); only rank 0 records events.
         try:
             train_step(resident)
             torch.cuda.synchronize()
-            _lib.profile_log = []
+            if rank == 0:
+                _lib.profile_log = []
             train_step(resident)
             torch.cuda.synchronize()
             agg = {}
-            for sig, e0, e1, info in _lib.profile_log:
+            for sig, e0, e1, info in (_lib.profile_log or []):
                 d = agg.setdefault(sig, {"ms": 0.0, "n": 0, "info": info})
                 d["ms"] += e0.elapsed_time(e1)
                 d["n"] += 1
             _lib.profile_log = None
-            total = sum(d["ms"] for d in agg.values())
+            total = sum(d["ms"] for d in agg.values()) or 1.0
             ranked = sorted(agg.items(), key=lambda kv: -kv[1]["ms"])
             res["top_kernels"] = [{"kernel": k, "share": round(v["ms"] / total, 4), "launches_per_step": v["n"],
                                    "avg_ms": round(v["ms"] / v["n"], 4)} for k, v in ranked[:12]]
@@ -513,8 +515,7 @@ def measure_train(args, dev, world, rank, barrier, steps, warmup, batch):
                     "alg_bytes_per_launch": byts, "avg_launch_ms": round(avg_s * 1e3, 4),
                     "share_of_step": round(v["ms"] / total, 4),
                     "note": "dominant convolution call of one eager training step (input + output (+ residual) bytes / "
-                            "CUDA-event time); the step's device time is spread over ~940 C-ABI calls, the largest "
-                            "single kernel is the SIMT attention backward of the conformer (top_kernels)"}
+                            "CUDA-event time); the step's device time is spread over ~940 C-ABI calls (top_kernels)"}
         except Exception as e:
             _lib.profile_log = None
             log(f"[bench] train-step kernel profile failed: {type(e).__name__}: {e}")
@@ -579,7 +580,9 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # a rank that dies or skips a collective must abort the job in minutes, not after the 10-minute default
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=240))
 
     def barrier():
         if world > 1:
@@ -812,7 +815,9 @@ def run_train(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # a rank that dies or skips a collective must abort the job in minutes, not after the 10-minute default
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=240))
 
     def barrier():
         if world > 1:
