@@ -1,7 +1,7 @@
 """Flat-arena AdamW and the data-parallel gradient exchange.
 
-CPU (gloo, world_size 2): gradient packing + sum all-reduce of the flat arena, unused parameters as zeros,
-identical result on both ranks.   GPU: the fused AdamW kernel against torch.optim.AdamW with the
+CPU (gloo, world_size 2): rank-0 parameter broadcast at construction, gradient packing + sum all-reduce of the flat
+arena, unused parameters as zeros, identical result on both ranks.   GPU: the fused AdamW kernel against torch.optim.AdamW with the
 reference's hyper-parameters (optimizers.py:106-117), including the 1/world gradient scaling."""
 import os
 import socket
@@ -29,10 +29,11 @@ def _worker(rank, world, port, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        params = _make_params()
-        before = [p.detach().clone() for p in params]
+        params = _make_params(seed=rank)  # every rank starts from its OWN initialisation ...
+        before = [p.detach().clone() for p in _make_params(seed=0)]
         opt = optim.FlatAdamW(params, world_size=world)
-        for p, b in zip(params, before):  # re-homed into the arena without changing values
+        for p, b in zip(params, before):  # ... re-homed into the arena and overwritten with rank 0's values (DDP's
+            # parameter broadcast at wrap time, train_context.py:94-104)
             assert torch.equal(p.detach(), b) and p.data_ptr() >= opt.flat.data_ptr()
         for i, p in enumerate(params):
             if i == 3:
