@@ -546,15 +546,18 @@ def tprls_generator(real, gen):
 
 
 class GeneratorLoss(nn.Module):
-    """GeneratorLoss.forward with used = the acoustic set (losses.py:316-327): sum over mrd0..2 of
-    [LSGAN + TPRLS on the generated / real scores] (+ disc_weight x the same on the waveform discriminator when
-    one is supplied).  Gradients flow into `pred_list` only; the discriminators' parameters are treated as constants
-    (the reference computes their gradients here and discards them with zero_grad, stage.py:127)."""
+    """GeneratorLoss of train/losses.py:291-337, same constructor and call keywords: for the acoustic set
+    (``used`` without a pitch / duration discriminator) the sum over mrd0..2 of [LSGAN + TPRLS on the generated / real
+    scores] + disc_weight x the same on the waveform discriminator; ``used=["pitch_disc"]`` / ``["dur_disc"]`` route
+    to the curve discriminators (losses.py:316-321).  Gradients flow into `pred_list` / `pred_audio` only; the
+    discriminators' parameters are treated as constants (the reference computes their gradients here and discards
+    them with zero_grad, stage.py:127)."""
 
-    def __init__(self, *, mrd0, mrd1, mrd2, disc: Optional[nn.Module] = None):
+    def __init__(self, *, mrd0, mrd1, mrd2, disc: Optional[nn.Module] = None, pitch: Optional[nn.Module] = None,
+                 duration: Optional[nn.Module] = None):
         super().__init__()
         self.mrd = nn.ModuleList([mrd0, mrd1, mrd2])
-        self.disc = disc
+        self.disc, self.pitch, self.duration = disc, pitch, duration
 
     @staticmethod
     def _one(model, target, pred):
@@ -563,15 +566,19 @@ class GeneratorLoss(nn.Module):
         gen, _ = model(pred)
         return lsgan_generator(gen) + tprls_generator(real, gen)
 
-    def forward(self, *, target_list, pred_list, target_audio=None, pred_audio=None):
-        models = list(self.mrd) + ([self.disc] if self.disc is not None else [])
+    def forward(self, *, target_list, pred_list, target_audio=None, pred_audio=None, used=None, index=0):
+        curve = _curve_model(self, used)
+        models = [curve] if curve is not None else list(self.mrd) + ([self.disc] if self.disc is not None else [])
         req = [p.requires_grad for m in models for p in m.parameters()]
         for m in models:
             m.requires_grad_(False)
         try:
-            loss = sum(self._one(m, t, p) for m, t, p in zip(self.mrd, target_list, pred_list))
-            if self.disc is not None:
-                loss = loss + DISC_WEIGHT * self._one(self.disc, target_audio, pred_audio)
+            if curve is not None:
+                loss = self._one(curve, target_list[0], pred_list[0])
+            else:
+                loss = sum(self._one(m, t, p) for m, t, p in zip(self.mrd, target_list, pred_list))
+                if self.disc is not None:
+                    loss = loss + DISC_WEIGHT * self._one(self.disc, target_audio, pred_audio)
         finally:
             it = iter(req)
             for m in models:
@@ -580,16 +587,50 @@ class GeneratorLoss(nn.Module):
         return loss
 
 
-class DiscriminatorLoss(nn.Module):
-    """DiscriminatorLoss.forward, acoustic set (losses.py:196-207) on DETACHED spectrograms, plus the moving
-    average of the plain LSGAN part per discriminator that drives its learning rate (losses.py:280-288)."""
+def _curve_model(owner, used):
+    """losses.py:196-200,316-321: `used` containing pitch_disc / dur_disc selects that discriminator alone"""
+    if used is not None and "pitch_disc" in used:
+        if owner.pitch is None:
+            raise ValueError("stylish_tts_b200: this loss was built without a pitch discriminator")
+        return owner.pitch
+    if used is not None and "dur_disc" in used:
+        if owner.duration is None:
+            raise ValueError("stylish_tts_b200: this loss was built without a duration discriminator")
+        return owner.duration
+    return None
 
-    def __init__(self, *, mrd0, mrd1, mrd2, disc: Optional[nn.Module] = None, device="cuda"):
+
+class DiscriminatorLoss(nn.Module):
+    """DiscriminatorLoss of train/losses.py:166-230, same constructor and call keywords, on DETACHED inputs, plus
+    the moving average of the plain LSGAN part per discriminator that drives its learning rate (losses.py:280-288;
+    device-resident, ``get_disc_lr_multiplier`` / ``state_dict`` as in the reference)."""
+
+    def __init__(self, *, mrd0, mrd1, mrd2, disc: Optional[nn.Module] = None, pitch: Optional[nn.Module] = None,
+                 duration: Optional[nn.Module] = None, device="cuda"):
         super().__init__()
         self.mrd = nn.ModuleList([mrd0, mrd1, mrd2])
-        self.disc = disc
+        self.disc, self.pitch, self.duration = disc, pitch, duration
         self.lr_control = {f"mrd{i}": DiscriminatorLR(5, device) for i in range(3)}
         self.lr_control["disc"] = DiscriminatorLR(1, device)
+        self.lr_control["pitch_disc"] = DiscriminatorLR(5, device)
+        self.lr_control["dur_disc"] = DiscriminatorLR(5, device)
+
+    def get_disc_lr_multiplier(self, key):
+        return self.lr_control[key].multiplier()
+
+    def state_dict(self, *args, **kwargs):  # losses.py:209-214
+        state = {}
+        for key, c in self.lr_control.items():
+            state[f"discriminators.{key}.last_loss"] = float(c.last_loss)
+            state[f"discriminators.{key}.weight"] = 1
+        return state
+
+    def load_state_dict(self, state_dict, strict=True):  # losses.py:216-220
+        for key, c in self.lr_control.items():
+            k = f"discriminators.{key}.last_loss"
+            if k in state_dict:
+                c.last_loss.fill_(float(state_dict[k]))
+        return state_dict
 
     def _one(self, key, model, target, pred):
         real, _ = model(target.detach())
@@ -598,7 +639,10 @@ class DiscriminatorLoss(nn.Module):
         self.lr_control[key].update(d)
         return d + tprls_discriminator(real, gen)
 
-    def forward(self, *, target_list, pred_list, target_audio=None, pred_audio=None):
+    def forward(self, *, target_list, pred_list, target_audio=None, pred_audio=None, used=None, index=0):
+        curve = _curve_model(self, used)
+        if curve is not None:
+            return self._one("pitch_disc" if curve is self.pitch else "dur_disc", curve, target_list[0], pred_list[0])
         loss = sum(self._one(f"mrd{i}", m, t, p) for i, (m, t, p) in enumerate(zip(self.mrd, target_list, pred_list)))
         if self.disc is not None:
             loss = loss + DISC_WEIGHT * self._one("disc", self.disc, target_audio, pred_audio)
@@ -671,7 +715,10 @@ class AdversarialTerms(nn.Module):
                 grads = torch.autograd.grad(st.gen_loss, st.leafs, retain_graph=True)
             return (None, None) + tuple(x * g for x in grads)
 
-    def generator_loss(self, *, target_list, pred_list, target_audio=None, pred_audio=None):
+    def generator_loss(self, *, target_list, pred_list, target_audio=None, pred_audio=None, used=None, index=0):
+        """same keywords as the reference's GeneratorLoss.forward (`used` / `index` name the acoustic set there)"""
+        if used is not None and ("pitch_disc" in used or "dur_disc" in used):
+            raise ValueError("stylish_tts_b200: AdversarialTerms carries the acoustic set (mrd0-2, disc) only")
         targets, preds = list(target_list), list(pred_list)
         if self.disc is not None:
             targets.append(target_audio)

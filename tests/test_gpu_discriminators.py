@@ -486,3 +486,64 @@ def test_adversarial_terms_with_waveform_discriminator():
     for k, p in mods[1].named_parameters():
         assert rel_l2(p.grad, grads_m1[k]) < 1e-4, (k, rel_l2(p.grad, grads_m1[k]))
     assert all(p.grad is None for i in (0, 2) for p in mods[i].parameters())
+
+
+def _reference_set():
+    """all six discriminators with the golden's state dicts (the reference's own values)"""
+    g = gold()
+    mods = {}
+    for key, cls in (("mrd0", D.SpecDiscriminator), ("mrd1", D.SpecDiscriminator), ("mrd2", D.SpecDiscriminator),
+                     ("disc", D.ContextFreeDiscriminator)):
+        m = cls()
+        m.load_state_dict(state_dict_from_table(g[f"{key}_names"], g[f"{key}_shapes"]), strict=True)
+        mods[key] = m.to(dev()).train()
+    for key, kw in (("pitch_disc", dict(dim_in=2, dim_hidden=64, kernel=21)), ("dur_disc", dict(dim_in=1, dim_hidden=64, kernel=5))):
+        m = D.PitchDiscriminator(**kw)
+        m.load_state_dict(state_dict_from_table(g[f"{key}_names"], g[f"{key}_shapes"]), strict=True)
+        mods[key] = m.to(dev()).train()
+    return g, mods
+
+
+def test_loss_classes_vs_reference_golden_full_acoustic_set():
+    """GeneratorLoss / DiscriminatorLoss with the reference's constructor and call keywords (mrd0-2 + disc + pitch +
+    duration; used=, index=) against the values the UNMODIFIED reference classes produced (tests/golden/
+    make_disc_golden.py): generator loss of the full acoustic set, its gradient w.r.t. the predicted audio and the
+    first predicted spectrogram, the pitch / duration routes, the discriminator loss, gradients of `disc.last.2` and of
+    an mrd1 weight-norm direction, the moving average and the learning-rate multiplier"""
+    from tests.golden.make_disc_golden import curve_inputs
+
+    g, mods = _reference_set()
+    kw = dict(mrd0=mods["mrd0"], mrd1=mods["mrd1"], mrd2=mods["mrd2"], disc=mods["disc"], pitch=mods["pitch_disc"],
+              duration=mods["dur_disc"])
+    gl, dl = D.GeneratorLoss(**kw), D.DiscriminatorLoss(**kw, device=dev())
+    tf, pf, ta, pa = inputs()
+    tfd, tad = [t.to(dev()) for t in tf], ta.to(dev())
+    pfd = [p.to(dev()).requires_grad_(True) for p in pf]
+    pad = pa.to(dev()).requires_grad_(True)
+    args = dict(target_list=tfd, target_audio=tad, used=["mrd0", "mrd1", "mrd2", "disc"], index=0)
+    loss = gl(pred_list=pfd, pred_audio=pad, **args).mean()
+    assert float(loss) == pytest.approx(float(g["gen_loss"]), rel=2e-4)
+    loss.backward()
+    assert rel_l2(pad.grad, torch.from_numpy(g["gen_d_pred_audio"])) < 2e-3
+    assert rel_l2(pfd[0].grad, torch.from_numpy(g["gen_d_pred_fft0"])) < 2e-3
+    assert all(p.grad is None for m in mods.values() for p in m.parameters())
+    pc, du = curve_inputs()
+    pc, du = pc.to(dev()), du.to(dev())
+    pg = gl(target_list=[pc], pred_list=[pc * 0.9 + 0.1], target_audio=None, pred_audio=None, used=["pitch_disc"], index=0)
+    assert float(pg) == pytest.approx(float(g["pitch_gen_loss"]), rel=2e-4)
+    dd = dl(target_list=[du], pred_list=[du * 1.1 - 0.2], target_audio=None, pred_audio=None, used=["dur_disc"], index=0)
+    assert float(dd) == pytest.approx(float(g["dur_disc_loss"]), rel=2e-4)
+    d = dl(pred_list=[p.detach() for p in pfd], pred_audio=pad.detach(), **args).mean()
+    assert float(d) == pytest.approx(float(g["disc_loss"]), rel=2e-4)
+    for m in mods.values():
+        m.zero_grad(set_to_none=True)
+    d.backward()
+    assert rel_l2(mods["disc"].last[2].weight.grad, torch.from_numpy(g["disc_d_last2_w"])) < 2e-3
+    w = mods["mrd1"].discriminators[2].parametrizations.weight.original1
+    assert float(w.grad.norm()) == pytest.approx(float(g["disc_d_mrd1_conv2_v_norm"]), rel=5e-3)
+    assert float(dl.lr_control["mrd0"].last_loss) == pytest.approx(float(g["last_loss_mrd0"]), rel=1e-4)
+    assert float(dl.get_disc_lr_multiplier("mrd0")) == pytest.approx(float(g["lr_mult_mrd0"]), rel=1e-3)
+    sd = dl.state_dict()
+    assert sd["discriminators.mrd0.last_loss"] == pytest.approx(float(g["last_loss_mrd0"]), rel=1e-4)
+    dl.load_state_dict({"discriminators.disc.last_loss": 0.25})
+    assert float(dl.lr_control["disc"].last_loss) == 0.25
