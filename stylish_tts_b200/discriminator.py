@@ -210,8 +210,7 @@ class SpecDiscriminator(nn.Module):
     fused = True  # False: the first version (generic conv kernels for every layer); kept for A/B tests
 
     def forward(self, y):
-        if not y.is_cuda:
-            raise RuntimeError("stylish_tts_b200: SpecDiscriminator needs CUDA tensors (no CPU fallback)")
+        L.require_cuda(y, "the input of SpecDiscriminator")
         if not self.fused:
             return self._forward_generic(y)
         B, one, K, N = y.shape
@@ -277,8 +276,7 @@ class PitchDiscriminator(nn.Module):
     def forward(self, y):
         from . import train_ops as T
 
-        if not y.is_cuda:
-            raise RuntimeError("stylish_tts_b200: PitchDiscriminator needs CUDA tensors (no CPU fallback)")
+        L.require_cuda(y, "the input of PitchDiscriminator")
         w = SpecDiscriminator._w
         result = []
         h = y.to(torch.float32).contiguous()
@@ -434,8 +432,7 @@ class ContextFreeDiscriminator(nn.Module):
         from . import train_ops as T
         from ._lib import ACT_RELU
 
-        if not x.is_cuda:
-            raise RuntimeError("stylish_tts_b200: ContextFreeDiscriminator needs CUDA tensors (no CPU fallback)")
+        L.require_cuda(x, "the input of ContextFreeDiscriminator")
         B = x.shape[0]
         conv = lambda *a, **kw: T.conv(*a, mode=self.backward_mode, **kw)
         win = x.to(torch.float32).unfold(1, 1024, 512)                       # (B, W, 1024), discriminator.py:160

@@ -676,9 +676,7 @@ class SpeechEngine:
     def forward(self, texts, text_lengths, alignment, pitch, energy, voiced, style,
                 denormal_pitch, *, source_draws=None, prior=None, taps=None):
         dev = texts.device
-        if dev.type != "cuda":
-            raise RuntimeError("stylish_tts_b200: inputs must live on a CUDA device; "
-                               "there is no CPU fallback")
+        L.require_cuda(dev, "inputs")
         P = self.packed(dev)
         f32 = lambda t: t.to(device=dev, dtype=torch.float32).contiguous()
         texts = texts.to(torch.int64).contiguous()
@@ -795,8 +793,7 @@ class DurationEngine(_EngineBase):
     @torch.no_grad()
     def forward(self, texts, text_lengths, style, taps=None):
         dev = texts.device
-        if dev.type != "cuda":
-            raise RuntimeError("stylish_tts_b200: inputs must live on a CUDA device; no CPU fallback")
+        L.require_cuda(dev, "inputs")
         P = self.packed(dev)
         texts = texts.to(torch.int64).contiguous()
         lengths = text_lengths.to(device=dev, dtype=torch.int64).contiguous()
@@ -874,8 +871,7 @@ class PitchEnergyEngine(_EngineBase):
     @torch.no_grad()
     def forward(self, texts, text_lengths, alignment, style, taps=None):
         dev = texts.device
-        if dev.type != "cuda":
-            raise RuntimeError("stylish_tts_b200: inputs must live on a CUDA device; no CPU fallback")
+        L.require_cuda(dev, "inputs")
         P = self.packed(dev)
         texts = texts.to(torch.int64).contiguous()
         lengths = text_lengths.to(device=dev, dtype=torch.int64).contiguous()

@@ -129,8 +129,7 @@ class SpectrogramPlan:
         return L_ // self.hop + 1
 
     def args(self, audio: torch.Tensor, n_frames: int, *, mean=0.0, std=1.0) -> SpecArgs:
-        if not audio.is_cuda:
-            raise RuntimeError("stylish_tts_b200: the spectral front-end needs CUDA tensors (no CPU fallback)")
+        L.require_cuda(audio, "the audio of the spectral front-end")
         assert audio.dim() == 2 and audio.dtype == torch.float32 and audio.stride(1) == 1
         d = self.dev(audio.device)
         a = SpecArgs()
@@ -230,8 +229,7 @@ def mel_energy(mel, mean, std):
     """log(||exp(mel*std+mean)||_2 + 1e-9) over mel bins: (B, n_mels, F) -> (B, F)
     (log_norm + the log of stage_type.py:88-97)."""
     mel = mel.to(torch.float32).contiguous()
-    if not mel.is_cuda:
-        raise RuntimeError("stylish_tts_b200: mel_energy needs a CUDA tensor (no CPU fallback)")
+    L.require_cuda(mel, "the mel of mel_energy")
     B, M, Fr = mel.shape
     out = torch.empty((B, Fr), device=mel.device, dtype=torch.float32)
     L.call("sty_mel_energy_fwd", mel.data_ptr(), out.data_ptr(), B, M, Fr, float(mean), float(std),
@@ -293,8 +291,7 @@ class _L1RatioFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, target, pred):
         target, pred = target.contiguous(), pred.contiguous()
-        if not pred.is_cuda:
-            raise RuntimeError("stylish_tts_b200: STFT loss needs CUDA tensors (no CPU fallback)")
+        L.require_cuda(pred, "the STFT loss input")
         sums = torch.zeros(2, device=pred.device, dtype=torch.float32)
         L.call("sty_l1_sums_fwd", target.data_ptr(), pred.data_ptr(), pred.numel(), sums.data_ptr(),
                L.stream_ptr())
@@ -336,8 +333,7 @@ class _PhaseLossFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, pred, target):
         pred, target = pred.contiguous(), target.contiguous()
-        if not pred.is_cuda:
-            raise RuntimeError("stylish_tts_b200: phase loss needs CUDA tensors (no CPU fallback)")
+        L.require_cuda(pred, "the phase loss input")
         B, K, N = pred.shape
         sums = torch.zeros(3, device=pred.device, dtype=torch.float32)
         L.call("sty_phase_loss_fwd", pred.data_ptr(), target.data_ptr(), B, K, N, sums.data_ptr(),

@@ -265,8 +265,7 @@ class MelStyleEncoder(nn.Module):
         return self._masks[key]
 
     def forward(self, x):
-        if not x.is_cuda:
-            raise RuntimeError("stylish_tts_b200: MelStyleEncoder needs CUDA tensors (no CPU fallback)")
+        L.require_cuda(x, "the mel of MelStyleEncoder")
         L.load()
         return self.encode(x[:, 0])
 
@@ -317,8 +316,7 @@ class PitchStyleEncoder(MelStyleEncoder):
         self.preconv = weight_norm(nn.Conv1d(dim_in + 2, dim_in, 1, 1, 1))
 
     def forward(self, x, pitch, energy):
-        if not x.is_cuda:
-            raise RuntimeError("stylish_tts_b200: PitchStyleEncoder needs CUDA tensors (no CPU fallback)")
+        L.require_cuda(x, "the mel of PitchStyleEncoder")
         pitch, energy = pitch.unsqueeze(1).to(torch.float32), energy.unsqueeze(1).to(torch.float32)
         if self.coarse_multiplier != 1:
             # two (B,1,F) curves resampled to the coarse frame rate (mel_style_encoder.py:189-197): index plumbing

@@ -325,8 +325,7 @@ class TrainGraph:
     def forward(self, texts, text_lengths, alignment, pitch, energy, voiced, style, denormal_pitch, *,
                 source_draws=None, prior=None):
         dev = texts.device
-        if dev.type != "cuda":
-            raise RuntimeError("stylish_tts_b200: inputs must live on a CUDA device; there is no CPU fallback")
+        L.require_cuda(dev, "inputs")
         f32 = lambda t: t.to(device=dev, dtype=torch.float32).contiguous()
         texts = texts.to(torch.int64).contiguous()
         lengths = text_lengths.to(device=dev, dtype=torch.int64).contiguous()
@@ -341,8 +340,7 @@ class TrainGraph:
 
 
 def _prep(dev, texts, text_lengths, *floats):
-    if dev.type != "cuda":
-        raise RuntimeError("stylish_tts_b200: inputs must live on a CUDA device; there is no CPU fallback")
+    L.require_cuda(dev, "inputs")
     f32 = lambda t: t.to(device=dev, dtype=torch.float32).contiguous()
     return (texts.to(torch.int64).contiguous(), text_lengths.to(device=dev, dtype=torch.int64).contiguous(),
             *[f32(t) for t in floats])
