@@ -39,14 +39,15 @@ def dry_run(monkeypatch):
     return calls
 
 
-def test_reference_acoustic_step_drives_our_modules(dry_run, monkeypatch):
+def _reference_side(monkeypatch):
+    """the reference's stage module with the three imports INTEGRATION.md re-points, and a `train` namespace made of
+    THIS repo's modules / TrainContext objects plus the reference's own helpers"""
     from oracle import ref_loader
 
     ref_loader.load()
     from stylish_tts.lib.config_loader import load_config_yaml
     import stylish_tts.train.train_context as tc       # (first: the reference's modules import each other in a cycle)
     import stylish_tts.train.stage_type as stage_type
-    from stylish_tts.train.loss_log import build_loss_log
     from stylish_tts.train.utils import DurationProcessor
 
     import stylish_tts_b200 as st
@@ -54,7 +55,6 @@ def test_reference_acoustic_step_drives_our_modules(dry_run, monkeypatch):
     from stylish_tts_b200 import spectral as b200
     from tests.golden.make_acoustic_step_golden import make_batch
 
-    # the three imports of stage_type.py that INTEGRATION.md points at our spectral module
     monkeypatch.setattr(stage_type, "calculate_mel", b200.calculate_mel)
     monkeypatch.setattr(stage_type, "log_norm", b200.log_norm)
     monkeypatch.setattr(stage_type, "multi_phase_loss", b200.multi_phase_loss)
@@ -62,9 +62,11 @@ def test_reference_acoustic_step_drives_our_modules(dry_run, monkeypatch):
     mc = ref_loader.model_config()                     # the reference's own pydantic ModelConfig
     cfg = load_config_yaml(os.path.join(ref_loader.REF_ROOT, "config", "config.yml"))
     nets = st.build_model(mc)
-    sp, se = nets.speech_predictor.train(), nets.speech_style_encoder.train()
-    sp.regularisers = False
+    for k in nets:
+        nets[k].train()
+    nets.speech_predictor.regularisers = False
     se_cfg = mc.style_encoder
+    backward_calls = []
     train = types.SimpleNamespace(
         model=nets, model_config=mc, config=cfg, logger=logging.getLogger("dryrun"), writer=None,
         normalization=tc.NormalizationStats(),
@@ -77,10 +79,29 @@ def test_reference_acoustic_step_drives_our_modules(dry_run, monkeypatch):
         multi_spectrogram=b200.MultiSpectrogram(sample_rate=mc.sample_rate),
         stft_loss=b200.MultiResolutionSTFTLoss(sample_rate=mc.sample_rate),
         generator_loss=D.GeneratorLoss(mrd0=nets.mrd0, mrd1=nets.mrd1, mrd2=nets.mrd2, disc=nets.disc,
-                                       pitch=nets.pitch_disc, duration=nets.dur_disc))
+                                       pitch=nets.pitch_disc, duration=nets.dur_disc),
+        # out of this engine's scope: the WavLM term is a stub that keeps the graph connected
+        wavlm_loss=lambda target, pred: pred.float().mean() * 0.0,
+        # what accelerate / the stage object do around a batch (train.py, stage.py:104-146)
+        accelerator=types.SimpleNamespace(backward=lambda loss: (backward_calls.append(1), loss.backward())),
+        stage=types.SimpleNamespace(optimizer=types.SimpleNamespace(zero_grad=lambda: None)))
+    from stylish_tts.train.losses import DurationLoss
 
+    classes = mc.duration_predictor.duration_classes
+    train.duration_loss = DurationLoss(class_count=classes, weight=torch.ones(classes))
     raw, _ = make_batch()
-    batch = ref_loader.Munch(**raw)
+    return stage_type, train, nets, mc, ref_loader.Munch(**raw), raw, backward_calls
+
+
+def _trained(nets, keys):
+    return [(f"{k}.{n}", p) for k in keys for n, p in nets[k].named_parameters()]
+
+
+def test_reference_acoustic_step_drives_our_modules(dry_run, monkeypatch):
+    stage_type, train, nets, mc, batch, raw, _ = _reference_side(monkeypatch)
+    from stylish_tts.train.loss_log import build_loss_log
+
+    sp, se = nets.speech_predictor, nets.speech_style_encoder
     log = build_loss_log(train)
     step = stage_type.AcousticStep(batch, train, log, use_predicted_pe=False, predict_audio=True)
     B, Fr = raw["pitch"].shape
@@ -112,3 +133,61 @@ def test_reference_acoustic_step_drives_our_modules(dry_run, monkeypatch):
         assert p.grad is None or p.grad.shape == p.shape, n
     # the generator step leaves the discriminators' parameters without gradients (constants of that step)
     assert all(p.grad is None for k in ("mrd0", "mrd1", "mrd2", "disc") for p in nets[k].parameters())
+
+
+def test_reference_stage_functions_run_on_our_modules(dry_run, monkeypatch):
+    """the reference's own per-batch stage functions, unmodified: ``train_acoustic`` (stage_type.py:346-373: mel,
+    multi-phase, generator, SLM stub, backward) and ``train_textual`` (:416-447: predicted pitch / energy through
+    ``pe_style_encoder`` + ``pitch_energy_predictor``, pitch discriminator term, pitch / energy losses)"""
+    stage_type, train, nets, mc, batch, raw, backward_calls = _reference_side(monkeypatch)
+    out = stage_type.train_acoustic(batch, nets, train, False, 2)
+    assert len(backward_calls) == 1 and len(out) == 5
+    log, target_spec, pred_spec, target_audio, pred_audio = out
+    assert {"mel", "multi_phase", "generator", "slm"} <= set(log.metrics)
+    assert len(target_spec) == len(pred_spec) == 3 and not pred_spec[0].requires_grad
+    assert pred_audio[0].shape == raw["audio_gt"].shape
+    missing = [n for n, p in _trained(nets, ("speech_predictor", "speech_style_encoder"))
+               if p.grad is None and "m_source.l_linear" not in n]
+    assert not missing, missing[:5]
+    for k in nets:
+        nets[k].zero_grad(set_to_none=True)
+    n0 = len(dry_run)
+    log, pitchcat, pred_pitchcat, _, _ = stage_type.train_textual(batch, nets, train, False, 0)
+    assert len(backward_calls) == 2 and {"mel", "generator", "pitch", "energy"} <= set(log.metrics)
+    B, Fr = raw["pitch"].shape
+    assert pitchcat[0].shape == pred_pitchcat[0].shape == (B, 2, Fr)
+    assert len(dry_run) > n0
+    # the textual stage trains the pitch / energy predictor and its style encoder (stage_type.py:449-470)
+    missing = [n for n, p in _trained(nets, ("pitch_energy_predictor", "pe_style_encoder")) if p.grad is None]
+    assert not missing, missing[:5]
+
+
+def test_reference_duration_stage_and_discriminator_half(dry_run, monkeypatch):
+    """``train_duration`` (stage_type.py:494-553: duration style encoder + duration predictor, the reference's own
+    DurationProcessor / DurationLoss, the duration discriminator term) and the discriminator half of
+    ``Stage.train_batch`` (stage.py:125-146) with our ``DiscriminatorLoss`` called with the reference's keywords"""
+    import math
+
+    from stylish_tts_b200 import discriminator as D
+
+    stage_type, train, nets, mc, batch, raw, backward_calls = _reference_side(monkeypatch)
+    log, target_disc, pred_disc, _, _ = stage_type.train_duration(batch, nets, train, False, 0)
+    assert len(backward_calls) == 1 and {"generator", "duration_ce", "duration"} <= set(log.metrics)
+    assert target_disc[0].shape == pred_disc[0].shape == (raw["text"].shape[0], 1, raw["text"].shape[1])
+    missing = [n for n, p in _trained(nets, ("duration_predictor", "duration_style_encoder")) if p.grad is None]
+    assert not missing, missing[:5]
+    assert all(p.grad is None for p in nets.dur_disc.parameters())
+    # discriminator half of an acoustic batch, exactly as stage.py:125-146 calls it
+    _, target_spec, pred_spec, target_audio, pred_audio = stage_type.train_acoustic(batch, nets, train, False, 1)
+    for k in nets:
+        nets[k].zero_grad(set_to_none=True)
+    dl = D.DiscriminatorLoss(mrd0=nets.mrd0, mrd1=nets.mrd1, mrd2=nets.mrd2, disc=nets.disc, pitch=nets.pitch_disc,
+                             duration=nets.dur_disc, device="cpu")
+    d_loss = dl(target_list=target_spec, pred_list=pred_spec, target_audio=target_audio[0], pred_audio=pred_audio[0],
+                used=["mrd0", "mrd1", "mrd2", "disc"], index=1)
+    (d_loss * math.sqrt(raw["text"].shape[0])).backward()
+    for key in ("mrd0", "mrd1", "mrd2", "disc"):
+        missing = [n for n, p in nets[key].named_parameters() if p.grad is None]
+        assert not missing, (key, missing[:5])
+    assert all(p.grad is None for p in nets.speech_predictor.parameters())  # detached inputs
+    assert isinstance(float(dl.get_disc_lr_multiplier("mrd1")), float)
