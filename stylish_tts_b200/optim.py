@@ -66,6 +66,47 @@ class FlatAdamW:
         self.hyper.copy_(hyper)
         L.param_epoch += 1
 
+    # -- checkpointing: the layout of torch.optim.AdamW.state_dict(), which is what the reference's per-key optimizers
+    #    write through accelerate.save_state (train.py:453-469) — a checkpoint of either side resumes on the other
+    def state_dict(self) -> dict:
+        state = {}
+        if self.step_count > 0:
+            for i, (p, o) in enumerate(zip(self.params, self.offsets)):
+                n = p.numel()
+                state[i] = {"step": torch.tensor(float(self.step_count)),
+                            "exp_avg": self.m[o:o + n].view(p.shape).clone(),
+                            "exp_avg_sq": self.v[o:o + n].view(p.shape).clone()}
+        group = {"lr": float(self.hyper[0]), "betas": tuple(self.betas), "eps": self.eps,
+                 "weight_decay": self.weight_decay, "amsgrad": False, "maximize": False, "foreach": None,
+                 "capturable": False, "differentiable": False, "fused": None, "decoupled_weight_decay": True,
+                 "params": list(range(len(self.params)))}
+        return {"state": state, "param_groups": [group]}
+
+    def load_state_dict(self, sd: dict) -> None:
+        groups = sd["param_groups"]
+        order = [i for g in groups for i in g["params"]]
+        if len(order) != len(self.params):
+            raise ValueError(f"FlatAdamW.load_state_dict: {len(order)} parameters in the checkpoint, {len(self.params)} here")
+        g0 = groups[0]
+        self.betas, self.eps, self.weight_decay = tuple(g0["betas"]), g0["eps"], g0["weight_decay"]
+        step = 0
+        with torch.no_grad():
+            self.m.zero_()
+            self.v.zero_()
+            for slot, (p, o) in zip(order, zip(self.params, self.offsets)):
+                st = sd["state"].get(slot)
+                if st is None:
+                    continue
+                n = p.numel()
+                if tuple(st["exp_avg"].shape) != tuple(p.shape):
+                    raise ValueError(f"FlatAdamW.load_state_dict: moment shape {tuple(st['exp_avg'].shape)} != {tuple(p.shape)}")
+                self.m[o:o + n].copy_(st["exp_avg"].reshape(-1))
+                self.v[o:o + n].copy_(st["exp_avg_sq"].reshape(-1))
+                step = max(step, int(float(st["step"])))
+            self.step_count = step
+            self.hyper[1] = float(step)
+        self.set_lr(float(g0["lr"]))
+
     def set_lr(self, lr: float):
         self.lr = lr
         self.hyper[0] = lr

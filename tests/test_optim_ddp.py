@@ -68,6 +68,62 @@ def test_gradient_exchange_gloo_world2():
     assert res == {0: "ok", 1: "ok"}, res
 
 
+def test_state_dict_is_torch_adamw_compatible():
+    """FlatAdamW.state_dict / load_state_dict speak torch.optim.AdamW's layout (what the reference's per-key
+    optimizers write through accelerate.save_state, train.py:453-469): a reference checkpoint resumes here and one
+    written here loads into torch.optim.AdamW (CPU: no update is launched)"""
+    kw = dict(lr=1e-4, betas=(0.85, 0.99), eps=1e-9, weight_decay=1e-4)
+    ref_params = _make_params(seed=3)
+    ref = torch.optim.AdamW(ref_params, **kw)
+    g = torch.Generator().manual_seed(1)
+    for _ in range(3):
+        for p in ref_params:
+            p.grad = torch.randn(p.shape, generator=g)
+        ref.step()
+    sd = ref.state_dict()
+    ours = optim.FlatAdamW(_make_params(seed=3), world_size=1, **kw)
+    assert ours.state_dict()["state"] == {}                      # like a fresh torch optimizer
+    ours.load_state_dict(sd)
+    assert ours.step_count == 3 and float(ours.hyper[1]) == 3.0 and float(ours.hyper[0]) == pytest.approx(1e-4)
+    for i, (p, o) in enumerate(zip(ours.params, ours.offsets)):
+        n = p.numel()
+        assert torch.equal(ours.m[o:o + n].view(p.shape), sd["state"][i]["exp_avg"])
+        assert torch.equal(ours.v[o:o + n].view(p.shape), sd["state"][i]["exp_avg_sq"])
+    back = ours.state_dict()
+    fresh = torch.optim.AdamW(_make_params(seed=3), **kw)
+    fresh.load_state_dict(back)                                   # torch accepts our layout
+    for i in range(len(ref_params)):
+        assert torch.equal(fresh.state_dict()["state"][i]["exp_avg_sq"], sd["state"][i]["exp_avg_sq"])
+        assert float(fresh.state_dict()["state"][i]["step"]) == 3.0
+    with pytest.raises(ValueError):
+        optim.FlatAdamW(_make_params()[:2], world_size=1).load_state_dict(sd)
+
+
+@pytest.mark.gpu
+def test_resume_from_torch_adamw_checkpoint_continues_identically():
+    """two steps with torch.optim.AdamW, checkpoint, then a third step here == the third step of torch"""
+    d = torch.device("cuda:0")
+    kw = dict(lr=1e-3, betas=(0.85, 0.99), eps=1e-9, weight_decay=1e-4)
+    ref_params = [torch.nn.Parameter(p.detach().to(d)) for p in _make_params(seed=5)]
+    ref = torch.optim.AdamW(ref_params, **kw)
+    g = torch.Generator().manual_seed(2)
+    grads = [[torch.randn(p.shape, generator=g).to(d) for p in ref_params] for _ in range(3)]
+    for it in range(2):
+        for p, gr in zip(ref_params, grads[it]):
+            p.grad = gr.clone()
+        ref.step()
+    ours_params = [torch.nn.Parameter(p.detach().clone()) for p in ref_params]
+    ours = optim.FlatAdamW(ours_params, world_size=1, **kw)
+    ours.load_state_dict(ref.state_dict())
+    for p, q, gr in zip(ref_params, ours_params, grads[2]):
+        p.grad, q.grad = gr.clone(), gr.clone()
+    ref.step()
+    ours.step()
+    torch.cuda.synchronize()
+    for p, q in zip(ref_params, ours_params):
+        assert torch.allclose(p, q, rtol=1e-6, atol=1e-7)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("world", [1, 4])
 def test_fused_adamw_matches_torch(world):
