@@ -1,19 +1,21 @@
 // 64-wide multi-head attention on the tensor cores, second generation: operands pre-split once, tiles moved by the
-// bulk-copy engine, MMAs of the next tile issued before the current tile's output is read back.
+// bulk-copy engine, a dedicated issuer warp, MMAs of the next tile queued behind the current tile's.
 // (conformer attention of the vocoder, conformer.py:112-131: 8 heads x 64, T ~ 800 frames, no mask / RoPE; and the
-// Transformer1d blocks of the style-diffusion denoiser.)
+// Transformer1d blocks of the style-diffusion denoiser.)  Forward AND backward.
 //
 //   prepare   q, k, v (fp32) -> bf16 hi | lo planes in the EXACT shared-memory image of one tile
-//             (Q: [2 split][8 d8][128 rows][8], K / V: [2][8][64 rows][8]); q is scaled on the way.  One pass over
-//             q, k, v; every 128-query CTA of the attention kernel then reads K / V without touching an ALU
-//             (the first version converted each K / V tile cdiv(T,128) times, in the critical path of every tile).
-//   attention one CTA = 128 queries of one (batch, head), 2 CTAs per SM.  Per 64-key tile
-//               cp.async.bulk  K, V tile -> shared memory (mbarrier complete_tx), issued one tile ahead
-//               S = Q K^T (M=128, N=64, K=64)                    tcgen05, accumulator in TMEM
-//               online softmax, one thread per query row; P as bf16 hi | lo -> shared memory
-//               O_t = P V (M=128, N=64, K=64)                    tcgen05; S of the NEXT tile is issued right behind it,
-//               so the tensor pipe works while the threads fold O_t into their register accumulators
+//             (Q: [2 split][8 d8][128 rows][8], K / V: [2][8][64 rows][8]); q is scaled by scale*log2(e) on the way.
+//             One pass over q, k, v; every 128-query CTA of the attention kernel then reads K / V without touching an
+//             ALU (the first version converted each K / V tile cdiv(T,128) times, in the critical path of every tile).
+//   attention one CTA = 128 queries of one (batch, head), 288 threads, 2 CTAs per SM.  Per 64-key tile
+//               issuer warp : cp.async.bulk K, V tile -> shared memory (mbarrier complete_tx), one tile ahead;
+//                             S = Q K^T (M=128, N=64, K=64), O_t = P V (M=128, N=64, K=64) on tcgen05, accumulators in
+//                             TMEM; S of the NEXT tile is queued right behind P V of the current one
+//               8 softmax warps: 2 threads per query row (TMEM lane), 32 columns each; tile maximum exchanged through
+//                             shared memory + a 64-thread named barrier, partial row sums combined at the end;
+//                             P = ex2(S - m) (one MUFU) as bf16 hi | lo -> shared memory; O_t folded into registers
 //             bf16x3 split precision (hi*hi + lo*hi + hi*lo, fp32 accumulation) as everywhere.
+//   backward  see the block comment above attn64_bwd_prepare_kernel.
 #include <math.h>
 
 #include "tma.cuh"

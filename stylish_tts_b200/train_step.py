@@ -1,8 +1,9 @@
 """The acoustic training step on the CUDA engine: the forward graph the reference builds in
 ``AcousticStep.__init__`` with ``use_predicted_pe=False, predict_audio=True`` (stage_type.py:61-180) plus its
 ``mel`` and ``multi_phase`` losses with ``LossLog.backwards_loss`` normalisation (stage_type.py:170-193,
-loss_log.py:82-94) — SURVEY §8a row A3 / §8d config 3.  Adversarial and SLM terms are outside the hot
-path.
+loss_log.py:82-94) — SURVEY §8a row A3 / §8d config 3 — and, when a ``generator_loss`` is passed, the adversarial
+term of ``step.generator_loss`` (stage_type.py:208-219); ``discriminator_step`` is the second half of
+``Stage.train_batch`` (stage.py:125-146).  The SLM (WavLM) term is outside the hot path.
 
     fe = FrontEnd(model_config, mel_log_mean, mel_log_std)
     out = acoustic_step(batch, nets, fe)      # out.total is differentiable; out.pred.audio (B,1,L)
