@@ -724,6 +724,11 @@ class AdversarialTerms(nn.Module):
 
     forward = generator_loss
 
+    def release(self) -> None:
+        """drop the kept evaluation (activations of mrd0-2 / disc on target and prediction) when no discriminator
+        half follows the generator term, e.g. in validation"""
+        self._state = None
+
     def discriminator_backward(self, index: int, scale: float = 1.0) -> torch.Tensor:
         st = self._state
         if st is None:
