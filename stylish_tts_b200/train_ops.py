@@ -435,6 +435,15 @@ class DropoutRng:
     def spec(self, site: int, p: float) -> "L.Dropout":
         return L.Dropout(self.dev.data_ptr(), int(site), float(p))
 
+    # checkpoint / resume: the mask stream continues where it stopped (the reference saves torch's RNG state through
+    # accelerate.save_state; here the whole state is two 64-bit integers)
+    def state_dict(self) -> dict:
+        return {"state": int(self.state), "value": int(self.value)}
+
+    def load_state_dict(self, sd: dict) -> None:
+        self.state = int(sd["state"]) & (2 ** 64 - 1)
+        self.set(int(sd["value"]))
+
 
 class DropoutFn(Function):
     """y = res + scale * act(x) * keep / (1-p)   (nn.Dropout / Dropout1d / DropPath, see sty_dropout_fwd)"""

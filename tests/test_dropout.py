@@ -370,3 +370,18 @@ def test_gpu_predictors_in_train_mode_match_oracle_and_reference():
     o1 = dp(c(inp["texts"]), c(inp["text_lengths"]), s1).detach().clone()
     o2 = dp(c(inp["texts"]), c(inp["text_lengths"]), s1).detach().clone()
     assert rel_l2(o1, o2) > 1e-3
+
+
+def test_dropout_rng_state_dict_resumes_the_mask_stream():
+    """DropoutRng.state_dict / load_state_dict (CPU cell): a restored generator continues with the same seeds"""
+    from stylish_tts_b200.train_ops import DropoutRng
+
+    a = DropoutRng(7, device="cpu")
+    for _ in range(3):
+        a.advance()
+    sd = a.state_dict()
+    expect = [a.advance() for _ in range(4)]
+    b = DropoutRng(123, device="cpu")
+    b.load_state_dict(sd)
+    assert int(b.dev.item()) & (2 ** 64 - 1) == sd["value"] & (2 ** 64 - 1) or int(b.dev.item()) == sd["value"] - 2 ** 64
+    assert [b.advance() for _ in range(4)] == expect
